@@ -1,0 +1,146 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of the C++ restatement of JAAD (oracle/*.hpp).  Only tests/,
+__graft_entry__.smoke() and bench.py's CPU-baseline legs may import this
+module; the product package (jaadec_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libjaad_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.jo_open_adts.restype = C.c_void_p
+        _lib.jo_open_adts.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        _lib.jo_open_asc.restype = C.c_void_p
+        _lib.jo_open_asc.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        _lib.jo_close.argtypes = [C.c_void_p]
+        _lib.jo_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _lib.jo_tap_ics.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.jo_tap_msused.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.jo_adts_index.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _lib.jo_decode_streams.restype = C.c_double
+        _lib.jo_decode_streams.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    return _lib
+
+
+class AACError(Exception):
+    def __init__(self, status):
+        super().__init__("oracle status %d" % status)
+        self.status = status
+
+
+class Decoder:
+    """Mirror of net.sourceforge.jaad.aac.Decoder (create + decodeFrame)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def create_adts(cls, profile: int, sf_index: int, chan_cfg: int) -> "Decoder":
+        st = C.c_int(0)
+        h = lib().jo_open_adts(profile, sf_index, chan_cfg, C.byref(st))
+        if not h:
+            raise AACError(st.value)
+        return cls(h)
+
+    @classmethod
+    def create_asc(cls, asc: bytes) -> "Decoder":
+        st = C.c_int(0)
+        buf = np.frombuffer(asc, np.uint8).copy()
+        h = lib().jo_open_asc(buf.ctypes.data, len(buf), C.byref(st))
+        if not h:
+            raise AACError(st.value)
+        return cls(h)
+
+    def close(self):
+        if self._h:
+            lib().jo_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def decode_frame(self, frame: np.ndarray, big_endian: bool = False):
+        """Returns dict(status, channels, sample_length, sample_rate, f32 [C,L], s16 [L,C])."""
+        frame = np.ascontiguousarray(frame, np.uint8)
+        meta = np.zeros(4, np.int32)
+        f32 = np.zeros(8 * 2048, np.float32)
+        s16 = np.zeros(8 * 2048, np.int16)
+        lib().jo_decode_frame(self._h, frame.ctypes.data, len(frame), f32.ctypes.data, s16.ctypes.data, int(big_endian), meta.ctypes.data)
+        st, ch, ln, sr = (int(x) for x in meta)
+        out = dict(status=st, channels=ch, sample_length=ln, sample_rate=sr)
+        if st == 0:
+            out["f32"] = f32[: ch * ln].reshape(ch, ln).copy()
+            out["s16"] = s16[: ch * ln].reshape(ln, ch).copy()
+        return out
+
+    def tap_ics(self, el: int, ch: int):
+        q = np.zeros(1024, np.int16)
+        sf = np.zeros(120, np.int16)
+        cb = np.zeros(120, np.uint8)
+        spec = np.zeros(1024, np.float32)
+        info = np.zeros(16, np.int32)
+        r = lib().jo_tap_ics(self._h, el, ch, q.ctypes.data, sf.ctypes.data, cb.ctypes.data, spec.ctypes.data, info.ctypes.data)
+        if r < 0:
+            return None
+        return dict(type=r, q=q, sfidx=sf, sfbcb=cb, spec=spec, info=info)
+
+    def tap_msused(self, el: int):
+        ms = np.zeros(128, np.uint8)
+        if lib().jo_tap_msused(self._h, el, ms.ctypes.data) < 0:
+            return None
+        return ms
+
+
+def adts_index(data: np.ndarray, max_frames: int = 1 << 20):
+    data = np.ascontiguousarray(data, np.uint8)
+    offs = np.zeros(max_frames, np.int64)
+    sizes = np.zeros(max_frames, np.int32)
+    hdr = np.zeros(3, np.int32)
+    n = lib().jo_adts_index(data.ctypes.data, len(data), offs.ctypes.data, sizes.ctypes.data, max_frames, hdr.ctypes.data)
+    return offs[:n].copy(), sizes[:n].copy(), tuple(int(x) for x in hdr)
+
+
+def decode_streams(blob, first, offsets, sizes, *, hdr=None, asc=None, threads=1, pcm_out=None, pcm_first=None, big_endian=False):
+    """CPU baseline: decode many independent streams with a pool of `threads` workers. Returns (seconds, samples, errors)."""
+    blob = np.ascontiguousarray(blob, np.uint8)
+    first = np.ascontiguousarray(first, np.int64)
+    offsets = np.ascontiguousarray(offsets, np.int64).ravel()
+    sizes = np.ascontiguousarray(sizes, np.int32).ravel()
+    n_streams = len(first) - 1
+    samples = C.c_int64(0)
+    errors = C.c_int64(0)
+    hdr_a = np.asarray(hdr if hdr is not None else (0, 0, 0), np.int32)
+    asc_a = np.frombuffer(asc, np.uint8).copy() if asc is not None else np.zeros(1, np.uint8)
+    sec = lib().jo_decode_streams(
+        n_streams, blob.ctypes.data, first.ctypes.data, offsets.ctypes.data, sizes.ctypes.data,
+        0 if asc is None else 1, hdr_a.ctypes.data, asc_a.ctypes.data, 0 if asc is None else len(asc_a), threads,
+        pcm_out.ctypes.data if pcm_out is not None else None,
+        np.ascontiguousarray(pcm_first, np.int64).ctypes.data if pcm_first is not None else None,
+        int(big_endian), C.byref(samples), C.byref(errors))
+    return sec, samples.value, errors.value

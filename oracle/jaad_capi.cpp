@@ -1,0 +1,194 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see jaad_bits.hpp for the full notice).
+//
+// Plain-C entry points over the restatement, loaded with ctypes by tests/,
+// __graft_entry__.smoke() and bench.py's CPU-baseline legs.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "jaad_adts.hpp"
+#include "jaad_lc.hpp"
+#ifdef JAAD_ORACLE_WITH_SBR
+#include "jaad_sbr.hpp"
+#endif
+
+using namespace jaad;
+
+namespace {
+struct Handle {
+  std::unique_ptr<Decoder> dec;
+  FrameOutput last;
+};
+}  // namespace
+
+extern "C" {
+
+int jo_has_sbr() {
+#ifdef JAAD_ORACLE_WITH_SBR
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+// Decoder.create(AudioDecoderInfo)  (Decoder.java:45-48)
+void* jo_open_adts(int profile, int sf_index, int chan_cfg, int* status) {
+  try {
+    DecoderConfig c = DecoderConfig::fromInfo(profile, sf_index, chan_cfg);
+    auto* h = new Handle();
+    h->dec.reset(new Decoder(c));
+    if (status) *status = 0;
+    return h;
+  } catch (const AACException& e) {
+    if (status) *status = e.code;
+    return nullptr;
+  }
+}
+
+// Decoder.create(byte[] audioSpecificConfig)  (Decoder.java:36-43)
+void* jo_open_asc(const uint8_t* asc, int n, int* status) {
+  try {
+    DecoderConfig c;
+    BitStream in(asc, (size_t)n);
+    c.decode(in);
+    auto* h = new Handle();
+    h->dec.reset(new Decoder(c));
+    if (status) *status = 0;
+    return h;
+  } catch (const AACException& e) {
+    if (status) *status = e.code;
+    return nullptr;
+  }
+}
+
+void jo_close(void* hv) { delete static_cast<Handle*>(hv); }
+
+// meta[0..3] = status, channels, sampleLength, sampleRate.
+// pcm_f32: planar [channels][sampleLength] (may be NULL); pcm_s16: interleaved (may be NULL).
+int jo_decode_frame(void* hv, const uint8_t* data, int n, float* pcm_f32, int16_t* pcm_s16, int big_endian, int* meta) {
+  Handle* h = static_cast<Handle*>(hv);
+  h->last = h->dec->decodeFrame(data, (size_t)n);
+  const FrameOutput& f = h->last;
+  if (meta) { meta[0] = f.status; meta[1] = f.channels; meta[2] = f.sampleLength; meta[3] = f.sampleRate; }
+  if (f.status != ST_OK) return f.status;
+  if (pcm_f32) {
+    for (int c = 0; c < f.channels; ++c)
+      for (int is = 0; is < f.sampleLength; ++is) {
+        int k = (int)((long long)f.planes[c].second * is / f.sampleLength);
+        pcm_f32[(size_t)c * f.sampleLength + is] = f.planes[c].first[k];
+      }
+  }
+  if (pcm_s16) sampleBufferAccept(f, pcm_s16, big_endian != 0);
+  return 0;
+}
+
+// Parity taps of the frame just decoded: element `el` in bitstream order, channel ch (0 = L / SCE, 1 = R).
+// info[0..15] = present, windowSequence, shapeCur, shapePrev, maxSFB, groups, glen[8], msMask, commonWindow
+int jo_tap_ics(void* hv, int el, int ch, int16_t* q1024, int16_t* sfidx120, uint8_t* sfbcb120, float* spec1024, int* info) {
+  Handle* h = static_cast<Handle*>(hv);
+  auto& ae = h->dec->syn.audioElements;
+  if (el < 0 || el >= (int)ae.size()) return -1;
+  ChannelElement* e = ae[el];
+  ICStream* ics;
+  int msMask = 0, common = 0;
+  if (e->type == EL_CPE) {
+    CPE* c = static_cast<CPE*>(e);
+    ics = ch ? &c->icsR : &c->icsL;
+    msMask = c->msMask;
+    common = c->commonWindow;
+  } else {
+    if (ch) return -1;
+    ics = &static_cast<SCE*>(e)->ics;
+  }
+  if (q1024) memcpy(q1024, ics->q, sizeof(ics->q));
+  if (sfidx120) memcpy(sfidx120, ics->sfIndex, sizeof(ics->sfIndex));
+  if (sfbcb120) for (int i = 0; i < 120; ++i) sfbcb120[i] = (uint8_t)ics->sfbCB[i];
+  if (spec1024) memcpy(spec1024, ics->iqData, sizeof(ics->iqData));
+  if (info) {
+    info[0] = 1;
+    info[1] = ics->info.windowSequence;
+    info[2] = ics->info.windowShape[1];
+    info[3] = ics->info.windowShape[0];
+    info[4] = ics->info.maxSFB;
+    info[5] = ics->info.windowGroupCount;
+    for (int i = 0; i < 8; ++i) info[6 + i] = i < ics->info.windowGroupCount ? ics->info.windowGroupLength[i] : 0;
+    info[14] = msMask;
+    info[15] = common;
+  }
+  return e->type;
+}
+
+int jo_tap_msused(void* hv, int el, uint8_t* ms128) {
+  Handle* h = static_cast<Handle*>(hv);
+  auto& ae = h->dec->syn.audioElements;
+  if (el < 0 || el >= (int)ae.size() || ae[el]->type != EL_CPE) return -1;
+  CPE* c = static_cast<CPE*>(ae[el]);
+  for (int i = 0; i < 128; ++i) ms128[i] = c->msUsed[i];
+  return 0;
+}
+
+// ADTS index: payload offsets/sizes of up to `max` frames; hdr[0..2] = profile, sf_index, chan_cfg of the first frame.
+int jo_adts_index(const uint8_t* data, size_t n, int64_t* offsets, int32_t* sizes, int max, int* hdr) {
+  ADTSDemultiplexer dm(data, n);
+  ADTSFrameInfo f;
+  int cnt = 0;
+  while (cnt < max && dm.next(f)) {
+    if (cnt == 0 && hdr) { hdr[0] = f.profile; hdr[1] = f.sfIndex; hdr[2] = f.channelConfiguration; }
+    offsets[cnt] = (int64_t)f.payloadOffset;
+    sizes[cnt] = f.payloadBytes;
+    ++cnt;
+  }
+  return cnt;
+}
+
+// CPU baseline: decode `n_streams` independent streams, one Decoder per stream, `n_threads` workers taking
+// whole streams round-robin (the "one thread per stream" model of S/Main.java:82-111).  Stream s owns frames
+// [first[s], first[s+1]) of (offsets, sizes) into blob.  kind: 0 = ADTS-style open (hdr = profile, sf, chan),
+// 1 = ASC open.  PCM is packed to int16 (SampleBuffer) into a per-thread scratch buffer; when pcm_out != NULL
+// stream s writes its frames consecutively at pcm_out + pcm_first[s] (bytes).  Returns wall seconds; fills
+// decoded_samples (per-channel output samples summed over streams) and n_errors.
+double jo_decode_streams(int n_streams, const uint8_t* blob, const int64_t* first, const int64_t* offsets,
+                         const int32_t* sizes, int kind, const int* hdr, const uint8_t* asc, int asc_len,
+                         int n_threads, uint8_t* pcm_out, const int64_t* pcm_first, int big_endian,
+                         int64_t* decoded_samples, int64_t* n_errors) {
+  std::atomic<int> nextStream(0);
+  std::atomic<long long> samples(0), errors(0);
+  auto worker = [&]() {
+    std::vector<int16_t> scratch(8 * 2048);
+    for (;;) {
+      int s = nextStream.fetch_add(1);
+      if (s >= n_streams) break;
+      std::unique_ptr<Decoder> dec;
+      try {
+        DecoderConfig c;
+        if (kind == 0) c = DecoderConfig::fromInfo(hdr[0], hdr[1], hdr[2]);
+        else { BitStream in(asc, (size_t)asc_len); c.decode(in); }
+        dec.reset(new Decoder(c));
+      } catch (const AACException&) { errors++; continue; }
+      uint8_t* dst = pcm_out ? pcm_out + pcm_first[s] : nullptr;
+      long long local = 0;
+      for (int64_t f = first[s]; f < first[s + 1]; ++f) {
+        FrameOutput o = dec->decodeFrame(blob + offsets[f], (size_t)sizes[f]);
+        if (o.status != ST_OK) { errors++; continue; }
+        int16_t* p = dst ? reinterpret_cast<int16_t*>(dst) : scratch.data();
+        sampleBufferAccept(o, p, big_endian != 0);
+        if (dst) dst += (size_t)o.channels * o.sampleLength * 2;
+        local += o.sampleLength;
+      }
+      samples += local;
+    }
+  };
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int i = 0; i < n_threads; ++i) th.emplace_back(worker);
+  for (auto& t : th) t.join();
+  auto t1 = std::chrono::steady_clock::now();
+  if (decoded_samples) *decoded_samples = samples.load();
+  if (n_errors) *n_errors = errors.load();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
