@@ -1,0 +1,298 @@
+#!/usr/bin/env python3
+"""Throughput benchmark of the batched AAC decode hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2]
+
+A "step" is one pass of the hot path over one batch: every frame of S independent
+streams (default: BASELINE config 2, 4096 AAC-LC 48 kHz stereo streams x 469 frames = 10 s
+each).  `value` times the kernels with the batch resident in HBM; `e2e` times the public
+one-call API with host buffers (indexing + H2D + kernels + D2H inside the region).
+One process per GPU; streams shard across GPUs with no collective (weak scaling: S per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SF_FREQ = [96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000]
+# algorithmic bytes per frame: compressed in + s16 PCM out + overlap state read+write
+ALGO_BYTES = {1: lambda avg: avg + 4096 + 16384, 2: lambda avg: avg + 4096 + 16384, 5: lambda avg: avg + 12288 + 49152}
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def make_workload(config_no, n_streams, n_frames, rank):
+    import gen
+    cfg = gen.config(config_no, n_frames=n_frames)
+    blob, offs, sizes, _ = gen.generate_many(cfg, gen.seed_for(config_no, rank * n_streams), n_streams)
+    return cfg, blob, offs, sizes
+
+
+def frame_table(offs, sizes, ids):
+    """Frame-major submission order: frame f of every stream, then frame f+1 ..."""
+    from jaadec_b200 import FRAME_DESC_DTYPE
+    S, F = offs.shape
+    fr = np.zeros(S * F, FRAME_DESC_DTYPE)
+    fr["offset"] = offs.T.reshape(-1)
+    fr["nbytes"] = sizes.T.reshape(-1)
+    fr["stream_id"] = np.tile(np.asarray(ids, np.int32), F)
+    return fr
+
+
+def cpu_baseline(cfg, blob, offs, sizes, asc, sample_streams, threads):
+    import oracle
+    S = min(sample_streams, offs.shape[0])
+    F = offs.shape[1]
+    first = np.arange(S + 1, dtype=np.int64) * F
+    kw = dict(asc=asc) if asc is not None else dict(hdr=(2, cfg.sf_index, cfg.chan_cfg))
+    sec, samples, errors = oracle.decode_streams(blob, first, offs[:S], sizes[:S], threads=threads, **kw)
+    rate = SF_FREQ[cfg.sf_index]
+    return (samples / rate) / sec, sec, S, errors
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  No JVM exists in the
+    image, so this is the C++ restatement of JAAD (oracle/, kind = "port"), one Decoder per stream, all host threads."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    cfg, blob, offs, sizes = make_workload(args.config, min(args.streams, args.ref_streams or 64 * cores), args.frames, 0)
+    asc = bytes([0x11, 0xB0]) if args.config == 5 else None
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(cfg, blob, offs, sizes, asc, max(8, offs.shape[0] // 8), cores)
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, sec, S, err = cpu_baseline(cfg, blob, offs, sizes, asc, offs.shape[0], cores)
+        vals.append(v)
+        t_all += sec
+    value = float(np.mean(vals))
+    sample = "%d streams x %d frames of config %d per step" % (offs.shape[0], args.frames, args.config)
+    line = {
+        "impl": "reference", "metric": "decoded audio-sec/sec (x realtime)", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_all / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cfg, sizes),
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, sizes):
+    names = {1: "AAC-LC 44.1 kHz stereo ADTS, long windows only", 2: "AAC-LC 48 kHz stereo, mixed ONLY_LONG/EIGHT_SHORT, M/S, IS, TNS side info",
+             5: "AAC-LC 5.1 48 kHz raw frames (MP4 samples)"}
+    return {"workload": "BASELINE config %d: %s" % (args.config, names.get(args.config, "?")), "streams_per_gpu": args.streams,
+            "frames_per_stream": args.frames, "avg_frame_bytes": float(sizes.mean()), "pcm": "s16le interleaved",
+            "l2_policy": "inputs+outputs per step far larger than the 126 MB L2 (no flush needed)", "parallelism": "streams sharded, no collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 5])
+    ap.add_argument("--streams", type=int, default=4096)
+    ap.add_argument("--frames", type=int, default=0)
+    ap.add_argument("--ref-streams", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.config == 1 and args.streams == 4096:
+        args.streams = 1
+    if not args.frames:
+        args.frames = {1: 431, 2: 469, 5: 469}[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from jaadec_b200 import Engine, FLAG_PROFILE, PCM_S16LE
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg, blob, offs, sizes = make_workload(args.config, args.streams, args.frames, rank)
+    S, F = offs.shape
+    rate = SF_FREQ[cfg.sf_index]
+    asc = bytes([0x11, 0xB0]) if args.config == 5 else None
+    audio_s_per_step = S * F * 1024.0 / rate
+
+    eng = Engine(device=local_rank, max_streams=S, pcm_format=PCM_S16LE, flags=FLAG_PROFILE)
+    ids = [eng.open_asc(asc) if asc else eng.open_adts(2, cfg.sf_index, cfg.chan_cfg) for _ in range(S)]
+    frames = frame_table(offs, sizes, ids)
+
+    # ---- value: kernels only, batch resident in HBM ------------------------------------------------
+    batch = eng.batch(frames, blob.nbytes)
+    batch.upload(blob)
+    batch.sync()
+    for _ in range(args.warmup):
+        batch.decode()
+    batch.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    parse_ms, fb_ms, dev_ms, launches = [], [], [], 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch.decode()
+        t = batch.timings()   # CUDA events on the engine's stream (synchronises the step)
+        parse_ms.append(t.parse_ms)
+        fb_ms.append(t.filterbank_ms)
+        dev_ms.append(t.total_ms)
+        launches += t.launches
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop()
+    elapsed = t1 - t0
+    if world > 1:
+        tt = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed = float(tt.item())
+    value = world * audio_s_per_step * args.steps / elapsed
+    _, results = batch.download(want_results=True)
+    n_bad = int((results["status"] != 0).sum())
+    pcm_bytes = batch.pcm_bytes
+    batch.close()
+
+    # ---- e2e: the public one-call API with pinned host buffers, copies inside the timed region --------
+    e2e = None
+    if not args.no_e2e:
+        blob_pin = torch.empty(blob.nbytes, dtype=torch.uint8, pin_memory=True)
+        blob_pin.numpy()[:] = blob
+        pcm_pin = torch.empty(pcm_bytes, dtype=torch.uint8, pin_memory=True)
+        bp, pp = blob_pin.numpy(), pcm_pin.numpy()
+        for _ in range(min(args.warmup, 2)):
+            eng.decode(bp, frames, pcm_out=pp)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _, res = eng.decode(bp, frames, pcm_out=pp)
+            chk = int(res["status"][0])  # read the step's result on the host
+        barrier()
+        t1 = time.perf_counter()
+        e_elapsed = t1 - t0
+        if world > 1:
+            tt = torch.tensor([e_elapsed], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e_elapsed = float(tt.item())
+        e2e = {"value": world * audio_s_per_step * args.steps / e_elapsed, "unit": "audio-s/s",
+               "h2d_bytes_per_step": int(blob.nbytes + frames.nbytes * 3), "d2h_bytes_per_step": int(pcm_bytes + len(frames) * 24),
+               "ms_per_step": 1000.0 * e_elapsed / args.steps}
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------------
+    peak, peak_kind = read_peaks()
+    avg_frame = float(sizes.mean())
+    algo_bytes = ALGO_BYTES[args.config](avg_frame) * S * F
+    k1, k2 = float(np.mean(parse_ms)), float(np.mean(fb_ms))
+    dom_name, dom_ms = ("k1_parse_kernel", k1) if k1 >= k2 else ("k2_filterbank_kernel", k2)
+    achieved = algo_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (burst copy)", "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "algo_bytes_per_launch": algo_bytes,
+                "kernel_ms": {"k1_parse": k1, "k2_filterbank": k2, "step_device_total": float(np.mean(dev_ms))},
+                "whole_path_frac": algo_bytes / (float(np.mean(dev_ms)) * 1e-3) / 1e9 / peak}
+
+    line = {
+        "metric": "decoded audio-sec/sec (x realtime)", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, sizes), "clocks": clocks,
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "bad_frames": n_bad,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample_streams = min(S, 96 * cores)
+        v, sec, Ss, err = cpu_baseline(cfg, blob, offs, sizes, asc, sample_streams, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                "sample": "%d of the %d streams x %d frames, %.1f s wall, C++ restatement of JAAD (no JVM in the image)" % (Ss, S, F, sec)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

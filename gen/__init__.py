@@ -143,4 +143,10 @@ def generate_many(cfg: GenConfig, base_seed: int, n_streams: int, threads: int |
                             sizes.ctypes.data, sb.ctypes.data, threads or min(32, os.cpu_count() or 8))
     if rc < 0:
         raise RuntimeError("generator failed: %d" % rc)
-    return blob, offs, sizes, sb
+    # compact: streams back to back (the stride layout only exists so threads can write independently)
+    starts = np.concatenate([[0], np.cumsum(sb)[:-1]]).astype(np.int64)
+    out = np.empty(int(sb.sum()), np.uint8)
+    for s in range(n_streams):
+        out[starts[s]: starts[s] + sb[s]] = blob[s * stride: s * stride + sb[s]]
+    offs += (starts - np.arange(n_streams, dtype=np.int64) * stride)[:, None]
+    return out, offs, sizes, sb

@@ -1,0 +1,175 @@
+/* jaadb200.h -- C ABI of the B200 batched AAC decode engine.
+ *
+ * Drop-in boundary for JAAD's per-frame decode path.  Each entry point names
+ * the reference interface it replaces (paths relative to /root/reference):
+ *   A/ = aac/src/main/java/net/sourceforge/jaad/aac/
+ *   S/ = src/main/java/net/sourceforge/jaad/
+ *
+ * Plain pointers and sizes only; no exceptions cross this boundary.  Engine
+ * level calls return 0 on success or a negative JAADB_E_* code; per-frame
+ * decode problems are reported in jaadb_frame_result.status (JAADB_ST_*),
+ * mirroring JAAD's AACException messages, and never abort the batch.
+ *
+ * Threading: one caller thread per engine (JAAD's Decoder is not thread-safe
+ * either, A/Decoder.java).  One engine drives one GPU; streams shard across
+ * engines/processes by stream id with no collective.
+ */
+#ifndef JAADB200_H
+#define JAADB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JAADB_ABI_VERSION 1
+
+/* engine-level error codes */
+#define JAADB_OK 0
+#define JAADB_E_INVALID (-1)     /* bad argument */
+#define JAADB_E_CUDA (-2)        /* CUDA runtime failure (see jaadb_last_error) */
+#define JAADB_E_NOMEM (-3)
+#define JAADB_E_CONFIG (-4)      /* unsupported / malformed stream configuration */
+#define JAADB_E_NOSTREAM (-5)    /* unknown stream id */
+#define JAADB_E_CAPACITY (-6)    /* max_streams exceeded / output buffer too small */
+
+/* per-frame status words (mirror A/AACException.java call sites) */
+#define JAADB_ST_OK 0
+#define JAADB_ST_EOS 1                /* EOSException, swallowed by Decoder.decodeFrame (A/Decoder.java:96-98) */
+#define JAADB_ST_INVALID_CODEBOOK 2   /* "invalid huffman codebook: 12"      A/syntax/ICStream.java:129 */
+#define JAADB_ST_TOO_MANY_BANDS 3     /* "too many bands"                    A/syntax/ICStream.java:138 */
+#define JAADB_ST_SF_RANGE 4           /* "scalefactor out of range"          A/syntax/ICStream.java:213 */
+#define JAADB_ST_PULSE_SHORT 5        /* "pulse data not allowed for short"  A/syntax/ICStream.java:79 */
+#define JAADB_ST_PULSE_RANGE 6        /* pulse SWB / offset out of range     A/syntax/ICStream.java:152,166 */
+#define JAADB_ST_MS_RESERVED 7        /* "reserved MS mask type used"        A/syntax/CPE.java:114 */
+#define JAADB_ST_TNS_ORDER 8          /* "TNS filter out of range"           A/tools/TNS.java:47 */
+#define JAADB_ST_LTP_PROFILE 9        /* "unexpected profile for LTP"        A/syntax/ICSInfo.java:139 */
+#define JAADB_ST_UNSUPPORTED_ELEMENT 10 /* CCE / PCE / SSR gain control / Main+LTP prediction / DRC / ADIF */
+#define JAADB_ST_LAYOUT 11            /* element sequence differs from the stream's channel layout */
+#define JAADB_ST_PROFILE 12           /* "unsupported profile"               A/Decoder.java:110 */
+#define JAADB_ST_ARRAY_BOUNDS 13      /* a Java ArrayIndexOutOfBoundsException (IQ index > 8190, sf index < 0 ...) */
+#define JAADB_ST_SBR 14               /* AACException raised inside the SBR tool */
+#define JAADB_ST_CONFIG 15
+
+/* PCM formats.  S16 interleaved is bit-identical to S/SampleBuffer.java:168-209
+ * (big-endian is SampleBuffer's default order, little-endian the AudioFormat one);
+ * F32 planar is the float[] list handed to A/Receiver.java:14. */
+#define JAADB_PCM_S16LE 0
+#define JAADB_PCM_S16BE 1
+#define JAADB_PCM_F32_PLANAR 2
+
+/* TNS modes.  JAAD parses TNS data and never applies it (A/tools/TNS.java:63-68);
+ * JAADB_TNS_JAAD reproduces that and is the parity mode. */
+#define JAADB_TNS_JAAD 0
+
+#define JAADB_FLAG_PROFILE 1u   /* record per-kernel CUDA-event timings (jaadb_batch_timings) */
+#define JAADB_FLAG_DEBUG_TAPS 2u /* keep the dequantised spectra for jaadb_batch_tap (parity tests) */
+
+typedef struct jaadb_engine jaadb_engine;
+typedef struct jaadb_batch jaadb_batch;
+
+typedef struct jaadb_options {
+  int32_t device;        /* CUDA device ordinal */
+  uint32_t max_streams;  /* capacity of the stream table */
+  int32_t pcm_format;    /* JAADB_PCM_* */
+  int32_t tns_mode;      /* JAADB_TNS_* */
+  uint32_t flags;        /* JAADB_FLAG_* */
+  uint32_t reserved[3];
+} jaadb_options;
+
+/* One AAC frame (an ADTS payload or an MP4 sample) inside the caller's blob.
+ * Replaces the BitStream argument of Decoder.decodeFrame (A/Decoder.java:89). */
+typedef struct jaadb_frame_desc {
+  uint64_t offset;     /* byte offset of the raw_data_block in the blob */
+  uint32_t nbytes;
+  int32_t stream_id;
+} jaadb_frame_desc;
+
+/* What SampleBuffer reports after accept() (S/SampleBuffer.java:72-110). */
+typedef struct jaadb_frame_result {
+  int32_t status;          /* JAADB_ST_* ; non-zero => no PCM for this frame, stream continues */
+  uint16_t channels;
+  uint16_t sample_length;  /* per channel: 1024, or 2048 with SBR up-sampling (A/DecoderConfig.java:83-86) */
+  uint32_t sample_rate;
+  uint32_t pcm_bytes;      /* bytes written at this frame's pcm offset */
+} jaadb_frame_result;
+
+typedef struct jaadb_stream_info {
+  int32_t profile;         /* audio object type of the core coder */
+  int32_t sf_index;        /* core sampling-frequency index */
+  int32_t channel_config;
+  int32_t channels;        /* A/DecoderConfig.java:108-115 (mono reports 2) */
+  int32_t sample_rate;     /* output rate */
+  int32_t sample_length;   /* per frame and channel */
+  int32_t sbr;             /* 1 if the stream is expected to carry SBR (decided at open) */
+  int32_t reserved;
+} jaadb_stream_info;
+
+typedef struct jaadb_timings {
+  float parse_ms;       /* K1: noiseless decode */
+  float filterbank_ms;  /* K2: dequant + stereo + IMDCT + overlap-add + PCM pack */
+  float sbr_ms;         /* K3..: SBR / PS stages (0 for AAC-LC) */
+  float total_ms;       /* first launch to last launch of the decode */
+  uint32_t launches;    /* kernels launched by the last jaadb_batch_decode */
+  uint32_t reserved[3];
+} jaadb_timings;
+
+int jaadb_abi_version(void);
+const char* jaadb_status_string(int32_t status);
+const char* jaadb_last_error(const jaadb_engine* e);
+
+/* ---- engine -------------------------------------------------------------- */
+int jaadb_engine_create(const jaadb_options* opts, jaadb_engine** out);
+void jaadb_engine_destroy(jaadb_engine* e);
+
+/* ---- streams -------------------------------------------------------------- */
+/* Decoder.create(byte[] audioSpecificConfig)   A/Decoder.java:36-43, A/DecoderConfig.java:175-254 */
+int jaadb_stream_open_asc(jaadb_engine* e, const uint8_t* asc, uint32_t asc_bytes, int32_t* stream_id);
+/* Decoder.create(AudioDecoderInfo) from an ADTS header   A/Decoder.java:45-48, S/adts/ADTSFrame.java:119-129
+ * `expect_sbr`: JAAD switches a stream to 2048-sample output when the first SBR
+ * payload arrives (A/sbr/SBR.java:98-101); the batched engine needs that decision at
+ * open time (0 = plain AAC-LC, 1 = SBR, 2 = SBR+PS). */
+int jaadb_stream_open_adts(jaadb_engine* e, int32_t profile, int32_t sf_index, int32_t channel_config,
+                           int32_t expect_sbr, int32_t* stream_id);
+int jaadb_stream_close(jaadb_engine* e, int32_t stream_id);
+int jaadb_stream_get_info(const jaadb_engine* e, int32_t stream_id, jaadb_stream_info* info);
+
+/* ---- one-call decode: host buffers in, host PCM out ----------------------
+ * Batched Decoder.decodeFrame (A/Decoder.java:89-121) + SampleBuffer.accept
+ * (S/SampleBuffer.java:168-209).  Frames of one stream are applied in array
+ * order; different streams are independent.  pcm_offsets[i] is the byte offset
+ * of frame i's PCM inside pcm_out (NULL: frames are packed back to back in
+ * array order, every frame taking its stream's full frame size).            */
+int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const jaadb_frame_desc* frames,
+                 uint32_t n_frames, void* pcm_out, uint64_t pcm_capacity, const uint64_t* pcm_offsets,
+                 jaadb_frame_result* results);
+
+/* ---- staged decode: the same work with the phases exposed ----------------
+ * create (index + upload descriptors) -> upload (H2D blob) -> decode (kernels
+ * only, everything resident in HBM) -> download (D2H PCM + results).         */
+int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* frames, uint32_t n_frames, uint64_t blob_bytes,
+                       const uint64_t* pcm_offsets, jaadb_batch** out);
+uint64_t jaadb_batch_pcm_bytes(const jaadb_batch* b);
+int jaadb_batch_upload(jaadb_batch* b, const uint8_t* blob, uint64_t blob_bytes);
+int jaadb_batch_decode(jaadb_batch* b);          /* asynchronous on the engine's stream */
+int jaadb_batch_sync(jaadb_batch* b);
+int jaadb_batch_download(jaadb_batch* b, void* pcm_out, uint64_t pcm_capacity, jaadb_frame_result* results);
+int jaadb_batch_timings(jaadb_batch* b, jaadb_timings* t);   /* needs JAADB_FLAG_PROFILE */
+void jaadb_batch_destroy(jaadb_batch* b);
+
+/* Parity taps (JAADB_FLAG_DEBUG_TAPS): integer and float intermediates of frame
+ * `frame`, channel slot `ch` of the last decode.  Any output pointer may be NULL.
+ *   q[1024]      quantised coefficients, de-interleaved as A/syntax/ICStream.java:258-271
+ *   sfidx[120]   SCALEFACTOR_TABLE index per (group, sfb); -1 where the scalefactor is 0.0f
+ *   sfbcb[120]   codebook per (group, sfb)
+ *   spec[1024]   dequantised spectrum after M/S and intensity stereo (input of the filterbank)
+ *   info[16]     present, window_sequence, window_shape, info_decoded, max_sfb, groups, group_len[8], ms_mask, common_window */
+int jaadb_batch_tap(jaadb_batch* b, uint32_t frame, uint32_t ch, int16_t* q, int16_t* sfidx, uint8_t* sfbcb,
+                    float* spec, int32_t* info, uint8_t* ms_used128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAADB200_H */

@@ -1,0 +1,86 @@
+"""ctypes binding of the C ABI declared in include/jaadb200.h.
+
+The product path has no CPU fallback: if the CUDA library is missing or cannot be
+loaded this module raises, it never substitutes another decoder.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+# symbols include/jaadb200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "jaadb_abi_version", "jaadb_status_string", "jaadb_last_error", "jaadb_engine_create", "jaadb_engine_destroy",
+    "jaadb_stream_open_asc", "jaadb_stream_open_adts", "jaadb_stream_close", "jaadb_stream_get_info", "jaadb_decode",
+    "jaadb_batch_create", "jaadb_batch_pcm_bytes", "jaadb_batch_upload", "jaadb_batch_decode", "jaadb_batch_sync",
+    "jaadb_batch_download", "jaadb_batch_timings", "jaadb_batch_destroy", "jaadb_batch_tap",
+]
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_streams", C.c_uint32), ("pcm_format", C.c_int32), ("tns_mode", C.c_int32),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
+class FrameDesc(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("nbytes", C.c_uint32), ("stream_id", C.c_int32)]
+
+
+class FrameResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("channels", C.c_uint16), ("sample_length", C.c_uint16), ("sample_rate", C.c_uint32),
+                ("pcm_bytes", C.c_uint32)]
+
+
+class StreamInfo(C.Structure):
+    _fields_ = [("profile", C.c_int32), ("sf_index", C.c_int32), ("channel_config", C.c_int32), ("channels", C.c_int32),
+                ("sample_rate", C.c_int32), ("sample_length", C.c_int32), ("sbr", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("parse_ms", C.c_float), ("filterbank_ms", C.c_float), ("sbr_ms", C.c_float), ("total_ms", C.c_float),
+                ("launches", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
+_lib = None
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.stale():
+        path = _build.build()
+    if not os.path.exists(path):
+        raise RuntimeError("libjaadb200.so is missing (%s): build it with __graft_entry__.build(); "
+                           "there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    vp, u8p = C.c_void_p, C.c_void_p
+    lib.jaadb_abi_version.restype = C.c_int
+    lib.jaadb_status_string.restype = C.c_char_p
+    lib.jaadb_status_string.argtypes = [C.c_int32]
+    lib.jaadb_last_error.restype = C.c_char_p
+    lib.jaadb_last_error.argtypes = [vp]
+    lib.jaadb_engine_create.argtypes = [C.POINTER(Options), C.POINTER(vp)]
+    lib.jaadb_engine_destroy.argtypes = [vp]
+    lib.jaadb_engine_destroy.restype = None
+    lib.jaadb_stream_open_asc.argtypes = [vp, u8p, C.c_uint32, C.POINTER(C.c_int32)]
+    lib.jaadb_stream_open_adts.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    lib.jaadb_stream_close.argtypes = [vp, C.c_int32]
+    lib.jaadb_stream_get_info.argtypes = [vp, C.c_int32, C.POINTER(StreamInfo)]
+    lib.jaadb_decode.argtypes = [vp, u8p, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, vp, vp]
+    lib.jaadb_batch_create.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp, C.POINTER(vp)]
+    lib.jaadb_batch_pcm_bytes.restype = C.c_uint64
+    lib.jaadb_batch_pcm_bytes.argtypes = [vp]
+    lib.jaadb_batch_upload.argtypes = [vp, u8p, C.c_uint64]
+    lib.jaadb_batch_decode.argtypes = [vp]
+    lib.jaadb_batch_sync.argtypes = [vp]
+    lib.jaadb_batch_download.argtypes = [vp, vp, C.c_uint64, vp]
+    lib.jaadb_batch_timings.argtypes = [vp, C.POINTER(Timings)]
+    lib.jaadb_batch_destroy.argtypes = [vp]
+    lib.jaadb_batch_destroy.restype = None
+    lib.jaadb_batch_tap.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp]
+    _lib = lib
+    return lib

@@ -1,0 +1,804 @@
+// Host runtime + C ABI of the B200 batched AAC decode engine (include/jaadb200.h).
+//
+// One engine = one GPU = one CUDA stream.  The stream table lives on the host,
+// per-stream persistent decode state (IMDCT overlap, window shapes) lives in HBM.
+// A batch indexes the caller's frames by stream, uploads the descriptors once and
+// can then be decoded any number of times with everything resident on the device.
+//
+// There is deliberately no CPU decode path in this file: if CUDA is unavailable
+// every entry point fails with JAADB_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jaadb200.h"
+#include "generated/jaad_tables_host.h"
+#include "k1_parse.cuh"
+#include "k2_filterbank.cuh"
+
+namespace T = ::jaad_tables;
+using namespace jaadb;
+
+namespace {
+
+#define CUDA_TRY(e, expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _err = (expr);                                                                 \
+    if (_err != cudaSuccess) {                                                                 \
+      (e)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_err));                    \
+      return JAADB_E_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+const int kSfFreq[12] = {96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000};
+
+struct StreamHost {
+  bool open = false;
+  int profile = 0, sf_index = 0, chan_cfg = 0;
+  int n_slots = 0;        // coded channels (channel slots)
+  int out_channels = 0;   // DecoderConfig.getChannelCount()
+  int sample_rate = 0, sample_length = 1024;
+  int sbr = 0;
+  bool profile_ok = true;
+};
+
+// Huffman LUT builder: two-level tables from the {len, code, values} rows (huffman/Codebooks.java).
+struct LutBuilder {
+  std::vector<uint32_t> lut;
+  uint32_t base[12];
+
+  static uint32_t leaf(int len, int nsign, uint32_t payload) { return (uint32_t)len | ((uint32_t)nsign << 5) | (payload << 16); }
+
+  void add_book(int book, const int32_t* rows, int nrows, int width, int first_bits, bool uns) {
+    const uint32_t b0 = (uint32_t)lut.size();
+    base[book] = b0;
+    lut.resize(b0 + (1u << first_bits), 0xFFFFFFFFu);
+    struct Sub { uint32_t prefix; int bits; uint32_t off; };
+    std::vector<Sub> subs;
+    // pass 1: sub-table sizes
+    for (int r = 0; r < nrows; ++r) {
+      int len = rows[r * width];
+      uint32_t code = (uint32_t)rows[r * width + 1];
+      if (len > first_bits) {
+        uint32_t pre = code >> (len - first_bits);
+        auto it = std::find_if(subs.begin(), subs.end(), [&](const Sub& s) { return s.prefix == pre; });
+        if (it == subs.end()) subs.push_back({pre, len - first_bits, 0});
+        else it->bits = std::max(it->bits, len - first_bits);
+      }
+    }
+    for (auto& s : subs) {
+      s.off = (uint32_t)lut.size();
+      lut.resize(lut.size() + (1u << s.bits), 0xFFFFFFFFu);
+      lut[b0 + s.prefix] = (uint32_t)s.bits | 0x100u | (s.off << 16);
+    }
+    // pass 2: leaves
+    for (int r = 0; r < nrows; ++r) {
+      int len = rows[r * width];
+      uint32_t code = (uint32_t)rows[r * width + 1];
+      uint32_t payload;
+      int nsign = 0;
+      if (width == 3) {
+        payload = (uint32_t)rows[r * width + 2];
+      } else if (width == 6) {
+        payload = 0;
+        for (int j = 0; j < 4; ++j) {
+          int v = rows[r * width + 2 + j];
+          payload |= ((uint32_t)v & 15u) << (4 * j);
+          if (uns && v != 0) ++nsign;
+        }
+      } else {
+        payload = 0;
+        for (int j = 0; j < 2; ++j) {
+          int v = rows[r * width + 2 + j];
+          payload |= ((uint32_t)v & 255u) << (8 * j);
+          if (uns && v != 0) ++nsign;
+        }
+      }
+      uint32_t e = leaf(len, nsign, payload);
+      if (len <= first_bits) {
+        uint32_t lo = code << (first_bits - len);
+        for (uint32_t i = 0; i < (1u << (first_bits - len)); ++i) lut[b0 + lo + i] = e;
+      } else {
+        uint32_t pre = code >> (len - first_bits);
+        auto it = std::find_if(subs.begin(), subs.end(), [&](const Sub& s) { return s.prefix == pre; });
+        int rem = len - first_bits;
+        uint32_t suffix = code & ((1u << rem) - 1u);
+        uint32_t lo = suffix << (it->bits - rem);
+        for (uint32_t i = 0; i < (1u << (it->bits - rem)); ++i) lut[it->off + lo + i] = e;
+      }
+    }
+  }
+};
+
+LayoutDev make_layout(int chan_cfg) {
+  LayoutDev l;
+  memset(&l, 0, sizeof l);
+  auto add = [&](int type) {
+    l.el_type[l.n_elements] = (uint8_t)type;
+    l.el_first_ch[l.n_elements] = l.n_channels;
+    l.n_channels += (type == EL_CPE) ? 2 : 1;
+    l.n_elements++;
+  };
+  switch (chan_cfg) {
+    case 1: add(EL_SCE); break;
+    case 2: add(EL_CPE); break;
+    case 3: add(EL_SCE); add(EL_CPE); break;
+    case 4: add(EL_SCE); add(EL_CPE); add(EL_SCE); break;
+    case 5: add(EL_SCE); add(EL_CPE); add(EL_CPE); break;
+    case 6: add(EL_SCE); add(EL_CPE); add(EL_CPE); add(EL_LFE); break;
+    case 7: add(EL_SCE); add(EL_CPE); add(EL_CPE); add(EL_CPE); add(EL_LFE); break;
+    default: break;
+  }
+  return l;
+}
+
+template <typename Tp>
+struct DevBuf {
+  Tp* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(Tp));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct jaadb_engine {
+  jaadb_options opts;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  std::vector<StreamHost> streams;
+  std::vector<int32_t> free_slots;
+  // device tables
+  std::vector<void*> table_allocs;
+  TablesDev tables;
+  LayoutDev* d_layouts = nullptr;
+  LayoutDev layouts[8];
+  uint32_t lut_entries = 0;
+  // persistent stream state
+  float* d_overlap = nullptr;
+  StreamState* d_sstate = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  void set_error(const std::string& s) { error = s; }
+
+  template <typename Tp>
+  int upload(const Tp* host, size_t n, const Tp** out) {
+    void* d = nullptr;
+    CUDA_TRY(this, cudaMalloc(&d, n * sizeof(Tp)));
+    table_allocs.push_back(d);
+    CUDA_TRY(this, cudaMemcpy(d, host, n * sizeof(Tp), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const Tp*>(d);
+    return 0;
+  }
+};
+
+struct jaadb_batch {
+  jaadb_engine* e = nullptr;
+  uint32_t n_frames = 0, n_ics = 0;
+  uint64_t blob_bytes = 0, pcm_bytes = 0;
+  std::vector<FrameDev> frames;
+  std::vector<RunDev> runs;           // grouped by channel count, see run_groups
+  std::vector<uint32_t> run_frames;
+  std::vector<uint64_t> pcm_off;
+  std::vector<uint32_t> frame_pcm_size;  // expected size per frame
+  struct Group { int nch; uint32_t first_run, n_runs; };
+  std::vector<Group> groups;
+  // device
+  DevBuf<uint8_t> d_blob, d_pcm;
+  DevBuf<FrameDev> d_frames;
+  DevBuf<FrameSide> d_fside;
+  DevBuf<IcsSide> d_iside;
+  DevBuf<int16_t> d_q;
+  DevBuf<RunDev> d_runs;
+  DevBuf<uint32_t> d_run_frames, d_pcm_bytes;
+  DevBuf<uint64_t> d_pcm_off;
+  DevBuf<float> d_spec_tap;
+  std::vector<FrameSide> h_fside;
+  std::vector<uint32_t> h_pcm_bytes;
+  jaadb_timings timings;
+  bool decoded = false;
+};
+
+namespace {
+
+int init_tables(jaadb_engine* e) {
+  TablesDev& D = e->tables;
+  memset(&D, 0, sizeof D);
+  LutBuilder lb;
+  lb.add_book(0, T::HCB_SF, 121, 3, kHuffSfFirstBits, false);
+  static const int32_t* rows[12] = {nullptr, T::HCB1, T::HCB2, T::HCB3, T::HCB4, T::HCB5, T::HCB6,
+                                    T::HCB7, T::HCB8, T::HCB9, T::HCB10, T::HCB11};
+  static const int nrows[12] = {0, 81, 81, 81, 81, 81, 81, 64, 64, 169, 169, 289};
+  static const bool uns[12] = {false, false, false, true, true, false, false, true, true, true, true, true};
+  for (int b = 1; b <= 11; ++b) lb.add_book(b, rows[b], nrows[b], b < 5 ? 6 : 4, kHuffFirstBits, uns[b]);
+  if (lb.lut.size() > 0xFFFF) { e->set_error("huffman LUT too large"); return JAADB_E_INVALID; }
+  for (uint32_t v : lb.lut)
+    if (v == 0xFFFFFFFFu) { e->set_error("huffman LUT has holes (codebook not complete)"); return JAADB_E_INVALID; }
+  for (int b = 0; b < 12; ++b) D.book_base[b] = lb.base[b];
+  D.huff_lut_entries = (uint32_t)lb.lut.size();
+  e->lut_entries = D.huff_lut_entries;
+  int rc;
+  if ((rc = e->upload(lb.lut.data(), lb.lut.size(), &D.huff_lut))) return rc;
+  if ((rc = e->upload(JT(IQ_TABLE), T::IQ_TABLE_N, &D.iq))) return rc;
+  if ((rc = e->upload(JT(SCALEFACTOR_TABLE), T::SCALEFACTOR_TABLE_N, &D.sf))) return rc;
+  if ((rc = e->upload(T::SWB_OFFSET_LONG, T::SWB_OFFSET_LONG_N, &D.swb_long))) return rc;
+  if ((rc = e->upload(T::SWB_OFFSET_SHORT, T::SWB_OFFSET_SHORT_N, &D.swb_short))) return rc;
+  uint8_t lc[12], sc[12];
+  std::vector<uint8_t> sfbl(12 * 1024, 255), sfbs(12 * 128, 255);
+  for (int s = 0; s < 12; ++s) {
+    lc[s] = (uint8_t)T::SWB_LONG_WINDOW_COUNT[s];
+    sc[s] = (uint8_t)T::SWB_SHORT_WINDOW_COUNT[s];
+    for (int b = 0; b < lc[s]; ++b)
+      for (int k = T::SWB_OFFSET_LONG[s * 53 + b]; k < T::SWB_OFFSET_LONG[s * 53 + b + 1]; ++k) sfbl[s * 1024 + k] = (uint8_t)b;
+    for (int b = 0; b < sc[s]; ++b)
+      for (int k = T::SWB_OFFSET_SHORT[s * 17 + b]; k < T::SWB_OFFSET_SHORT[s * 17 + b + 1]; ++k) sfbs[s * 128 + k] = (uint8_t)b;
+  }
+  if ((rc = e->upload(lc, 12, &D.swb_long_count))) return rc;
+  if ((rc = e->upload(sc, 12, &D.swb_short_count))) return rc;
+  if ((rc = e->upload(sfbl.data(), sfbl.size(), &D.sfb_of_long))) return rc;
+  if ((rc = e->upload(sfbs.data(), sfbs.size(), &D.sfb_of_short))) return rc;
+  if ((rc = e->upload(JT(MDCT_TABLE_2048), T::MDCT_TABLE_2048_N, &D.mdct_long))) return rc;
+  if ((rc = e->upload(JT(MDCT_TABLE_128), T::MDCT_TABLE_128_N, &D.mdct_short))) return rc;
+  if ((rc = e->upload(JT(FFT_TABLE_512), T::FFT_TABLE_512_N, &D.fft512))) return rc;
+  if ((rc = e->upload(JT(FFT_TABLE_64), T::FFT_TABLE_64_N, &D.fft64))) return rc;
+  if ((rc = e->upload(JT(SINE_1024), 1024, &D.win_long[0]))) return rc;
+  if ((rc = e->upload(JT(KBD_1024), 1024, &D.win_long[1]))) return rc;
+  if ((rc = e->upload(JT(SINE_128), 128, &D.win_short[0]))) return rc;
+  if ((rc = e->upload(JT(KBD_128), 128, &D.win_short[1]))) return rc;
+  for (int c = 0; c < 8; ++c) e->layouts[c] = make_layout(c);
+  const LayoutDev* dl = nullptr;
+  if ((rc = e->upload(e->layouts, 8, &dl))) return rc;
+  e->d_layouts = const_cast<LayoutDev*>(dl);
+  return 0;
+}
+
+// Minimal MSB-first reader for the AudioSpecificConfig (host side only).
+struct HostBits {
+  const uint8_t* d; uint32_t n, pos = 0;
+  bool ok = true;
+  uint32_t left() const { return 8 * n - pos; }
+  uint32_t read(int k) {
+    if (left() < (uint32_t)k) { ok = false; pos = 8 * n; return 0; }
+    uint32_t v = 0;
+    for (int i = 0; i < k; ++i, ++pos) v = (v << 1) | ((d[pos >> 3] >> (7 - (pos & 7))) & 1u);
+    return v;
+  }
+};
+
+bool profile_supported(int aot) {  // Profile.isDecodingSupported (Profile.java:5-21)
+  switch (aot) { case 1: case 2: case 4: case 5: case 17: case 19: case 29: return true; default: return false; }
+}
+
+int profile_for_int(int i) {  // Profile.forInt (Profile.java:23-57); -1 = UNKNOWN
+  static const int ALL[30] = {1, 2, 3, 4, 5, 6, 7, -1, -1, -1, 11, -1, -1, -1, -1, -1, 17, 18,
+                              19, 20, 21, 22, 23, -1, -1, -1, -1, -1, 29, -1};
+  return (i >= 1 && i <= 30) ? ALL[i - 1] : -1;
+}
+
+int nominal_index(int freq) {  // SampleFrequency.nominalFrequency (SampleFrequency.java:68-93)
+  int result = -1;
+  float dev = INFINITY;
+  for (int i = 0; i < 12; ++i) {
+    float d = ((float)freq - (float)kSfFreq[i]) / (float)kSfFreq[i];
+    if (d == 0) return i;
+    if (d < dev) { result = i; dev = d; }
+    if (kSfFreq[i] < freq) break;
+  }
+  return result;
+}
+
+int finish_open(jaadb_engine* e, StreamHost& s, int32_t* stream_id) {
+  if (s.chan_cfg < 1 || s.chan_cfg > 7) { e->set_error("unsupported channel configuration"); return JAADB_E_CONFIG; }
+  if (s.sf_index < 0 || s.sf_index > 11) { e->set_error("unsupported sampling frequency index"); return JAADB_E_CONFIG; }
+  const LayoutDev& l = e->layouts[s.chan_cfg];
+  s.n_slots = l.n_channels;
+  s.out_channels = (s.chan_cfg == 1) ? 2 : l.n_channels;  // DecoderConfig.getChannelCount (DecoderConfig.java:108-115)
+  s.profile_ok = profile_supported(s.profile);
+  if (s.sbr) { e->set_error("SBR/PS streams are not implemented in this build"); return JAADB_E_CONFIG; }
+  if (e->free_slots.empty()) { e->set_error("stream table full"); return JAADB_E_CAPACITY; }
+  int32_t slot = e->free_slots.back();
+  e->free_slots.pop_back();
+  s.open = true;
+  e->streams[slot] = s;
+  CUDA_TRY(e, cudaMemsetAsync(e->d_overlap + (size_t)slot * kMaxChannels * 1024, 0, sizeof(float) * kMaxChannels * 1024, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(e->d_sstate + slot, 0, sizeof(StreamState), e->stream));
+  *stream_id = slot;
+  return JAADB_OK;
+}
+
+uint32_t frame_pcm_bytes(const jaadb_engine* e, const StreamHost& s) {
+  const uint32_t per = (e->opts.pcm_format == JAADB_PCM_F32_PLANAR) ? 4u : 2u;
+  return (uint32_t)s.out_channels * (uint32_t)s.sample_length * per;
+}
+
+size_t k2_smem_bytes(int nch, int out_ch) {
+  const int per_ch = kSpecStride + 1024 + 2 * kXchgStride;
+  size_t b = sizeof(float) * (2 * 256 + 2 * 32 + (size_t)nch * per_ch);
+  b += sizeof(IcsSide) * nch + 8 * kMaxChannels;
+  b += sizeof(int16_t) * 1024 * out_ch;
+  return (b + 15) & ~size_t(15);
+}
+
+}  // namespace
+
+extern "C" {
+
+int jaadb_abi_version(void) { return JAADB_ABI_VERSION; }
+
+const char* jaadb_status_string(int32_t st) {
+  switch (st) {
+    case JAADB_ST_OK: return "ok";
+    case JAADB_ST_EOS: return "unexpected end of frame";
+    case JAADB_ST_INVALID_CODEBOOK: return "invalid huffman codebook: 12";
+    case JAADB_ST_TOO_MANY_BANDS: return "too many bands";
+    case JAADB_ST_SF_RANGE: return "scalefactor out of range";
+    case JAADB_ST_PULSE_SHORT: return "pulse data not allowed for short frames";
+    case JAADB_ST_PULSE_RANGE: return "pulse data out of range";
+    case JAADB_ST_MS_RESERVED: return "reserved MS mask type used";
+    case JAADB_ST_TNS_ORDER: return "TNS filter out of range";
+    case JAADB_ST_LTP_PROFILE: return "unexpected profile for LTP";
+    case JAADB_ST_UNSUPPORTED_ELEMENT: return "syntax element outside the engine's scope";
+    case JAADB_ST_LAYOUT: return "element sequence differs from the stream's channel layout";
+    case JAADB_ST_PROFILE: return "unsupported profile";
+    case JAADB_ST_ARRAY_BOUNDS: return "table index out of bounds";
+    case JAADB_ST_SBR: return "SBR error";
+    case JAADB_ST_CONFIG: return "bad configuration";
+    default: return "unknown status";
+  }
+}
+
+const char* jaadb_last_error(const jaadb_engine* e) { return e ? e->error.c_str() : "null engine"; }
+
+int jaadb_engine_create(const jaadb_options* opts, jaadb_engine** out) {
+  if (!opts || !out) return JAADB_E_INVALID;
+  *out = nullptr;
+  if (opts->pcm_format < 0 || opts->pcm_format > 2 || opts->tns_mode != JAADB_TNS_JAAD || opts->max_streams == 0)
+    return JAADB_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || opts->device < 0 || opts->device >= ndev) return JAADB_E_CUDA;
+  jaadb_engine* e = new jaadb_engine();
+  e->opts = *opts;
+  auto fail = [&](int rc) { jaadb_engine_destroy(e); return rc; };
+  if (cudaSetDevice(opts->device) != cudaSuccess) return fail(JAADB_E_CUDA);
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(JAADB_E_CUDA);
+  for (auto& ev : e->ev)
+    if (cudaEventCreate(&ev) != cudaSuccess) return fail(JAADB_E_CUDA);
+  int rc = init_tables(e);
+  if (rc) return fail(rc);
+  e->streams.resize(opts->max_streams);
+  e->free_slots.reserve(opts->max_streams);
+  for (int32_t i = (int32_t)opts->max_streams - 1; i >= 0; --i) e->free_slots.push_back(i);
+  if (cudaMalloc(reinterpret_cast<void**>(&e->d_overlap), sizeof(float) * (size_t)opts->max_streams * kMaxChannels * 1024) != cudaSuccess)
+    return fail(JAADB_E_NOMEM);
+  if (cudaMalloc(reinterpret_cast<void**>(&e->d_sstate), sizeof(StreamState) * (size_t)opts->max_streams) != cudaSuccess)
+    return fail(JAADB_E_NOMEM);
+  // opt in to the shared-memory sizes the kernels need
+  cudaFuncSetAttribute(k1_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e->lut_entries * 4));
+  const int k2max = (int)k2_smem_bytes(kMaxChannels, kMaxChannels);
+  cudaFuncSetAttribute(k2_filterbank_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max);
+  cudaFuncSetAttribute(k2_filterbank_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max);
+  cudaFuncSetAttribute(k2_filterbank_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max);
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess) return fail(JAADB_E_CUDA);
+  *out = e;
+  return JAADB_OK;
+}
+
+void jaadb_engine_destroy(jaadb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->opts.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void* p : e->table_allocs) cudaFree(p);
+  if (e->d_overlap) cudaFree(e->d_overlap);
+  if (e->d_sstate) cudaFree(e->d_sstate);
+  for (auto& ev : e->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int jaadb_stream_open_adts(jaadb_engine* e, int32_t profile, int32_t sf_index, int32_t channel_config,
+                           int32_t expect_sbr, int32_t* stream_id) {
+  if (!e || !stream_id) return JAADB_E_INVALID;
+  cudaSetDevice(e->opts.device);
+  StreamHost s;
+  s.profile = profile_for_int(profile);   // ADTSFrame.getProfile -> Profile.forInt (S/adts/ADTSFrame.java:119-121)
+  s.sf_index = sf_index;
+  int cc = channel_config >= 7 ? channel_config + 1 : channel_config;  // ChannelConfiguration.forInt (:26-33)
+  if (cc > 8 || cc == 7) { e->set_error("invalid channel configuration"); return JAADB_E_CONFIG; }
+  s.chan_cfg = (cc == 8) ? 7 : cc;  // layout index 7 = 7.1 (8 channels)
+  if (sf_index < 0 || sf_index > 11) { e->set_error("unsupported sampling frequency index"); return JAADB_E_CONFIG; }
+  s.sample_rate = kSfFreq[sf_index];
+  s.sample_length = 1024;
+  if (expect_sbr < 0) expect_sbr = (sf_index >= 6) ? 1 : 0;
+  s.sbr = expect_sbr;
+  if (s.sbr) {
+    // DecoderConfig.setSBRPresent (A/DecoderConfig.java:124-135): ADTS streams have no output frequency yet
+    if (sf_index >= 3) { s.sample_rate = kSfFreq[sf_index - 3]; s.sample_length = 2048; }
+  }
+  return finish_open(e, s, stream_id);
+}
+
+int jaadb_stream_open_asc(jaadb_engine* e, const uint8_t* asc, uint32_t n, int32_t* stream_id) {
+  if (!e || !asc || !stream_id) return JAADB_E_INVALID;
+  cudaSetDevice(e->opts.device);
+  // DecoderConfig.decode (A/DecoderConfig.java:175-254)
+  HostBits in{asc, n};
+  auto read_profile = [&]() { int i = (int)in.read(5); if (i == 31) i = 32 + (int)in.read(6); return profile_for_int(i); };
+  auto read_rate = [&](int& index, int& freq) {
+    int idx = (int)in.read(4);
+    if (idx != 15) { if (idx >= 12) return false; index = idx; freq = kSfFreq[idx]; return true; }
+    freq = (int)in.read(24);
+    index = nominal_index(freq);
+    return index >= 0;
+  };
+  StreamHost s;
+  int profile = read_profile();
+  int sf_index = -1, freq = 0;
+  if (!read_rate(sf_index, freq)) { e->set_error("bad sampling frequency in AudioSpecificConfig"); return JAADB_E_CONFIG; }
+  int out_freq = freq;
+  int cc = (int)in.read(4);
+  if (cc >= 7) ++cc;
+  if (cc > 8 || cc == 7 || cc == 0) { e->set_error("unsupported channel configuration in AudioSpecificConfig"); return JAADB_E_CONFIG; }
+  int sbr = 0;
+  switch (profile) {
+    case 29: sbr = 2;  // fall through: PS implies SBR
+    case 5: {
+      if (!sbr) sbr = 1;
+      int ext_index, ext_freq;
+      if (!read_rate(ext_index, ext_freq)) { e->set_error("bad extension sampling frequency"); return JAADB_E_CONFIG; }
+      profile = read_profile();
+      out_freq = ext_freq;
+      break;
+    }
+    case 1: case 2: case 3: case 4: case 17: case 19: case 23: {
+      if (in.read(1)) { e->set_error("config uses 960-sample frames, not yet supported"); return JAADB_E_CONFIG; }
+      if (in.read(1)) in.read(14);
+      if (in.read(1)) {
+        if (profile > 16) in.read(3);
+        in.read(1);
+      }
+      if (in.left() > 10) {
+        // readSyncExtension (A/DecoderConfig.java:268-291)
+        if (in.read(11) == 0x2B7) {
+          int ext = profile_for_int((int)in.read(5));
+          if (ext == 5 || ext == 22) {
+            bool present = in.read(1) != 0;
+            if (present) {
+              int ext_index, ext_freq;
+              if (!read_rate(ext_index, ext_freq)) { e->set_error("bad extension sampling frequency"); return JAADB_E_CONFIG; }
+              out_freq = ext_freq;
+              sbr = 1;
+            }
+            if (ext == 5 && in.left() > 12 && in.read(11) == 0x548 && in.read(1)) sbr = 2;
+          }
+        }
+      }
+      break;
+    }
+    default:
+      e->set_error("profile not supported");
+      return JAADB_E_CONFIG;
+  }
+  if (!in.ok) { e->set_error("AudioSpecificConfig truncated"); return JAADB_E_CONFIG; }
+  s.profile = profile;
+  s.sf_index = sf_index;
+  s.chan_cfg = (cc == 8) ? 7 : cc;
+  s.sample_rate = out_freq;
+  // outputFrequency was set from the ASC: sample length doubles only if it differs (A/DecoderConfig.java:83-86)
+  s.sample_length = (out_freq != freq) ? 2048 : 1024;
+  s.sbr = sbr;
+  return finish_open(e, s, stream_id);
+}
+
+int jaadb_stream_close(jaadb_engine* e, int32_t id) {
+  if (!e) return JAADB_E_INVALID;
+  if (id < 0 || id >= (int32_t)e->streams.size() || !e->streams[id].open) return JAADB_E_NOSTREAM;
+  e->streams[id].open = false;
+  e->free_slots.push_back(id);
+  return JAADB_OK;
+}
+
+int jaadb_stream_get_info(const jaadb_engine* e, int32_t id, jaadb_stream_info* info) {
+  if (!e || !info) return JAADB_E_INVALID;
+  if (id < 0 || id >= (int32_t)e->streams.size() || !e->streams[id].open) return JAADB_E_NOSTREAM;
+  const StreamHost& s = e->streams[id];
+  info->profile = s.profile;
+  info->sf_index = s.sf_index;
+  info->channel_config = s.chan_cfg;
+  info->channels = s.out_channels;
+  info->sample_rate = s.sample_rate;
+  info->sample_length = s.sample_length;
+  info->sbr = s.sbr;
+  info->reserved = 0;
+  return JAADB_OK;
+}
+
+int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64_t blob_bytes,
+                       const uint64_t* pcm_offsets, jaadb_batch** out) {
+  if (!e || !out || (n && !fd)) return JAADB_E_INVALID;
+  *out = nullptr;
+  cudaSetDevice(e->opts.device);
+  jaadb_batch* b = new jaadb_batch();
+  b->e = e;
+  b->n_frames = n;
+  b->blob_bytes = blob_bytes;
+  b->frames.resize(n);
+  b->pcm_off.resize(n);
+  b->frame_pcm_size.resize(n);
+  auto fail = [&](int rc) { jaadb_batch_destroy(b); return rc; };
+  // per-stream frame counts (counting sort keeps array order inside each stream)
+  std::vector<uint32_t> count(e->streams.size(), 0);
+  uint32_t ics = 0;
+  uint64_t pcm_pos = 0, pcm_end = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const jaadb_frame_desc& d = fd[i];
+    if (d.stream_id < 0 || d.stream_id >= (int32_t)e->streams.size() || !e->streams[d.stream_id].open) {
+      e->set_error("frame refers to an unknown stream");
+      return fail(JAADB_E_NOSTREAM);
+    }
+    if (d.offset + d.nbytes > blob_bytes) { e->set_error("frame exceeds the blob"); return fail(JAADB_E_INVALID); }
+    const StreamHost& s = e->streams[d.stream_id];
+    FrameDev& f = b->frames[i];
+    f.blob_off = d.offset;
+    f.nbytes = d.nbytes;
+    f.stream_slot = d.stream_id;
+    f.ics_base = ics;
+    f.sf_index = (uint8_t)s.sf_index;
+    f.layout = (uint8_t)s.chan_cfg;
+    f.profile_ok = s.profile_ok ? 1 : 0;
+    f.flags = 0;
+    ics += (uint32_t)s.n_slots;
+    count[d.stream_id]++;
+    const uint32_t sz = frame_pcm_bytes(e, s);
+    b->frame_pcm_size[i] = sz;
+    if (pcm_offsets) {
+      if (pcm_offsets[i] & 3u) { e->set_error("pcm offsets must be 4-byte aligned"); return fail(JAADB_E_INVALID); }
+      b->pcm_off[i] = pcm_offsets[i];
+    } else {
+      b->pcm_off[i] = pcm_pos;
+      pcm_pos += sz;
+    }
+    pcm_end = std::max(pcm_end, b->pcm_off[i] + sz);
+  }
+  b->n_ics = ics;
+  b->pcm_bytes = pcm_end;
+  // runs, grouped by channel-slot count so every launch has a uniform block size
+  std::vector<uint32_t> run_of(e->streams.size(), 0xFFFFFFFFu);
+  for (int nch = 1; nch <= kMaxChannels; ++nch) {
+    jaadb_batch::Group g{nch, (uint32_t)b->runs.size(), 0};
+    for (size_t s = 0; s < e->streams.size(); ++s) {
+      if (!count[s] || e->streams[s].n_slots != nch) continue;
+      RunDev r;
+      memset(&r, 0, sizeof r);
+      r.stream_slot = (int32_t)s;
+      r.count = count[s];
+      r.layout = (uint8_t)e->streams[s].chan_cfg;
+      r.sf_index = (uint8_t)e->streams[s].sf_index;
+      r.mono_dup = (e->streams[s].chan_cfg == 1) ? 1 : 0;
+      run_of[s] = (uint32_t)b->runs.size();
+      b->runs.push_back(r);
+      g.n_runs++;
+    }
+    if (g.n_runs) b->groups.push_back(g);
+  }
+  uint32_t acc = 0;
+  for (auto& r : b->runs) { r.first = acc; acc += r.count; }
+  b->run_frames.resize(n);
+  std::vector<uint32_t> fill(b->runs.size(), 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t r = run_of[fd[i].stream_id];
+    b->run_frames[b->runs[r].first + fill[r]++] = i;
+  }
+  // device side
+  cudaError_t ce = cudaSuccess;
+  auto chk = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
+  chk(b->d_blob.ensure(blob_bytes + 64));
+  chk(b->d_pcm.ensure(std::max<uint64_t>(b->pcm_bytes, 16)));
+  chk(b->d_frames.ensure(std::max<uint32_t>(n, 1)));
+  chk(b->d_fside.ensure(std::max<uint32_t>(n, 1)));
+  chk(b->d_iside.ensure(std::max<uint32_t>(ics, 1)));
+  chk(b->d_q.ensure(std::max<size_t>((size_t)ics * 1024, 16)));
+  chk(b->d_runs.ensure(std::max<size_t>(b->runs.size(), 1)));
+  chk(b->d_run_frames.ensure(std::max<uint32_t>(n, 1)));
+  chk(b->d_pcm_bytes.ensure(std::max<uint32_t>(n, 1)));
+  chk(b->d_pcm_off.ensure(std::max<uint32_t>(n, 1)));
+  if (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) chk(b->d_spec_tap.ensure(std::max<size_t>((size_t)ics * 1024, 16)));
+  if (ce != cudaSuccess) { e->set_error(std::string("batch allocation: ") + cudaGetErrorString(ce)); return fail(JAADB_E_NOMEM); }
+  if (n) {
+    chk(cudaMemcpyAsync(b->d_frames.p, b->frames.data(), sizeof(FrameDev) * n, cudaMemcpyHostToDevice, e->stream));
+    chk(cudaMemcpyAsync(b->d_runs.p, b->runs.data(), sizeof(RunDev) * b->runs.size(), cudaMemcpyHostToDevice, e->stream));
+    chk(cudaMemcpyAsync(b->d_run_frames.p, b->run_frames.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    chk(cudaMemcpyAsync(b->d_pcm_off.p, b->pcm_off.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream));
+    chk(cudaMemsetAsync(b->d_blob.p + blob_bytes, 0, 64, e->stream));
+    chk(cudaStreamSynchronize(e->stream));
+  }
+  if (ce != cudaSuccess) { e->set_error(std::string("batch upload: ") + cudaGetErrorString(ce)); return fail(JAADB_E_CUDA); }
+  memset(&b->timings, 0, sizeof b->timings);
+  *out = b;
+  return JAADB_OK;
+}
+
+uint64_t jaadb_batch_pcm_bytes(const jaadb_batch* b) { return b ? b->pcm_bytes : 0; }
+
+int jaadb_batch_upload(jaadb_batch* b, const uint8_t* blob, uint64_t blob_bytes) {
+  if (!b || (!blob && blob_bytes) || blob_bytes != b->blob_bytes) return JAADB_E_INVALID;
+  jaadb_engine* e = b->e;
+  cudaSetDevice(e->opts.device);
+  if (blob_bytes) CUDA_TRY(e, cudaMemcpyAsync(b->d_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, e->stream));
+  return JAADB_OK;
+}
+
+int jaadb_batch_decode(jaadb_batch* b) {
+  if (!b) return JAADB_E_INVALID;
+  jaadb_engine* e = b->e;
+  cudaSetDevice(e->opts.device);
+  const bool prof = (e->opts.flags & JAADB_FLAG_PROFILE) != 0;
+  uint32_t launches = 0;
+  if (b->n_frames == 0) { b->decoded = true; return JAADB_OK; }
+  if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[0], e->stream));
+  {
+    const int threads = 128;
+    const int blocks = (int)((b->n_frames + threads - 1) / threads);
+    k1_parse_kernel<<<blocks, threads, e->lut_entries * 4, e->stream>>>(
+        b->d_blob.p, b->d_frames.p, b->n_frames, b->d_fside.p, b->d_iside.p, b->d_q.p, e->tables, e->d_layouts);
+    ++launches;
+  }
+  if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[1], e->stream));
+  for (const auto& g : b->groups) {
+    const int threads = g.nch * kThreadsPerChannel;
+    const int out_ch = (g.nch == 1) ? 2 : g.nch;
+    const size_t smem = k2_smem_bytes(g.nch, out_ch);
+    const RunDev* runs = b->d_runs.p + g.first_run;
+    float* tap = (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) ? b->d_spec_tap.p : nullptr;
+#define LAUNCH_K2(FMT)                                                                                         \
+  k2_filterbank_kernel<FMT><<<g.n_runs, threads, smem, e->stream>>>(                                           \
+      runs, b->d_run_frames.p, b->d_frames.p, b->d_fside.p, b->d_iside.p, b->d_q.p, e->d_overlap, e->d_sstate, \
+      b->d_pcm.p, b->d_pcm_off.p, b->d_pcm_bytes.p, tap, e->tables, e->d_layouts, g.nch)
+    if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K2(0);
+    else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K2(1);
+    else LAUNCH_K2(2);
+#undef LAUNCH_K2
+    ++launches;
+  }
+  if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[2], e->stream));
+  CUDA_TRY(e, cudaGetLastError());
+  b->timings.launches = launches;
+  b->decoded = true;
+  return JAADB_OK;
+}
+
+int jaadb_batch_sync(jaadb_batch* b) {
+  if (!b) return JAADB_E_INVALID;
+  CUDA_TRY(b->e, cudaStreamSynchronize(b->e->stream));
+  return JAADB_OK;
+}
+
+int jaadb_batch_timings(jaadb_batch* b, jaadb_timings* t) {
+  if (!b || !t) return JAADB_E_INVALID;
+  jaadb_engine* e = b->e;
+  if (!(e->opts.flags & JAADB_FLAG_PROFILE) || !b->decoded) return JAADB_E_INVALID;
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  if (b->n_frames) {
+    CUDA_TRY(e, cudaEventElapsedTime(&b->timings.parse_ms, e->ev[0], e->ev[1]));
+    CUDA_TRY(e, cudaEventElapsedTime(&b->timings.filterbank_ms, e->ev[1], e->ev[2]));
+    CUDA_TRY(e, cudaEventElapsedTime(&b->timings.total_ms, e->ev[0], e->ev[2]));
+  }
+  *t = b->timings;
+  return JAADB_OK;
+}
+
+int jaadb_batch_download(jaadb_batch* b, void* pcm_out, uint64_t cap, jaadb_frame_result* results) {
+  if (!b || !b->decoded) return JAADB_E_INVALID;
+  jaadb_engine* e = b->e;
+  cudaSetDevice(e->opts.device);
+  if (pcm_out) {
+    if (cap < b->pcm_bytes) { e->set_error("pcm buffer too small"); return JAADB_E_CAPACITY; }
+    if (b->pcm_bytes) CUDA_TRY(e, cudaMemcpyAsync(pcm_out, b->d_pcm.p, b->pcm_bytes, cudaMemcpyDeviceToHost, e->stream));
+  }
+  if (results && b->n_frames) {
+    b->h_fside.resize(b->n_frames);
+    b->h_pcm_bytes.resize(b->n_frames);
+    CUDA_TRY(e, cudaMemcpyAsync(b->h_fside.data(), b->d_fside.p, sizeof(FrameSide) * b->n_frames, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(b->h_pcm_bytes.data(), b->d_pcm_bytes.p, sizeof(uint32_t) * b->n_frames, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  if (results) {
+    for (uint32_t i = 0; i < b->n_frames; ++i) {
+      const StreamHost& s = e->streams[b->frames[i].stream_slot];
+      jaadb_frame_result& r = results[i];
+      r.status = b->h_fside[i].status;
+      r.pcm_bytes = b->h_pcm_bytes[i];
+      r.channels = r.status ? 0 : (uint16_t)s.out_channels;
+      r.sample_length = r.status ? 0 : (uint16_t)s.sample_length;
+      r.sample_rate = (uint32_t)s.sample_rate;
+    }
+  }
+  return JAADB_OK;
+}
+
+void jaadb_batch_destroy(jaadb_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->e->opts.device);
+  cudaStreamSynchronize(b->e->stream);
+  b->d_blob.release(); b->d_pcm.release(); b->d_frames.release(); b->d_fside.release(); b->d_iside.release();
+  b->d_q.release(); b->d_runs.release(); b->d_run_frames.release(); b->d_pcm_bytes.release(); b->d_pcm_off.release();
+  b->d_spec_tap.release();
+  delete b;
+}
+
+int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const jaadb_frame_desc* frames,
+                 uint32_t n_frames, void* pcm_out, uint64_t pcm_capacity, const uint64_t* pcm_offsets,
+                 jaadb_frame_result* results) {
+  jaadb_batch* b = nullptr;
+  int rc = jaadb_batch_create(e, frames, n_frames, blob_bytes, pcm_offsets, &b);
+  if (rc) return rc;
+  rc = jaadb_batch_upload(b, blob, blob_bytes);
+  if (!rc) rc = jaadb_batch_decode(b);
+  if (!rc) rc = jaadb_batch_download(b, pcm_out, pcm_capacity, results);
+  jaadb_batch_destroy(b);
+  return rc;
+}
+
+int jaadb_batch_tap(jaadb_batch* b, uint32_t frame, uint32_t ch, int16_t* q, int16_t* sfidx, uint8_t* sfbcb, float* spec,
+                    int32_t* info, uint8_t* ms_used128) {
+  if (!b || !b->decoded || frame >= b->n_frames) return JAADB_E_INVALID;
+  jaadb_engine* e = b->e;
+  cudaSetDevice(e->opts.device);
+  const StreamHost& s = e->streams[b->frames[frame].stream_slot];
+  if ((int)ch >= s.n_slots) return JAADB_E_INVALID;
+  const uint32_t ics = b->frames[frame].ics_base + ch;
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  IcsSide side;
+  CUDA_TRY(e, cudaMemcpy(&side, b->d_iside.p + ics, sizeof side, cudaMemcpyDeviceToHost));
+  const int nb = side.num_groups * side.max_sfb;
+  if (info) {
+    info[0] = side.present; info[1] = side.window_sequence; info[2] = side.window_shape; info[3] = side.info_decoded;
+    info[4] = side.max_sfb; info[5] = side.num_groups;
+    for (int i = 0; i < 8; ++i) info[6 + i] = i < side.num_groups ? side.group_len[i] : 0;
+    info[14] = side.ms_mask; info[15] = side.common_window;
+  }
+  if (sfbcb) { memset(sfbcb, 0, 120); for (int i = 0; i < nb && i < 120; ++i) sfbcb[i] = side.sfb_cb[i]; }
+  if (sfidx) {
+    for (int i = 0; i < 120; ++i) sfidx[i] = -1;
+    for (int i = 0; i < nb && i < 120; ++i) sfidx[i] = side.sf_idx[i] == 0xFFFF ? (int16_t)-1 : (int16_t)side.sf_idx[i];
+  }
+  if (ms_used128) for (int i = 0; i < 128; ++i) ms_used128[i] = (side.ms_used[i >> 3] >> (i & 7)) & 1;
+  if (q) {
+    std::vector<int16_t> raw(1024);
+    CUDA_TRY(e, cudaMemcpy(raw.data(), b->d_q.p + (size_t)ics * 1024, 2048, cudaMemcpyDeviceToHost));
+    // present the coefficients the way ICStream.decodeSpectralData leaves them: zero outside coded bands
+    memset(q, 0, 2048);
+    const bool sh = side.window_sequence == 2;
+    const int16_t* swb = sh ? T::SWB_OFFSET_SHORT + 17 * s.sf_index : T::SWB_OFFSET_LONG + 53 * s.sf_index;
+    const int swbc = sh ? T::SWB_SHORT_WINDOW_COUNT[s.sf_index] : T::SWB_LONG_WINDOW_COUNT[s.sf_index];
+    int goff = 0, idx = 0;
+    for (int g = 0; g < side.num_groups; ++g) {
+      for (int sfb = 0; sfb < side.max_sfb; ++sfb, ++idx) {
+        int cb = side.sfb_cb[idx];
+        if (cb < 1 || cb > 11 || sfb >= swbc) continue;
+        for (int w = 0; w < side.group_len[g]; ++w)
+          for (int k = swb[sfb]; k < swb[sfb + 1]; ++k) q[goff + w * 128 + k] = raw[goff + w * 128 + k];
+      }
+      goff += side.group_len[g] * 128;
+    }
+  }
+  if (spec) {
+    if (!b->d_spec_tap.p) return JAADB_E_INVALID;
+    CUDA_TRY(e, cudaMemcpy(spec, b->d_spec_tap.p + (size_t)ics * 1024, 4096, cudaMemcpyDeviceToHost));
+  }
+  return JAADB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// Device-side data layout shared by the kernels and the host runtime.
+//
+// HBM layout (all arrays are engine- or batch-owned, SoA across frames/streams):
+//   blob            uint8  [blob_bytes + 16]        compressed frames (caller's blob, padded)
+//   frames          FrameDev [n_frames]             per frame: where it is and which stream it belongs to
+//   frame_side      FrameSide [n_frames]            K1 out: status word per frame
+//   ics_side        IcsSide [n_ics]                 K1 out: window flags, sections, scalefactors per channel-frame
+//   q               int16  [n_ics][1024]            K1 out: quantised coefficients (window de-interleaved)
+//   runs / run_frames                               per stream: its frames of this batch in decode order
+//   overlap         float  [max_streams][8][1024]   persistent IMDCT overlap per channel slot (ICStream.java:47)
+//   stream_state    StreamState [max_streams]       persistent window_shape[CURRENT] per channel slot
+//   pcm             int16/float                     K2 out
+#pragma once
+#include <cstdint>
+
+namespace jaadb {
+
+constexpr int kMaxChannels = 8;      // channel slots per stream (7.1)
+constexpr int kMaxElements = 5;      // SCE,CPE,CPE,CPE,LFE
+constexpr int kMaxSfbEntries = 120;  // ICStream.MAX_SECTIONS
+
+enum ElementType : int { EL_SCE = 0, EL_CPE = 1, EL_CCE = 2, EL_LFE = 3, EL_DSE = 4, EL_PCE = 5, EL_FIL = 6, EL_END = 7 };
+
+// Channel layouts by channel_configuration (SyntacticElements.java:89-127 lists the same orders).
+struct LayoutDev {
+  uint8_t n_elements;
+  uint8_t n_channels;
+  uint8_t el_type[kMaxElements];
+  uint8_t el_first_ch[kMaxElements];
+};
+
+struct FrameDev {
+  uint64_t blob_off;
+  uint32_t nbytes;
+  int32_t stream_slot;
+  uint32_t ics_base;      // index of this frame's first channel slot in ics_side / q
+  uint8_t sf_index;
+  uint8_t layout;         // channel_configuration (1..7)
+  uint8_t profile_ok;
+  uint8_t flags;
+};
+
+struct FrameSide {
+  int32_t status;
+  uint16_t tags;          // 4-bit instance tag of up to 4 elements... (element i in bits 4i..4i+3)
+  uint8_t n_elements;
+  uint8_t pad;
+  uint32_t sbr_bit_off[2];  // bit offset of an SBR FIL payload following element 0/1 (0 = none)
+  uint32_t sbr_bits[2];
+};
+
+// Side information of one individual_channel_stream (one channel of one frame).
+struct __align__(16) IcsSide {
+  uint8_t present;          // spectral data completely decoded
+  uint8_t info_decoded;     // ics_info was read (window_shape bookkeeping, ICSInfo.java:90-91)
+  uint8_t window_sequence;
+  uint8_t window_shape;
+  uint8_t max_sfb;
+  uint8_t num_groups;
+  uint8_t ms_mask;          // CPE only: ms_mask_present
+  uint8_t common_window;    // CPE only
+  uint8_t group_len[8];
+  uint8_t ms_used[16];      // CPE only: bit (g*max_sfb+sfb)
+  uint8_t sfb_cb[kMaxSfbEntries];
+  uint16_t sf_idx[kMaxSfbEntries];  // SCALEFACTOR_TABLE index, 0xFFFF: scalefactor is 0.0f
+  uint8_t tns_present;
+  uint8_t pad[7];
+};
+static_assert(sizeof(IcsSide) == 400, "IcsSide layout");
+
+struct StreamState {
+  uint8_t window_shape[kMaxChannels];  // windowShape[CURRENT] of each channel slot
+  uint16_t tags;                       // instance tags seen on the first frame
+  uint8_t tags_valid;
+  uint8_t pad[5];
+};
+
+struct RunDev {
+  int32_t stream_slot;
+  uint32_t first;      // index into run_frames
+  uint32_t count;
+  uint8_t layout;
+  uint8_t sf_index;
+  uint8_t mono_dup;    // duplicate the single channel (SyntacticElements.java:244-245)
+  uint8_t pad;
+};
+
+// Huffman LUT entry (uint32):
+//   leaf: [4:0] code length, [7:5] number of sign bits that follow, [8]=0, [31:16] payload
+//         payload quads: 4 x 4-bit two's complement; pairs: 2 x 8-bit two's complement; sf book: value
+//   link: [4:0] extra index bits, [8]=1, [31:16] sub-table offset (entries, from the LUT base)
+constexpr int kHuffFirstBits = 8;
+constexpr int kHuffSfFirstBits = 9;
+
+struct TablesDev {
+  const uint32_t* huff_lut;      // all books
+  uint32_t huff_lut_entries;
+  uint32_t book_base[12];        // [0] = scalefactor book, [1..11] spectral
+  const float* iq;               // [8191]
+  const float* sf;               // [428]
+  const int16_t* swb_long;       // [12][53]
+  const int16_t* swb_short;      // [12][17]
+  const uint8_t* swb_long_count; // [12]
+  const uint8_t* swb_short_count;
+  const uint8_t* sfb_of_long;    // [12][1024] coefficient -> sfb
+  const uint8_t* sfb_of_short;   // [12][128]
+  const float* mdct_long;        // [512][2]
+  const float* mdct_short;       // [64][2]
+  const float* fft512;           // [512][3]
+  const float* fft64;            // [64][2]
+  const float* win_long[2];      // sine, kbd [1024]
+  const float* win_short[2];     // [128]
+};
+
+}  // namespace jaadb

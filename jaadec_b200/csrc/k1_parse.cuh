@@ -1,0 +1,473 @@
+// K1 -- noiseless decode.  One thread parses one AAC frame (raw_data_block):
+// element loop, ics_info, section data, scalefactors, pulse/TNS side info and the
+// spectral Huffman codewords, with the codebook LUTs staged in shared memory.
+// 32 frames advance per warp; frames are independent at this stage (the only
+// cross-frame state of AAC-LC -- window_shape[PREVIOUS] and the IMDCT overlap --
+// is resolved in K2), so a batch of T frames of one stream parses in parallel.
+//
+// Output per channel-frame: quantised coefficients q[1024] (int16, windows
+// de-interleaved like ICStream.decodeSpectralData) and an IcsSide record.
+// Reference behaviour followed (paths relative to aac/src/main/java/net/sourceforge/jaad/aac/):
+//   syntax/SyntacticElements.java:57-203   element loop, FIL, DSE
+//   syntax/CPE.java:85-123                 common_window, ms_mask
+//   syntax/ICSInfo.java:86-119,193-211     ics_info
+//   syntax/ICStream.java:60-275            section / scalefactor / pulse / spectral data
+//   huffman/Huffman.java:15-84             codeword, sign bits, escape
+//   tools/TNS.java:35-61                   TNS side info (parsed, not applied)
+#pragma once
+#include "jaadb_types.cuh"
+
+namespace jaadb {
+
+#define JAADB_ST_OK 0
+#define JAADB_ST_EOS 1
+#define JAADB_ST_INVALID_CODEBOOK 2
+#define JAADB_ST_TOO_MANY_BANDS 3
+#define JAADB_ST_SF_RANGE 4
+#define JAADB_ST_PULSE_SHORT 5
+#define JAADB_ST_PULSE_RANGE 6
+#define JAADB_ST_MS_RESERVED 7
+#define JAADB_ST_TNS_ORDER 8
+#define JAADB_ST_LTP_PROFILE 9
+#define JAADB_ST_UNSUPPORTED_ELEMENT 10
+#define JAADB_ST_LAYOUT 11
+#define JAADB_ST_PROFILE 12
+#define JAADB_ST_ARRAY_BOUNDS 13
+
+// MSB-first bit reader over 32-bit words of the blob (ByteArrayBitStream.java semantics:
+// a read that would pass the end of the frame is an EOSException; here the reader runs on
+// and the caller tests overrun() at element/error boundaries, which yields the same status).
+struct BitReader {
+  const uint32_t* __restrict__ words;  // 4-byte aligned, <= frame start
+  uint32_t pos;                        // bit position relative to words
+  uint32_t end;                        // first bit after the frame
+  uint32_t last_word;                  // index of the last word that holds frame bits
+  uint32_t widx;
+  uint32_t w0, w1;
+
+  __device__ __forceinline__ uint32_t load(uint32_t i) const {
+    uint32_t v = (i <= last_word) ? __ldg(words + i) : 0u;
+    return __byte_perm(v, 0, 0x0123);
+  }
+  __device__ __forceinline__ void init(const uint8_t* blob, uint64_t off, uint32_t nbytes) {
+    uint64_t addr = reinterpret_cast<uint64_t>(blob) + off;
+    uint32_t mis = (uint32_t)(addr & 3u);
+    words = reinterpret_cast<const uint32_t*>(addr - mis);
+    pos = mis * 8u;
+    end = pos + nbytes * 8u;
+    last_word = (end - 1u) >> 5;
+    widx = pos >> 5;
+    w0 = load(widx);
+    w1 = load(widx + 1);
+  }
+  // the next 32 bits, left aligned
+  __device__ __forceinline__ uint32_t peek() {
+    uint32_t wi = pos >> 5;
+    if (wi != widx) {
+      w0 = (wi == widx + 1) ? w1 : load(wi);
+      w1 = load(wi + 1);
+      widx = wi;
+    }
+    return __funnelshift_l(w1, w0, pos & 31u);
+  }
+  __device__ __forceinline__ uint32_t read(int n) {  // 1 <= n <= 32
+    uint32_t v = peek() >> (32 - n);
+    pos += n;
+    return v;
+  }
+  __device__ __forceinline__ uint32_t read1() { return read(1); }
+  __device__ __forceinline__ void skip(uint32_t n) { pos += n; }
+  __device__ __forceinline__ bool overrun() const { return pos > end; }
+  __device__ __forceinline__ uint32_t bits_left() const { return end > pos ? end - pos : 0u; }
+};
+
+__device__ __forceinline__ uint32_t huff_lookup(const uint32_t* lut, uint32_t base, int first_bits, uint32_t w) {
+  uint32_t e = lut[base + (w >> (32 - first_bits))];
+  if (e & 0x100u) {
+    uint32_t x = e & 31u;
+    e = lut[(e >> 16) + ((w << first_bits) >> (32 - x))];
+  }
+  return e;
+}
+
+struct IcsInfoRegs {
+  int ws, shape, max_sfb, ngroups;
+  uint32_t glen_packed;  // 8 x 4 bits
+  __device__ __forceinline__ int glen(int g) const { return (glen_packed >> (4 * g)) & 15; }
+};
+
+// ICSInfo.decode (ICSInfo.java:86-119).  Returns a status.
+__device__ __forceinline__ int parse_ics_info(BitReader& br, IcsInfoRegs& in) {
+  br.skip(1);
+  in.ws = (int)br.read(2);
+  in.shape = (int)br.read(1);
+  in.ngroups = 1;
+  in.glen_packed = 1u;
+  if (in.ws == 2) {
+    in.max_sfb = (int)br.read(4);
+    uint32_t grouping = br.read(7);
+    int g = 0;
+    for (int i = 6; i >= 0; --i) {
+      if ((grouping >> i) & 1u) in.glen_packed += 1u << (4 * g);
+      else { ++g; in.glen_packed |= 1u << (4 * g); }
+    }
+    in.ngroups = g + 1;
+  } else {
+    in.max_sfb = (int)br.read(6);
+    if (br.read1()) return JAADB_ST_LTP_PROFILE;  // predictor_data_present on an LC stream (ICSInfo.java:121-141)
+  }
+  return JAADB_ST_OK;
+}
+
+__device__ __forceinline__ void store_ics_header(IcsSide* s, const IcsInfoRegs& in, int present, int info_decoded,
+                                                 int ms_mask, int common) {
+  uint32_t h0 = (uint32_t)present | ((uint32_t)info_decoded << 8) | ((uint32_t)in.ws << 16) | ((uint32_t)in.shape << 24);
+  uint32_t h1 = (uint32_t)in.max_sfb | ((uint32_t)in.ngroups << 8) | ((uint32_t)ms_mask << 16) | ((uint32_t)common << 24);
+  uint32_t g0 = 0, g1 = 0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    g0 |= (uint32_t)in.glen(g) << (8 * g);
+    g1 |= (uint32_t)in.glen(g + 4) << (8 * g);
+  }
+  *reinterpret_cast<uint4*>(s) = make_uint4(h0, h1, g0, g1);
+}
+
+// individual_channel_stream (ICStream.decode, ICStream.java:60-111).
+// `in` holds the shared ics_info when common_window is set.
+__device__ int parse_ics(BitReader& br, const uint32_t* __restrict__ lut, const TablesDev& T, int sf_index,
+                         bool common, IcsInfoRegs& in, IcsSide* side, int16_t* __restrict__ q, int ms_mask) {
+  uint8_t cb[kMaxSfbEntries];
+  const int global_gain = (int)br.read(8);
+  if (!common) {
+    int st = parse_ics_info(br, in);
+    // window_shape bookkeeping happens before predictor data is looked at (ICSInfo.java:90-91)
+    store_ics_header(side, in, 0, 1, 0, 0);
+    if (st) return st;
+  }
+  const bool is_short = in.ws == 2;
+  const int max_sfb = in.max_sfb;
+  const int ngroups = in.ngroups;
+
+  // ---- section_data (ICStream.java:113-146)
+  {
+    const int bits = is_short ? 3 : 5;
+    const uint32_t esc = (1u << bits) - 1u;
+    int idx = 0;
+    for (int g = 0; g < ngroups; ++g) {
+      for (int k = 0; k < max_sfb;) {
+        int end = k;
+        uint32_t c = br.read(4);
+        if (c == 12) return JAADB_ST_INVALID_CODEBOOK;
+        uint32_t incr;
+        do {
+          incr = br.read(bits);
+          end += (int)incr;
+          if (br.overrun()) return JAADB_ST_EOS;
+        } while (incr == esc);
+        if (end > max_sfb) return JAADB_ST_TOO_MANY_BANDS;
+        for (; k < end; ++k, ++idx) cb[idx] = (uint8_t)c;
+      }
+    }
+  }
+  const int nbands = ngroups * max_sfb;
+
+  // ---- scale_factor_data (ICStream.java:172-220)
+  {
+    int off0 = global_gain, off1 = global_gain - 90, off2 = 0;
+    bool noise_flag = true;
+    const uint32_t sfbase = T.book_base[0];
+    uint16_t* sfo = side->sf_idx;
+    for (int idx = 0; idx < nbands; ++idx) {
+      const int c = cb[idx];
+      uint32_t out;
+      if (c == 0) {
+        out = 0xFFFFu;
+      } else if (c == 13 && noise_flag) {
+        off1 += (int)br.read(9) - 256;
+        noise_flag = false;
+        int t = min(max(off1, -100), 155);
+        out = (uint32_t)(t + 200) | 0x4000u;
+      } else {
+        uint32_t w = br.peek();
+        uint32_t e = huff_lookup(lut, sfbase, kHuffSfFirstBits, w);
+        br.skip(e & 31u);
+        int delta = (int)(e >> 16) - 60;
+        if (c >= 14) {
+          off2 += delta;
+          int t = min(max(off2, -155), 100);
+          out = (uint32_t)(200 - t);
+        } else if (c == 13) {
+          off1 += delta;
+          int t = min(max(off1, -100), 155);
+          out = (uint32_t)(t + 200) | 0x4000u;
+        } else {
+          off0 += delta;
+          if (off0 > 255) return JAADB_ST_SF_RANGE;
+          if (off0 + 100 < 0) return JAADB_ST_ARRAY_BOUNDS;
+          out = (uint32_t)(off0 + 100);
+        }
+      }
+      sfo[idx] = (uint16_t)out;
+    }
+  }
+
+  // ---- pulse_data (ICStream.java:76-83,148-170): parsed, never applied by JAAD
+  if (br.read1()) {
+    if (is_short) return JAADB_ST_PULSE_SHORT;
+    int count = (int)br.read(2) + 1;
+    int start = (int)br.read(6);
+    int swb_count = T.swb_long_count[sf_index];
+    if (start >= swb_count) return JAADB_ST_PULSE_RANGE;
+    int off = T.swb_long[sf_index * 53 + start];
+    off += (int)br.read(5);
+    br.skip(4);
+    for (int i = 1; i < count; ++i) {
+      off += (int)br.read(5);
+      if (off > 1023) return JAADB_ST_PULSE_RANGE;
+      br.skip(4);
+    }
+  }
+
+  // ---- tns_data (TNS.java:35-61): parsed, never applied by JAAD
+  const uint32_t tns_present = br.read1();
+  if (tns_present) {
+    const int nwin = is_short ? 8 : 1;
+    const int b0 = is_short ? 1 : 2, b1 = is_short ? 4 : 6, b2 = is_short ? 3 : 5;
+    for (int w = 0; w < nwin; ++w) {
+      int nfilt = (int)br.read(b0);
+      if (nfilt) {
+        int coef_res = (int)br.read1();
+        for (int f = 0; f < nfilt; ++f) {
+          br.skip(b1);
+          int order = (int)br.read(b2);
+          if (order > 20) return JAADB_ST_TNS_ORDER;
+          if (order) {
+            br.skip(1);
+            int compress = (int)br.read1();
+            br.skip((uint32_t)(order * (coef_res + 3 - compress)));
+          }
+        }
+      }
+      if (br.overrun()) return JAADB_ST_EOS;
+    }
+  }
+  side->tns_present = (uint8_t)tns_present;
+
+  // ---- gain_control_data: SSR only, outside the engine's scope
+  if (br.read1()) return JAADB_ST_UNSUPPORTED_ELEMENT;
+
+  // section table out (K2 needs it for dequantisation / stereo tools)
+  {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(side->sfb_cb);
+    for (int i = 0; i < (nbands + 3) / 4; ++i) {
+      uint32_t v = (uint32_t)cb[4 * i] | ((uint32_t)cb[4 * i + 1] << 8) | ((uint32_t)cb[4 * i + 2] << 16) |
+                   ((uint32_t)cb[4 * i + 3] << 24);
+      dst[i] = v;
+    }
+  }
+
+  // ---- spectral_data (ICStream.java:222-275, Huffman.java:56-84)
+  {
+    const int16_t* __restrict__ swb = is_short ? (T.swb_short + sf_index * 17) : (T.swb_long + sf_index * 53);
+    const int swb_count = is_short ? T.swb_short_count[sf_index] : T.swb_long_count[sf_index];
+    int group_off = 0, idx = 0;
+    for (int g = 0; g < ngroups; ++g) {
+      const int glen = in.glen(g);
+      for (int sfb = 0; sfb < max_sfb; ++sfb, ++idx) {
+        const int hcb = cb[idx];
+        if (sfb > swb_count) return JAADB_ST_ARRAY_BOUNDS;     // offsets[sfb+1] past the table
+        if (hcb == 0 || hcb >= 14) {
+          if (sfb == swb_count) return JAADB_ST_ARRAY_BOUNDS;  // Arrays.fill with a negative range
+          continue;
+        }
+        if (hcb == 13) return JAADB_ST_UNSUPPORTED_ELEMENT;    // PNS: JAAD's process-wide RNG, see DESIGN.md
+        if (sfb == swb_count) continue;                        // negative width: loop body never runs
+        const int lo = swb[sfb], width = swb[sfb + 1] - lo;
+        const uint32_t base = T.book_base[hcb];
+        const bool quad = hcb < 5;
+        for (int w = 0; w < glen; ++w) {
+          int16_t* __restrict__ dst = q + group_off + w * 128 + lo;
+          if (quad) {
+            for (int k = 0; k < width; k += 4) {
+              uint32_t bits = br.peek();
+              uint32_t e = huff_lookup(lut, base, kHuffFirstBits, bits);
+              uint32_t len = e & 31u, ns = (e >> 5) & 7u, pay = e >> 16;
+              int v0 = ((int)(pay << 28)) >> 28, v1 = ((int)(pay << 24)) >> 28;
+              int v2 = ((int)(pay << 20)) >> 28, v3 = ((int)(pay << 16)) >> 28;
+              if (ns) {
+                uint32_t sb = (bits << len) >> (32 - ns);
+                int i = (int)ns;
+                if (v0) { --i; if ((sb >> i) & 1u) v0 = -v0; }
+                if (v1) { --i; if ((sb >> i) & 1u) v1 = -v1; }
+                if (v2) { --i; if ((sb >> i) & 1u) v2 = -v2; }
+                if (v3) { --i; if ((sb >> i) & 1u) v3 = -v3; }
+              }
+              br.skip(len + ns);
+              uint2 o;
+              o.x = ((uint32_t)v0 & 0xFFFFu) | ((uint32_t)v1 << 16);
+              o.y = ((uint32_t)v2 & 0xFFFFu) | ((uint32_t)v3 << 16);
+              *reinterpret_cast<uint2*>(dst + k) = o;
+            }
+          } else {
+            for (int k = 0; k < width; k += 2) {
+              uint32_t bits = br.peek();
+              uint32_t e = huff_lookup(lut, base, kHuffFirstBits, bits);
+              uint32_t len = e & 31u, ns = (e >> 5) & 7u, pay = e >> 16;
+              int v0 = ((int)(pay << 24)) >> 24, v1 = ((int)(pay << 16)) >> 24;
+              if (ns) {
+                uint32_t sb = (bits << len) >> (32 - ns);
+                int i = (int)ns;
+                if (v0) { --i; if ((sb >> i) & 1u) v0 = -v0; }
+                if (v1) { --i; if ((sb >> i) & 1u) v1 = -v1; }
+              }
+              br.skip(len + ns);
+              if (hcb == 11) {
+                // getEscape (Huffman.java:39-49): N ones, a zero, then 4+N bits; value = bits | 1<<(4+N)
+                if (v0 == 16 || v0 == -16) {
+                  uint32_t eb = br.peek();
+                  int n1 = __clz((int)~eb);
+                  if (n1 > 8) { br.skip(n1 + 1 + 4 + n1); return JAADB_ST_ARRAY_BOUNDS; }
+                  int i = 4 + n1;
+                  int mag = (int)((eb << (n1 + 1)) >> (32 - i)) | (1 << i);
+                  br.skip(n1 + 1 + i);
+                  v0 = v0 < 0 ? -mag : mag;
+                }
+                if (v1 == 16 || v1 == -16) {
+                  uint32_t eb = br.peek();
+                  int n1 = __clz((int)~eb);
+                  if (n1 > 8) { br.skip(n1 + 1 + 4 + n1); return JAADB_ST_ARRAY_BOUNDS; }
+                  int i = 4 + n1;
+                  int mag = (int)((eb << (n1 + 1)) >> (32 - i)) | (1 << i);
+                  br.skip(n1 + 1 + i);
+                  v1 = v1 < 0 ? -mag : mag;
+                }
+                if (v0 > 8190 || v0 < -8190 || v1 > 8190 || v1 < -8190) return JAADB_ST_ARRAY_BOUNDS;  // IQ_TABLE has 8191 entries
+              }
+              *reinterpret_cast<uint32_t*>(dst + k) = ((uint32_t)v0 & 0xFFFFu) | ((uint32_t)v1 << 16);
+            }
+          }
+        }
+        if (br.overrun()) return JAADB_ST_EOS;
+      }
+      group_off += glen * 128;
+    }
+  }
+  store_ics_header(side, in, 1, 1, ms_mask, common ? 1 : 0);
+  return JAADB_ST_OK;
+}
+
+__device__ int parse_frame(const uint8_t* __restrict__ blob, const FrameDev& fr, const uint32_t* __restrict__ lut,
+                           const TablesDev& T, const LayoutDev& lay, FrameSide& fs, IcsSide* __restrict__ iside,
+                           int16_t* __restrict__ qbase) {
+  fs.tags = 0;
+  fs.n_elements = 0;
+  fs.sbr_bit_off[0] = fs.sbr_bit_off[1] = 0;
+  fs.sbr_bits[0] = fs.sbr_bits[1] = 0;
+  // every channel slot starts out "absent"
+  for (int c = 0; c < lay.n_channels; ++c) *reinterpret_cast<uint4*>(iside + c) = make_uint4(0, 0, 0, 0);
+  if (fr.nbytes < 4) return JAADB_ST_EOS;  // ADIFHeader.isPresent peeks 32 bits (transport/ADIFHeader.java:18)
+  BitReader br;
+  br.init(blob, fr.blob_off, fr.nbytes);
+  const uint32_t start = br.pos;
+  if (br.peek() == 0x41444946u) return JAADB_ST_UNSUPPORTED_ELEMENT;  // 'ADIF'
+  if (!fr.profile_ok) return JAADB_ST_PROFILE;
+  const int sf_index = fr.sf_index;
+  int el = 0;
+  int status = JAADB_ST_OK;
+  for (;;) {
+    if (br.overrun()) { status = JAADB_ST_EOS; break; }
+    const int type = (int)br.read(3);
+    if (type == EL_END) break;
+    if (type == EL_SCE || type == EL_LFE || type == EL_CPE) {
+      const uint32_t tag = br.read(4);
+      if (el >= lay.n_elements || lay.el_type[el] != type) { status = JAADB_ST_LAYOUT; break; }
+      const int ch0 = lay.el_first_ch[el];
+      fs.tags |= (uint16_t)(tag << (4 * el));
+      IcsInfoRegs in;
+      in.ws = 0; in.shape = 0; in.max_sfb = 0; in.ngroups = 1; in.glen_packed = 1;
+      if (type == EL_CPE) {
+        // CPE.decode (CPE.java:85-123)
+        const bool common = br.read1() != 0;
+        int ms_mask = 0;
+        if (common) {
+          status = parse_ics_info(br, in);
+          store_ics_header(iside + ch0, in, 0, 1, 0, 1);
+          if (status) break;  // thrown inside infoL.decode: R's setCommonData never ran (CPE.java:95-96)
+          store_ics_header(iside + ch0 + 1, in, 0, 1, 0, 1);  // setCommonData updates R's window shape too
+          ms_mask = (int)br.read(2);
+          uint32_t* ms = reinterpret_cast<uint32_t*>((iside + ch0)->ms_used);
+          if (ms_mask == 1) {
+            int n = in.ngroups * in.max_sfb;
+            for (int i = 0; i < 4; ++i) {
+              int take = min(32, n - 32 * i);
+              uint32_t v = 0;
+              if (take > 0) v = __brev(br.read(take) << (32 - take));
+              ms[i] = v;
+            }
+          } else if (ms_mask == 2) {
+            ms[0] = ms[1] = ms[2] = ms[3] = 0xFFFFFFFFu;
+          } else if (ms_mask == 0) {
+            ms[0] = ms[1] = ms[2] = ms[3] = 0u;
+          } else { status = JAADB_ST_MS_RESERVED; break; }
+        }
+        IcsInfoRegs inR = in;
+        status = parse_ics(br, lut, T, sf_index, common, in, iside + ch0, qbase + ch0 * 1024, ms_mask);
+        if (status) break;
+        status = parse_ics(br, lut, T, sf_index, common, inR, iside + ch0 + 1, qbase + (ch0 + 1) * 1024, ms_mask);
+        if (status) break;
+      } else {
+        status = parse_ics(br, lut, T, sf_index, false, in, iside + ch0, qbase + ch0 * 1024, 0);
+        if (status) break;
+      }
+      ++el;
+    } else if (type == EL_DSE) {
+      // DSE.decode (syntax/DSE.java:54-66)
+      br.skip(4);
+      const bool align = br.read1() != 0;
+      uint32_t count = br.read(8);
+      if (count == 255) count += br.read(8);
+      if (align) br.pos = start + (((br.pos - start) + 7u) & ~7u);
+      br.skip(8 * count);
+    } else if (type == EL_FIL) {
+      // decodeFIL (SyntacticElements.java:169-203)
+      int count = (int)br.read(4);
+      if (count == 15) count += (int)br.read(8) - 1;
+      if (count > 0) {
+        if (br.bits_left() < (uint32_t)(8 * count) || br.overrun()) { br.skip(8 * count); status = JAADB_ST_EOS; break; }
+        const uint32_t ext = br.peek() >> 28;
+        if (ext == 11) { status = JAADB_ST_UNSUPPORTED_ELEMENT; break; }  // dynamic range info
+        if ((ext == 13 || ext == 14) && el > 0 && el <= 2) {
+          fs.sbr_bit_off[el - 1] = br.pos;   // relative to the aligned word base of the frame
+          fs.sbr_bits[el - 1] = 8u * (uint32_t)count;
+        }
+        br.skip(8 * count);
+      }
+    } else {
+      status = JAADB_ST_UNSUPPORTED_ELEMENT;  // CCE / PCE
+      break;
+    }
+  }
+  fs.n_elements = (uint8_t)el;
+  if (br.overrun()) status = JAADB_ST_EOS;
+  if (status == JAADB_ST_OK && el != lay.n_elements) status = JAADB_ST_LAYOUT;
+  return status;
+}
+
+__global__ void __launch_bounds__(128)
+k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ frames, uint32_t n_frames,
+                FrameSide* __restrict__ fside, IcsSide* __restrict__ iside, int16_t* __restrict__ q, TablesDev T,
+                const LayoutDev* __restrict__ layouts) {
+  extern __shared__ uint32_t s_lut[];
+  for (uint32_t i = threadIdx.x; i < T.huff_lut_entries; i += blockDim.x) s_lut[i] = T.huff_lut[i];
+  __syncthreads();
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  const FrameDev fr = frames[f];
+  const LayoutDev lay = layouts[fr.layout];
+  FrameSide fs;
+  fs.pad = 0;
+  fs.status = parse_frame(blob, fr, s_lut, T, lay, fs, iside + fr.ics_base, q + (size_t)fr.ics_base * 1024);
+  fside[f] = fs;
+}
+
+}  // namespace jaadb

@@ -1,0 +1,154 @@
+"""Engine / Batch: thin Python objects over the C ABI (include/jaadb200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FrameDesc, FrameResult, Options, StreamInfo, Timings
+
+PCM_S16LE, PCM_S16BE, PCM_F32_PLANAR = 0, 1, 2
+FLAG_PROFILE, FLAG_DEBUG_TAPS = 1, 2
+
+FRAME_DESC_DTYPE = np.dtype([("offset", "<u8"), ("nbytes", "<u4"), ("stream_id", "<i4")])
+FRAME_RESULT_DTYPE = np.dtype([("status", "<i4"), ("channels", "<u2"), ("sample_length", "<u2"), ("sample_rate", "<u4"),
+                               ("pcm_bytes", "<u4")])
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Engine:
+    def __init__(self, device: int = 0, max_streams: int = 4096, pcm_format: int = PCM_S16LE, flags: int = 0):
+        self._lib = _lib.load()
+        opts = Options(device, max_streams, pcm_format, 0, flags, (C.c_uint32 * 3)(0, 0, 0))
+        h = C.c_void_p()
+        rc = self._lib.jaadb_engine_create(C.byref(opts), C.byref(h))
+        if rc != 0:
+            raise EngineError("jaadb_engine_create failed: %d (no CUDA device? there is no CPU fallback)" % rc)
+        self._h = h
+        self.pcm_format = pcm_format
+        self.flags = flags
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.jaadb_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError("%s failed: %d (%s)" % (what, rc, self._lib.jaadb_last_error(self._h).decode()))
+
+    def open_adts(self, profile: int, sf_index: int, channel_config: int, expect_sbr: int = 0) -> int:
+        sid = C.c_int32(-1)
+        self._check(self._lib.jaadb_stream_open_adts(self._h, profile, sf_index, channel_config, expect_sbr, C.byref(sid)), "stream_open_adts")
+        return sid.value
+
+    def open_asc(self, asc: bytes) -> int:
+        sid = C.c_int32(-1)
+        buf = np.frombuffer(bytes(asc), np.uint8).copy()
+        self._check(self._lib.jaadb_stream_open_asc(self._h, buf.ctypes.data, len(buf), C.byref(sid)), "stream_open_asc")
+        return sid.value
+
+    def close_stream(self, sid: int):
+        self._check(self._lib.jaadb_stream_close(self._h, sid), "stream_close")
+
+    def stream_info(self, sid: int) -> StreamInfo:
+        info = StreamInfo()
+        self._check(self._lib.jaadb_stream_get_info(self._h, sid, C.byref(info)), "stream_get_info")
+        return info
+
+    def decode(self, blob: np.ndarray, frames: np.ndarray, pcm_out: np.ndarray | None = None, pcm_offsets: np.ndarray | None = None):
+        """One-call decode with host buffers. Returns (pcm uint8 array, results structured array)."""
+        blob = np.ascontiguousarray(blob, np.uint8)
+        frames = np.ascontiguousarray(frames, FRAME_DESC_DTYPE)
+        results = np.zeros(len(frames), FRAME_RESULT_DTYPE)
+        if pcm_out is None:
+            need = self._packed_bytes(frames) if pcm_offsets is None else int(pcm_offsets.max(initial=0)) + 8 * 2048 * 4
+            pcm_out = np.zeros(need, np.uint8)
+        if pcm_offsets is not None:
+            pcm_offsets = np.ascontiguousarray(pcm_offsets, np.uint64)
+        self._check(self._lib.jaadb_decode(self._h, _ptr(blob), blob.nbytes, _ptr(frames), len(frames), _ptr(pcm_out),
+                                           pcm_out.nbytes, _ptr(pcm_offsets), _ptr(results)), "decode")
+        return pcm_out, results
+
+    def _packed_bytes(self, frames) -> int:
+        per = 4 if self.pcm_format == PCM_F32_PLANAR else 2
+        total = 0
+        ids, counts = np.unique(frames["stream_id"], return_counts=True)
+        for sid, n in zip(ids, counts):
+            i = self.stream_info(int(sid))
+            total += int(n) * i.channels * i.sample_length * per
+        return total
+
+    def batch(self, frames: np.ndarray, blob_bytes: int, pcm_offsets: np.ndarray | None = None) -> "Batch":
+        return Batch(self, frames, blob_bytes, pcm_offsets)
+
+
+class Batch:
+    """Staged decode: create -> upload -> decode (device resident) -> download."""
+
+    def __init__(self, engine: Engine, frames: np.ndarray, blob_bytes: int, pcm_offsets=None):
+        self.engine = engine
+        self._lib = engine._lib
+        self.frames = np.ascontiguousarray(frames, FRAME_DESC_DTYPE)
+        if pcm_offsets is not None:
+            pcm_offsets = np.ascontiguousarray(pcm_offsets, np.uint64)
+        h = C.c_void_p()
+        engine._check(self._lib.jaadb_batch_create(engine._h, _ptr(self.frames), len(self.frames), blob_bytes, _ptr(pcm_offsets), C.byref(h)), "batch_create")
+        self._h = h
+        self.pcm_bytes = int(self._lib.jaadb_batch_pcm_bytes(h))
+
+    def upload(self, blob: np.ndarray):
+        self.engine._check(self._lib.jaadb_batch_upload(self._h, blob.ctypes.data, blob.nbytes), "batch_upload")
+
+    def decode(self):
+        self.engine._check(self._lib.jaadb_batch_decode(self._h), "batch_decode")
+
+    def sync(self):
+        self.engine._check(self._lib.jaadb_batch_sync(self._h), "batch_sync")
+
+    def download(self, pcm_out: np.ndarray | None = None, want_results: bool = True):
+        if pcm_out is None:
+            pcm_out = np.zeros(self.pcm_bytes, np.uint8)
+        results = np.zeros(len(self.frames), FRAME_RESULT_DTYPE) if want_results else None
+        self.engine._check(self._lib.jaadb_batch_download(self._h, _ptr(pcm_out), pcm_out.nbytes, _ptr(results)), "batch_download")
+        return pcm_out, results
+
+    def timings(self) -> Timings:
+        t = Timings()
+        self.engine._check(self._lib.jaadb_batch_timings(self._h, C.byref(t)), "batch_timings")
+        return t
+
+    def tap(self, frame: int, ch: int, want_spec: bool = True):
+        q = np.zeros(1024, np.int16)
+        sf = np.zeros(120, np.int16)
+        cb = np.zeros(120, np.uint8)
+        spec = np.zeros(1024, np.float32) if want_spec else None
+        info = np.zeros(16, np.int32)
+        ms = np.zeros(128, np.uint8)
+        self.engine._check(self._lib.jaadb_batch_tap(self._h, frame, ch, _ptr(q), _ptr(sf), _ptr(cb), _ptr(spec), _ptr(info), _ptr(ms)), "batch_tap")
+        return dict(q=q, sfidx=sf, sfbcb=cb, spec=spec, info=info, msused=ms)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.jaadb_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,169 @@
+"""GPU parity tests for the AAC-LC path: CUDA engine (through the C ABI) vs the CPU oracle.
+
+Bit-exact everywhere: quantised coefficients, scalefactors, sections, the dequantised
+spectrum after M/S + intensity stereo, float PCM and int16 PCM (BASELINE.json asks for
+bit-exact integers and <= 1e-5 of full scale on float PCM; the engine keeps JAAD's float
+operation graph, so the float stage is bit-exact too and is tested as such).
+"""
+import numpy as np
+import pytest
+
+import gen
+from helpers import Workload, same_float_bits
+from jaadec_b200 import Engine, FLAG_DEBUG_TAPS, PCM_F32_PLANAR, PCM_S16BE, PCM_S16LE
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # (label, generator config, streams)
+    ("c1_long_only_44k", gen.config(1, n_frames=24), 3),
+    ("c2_mixed_48k", gen.config(2, n_frames=40, p_transient=0.3), 6),
+    ("c2_no_common", gen.config(2, n_frames=16, p_common_window=0.0, p_transient=0.3), 2),
+    ("mono_24k", gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=20, target_bytes=171, p_transient=0.3), 3),
+    ("c5_51_48k", gen.config(5, n_frames=16, adts=True, p_transient=0.3), 3),
+    ("sf_8k", gen.GenConfig(sf_index=11, chan_cfg=2, n_frames=12, target_bytes=300, p_transient=0.3), 2),
+    ("sf_96k", gen.GenConfig(sf_index=0, chan_cfg=2, n_frames=12, target_bytes=400, p_transient=0.3), 2),
+]
+
+
+def run_oracle(wl):
+    decs = wl.oracle_decoders()
+    out = {}
+    for f in range(wl.cfg.n_frames):
+        for s in range(wl.n_streams):
+            r = decs[s].decode_frame(wl.frame_bytes(s, f))
+            taps = []
+            if r["status"] == 0:
+                el = 0
+                while True:
+                    t = decs[s].tap_ics(el, 0)
+                    if t is None:
+                        break
+                    taps.append(t)
+                    t2 = decs[s].tap_ics(el, 1)
+                    if t2 is not None:
+                        taps.append(t2)
+                    el += 1
+            r["taps"] = taps
+            out[(s, f)] = r
+    return out
+
+
+@pytest.mark.parametrize("label,cfg,n_streams", CASES, ids=[c[0] for c in CASES])
+def test_lc_bit_exact(label, cfg, n_streams):
+    wl = Workload(cfg, n_streams, base_seed=gen.seed_for(2, 100))
+    ref = run_oracle(wl)
+    eng = Engine(max_streams=64, pcm_format=PCM_F32_PLANAR, flags=FLAG_DEBUG_TAPS)
+    ids = [eng.open_adts(*wl.hdr) for _ in range(n_streams)]
+    frames, index = wl.frame_table(ids)
+    b = eng.batch(frames, wl.blob.nbytes)
+    b.upload(wl.blob)
+    b.decode()
+    pcm, res = b.download()
+    info0 = eng.stream_info(ids[0])
+    ch, ln = info0.channels, info0.sample_length
+    per = ch * ln * 4
+    n_checked = 0
+    for i, (s, f) in enumerate(index):
+        r = ref[(s, f)]
+        assert res["status"][i] == r["status"], (label, s, f)
+        assert r["status"] == 0
+        assert (res["channels"][i], res["sample_length"][i], res["sample_rate"][i]) == (r["channels"], r["sample_length"], r["sample_rate"])
+        # integer stage + dequantised spectrum vs oracle AND vs the generator's own ground truth
+        truth = wl.streams[s].truth
+        for c, t in enumerate(r["taps"]):
+            g = b.tap(i, c)
+            assert np.array_equal(g["q"], t["q"]), (label, s, f, c, "q")
+            assert np.array_equal(g["q"], truth["q"][f, c]), (label, s, f, c, "q vs generator")
+            assert np.array_equal(g["sfbcb"], t["sfbcb"]), (label, s, f, c, "sfbcb")
+            assert np.array_equal(g["sfidx"], t["sfidx"]), (label, s, f, c, "sfidx")
+            assert np.array_equal(g["sfidx"], truth["sfidx"][f, c]), (label, s, f, c, "sfidx vs generator")
+            assert np.array_equal(g["info"][[1, 2, 4, 5]], t["info"][[1, 2, 4, 5]]), (label, s, f, c, "info")
+            assert np.array_equal(g["info"][6:16], t["info"][6:16]), (label, s, f, c, "groups/ms")
+            assert same_float_bits(g["spec"], t["spec"]), (label, s, f, c, "spectrum")
+        got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(ch, ln)
+        assert same_float_bits(got, r["f32"]), (label, s, f, "float pcm", np.abs(got - r["f32"]).max())
+        n_checked += 1
+    assert n_checked == len(index)
+    b.close()
+    eng.close()
+
+
+@pytest.mark.parametrize("fmt,big", [(PCM_S16LE, False), (PCM_S16BE, True)])
+def test_s16_identical_and_state_carries_across_calls(fmt, big):
+    cfg = gen.config(2, n_frames=30, p_transient=0.3)
+    wl = Workload(cfg, 4, base_seed=777, with_truth=False)
+    decs = wl.oracle_decoders()
+    eng = Engine(max_streams=16, pcm_format=fmt)
+    ids = [eng.open_adts(*wl.hdr) for _ in range(4)]
+    # three calls of uneven size: the overlap / window-shape state must carry over
+    for lo, hi in ((0, 1), (1, 17), (17, 30)):
+        frames, index = wl.frame_table(ids, lo, hi)
+        pcm, res = eng.decode(wl.blob, frames)
+        per = 2 * 1024 * 2
+        for i, (s, f) in enumerate(index):
+            r = decs[s].decode_frame(wl.frame_bytes(s, f), big_endian=big)
+            assert res["status"][i] == 0 and r["status"] == 0
+            assert res["pcm_bytes"][i] == per
+            got = pcm[i * per:(i + 1) * per].view(np.int16).reshape(1024, 2)
+            assert np.array_equal(got, r["s16"]), (s, f)
+    eng.close()
+
+
+def test_bad_frames_do_not_poison_the_batch():
+    cfg = gen.config(2, n_frames=12, p_transient=0.3)
+    wl = Workload(cfg, 3, base_seed=4242, with_truth=False)
+    blob = wl.blob.copy()
+    frames, index = wl.frame_table([0, 1, 2])
+    frames = frames.copy()
+    # stream 1 frame 4: truncated (EOS); stream 2 frame 6: 3 bytes (EOS at the ADIF peek);
+    # stream 0 frame 5: corrupt the first bytes (whatever status the oracle reports)
+    mutate = {}
+    for i, (s, f) in enumerate(index):
+        if (s, f) == (1, 4):
+            frames["nbytes"][i] //= 2
+        if (s, f) == (2, 6):
+            frames["nbytes"][i] = 3
+        if (s, f) == (0, 5):
+            o = int(frames["offset"][i])
+            blob[o:o + 6] = [0x21, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF]
+        mutate[(s, f)] = (int(frames["offset"][i]), int(frames["nbytes"][i]))
+    decs = wl.oracle_decoders()
+    eng = Engine(max_streams=8, pcm_format=PCM_F32_PLANAR)
+    ids = [eng.open_adts(*wl.hdr) for _ in range(3)]
+    assert ids == [0, 1, 2]
+    pcm, res = eng.decode(blob, frames)
+    per = 2 * 1024 * 4
+    statuses = []
+    for i, (s, f) in enumerate(index):
+        o, n = mutate[(s, f)]
+        r = decs[s].decode_frame(blob[o:o + n])
+        statuses.append(r["status"])
+        assert res["status"][i] == r["status"], (s, f, res["status"][i], r["status"])
+        if r["status"] == 0:
+            got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(2, 1024)
+            assert same_float_bits(got, r["f32"]), (s, f)
+        else:
+            assert res["pcm_bytes"][i] == 0
+    assert sum(1 for x in statuses if x != 0) >= 2
+    eng.close()
+
+
+def test_asc_open_5_1_raw_frames():
+    cfg = gen.config(5, n_frames=10, p_transient=0.3)  # raw frames, as MP4 samples
+    asc = bytes([0x11, 0xB0])
+    wl = Workload(cfg, 2, base_seed=31337, with_truth=False, asc=asc)
+    decs = wl.oracle_decoders()
+    eng = Engine(max_streams=4, pcm_format=PCM_S16LE)
+    ids = [eng.open_asc(asc) for _ in range(2)]
+    info = eng.stream_info(ids[0])
+    assert (info.channels, info.sample_rate, info.sample_length) == (6, 48000, 1024)
+    frames, index = wl.frame_table(ids)
+    pcm, res = eng.decode(wl.blob, frames)
+    per = 6 * 1024 * 2
+    for i, (s, f) in enumerate(index):
+        r = decs[s].decode_frame(wl.frame_bytes(s, f))
+        assert res["status"][i] == 0 and r["status"] == 0
+        got = pcm[i * per:(i + 1) * per].view(np.int16).reshape(1024, 6)
+        assert np.array_equal(got, r["s16"]), (s, f)
+    eng.close()
