@@ -326,7 +326,7 @@ uint32_t frame_pcm_bytes(const jaadb_engine* e, const StreamHost& s) {
 size_t k2_smem_bytes(int nch, int out_ch) {
   const int per_ch = kSpecStride + 1024 + 2 * kXchgStride;
   size_t b = sizeof(float) * (2 * 256 + 2 * 32 + (size_t)nch * per_ch);
-  b += sizeof(IcsSide) * nch + 8 * kMaxChannels;
+  b += sizeof(IcsSide) * nch + 4 * 8 * kMaxChannels;
   b += sizeof(int16_t) * 1024 * out_ch;
   return (b + 15) & ~size_t(15);
 }
@@ -783,15 +783,18 @@ int jaadb_batch_tap(jaadb_batch* b, uint32_t frame, uint32_t ch, int16_t* q, int
     const bool sh = side.window_sequence == 2;
     const int16_t* swb = sh ? T::SWB_OFFSET_SHORT + 17 * s.sf_index : T::SWB_OFFSET_LONG + 53 * s.sf_index;
     const int swbc = sh ? T::SWB_SHORT_WINDOW_COUNT[s.sf_index] : T::SWB_LONG_WINDOW_COUNT[s.sf_index];
+    // K1 leaves q in bitstream order (group base = 128 * first window; band at glen * swb[sfb]; window-major inside)
     int goff = 0, idx = 0;
     for (int g = 0; g < side.num_groups; ++g) {
+      const int glen = side.group_len[g];
       for (int sfb = 0; sfb < side.max_sfb; ++sfb, ++idx) {
         int cb = side.sfb_cb[idx];
         if (cb < 1 || cb > 11 || sfb >= swbc) continue;
-        for (int w = 0; w < side.group_len[g]; ++w)
-          for (int k = swb[sfb]; k < swb[sfb + 1]; ++k) q[goff + w * 128 + k] = raw[goff + w * 128 + k];
+        const int lo = swb[sfb], width = swb[sfb + 1] - lo;
+        for (int w = 0; w < glen; ++w)
+          for (int k = 0; k < width; ++k) q[goff + w * 128 + lo + k] = raw[goff + glen * lo + w * width + k];
       }
-      goff += side.group_len[g] * 128;
+      goff += glen * 128;
     }
   }
   if (spec) {

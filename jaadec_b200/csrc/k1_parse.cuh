@@ -132,342 +132,431 @@ __device__ __forceinline__ void store_ics_header(IcsSide* s, const IcsInfoRegs& 
   *reinterpret_cast<uint4*>(s) = make_uint4(h0, h1, g0, g1);
 }
 
-// individual_channel_stream (ICStream.decode, ICStream.java:60-111).
-// `in` holds the shared ics_info when common_window is set.
-__device__ int parse_ics(BitReader& br, const uint32_t* __restrict__ lut, const TablesDev& T, int sf_index,
-                         bool common, IcsInfoRegs& in, IcsSide* side, int16_t* __restrict__ q, int ms_mask) {
-  uint8_t cb[kMaxSfbEntries];
-  const int global_gain = (int)br.read(8);
-  if (!common) {
-    int st = parse_ics_info(br, in);
-    // window_shape bookkeeping happens before predictor data is looked at (ICSInfo.java:90-91)
-    store_ics_header(side, in, 0, 1, 0, 0);
-    if (st) return st;
+// ---------------------------------------------------------------------------------------------------------
+// Warp-convergent frame parser.
+//
+// One thread owns one frame, but the 32 frames of a warp advance through the SAME instruction stream: every
+// loop below runs until a warp vote says no lane needs another iteration, and a lane that has nothing to do in
+// an iteration idles under a predicate.  There is no early return anywhere -- a lane that hits an error (or has
+// no frame at all) records its status, goes inactive and keeps voting -- so the warp never splits into
+// independently scheduled fragments.  The spectral loop, where ~90 % of the work is, executes one Huffman
+// codeword per lane per iteration regardless of window sequence, group, band or codebook.
+//
+// q is written in BITSTREAM order: group g starts at 128 * (first window of g); inside the group, scalefactor
+// band sfb starts at glen * swb[sfb] and holds glen windows x width coefficients, window-major
+// (ICStream.java:258-271 walks the data in exactly this order).  K2 undoes the interleave when it dequantises.
+// Bands with codebook 0 / 13 / 14 / 15 are not written and never read.
+// ---------------------------------------------------------------------------------------------------------
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+__device__ __forceinline__ void fail(int& status, bool& flag, int code) { status = code; flag = false; }
+
+// individual_channel_stream (ICStream.decode, ICStream.java:60-111) for the lanes with go == true.
+// `in` holds the shared ics_info when common_window is set.  Returns with status updated.
+__device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& status, const uint32_t* __restrict__ lut,
+                                               const TablesDev& T, int sf_index, bool common, IcsInfoRegs& in,
+                                               IcsSide* side, int16_t* __restrict__ q, int ms_mask) {
+  uint8_t cb[kMaxSfbEntries + 8];
+  int global_gain = 0;
+  if (go) {
+    global_gain = (int)br.read(8);
+    if (!common) {
+      int st = parse_ics_info(br, in);
+      // window_shape bookkeeping happens before predictor data is looked at (ICSInfo.java:90-91)
+      store_ics_header(side, in, 0, 1, 0, 0);
+      if (st) fail(status, go, st);
+    }
   }
+  __syncwarp();
   const bool is_short = in.ws == 2;
   const int max_sfb = in.max_sfb;
   const int ngroups = in.ngroups;
+  const int nbands = go ? ngroups * max_sfb : 0;
 
-  // ---- section_data (ICStream.java:113-146)
+  // ---- section_data (ICStream.java:113-146), one section per iteration
   {
     const int bits = is_short ? 3 : 5;
     const uint32_t esc = (1u << bits) - 1u;
-    int idx = 0;
-    for (int g = 0; g < ngroups; ++g) {
-      for (int k = 0; k < max_sfb;) {
-        int end = k;
-        uint32_t c = br.read(4);
-        if (c == 12) return JAADB_ST_INVALID_CODEBOOK;
-        uint32_t incr;
-        do {
-          incr = br.read(bits);
-          end += (int)incr;
-          if (br.overrun()) return JAADB_ST_EOS;
-        } while (incr == esc);
-        if (end > max_sfb) return JAADB_ST_TOO_MANY_BANDS;
-        for (; k < end; ++k, ++idx) cb[idx] = (uint8_t)c;
+    int g = 0, k = 0;
+    bool sec = go && max_sfb > 0;
+    while (__any_sync(kFullMask, sec)) {
+      if (sec) {
+        const uint32_t c = br.read(4);
+        if (c == 12) fail(status, sec, JAADB_ST_INVALID_CODEBOOK);
+        else {
+          int end = k;
+          uint32_t incr;
+          do {
+            incr = br.read(bits);
+            end += (int)incr;
+          } while (incr == esc && !br.overrun());
+          if (br.overrun()) fail(status, sec, JAADB_ST_EOS);
+          else if (end > max_sfb) fail(status, sec, JAADB_ST_TOO_MANY_BANDS);
+          else {
+            for (int idx = g * max_sfb + k; k < end; ++k, ++idx) cb[idx] = (uint8_t)c;
+            if (k == max_sfb) { k = 0; if (++g == ngroups) sec = false; }
+          }
+        }
       }
     }
+    if (status) go = false;
   }
-  const int nbands = ngroups * max_sfb;
 
-  // ---- scale_factor_data (ICStream.java:172-220)
+  // ---- scale_factor_data (ICStream.java:172-220), one band per iteration
   {
     int off0 = global_gain, off1 = global_gain - 90, off2 = 0;
     bool noise_flag = true;
     const uint32_t sfbase = T.book_base[0];
     uint16_t* sfo = side->sf_idx;
-    for (int idx = 0; idx < nbands; ++idx) {
-      const int c = cb[idx];
-      uint32_t out;
-      if (c == 0) {
-        out = 0xFFFFu;
-      } else if (c == 13 && noise_flag) {
-        off1 += (int)br.read(9) - 256;
-        noise_flag = false;
-        int t = min(max(off1, -100), 155);
-        out = (uint32_t)(t + 200) | 0x4000u;
-      } else {
-        uint32_t w = br.peek();
-        uint32_t e = huff_lookup(lut, sfbase, kHuffSfFirstBits, w);
-        br.skip(e & 31u);
-        int delta = (int)(e >> 16) - 60;
-        if (c >= 14) {
-          off2 += delta;
-          int t = min(max(off2, -155), 100);
-          out = (uint32_t)(200 - t);
-        } else if (c == 13) {
-          off1 += delta;
-          int t = min(max(off1, -100), 155);
-          out = (uint32_t)(t + 200) | 0x4000u;
-        } else {
-          off0 += delta;
-          if (off0 > 255) return JAADB_ST_SF_RANGE;
-          if (off0 + 100 < 0) return JAADB_ST_ARRAY_BOUNDS;
-          out = (uint32_t)(off0 + 100);
+    int idx = 0;
+    bool sfa = go && nbands > 0;
+    while (__any_sync(kFullMask, sfa)) {
+      if (sfa) {
+        const int c = cb[idx];
+        uint32_t out = 0xFFFFu;
+        if (c != 0) {
+          if (c == 13 && noise_flag) {
+            off1 += (int)br.read(9) - 256;
+            noise_flag = false;
+            out = (uint32_t)(min(max(off1, -100), 155) + 200) | 0x4000u;
+          } else {
+            const uint32_t w = br.peek();
+            const uint32_t e = huff_lookup(lut, sfbase, kHuffSfFirstBits, w);
+            br.skip(e & 31u);
+            const int delta = (int)(e >> 16) - 60;
+            if (c >= 14) {
+              off2 += delta;
+              out = (uint32_t)(200 - min(max(off2, -155), 100));
+            } else if (c == 13) {
+              off1 += delta;
+              out = (uint32_t)(min(max(off1, -100), 155) + 200) | 0x4000u;
+            } else {
+              off0 += delta;
+              if (off0 > 255) fail(status, sfa, JAADB_ST_SF_RANGE);
+              else if (off0 + 100 < 0) fail(status, sfa, JAADB_ST_ARRAY_BOUNDS);
+              out = (uint32_t)(off0 + 100);
+            }
+          }
+        }
+        if (sfa) {
+          sfo[idx] = (uint16_t)out;
+          if (++idx == nbands) sfa = false;
         }
       }
-      sfo[idx] = (uint16_t)out;
     }
+    if (status) go = false;
   }
 
-  // ---- pulse_data (ICStream.java:76-83,148-170): parsed, never applied by JAAD
-  if (br.read1()) {
-    if (is_short) return JAADB_ST_PULSE_SHORT;
-    int count = (int)br.read(2) + 1;
-    int start = (int)br.read(6);
-    int swb_count = T.swb_long_count[sf_index];
-    if (start >= swb_count) return JAADB_ST_PULSE_RANGE;
-    int off = T.swb_long[sf_index * 53 + start];
-    off += (int)br.read(5);
-    br.skip(4);
-    for (int i = 1; i < count; ++i) {
-      off += (int)br.read(5);
-      if (off > 1023) return JAADB_ST_PULSE_RANGE;
-      br.skip(4);
-    }
-  }
-
-  // ---- tns_data (TNS.java:35-61): parsed, never applied by JAAD
-  const uint32_t tns_present = br.read1();
-  if (tns_present) {
-    const int nwin = is_short ? 8 : 1;
-    const int b0 = is_short ? 1 : 2, b1 = is_short ? 4 : 6, b2 = is_short ? 3 : 5;
-    for (int w = 0; w < nwin; ++w) {
-      int nfilt = (int)br.read(b0);
-      if (nfilt) {
-        int coef_res = (int)br.read1();
-        for (int f = 0; f < nfilt; ++f) {
-          br.skip(b1);
-          int order = (int)br.read(b2);
-          if (order > 20) return JAADB_ST_TNS_ORDER;
-          if (order) {
-            br.skip(1);
-            int compress = (int)br.read1();
-            br.skip((uint32_t)(order * (coef_res + 3 - compress)));
+  // ---- pulse_data (ICStream.java:76-83,148-170) and tns_data (TNS.java:35-61): parsed, never applied by JAAD;
+  //      gain_control_data: SSR only.  Rare and short: the lanes diverge here and rejoin at the __syncwarp.
+  if (go) {
+    if (br.read1()) {
+      if (is_short) fail(status, go, JAADB_ST_PULSE_SHORT);
+      else {
+        const int count = (int)br.read(2) + 1;
+        const int start = (int)br.read(6);
+        const int swb_count = T.swb_long_count[sf_index];
+        if (start >= swb_count) fail(status, go, JAADB_ST_PULSE_RANGE);
+        else {
+          int off = T.swb_long[sf_index * 53 + start];
+          off += (int)br.read(5);
+          br.skip(4);
+          for (int i = 1; i < count && go; ++i) {
+            off += (int)br.read(5);
+            if (off > 1023) fail(status, go, JAADB_ST_PULSE_RANGE);
+            else br.skip(4);
           }
         }
       }
-      if (br.overrun()) return JAADB_ST_EOS;
     }
   }
-  side->tns_present = (uint8_t)tns_present;
-
-  // ---- gain_control_data: SSR only, outside the engine's scope
-  if (br.read1()) return JAADB_ST_UNSUPPORTED_ELEMENT;
-
+  if (go) {
+    const uint32_t tns_present = br.read1();
+    if (tns_present) {
+      const int nwin = is_short ? 8 : 1;
+      const int b0 = is_short ? 1 : 2, b1 = is_short ? 4 : 6, b2 = is_short ? 3 : 5;
+      for (int w = 0; w < nwin && go; ++w) {
+        const int nfilt = (int)br.read(b0);
+        if (nfilt) {
+          const int coef_res = (int)br.read1();
+          for (int f = 0; f < nfilt && go; ++f) {
+            br.skip(b1);
+            const int order = (int)br.read(b2);
+            if (order > 20) fail(status, go, JAADB_ST_TNS_ORDER);
+            else if (order) {
+              br.skip(1);
+              const int compress = (int)br.read1();
+              br.skip((uint32_t)(order * (coef_res + 3 - compress)));
+            }
+          }
+        }
+        if (go && br.overrun()) fail(status, go, JAADB_ST_EOS);
+      }
+    }
+    if (go) {
+      side->tns_present = (uint8_t)tns_present;
+      if (br.read1()) fail(status, go, JAADB_ST_UNSUPPORTED_ELEMENT);  // gain control: outside the engine's scope
+    }
+  }
   // section table out (K2 needs it for dequantisation / stereo tools)
-  {
+  if (go) {
     uint32_t* dst = reinterpret_cast<uint32_t*>(side->sfb_cb);
-    for (int i = 0; i < (nbands + 3) / 4; ++i) {
-      uint32_t v = (uint32_t)cb[4 * i] | ((uint32_t)cb[4 * i + 1] << 8) | ((uint32_t)cb[4 * i + 2] << 16) |
-                   ((uint32_t)cb[4 * i + 3] << 24);
-      dst[i] = v;
-    }
+    for (int i = 0; i < (nbands + 3) / 4; ++i)
+      dst[i] = (uint32_t)cb[4 * i] | ((uint32_t)cb[4 * i + 1] << 8) | ((uint32_t)cb[4 * i + 2] << 16) | ((uint32_t)cb[4 * i + 3] << 24);
   }
+  __syncwarp();
 
-  // ---- spectral_data (ICStream.java:222-275, Huffman.java:56-84)
+  // ---- spectral_data (ICStream.java:222-275, Huffman.java:56-84): one codeword per lane per iteration
   {
     const int16_t* __restrict__ swb = is_short ? (T.swb_short + sf_index * 17) : (T.swb_long + sf_index * 53);
     const int swb_count = is_short ? T.swb_short_count[sf_index] : T.swb_long_count[sf_index];
-    int group_off = 0, idx = 0;
-    for (int g = 0; g < ngroups; ++g) {
-      const int glen = in.glen(g);
-      for (int sfb = 0; sfb < max_sfb; ++sfb, ++idx) {
-        const int hcb = cb[idx];
-        if (sfb > swb_count) return JAADB_ST_ARRAY_BOUNDS;     // offsets[sfb+1] past the table
-        if (hcb == 0 || hcb >= 14) {
-          if (sfb == swb_count) return JAADB_ST_ARRAY_BOUNDS;  // Arrays.fill with a negative range
-          continue;
-        }
-        if (hcb == 13) return JAADB_ST_UNSUPPORTED_ELEMENT;    // PNS: JAAD's process-wide RNG, see DESIGN.md
-        if (sfb == swb_count) continue;                        // negative width: loop body never runs
-        const int lo = swb[sfb], width = swb[sfb + 1] - lo;
-        const uint32_t base = T.book_base[hcb];
-        const bool quad = hcb < 5;
-        for (int w = 0; w < glen; ++w) {
-          int16_t* __restrict__ dst = q + group_off + w * 128 + lo;
-          if (quad) {
-            for (int k = 0; k < width; k += 4) {
-              uint32_t bits = br.peek();
-              uint32_t e = huff_lookup(lut, base, kHuffFirstBits, bits);
-              uint32_t len = e & 31u, ns = (e >> 5) & 7u, pay = e >> 16;
-              int v0 = ((int)(pay << 28)) >> 28, v1 = ((int)(pay << 24)) >> 28;
-              int v2 = ((int)(pay << 20)) >> 28, v3 = ((int)(pay << 16)) >> 28;
-              if (ns) {
-                uint32_t sb = (bits << len) >> (32 - ns);
-                int i = (int)ns;
-                if (v0) { --i; if ((sb >> i) & 1u) v0 = -v0; }
-                if (v1) { --i; if ((sb >> i) & 1u) v1 = -v1; }
-                if (v2) { --i; if ((sb >> i) & 1u) v2 = -v2; }
-                if (v3) { --i; if ((sb >> i) & 1u) v3 = -v3; }
-              }
-              br.skip(len + ns);
-              uint2 o;
-              o.x = ((uint32_t)v0 & 0xFFFFu) | ((uint32_t)v1 << 16);
-              o.y = ((uint32_t)v2 & 0xFFFFu) | ((uint32_t)v3 << 16);
-              *reinterpret_cast<uint2*>(dst + k) = o;
-            }
-          } else {
-            for (int k = 0; k < width; k += 2) {
-              uint32_t bits = br.peek();
-              uint32_t e = huff_lookup(lut, base, kHuffFirstBits, bits);
-              uint32_t len = e & 31u, ns = (e >> 5) & 7u, pay = e >> 16;
-              int v0 = ((int)(pay << 24)) >> 24, v1 = ((int)(pay << 16)) >> 24;
-              if (ns) {
-                uint32_t sb = (bits << len) >> (32 - ns);
-                int i = (int)ns;
-                if (v0) { --i; if ((sb >> i) & 1u) v0 = -v0; }
-                if (v1) { --i; if ((sb >> i) & 1u) v1 = -v1; }
-              }
-              br.skip(len + ns);
-              if (hcb == 11) {
-                // getEscape (Huffman.java:39-49): N ones, a zero, then 4+N bits; value = bits | 1<<(4+N)
-                if (v0 == 16 || v0 == -16) {
-                  uint32_t eb = br.peek();
-                  int n1 = __clz((int)~eb);
-                  if (n1 > 8) { br.skip(n1 + 1 + 4 + n1); return JAADB_ST_ARRAY_BOUNDS; }
-                  int i = 4 + n1;
-                  int mag = (int)((eb << (n1 + 1)) >> (32 - i)) | (1 << i);
-                  br.skip(n1 + 1 + i);
-                  v0 = v0 < 0 ? -mag : mag;
-                }
-                if (v1 == 16 || v1 == -16) {
-                  uint32_t eb = br.peek();
-                  int n1 = __clz((int)~eb);
-                  if (n1 > 8) { br.skip(n1 + 1 + 4 + n1); return JAADB_ST_ARRAY_BOUNDS; }
-                  int i = 4 + n1;
-                  int mag = (int)((eb << (n1 + 1)) >> (32 - i)) | (1 << i);
-                  br.skip(n1 + 1 + i);
-                  v1 = v1 < 0 ? -mag : mag;
-                }
-                if (v0 > 8190 || v0 < -8190 || v1 > 8190 || v1 < -8190) return JAADB_ST_ARRAY_BOUNDS;  // IQ_TABLE has 8191 entries
-              }
-              *reinterpret_cast<uint32_t*>(dst + k) = ((uint32_t)v0 & 0xFFFFu) | ((uint32_t)v1 << 16);
-            }
+    int idx = 0, sfb = 0, g = 0, gbase = 0, glen = in.glen(0);
+    int rem = 0, pos = 0, hcb = 0;
+    uint32_t base = 0;
+    bool sp = go && nbands > 0;
+    while (__any_sync(kFullMask, sp)) {
+      if (sp && rem == 0) {
+        // open the next scalefactor band
+        if (idx == nbands) sp = false;
+        else {
+          hcb = cb[idx];
+          if (sfb > swb_count) fail(status, sp, JAADB_ST_ARRAY_BOUNDS);          // offsets[sfb+1] past the table
+          else if (hcb == 0 || hcb >= 14) {
+            if (sfb == swb_count) fail(status, sp, JAADB_ST_ARRAY_BOUNDS);       // Arrays.fill with a negative range
+          } else if (hcb == 13) fail(status, sp, JAADB_ST_UNSUPPORTED_ELEMENT);  // PNS: JAAD's process-wide RNG, see DESIGN.md
+          else if (sfb < swb_count) {                                            // (== swb_count: negative width, body never runs)
+            const int lo = swb[sfb], width = swb[sfb + 1] - lo;
+            pos = gbase + glen * lo;
+            rem = (glen * width) >> (hcb < 5 ? 2 : 1);
+            base = T.book_base[hcb];
+          }
+          ++idx;
+          if (++sfb == max_sfb) {
+            sfb = 0;
+            gbase += glen << 7;
+            ++g;
+            glen = in.glen(g & 7);
           }
         }
-        if (br.overrun()) return JAADB_ST_EOS;
       }
-      group_off += glen * 128;
-    }
-  }
-  store_ics_header(side, in, 1, 1, ms_mask, common ? 1 : 0);
-  return JAADB_ST_OK;
-}
-
-__device__ int parse_frame(const uint8_t* __restrict__ blob, const FrameDev& fr, const uint32_t* __restrict__ lut,
-                           const TablesDev& T, const LayoutDev& lay, FrameSide& fs, IcsSide* __restrict__ iside,
-                           int16_t* __restrict__ qbase) {
-  fs.tags = 0;
-  fs.n_elements = 0;
-  fs.sbr_bit_off[0] = fs.sbr_bit_off[1] = 0;
-  fs.sbr_bits[0] = fs.sbr_bits[1] = 0;
-  // every channel slot starts out "absent"
-  for (int c = 0; c < lay.n_channels; ++c) *reinterpret_cast<uint4*>(iside + c) = make_uint4(0, 0, 0, 0);
-  if (fr.nbytes < 4) return JAADB_ST_EOS;  // ADIFHeader.isPresent peeks 32 bits (transport/ADIFHeader.java:18)
-  BitReader br;
-  br.init(blob, fr.blob_off, fr.nbytes);
-  const uint32_t start = br.pos;
-  if (br.peek() == 0x41444946u) return JAADB_ST_UNSUPPORTED_ELEMENT;  // 'ADIF'
-  if (!fr.profile_ok) return JAADB_ST_PROFILE;
-  const int sf_index = fr.sf_index;
-  int el = 0;
-  int status = JAADB_ST_OK;
-  for (;;) {
-    if (br.overrun()) { status = JAADB_ST_EOS; break; }
-    const int type = (int)br.read(3);
-    if (type == EL_END) break;
-    if (type == EL_SCE || type == EL_LFE || type == EL_CPE) {
-      const uint32_t tag = br.read(4);
-      if (el >= lay.n_elements || lay.el_type[el] != type) { status = JAADB_ST_LAYOUT; break; }
-      const int ch0 = lay.el_first_ch[el];
-      fs.tags |= (uint16_t)(tag << (4 * el));
-      IcsInfoRegs in;
-      in.ws = 0; in.shape = 0; in.max_sfb = 0; in.ngroups = 1; in.glen_packed = 1;
-      if (type == EL_CPE) {
-        // CPE.decode (CPE.java:85-123)
-        const bool common = br.read1() != 0;
-        int ms_mask = 0;
-        if (common) {
-          status = parse_ics_info(br, in);
-          store_ics_header(iside + ch0, in, 0, 1, 0, 1);
-          if (status) break;  // thrown inside infoL.decode: R's setCommonData never ran (CPE.java:95-96)
-          store_ics_header(iside + ch0 + 1, in, 0, 1, 0, 1);  // setCommonData updates R's window shape too
-          ms_mask = (int)br.read(2);
-          uint32_t* ms = reinterpret_cast<uint32_t*>((iside + ch0)->ms_used);
-          if (ms_mask == 1) {
-            int n = in.ngroups * in.max_sfb;
-            for (int i = 0; i < 4; ++i) {
-              int take = min(32, n - 32 * i);
-              uint32_t v = 0;
-              if (take > 0) v = __brev(br.read(take) << (32 - take));
-              ms[i] = v;
+      if (sp && rem > 0) {
+        const uint32_t bits = br.peek();
+        const uint32_t e = huff_lookup(lut, base, kHuffFirstBits, bits);
+        const uint32_t len = e & 31u, ns = (e >> 5) & 7u, pay = e >> 16;
+        const bool quad = hcb < 5;
+        int v0, v1, v2, v3;
+        if (quad) {
+          v0 = ((int)(pay << 28)) >> 28; v1 = ((int)(pay << 24)) >> 28;
+          v2 = ((int)(pay << 20)) >> 28; v3 = ((int)(pay << 16)) >> 28;
+        } else {
+          v0 = ((int)(pay << 24)) >> 24; v1 = ((int)(pay << 16)) >> 24;
+          v2 = 0; v3 = 0;
+        }
+        if (ns) {
+          const uint32_t sb = (bits << len) >> (32 - ns);
+          int i = (int)ns;
+          if (v0) { --i; if ((sb >> i) & 1u) v0 = -v0; }
+          if (v1) { --i; if ((sb >> i) & 1u) v1 = -v1; }
+          if (v2) { --i; if ((sb >> i) & 1u) v2 = -v2; }
+          if (v3) { --i; if ((sb >> i) & 1u) v3 = -v3; }
+        }
+        br.skip(len + ns);
+        if (hcb == 11) {
+          // getEscape (Huffman.java:39-49): N ones, a zero, then 4+N bits; value = bits | 1<<(4+N)
+          if (v0 == 16 || v0 == -16) {
+            const uint32_t eb = br.peek();
+            const int n1 = __clz((int)~eb);
+            if (n1 > 8) { br.skip(n1 + 1 + 4 + n1); fail(status, sp, JAADB_ST_ARRAY_BOUNDS); }
+            else {
+              const int i = 4 + n1;
+              const int mag = (int)((eb << (n1 + 1)) >> (32 - i)) | (1 << i);
+              br.skip(n1 + 1 + i);
+              v0 = v0 < 0 ? -mag : mag;
             }
-          } else if (ms_mask == 2) {
-            ms[0] = ms[1] = ms[2] = ms[3] = 0xFFFFFFFFu;
-          } else if (ms_mask == 0) {
-            ms[0] = ms[1] = ms[2] = ms[3] = 0u;
-          } else { status = JAADB_ST_MS_RESERVED; break; }
+          }
+          if (sp && (v1 == 16 || v1 == -16)) {
+            const uint32_t eb = br.peek();
+            const int n1 = __clz((int)~eb);
+            if (n1 > 8) { br.skip(n1 + 1 + 4 + n1); fail(status, sp, JAADB_ST_ARRAY_BOUNDS); }
+            else {
+              const int i = 4 + n1;
+              const int mag = (int)((eb << (n1 + 1)) >> (32 - i)) | (1 << i);
+              br.skip(n1 + 1 + i);
+              v1 = v1 < 0 ? -mag : mag;
+            }
+          }
+          if (sp && (v0 > 8190 || v0 < -8190 || v1 > 8190 || v1 < -8190)) fail(status, sp, JAADB_ST_ARRAY_BOUNDS);  // IQ_TABLE has 8191 entries
         }
-        IcsInfoRegs inR = in;
-        status = parse_ics(br, lut, T, sf_index, common, in, iside + ch0, qbase + ch0 * 1024, ms_mask);
-        if (status) break;
-        status = parse_ics(br, lut, T, sf_index, common, inR, iside + ch0 + 1, qbase + (ch0 + 1) * 1024, ms_mask);
-        if (status) break;
-      } else {
-        status = parse_ics(br, lut, T, sf_index, false, in, iside + ch0, qbase + ch0 * 1024, 0);
-        if (status) break;
-      }
-      ++el;
-    } else if (type == EL_DSE) {
-      // DSE.decode (syntax/DSE.java:54-66)
-      br.skip(4);
-      const bool align = br.read1() != 0;
-      uint32_t count = br.read(8);
-      if (count == 255) count += br.read(8);
-      if (align) br.pos = start + (((br.pos - start) + 7u) & ~7u);
-      br.skip(8 * count);
-    } else if (type == EL_FIL) {
-      // decodeFIL (SyntacticElements.java:169-203)
-      int count = (int)br.read(4);
-      if (count == 15) count += (int)br.read(8) - 1;
-      if (count > 0) {
-        if (br.bits_left() < (uint32_t)(8 * count) || br.overrun()) { br.skip(8 * count); status = JAADB_ST_EOS; break; }
-        const uint32_t ext = br.peek() >> 28;
-        if (ext == 11) { status = JAADB_ST_UNSUPPORTED_ELEMENT; break; }  // dynamic range info
-        if ((ext == 13 || ext == 14) && el > 0 && el <= 2) {
-          fs.sbr_bit_off[el - 1] = br.pos;   // relative to the aligned word base of the frame
-          fs.sbr_bits[el - 1] = 8u * (uint32_t)count;
+        if (sp) {
+          const uint32_t lo32 = ((uint32_t)v0 & 0xFFFFu) | ((uint32_t)v1 << 16);
+          if (quad) {
+            *reinterpret_cast<uint2*>(q + pos) = make_uint2(lo32, ((uint32_t)v2 & 0xFFFFu) | ((uint32_t)v3 << 16));
+            pos += 4;
+          } else {
+            *reinterpret_cast<uint32_t*>(q + pos) = lo32;
+            pos += 2;
+          }
+          --rem;
+          // JAAD tests for the end of the frame on every read; here once per band is enough (the reader
+          // returns zeros past the end and any status found there is replaced by EOS below)
+          if (rem == 0 && br.overrun()) fail(status, sp, JAADB_ST_EOS);
         }
-        br.skip(8 * count);
       }
-    } else {
-      status = JAADB_ST_UNSUPPORTED_ELEMENT;  // CCE / PCE
-      break;
     }
+    if (status) go = false;
   }
-  fs.n_elements = (uint8_t)el;
-  if (br.overrun()) status = JAADB_ST_EOS;
-  if (status == JAADB_ST_OK && el != lay.n_elements) status = JAADB_ST_LAYOUT;
-  return status;
+  if (go) store_ics_header(side, in, 1, 1, ms_mask, common ? 1 : 0);
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(128)
 k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ frames, uint32_t n_frames,
-                FrameSide* __restrict__ fside, IcsSide* __restrict__ iside, int16_t* __restrict__ q, TablesDev T,
+                FrameSide* __restrict__ fside, IcsSide* __restrict__ iside_all, int16_t* __restrict__ q_all, TablesDev T,
                 const LayoutDev* __restrict__ layouts) {
   extern __shared__ uint32_t s_lut[];
   for (uint32_t i = threadIdx.x; i < T.huff_lut_entries; i += blockDim.x) s_lut[i] = T.huff_lut[i];
   __syncthreads();
   const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= n_frames) return;
-  const FrameDev fr = frames[f];
+  const bool valid = f < n_frames;
+  FrameDev fr;
+  fr.blob_off = 0; fr.nbytes = 0; fr.stream_slot = 0; fr.ics_base = 0; fr.sf_index = 0; fr.layout = 0; fr.profile_ok = 1; fr.flags = 0;
+  if (valid) fr = frames[f];
   const LayoutDev lay = layouts[fr.layout];
+  IcsSide* const iside = iside_all + fr.ics_base;
+  int16_t* const qbase = q_all + (size_t)fr.ics_base * 1024;
+  const int sf_index = fr.sf_index;
+
   FrameSide fs;
   fs.pad = 0;
-  fs.status = parse_frame(blob, fr, s_lut, T, lay, fs, iside + fr.ics_base, q + (size_t)fr.ics_base * 1024);
-  fside[f] = fs;
+  fs.tags = 0;
+  fs.n_elements = 0;
+  fs.sbr_bit_off[0] = fs.sbr_bit_off[1] = 0;
+  fs.sbr_bits[0] = fs.sbr_bits[1] = 0;
+  int status = JAADB_ST_OK;
+  bool active = valid;
+  BitReader br;
+  br.init(blob, fr.blob_off, valid ? fr.nbytes : 0u);
+  const uint32_t start = br.pos;
+  if (valid) {
+    // every channel slot starts out "absent"
+    for (int c = 0; c < lay.n_channels; ++c) *reinterpret_cast<uint4*>(iside + c) = make_uint4(0, 0, 0, 0);
+    if (fr.nbytes < 4) fail(status, active, JAADB_ST_EOS);  // ADIFHeader.isPresent peeks 32 bits (transport/ADIFHeader.java:18)
+    else if (br.peek() == 0x41444946u) fail(status, active, JAADB_ST_UNSUPPORTED_ELEMENT);  // 'ADIF'
+    else if (!fr.profile_ok) fail(status, active, JAADB_ST_PROFILE);
+  }
+
+  int el = 0;
+  bool pend_r = false;            // the right channel of the current CPE is next
+  int ch0 = 0, ms_mask = 0;
+  bool common = false;
+  IcsInfoRegs in, in_r;
+  in.ws = 0; in.shape = 0; in.max_sfb = 0; in.ngroups = 1; in.glen_packed = 1;
+  in_r = in;
+
+  // one syntactic element (or one channel of a CPE) per iteration
+  while (__any_sync(kFullMask, active)) {
+    bool go = false;   // this lane parses an individual_channel_stream in this iteration
+    int ch = 0;
+    bool is_cpe_left = false;
+    if (active) {
+      if (pend_r) {
+        pend_r = false;
+        go = true;
+        ch = ch0 + 1;
+        in = in_r;
+      } else if (br.overrun()) {
+        fail(status, active, JAADB_ST_EOS);
+      } else {
+        const int type = (int)br.read(3);
+        if (type == EL_END) {
+          active = false;
+        } else if (type == EL_SCE || type == EL_LFE || type == EL_CPE) {
+          const uint32_t tag = br.read(4);
+          if (el >= lay.n_elements || lay.el_type[el] != type) fail(status, active, JAADB_ST_LAYOUT);
+          else {
+            ch0 = lay.el_first_ch[el];
+            ch = ch0;
+            fs.tags |= (uint16_t)(tag << (4 * el));
+            in.ws = 0; in.shape = 0; in.max_sfb = 0; in.ngroups = 1; in.glen_packed = 1;
+            common = false;
+            ms_mask = 0;
+            go = true;
+            if (type == EL_CPE) {
+              // CPE.decode (CPE.java:85-123)
+              is_cpe_left = true;
+              common = br.read1() != 0;
+              if (common) {
+                const int st = parse_ics_info(br, in);
+                store_ics_header(iside + ch0, in, 0, 1, 0, 1);
+                if (st) { fail(status, active, st); go = false; }  // thrown inside infoL.decode: R's setCommonData never ran (CPE.java:95-96)
+                else {
+                  store_ics_header(iside + ch0 + 1, in, 0, 1, 0, 1);  // setCommonData updates R's window shape too
+                  ms_mask = (int)br.read(2);
+                  uint32_t* ms = reinterpret_cast<uint32_t*>((iside + ch0)->ms_used);
+                  if (ms_mask == 1) {
+                    const int n = in.ngroups * in.max_sfb;
+                    for (int i = 0; i < 4; ++i) {
+                      const int take = min(32, n - 32 * i);
+                      uint32_t v = 0;
+                      if (take > 0) v = __brev(br.read(take) << (32 - take));
+                      ms[i] = v;
+                    }
+                  } else if (ms_mask == 2) {
+                    ms[0] = ms[1] = ms[2] = ms[3] = 0xFFFFFFFFu;
+                  } else if (ms_mask == 0) {
+                    ms[0] = ms[1] = ms[2] = ms[3] = 0u;
+                  } else { fail(status, active, JAADB_ST_MS_RESERVED); go = false; }
+                }
+              }
+              in_r = in;
+            }
+          }
+        } else if (type == EL_DSE) {
+          // DSE.decode (syntax/DSE.java:54-66)
+          br.skip(4);
+          const bool align = br.read1() != 0;
+          uint32_t count = br.read(8);
+          if (count == 255) count += br.read(8);
+          if (align) br.pos = start + (((br.pos - start) + 7u) & ~7u);
+          br.skip(8 * count);
+        } else if (type == EL_FIL) {
+          // decodeFIL (SyntacticElements.java:169-203)
+          int count = (int)br.read(4);
+          if (count == 15) count += (int)br.read(8) - 1;
+          if (count > 0) {
+            if (br.bits_left() < (uint32_t)(8 * count) || br.overrun()) { br.skip(8 * count); fail(status, active, JAADB_ST_EOS); }
+            else {
+              const uint32_t ext = br.peek() >> 28;
+              if (ext == 11) fail(status, active, JAADB_ST_UNSUPPORTED_ELEMENT);  // dynamic range info
+              else {
+                if ((ext == 13 || ext == 14) && el > 0 && el <= 2) {
+                  fs.sbr_bit_off[el - 1] = br.pos;   // relative to the aligned word base of the frame
+                  fs.sbr_bits[el - 1] = 8u * (uint32_t)count;
+                }
+                br.skip(8 * count);
+              }
+            }
+          }
+        } else {
+          fail(status, active, JAADB_ST_UNSUPPORTED_ELEMENT);  // CCE / PCE
+        }
+      }
+    }
+    __syncwarp();
+    parse_ics_warp(go, br, status, s_lut, T, sf_index, common, in, iside + ch, qbase + ch * 1024, ms_mask);
+    if (go) {
+      if (status) active = false;
+      else if (is_cpe_left) pend_r = true;
+      else ++el;
+    }
+  }
+  fs.n_elements = (uint8_t)el;
+  if (valid) {
+    if (br.overrun()) status = JAADB_ST_EOS;
+    if (status == JAADB_ST_OK && el != lay.n_elements) status = JAADB_ST_LAYOUT;
+    fs.status = status;
+    fside[f] = fs;
+  }
 }
 
 }  // namespace jaadb

@@ -90,13 +90,19 @@ struct ChanCtx {
   const int16_t* q;         // global
 };
 
-// dequantised value of coefficient i of one channel before the stereo tools; cb_out gets the band's codebook
+// dequantised value of coefficient i (window de-interleaved index, as ICStream.iqData) of one channel before the
+// stereo tools; cb_out gets the band's codebook.  K1 leaves q in bitstream order: group g starts at
+// 128 * first_window(g), band sfb at glen * swb[sfb], glen windows x width coefficients, window-major.
+// win_info[w] = group | first window of the group << 8 | group length << 16.
 __device__ __forceinline__ float dequant_at(const IcsSide* __restrict__ s, const int16_t* __restrict__ q,
-                                            const TablesDev& T, const uint8_t* __restrict__ sfb_of, int i,
-                                            const uint8_t* __restrict__ win_group, int& cb_out, int& idx_out) {
-  int sfb, g;
-  if (s->window_sequence == 2) { sfb = sfb_of[i & 127]; g = win_group[i >> 7]; }
-  else { sfb = sfb_of[i]; g = 0; }
+                                            const TablesDev& T, const uint8_t* __restrict__ sfb_of,
+                                            const int16_t* __restrict__ swb_short, int i,
+                                            const uint32_t* __restrict__ win_info, int& cb_out, int& idx_out) {
+  int sfb, g = 0, qpos = i;
+  const bool sh = s->window_sequence == 2;
+  uint32_t wi = 0;
+  if (sh) { sfb = sfb_of[i & 127]; wi = win_info[i >> 7]; g = (int)(wi & 255u); }
+  else sfb = sfb_of[i];
   cb_out = 0;
   idx_out = 0;
   if (sfb >= s->max_sfb) return 0.f;
@@ -105,7 +111,12 @@ __device__ __forceinline__ float dequant_at(const IcsSide* __restrict__ s, const
   const int cb = s->sfb_cb[idx];
   cb_out = cb;
   if (cb == 0 || cb > 11) return 0.f;
-  const int v = q[i];
+  if (sh) {
+    const int gstart = (int)((wi >> 8) & 255u), glen = (int)(wi >> 16);
+    const int lo = swb_short[sfb], width = swb_short[sfb + 1] - lo;
+    qpos = 128 * gstart + glen * lo + ((i >> 7) - gstart) * width + ((i & 127) - lo);
+  }
+  const int v = q[qpos];
   const float sf = __ldg(T.sf + s->sf_idx[idx]);
   const float m = __ldg(T.iq + (v < 0 ? -v : v));
   // iqData = (v>0) ? IQ[v] : -IQ[-v]; iqData *= scaleFactors[idx]   (ICStream.java:266-267)
@@ -126,7 +137,7 @@ __global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint
   float* s_fft_tw = smem;                         // fft512 re/im (inverse) [256][2] + fft64 [32][2]
   float* s_ch = s_fft_tw + 2 * 256 + 2 * 32;
   IcsSide* s_side = reinterpret_cast<IcsSide*>(s_ch + nch * per_ch);
-  uint8_t* s_wgroup = reinterpret_cast<uint8_t*>(s_side + nch);   // [nch][8]
+  uint32_t* s_wgroup = reinterpret_cast<uint32_t*>(s_side + nch);   // [nch][8] window -> group info
   int16_t* s_pcm = reinterpret_cast<int16_t*>(s_wgroup + 8 * kMaxChannels);  // [1024][out_ch] (s16 formats)
 
   const RunDev run = runs[blockIdx.x];
@@ -187,9 +198,10 @@ __global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint
     if (sd->info_decoded) { shape_prev = shape_cur; shape_cur = sd->window_shape; }
     if (t < 8) {
       // window -> group map for short frames
-      int w = t, g = 0, acc = 0;
-      for (int k = 0; k < 8; ++k) { acc += sd->group_len[k]; if (w >= acc) g = k + 1; }
-      s_wgroup[c * 8 + t] = (uint8_t)min(g, 7);
+      int w = t, g = 0, acc = 0, gstart = 0;
+      for (int k = 0; k < 8; ++k) { acc += sd->group_len[k]; if (w >= acc) { g = k + 1; gstart = acc; } }
+      g = min(g, 7);
+      s_wgroup[c * 8 + t] = (uint32_t)g | ((uint32_t)gstart << 8) | ((uint32_t)sd->group_len[g] << 16);
     }
     __syncthreads();
     if (status != 0) {
@@ -206,11 +218,12 @@ __global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint
       const int16_t* qL = qall + ((size_t)fr.ics_base + el_first) * 1024;
       const IcsSide* sL = s_side + el_first;
       float* specL = s_ch + el_first * per_ch;
+      const int16_t* swb_sh = T.swb_short + sf_index * 17;
       if (el_nch == 1) {
         const uint8_t* sfb_of = (ws == 2) ? T.sfb_of_short + sf_index * 128 : T.sfb_of_long + sf_index * 1024;
         for (int i = et; i < 1024; i += el_threads) {
           int cb, idx;
-          float v = dequant_at(sL, qL, T, sfb_of, i, s_wgroup + el_first * 8, cb, idx);
+          float v = dequant_at(sL, qL, T, sfb_of, swb_sh, i, s_wgroup + el_first * 8, cb, idx);
           specL[spec_addr(i)] = v;
           if (spec_tap) spec_tap[((size_t)fr.ics_base + el_first) * 1024 + i] = v;
         }
@@ -224,8 +237,8 @@ __global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint
         const bool ms_present = sL->ms_mask != 0;                   // CPE.isMSMaskPresent
         for (int i = et; i < 1024; i += el_threads) {
           int cbL, idxL, cbR, idxR;
-          float l = dequant_at(sL, qL, T, sfb_ofL, i, s_wgroup + el_first * 8, cbL, idxL);
-          float r = dequant_at(sR, qR, T, sfb_ofR, i, s_wgroup + (el_first + 1) * 8, cbR, idxR);
+          float l = dequant_at(sL, qL, T, sfb_ofL, swb_sh, i, s_wgroup + el_first * 8, cbL, idxL);
+          float r = dequant_at(sR, qR, T, sfb_ofR, swb_sh, i, s_wgroup + (el_first + 1) * 8, cbR, idxR);
           // MS.process: both codebooks < NOISE_HCB, band flagged (MS.java:28-36)
           if (ms_on && cbL < 13 && cbR < 13) {
             // idxL == idxR here (common window); bands above max_sfb have cb 0 but are never flagged
