@@ -1,0 +1,153 @@
+package net.sourceforge.jaad.b200;
+
+import java.lang.foreign.*;
+import java.lang.invoke.MethodHandle;
+
+import static java.lang.foreign.ValueLayout.*;
+
+/**
+ * Panama FFM (Java 22+, the reference builds at source level 21 with preview or 22) binding of
+ * include/jaadb200.h.  One NativeEngine drives one GPU.  SOURCE ONLY: the build image has no JVM;
+ * tests drive the same C ABI from Python ctypes (jaadec_b200/_lib.py).
+ *
+ * Replaces, for the decode path only, the objects JAAD creates in
+ * net.sourceforge.jaad.aac.Decoder.create(...) (aac/.../Decoder.java:36-54).
+ */
+public final class NativeEngine implements AutoCloseable {
+
+	public static final int PCM_S16LE = 0, PCM_S16BE = 1, PCM_F32_PLANAR = 2;
+
+	/** jaadb_frame_desc { uint64 offset; uint32 nbytes; int32 stream_id; } */
+	public static final StructLayout FRAME_DESC = MemoryLayout.structLayout(
+			JAVA_LONG.withName("offset"), JAVA_INT.withName("nbytes"), JAVA_INT.withName("stream_id"));
+	/** jaadb_frame_result { int32 status; uint16 channels; uint16 sample_length; uint32 sample_rate; uint32 pcm_bytes; } */
+	public static final StructLayout FRAME_RESULT = MemoryLayout.structLayout(
+			JAVA_INT.withName("status"), JAVA_SHORT.withName("channels"), JAVA_SHORT.withName("sample_length"),
+			JAVA_INT.withName("sample_rate"), JAVA_INT.withName("pcm_bytes"));
+	/** jaadb_options { int32 device; uint32 max_streams; int32 pcm_format; int32 tns_mode; uint32 flags; uint32 reserved[3]; } */
+	static final StructLayout OPTIONS = MemoryLayout.structLayout(
+			JAVA_INT.withName("device"), JAVA_INT.withName("max_streams"), JAVA_INT.withName("pcm_format"),
+			JAVA_INT.withName("tns_mode"), JAVA_INT.withName("flags"), MemoryLayout.sequenceLayout(3, JAVA_INT));
+
+	private static final Linker LINKER = Linker.nativeLinker();
+	private static final SymbolLookup LIB = SymbolLookup.libraryLookup(
+			System.getProperty("jaadb200.library", "libjaadb200.so"), Arena.global());
+
+	private static MethodHandle h(String name, FunctionDescriptor fd) {
+		return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), fd);
+	}
+
+	private static final MethodHandle ENGINE_CREATE = h("jaadb_engine_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+	private static final MethodHandle ENGINE_DESTROY = h("jaadb_engine_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+	private static final MethodHandle LAST_ERROR = h("jaadb_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
+	private static final MethodHandle STATUS_STRING = h("jaadb_status_string", FunctionDescriptor.of(ADDRESS, JAVA_INT));
+	private static final MethodHandle OPEN_ASC = h("jaadb_stream_open_asc", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+	private static final MethodHandle OPEN_ADTS = h("jaadb_stream_open_adts", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS));
+	private static final MethodHandle STREAM_CLOSE = h("jaadb_stream_close", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+	private static final MethodHandle DECODE = h("jaadb_decode", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS));
+
+	private final MemorySegment engine;
+	public final int pcmFormat;
+
+	public NativeEngine(int device, int maxStreams, int pcmFormat) {
+		this.pcmFormat = pcmFormat;
+		try (Arena a = Arena.ofConfined()) {
+			MemorySegment o = a.allocate(OPTIONS);
+			o.set(JAVA_INT, 0, device);
+			o.set(JAVA_INT, 4, maxStreams);
+			o.set(JAVA_INT, 8, pcmFormat);
+			MemorySegment out = a.allocate(ADDRESS);
+			int rc = (int) ENGINE_CREATE.invokeExact(o, out);
+			if (rc != 0)
+				throw new IllegalStateException("jaadb_engine_create failed: " + rc + " (no CUDA device? there is no CPU fallback)");
+			engine = out.get(ADDRESS, 0);
+		} catch (RuntimeException | Error e) {
+			throw e;
+		} catch (Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	String lastError() {
+		try {
+			return ((MemorySegment) LAST_ERROR.invokeExact(engine)).reinterpret(4096).getString(0);
+		} catch (Throwable t) {
+			return t.toString();
+		}
+	}
+
+	public static String statusString(int status) {
+		try {
+			return ((MemorySegment) STATUS_STRING.invokeExact(status)).reinterpret(256).getString(0);
+		} catch (Throwable t) {
+			return "status " + status;
+		}
+	}
+
+	/** Decoder.create(byte[] audioSpecificConfig), aac/.../Decoder.java:36-43. */
+	public int openAsc(byte[] asc) {
+		try (Arena a = Arena.ofConfined()) {
+			MemorySegment buf = a.allocateFrom(JAVA_BYTE, asc);
+			MemorySegment id = a.allocate(JAVA_INT);
+			int rc = (int) OPEN_ASC.invokeExact(engine, buf, asc.length, id);
+			if (rc != 0) throw new IllegalArgumentException("jaadb_stream_open_asc: " + lastError());
+			return id.get(JAVA_INT, 0);
+		} catch (RuntimeException e) {
+			throw e;
+		} catch (Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	/** Decoder.create(AudioDecoderInfo) from an ADTS header, aac/.../Decoder.java:45-48. */
+	public int openAdts(int profileIndex, int sfIndex, int channelConfig, int expectSbr) {
+		try (Arena a = Arena.ofConfined()) {
+			MemorySegment id = a.allocate(JAVA_INT);
+			int rc = (int) OPEN_ADTS.invokeExact(engine, profileIndex, sfIndex, channelConfig, expectSbr, id);
+			if (rc != 0) throw new IllegalArgumentException("jaadb_stream_open_adts: " + lastError());
+			return id.get(JAVA_INT, 0);
+		} catch (RuntimeException e) {
+			throw e;
+		} catch (Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	public void closeStream(int id) {
+		try {
+			int rc = (int) STREAM_CLOSE.invokeExact(engine, id);
+			if (rc != 0) throw new IllegalArgumentException("jaadb_stream_close: " + rc);
+		} catch (RuntimeException e) {
+			throw e;
+		} catch (Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	/**
+	 * Batched decodeFrame (aac/.../Decoder.java:89-121) + SampleBuffer.accept (src/.../SampleBuffer.java:168-209).
+	 * All segments are caller-owned native memory (use pinned/direct buffers); frames of one stream are applied in
+	 * array order. Returns 0, per-frame status words land in `results`.
+	 */
+	public void decode(MemorySegment blob, MemorySegment frames, int nFrames, MemorySegment pcmOut, MemorySegment pcmOffsets,
+					   MemorySegment results) {
+		try {
+			int rc = (int) DECODE.invokeExact(engine, blob, blob.byteSize(), frames, nFrames, pcmOut, pcmOut.byteSize(),
+					pcmOffsets == null ? MemorySegment.NULL : pcmOffsets, results);
+			if (rc != 0) throw new IllegalStateException("jaadb_decode: " + rc + " " + lastError());
+		} catch (RuntimeException e) {
+			throw e;
+		} catch (Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	@Override
+	public void close() {
+		try {
+			ENGINE_DESTROY.invokeExact(engine);
+		} catch (Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+}
