@@ -190,7 +190,7 @@ struct jaadb_batch {
   uint64_t blob_bytes = 0, pcm_bytes = 0;
   std::vector<FrameDev> frames;
   std::vector<RunDev> runs;           // grouped by channel count, see run_groups
-  std::vector<uint32_t> run_frames;
+  std::vector<RunFrameDev> run_frames;
   std::vector<uint64_t> pcm_off;
   std::vector<uint32_t> frame_pcm_size;  // expected size per frame
   struct Group { int nch; uint32_t first_run, n_runs; };
@@ -202,7 +202,8 @@ struct jaadb_batch {
   DevBuf<IcsSide> d_iside;
   DevBuf<int16_t> d_q;
   DevBuf<RunDev> d_runs;
-  DevBuf<uint32_t> d_run_frames, d_pcm_bytes;
+  DevBuf<RunFrameDev> d_run_frames;
+  DevBuf<uint32_t> d_pcm_bytes;
   DevBuf<uint64_t> d_pcm_off;
   DevBuf<float> d_spec_tap;
   std::vector<FrameSide> h_fside;
@@ -599,7 +600,7 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
   std::vector<uint32_t> fill(b->runs.size(), 0);
   for (uint32_t i = 0; i < n; ++i) {
     uint32_t r = run_of[fd[i].stream_id];
-    b->run_frames[b->runs[r].first + fill[r]++] = i;
+    b->run_frames[b->runs[r].first + fill[r]++] = RunFrameDev{i, b->frames[i].ics_base};
   }
   // device side
   cudaError_t ce = cudaSuccess;
@@ -619,7 +620,7 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
   if (n) {
     chk(cudaMemcpyAsync(b->d_frames.p, b->frames.data(), sizeof(FrameDev) * n, cudaMemcpyHostToDevice, e->stream));
     chk(cudaMemcpyAsync(b->d_runs.p, b->runs.data(), sizeof(RunDev) * b->runs.size(), cudaMemcpyHostToDevice, e->stream));
-    chk(cudaMemcpyAsync(b->d_run_frames.p, b->run_frames.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    chk(cudaMemcpyAsync(b->d_run_frames.p, b->run_frames.data(), sizeof(RunFrameDev) * n, cudaMemcpyHostToDevice, e->stream));
     chk(cudaMemcpyAsync(b->d_pcm_off.p, b->pcm_off.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream));
     chk(cudaMemsetAsync(b->d_blob.p + blob_bytes, 0, 64, e->stream));
     chk(cudaStreamSynchronize(e->stream));
@@ -664,7 +665,7 @@ int jaadb_batch_decode(jaadb_batch* b) {
     float* tap = (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) ? b->d_spec_tap.p : nullptr;
 #define LAUNCH_K2(FMT)                                                                                         \
   k2_filterbank_kernel<FMT><<<g.n_runs, threads, smem, e->stream>>>(                                           \
-      runs, b->d_run_frames.p, b->d_frames.p, b->d_fside.p, b->d_iside.p, b->d_q.p, e->d_overlap, e->d_sstate, \
+      runs, b->d_run_frames.p, b->d_fside.p, b->d_iside.p, b->d_q.p, e->d_overlap, e->d_sstate,                \
       b->d_pcm.p, b->d_pcm_off.p, b->d_pcm_bytes.p, tap, e->tables, e->d_layouts, g.nch)
     if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K2(0);
     else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K2(1);

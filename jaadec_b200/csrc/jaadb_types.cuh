@@ -85,6 +85,12 @@ struct RunDev {
   uint8_t pad;
 };
 
+// One frame of a run, in decode order (what K2 walks).
+struct RunFrameDev {
+  uint32_t frame;      // index into frames / frame_side / pcm_off
+  uint32_t ics_base;   // that frame's first channel slot in ics_side / q
+};
+
 // Huffman LUT entry (uint32):
 //   leaf: [4:0] code length, [7:5] number of sign bits that follow, [8]=0, [31:16] payload
 //         payload quads: 4 x 4-bit two's complement; pairs: 2 x 8-bit two's complement; sf book: value

@@ -1,5 +1,8 @@
 // K2 -- spectral processing.  One CTA owns one stream and walks that stream's
-// frames of the batch in decode order, 64 threads per channel:
+// frames of the batch in decode order, 64 threads per channel.  The next frame's
+// descriptor, side information and quantised coefficients are fetched into
+// registers while the current frame is in its FFT, so HBM latency stays off the
+// per-frame critical path:
 //   dequantisation (|q|^(4/3) LUT x 2^((sf-100)/4) LUT, ICStream.java:264-269)
 //   -> M/S (tools/MS.java:17-41) -> intensity stereo (tools/IS.java:17-53)
 //   -> IMDCT as an N/4-point complex FFT in registers + shared memory
@@ -76,69 +79,99 @@ __device__ __forceinline__ float mdct_out(const float* __restrict__ re, const fl
   }
 }
 
-// Java Math.round(float) + SampleBuffer clamp (S/SampleBuffer.java:193-205)
+// Java Math.round(float) + SampleBuffer clamp (S/SampleBuffer.java:193-205).
+// floor + exact fractional test is Math.round for every float: |x| >= 2^23 has no fraction, +-inf give a NaN
+// difference (test false) and saturate in the conversion, NaN converts to 0 -- the same values Java produces.
 __device__ __forceinline__ int pcm_round(float x) {
-  if (x != x) return 0;
-  x = fminf(fmaxf(x, -40000.f), 40000.f);
-  float f = floorf(x);
-  int r = (int)f + ((x - f) >= 0.5f ? 1 : 0);
+  const float f = floorf(x);
+  const int r = __float2int_rz(f) + ((x - f) >= 0.5f ? 1 : 0);
   return min(max(r, -32768), 32767);
 }
 
-struct ChanCtx {
-  const IcsSide* side;      // shared-memory copy
-  const int16_t* q;         // global
-};
+// Per-thread constants of one 4-coefficient sub-chunk (all SWB offsets are multiples of 4, so the four
+// coefficients i0..i0+3 always share a scalefactor band):
+//   [5:0] sfb if the window is long (63: beyond the table)   [9:6] sfb if short (15: beyond the table)
+//   [17:10] swb_short[sfb]   [23:18] width of that short band   [26:24] short window index (i0 >> 7)
+__device__ __forceinline__ uint32_t subchunk_consts(const TablesDev& T, int sf_index, int i0) {
+  int sl = T.sfb_of_long[sf_index * 1024 + i0];
+  if (sl > 62) sl = 63;
+  int ss = T.sfb_of_short[sf_index * 128 + (i0 & 127)];
+  int lo = 0, width = 0;
+  if (ss > 14) ss = 15;
+  else { lo = T.swb_short[sf_index * 17 + ss]; width = T.swb_short[sf_index * 17 + ss + 1] - lo; }
+  return (uint32_t)sl | ((uint32_t)ss << 6) | ((uint32_t)lo << 10) | ((uint32_t)width << 18) | ((uint32_t)(i0 >> 7) << 24);
+}
 
-// dequantised value of coefficient i (window de-interleaved index, as ICStream.iqData) of one channel before the
-// stereo tools; cb_out gets the band's codebook.  K1 leaves q in bitstream order: group g starts at
-// 128 * first_window(g), band sfb at glen * swb[sfb], glen windows x width coefficients, window-major.
-// win_info[w] = group | first window of the group << 8 | group length << 16.
-__device__ __forceinline__ float dequant_at(const IcsSide* __restrict__ s, const int16_t* __restrict__ q,
-                                            const TablesDev& T, const uint8_t* __restrict__ sfb_of,
-                                            const int16_t* __restrict__ swb_short, int i,
-                                            const uint32_t* __restrict__ win_info, int& cb_out, int& idx_out) {
-  int sfb, g = 0, qpos = i;
-  const bool sh = s->window_sequence == 2;
-  uint32_t wi = 0;
-  if (sh) { sfb = sfb_of[i & 127]; wi = win_info[i >> 7]; g = (int)(wi & 255u); }
-  else sfb = sfb_of[i];
+// Dequantises coefficients i0..i0+3 of one channel (ICStream.java:264-269): v = +-IQ_TABLE[|q|] * scaleFactors[idx].
+// `qpre` holds q[i0..i0+3] as fetched at the natural position, which is where K1 put them for long windows; for
+// EIGHT_SHORT the bitstream position is computed from the grouping and the four values are re-read.
+// cb_out / idx_out: the band's codebook and its (group, sfb) index; cb_out = 0 for bands at or above max_sfb.
+__device__ __forceinline__ void dequant4(const IcsSide* __restrict__ s, const int16_t* __restrict__ q, uint2 qpre,
+                                         uint32_t pk, int i0, const TablesDev& T, float v[4], int& cb_out, int& idx_out) {
+  v[0] = v[1] = v[2] = v[3] = 0.f;
   cb_out = 0;
   idx_out = 0;
-  if (sfb >= s->max_sfb) return 0.f;
-  const int idx = g * s->max_sfb + sfb;
-  idx_out = idx;
-  const int cb = s->sfb_cb[idx];
-  cb_out = cb;
-  if (cb == 0 || cb > 11) return 0.f;
-  if (sh) {
-    const int gstart = (int)((wi >> 8) & 255u), glen = (int)(wi >> 16);
-    const int lo = swb_short[sfb], width = swb_short[sfb + 1] - lo;
-    qpos = 128 * gstart + glen * lo + ((i >> 7) - gstart) * width + ((i & 127) - lo);
+  const int max_sfb = s->max_sfb;
+  int sfb, idx;
+  if (s->window_sequence == 2) {
+    sfb = (int)((pk >> 6) & 15u);
+    if (sfb >= max_sfb) return;
+    // window -> group: first window and length of the group that holds this window
+    const int w = (int)((pk >> 24) & 7u);
+    int g = 0, gstart = 0, glen = s->group_len[0];
+    for (int k = 0, acc = 0; k < 7; ++k) {
+      acc += s->group_len[k];
+      if (w >= acc && k + 1 < s->num_groups) { g = k + 1; gstart = acc; glen = s->group_len[k + 1]; }
+    }
+    idx = g * max_sfb + sfb;
+    const int cb = s->sfb_cb[idx];
+    cb_out = cb;
+    idx_out = idx;
+    if (cb == 0 || cb > 11) return;
+    const int lo = (int)((pk >> 10) & 255u), width = (int)((pk >> 18) & 63u);
+    const int qpos = 128 * gstart + glen * lo + (w - gstart) * width + ((i0 & 127) - lo);
+    qpre = *reinterpret_cast<const uint2*>(q + qpos);
+  } else {
+    sfb = (int)(pk & 63u);
+    if (sfb >= max_sfb) return;
+    idx = sfb;
+    const int cb = s->sfb_cb[idx];
+    cb_out = cb;
+    idx_out = idx;
+    if (cb == 0 || cb > 11) return;
   }
-  const int v = q[qpos];
   const float sf = __ldg(T.sf + s->sf_idx[idx]);
-  const float m = __ldg(T.iq + (v < 0 ? -v : v));
+  const int q0 = (int)(int16_t)(qpre.x & 0xFFFFu), q1 = (int)qpre.x >> 16;
+  const int q2 = (int)(int16_t)(qpre.y & 0xFFFFu), q3 = (int)qpre.y >> 16;
+  const float m0 = __ldg(T.iq + abs(q0)), m1 = __ldg(T.iq + abs(q1));
+  const float m2 = __ldg(T.iq + abs(q2)), m3 = __ldg(T.iq + abs(q3));
   // iqData = (v>0) ? IQ[v] : -IQ[-v]; iqData *= scaleFactors[idx]   (ICStream.java:266-267)
-  return (v > 0 ? m : -m) * sf;
+  v[0] = (q0 > 0 ? m0 : -m0) * sf;
+  v[1] = (q1 > 0 ? m1 : -m1) * sf;
+  v[2] = (q2 > 0 ? m2 : -m2) * sf;
+  v[3] = (q3 > 0 ? m3 : -m3) * sf;
+}
+
+__device__ __forceinline__ void channel_barrier(int c) {
+  // the 64 threads (two warps) of one channel
+  asm volatile("bar.sync %0, 64;" ::"r"(c + 1) : "memory");
 }
 
 template <int PCM_FORMAT>
-__global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint32_t* __restrict__ run_frames,
-                                     const FrameDev* __restrict__ frames, const FrameSide* __restrict__ fside,
-                                     const IcsSide* __restrict__ iside, const int16_t* __restrict__ qall,
-                                     float* __restrict__ overlap_all, StreamState* __restrict__ sstate,
-                                     uint8_t* __restrict__ pcm, const uint64_t* __restrict__ pcm_off,
-                                     uint32_t* __restrict__ pcm_bytes_out, float* __restrict__ spec_tap,
-                                     TablesDev T, const LayoutDev* __restrict__ layouts, int nch) {
+__global__ void __launch_bounds__(512)
+k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restrict__ run_frames,
+                     const FrameSide* __restrict__ fside, const IcsSide* __restrict__ iside,
+                     const int16_t* __restrict__ qall, float* __restrict__ overlap_all, StreamState* __restrict__ sstate,
+                     uint8_t* __restrict__ pcm, const uint64_t* __restrict__ pcm_off,
+                     uint32_t* __restrict__ pcm_bytes_out, float* __restrict__ spec_tap, TablesDev T,
+                     const LayoutDev* __restrict__ layouts, int nch) {
   extern __shared__ __align__(16) float smem[];
-  // carve: per channel [spec kSpecStride][overlap 1024][xre kXchgStride][xim kXchgStride]; then sides, pcm staging
+  // carve: twiddles; per channel [spec kSpecStride][overlap 1024][xre kXchgStride][xim kXchgStride]; sides; pcm staging
   const int per_ch = kSpecStride + 1024 + 2 * kXchgStride;
   float* s_fft_tw = smem;                         // fft512 re/im (inverse) [256][2] + fft64 [32][2]
   float* s_ch = s_fft_tw + 2 * 256 + 2 * 32;
   IcsSide* s_side = reinterpret_cast<IcsSide*>(s_ch + nch * per_ch);
-  uint32_t* s_wgroup = reinterpret_cast<uint32_t*>(s_side + nch);   // [nch][8] window -> group info
-  int16_t* s_pcm = reinterpret_cast<int16_t*>(s_wgroup + 8 * kMaxChannels);  // [1024][out_ch] (s16 formats)
+  int16_t* s_pcm = reinterpret_cast<int16_t*>(s_side + nch);  // [1024][out_ch] (s16 formats)
 
   const RunDev run = runs[blockIdx.x];
   const LayoutDev lay = layouts[run.layout];
@@ -168,9 +201,9 @@ __global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint
 
   // persistent state in: overlap + current window shapes
   float* g_ovl = overlap_all + ((size_t)run.stream_slot * kMaxChannels + c) * 1024;
-  for (int i = t; i < 1024; i += kThreadsPerChannel) my_ovl[i] = g_ovl[i];
+  for (int i = t; i < 256; i += kThreadsPerChannel)
+    reinterpret_cast<float4*>(my_ovl)[i] = reinterpret_cast<const float4*>(g_ovl)[i];
   int shape_cur = sstate[run.stream_slot].window_shape[c];
-  __syncthreads();
 
   // element of this thread's channel
   int el_first = c, el_nch = 1;
@@ -179,98 +212,113 @@ __global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint
     int n = lay.el_type[e] == EL_CPE ? 2 : 1;
     if (c >= f0 && c < f0 + n) { el_first = f0; el_nch = n; }
   }
+  // dequantisation work split: a CPE thread owns coefficients 8*et .. 8*et+7 of L and of R (M/S and IS are
+  // element-wise across the pair); an SCE/LFE thread owns 16*et .. 16*et+15 of its channel.
+  const int et = tid - el_first * kThreadsPerChannel;
+  const int chA = el_first, chB = el_first + (el_nch == 2 ? 1 : 0);
+  const int iA = (el_nch == 2) ? 8 * et : 16 * et;
+  const int iB = (el_nch == 2) ? iA : iA + 8;
+  const uint32_t pkA0 = subchunk_consts(T, sf_index, iA), pkA1 = subchunk_consts(T, sf_index, iA + 4);
+  const uint32_t pkB0 = subchunk_consts(T, sf_index, iB), pkB1 = subchunk_consts(T, sf_index, iB + 4);
+
+  // ---- software pipeline: descriptor, status, side information and q of the next frame live in registers
+  RunFrameDev cur = run_frames[run.first];
+  int status = fside[cur.frame].status;
+  uint4 side_pf = make_uint4(0, 0, 0, 0);
+  const int side_vecs = nch * (int)(sizeof(IcsSide) / 16);
+  if (tid < side_vecs) side_pf = reinterpret_cast<const uint4*>(iside + cur.ics_base)[tid];
+  uint4 qA = *reinterpret_cast<const uint4*>(qall + ((size_t)cur.ics_base + chA) * 1024 + iA);
+  uint4 qB = *reinterpret_cast<const uint4*>(qall + ((size_t)cur.ics_base + chB) * 1024 + iB);
+  __syncthreads();
 
   for (uint32_t it = 0; it < run.count; ++it) {
-    const uint32_t f = run_frames[run.first + it];
-    const FrameDev fr = frames[f];
-    const int status = fside[f].status;
+    const uint32_t f = cur.frame;
+    const uint32_t ics_base = cur.ics_base;
+    const uint64_t poff = pcm_off[f];
+    const bool have_next = it + 1 < run.count;
+    RunFrameDev nxt = cur;
+    if (have_next) nxt = run_frames[run.first + it + 1];
     // side info -> shared
-    {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(iside + fr.ics_base);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(s_side);
-      const int nwords = nch * (int)(sizeof(IcsSide) / 4);
-      for (int i = tid; i < nwords; i += nthreads) dst[i] = src[i];
-    }
+    if (tid < side_vecs) reinterpret_cast<uint4*>(s_side)[tid] = side_pf;
     __syncthreads();
     const IcsSide* sd = s_side + c;
     // window-shape bookkeeping of ICSInfo.decode / setCommonData (ICSInfo.java:90-91,196-197)
     int shape_prev = shape_cur;
     if (sd->info_decoded) { shape_prev = shape_cur; shape_cur = sd->window_shape; }
-    if (t < 8) {
-      // window -> group map for short frames
-      int w = t, g = 0, acc = 0, gstart = 0;
-      for (int k = 0; k < 8; ++k) { acc += sd->group_len[k]; if (w >= acc) { g = k + 1; gstart = acc; } }
-      g = min(g, 7);
-      s_wgroup[c * 8 + t] = (uint32_t)g | ((uint32_t)gstart << 8) | ((uint32_t)sd->group_len[g] << 16);
-    }
-    __syncthreads();
-    if (status != 0) {
-      if (tid == 0) pcm_bytes_out[f] = 0;
-      __syncthreads();
-      continue;  // the frame produced no PCM; overlap untouched (Decoder.java:96-98)
-    }
+    const int ws = sd->window_sequence;
+    const int frame_status = status;
 
-    // ---- phase 1: dequantise + M/S + IS into my_spec (threads of an element cover all its channels)
-    {
-      const int ws = sd->window_sequence;
-      const int el_threads = el_nch * kThreadsPerChannel;
-      const int et = tid - el_first * kThreadsPerChannel;
-      const int16_t* qL = qall + ((size_t)fr.ics_base + el_first) * 1024;
-      const IcsSide* sL = s_side + el_first;
-      float* specL = s_ch + el_first * per_ch;
-      const int16_t* swb_sh = T.swb_short + sf_index * 17;
-      if (el_nch == 1) {
-        const uint8_t* sfb_of = (ws == 2) ? T.sfb_of_short + sf_index * 128 : T.sfb_of_long + sf_index * 1024;
-        for (int i = et; i < 1024; i += el_threads) {
-          int cb, idx;
-          float v = dequant_at(sL, qL, T, sfb_of, swb_sh, i, s_wgroup + el_first * 8, cb, idx);
-          specL[spec_addr(i)] = v;
-          if (spec_tap) spec_tap[((size_t)fr.ics_base + el_first) * 1024 + i] = v;
-        }
-      } else {
-        const IcsSide* sR = sL + 1;
-        const int16_t* qR = qL + 1024;
-        float* specR = specL + per_ch;
-        const uint8_t* sfb_ofL = (sL->window_sequence == 2) ? T.sfb_of_short + sf_index * 128 : T.sfb_of_long + sf_index * 1024;
-        const uint8_t* sfb_ofR = (sR->window_sequence == 2) ? T.sfb_of_short + sf_index * 128 : T.sfb_of_long + sf_index * 1024;
+    if (frame_status == 0) {
+      // ---- phase 1: dequantise + M/S + IS into the element's spectra
+      const int16_t* qL = qall + ((size_t)ics_base + chA) * 1024;
+      const int16_t* qR = qall + ((size_t)ics_base + chB) * 1024;
+      const IcsSide* sL = s_side + chA;
+      const IcsSide* sR = s_side + chB;
+      float* specA = s_ch + chA * per_ch;
+      float* specB = s_ch + chB * per_ch;
+      float a[8], b[8];
+      int cbA0, cbA1, cbB0, cbB1, idxA0, idxA1, idxB0, idxB1;
+      dequant4(sL, qL, make_uint2(qA.x, qA.y), pkA0, iA, T, a, cbA0, idxA0);
+      dequant4(sL, qL, make_uint2(qA.z, qA.w), pkA1, iA + 4, T, a + 4, cbA1, idxA1);
+      dequant4(sR, qR, make_uint2(qB.x, qB.y), pkB0, iB, T, b, cbB0, idxB0);
+      dequant4(sR, qR, make_uint2(qB.z, qB.w), pkB1, iB + 4, T, b + 4, cbB1, idxB1);
+      if (el_nch == 2) {
         const bool ms_on = sL->common_window && sL->ms_mask != 0;   // CPE.java:159-160
         const bool ms_present = sL->ms_mask != 0;                   // CPE.isMSMaskPresent
-        for (int i = et; i < 1024; i += el_threads) {
-          int cbL, idxL, cbR, idxR;
-          float l = dequant_at(sL, qL, T, sfb_ofL, swb_sh, i, s_wgroup + el_first * 8, cbL, idxL);
-          float r = dequant_at(sR, qR, T, sfb_ofR, swb_sh, i, s_wgroup + (el_first + 1) * 8, cbR, idxR);
-          // MS.process: both codebooks < NOISE_HCB, band flagged (MS.java:28-36)
-          if (ms_on && cbL < 13 && cbR < 13) {
-            // idxL == idxR here (common window); bands above max_sfb have cb 0 but are never flagged
-            const bool band_in = (sL->window_sequence == 2 ? sfb_ofL[i & 127] : sfb_ofL[i]) < sL->max_sfb;
-            if (band_in && ((sL->ms_used[idxL >> 3] >> (idxL & 7)) & 1)) {
-              float tt = l - r;
-              l = l + r;
-              r = tt;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int cbL = h ? cbA1 : cbA0, cbR = h ? cbB1 : cbB0;
+          const int idxL = h ? idxA1 : idxA0, idxR = h ? idxB1 : idxB0;
+          // MS.process: both codebooks < NOISE_HCB, band flagged (MS.java:28-36).  Bands at or above max_sfb have
+          // cb_out 0 and idx 0: they hold zeros, for which the butterfly is the identity up to the sign of zero --
+          // JAAD never touches them, so they are excluded through the left channel's band test.
+          const bool in_band = ((sL->window_sequence == 2) ? (int)(((h ? pkA1 : pkA0) >> 6) & 15u) : (int)((h ? pkA1 : pkA0) & 63u)) < sL->max_sfb;
+          if (ms_on && cbL < 13 && cbR < 13 && in_band && ((sL->ms_used[idxL >> 3] >> (idxL & 7)) & 1)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float l = a[4 * h + j], r = b[4 * h + j];
+              a[4 * h + j] = l + r;
+              b[4 * h + j] = l - r;
             }
           }
           // IS.process: right channel bands with codebook 14/15 (IS.java:29-44)
           if (cbR == 15 || cbR == 14) {
             int sgn = cbR == 15 ? 1 : -1;
             if (ms_present) sgn *= ((sL->ms_used[idxR >> 3] >> (idxR & 7)) & 1) ? -1 : 1;
-            const unsigned si = sR->sf_idx[idxR];
-            float scale = __ldg(T.sf + si);
+            float scale = __ldg(T.sf + sR->sf_idx[idxR]);
             if (sgn < 0) scale = -scale;
-            r = l * scale;
-          }
-          specL[spec_addr(i)] = l;
-          specR[spec_addr(i)] = r;
-          if (spec_tap) {
-            spec_tap[((size_t)fr.ics_base + el_first) * 1024 + i] = l;
-            spec_tap[((size_t)fr.ics_base + el_first + 1) * 1024 + i] = r;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[4 * h + j] = a[4 * h + j] * scale;
           }
         }
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        specA[spec_addr(iA + j)] = a[j];
+        specB[spec_addr(iB + j)] = b[j];
+      }
+      if (spec_tap) {
+        float* tA = spec_tap + ((size_t)ics_base + chA) * 1024 + iA;
+        float* tB = spec_tap + ((size_t)ics_base + chB) * 1024 + iB;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { tA[j] = a[j]; tB[j] = b[j]; }
+      }
     }
+    // ---- prefetch the next frame while this one is transformed
+    if (have_next) {
+      status = fside[nxt.frame].status;
+      if (tid < side_vecs) side_pf = reinterpret_cast<const uint4*>(iside + nxt.ics_base)[tid];
+      qA = *reinterpret_cast<const uint4*>(qall + ((size_t)nxt.ics_base + chA) * 1024 + iA);
+      qB = *reinterpret_cast<const uint4*>(qall + ((size_t)nxt.ics_base + chB) * 1024 + iB);
+    }
+    cur = nxt;
     __syncthreads();
+    if (frame_status != 0) {
+      if (tid == 0) pcm_bytes_out[f] = 0;
+      continue;  // the frame produced no PCM; overlap untouched (Decoder.java:96-98)
+    }
 
     // ---- phase 2: IMDCT of this channel (thread t owns points 8t..8t+7 of the bit-reversed input)
-    const int ws = sd->window_sequence;
     const bool is_short = ws == 2;
     Cplx a[8];
     {
@@ -282,9 +330,9 @@ __global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint
           const int k = kb + 64 * brev3(j);
           const float x0 = my_spec[spec_addr(2 * k)];
           const float x1 = my_spec[spec_addr(1023 - 2 * k)];
-          const float cs = __ldg(T.mdct_long + 2 * k), sn = __ldg(T.mdct_long + 2 * k + 1);
-          a[j].im = (x0 * cs) + (x1 * sn);
-          a[j].re = (x1 * cs) - (x0 * sn);
+          const float2 cs = __ldg(reinterpret_cast<const float2*>(T.mdct_long) + k);
+          a[j].im = (x0 * cs.x) + (x1 * cs.y);
+          a[j].re = (x1 * cs.x) - (x0 * cs.y);
         }
       } else {
         const int w = t >> 3;                                  // short window handled by this thread
@@ -294,9 +342,9 @@ __global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint
           const int k = kb + 8 * brev3(j);                     // bitrev6(8*(t&7)+j)
           const float x0 = my_spec[spec_addr(128 * w + 2 * k)];
           const float x1 = my_spec[spec_addr(128 * w + 127 - 2 * k)];
-          const float cs = __ldg(T.mdct_short + 2 * k), sn = __ldg(T.mdct_short + 2 * k + 1);
-          a[j].im = (x0 * cs) + (x1 * sn);
-          a[j].re = (x1 * cs) - (x0 * sn);
+          const float2 cs = __ldg(reinterpret_cast<const float2*>(T.mdct_short) + k);
+          a[j].im = (x0 * cs.x) + (x1 * cs.y);
+          a[j].re = (x1 * cs.x) - (x0 * cs.y);
         }
       }
       // stage A: radix-4 on (0..3), (4..7), then radix-2 stage i=4 with roots[k*m], m = length/8
@@ -316,7 +364,7 @@ __global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint
         }
       }
     }
-    __syncthreads();
+    channel_barrier(c);
     {
       const int blk = t >> 3, col = t & 7;
 #pragma unroll
@@ -344,26 +392,29 @@ __global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint
         bfly(a[j], a[j + 4], tw[2 * k * (mB >> 2)], tw[2 * k * (mB >> 2) + 1]);
       }
     }
-    __syncthreads();  // everyone finished reading exchange 1
-    float* bre = my_spec;              // reuse: post-twiddled buffer as planes re[512] | im[512]
-    float* bim = my_spec + 512;
+    // The spectrum was consumed before the channel barrier above, so its storage now carries exchange 2
+    // (planes re | im, 528 floats each); the post-twiddled buffer then goes where exchange 1 was.
+    float* x2re = my_spec;
+    float* x2im = my_spec + 528;
+    float* bre = my_xre;               // post-twiddled buffer as planes re[512] | im[512]
+    float* bim = my_xim;
     if (!is_short) {
-      // exchange 2 through the same planes: write n = 64*blk + col + 8*j, read n = t + 64*j
+      // exchange 2: write n = 64*blk + col + 8*j, read n = t + 64*j
       const int blk = t >> 3, col = t & 7;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int n = 64 * blk + col + 8 * j;
-        my_xre[n + (n >> 5)] = a[j].re;   // kXchgStride = 576 >= 512 + 16
-        my_xim[n + (n >> 5)] = a[j].im;
+        x2re[n + (n >> 5)] = a[j].re;
+        x2im[n + (n >> 5)] = a[j].im;
       }
     }
-    __syncthreads();  // unconditional: channels of one CTA may mix long and short windows
+    channel_barrier(c);   // also: every thread of the channel is done reading exchange 1
     if (!is_short) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int n = t + 64 * j;
-        a[j].re = my_xre[n + (n >> 5)];
-        a[j].im = my_xim[n + (n >> 5)];
+        a[j].re = x2re[n + (n >> 5)];
+        a[j].im = x2im[n + (n >> 5)];
       }
       // stage C: i = 64, 128, 256 on local index j
 #pragma unroll
@@ -385,119 +436,150 @@ __global__ void k2_filterbank_kernel(const RunDev* __restrict__ runs, const uint
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int n = t + 64 * j;
-        const float cs = __ldg(T.mdct_long + 2 * n), sn = __ldg(T.mdct_long + 2 * n + 1);
+        const float2 cs = __ldg(reinterpret_cast<const float2*>(T.mdct_long) + n);
         const float t0 = a[j].re, t1 = a[j].im;
-        bim[n] = (t1 * cs) + (t0 * sn);
-        bre[n] = (t0 * cs) - (t1 * sn);
+        bim[n] = (t1 * cs.x) + (t0 * cs.y);
+        bre[n] = (t0 * cs.x) - (t1 * cs.y);
       }
     } else {
       const int blk = t >> 3, col = t & 7;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int nl = col + 8 * j;         // index inside the 64-point FFT of window blk
-        const float cs = __ldg(T.mdct_short + 2 * nl), sn = __ldg(T.mdct_short + 2 * nl + 1);
+        const float2 cs = __ldg(reinterpret_cast<const float2*>(T.mdct_short) + nl);
         const float t0 = a[j].re, t1 = a[j].im;
-        bim[64 * blk + nl] = (t1 * cs) + (t0 * sn);
-        bre[64 * blk + nl] = (t0 * cs) - (t1 * sn);
+        bim[64 * blk + nl] = (t1 * cs.x) + (t0 * cs.y);
+        bre[64 * blk + nl] = (t0 * cs.x) - (t1 * cs.y);
       }
     }
-    __syncthreads();
+    channel_barrier(c);
 
-    // ---- phase 3: windowing + overlap-add (FilterBank.java:39-123) + PCM
+    // ---- phase 3: windowing + overlap-add (FilterBank.java:39-123) + PCM.  Thread t owns the sample pairs
+    // i = 2t + 128j, i+1 (j = 0..7): the MDCT reorder (MDCT.java:60-80) then reads mirrored positions of the two
+    // planes without any per-lane case split, and the overlap goes back as float2.
     {
       const float* LWp = T.win_long[shape_prev];
       const float* LW = T.win_long[shape_cur];
       const float* SWp = T.win_short[shape_prev];
       const float* SW = T.win_short[shape_cur];
-      float outv[16], ovlv[16];
+      uint8_t* dst = pcm + poff;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int i = t + 64 * j;
-        const float ov = my_ovl[i];
-        float o, nv;
-        if (ws == 0) {
-          o = ov + (mdct_out(bre, bim, 512, 256, i) * __ldg(LWp + i));
-          nv = mdct_out(bre, bim, 512, 256, 1024 + i) * __ldg(LW + 1023 - i);
-        } else if (ws == 1) {
-          o = ov + (mdct_out(bre, bim, 512, 256, i) * __ldg(LWp + i));
-          if (i < 448) nv = mdct_out(bre, bim, 512, 256, 1024 + i);
-          else if (i < 576) nv = mdct_out(bre, bim, 512, 256, 1024 + i) * __ldg(SW + 127 - (i - 448));
-          else nv = 0.f;
-        } else if (ws == 3) {
-          if (i < 448) o = ov;
-          else if (i < 576) o = ov + (mdct_out(bre, bim, 512, 256, i) * __ldg(SWp + (i - 448)));
-          else o = ov + mdct_out(bre, bim, 512, 256, i);
-          nv = mdct_out(bre, bim, 512, 256, 1024 + i) * __ldg(LW + 1023 - i);
+      for (int j = 0; j < 8; ++j) {
+        const int i = 2 * t + 128 * j;
+        const float2 ov = *reinterpret_cast<const float2*>(my_ovl + i);
+        float o0, o1, n0, n1;
+        if (!is_short) {
+          // x1* = first half of the IMDCT output at i, i+1; x2* = second half (index 1024+i, 1024+i+1)
+          float x10, x11, x20, x21;
+          if (j < 4) {
+            const int H = t + 64 * j;
+            x10 = bim[256 + H]; x11 = -bre[255 - H];
+            x20 = bre[256 + H]; x21 = -bim[255 - H];
+          } else {
+            const int H = t + 64 * (j - 4);
+            x10 = bre[H]; x11 = -bim[511 - H];
+            x20 = -bim[H]; x21 = bre[511 - H];
+          }
+          if (ws == 3) {
+            // LONG_STOP
+            if (i < 448) { o0 = ov.x; o1 = ov.y; }
+            else if (i < 576) {
+              const float2 w = __ldg(reinterpret_cast<const float2*>(SWp + (i - 448)));
+              o0 = ov.x + (x10 * w.x); o1 = ov.y + (x11 * w.y);
+            } else { o0 = ov.x + x10; o1 = ov.y + x11; }
+          } else {
+            const float2 w = __ldg(reinterpret_cast<const float2*>(LWp + i));
+            o0 = ov.x + (x10 * w.x); o1 = ov.y + (x11 * w.y);
+          }
+          if (ws == 1) {
+            // LONG_START
+            if (i < 448) { n0 = x20; n1 = x21; }
+            else if (i < 576) {
+              const float2 w = __ldg(reinterpret_cast<const float2*>(SW + 126 - (i - 448)));
+              n0 = x20 * w.y; n1 = x21 * w.x;
+            } else { n0 = 0.f; n1 = 0.f; }
+          } else {
+            const float2 w = __ldg(reinterpret_cast<const float2*>(LW + 1022 - i));
+            n0 = x20 * w.y; n1 = x21 * w.x;
+          }
         } else {
           // EIGHT_SHORT: window w occupies b[256w .. 256w+255]; its samples come from FFT block w
-          // out[448 + 128*s + r]
-          if (i < 448) o = ov;
-          else {
-            const int s = (i - 448) >> 7, r = (i - 448) & 127;
-            if (s == 0) {
-              o = ov + (mdct_out(bre, bim, 64, 32, r) * __ldg(SWp + r));
-            } else {
-              // second half of window s-1 + first half of window s (s = 1..4; s==4 only for r < 64)
-              const float a2 = mdct_out(bre + 64 * (s - 1), bim + 64 * (s - 1), 64, 32, 128 + r) * __ldg(SW + 127 - r);
-              const float b2 = mdct_out(bre + 64 * s, bim + 64 * s, 64, 32, r) * __ldg(SW + r);
-              o = (ov + a2) + b2;
+          float oo[2], nn[2];
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const int ii = i + p;
+            const float ovp = p ? ov.y : ov.x;
+            float o, nv;
+            if (ii < 448) o = ovp;
+            else {
+              const int s = (ii - 448) >> 7, r = (ii - 448) & 127;
+              if (s == 0) {
+                o = ovp + (mdct_out(bre, bim, 64, 32, r) * __ldg(SWp + r));
+              } else {
+                // second half of window s-1 + first half of window s (s = 1..4; s==4 only for r < 64)
+                const float a2 = mdct_out(bre + 64 * (s - 1), bim + 64 * (s - 1), 64, 32, 128 + r) * __ldg(SW + 127 - r);
+                const float b2 = mdct_out(bre + 64 * s, bim + 64 * s, 64, 32, r) * __ldg(SW + r);
+                o = (ovp + a2) + b2;
+              }
             }
-          }
-          // new overlap
-          if (i >= 576) nv = 0.f;
-          else {
-            // overlap[i]: i in [0,64): window 3 second half (r = 64+i) + window 4 first half
-            //             i = 64 + 128*u + r: window 4+u second half + window 5+u first half (u = 0..2)
-            //             i in [448,576): window 7 second half only
-            if (i < 64) {
-              const int r = 64 + i;
+            if (ii >= 576) nv = 0.f;
+            else if (ii < 64) {
+              // overlap[i], i in [0,64): window 3 second half (r = 64+i) + window 4 first half
+              const int r = 64 + ii;
               nv = (mdct_out(bre + 64 * 3, bim + 64 * 3, 64, 32, 128 + r) * __ldg(SW + 127 - r)) +
                    (mdct_out(bre + 64 * 4, bim + 64 * 4, 64, 32, r) * __ldg(SW + r));
-            } else if (i < 448) {
-              const int u = (i - 64) >> 7, r = (i - 64) & 127;
+            } else if (ii < 448) {
+              // i = 64 + 128*u + r: window 4+u second half + window 5+u first half (u = 0..2)
+              const int u = (ii - 64) >> 7, r = (ii - 64) & 127;
               nv = (mdct_out(bre + 64 * (4 + u), bim + 64 * (4 + u), 64, 32, 128 + r) * __ldg(SW + 127 - r)) +
                    (mdct_out(bre + 64 * (5 + u), bim + 64 * (5 + u), 64, 32, r) * __ldg(SW + r));
             } else {
-              const int r = i - 448;
+              // i in [448,576): window 7 second half only
+              const int r = ii - 448;
               nv = mdct_out(bre + 64 * 7, bim + 64 * 7, 64, 32, 128 + r) * __ldg(SW + 127 - r);
             }
+            oo[p] = o;
+            nn[p] = nv;
           }
+          o0 = oo[0]; o1 = oo[1]; n0 = nn[0]; n1 = nn[1];
         }
-        outv[j] = o;
-        ovlv[j] = nv;
-      }
-      uint8_t* dst = pcm + pcm_off[f];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int i = t + 64 * j;
-        my_ovl[i] = ovlv[j];
+        *reinterpret_cast<float2*>(my_ovl + i) = make_float2(n0, n1);
         if (PCM_FORMAT == 2) {
           float* d = reinterpret_cast<float*>(dst);
-          d[(size_t)c * 1024 + i] = outv[j];
-          if (run.mono_dup) d[1024 + i] = outv[j];
+          *reinterpret_cast<float2*>(d + (size_t)c * 1024 + i) = make_float2(o0, o1);
+          if (run.mono_dup) *reinterpret_cast<float2*>(d + 1024 + i) = make_float2(o0, o1);
         } else {
-          const int v = pcm_round(outv[j]);
-          uint16_t u = (uint16_t)(int16_t)v;
-          if (PCM_FORMAT == 1) u = (uint16_t)((u >> 8) | (u << 8));
-          if (run.mono_dup) { s_pcm[2 * i] = (int16_t)u; s_pcm[2 * i + 1] = (int16_t)u; }
-          else s_pcm[i * out_ch + c] = (int16_t)u;
+          uint32_t u0 = (uint32_t)pcm_round(o0) & 0xFFFFu, u1 = (uint32_t)pcm_round(o1) & 0xFFFFu;
+          if (PCM_FORMAT == 1) { u0 = __byte_perm(u0, 0, 0x4401); u1 = __byte_perm(u1, 0, 0x4401); }
+          if (run.mono_dup) {
+            *reinterpret_cast<uint2*>(s_pcm + 2 * i) = make_uint2(u0 | (u0 << 16), u1 | (u1 << 16));
+          } else {
+            s_pcm[i * out_ch + c] = (int16_t)u0;
+            s_pcm[(i + 1) * out_ch + c] = (int16_t)u1;
+          }
         }
       }
       __syncthreads();
       if (PCM_FORMAT != 2) {
-        // coalesced copy-out of the interleaved frame
+        // coalesced copy-out of the interleaved frame (pcm offsets are 4-byte aligned; 16 B when the caller packs)
         const int nwords = 1024 * out_ch / 2;   // 32-bit words
         const uint32_t* src = reinterpret_cast<const uint32_t*>(s_pcm);
         uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-        for (int i = tid; i < nwords; i += nthreads) d[i] = src[i];
+        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+          for (int i = tid; i < nwords / 4; i += nthreads)
+            reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(src)[i];
+        } else {
+          for (int i = tid; i < nwords; i += nthreads) d[i] = src[i];
+        }
       }
       if (tid == 0) pcm_bytes_out[f] = (uint32_t)(1024 * out_ch * (PCM_FORMAT == 2 ? 4 : 2));
     }
-    __syncthreads();
   }
 
-  // persistent state out
-  for (int i = t; i < 1024; i += kThreadsPerChannel) g_ovl[i] = my_ovl[i];
+  // persistent state out (the last frame's phase 3 wrote my_ovl; the loop's trailing barrier ordered it)
+  __syncthreads();
+  for (int i = t; i < 256; i += kThreadsPerChannel)
+    reinterpret_cast<float4*>(g_ovl)[i] = reinterpret_cast<const float4*>(my_ovl)[i];
   if (t == 0) sstate[run.stream_slot].window_shape[c] = (uint8_t)shape_cur;
 }
 
