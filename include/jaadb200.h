@@ -76,7 +76,8 @@ typedef struct jaadb_options {
   int32_t pcm_format;    /* JAADB_PCM_* */
   int32_t tns_mode;      /* JAADB_TNS_* */
   uint32_t flags;        /* JAADB_FLAG_* */
-  uint32_t reserved[3];
+  uint32_t chunk_frames; /* jaadb_decode pipelines chunks of this many consecutive frames (0: default, 131072) */
+  uint32_t reserved[2];
 } jaadb_options;
 
 /* One AAC frame (an ADTS payload or an MP4 sample) inside the caller's blob.

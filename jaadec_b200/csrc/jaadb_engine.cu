@@ -136,6 +136,18 @@ LayoutDev make_layout(int chan_cfg) {
   return l;
 }
 
+struct FrameIndex {
+  struct Group { int nch; uint32_t first_run, n_runs; };
+  std::vector<FrameDev> frames;          // in the caller's order
+  std::vector<RunDev> runs;              // grouped by channel-slot count so every K2 launch has one block size
+  std::vector<RunFrameDev> run_frames;   // per run, its frames in the caller's order
+  std::vector<Group> groups;
+  uint32_t n_ics = 0;
+  // when set, frames / run_frames are written here (pinned staging of the one-call path) instead of the vectors
+  FrameDev* frames_out = nullptr;
+  RunFrameDev* run_frames_out = nullptr;
+};
+
 template <typename Tp>
 struct DevBuf {
   Tp* p = nullptr;
@@ -160,6 +172,9 @@ struct jaadb_engine {
   std::string error;
   std::vector<StreamHost> streams;
   std::vector<int32_t> free_slots;
+  std::vector<uint32_t> scratch_count, scratch_run_of, scratch_fill, scratch_size;
+  std::vector<uint64_t> scratch_off;
+  FrameIndex scratch_ix;
   // device tables
   std::vector<void*> table_allocs;
   TablesDev tables;
@@ -170,6 +185,32 @@ struct jaadb_engine {
   float* d_overlap = nullptr;
   StreamState* d_sstate = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  // workspace of the one-call path (jaadb_decode): grow-only, so a steady stream of calls allocates nothing.
+  // The call is cut into chunks of consecutive frames; chunk k's PCM goes out over PCIe on copy_stream while
+  // chunk k+1 is parsed and transformed on `stream` (two PCM buffers, ping-pong).
+  struct Workspace {
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t k_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+    DevBuf<uint8_t> blob, pcm[2];
+    DevBuf<FrameDev> frames;
+    DevBuf<FrameSide> fside;
+    DevBuf<IcsSide> iside;
+    DevBuf<int16_t> q;
+    DevBuf<RunDev> runs;
+    DevBuf<RunFrameDev> run_frames;
+    DevBuf<uint32_t> pcm_bytes;
+    DevBuf<uint64_t> pcm_off;
+    FrameSide* h_fside = nullptr;      // pinned
+    uint32_t* h_pcm_bytes = nullptr;   // pinned
+    size_t h_cap = 0;
+    // pinned descriptor staging, double buffered (chunk k uses slot k & 1)
+    cudaEvent_t desc_done[2] = {nullptr, nullptr};
+    FrameDev* h_frames[2] = {nullptr, nullptr};
+    RunFrameDev* h_run_frames[2] = {nullptr, nullptr};
+    RunDev* h_runs[2] = {nullptr, nullptr};
+    size_t h_chunk_cap = 0, h_runs_cap = 0;
+  } ws;
 
   void set_error(const std::string& s) { error = s; }
 
@@ -193,7 +234,7 @@ struct jaadb_batch {
   std::vector<RunFrameDev> run_frames;
   std::vector<uint64_t> pcm_off;
   std::vector<uint32_t> frame_pcm_size;  // expected size per frame
-  struct Group { int nch; uint32_t first_run, n_runs; };
+  typedef FrameIndex::Group Group;
   std::vector<Group> groups;
   // device
   DevBuf<uint8_t> d_blob, d_pcm;
@@ -332,6 +373,129 @@ size_t k2_smem_bytes(int nch, int out_ch) {
   return (b + 15) & ~size_t(15);
 }
 
+// ---- host-side indexing shared by the staged and the one-call paths -----------------------------------------
+
+// PCM placement: the caller's offsets, or frames packed back to back in array order.
+int layout_pcm(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, const uint64_t* pcm_offsets,
+               std::vector<uint64_t>& off, std::vector<uint32_t>& size, uint64_t* total) {
+  off.resize(n);
+  size.resize(n);
+  uint64_t pos = 0, end = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const int32_t sid = fd[i].stream_id;
+    if (sid < 0 || sid >= (int32_t)e->streams.size() || !e->streams[sid].open) {
+      e->set_error("frame refers to an unknown stream");
+      return JAADB_E_NOSTREAM;
+    }
+    const uint32_t sz = frame_pcm_bytes(e, e->streams[sid]);
+    size[i] = sz;
+    if (pcm_offsets) {
+      if (pcm_offsets[i] & 3u) { e->set_error("pcm offsets must be 4-byte aligned"); return JAADB_E_INVALID; }
+      off[i] = pcm_offsets[i];
+    } else {
+      off[i] = pos;
+      pos += sz;
+    }
+    end = std::max(end, off[i] + sz);
+  }
+  *total = end;
+  return JAADB_OK;
+}
+
+// Frames [0, n) of fd -> device descriptors + per-stream runs.  Frame indices in the result are relative to fd.
+int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64_t blob_bytes, FrameIndex& ix) {
+  if (!ix.frames_out) ix.frames.resize(n);
+  FrameDev* const fout = ix.frames_out ? ix.frames_out : ix.frames.data();
+  ix.runs.clear();
+  ix.groups.clear();
+  // per-stream frame counts (counting sort keeps array order inside each stream)
+  std::vector<uint32_t>& count = e->scratch_count;
+  count.assign(e->streams.size(), 0);
+  uint32_t ics = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const jaadb_frame_desc& d = fd[i];
+    if (d.stream_id < 0 || d.stream_id >= (int32_t)e->streams.size() || !e->streams[d.stream_id].open) {
+      e->set_error("frame refers to an unknown stream");
+      return JAADB_E_NOSTREAM;
+    }
+    if (d.offset + d.nbytes > blob_bytes) { e->set_error("frame exceeds the blob"); return JAADB_E_INVALID; }
+    const StreamHost& s = e->streams[d.stream_id];
+    FrameDev& f = fout[i];
+    f.blob_off = d.offset;
+    f.nbytes = d.nbytes;
+    f.stream_slot = d.stream_id;
+    f.ics_base = ics;
+    f.sf_index = (uint8_t)s.sf_index;
+    f.layout = (uint8_t)s.chan_cfg;
+    f.profile_ok = s.profile_ok ? 1 : 0;
+    f.flags = 0;
+    ics += (uint32_t)s.n_slots;
+    count[d.stream_id]++;
+  }
+  ix.n_ics = ics;
+  std::vector<uint32_t>& run_of = e->scratch_run_of;
+  run_of.assign(e->streams.size(), 0xFFFFFFFFu);
+  for (int nch = 1; nch <= kMaxChannels; ++nch) {
+    FrameIndex::Group g{nch, (uint32_t)ix.runs.size(), 0};
+    for (size_t s = 0; s < e->streams.size(); ++s) {
+      if (!count[s] || e->streams[s].n_slots != nch) continue;
+      RunDev r;
+      memset(&r, 0, sizeof r);
+      r.stream_slot = (int32_t)s;
+      r.count = count[s];
+      r.layout = (uint8_t)e->streams[s].chan_cfg;
+      r.sf_index = (uint8_t)e->streams[s].sf_index;
+      r.mono_dup = (e->streams[s].chan_cfg == 1) ? 1 : 0;
+      run_of[s] = (uint32_t)ix.runs.size();
+      ix.runs.push_back(r);
+      g.n_runs++;
+    }
+    if (g.n_runs) ix.groups.push_back(g);
+  }
+  uint32_t acc = 0;
+  for (auto& r : ix.runs) { r.first = acc; acc += r.count; }
+  if (!ix.run_frames_out) ix.run_frames.resize(n);
+  RunFrameDev* const rout = ix.run_frames_out ? ix.run_frames_out : ix.run_frames.data();
+  std::vector<uint32_t>& fill = e->scratch_fill;
+  fill.assign(ix.runs.size(), 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t r = run_of[fd[i].stream_id];
+    rout[ix.runs[r].first + fill[r]++] = RunFrameDev{i, fout[i].ics_base};
+  }
+  return JAADB_OK;
+}
+
+// K1 + K2 over an indexed set of frames, everything already on the device.
+void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_groups, uint32_t n_frames,
+                   const uint8_t* d_blob, const FrameDev* d_frames, FrameSide* d_fside, IcsSide* d_iside, int16_t* d_q,
+                   const RunDev* d_runs, const RunFrameDev* d_run_frames, uint8_t* d_pcm, const uint64_t* d_pcm_off,
+                   uint32_t* d_pcm_bytes, float* d_tap, cudaEvent_t after_k1, uint32_t* launches) {
+  {
+    const int threads = 128;
+    const int blocks = (int)((n_frames + threads - 1) / threads);
+    k1_parse_kernel<<<blocks, threads, e->lut_entries * 4, e->stream>>>(d_blob, d_frames, n_frames, d_fside, d_iside, d_q,
+                                                                        e->tables, e->d_layouts);
+    ++*launches;
+  }
+  if (after_k1) cudaEventRecord(after_k1, e->stream);
+  for (size_t gi = 0; gi < n_groups; ++gi) {
+    const FrameIndex::Group& g = groups[gi];
+    const int threads = g.nch * kThreadsPerChannel;
+    const int out_ch = (g.nch == 1) ? 2 : g.nch;
+    const size_t smem = k2_smem_bytes(g.nch, out_ch);
+    const RunDev* runs = d_runs + g.first_run;
+#define LAUNCH_K2(FMT)                                                                                              \
+  k2_filterbank_kernel<FMT><<<g.n_runs, threads, smem, e->stream>>>(runs, d_run_frames, d_fside, d_iside, d_q,     \
+                                                                    e->d_overlap, e->d_sstate, d_pcm, d_pcm_off,   \
+                                                                    d_pcm_bytes, d_tap, e->tables, e->d_layouts, g.nch)
+    if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K2(0);
+    else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K2(1);
+    else LAUNCH_K2(2);
+#undef LAUNCH_K2
+    ++*launches;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -405,6 +569,21 @@ void jaadb_engine_destroy(jaadb_engine* e) {
   if (e->d_sstate) cudaFree(e->d_sstate);
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);
+  auto& W = e->ws;
+  if (W.copy_stream) { cudaStreamSynchronize(W.copy_stream); cudaStreamDestroy(W.copy_stream); }
+  for (int i = 0; i < 2; ++i) {
+    if (W.k_done[i]) cudaEventDestroy(W.k_done[i]);
+    if (W.d2h_done[i]) cudaEventDestroy(W.d2h_done[i]);
+    if (W.desc_done[i]) cudaEventDestroy(W.desc_done[i]);
+    if (W.h_frames[i]) cudaFreeHost(W.h_frames[i]);
+    if (W.h_run_frames[i]) cudaFreeHost(W.h_run_frames[i]);
+    if (W.h_runs[i]) cudaFreeHost(W.h_runs[i]);
+    W.pcm[i].release();
+  }
+  W.blob.release(); W.frames.release(); W.fside.release(); W.iside.release(); W.q.release(); W.runs.release();
+  W.run_frames.release(); W.pcm_bytes.release(); W.pcm_off.release();
+  if (W.h_fside) cudaFreeHost(W.h_fside);
+  if (W.h_pcm_bytes) cudaFreeHost(W.h_pcm_bytes);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -535,73 +714,18 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
   b->e = e;
   b->n_frames = n;
   b->blob_bytes = blob_bytes;
-  b->frames.resize(n);
-  b->pcm_off.resize(n);
-  b->frame_pcm_size.resize(n);
   auto fail = [&](int rc) { jaadb_batch_destroy(b); return rc; };
-  // per-stream frame counts (counting sort keeps array order inside each stream)
-  std::vector<uint32_t> count(e->streams.size(), 0);
-  uint32_t ics = 0;
-  uint64_t pcm_pos = 0, pcm_end = 0;
-  for (uint32_t i = 0; i < n; ++i) {
-    const jaadb_frame_desc& d = fd[i];
-    if (d.stream_id < 0 || d.stream_id >= (int32_t)e->streams.size() || !e->streams[d.stream_id].open) {
-      e->set_error("frame refers to an unknown stream");
-      return fail(JAADB_E_NOSTREAM);
-    }
-    if (d.offset + d.nbytes > blob_bytes) { e->set_error("frame exceeds the blob"); return fail(JAADB_E_INVALID); }
-    const StreamHost& s = e->streams[d.stream_id];
-    FrameDev& f = b->frames[i];
-    f.blob_off = d.offset;
-    f.nbytes = d.nbytes;
-    f.stream_slot = d.stream_id;
-    f.ics_base = ics;
-    f.sf_index = (uint8_t)s.sf_index;
-    f.layout = (uint8_t)s.chan_cfg;
-    f.profile_ok = s.profile_ok ? 1 : 0;
-    f.flags = 0;
-    ics += (uint32_t)s.n_slots;
-    count[d.stream_id]++;
-    const uint32_t sz = frame_pcm_bytes(e, s);
-    b->frame_pcm_size[i] = sz;
-    if (pcm_offsets) {
-      if (pcm_offsets[i] & 3u) { e->set_error("pcm offsets must be 4-byte aligned"); return fail(JAADB_E_INVALID); }
-      b->pcm_off[i] = pcm_offsets[i];
-    } else {
-      b->pcm_off[i] = pcm_pos;
-      pcm_pos += sz;
-    }
-    pcm_end = std::max(pcm_end, b->pcm_off[i] + sz);
-  }
-  b->n_ics = ics;
-  b->pcm_bytes = pcm_end;
-  // runs, grouped by channel-slot count so every launch has a uniform block size
-  std::vector<uint32_t> run_of(e->streams.size(), 0xFFFFFFFFu);
-  for (int nch = 1; nch <= kMaxChannels; ++nch) {
-    jaadb_batch::Group g{nch, (uint32_t)b->runs.size(), 0};
-    for (size_t s = 0; s < e->streams.size(); ++s) {
-      if (!count[s] || e->streams[s].n_slots != nch) continue;
-      RunDev r;
-      memset(&r, 0, sizeof r);
-      r.stream_slot = (int32_t)s;
-      r.count = count[s];
-      r.layout = (uint8_t)e->streams[s].chan_cfg;
-      r.sf_index = (uint8_t)e->streams[s].sf_index;
-      r.mono_dup = (e->streams[s].chan_cfg == 1) ? 1 : 0;
-      run_of[s] = (uint32_t)b->runs.size();
-      b->runs.push_back(r);
-      g.n_runs++;
-    }
-    if (g.n_runs) b->groups.push_back(g);
-  }
-  uint32_t acc = 0;
-  for (auto& r : b->runs) { r.first = acc; acc += r.count; }
-  b->run_frames.resize(n);
-  std::vector<uint32_t> fill(b->runs.size(), 0);
-  for (uint32_t i = 0; i < n; ++i) {
-    uint32_t r = run_of[fd[i].stream_id];
-    b->run_frames[b->runs[r].first + fill[r]++] = RunFrameDev{i, b->frames[i].ics_base};
-  }
+  int rc = layout_pcm(e, fd, n, pcm_offsets, b->pcm_off, b->frame_pcm_size, &b->pcm_bytes);
+  if (rc) return fail(rc);
+  FrameIndex ix;
+  rc = index_frames(e, fd, n, blob_bytes, ix);
+  if (rc) return fail(rc);
+  b->frames.swap(ix.frames);
+  b->runs.swap(ix.runs);
+  b->run_frames.swap(ix.run_frames);
+  for (const auto& g : ix.groups) b->groups.push_back(jaadb_batch::Group{g.nch, g.first_run, g.n_runs});
+  b->n_ics = ix.n_ics;
+  const uint32_t ics = ix.n_ics;
   // device side
   cudaError_t ce = cudaSuccess;
   auto chk = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
@@ -649,30 +773,9 @@ int jaadb_batch_decode(jaadb_batch* b) {
   uint32_t launches = 0;
   if (b->n_frames == 0) { b->decoded = true; return JAADB_OK; }
   if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[0], e->stream));
-  {
-    const int threads = 128;
-    const int blocks = (int)((b->n_frames + threads - 1) / threads);
-    k1_parse_kernel<<<blocks, threads, e->lut_entries * 4, e->stream>>>(
-        b->d_blob.p, b->d_frames.p, b->n_frames, b->d_fside.p, b->d_iside.p, b->d_q.p, e->tables, e->d_layouts);
-    ++launches;
-  }
-  if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[1], e->stream));
-  for (const auto& g : b->groups) {
-    const int threads = g.nch * kThreadsPerChannel;
-    const int out_ch = (g.nch == 1) ? 2 : g.nch;
-    const size_t smem = k2_smem_bytes(g.nch, out_ch);
-    const RunDev* runs = b->d_runs.p + g.first_run;
-    float* tap = (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) ? b->d_spec_tap.p : nullptr;
-#define LAUNCH_K2(FMT)                                                                                         \
-  k2_filterbank_kernel<FMT><<<g.n_runs, threads, smem, e->stream>>>(                                           \
-      runs, b->d_run_frames.p, b->d_fside.p, b->d_iside.p, b->d_q.p, e->d_overlap, e->d_sstate,                \
-      b->d_pcm.p, b->d_pcm_off.p, b->d_pcm_bytes.p, tap, e->tables, e->d_layouts, g.nch)
-    if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K2(0);
-    else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K2(1);
-    else LAUNCH_K2(2);
-#undef LAUNCH_K2
-    ++launches;
-  }
+  launch_decode(e, b->groups.data(), b->groups.size(), b->n_frames, b->d_blob.p, b->d_frames.p, b->d_fside.p, b->d_iside.p,
+                b->d_q.p, b->d_runs.p, b->d_run_frames.p, b->d_pcm.p, b->d_pcm_off.p, b->d_pcm_bytes.p,
+                (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) ? b->d_spec_tap.p : nullptr, prof ? e->ev[1] : nullptr, &launches);
   if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[2], e->stream));
   CUDA_TRY(e, cudaGetLastError());
   b->timings.launches = launches;
@@ -739,17 +842,146 @@ void jaadb_batch_destroy(jaadb_batch* b) {
   delete b;
 }
 
+// One-call decode, pipelined.  The frame array is cut into chunks of consecutive frames; per chunk: index on the
+// host, upload descriptors, K1, K2 into one of two device PCM buffers, then the chunk's PCM byte range and result
+// words go back over PCIe on a second stream while the next chunk is decoded.  Frames of a stream stay in array
+// order across chunks because chunks run in order on one stream and the overlap state lives in HBM in between.
 int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const jaadb_frame_desc* frames,
                  uint32_t n_frames, void* pcm_out, uint64_t pcm_capacity, const uint64_t* pcm_offsets,
                  jaadb_frame_result* results) {
-  jaadb_batch* b = nullptr;
-  int rc = jaadb_batch_create(e, frames, n_frames, blob_bytes, pcm_offsets, &b);
+  if (!e || (n_frames && !frames) || (!blob && blob_bytes)) return JAADB_E_INVALID;
+  cudaSetDevice(e->opts.device);
+  if (n_frames == 0) return JAADB_OK;
+  auto& W = e->ws;
+  std::vector<uint64_t>& off = e->scratch_off;
+  std::vector<uint32_t>& size = e->scratch_size;
+  uint64_t pcm_total = 0;
+  int rc = layout_pcm(e, frames, n_frames, pcm_offsets, off, size, &pcm_total);
   if (rc) return rc;
-  rc = jaadb_batch_upload(b, blob, blob_bytes);
-  if (!rc) rc = jaadb_batch_decode(b);
-  if (!rc) rc = jaadb_batch_download(b, pcm_out, pcm_capacity, results);
-  jaadb_batch_destroy(b);
-  return rc;
+  if (pcm_out && pcm_capacity < pcm_total) { e->set_error("pcm buffer too small"); return JAADB_E_CAPACITY; }
+
+  // chunking: ~128 Ki frames per chunk, unless the caller's PCM placement is not monotonic over chunks
+  uint32_t chunk = e->opts.chunk_frames ? e->opts.chunk_frames : 131072u;
+  if (n_frames <= chunk + chunk / 2) chunk = n_frames;
+  struct Range { uint32_t i0, i1; uint64_t lo, hi; };
+  std::vector<Range> ranges;
+  for (uint32_t i0 = 0; i0 < n_frames; i0 += chunk) {
+    Range r{i0, std::min(n_frames, i0 + chunk), ~0ull, 0};
+    for (uint32_t i = r.i0; i < r.i1; ++i) { r.lo = std::min(r.lo, off[i]); r.hi = std::max(r.hi, off[i] + size[i]); }
+    ranges.push_back(r);
+  }
+  bool monotonic = true;
+  for (size_t k = 1; k < ranges.size(); ++k) monotonic = monotonic && ranges[k].lo >= ranges[k - 1].hi;
+  if (!monotonic) { ranges.assign(1, Range{0, n_frames, 0, pcm_total}); chunk = n_frames; }
+  uint64_t max_pcm = 16;
+  for (const auto& r : ranges) max_pcm = std::max(max_pcm, r.hi - r.lo);
+
+  // workspace
+  if (!W.copy_stream) {
+    CUDA_TRY(e, cudaStreamCreateWithFlags(&W.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(e, cudaEventCreateWithFlags(&W.k_done[i], cudaEventDisableTiming));
+      CUDA_TRY(e, cudaEventCreateWithFlags(&W.d2h_done[i], cudaEventDisableTiming));
+      CUDA_TRY(e, cudaEventCreateWithFlags(&W.desc_done[i], cudaEventDisableTiming));
+    }
+  }
+  size_t max_ics = 0;
+  {
+    // worst case channel slots per frame in this call
+    int slots = 1;
+    for (uint32_t i = 0; i < n_frames; ++i) slots = std::max(slots, e->streams[frames[i].stream_id].n_slots);
+    max_ics = (size_t)chunk * slots;
+  }
+  cudaError_t ce = cudaSuccess;
+  auto chk = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
+  chk(W.blob.ensure(blob_bytes + 64));
+  chk(W.pcm[0].ensure(max_pcm));
+  if (ranges.size() > 1) chk(W.pcm[1].ensure(max_pcm));
+  chk(W.frames.ensure(chunk));
+  chk(W.fside.ensure(n_frames));
+  chk(W.pcm_bytes.ensure(n_frames));
+  chk(W.iside.ensure(max_ics));
+  chk(W.q.ensure(max_ics * 1024));
+  chk(W.runs.ensure(e->streams.size()));
+  chk(W.run_frames.ensure(chunk));
+  chk(W.pcm_off.ensure(n_frames));
+  if (ce == cudaSuccess && (W.h_chunk_cap < chunk || W.h_runs_cap < e->streams.size())) {
+    for (int i = 0; i < 2; ++i) {
+      if (W.h_frames[i]) cudaFreeHost(W.h_frames[i]);
+      if (W.h_run_frames[i]) cudaFreeHost(W.h_run_frames[i]);
+      if (W.h_runs[i]) cudaFreeHost(W.h_runs[i]);
+      W.h_frames[i] = nullptr; W.h_run_frames[i] = nullptr; W.h_runs[i] = nullptr;
+    }
+    W.h_chunk_cap = W.h_runs_cap = 0;
+    const size_t cc = std::max<size_t>(chunk, W.h_chunk_cap), rr = e->streams.size();
+    for (int i = 0; i < 2; ++i) {
+      chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_frames[i]), sizeof(FrameDev) * cc, cudaHostAllocDefault));
+      chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_run_frames[i]), sizeof(RunFrameDev) * cc, cudaHostAllocDefault));
+      chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_runs[i]), sizeof(RunDev) * rr, cudaHostAllocDefault));
+    }
+    if (ce == cudaSuccess) { W.h_chunk_cap = cc; W.h_runs_cap = rr; }
+  }
+  if (ce == cudaSuccess && W.h_cap < n_frames) {
+    if (W.h_fside) cudaFreeHost(W.h_fside);
+    if (W.h_pcm_bytes) cudaFreeHost(W.h_pcm_bytes);
+    W.h_fside = nullptr; W.h_pcm_bytes = nullptr; W.h_cap = 0;
+    chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_fside), sizeof(FrameSide) * (size_t)n_frames, cudaHostAllocDefault));
+    chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_pcm_bytes), sizeof(uint32_t) * (size_t)n_frames, cudaHostAllocDefault));
+    if (ce == cudaSuccess) W.h_cap = n_frames;
+  }
+  if (ce != cudaSuccess) { e->set_error(std::string("workspace allocation: ") + cudaGetErrorString(ce)); return JAADB_E_NOMEM; }
+
+  // PCM placement of every frame and the compressed frames (one copy each: frames of a chunk may sit anywhere
+  // in the caller's blob)
+  CUDA_TRY(e, cudaMemcpyAsync(W.pcm_off.p, off.data(), sizeof(uint64_t) * n_frames, cudaMemcpyHostToDevice, e->stream));
+  if (blob_bytes) CUDA_TRY(e, cudaMemcpyAsync(W.blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(W.blob.p + blob_bytes, 0, 64, e->stream));
+
+  FrameIndex& ix = e->scratch_ix;
+  uint32_t launches = 0;
+  for (size_t k = 0; k < ranges.size(); ++k) {
+    const Range& r = ranges[k];
+    const uint32_t n = r.i1 - r.i0;
+    const int pb = (int)(k & 1);
+    if (k >= 2) CUDA_TRY(e, cudaEventSynchronize(W.desc_done[pb]));   // staging slot pb has been consumed
+    ix.frames_out = W.h_frames[pb];
+    ix.run_frames_out = W.h_run_frames[pb];
+    rc = index_frames(e, frames + r.i0, n, blob_bytes, ix);
+    if (rc) { cudaStreamSynchronize(e->stream); cudaStreamSynchronize(W.copy_stream); return rc; }
+    memcpy(W.h_runs[pb], ix.runs.data(), sizeof(RunDev) * ix.runs.size());
+    // the device descriptor buffers are still being read by the previous chunk's kernels: stream order protects them
+    CUDA_TRY(e, cudaMemcpyAsync(W.frames.p, W.h_frames[pb], sizeof(FrameDev) * n, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(W.runs.p, W.h_runs[pb], sizeof(RunDev) * ix.runs.size(), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(W.run_frames.p, W.h_run_frames[pb], sizeof(RunFrameDev) * n, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaEventRecord(W.desc_done[pb], e->stream));
+    if (k >= 2) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, W.d2h_done[pb], 0));   // PCM buffer pb is free again
+    launch_decode(e, ix.groups.data(), ix.groups.size(), n, W.blob.p, W.frames.p, W.fside.p + r.i0, W.iside.p, W.q.p,
+                  W.runs.p, W.run_frames.p, W.pcm[pb].p - r.lo, W.pcm_off.p + r.i0, W.pcm_bytes.p + r.i0, nullptr, nullptr, &launches);
+    CUDA_TRY(e, cudaGetLastError());
+    CUDA_TRY(e, cudaEventRecord(W.k_done[pb], e->stream));
+    CUDA_TRY(e, cudaStreamWaitEvent(W.copy_stream, W.k_done[pb], 0));
+    if (pcm_out && r.hi > r.lo)
+      CUDA_TRY(e, cudaMemcpyAsync(static_cast<uint8_t*>(pcm_out) + r.lo, W.pcm[pb].p, r.hi - r.lo, cudaMemcpyDeviceToHost, W.copy_stream));
+    if (results) {
+      CUDA_TRY(e, cudaMemcpyAsync(W.h_fside + r.i0, W.fside.p + r.i0, sizeof(FrameSide) * n, cudaMemcpyDeviceToHost, W.copy_stream));
+      CUDA_TRY(e, cudaMemcpyAsync(W.h_pcm_bytes + r.i0, W.pcm_bytes.p + r.i0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, W.copy_stream));
+    }
+    CUDA_TRY(e, cudaEventRecord(W.d2h_done[pb], W.copy_stream));
+  }
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(W.copy_stream));
+  if (results) {
+    for (uint32_t i = 0; i < n_frames; ++i) {
+      const StreamHost& s = e->streams[frames[i].stream_id];
+      jaadb_frame_result& r = results[i];
+      r.status = W.h_fside[i].status;
+      r.pcm_bytes = W.h_pcm_bytes[i];
+      r.channels = r.status ? 0 : (uint16_t)s.out_channels;
+      r.sample_length = r.status ? 0 : (uint16_t)s.sample_length;
+      r.sample_rate = (uint32_t)s.sample_rate;
+    }
+  }
+  return JAADB_OK;
 }
 
 int jaadb_batch_tap(jaadb_batch* b, uint32_t frame, uint32_t ch, int16_t* q, int16_t* sfidx, uint8_t* sfbcb, float* spec,

@@ -25,9 +25,10 @@ def _ptr(a):
 
 
 class Engine:
-    def __init__(self, device: int = 0, max_streams: int = 4096, pcm_format: int = PCM_S16LE, flags: int = 0):
+    def __init__(self, device: int = 0, max_streams: int = 4096, pcm_format: int = PCM_S16LE, flags: int = 0,
+                 chunk_frames: int = 0):
         self._lib = _lib.load()
-        opts = Options(device, max_streams, pcm_format, 0, flags, (C.c_uint32 * 3)(0, 0, 0))
+        opts = Options(device, max_streams, pcm_format, 0, flags, chunk_frames, (C.c_uint32 * 2)(0, 0))
         h = C.c_void_p()
         rc = self._lib.jaadb_engine_create(C.byref(opts), C.byref(h))
         if rc != 0:

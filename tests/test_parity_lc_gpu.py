@@ -206,3 +206,32 @@ def test_engine_reproduces_committed_golden(name):
                 seen[s] += 1
         b.close()
         eng.close()
+
+
+def test_one_call_decode_pipelines_chunks_and_honours_pcm_offsets():
+    """jaadb_decode cuts the frame array into chunks (here 10 frames, so chunks straddle frames of all streams and
+    leave a remainder) and overlaps PCM download with the next chunk; caller-placed, non-monotonic PCM offsets take
+    the single-range path.  Both must equal the oracle frame by frame."""
+    cfg = gen.config(2, n_frames=23, p_transient=0.3)
+    wl = Workload(cfg, 5, base_seed=2024, with_truth=False)
+    decs = wl.oracle_decoders()
+    per = 2 * 1024 * 2
+    ref = {}
+    for f in range(cfg.n_frames):
+        for s in range(5):
+            ref[(s, f)] = decs[s].decode_frame(wl.frame_bytes(s, f))["s16"]
+    for mode in ("packed", "reversed"):
+        eng = Engine(max_streams=8, pcm_format=PCM_S16LE, chunk_frames=10)
+        ids = [eng.open_adts(*wl.hdr) for _ in range(5)]
+        frames, index = wl.frame_table(ids)
+        n = len(frames)
+        offs = None
+        if mode == "reversed":
+            offs = (np.arange(n)[::-1] * per).astype(np.uint64)
+        pcm, res = eng.decode(wl.blob, frames, pcm_out=np.zeros(n * per, np.uint8), pcm_offsets=offs)
+        assert (res["status"] == 0).all() and (res["pcm_bytes"] == per).all()
+        for i, (s, f) in enumerate(index):
+            o = i * per if offs is None else int(offs[i])
+            got = pcm[o:o + per].view(np.int16).reshape(1024, 2)
+            assert np.array_equal(got, ref[(s, f)]), (mode, s, f)
+        eng.close()
