@@ -42,6 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; cannot build libjaadb200.so")
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "jaadb_engine.cu")]
+    extra = os.environ.get("JAADB200_NVCC_DEFS", "").split()   # tuning experiments only, e.g. -DK2_STEREO_MIN_BLOCKS=6
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "jaadb_engine.cu")]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB

@@ -20,6 +20,10 @@
 #include "k1_parse.cuh"
 #include "k2_filterbank.cuh"
 
+#ifndef K2_STEREO_MIN_BLOCKS
+#define K2_STEREO_MIN_BLOCKS 4
+#endif
+
 namespace T = ::jaad_tables;
 using namespace jaadb;
 
@@ -471,9 +475,9 @@ void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_gr
                    const RunDev* d_runs, const RunFrameDev* d_run_frames, uint8_t* d_pcm, const uint64_t* d_pcm_off,
                    uint32_t* d_pcm_bytes, float* d_tap, cudaEvent_t after_k1, uint32_t* launches) {
   {
-    const int threads = 128;
+    const int threads = kK1Threads;
     const int blocks = (int)((n_frames + threads - 1) / threads);
-    k1_parse_kernel<<<blocks, threads, e->lut_entries * 4, e->stream>>>(d_blob, d_frames, n_frames, d_fside, d_iside, d_q,
+    k1_parse_kernel<<<blocks, threads, k1_smem_bytes(e->lut_entries), e->stream>>>(d_blob, d_frames, n_frames, d_fside, d_iside, d_q,
                                                                         e->tables, e->d_layouts);
     ++*launches;
   }
@@ -484,14 +488,17 @@ void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_gr
     const int out_ch = (g.nch == 1) ? 2 : g.nch;
     const size_t smem = k2_smem_bytes(g.nch, out_ch);
     const RunDev* runs = d_runs + g.first_run;
+#define K2_ARGS runs, d_run_frames, d_fside, d_iside, d_q, e->d_overlap, e->d_sstate, d_pcm, d_pcm_off, d_pcm_bytes, d_tap, e->tables, e->d_layouts, g.nch
 #define LAUNCH_K2(FMT)                                                                                              \
-  k2_filterbank_kernel<FMT><<<g.n_runs, threads, smem, e->stream>>>(runs, d_run_frames, d_fside, d_iside, d_q,     \
-                                                                    e->d_overlap, e->d_sstate, d_pcm, d_pcm_off,   \
-                                                                    d_pcm_bytes, d_tap, e->tables, e->d_layouts, g.nch)
+  do {                                                                                                              \
+    if (threads <= 128) k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS><<<g.n_runs, threads, smem, e->stream>>>(K2_ARGS); \
+    else k2_filterbank_kernel<FMT, 512, 1><<<g.n_runs, threads, smem, e->stream>>>(K2_ARGS);                        \
+  } while (0)
     if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K2(0);
     else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K2(1);
     else LAUNCH_K2(2);
 #undef LAUNCH_K2
+#undef K2_ARGS
     ++*launches;
   }
 }
@@ -550,11 +557,13 @@ int jaadb_engine_create(const jaadb_options* opts, jaadb_engine** out) {
   if (cudaMalloc(reinterpret_cast<void**>(&e->d_sstate), sizeof(StreamState) * (size_t)opts->max_streams) != cudaSuccess)
     return fail(JAADB_E_NOMEM);
   // opt in to the shared-memory sizes the kernels need
-  cudaFuncSetAttribute(k1_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e->lut_entries * 4));
+  cudaFuncSetAttribute(k1_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(e->lut_entries));
   const int k2max = (int)k2_smem_bytes(kMaxChannels, kMaxChannels);
-  cudaFuncSetAttribute(k2_filterbank_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max);
-  cudaFuncSetAttribute(k2_filterbank_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max);
-  cudaFuncSetAttribute(k2_filterbank_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max);
+#define K2_ATTR(FMT)                                                                                                     \
+  cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max);             \
+  cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max)
+  K2_ATTR(0); K2_ATTR(1); K2_ATTR(2);
+#undef K2_ATTR
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) return fail(JAADB_E_CUDA);
   *out = e;
   return JAADB_OK;

@@ -59,6 +59,9 @@ struct BitReader {
     widx = pos >> 5;
     w0 = load(widx);
     w1 = load(widx + 1);
+#pragma unroll
+    for (uint32_t k = 8; k <= 64; k += 8)
+      if (widx + k <= last_word) asm volatile("prefetch.global.L2 [%0];" ::"l"(words + widx + k));
   }
   // the next 32 bits, left aligned
   __device__ __forceinline__ uint32_t peek() {
@@ -67,6 +70,9 @@ struct BitReader {
       w0 = (wi == widx + 1) ? w1 : load(wi);
       w1 = load(wi + 1);
       widx = wi;
+      // one 32-byte sector, 256 bytes ahead of the read position, per sector consumed: the compressed frame
+      // streams through L2 ahead of the serial Huffman walk instead of stalling it on HBM
+      if ((wi & 7u) == 0u && wi + 64u <= last_word) asm volatile("prefetch.global.L2 [%0];" ::"l"(words + wi + 64u));
     }
     return __funnelshift_l(w1, w0, pos & 31u);
   }
@@ -148,6 +154,11 @@ __device__ __forceinline__ void store_ics_header(IcsSide* s, const IcsInfoRegs& 
 // Bands with codebook 0 / 13 / 14 / 15 are not written and never read.
 // ---------------------------------------------------------------------------------------------------------
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
+constexpr int kSwbTableEntries = 12 * 53 + 12 * 17 + 4;   // int16 entries (+4 keeps what follows 8-byte aligned)
+constexpr int kK1Threads = 256;
+__host__ __device__ constexpr size_t k1_smem_bytes(uint32_t lut_entries) {
+  return (size_t)lut_entries * 4 + kSwbTableEntries * 2 + (size_t)(kMaxSfbEntries + 8) * kK1Threads;
+}
 
 __device__ __forceinline__ void fail(int& status, bool& flag, int code) { status = code; flag = false; }
 
@@ -155,8 +166,10 @@ __device__ __forceinline__ void fail(int& status, bool& flag, int code) { status
 // `in` holds the shared ics_info when common_window is set.  Returns with status updated.
 __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& status, const uint32_t* __restrict__ lut,
                                                const TablesDev& T, int sf_index, bool common, IcsInfoRegs& in,
-                                               IcsSide* side, int16_t* __restrict__ q, int ms_mask) {
-  uint8_t cb[kMaxSfbEntries + 8];
+                                               IcsSide* side, int16_t* __restrict__ q, int ms_mask,
+                                               uint8_t* __restrict__ cb_lane, const int16_t* __restrict__ s_swb) {
+  // codebook per (group, sfb) of this lane's ICS: shared memory, one byte column per thread
+#define CB(i) cb_lane[(i) * kK1Threads]
   int global_gain = 0;
   if (go) {
     global_gain = (int)br.read(8);
@@ -193,7 +206,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
           if (br.overrun()) fail(status, sec, JAADB_ST_EOS);
           else if (end > max_sfb) fail(status, sec, JAADB_ST_TOO_MANY_BANDS);
           else {
-            for (int idx = g * max_sfb + k; k < end; ++k, ++idx) cb[idx] = (uint8_t)c;
+            for (int idx = g * max_sfb + k; k < end; ++k, ++idx) CB(idx) = (uint8_t)c;
             if (k == max_sfb) { k = 0; if (++g == ngroups) sec = false; }
           }
         }
@@ -212,7 +225,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
     bool sfa = go && nbands > 0;
     while (__any_sync(kFullMask, sfa)) {
       if (sfa) {
-        const int c = cb[idx];
+        const int c = CB(idx);
         uint32_t out = 0xFFFFu;
         if (c != 0) {
           if (c == 13 && noise_flag) {
@@ -302,13 +315,13 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
   if (go) {
     uint32_t* dst = reinterpret_cast<uint32_t*>(side->sfb_cb);
     for (int i = 0; i < (nbands + 3) / 4; ++i)
-      dst[i] = (uint32_t)cb[4 * i] | ((uint32_t)cb[4 * i + 1] << 8) | ((uint32_t)cb[4 * i + 2] << 16) | ((uint32_t)cb[4 * i + 3] << 24);
+      dst[i] = (uint32_t)CB(4 * i) | ((uint32_t)CB(4 * i + 1) << 8) | ((uint32_t)CB(4 * i + 2) << 16) | ((uint32_t)CB(4 * i + 3) << 24);
   }
   __syncwarp();
 
   // ---- spectral_data (ICStream.java:222-275, Huffman.java:56-84): one codeword per lane per iteration
   {
-    const int16_t* __restrict__ swb = is_short ? (T.swb_short + sf_index * 17) : (T.swb_long + sf_index * 53);
+    const int16_t* __restrict__ swb = is_short ? (s_swb + 12 * 53 + sf_index * 17) : (s_swb + sf_index * 53);
     const int swb_count = is_short ? T.swb_short_count[sf_index] : T.swb_long_count[sf_index];
     int idx = 0, sfb = 0, g = 0, gbase = 0, glen = in.glen(0);
     int rem = 0, pos = 0, hcb = 0;
@@ -319,7 +332,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
         // open the next scalefactor band
         if (idx == nbands) sp = false;
         else {
-          hcb = cb[idx];
+          hcb = CB(idx);
           if (sfb > swb_count) fail(status, sp, JAADB_ST_ARRAY_BOUNDS);          // offsets[sfb+1] past the table
           else if (hcb == 0 || hcb >= 14) {
             if (sfb == swb_count) fail(status, sp, JAADB_ST_ARRAY_BOUNDS);       // Arrays.fill with a negative range
@@ -407,14 +420,20 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
   }
   if (go) store_ics_header(side, in, 1, 1, ms_mask, common ? 1 : 0);
   __syncwarp();
+#undef CB
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kK1Threads)
 k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ frames, uint32_t n_frames,
                 FrameSide* __restrict__ fside, IcsSide* __restrict__ iside_all, int16_t* __restrict__ q_all, TablesDev T,
                 const LayoutDev* __restrict__ layouts) {
   extern __shared__ uint32_t s_lut[];
+  // shared memory: Huffman LUTs | SWB offset tables (long [12][53], short [12][17]) | per-lane codebook columns
+  int16_t* s_swb = reinterpret_cast<int16_t*>(s_lut + T.huff_lut_entries);
+  uint8_t* s_cb = reinterpret_cast<uint8_t*>(s_swb + kSwbTableEntries);
   for (uint32_t i = threadIdx.x; i < T.huff_lut_entries; i += blockDim.x) s_lut[i] = T.huff_lut[i];
+  for (int i = threadIdx.x; i < 12 * 53; i += blockDim.x) s_swb[i] = T.swb_long[i];
+  for (int i = threadIdx.x; i < 12 * 17; i += blockDim.x) s_swb[12 * 53 + i] = T.swb_short[i];
   __syncthreads();
   const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = f < n_frames;
@@ -543,7 +562,8 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
       }
     }
     __syncwarp();
-    parse_ics_warp(go, br, status, s_lut, T, sf_index, common, in, iside + ch, qbase + ch * 1024, ms_mask);
+    parse_ics_warp(go, br, status, s_lut, T, sf_index, common, in, iside + ch, qbase + ch * 1024, ms_mask,
+                   s_cb + threadIdx.x, s_swb);
     if (go) {
       if (status) active = false;
       else if (is_cpe_left) pend_r = true;

@@ -157,8 +157,8 @@ __device__ __forceinline__ void channel_barrier(int c) {
   asm volatile("bar.sync %0, 64;" ::"r"(c + 1) : "memory");
 }
 
-template <int PCM_FORMAT>
-__global__ void __launch_bounds__(512)
+template <int PCM_FORMAT, int MAX_THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
 k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restrict__ run_frames,
                      const FrameSide* __restrict__ fside, const IcsSide* __restrict__ iside,
                      const int16_t* __restrict__ qall, float* __restrict__ overlap_all, StreamState* __restrict__ sstate,
@@ -198,6 +198,10 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
   }
   const float* tw512 = s_fft_tw;
   const float* tw64 = s_fft_tw + 512;
+  // windows and MDCT twiddles stay in global memory (L1-resident, 13.8 KB): staging them in shared memory was measured
+  // to give nothing and costs a resident CTA per SM
+  const float2* mdct_long2 = reinterpret_cast<const float2*>(T.mdct_long);
+  const float2* mdct_short2 = reinterpret_cast<const float2*>(T.mdct_short);
 
   // persistent state in: overlap + current window shapes
   float* g_ovl = overlap_all + ((size_t)run.stream_slot * kMaxChannels + c) * 1024;
@@ -229,12 +233,13 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
   if (tid < side_vecs) side_pf = reinterpret_cast<const uint4*>(iside + cur.ics_base)[tid];
   uint4 qA = *reinterpret_cast<const uint4*>(qall + ((size_t)cur.ics_base + chA) * 1024 + iA);
   uint4 qB = *reinterpret_cast<const uint4*>(qall + ((size_t)cur.ics_base + chB) * 1024 + iB);
+  uint64_t poff_pf = pcm_off[cur.frame];
   __syncthreads();
 
   for (uint32_t it = 0; it < run.count; ++it) {
     const uint32_t f = cur.frame;
     const uint32_t ics_base = cur.ics_base;
-    const uint64_t poff = pcm_off[f];
+    const uint64_t poff = poff_pf;
     const bool have_next = it + 1 < run.count;
     RunFrameDev nxt = cur;
     if (have_next) nxt = run_frames[run.first + it + 1];
@@ -310,6 +315,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
       if (tid < side_vecs) side_pf = reinterpret_cast<const uint4*>(iside + nxt.ics_base)[tid];
       qA = *reinterpret_cast<const uint4*>(qall + ((size_t)nxt.ics_base + chA) * 1024 + iA);
       qB = *reinterpret_cast<const uint4*>(qall + ((size_t)nxt.ics_base + chB) * 1024 + iB);
+      poff_pf = pcm_off[nxt.frame];
     }
     cur = nxt;
     __syncthreads();
@@ -330,7 +336,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
           const int k = kb + 64 * brev3(j);
           const float x0 = my_spec[spec_addr(2 * k)];
           const float x1 = my_spec[spec_addr(1023 - 2 * k)];
-          const float2 cs = __ldg(reinterpret_cast<const float2*>(T.mdct_long) + k);
+          const float2 cs = __ldg(mdct_long2 + k);
           a[j].im = (x0 * cs.x) + (x1 * cs.y);
           a[j].re = (x1 * cs.x) - (x0 * cs.y);
         }
@@ -342,7 +348,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
           const int k = kb + 8 * brev3(j);                     // bitrev6(8*(t&7)+j)
           const float x0 = my_spec[spec_addr(128 * w + 2 * k)];
           const float x1 = my_spec[spec_addr(128 * w + 127 - 2 * k)];
-          const float2 cs = __ldg(reinterpret_cast<const float2*>(T.mdct_short) + k);
+          const float2 cs = __ldg(mdct_short2 + k);
           a[j].im = (x0 * cs.x) + (x1 * cs.y);
           a[j].re = (x1 * cs.x) - (x0 * cs.y);
         }
@@ -436,7 +442,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int n = t + 64 * j;
-        const float2 cs = __ldg(reinterpret_cast<const float2*>(T.mdct_long) + n);
+        const float2 cs = __ldg(mdct_long2 + n);
         const float t0 = a[j].re, t1 = a[j].im;
         bim[n] = (t1 * cs.x) + (t0 * cs.y);
         bre[n] = (t0 * cs.x) - (t1 * cs.y);
@@ -446,7 +452,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int nl = col + 8 * j;         // index inside the 64-point FFT of window blk
-        const float2 cs = __ldg(reinterpret_cast<const float2*>(T.mdct_short) + nl);
+        const float2 cs = __ldg(mdct_short2 + nl);
         const float t0 = a[j].re, t1 = a[j].im;
         bim[64 * blk + nl] = (t1 * cs.x) + (t0 * cs.y);
         bre[64 * blk + nl] = (t0 * cs.x) - (t1 * cs.y);
@@ -458,10 +464,10 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
     // i = 2t + 128j, i+1 (j = 0..7): the MDCT reorder (MDCT.java:60-80) then reads mirrored positions of the two
     // planes without any per-lane case split, and the overlap goes back as float2.
     {
-      const float* LWp = T.win_long[shape_prev];
-      const float* LW = T.win_long[shape_cur];
-      const float* SWp = T.win_short[shape_prev];
-      const float* SW = T.win_short[shape_cur];
+      const float* __restrict__ LWp = T.win_long[shape_prev];
+      const float* __restrict__ LW = T.win_long[shape_cur];
+      const float* __restrict__ SWp = T.win_short[shape_prev];
+      const float* __restrict__ SW = T.win_short[shape_cur];
       uint8_t* dst = pcm + poff;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
