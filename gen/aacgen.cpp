@@ -20,6 +20,7 @@
 #include "../jaadec_b200/csrc/generated/jaad_tables_host.h"
 
 namespace T = ::jaad_tables;
+static const int T_SF_FREQ[12] = {96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000};
 
 namespace {
 
@@ -460,6 +461,8 @@ void writeIcs(Ctx& c, BitWriter& bw, const IcsPlan& p, bool commonWindow) {
   }
 }
 
+#include "aacgen_sbr.inc"
+
 }  // namespace
 
 extern "C" {
@@ -488,7 +491,11 @@ struct jg_truth {
   uint8_t* sfbcb;    // [n_frames][n_ics][120]
   int32_t* info;     // [n_frames][n_ics][16]: present, ws, shape, (unused), maxSfb, ngroups, glen[8], msMask, common
   uint8_t* msused;   // [n_frames][n_elements][128]
+  int32_t* sbr;      // [n_frames][n_ics][480] SBR streams only: L_E, L_Q, frame class, pointer, t_E[6], f[6], amp_res,
+                     //   coupling, (pad to 32), E[5][64], Q[2][64] as a decoder reconstructs them (aacgen_sbr.inc)
 };
+
+int jg_sbr_truth_ints(void) { return kSbrTruthInts; }
 
 int jg_ics_per_frame(int chan_cfg) { return chan_cfg == 6 ? 6 : chan_cfg; }
 int jg_elements_per_frame(int chan_cfg) { return chan_cfg == 6 ? 4 : 1; }
@@ -509,12 +516,16 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
   else if (cfg->chan_cfg == 6) els = {{0, 0, 1, false}, {1, 0, 2, false}, {1, 1, 2, false}, {3, 0, 1, true}};
   else return -2;
   std::vector<int> wsState(els.size(), 0);  // 0 long, 1 start sent -> shorts, 2 in shorts
+  std::vector<SbrElemState> sbrState(els.size());
+  const int sbrSrIndex = cfg->sf_index - 3, sbrSrFreq = cfg->sf_index >= 3 ? T_SF_FREQ[cfg->sf_index - 3] : 0;
+  if (cfg->sbr_mode && (cfg->sf_index < 3 || cfg->sbr_mode > 1)) return -3;  // PS payloads: aacgen_ps.inc, not in this build
   const double targetRms = cfg->target_rms > 0 ? cfg->target_rms : 2500.0;
   int64_t pos = 0;
   for (int f = 0; f < cfg->n_frames; ++f) {
     BitWriter bw;
     int icsIdx = 0;
     int payloadBudget = cfg->target_bytes * 8 - 3 - 8;
+    if (cfg->sbr_mode) payloadBudget -= (cfg->chan_cfg == 2 ? 60 : 36) * 8;   // room for the SBR fill element
     for (size_t ei = 0; ei < els.size(); ++ei) {
       const El& el = els[ei];
       // window sequence state machine (per element): ONLY_LONG -> LONG_START -> EIGHT_SHORT+ -> LONG_STOP -> ONLY_LONG
@@ -551,6 +562,9 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
             in[14] = 0; in[15] = 0;
           }
         }
+        if (cfg->sbr_mode && !el.lfe)
+          sbrEmitFill(c, bw, sbrState[ei], false, f, sbrSrIndex, sbrSrFreq,
+                      (truth && truth->sbr) ? truth->sbr + ((size_t)f * nIcs + icsIdx) * kSbrTruthInts : nullptr, nullptr);
         icsIdx += 1;
       } else {
         bool common = c.rng.chance(cfg->p_common_window);
@@ -630,6 +644,9 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
           }
           if (truth->msused) memcpy(truth->msused + ((size_t)f * nEl + ei) * 128, ms, 128);
         }
+        if (cfg->sbr_mode)
+          sbrEmitFill(c, bw, sbrState[ei], true, f, sbrSrIndex, sbrSrFreq,
+                      (truth && truth->sbr) ? truth->sbr + ((size_t)f * nIcs + icsIdx) * kSbrTruthInts : nullptr, nullptr);
         icsIdx += 2;
       }
     }

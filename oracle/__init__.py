@@ -38,6 +38,7 @@ def lib():
         _lib.jo_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.jo_tap_ics.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.jo_tap_msused.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.jo_tap_sbr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib.jo_adts_index.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.jo_decode_streams.restype = C.c_double
         _lib.jo_decode_streams.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
@@ -109,6 +110,15 @@ class Decoder:
         if r < 0:
             return None
         return dict(type=r, q=q, sfidx=sf, sfbcb=cb, spec=spec, info=info)
+
+    def tap_sbr(self, el: int, ch: int):
+        """SBR state of the frame just decoded (None if the element carries no SBR): dict(ints[480], extra[16],
+        e_orig[5,64] float32, q_div[2,64] float32); ints uses the generator's truth layout."""
+        out = np.zeros(480 + 16 + 320 + 128, np.int32)
+        if lib().jo_tap_sbr(self._h, el, ch, out.ctypes.data) < 0:
+            return None
+        return dict(ints=out[:480].copy(), extra=out[480:496].copy(), e_orig=out[496:816].view(np.float32).reshape(5, 64).copy(),
+                    q_div=out[816:944].view(np.float32).reshape(2, 64).copy())
 
     def tap_msused(self, el: int):
         ms = np.zeros(128, np.uint8)

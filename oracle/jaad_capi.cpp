@@ -71,6 +71,7 @@ void jo_close(void* hv) { delete static_cast<Handle*>(hv); }
 int jo_decode_frame(void* hv, const uint8_t* data, int n, float* pcm_f32, int16_t* pcm_s16, int big_endian, int* meta) {
   Handle* h = static_cast<Handle*>(hv);
   h->last = h->dec->decodeFrame(data, (size_t)n);
+  if (h->last.status != ST_OK && getenv("JO_DBG_EXC")) fprintf(stderr, "oracle: %s\n", h->dec->lastError.c_str());
   const FrameOutput& f = h->last;
   if (meta) { meta[0] = f.status; meta[1] = f.channels; meta[2] = f.sampleLength; meta[3] = f.sampleRate; }
   if (f.status != ST_OK) return f.status;
@@ -128,6 +129,44 @@ int jo_tap_msused(void* hv, int el, uint8_t* ms128) {
   CPE* c = static_cast<CPE*>(ae[el]);
   for (int i = 0; i < 128; ++i) ms128[i] = c->msUsed[i];
   return 0;
+}
+
+// SBR parity tap of the frame just decoded: element `el`, channel ch.  Same layout as the generator's truth
+// (gen/aacgen_sbr.inc): L_E, L_Q, frame class, pointer, t_E[6], f[6], amp_res, coupling, pad to 32, E[5][64], Q[2][64];
+// then (from out[480]) kx, M, N_high, N_low, N_Q, k0, N_master, noPatches, reset, and E_orig bits [5][64], Q_div bits [2][64].
+int jo_tap_sbr(void* hv, int el, int ch, int32_t* out) {
+#ifdef JAAD_ORACLE_WITH_SBR
+  Handle* h = static_cast<Handle*>(hv);
+  auto& ae = h->dec->syn.audioElements;
+  if (el < 0 || el >= (int)ae.size() || !ae[el]->sbr) return -1;
+  sbr::SBR* s = static_cast<sbr::SBR*>(ae[el]->sbr.get());
+  sbr::Channel* c;
+  int coupling = 0;
+  if (ae[el]->type == EL_CPE) {
+    sbr::SBR2* s2 = static_cast<sbr::SBR2*>(s);
+    c = ch ? &s2->ch1 : &s2->ch0;
+    coupling = s2->bs_coupling ? 1 : 0;
+  } else {
+    if (ch) return -1;
+    c = &static_cast<sbr::SBR1*>(s)->ch0;
+  }
+  memset(out, 0, sizeof(int32_t) * 480);
+  out[0] = c->L_E; out[1] = c->L_Q; out[2] = c->bs_frame_class; out[3] = c->bs_pointer;
+  for (int i = 0; i < 6; ++i) { out[4 + i] = c->t_E[i]; out[10 + i] = c->f[i]; }
+  out[16] = c->amp_res ? 1 : 0;
+  out[17] = coupling;
+  for (int l = 0; l < 5; ++l) for (int k = 0; k < 64; ++k) out[32 + l * 64 + k] = c->E[k][l];
+  for (int l = 0; l < 2; ++l) for (int k = 0; k < 64; ++k) out[32 + 320 + l * 64 + k] = c->Q[k][l];
+  int32_t* x = out + 480;
+  x[0] = s->kx; x[1] = s->M; x[2] = s->N_high; x[3] = s->N_low; x[4] = s->N_Q; x[5] = s->k0; x[6] = s->N_master;
+  x[7] = s->noPatches; x[8] = s->reset ? 1 : 0; x[9] = s->isValid() ? 1 : 0;
+  for (int l = 0; l < 5; ++l) for (int k = 0; k < 64; ++k) memcpy(&x[16 + l * 64 + k], &c->E_orig[k][l], 4);
+  for (int l = 0; l < 2; ++l) for (int k = 0; k < 64; ++k) memcpy(&x[16 + 320 + l * 64 + k], &c->Q_div[k][l], 4);
+  return 0;
+#else
+  (void)hv; (void)el; (void)ch; (void)out;
+  return -1;
+#endif
 }
 
 // ADTS index: payload offsets/sizes of up to `max` frames; hdr[0..2] = profile, sf_index, chan_cfg of the first frame.

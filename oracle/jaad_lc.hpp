@@ -1017,6 +1017,7 @@ struct Decoder {
   DecoderConfig config;
   SyntacticElements syn;
   int frames = 0;
+  std::string lastError;
 
   explicit Decoder(const DecoderConfig& c) : config(c), syn(config) {}
 
@@ -1038,6 +1039,7 @@ struct Decoder {
       out.sampleRate = config.getOutputFrequency().frequency;
     } catch (const AACException& e) {
       out.status = e.code;
+      lastError = e.what();
     }
     ++frames;
     return out;
