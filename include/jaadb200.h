@@ -170,6 +170,11 @@ void jaadb_batch_destroy(jaadb_batch* b);
 int jaadb_batch_tap(jaadb_batch* b, uint32_t frame, uint32_t ch, int16_t* q, int16_t* sfidx, uint8_t* sfbcb,
                     float* spec, int32_t* info, uint8_t* ms_used128);
 
+/* SBR parity tap: the per-frame SBR record (dequantised envelopes, band tables, grid) the parse kernel produced for
+ * frame `frame`, channel `ch` of the last decode, as raw bytes of the engine's internal layout (jaadec_b200/csrc/
+ * sbr_types.cuh, SbrFrameDev); returns its size, 0 if the frame's stream carries no SBR, or a negative JAADB_E_* code. */
+int jaadb_batch_tap_sbr(jaadb_batch* b, uint32_t frame, uint32_t ch, void* out, uint32_t out_bytes);
+
 #ifdef __cplusplus
 }
 #endif

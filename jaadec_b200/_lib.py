@@ -15,7 +15,7 @@ SYMBOLS = [
     "jaadb_abi_version", "jaadb_status_string", "jaadb_last_error", "jaadb_engine_create", "jaadb_engine_destroy",
     "jaadb_stream_open_asc", "jaadb_stream_open_adts", "jaadb_stream_close", "jaadb_stream_get_info", "jaadb_decode",
     "jaadb_batch_create", "jaadb_batch_pcm_bytes", "jaadb_batch_upload", "jaadb_batch_decode", "jaadb_batch_sync",
-    "jaadb_batch_download", "jaadb_batch_timings", "jaadb_batch_destroy", "jaadb_batch_tap",
+    "jaadb_batch_download", "jaadb_batch_timings", "jaadb_batch_destroy", "jaadb_batch_tap", "jaadb_batch_tap_sbr",
 ]
 
 
@@ -82,5 +82,6 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.jaadb_batch_destroy.argtypes = [vp]
     lib.jaadb_batch_destroy.restype = None
     lib.jaadb_batch_tap.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp]
+    lib.jaadb_batch_tap_sbr.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32]
     _lib = lib
     return lib

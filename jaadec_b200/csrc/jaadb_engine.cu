@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -19,6 +20,8 @@
 #include "generated/jaad_tables_host.h"
 #include "k1_parse.cuh"
 #include "k2_filterbank.cuh"
+#include "k3_sbr_parse.cuh"
+#include "k4_sbr_process.cuh"
 
 #ifndef K2_STEREO_MIN_BLOCKS
 #define K2_STEREO_MIN_BLOCKS 4
@@ -147,6 +150,10 @@ struct FrameIndex {
   std::vector<RunFrameDev> run_frames;   // per run, its frames in the caller's order
   std::vector<Group> groups;
   uint32_t n_ics = 0;
+  // SBR streams: one parse run per element (K3), one process run per channel (K4)
+  std::vector<SbrRunDev> sbr_runs;
+  std::vector<K4RunDev> k4_runs;
+  uint32_t n_sbr_frames = 0;
   // when set, frames / run_frames are written here (pinned staging of the one-call path) instead of the vectors
   FrameDev* frames_out = nullptr;
   RunFrameDev* run_frames_out = nullptr;
@@ -188,6 +195,12 @@ struct jaadb_engine {
   // persistent stream state
   float* d_overlap = nullptr;
   StreamState* d_sstate = nullptr;
+  // SBR: tables + persistent state (allocated when the first SBR stream is opened)
+  SbrTablesDev sbr_tables;
+  SbrConstTables sbr_const;
+  bool sbr_ready = false;
+  SbrElemDev* d_sbr_elem = nullptr;   // [max_streams][2]
+  SbrChanDev* d_sbr_chan = nullptr;   // [max_streams][kSbrChansPerStream]
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
   // workspace of the one-call path (jaadb_decode): grow-only, so a steady stream of calls allocates nothing.
@@ -205,6 +218,10 @@ struct jaadb_engine {
     DevBuf<RunFrameDev> run_frames;
     DevBuf<uint32_t> pcm_bytes;
     DevBuf<uint64_t> pcm_off;
+    DevBuf<SbrRunDev> sbr_runs;
+    DevBuf<K4RunDev> k4_runs;
+    DevBuf<SbrFrameDev> sbr_frames;
+    DevBuf<float> core;
     FrameSide* h_fside = nullptr;      // pinned
     uint32_t* h_pcm_bytes = nullptr;   // pinned
     size_t h_cap = 0;
@@ -251,6 +268,13 @@ struct jaadb_batch {
   DevBuf<uint32_t> d_pcm_bytes;
   DevBuf<uint64_t> d_pcm_off;
   DevBuf<float> d_spec_tap;
+  std::vector<SbrRunDev> sbr_runs;
+  std::vector<K4RunDev> k4_runs;
+  uint32_t n_sbr_frames = 0;
+  DevBuf<SbrRunDev> d_sbr_runs;
+  DevBuf<K4RunDev> d_k4_runs;
+  DevBuf<SbrFrameDev> d_sbr_frames;
+  DevBuf<float> d_core;
   std::vector<FrameSide> h_fside;
   std::vector<uint32_t> h_pcm_bytes;
   jaadb_timings timings;
@@ -310,6 +334,80 @@ int init_tables(jaadb_engine* e) {
   return 0;
 }
 
+// SBR tables + persistent state, set up when the first SBR stream is opened.
+int init_sbr(jaadb_engine* e) {
+  if (e->sbr_ready) return 0;
+  SbrTablesDev& D = e->sbr_tables;
+  memset(&D, 0, sizeof D);
+  int rc;
+  static const int16_t* huff[10] = {T::SBR_T_HUFFMAN_ENV_1_5DB, T::SBR_F_HUFFMAN_ENV_1_5DB, T::SBR_T_HUFFMAN_ENV_BAL_1_5DB,
+                                    T::SBR_F_HUFFMAN_ENV_BAL_1_5DB, T::SBR_T_HUFFMAN_ENV_3_0DB, T::SBR_F_HUFFMAN_ENV_3_0DB,
+                                    T::SBR_T_HUFFMAN_ENV_BAL_3_0DB, T::SBR_F_HUFFMAN_ENV_BAL_3_0DB, T::SBR_T_HUFFMAN_NOISE_3_0DB,
+                                    T::SBR_T_HUFFMAN_NOISE_BAL_3_0DB};
+  static const int huff_n[10] = {T::SBR_T_HUFFMAN_ENV_1_5DB_N, T::SBR_F_HUFFMAN_ENV_1_5DB_N, T::SBR_T_HUFFMAN_ENV_BAL_1_5DB_N,
+                                 T::SBR_F_HUFFMAN_ENV_BAL_1_5DB_N, T::SBR_T_HUFFMAN_ENV_3_0DB_N, T::SBR_F_HUFFMAN_ENV_3_0DB_N,
+                                 T::SBR_T_HUFFMAN_ENV_BAL_3_0DB_N, T::SBR_F_HUFFMAN_ENV_BAL_3_0DB_N, T::SBR_T_HUFFMAN_NOISE_3_0DB_N,
+                                 T::SBR_T_HUFFMAN_NOISE_BAL_3_0DB_N};
+  for (int i = 0; i < 10; ++i)
+    if ((rc = e->upload(huff[i], huff_n[i], &D.huff[i]))) return rc;
+  if ((rc = e->upload(JT(SBR_E_DEQ_TAB), T::SBR_E_DEQ_TAB_N, &D.e_deq))) return rc;
+  if ((rc = e->upload(JT(SBR_Q_DIV_TAB), T::SBR_Q_DIV_TAB_N, &D.q_div))) return rc;
+  if ((rc = e->upload(JT(SBR_Q_DIV2_TAB), T::SBR_Q_DIV2_TAB_N, &D.q_div2))) return rc;
+  if ((rc = e->upload(JT(SBR_Q_DIV_TAB_LEFT), T::SBR_Q_DIV_TAB_LEFT_N, &D.q_div_left))) return rc;
+  if ((rc = e->upload(JT(SBR_Q_DIV_TAB_RIGHT), T::SBR_Q_DIV_TAB_RIGHT_N, &D.q_div_right))) return rc;
+  if ((rc = e->upload(JT(SBR_Q_DIV2_TAB_LEFT), T::SBR_Q_DIV2_TAB_LEFT_N, &D.q_div2_left))) return rc;
+  if ((rc = e->upload(JT(SBR_Q_DIV2_TAB_RIGHT), T::SBR_Q_DIV2_TAB_RIGHT_N, &D.q_div2_right))) return rc;
+  if ((rc = e->upload(JT(SBR_E_PAN_TAB), T::SBR_E_PAN_TAB_N, &D.e_pan))) return rc;
+  if ((rc = e->upload(JT(SBR_QMF_C), T::SBR_QMF_C_N, &D.qmf_c))) return rc;
+  if ((rc = e->upload(JT(SBR_DCT4_64_TAB), T::SBR_DCT4_64_TAB_N, &D.dct4_tab))) return rc;
+  if ((rc = e->upload(JT(SBR_W_ARRAY_REAL), 16, &D.w_real))) return rc;
+  if ((rc = e->upload(JT(SBR_W_ARRAY_IMAG), 16, &D.w_imag))) return rc;
+  if ((rc = e->upload(JT(SBR_NOISE_TABLE), T::SBR_NOISE_TABLE_N, &D.noise_table))) return rc;
+  // FBT.find_bands / find_initial_power (sbr/FBT.java:135-145) for every argument the band-table code can pass, evaluated
+  // here on the host in double precision exactly as the Java expressions are
+  {
+    std::vector<uint8_t> fb((size_t)2 * 7 * 65 * 65, 0);
+    for (int warp = 0; warp < 2; ++warp)
+      for (int bands = 0; bands <= 6; ++bands)
+        for (int a0 = 1; a0 <= 64; ++a0)
+          for (int a1 = 1; a1 <= 64; ++a1) {
+            float div = (float)std::log(2.0);
+            if (warp != 0) div *= 1.3f;
+            int v = (int)(bands * std::log((double)((float)a1 / (float)a0)) / div + 0.5);
+            fb[(((size_t)warp * 7 + bands) * 65 + a0) * 65 + a1] = (uint8_t)std::min(std::max(v, 0), 255);
+          }
+    if ((rc = e->upload(fb.data(), fb.size(), &D.find_bands))) return rc;
+    std::vector<float> ip((size_t)64 * 65 * 65, 1.0f);
+    for (int bands = 1; bands < 64; ++bands)
+      for (int a0 = 1; a0 <= 64; ++a0)
+        for (int a1 = 1; a1 <= 64; ++a1)
+          ip[((size_t)bands * 65 + a0) * 65 + a1] = (float)std::pow((double)((float)a1 / (float)a0), (double)(1.0f / (float)bands));
+    if ((rc = e->upload(ip.data(), ip.size(), &D.init_power))) return rc;
+  }
+  SbrConstTables& K = e->sbr_const;
+  if ((rc = e->upload(T::SBR_START_MIN_TABLE, 12, &K.start_min))) return rc;
+  if ((rc = e->upload(T::SBR_OFFSET_INDEX_TABLE, 12, &K.offset_index))) return rc;
+  if ((rc = e->upload(T::SBR_OFFSET, T::SBR_OFFSET_N, &K.offset))) return rc;
+  if ((rc = e->upload(T::SBR_STOP_MIN_TABLE, 12, &K.stop_min))) return rc;
+  if ((rc = e->upload(T::SBR_STOP_OFFSET_TABLE, T::SBR_STOP_OFFSET_TABLE_N, &K.stop_offset))) return rc;
+  if ((rc = e->upload(T::SBR_GOAL_SB_TAB, 12, &K.goal_sb))) return rc;
+  if ((rc = e->upload(JT(SBR_LIMITER_BANDS_COMPARE), 3, &K.limiter_cmp))) return rc;
+  CUDA_TRY(e, cudaMemcpyToSymbol(c_sbr_dct4, JT(SBR_DCT4_64_TAB), sizeof(float) * 192));
+  CUDA_TRY(e, cudaMemcpyToSymbol(c_sbr_w_real, JT(SBR_W_ARRAY_REAL), sizeof(float) * 16));
+  CUDA_TRY(e, cudaMemcpyToSymbol(c_sbr_w_imag, JT(SBR_W_ARRAY_IMAG), sizeof(float) * 16));
+  CUDA_TRY(e, cudaMemcpyToSymbol(c_sbr_qmf_c, JT(SBR_QMF_C), sizeof(float) * 640));
+  CUDA_TRY(e, cudaMemcpyToSymbol(c_sbr_bit_rev, T::SBR_BIT_REV_TAB, sizeof(int) * 32));
+  const size_t ns = e->streams.size();
+  CUDA_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->d_sbr_elem), sizeof(SbrElemDev) * ns * 2));
+  CUDA_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->d_sbr_chan), sizeof(SbrChanDev) * ns * kSbrChansPerStream));
+  cudaFuncSetAttribute(k3_sbr_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SbrElemDev) * kK3WarpsPerBlock));
+  cudaFuncSetAttribute(k4_sbr_process_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_bytes());
+  cudaFuncSetAttribute(k4_sbr_process_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_bytes());
+  cudaFuncSetAttribute(k4_sbr_process_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_bytes());
+  e->sbr_ready = true;
+  return 0;
+}
+
 // Minimal MSB-first reader for the AudioSpecificConfig (host side only).
 struct HostBits {
   const uint8_t* d; uint32_t n, pos = 0;
@@ -352,12 +450,29 @@ int finish_open(jaadb_engine* e, StreamHost& s, int32_t* stream_id) {
   s.n_slots = l.n_channels;
   s.out_channels = (s.chan_cfg == 1) ? 2 : l.n_channels;  // DecoderConfig.getChannelCount (DecoderConfig.java:108-115)
   s.profile_ok = profile_supported(s.profile);
-  if (s.sbr) { e->set_error("SBR/PS streams are not implemented in this build"); return JAADB_E_CONFIG; }
+  if (s.sbr > 1) { e->set_error("parametric stereo (HE-AAC v2) streams are not implemented in this build"); return JAADB_E_CONFIG; }
+  if (s.sbr) {
+    if (s.chan_cfg > 2) { e->set_error("SBR is implemented for mono and stereo streams only"); return JAADB_E_CONFIG; }
+    if (s.sample_length != 2048) { e->set_error("down-sampled SBR (32-band synthesis) is not implemented"); return JAADB_E_CONFIG; }
+    if (s.sf_index < 3) { e->set_error("SBR core sampling rate too high"); return JAADB_E_CONFIG; }
+    int rc = init_sbr(e);
+    if (rc) return rc;
+    s.out_channels = 2;   // SCE: SBR1.process fills a second channel (PS or a copy), CPE: two channels
+  }
   if (e->free_slots.empty()) { e->set_error("stream table full"); return JAADB_E_CAPACITY; }
   int32_t slot = e->free_slots.back();
   e->free_slots.pop_back();
   s.open = true;
   e->streams[slot] = s;
+  if (s.sbr) {
+    // a fresh SBR object per element: everything zero except Channel.prevEnvIsShort = -1 (Channel.java:51)
+    static SbrElemDev fresh[2];
+    memset(fresh, 0, sizeof fresh);
+    for (auto& el : fresh) { el.ch[0].prevEnvIsShort = -1; el.ch[1].prevEnvIsShort = -1; }
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_sbr_elem + (size_t)slot * 2, fresh, sizeof fresh, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemsetAsync(e->d_sbr_chan + (size_t)slot * kSbrChansPerStream, 0, sizeof(SbrChanDev) * kSbrChansPerStream, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  }
   CUDA_TRY(e, cudaMemsetAsync(e->d_overlap + (size_t)slot * kMaxChannels * 1024, 0, sizeof(float) * kMaxChannels * 1024, e->stream));
   CUDA_TRY(e, cudaMemsetAsync(e->d_sstate + slot, 0, sizeof(StreamState), e->stream));
   *stream_id = slot;
@@ -412,6 +527,9 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
   FrameDev* const fout = ix.frames_out ? ix.frames_out : ix.frames.data();
   ix.runs.clear();
   ix.groups.clear();
+  ix.sbr_runs.clear();
+  ix.k4_runs.clear();
+  ix.n_sbr_frames = 0;
   // per-stream frame counts (counting sort keeps array order inside each stream)
   std::vector<uint32_t>& count = e->scratch_count;
   count.assign(e->streams.size(), 0);
@@ -450,6 +568,7 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
       r.layout = (uint8_t)e->streams[s].chan_cfg;
       r.sf_index = (uint8_t)e->streams[s].sf_index;
       r.mono_dup = (e->streams[s].chan_cfg == 1) ? 1 : 0;
+      r.sbr = e->streams[s].sbr ? 1 : 0;
       run_of[s] = (uint32_t)ix.runs.size();
       ix.runs.push_back(r);
       g.n_runs++;
@@ -458,6 +577,37 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
   }
   uint32_t acc = 0;
   for (auto& r : ix.runs) { r.first = acc; acc += r.count; }
+  for (const auto& r : ix.runs) {
+    if (!r.sbr) continue;
+    const StreamHost& sh = e->streams[r.stream_slot];
+    const bool stereo = sh.chan_cfg == 2;
+    SbrRunDev sr;
+    memset(&sr, 0, sizeof sr);
+    sr.stream_slot = r.stream_slot;
+    sr.first = r.first;
+    sr.count = r.count;
+    sr.sbr_base = ix.n_sbr_frames;
+    sr.element = 0;
+    sr.stereo = stereo ? 1 : 0;
+    sr.sr_index = (uint8_t)(sh.sf_index - 3);
+    sr.first_ch = 0;
+    ix.sbr_runs.push_back(sr);
+    for (int c = 0; c < (stereo ? 2 : 1); ++c) {
+      K4RunDev kr;
+      memset(&kr, 0, sizeof kr);
+      kr.stream_slot = r.stream_slot;
+      kr.first = r.first;
+      kr.count = r.count;
+      kr.sbr_base = sr.sbr_base;
+      kr.chan = (uint8_t)c;
+      kr.ch_slot = (uint8_t)c;
+      kr.out_ch = (uint8_t)c;
+      kr.n_out = 2;
+      kr.dup = stereo ? 0 : 1;
+      ix.k4_runs.push_back(kr);
+    }
+    ix.n_sbr_frames += r.count;
+  }
   if (!ix.run_frames_out) ix.run_frames.resize(n);
   RunFrameDev* const rout = ix.run_frames_out ? ix.run_frames_out : ix.run_frames.data();
   std::vector<uint32_t>& fill = e->scratch_fill;
@@ -469,16 +619,41 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
   return JAADB_OK;
 }
 
-// K1 + K2 over an indexed set of frames, everything already on the device.
-void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_groups, uint32_t n_frames,
-                   const uint8_t* d_blob, const FrameDev* d_frames, FrameSide* d_fside, IcsSide* d_iside, int16_t* d_q,
-                   const RunDev* d_runs, const RunFrameDev* d_run_frames, uint8_t* d_pcm, const uint64_t* d_pcm_off,
-                   uint32_t* d_pcm_bytes, float* d_tap, cudaEvent_t after_k1, uint32_t* launches) {
+// Device buffers of one decode pass.
+struct DecodeBufs {
+  const uint8_t* blob;
+  const FrameDev* frames;
+  FrameSide* fside;
+  IcsSide* iside;
+  int16_t* q;
+  const RunDev* runs;
+  const RunFrameDev* run_frames;
+  uint8_t* pcm;
+  const uint64_t* pcm_off;
+  uint32_t* pcm_bytes;
+  float* tap;
+  // SBR
+  const SbrRunDev* sbr_runs;
+  const K4RunDev* k4_runs;
+  SbrFrameDev* sbr_frames;
+  float* core;
+};
+
+// K1 (+ K3) + K2 (+ K4) over an indexed set of frames, everything already on the device.
+void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_groups, uint32_t n_frames, uint32_t n_sbr_runs,
+                   uint32_t n_k4_runs, const DecodeBufs& B, cudaEvent_t after_k1, cudaEvent_t after_k2, uint32_t* launches) {
   {
     const int threads = kK1Threads;
     const int blocks = (int)((n_frames + threads - 1) / threads);
-    k1_parse_kernel<<<blocks, threads, k1_smem_bytes(e->lut_entries), e->stream>>>(d_blob, d_frames, n_frames, d_fside, d_iside, d_q,
-                                                                        e->tables, e->d_layouts);
+    k1_parse_kernel<<<blocks, threads, k1_smem_bytes(e->lut_entries), e->stream>>>(B.blob, B.frames, n_frames, B.fside, B.iside, B.q,
+                                                                                   e->tables, e->d_layouts);
+    ++*launches;
+  }
+  if (n_sbr_runs) {
+    // SBR payload parse before the filterbank: an exception inside SBR.decode fails the whole frame
+    const int blocks = (int)((n_sbr_runs + kK3WarpsPerBlock - 1) / kK3WarpsPerBlock);
+    k3_sbr_parse_kernel<<<blocks, 32 * kK3WarpsPerBlock, sizeof(SbrElemDev) * kK3WarpsPerBlock, e->stream>>>(
+        B.blob, B.frames, B.fside, B.sbr_runs, n_sbr_runs, B.run_frames, e->d_sbr_elem, B.sbr_frames, e->sbr_tables, e->sbr_const);
     ++*launches;
   }
   if (after_k1) cudaEventRecord(after_k1, e->stream);
@@ -487,8 +662,8 @@ void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_gr
     const int threads = g.nch * kThreadsPerChannel;
     const int out_ch = (g.nch == 1) ? 2 : g.nch;
     const size_t smem = k2_smem_bytes(g.nch, out_ch);
-    const RunDev* runs = d_runs + g.first_run;
-#define K2_ARGS runs, d_run_frames, d_fside, d_iside, d_q, e->d_overlap, e->d_sstate, d_pcm, d_pcm_off, d_pcm_bytes, d_tap, e->tables, e->d_layouts, g.nch
+    const RunDev* runs = B.runs + g.first_run;
+#define K2_ARGS runs, B.run_frames, B.fside, B.iside, B.q, e->d_overlap, e->d_sstate, B.pcm, B.pcm_off, B.pcm_bytes, B.tap, B.core, e->tables, e->d_layouts, g.nch
 #define LAUNCH_K2(FMT)                                                                                              \
   do {                                                                                                              \
     if (threads <= 128) k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS><<<g.n_runs, threads, smem, e->stream>>>(K2_ARGS); \
@@ -499,6 +674,17 @@ void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_gr
     else LAUNCH_K2(2);
 #undef LAUNCH_K2
 #undef K2_ARGS
+    ++*launches;
+  }
+  if (after_k2) cudaEventRecord(after_k2, e->stream);
+  if (n_k4_runs) {
+#define LAUNCH_K4(FMT)                                                                                              \
+  k4_sbr_process_kernel<FMT><<<n_k4_runs, kK4Threads, k4_smem_bytes(), e->stream>>>(                                \
+      B.k4_runs, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, B.pcm, B.pcm_off, B.pcm_bytes, e->sbr_tables)
+    if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K4(0);
+    else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K4(1);
+    else LAUNCH_K4(2);
+#undef LAUNCH_K4
     ++*launches;
   }
 }
@@ -576,6 +762,8 @@ void jaadb_engine_destroy(jaadb_engine* e) {
   for (void* p : e->table_allocs) cudaFree(p);
   if (e->d_overlap) cudaFree(e->d_overlap);
   if (e->d_sstate) cudaFree(e->d_sstate);
+  if (e->d_sbr_elem) cudaFree(e->d_sbr_elem);
+  if (e->d_sbr_chan) cudaFree(e->d_sbr_chan);
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);
   auto& W = e->ws;
@@ -591,6 +779,7 @@ void jaadb_engine_destroy(jaadb_engine* e) {
   }
   W.blob.release(); W.frames.release(); W.fside.release(); W.iside.release(); W.q.release(); W.runs.release();
   W.run_frames.release(); W.pcm_bytes.release(); W.pcm_off.release();
+  W.sbr_runs.release(); W.k4_runs.release(); W.sbr_frames.release(); W.core.release();
   if (W.h_fside) cudaFreeHost(W.h_fside);
   if (W.h_pcm_bytes) cudaFreeHost(W.h_pcm_bytes);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -734,6 +923,9 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
   b->run_frames.swap(ix.run_frames);
   for (const auto& g : ix.groups) b->groups.push_back(jaadb_batch::Group{g.nch, g.first_run, g.n_runs});
   b->n_ics = ix.n_ics;
+  b->sbr_runs.swap(ix.sbr_runs);
+  b->k4_runs.swap(ix.k4_runs);
+  b->n_sbr_frames = ix.n_sbr_frames;
   const uint32_t ics = ix.n_ics;
   // device side
   cudaError_t ce = cudaSuccess;
@@ -749,6 +941,12 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
   chk(b->d_pcm_bytes.ensure(std::max<uint32_t>(n, 1)));
   chk(b->d_pcm_off.ensure(std::max<uint32_t>(n, 1)));
   if (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) chk(b->d_spec_tap.ensure(std::max<size_t>((size_t)ics * 1024, 16)));
+  if (b->n_sbr_frames) {
+    chk(b->d_sbr_runs.ensure(b->sbr_runs.size()));
+    chk(b->d_k4_runs.ensure(b->k4_runs.size()));
+    chk(b->d_sbr_frames.ensure((size_t)b->n_sbr_frames * 2));
+    chk(b->d_core.ensure((size_t)ics * 1024));
+  }
   if (ce != cudaSuccess) { e->set_error(std::string("batch allocation: ") + cudaGetErrorString(ce)); return fail(JAADB_E_NOMEM); }
   if (n) {
     chk(cudaMemcpyAsync(b->d_frames.p, b->frames.data(), sizeof(FrameDev) * n, cudaMemcpyHostToDevice, e->stream));
@@ -756,6 +954,10 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
     chk(cudaMemcpyAsync(b->d_run_frames.p, b->run_frames.data(), sizeof(RunFrameDev) * n, cudaMemcpyHostToDevice, e->stream));
     chk(cudaMemcpyAsync(b->d_pcm_off.p, b->pcm_off.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream));
     chk(cudaMemsetAsync(b->d_blob.p + blob_bytes, 0, 64, e->stream));
+    if (b->n_sbr_frames) {
+      chk(cudaMemcpyAsync(b->d_sbr_runs.p, b->sbr_runs.data(), sizeof(SbrRunDev) * b->sbr_runs.size(), cudaMemcpyHostToDevice, e->stream));
+      chk(cudaMemcpyAsync(b->d_k4_runs.p, b->k4_runs.data(), sizeof(K4RunDev) * b->k4_runs.size(), cudaMemcpyHostToDevice, e->stream));
+    }
     chk(cudaStreamSynchronize(e->stream));
   }
   if (ce != cudaSuccess) { e->set_error(std::string("batch upload: ") + cudaGetErrorString(ce)); return fail(JAADB_E_CUDA); }
@@ -782,9 +984,11 @@ int jaadb_batch_decode(jaadb_batch* b) {
   uint32_t launches = 0;
   if (b->n_frames == 0) { b->decoded = true; return JAADB_OK; }
   if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[0], e->stream));
-  launch_decode(e, b->groups.data(), b->groups.size(), b->n_frames, b->d_blob.p, b->d_frames.p, b->d_fside.p, b->d_iside.p,
-                b->d_q.p, b->d_runs.p, b->d_run_frames.p, b->d_pcm.p, b->d_pcm_off.p, b->d_pcm_bytes.p,
-                (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) ? b->d_spec_tap.p : nullptr, prof ? e->ev[1] : nullptr, &launches);
+  DecodeBufs B{b->d_blob.p, b->d_frames.p, b->d_fside.p, b->d_iside.p, b->d_q.p, b->d_runs.p, b->d_run_frames.p, b->d_pcm.p,
+               b->d_pcm_off.p, b->d_pcm_bytes.p, (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) ? b->d_spec_tap.p : nullptr,
+               b->d_sbr_runs.p, b->d_k4_runs.p, b->d_sbr_frames.p, b->d_core.p};
+  launch_decode(e, b->groups.data(), b->groups.size(), b->n_frames, (uint32_t)b->sbr_runs.size(), (uint32_t)b->k4_runs.size(), B,
+                prof ? e->ev[1] : nullptr, prof ? e->ev[3] : nullptr, &launches);
   if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[2], e->stream));
   CUDA_TRY(e, cudaGetLastError());
   b->timings.launches = launches;
@@ -805,7 +1009,8 @@ int jaadb_batch_timings(jaadb_batch* b, jaadb_timings* t) {
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   if (b->n_frames) {
     CUDA_TRY(e, cudaEventElapsedTime(&b->timings.parse_ms, e->ev[0], e->ev[1]));
-    CUDA_TRY(e, cudaEventElapsedTime(&b->timings.filterbank_ms, e->ev[1], e->ev[2]));
+    CUDA_TRY(e, cudaEventElapsedTime(&b->timings.filterbank_ms, e->ev[1], e->ev[3]));
+    CUDA_TRY(e, cudaEventElapsedTime(&b->timings.sbr_ms, e->ev[3], e->ev[2]));
     CUDA_TRY(e, cudaEventElapsedTime(&b->timings.total_ms, e->ev[0], e->ev[2]));
   }
   *t = b->timings;
@@ -848,6 +1053,7 @@ void jaadb_batch_destroy(jaadb_batch* b) {
   b->d_blob.release(); b->d_pcm.release(); b->d_frames.release(); b->d_fside.release(); b->d_iside.release();
   b->d_q.release(); b->d_runs.release(); b->d_run_frames.release(); b->d_pcm_bytes.release(); b->d_pcm_off.release();
   b->d_spec_tap.release();
+  b->d_sbr_runs.release(); b->d_k4_runs.release(); b->d_sbr_frames.release(); b->d_core.release();
   delete b;
 }
 
@@ -914,6 +1120,14 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   chk(W.runs.ensure(e->streams.size()));
   chk(W.run_frames.ensure(chunk));
   chk(W.pcm_off.ensure(n_frames));
+  bool any_sbr = false;
+  for (uint32_t i = 0; i < n_frames && !any_sbr; ++i) any_sbr = e->streams[frames[i].stream_id].sbr != 0;
+  if (any_sbr) {
+    chk(W.sbr_runs.ensure(e->streams.size()));
+    chk(W.k4_runs.ensure(e->streams.size() * 2));
+    chk(W.sbr_frames.ensure((size_t)chunk * 2));
+    chk(W.core.ensure(max_ics * 1024));
+  }
   if (ce == cudaSuccess && (W.h_chunk_cap < chunk || W.h_runs_cap < e->streams.size())) {
     for (int i = 0; i < 2; ++i) {
       if (W.h_frames[i]) cudaFreeHost(W.h_frames[i]);
@@ -964,8 +1178,17 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
     CUDA_TRY(e, cudaMemcpyAsync(W.run_frames.p, W.h_run_frames[pb], sizeof(RunFrameDev) * n, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaEventRecord(W.desc_done[pb], e->stream));
     if (k >= 2) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, W.d2h_done[pb], 0));   // PCM buffer pb is free again
-    launch_decode(e, ix.groups.data(), ix.groups.size(), n, W.blob.p, W.frames.p, W.fside.p + r.i0, W.iside.p, W.q.p,
-                  W.runs.p, W.run_frames.p, W.pcm[pb].p - r.lo, W.pcm_off.p + r.i0, W.pcm_bytes.p + r.i0, nullptr, nullptr, &launches);
+    if (!ix.sbr_runs.empty()) {
+      // small and rare enough for pageable staging (the copies below synchronise the stream; SBR batches trade a little
+      // overlap for simplicity here)
+      CUDA_TRY(e, cudaMemcpyAsync(W.sbr_runs.p, ix.sbr_runs.data(), sizeof(SbrRunDev) * ix.sbr_runs.size(), cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(e, cudaMemcpyAsync(W.k4_runs.p, ix.k4_runs.data(), sizeof(K4RunDev) * ix.k4_runs.size(), cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    }
+    DecodeBufs B{W.blob.p, W.frames.p, W.fside.p + r.i0, W.iside.p, W.q.p, W.runs.p, W.run_frames.p, W.pcm[pb].p - r.lo,
+                 W.pcm_off.p + r.i0, W.pcm_bytes.p + r.i0, nullptr, W.sbr_runs.p, W.k4_runs.p, W.sbr_frames.p, W.core.p};
+    launch_decode(e, ix.groups.data(), ix.groups.size(), n, (uint32_t)ix.sbr_runs.size(), (uint32_t)ix.k4_runs.size(), B, nullptr,
+                  nullptr, &launches);
     CUDA_TRY(e, cudaGetLastError());
     CUDA_TRY(e, cudaEventRecord(W.k_done[pb], e->stream));
     CUDA_TRY(e, cudaStreamWaitEvent(W.copy_stream, W.k_done[pb], 0));
@@ -1044,6 +1267,24 @@ int jaadb_batch_tap(jaadb_batch* b, uint32_t frame, uint32_t ch, int16_t* q, int
     CUDA_TRY(e, cudaMemcpy(spec, b->d_spec_tap.p + (size_t)ics * 1024, 4096, cudaMemcpyDeviceToHost));
   }
   return JAADB_OK;
+}
+
+int jaadb_batch_tap_sbr(jaadb_batch* b, uint32_t frame, uint32_t ch, void* out, uint32_t out_bytes) {
+  if (!b || !b->decoded || frame >= b->n_frames || ch > 1 || !out) return JAADB_E_INVALID;
+  jaadb_engine* e = b->e;
+  cudaSetDevice(e->opts.device);
+  const int32_t slot = b->frames[frame].stream_slot;
+  for (const SbrRunDev& r : b->sbr_runs) {
+    if (r.stream_slot != slot) continue;
+    for (uint32_t it = 0; it < r.count; ++it) {
+      if (b->run_frames[r.first + it].frame != frame) continue;
+      if (out_bytes < sizeof(SbrFrameDev)) return JAADB_E_CAPACITY;
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+      CUDA_TRY(e, cudaMemcpy(out, b->d_sbr_frames.p + ((size_t)r.sbr_base + it) * 2 + ch, sizeof(SbrFrameDev), cudaMemcpyDeviceToHost));
+      return (int)sizeof(SbrFrameDev);
+    }
+  }
+  return 0;
 }
 
 }  // extern "C"

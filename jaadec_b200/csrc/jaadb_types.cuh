@@ -82,7 +82,7 @@ struct RunDev {
   uint8_t layout;
   uint8_t sf_index;
   uint8_t mono_dup;    // duplicate the single channel (SyntacticElements.java:244-245)
-  uint8_t pad;
+  uint8_t sbr;         // SBR stream: K2 hands the core PCM (float, 1024 per channel) to K4 instead of packing output
 };
 
 // One frame of a run, in decode order (what K2 walks).

@@ -163,7 +163,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
                      const FrameSide* __restrict__ fside, const IcsSide* __restrict__ iside,
                      const int16_t* __restrict__ qall, float* __restrict__ overlap_all, StreamState* __restrict__ sstate,
                      uint8_t* __restrict__ pcm, const uint64_t* __restrict__ pcm_off,
-                     uint32_t* __restrict__ pcm_bytes_out, float* __restrict__ spec_tap, TablesDev T,
+                     uint32_t* __restrict__ pcm_bytes_out, float* __restrict__ spec_tap, float* __restrict__ core, TablesDev T,
                      const LayoutDev* __restrict__ layouts, int nch) {
   extern __shared__ __align__(16) float smem[];
   // carve: twiddles; per channel [spec kSpecStride][overlap 1024][xre kXchgStride][xim kXchgStride]; sides; pcm staging
@@ -320,7 +320,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
     cur = nxt;
     __syncthreads();
     if (frame_status != 0) {
-      if (tid == 0) pcm_bytes_out[f] = 0;
+      if (tid == 0 && !run.sbr) pcm_bytes_out[f] = 0;
       continue;  // the frame produced no PCM; overlap untouched (Decoder.java:96-98)
     }
 
@@ -550,7 +550,10 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
           o0 = oo[0]; o1 = oo[1]; n0 = nn[0]; n1 = nn[1];
         }
         *reinterpret_cast<float2*>(my_ovl + i) = make_float2(n0, n1);
-        if (PCM_FORMAT == 2) {
+        if (run.sbr) {
+          // core-coder output of an SBR stream: K4 continues from here
+          *reinterpret_cast<float2*>(core + ((size_t)ics_base + c) * 1024 + i) = make_float2(o0, o1);
+        } else if (PCM_FORMAT == 2) {
           float* d = reinterpret_cast<float*>(dst);
           *reinterpret_cast<float2*>(d + (size_t)c * 1024 + i) = make_float2(o0, o1);
           if (run.mono_dup) *reinterpret_cast<float2*>(d + 1024 + i) = make_float2(o0, o1);
@@ -566,7 +569,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
         }
       }
       __syncthreads();
-      if (PCM_FORMAT != 2) {
+      if (PCM_FORMAT != 2 && !run.sbr) {
         // coalesced copy-out of the interleaved frame (pcm offsets are 4-byte aligned; 16 B when the caller packs)
         const int nwords = 1024 * out_ch / 2;   // 32-bit words
         const uint32_t* src = reinterpret_cast<const uint32_t*>(s_pcm);
@@ -578,7 +581,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
           for (int i = tid; i < nwords; i += nthreads) d[i] = src[i];
         }
       }
-      if (tid == 0) pcm_bytes_out[f] = (uint32_t)(1024 * out_ch * (PCM_FORMAT == 2 ? 4 : 2));
+      if (tid == 0 && !run.sbr) pcm_bytes_out[f] = (uint32_t)(1024 * out_ch * (PCM_FORMAT == 2 ? 4 : 2));
     }
   }
 

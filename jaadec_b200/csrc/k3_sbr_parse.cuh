@@ -1,0 +1,976 @@
+// K3 -- SBR payload parse.  One warp owns one SBR element of one stream and walks that stream's frames of the batch in
+// order (delta-time coding, header state and the grid-restore rules make the parse sequential per element); lane 0 runs
+// the bit-serial syntax on a shared-memory copy of the element's persistent state, all 32 lanes build the per-frame
+// record K4 consumes (dequantised envelopes + the band tables in force for that frame).
+//
+// Reference behaviour followed (paths relative to aac/src/main/java/net/sourceforge/jaad/aac/sbr/):
+//   SBR.java:125-300        decode, readHeader/swapHeaders, calc_sbr_tables, extended data, save_prev_data
+//   Header.java:24-78       header syntax and the reset test
+//   SBR1.java:34-73, SBR2.java:35-135   sbr_data for SCE / CPE (incl. the coupled-branch flag-count quirk)
+//   Channel.java:85-583     grid, dtdf, invf, envelope, noise, Huffman tree walk, delta decoding, time borders
+//   FBT.java:29-416         start/stop channel, master / derived / limiter band tables
+//   HFGeneration.java:247-309  patch construction
+//   NoiseEnvelope.java:186-345 dequantisation, coupled un-mapping
+//   HFAdjustment.java:24-38 l_A
+// A read past the end of the payload is an EOSException in JAAD, which fails the whole frame: every read here is
+// checked before anything is stored, so the persistent state is left exactly as the exception would leave it.
+#pragma once
+#include "jaadb_types.cuh"
+#include "sbr_types.cuh"
+
+namespace jaadb {
+
+#define JAADB_ST_SBR 14
+
+enum { SBR_FIXFIX = 0, SBR_FIXVAR = 1, SBR_VARFIX = 2, SBR_VARVAR = 3 };
+enum { SBR_LO_RES = 0, SBR_HI_RES = 1 };
+
+struct SbrBits {
+  const uint32_t* words;
+  uint32_t pos, end;
+  __device__ __forceinline__ uint32_t word(uint32_t i) const { return __byte_perm(__ldg(words + i), 0, 0x0123); }
+  __device__ __forceinline__ uint32_t left() const { return end > pos ? end - pos : 0u; }
+  // n <= 25
+  __device__ __forceinline__ bool get(int n, int& v) {
+    if (n == 0) { v = 0; return true; }
+    if (left() < (uint32_t)n) return false;
+    const uint32_t wi = pos >> 5;
+    const uint32_t w = __funnelshift_l(word(wi + 1), word(wi), pos & 31u);
+    v = (int)(w >> (32 - n));
+    pos += n;
+    return true;
+  }
+};
+
+// every syntax function returns 0, or a JAADB_ST_* code; EOS aborts immediately
+#define SBR_RD(var, n) do { if (!ld.get((n), (var))) return JAADB_ST_EOS; } while (0)
+#define SBR_TRY(expr) do { int _st = (expr); if (_st) return _st; } while (0)
+
+struct SbrCtx {
+  SbrElemDev* S;
+  const SbrTablesDev* T;
+  const int32_t* start_min, *offset_index, *offset, *stop_min, *stop_offset, *goal_sb;
+  const float* limiter_cmp;
+  int sr_index;
+};
+
+__device__ inline void sbr_sort(int* a, int lo, int hi) {  // Arrays.sort(a, lo, hi)
+  for (int i = lo + 1; i < hi; ++i) {
+    int v = a[i], j = i - 1;
+    while (j >= lo && a[j] > v) { a[j + 1] = a[j]; --j; }
+    a[j + 1] = v;
+  }
+}
+
+// ---- Header.java -------------------------------------------------------------------------------------------
+__device__ inline int sbr_header_decode(SbrBits& ld, SbrHeaderDev& h) {
+  int v, e1, e2;
+  SBR_RD(v, 1); h.amp_res = (uint8_t)v;
+  SBR_RD(v, 4); h.start_freq = (uint8_t)v;
+  SBR_RD(v, 4); h.stop_freq = (uint8_t)v;
+  SBR_RD(v, 3); h.xover_band = (uint8_t)v;
+  SBR_RD(v, 2);
+  SBR_RD(e1, 1);
+  SBR_RD(e2, 1);
+  if (e1) {
+    SBR_RD(v, 2); h.freq_scale = (uint8_t)v;
+    SBR_RD(v, 1); h.alter_scale = (uint8_t)v;
+    SBR_RD(v, 2); h.noise_bands = (uint8_t)v;
+  } else { h.freq_scale = 2; h.alter_scale = 1; h.noise_bands = 2; }
+  if (e2) {
+    SBR_RD(v, 2); h.limiter_bands = (uint8_t)v;
+    SBR_RD(v, 2); h.limiter_gains = (uint8_t)v;
+    SBR_RD(v, 1); h.interpol_freq = (uint8_t)v;
+    SBR_RD(v, 1); h.smoothing_mode = (uint8_t)v;
+  } else { h.limiter_bands = 2; h.limiter_gains = 2; h.interpol_freq = 1; h.smoothing_mode = 1; }
+  return 0;
+}
+
+__device__ inline bool sbr_header_differs(const SbrHeaderDev& a, const SbrHeaderDev& prev) {
+  return !prev.present || a.start_freq != prev.start_freq || a.stop_freq != prev.stop_freq || a.freq_scale != prev.freq_scale ||
+         a.alter_scale != prev.alter_scale || a.xover_band != prev.xover_band || a.noise_bands != prev.noise_bands;
+}
+
+// a freshly constructed Header (Header.java:14-22)
+__device__ inline SbrHeaderDev sbr_header_new() {
+  SbrHeaderDev h;
+  h.present = 1; h.amp_res = 1; h.start_freq = 5; h.stop_freq = 0; h.xover_band = 0; h.freq_scale = 2; h.alter_scale = 1;
+  h.noise_bands = 2; h.limiter_bands = 2; h.limiter_gains = 2; h.interpol_freq = 0; h.smoothing_mode = 0;
+  return h;
+}
+
+// SBR.swapHeaders (:192-204)
+__device__ inline void sbr_swap_headers(SbrElemDev& S) {
+  SbrHeaderDev h = S.hdr_saved;
+  S.hdr_saved = S.hdr;
+  if (!h.present) h = sbr_header_new();
+  S.hdr = h;
+}
+
+// ---- FBT.java ----------------------------------------------------------------------------------------------
+__device__ inline int sbr_find_bands(const SbrCtx& C, int warp, int bands, int a0, int a1) {
+  if (a0 < 1 || a0 > 64 || a1 < 0 || a1 > 64 || bands < 0 || bands > 6) return 0;
+  return C.T->find_bands[((warp * 7 + bands) * 65 + a0) * 65 + a1];
+}
+__device__ inline float sbr_initial_power(const SbrCtx& C, int bands, int a0, int a1) {
+  return C.T->init_power[(bands * 65 + a0) * 65 + a1];
+}
+
+__device__ inline int sbr_master_table_fs0(const SbrCtx& C, int k0, int k2, bool alter) {  // :82-129
+  SbrElemDev& S = *C.S;
+  int vDk[64];
+  if (k2 <= k0) { S.N_master = 0; return 1; }
+  const int dk = alter ? 2 : 1;
+  int nrBands = alter ? (((k2 - k0 + 2) >> 2) << 1) : (((k2 - k0) >> 1) << 1);
+  nrBands = min(nrBands, 63);
+  if (nrBands <= 0) return 1;
+  int k2Diff = k2 - (k0 + nrBands * dk);
+  for (int k = 0; k < nrBands; k++) vDk[k] = dk;
+  if (k2Diff != 0) {
+    const int incr = (k2Diff > 0) ? -1 : 1;
+    int k = (k2Diff > 0) ? (nrBands - 1) : 0;
+    while (k2Diff != 0) {
+      if (k < 0 || k >= 64) return -JAADB_ST_SBR;
+      vDk[k] -= incr;
+      k += incr;
+      k2Diff += incr;
+    }
+  }
+  int fm = k0;
+  S.f_master[0] = (uint8_t)fm;
+  for (int k = 1; k <= nrBands; k++) { fm += vDk[k - 1]; S.f_master[k] = (uint8_t)fm; }
+  S.N_master = (uint8_t)min(nrBands, 64);
+  return 0;
+}
+
+__device__ inline int sbr_master_table(const SbrCtx& C, int k0, int k2, int freq_scale, bool alter) {  // :150-260
+  (void)alter;
+  SbrElemDev& S = *C.S;
+  int vDk0[64], vDk1[64], vk0[64], vk1[64];
+  for (int i = 0; i < 64; ++i) { vDk0[i] = 0; vDk1[i] = 0; vk0[i] = 0; vk1[i] = 0; }
+  if (k2 <= k0) { S.N_master = 0; return 1; }
+  const int bands = freq_scale == 1 ? 6 : (freq_scale == 2 ? 5 : 4);
+  bool twoRegions;
+  int k1;
+  if ((double)((float)k2 / (float)k0) > 2.2449) { twoRegions = true; k1 = k0 << 1; }
+  else { twoRegions = false; k1 = k2; }
+  int nrBand0 = 2 * sbr_find_bands(C, 0, bands, k0, k1);
+  nrBand0 = min(nrBand0, 63);
+  if (nrBand0 <= 0) return 1;
+  float q = sbr_initial_power(C, nrBand0, k0, k1);
+  float qk = (float)k0;
+  int A_1 = (int)(qk + 0.5f);
+  for (int k = 0; k <= nrBand0; k++) {
+    const int A_0 = A_1;
+    qk *= q;
+    A_1 = (int)(qk + 0.5f);
+    vDk0[k] = A_1 - A_0;
+  }
+  sbr_sort(vDk0, 0, nrBand0);
+  vk0[0] = k0;
+  for (int k = 1; k <= nrBand0; k++) {
+    vk0[k] = vk0[k - 1] + vDk0[k - 1];
+    if (vDk0[k - 1] == 0) return 1;
+  }
+  if (!twoRegions) {
+    for (int k = 0; k <= nrBand0; k++) S.f_master[k] = (uint8_t)vk0[k];
+    S.N_master = (uint8_t)min(nrBand0, 64);
+    return 0;
+  }
+  int nrBand1 = 2 * sbr_find_bands(C, 1, bands, k1, k2);
+  nrBand1 = min(nrBand1, 63);
+  if (nrBand1 < 1) return -JAADB_ST_SBR;   // Math.pow(x, 1/0) / negative sort ranges: outside the decodable subset
+  q = sbr_initial_power(C, nrBand1, k1, k2);
+  qk = (float)k1;
+  A_1 = (int)(qk + 0.5f);
+  for (int k = 0; k <= nrBand1 - 1; k++) {
+    const int A_0 = A_1;
+    qk *= q;
+    A_1 = (int)(qk + 0.5f);
+    vDk1[k] = A_1 - A_0;
+  }
+  if (vDk1[0] < vDk0[nrBand0 - 1]) {
+    sbr_sort(vDk1, 0, nrBand1 + 1);
+    const int change = vDk0[nrBand0 - 1] - vDk1[0];
+    vDk1[0] = vDk0[nrBand0 - 1];
+    vDk1[nrBand1 - 1] = vDk1[nrBand1 - 1] - change;
+  }
+  sbr_sort(vDk1, 0, nrBand1);
+  vk1[0] = k1;
+  for (int k = 1; k <= nrBand1; k++) {
+    vk1[k] = vk1[k - 1] + vDk1[k - 1];
+    if (vDk1[k - 1] == 0) return 1;
+  }
+  const int nm = min(nrBand0 + nrBand1, 64);
+  S.N_master = (uint8_t)nm;
+  for (int k = 0; k <= nrBand0; k++) S.f_master[k] = (uint8_t)vk0[k];
+  for (int k = nrBand0 + 1; k <= nm; k++) {
+    if (k >= 64) return -JAADB_ST_SBR;
+    S.f_master[k] = (uint8_t)vk1[k - nrBand0];
+  }
+  return 0;
+}
+
+__device__ inline int sbr_derived_table(const SbrCtx& C, int xover, int k2) {  // :263-320
+  SbrElemDev& S = *C.S;
+  if (S.N_master <= xover) return 1;
+  const int N_high = S.N_master - xover;
+  const int N_low = (N_high >> 1) + (N_high - ((N_high >> 1) << 1));
+  S.N_high = (uint8_t)N_high;
+  S.N_low = (uint8_t)N_low;
+  S.n[0] = (uint8_t)N_low;
+  S.n[1] = (uint8_t)N_high;
+  for (int k = 0; k <= N_high; k++) S.f_table_res[SBR_HI_RES][k] = S.f_master[k + xover];
+  const int M = S.f_table_res[SBR_HI_RES][N_high] - S.f_table_res[SBR_HI_RES][0];
+  const int kx = S.f_table_res[SBR_HI_RES][0];
+  S.M = (uint8_t)M;
+  S.kx = (uint8_t)kx;
+  if (kx > 32) return 1;
+  if (kx + M > 64) return 1;
+  const int minus = (N_high & 1) ? 1 : 0;
+  for (int i = 0, k = 0; k <= N_low; k++) {
+    if (k > 0) i = 2 * k - minus;
+    S.f_table_res[SBR_LO_RES][k] = S.f_table_res[SBR_HI_RES][i];
+  }
+  int N_Q;
+  if (S.hdr.noise_bands == 0) N_Q = 1;
+  else {
+    N_Q = max(1, sbr_find_bands(C, 0, S.hdr.noise_bands, kx, k2));
+    N_Q = min(5, N_Q);
+  }
+  S.N_Q = (uint8_t)N_Q;
+  for (int i = 0, k = 0; k <= N_Q; k++) {
+    if (k > 0) i += (N_low - i) / (N_Q + 1 - k);
+    S.f_table_noise[k] = S.f_table_res[SBR_LO_RES][i];
+  }
+  for (int k = 0; k < 64; k++)
+    for (int g = 0; g < N_Q; g++)
+      if ((S.f_table_noise[g] <= k) && (k < S.f_table_noise[g + 1])) { S.table_map_k_to_g[k] = (uint8_t)g; break; }
+  return 0;
+}
+
+// SBR.calc_sbr_tables (:125-158).  Negative return: an internal index ran out of bounds (a Java exception).
+__device__ inline int sbr_calc_tables(const SbrCtx& C) {
+  SbrElemDev& S = *C.S;
+  const SbrHeaderDev& h = S.hdr;
+  int result = 0;
+  const int si = C.sr_index;
+  const int k0 = C.start_min[si] + C.offset[C.offset_index[si] * 16 + h.start_freq];   // bs_samplerate_mode = 1
+  int k2;
+  if (h.stop_freq == 15) k2 = min(64, k0 * 3);
+  else if (h.stop_freq == 14) k2 = min(64, k0 * 2);
+  else k2 = min(64, C.stop_min[si] + C.stop_offset[si * 14 + min((int)h.stop_freq, 13)]);
+  S.k0 = (uint8_t)k0;
+  const int freq = si == 0 ? 96000 : si == 1 ? 88200 : si == 2 ? 64000 : si == 3 ? 48000 : si == 4 ? 44100 : si == 5 ? 32000 :
+                   si == 6 ? 24000 : si == 7 ? 22050 : si == 8 ? 16000 : si == 9 ? 12000 : si == 10 ? 11025 : 8000;
+  if (freq >= 48000) { if ((k2 - k0) > 32) result += 1; }
+  else if (freq <= 32000) { if ((k2 - k0) > 48) result += 1; }
+  else { if ((k2 - k0) > 45) result += 1; }
+  int r;
+  if (h.freq_scale == 0) r = sbr_master_table_fs0(C, k0, k2, h.alter_scale != 0);
+  else r = sbr_master_table(C, k0, k2, h.freq_scale, h.alter_scale != 0);
+  if (r < 0) return r;
+  result += r;
+  r = sbr_derived_table(C, h.xover_band, k2);
+  if (r < 0) return r;
+  result += r;
+  return result > 0 ? 1 : 0;
+}
+
+// HFGeneration.patch_construction (:247-309)
+__device__ inline int sbr_patch_construction(const SbrCtx& C) {
+  SbrElemDev& S = *C.S;
+  int msb = S.k0, usb = S.kx;
+  const int goalSb = C.goal_sb[C.sr_index];
+  int noPatches = 0;
+  int k = 0;
+  if (goalSb < (S.kx + S.M)) { for (int i = 0; i < 64 && S.f_master[i] < goalSb; i++) k = i + 1; }
+  else k = S.N_master;
+  if (S.N_master == 0) { S.noPatches = 0; S.patchNoSubbands[0] = 0; S.patchStartSubband[0] = 0; return 0; }
+  int sb, guard = 0;
+  do {
+    int j = k + 1, odd;
+    do {
+      j--;
+      if (j < 0 || j >= 64) return JAADB_ST_SBR;
+      sb = S.f_master[j];
+      odd = (sb - 2 + S.k0) % 2;
+    } while (sb > (S.k0 - 1 + msb - odd));
+    const int nsub = max(sb - usb, 0);
+    S.patchNoSubbands[noPatches] = (uint8_t)nsub;
+    S.patchStartSubband[noPatches] = (int8_t)(S.k0 - odd - nsub);
+    if (nsub > 0) { usb = sb; msb = sb; noPatches++; }
+    else msb = S.kx;
+    if (k >= 0 && k < 64 && S.f_master[k] - sb < 3) k = S.N_master;
+    if (++guard > 1000 || noPatches >= 63) return JAADB_ST_SBR;
+  } while (sb != (S.kx + S.M));
+  if ((S.patchNoSubbands[noPatches - 1] < 3) && (noPatches > 1)) noPatches--;
+  S.noPatches = (uint8_t)min(noPatches, 5);
+  return 0;
+}
+
+// FBT.limiter_frequency_table (:329-416)
+__device__ inline void sbr_limiter_table(const SbrCtx& C) {
+  SbrElemDev& S = *C.S;
+  const int N_low = S.N_low, kx = S.kx, noPatches = S.noPatches;
+  S.f_table_lim[0][0] = (int8_t)(S.f_table_res[SBR_LO_RES][0] - kx);
+  S.f_table_lim[0][1] = (int8_t)(S.f_table_res[SBR_LO_RES][N_low] - kx);
+  S.N_L[0] = 1;
+  for (int s = 1; s < 4; s++) {
+    int limTable[100];
+    int patchBorders[64];
+    for (int i = 0; i < 100; ++i) limTable[i] = 0;
+    for (int i = 0; i < 64; ++i) patchBorders[i] = 0;
+    patchBorders[0] = kx;
+    for (int k = 1; k <= noPatches; k++) patchBorders[k] = patchBorders[k - 1] + S.patchNoSubbands[k - 1];
+    for (int k = 0; k <= N_low; k++) limTable[k] = S.f_table_res[SBR_LO_RES][k];
+    for (int k = 1; k < noPatches; k++) limTable[k + N_low] = patchBorders[k];
+    sbr_sort(limTable, 0, noPatches + N_low);
+    int k = 1;
+    int nrLim = noPatches + N_low - 1;
+    if (nrLim < 0) return;
+    while (k <= nrLim) {
+      float nOctaves;
+      if (limTable[k - 1] != 0) nOctaves = (float)limTable[k] / (float)limTable[k - 1];
+      else nOctaves = 0;
+      if (nOctaves < C.limiter_cmp[s - 1]) {
+        if (limTable[k] != limTable[k - 1]) {
+          bool found = false, found2 = false;
+          for (int i = 0; i <= noPatches; i++) if (limTable[k] == patchBorders[i]) found = true;
+          if (found) {
+            for (int i = 0; i <= noPatches; i++) if (limTable[k - 1] == patchBorders[i]) found2 = true;
+            if (found2) { k++; continue; }
+            limTable[k - 1] = S.f_table_res[SBR_LO_RES][N_low];
+            sbr_sort(limTable, 0, noPatches + N_low);
+            nrLim--;
+            continue;
+          }
+        }
+        limTable[k] = S.f_table_res[SBR_LO_RES][N_low];
+        sbr_sort(limTable, 0, nrLim);
+        nrLim--;
+      } else {
+        k++;
+      }
+    }
+    S.N_L[s] = (uint8_t)nrLim;
+    for (int l = 0; l <= nrLim; l++) S.f_table_lim[s][l] = (int8_t)(limTable[l] - kx);
+  }
+}
+
+// ---- Channel.java ------------------------------------------------------------------------------------------
+__device__ inline int sbr_log2(int val) {
+  return (val < 10 && val >= 0) ? ((0x4333322100ull >> (4 * val)) & 15) : 0;   // {0,0,1,2,2,3,3,3,3,4}
+}
+
+__device__ inline int sbr_middle_border(const SbrChanParse& c) {  // :543-568
+  int retval = 0;
+  switch (c.frame_class) {
+    case SBR_FIXFIX: retval = c.L_E / 2; break;
+    case SBR_VARFIX:
+      if (c.bs_pointer == 0) retval = 1;
+      else if (c.bs_pointer == 1) retval = c.L_E - 1;
+      else retval = c.bs_pointer - 1;
+      break;
+    default:
+      if (c.bs_pointer > 1) retval = c.L_E + 1 - c.bs_pointer;
+      else retval = c.L_E - 1;
+      break;
+  }
+  return retval > 0 ? retval : 0;
+}
+
+__device__ inline int sbr_time_border_vector(SbrChanParse& c) {  // :452-527; 1 = invalid grid
+  const int rate = 2, numTimeSlots = 16, numTimeSlotsRate = 32, tHFAdj = kSbrHfAdj, tHFGen = kSbrHfGen;
+  int eTmp[6];
+  for (int i = 0; i < 6; ++i) eTmp[i] = c.t_E[i];   // `eTmp` is a Channel field in the reference: it keeps old entries
+  // (every entry that is read below is written first, so the carried values never reach t_E beyond index L_E; they are
+  // copied along with System.arraycopy(eTmp, 0, t_E, 0, 6) and kept here for the same reason)
+  eTmp[0] = rate * c.abs_bord_lead;
+  eTmp[c.L_E] = rate * c.abs_bord_trail;
+  switch (c.frame_class) {
+    case SBR_FIXFIX:
+      if (c.L_E == 4) { const int temp = numTimeSlots / 4; eTmp[3] = rate * 3 * temp; eTmp[2] = rate * 2 * temp; eTmp[1] = rate * temp; }
+      else if (c.L_E == 2) eTmp[1] = rate * (numTimeSlots / 2);
+      break;
+    case SBR_FIXVAR:
+      if (c.L_E > 1) {
+        int i = c.L_E, border = c.abs_bord_trail;
+        for (int l = 0; l < (c.L_E - 1); l++) {
+          if (border < c.bs_rel_bord[l]) return 1;
+          border -= c.bs_rel_bord[l];
+          eTmp[--i] = rate * border;
+        }
+      }
+      break;
+    case SBR_VARFIX:
+      if (c.L_E > 1) {
+        int i = 1, border = c.abs_bord_lead;
+        for (int l = 0; l < (c.L_E - 1); l++) {
+          border += c.bs_rel_bord[l];
+          if (rate * border + tHFAdj > numTimeSlotsRate + tHFGen) return 1;
+          eTmp[i++] = rate * border;
+        }
+      }
+      break;
+    default:
+      if (c.bs_num_rel_0 != 0) {
+        int i = 1, border = c.abs_bord_lead;
+        for (int l = 0; l < c.bs_num_rel_0; l++) {
+          border += c.bs_rel_bord_0[l];
+          if (rate * border + tHFAdj > numTimeSlotsRate + tHFGen) return 1;
+          if (i > 5) return -JAADB_ST_SBR;
+          eTmp[i++] = rate * border;
+        }
+      }
+      if (c.bs_num_rel_1 != 0) {
+        int i = c.L_E, border = c.abs_bord_trail;
+        for (int l = 0; l < c.bs_num_rel_1; l++) {
+          if (border < c.bs_rel_bord_1[l]) return 1;
+          border -= c.bs_rel_bord_1[l];
+          if (i < 1) return -JAADB_ST_SBR;
+          eTmp[--i] = rate * border;
+        }
+      }
+      break;
+  }
+  for (int i = 0; i < 6; ++i) c.t_E[i] = (uint8_t)eTmp[i];
+  return 0;
+}
+
+// Channel.sbr_grid (:315-437).  Returns 0, 1 (invalid grid: sbr_data gives up, valid = false) or a negative status.
+__device__ inline int sbr_grid(SbrBits& ld, SbrChanParse& c, int& eos) {
+  const int numTimeSlots = 16;
+  eos = 0;
+#define GRID_RD(var, n) do { if (!ld.get((n), (var))) { eos = 1; return -JAADB_ST_EOS; } } while (0)
+  const int saved_L_E = c.L_E, saved_L_Q = c.L_Q, saved_class = c.frame_class;
+  int v;
+  GRID_RD(v, 2);
+  c.frame_class = (uint8_t)v;
+  switch (c.frame_class) {
+    case SBR_FIXFIX: {
+      int i;
+      GRID_RD(i, 2);
+      const int bs_num_env = min(1 << i, 5);
+      GRID_RD(i, 1);
+      for (int env = 0; env < bs_num_env; env++) c.f[env] = (uint8_t)i;
+      c.L_E = (uint8_t)min(bs_num_env, 4);
+      c.abs_bord_lead = 0;
+      c.abs_bord_trail = numTimeSlots;
+      break;
+    }
+    case SBR_FIXVAR: {
+      int bs_abs_bord, bs_num_env;
+      GRID_RD(bs_abs_bord, 2);
+      bs_abs_bord += numTimeSlots;
+      GRID_RD(bs_num_env, 2);
+      bs_num_env += 1;
+      for (int rel = 0; rel < bs_num_env - 1; rel++) { GRID_RD(v, 2); c.bs_rel_bord[rel] = (uint8_t)(2 * v + 2); }
+      GRID_RD(v, sbr_log2(bs_num_env + 1));
+      c.bs_pointer = (uint8_t)v;
+      for (int env = 0; env < bs_num_env; env++) { GRID_RD(v, 1); c.f[bs_num_env - env - 1] = (uint8_t)v; }
+      c.L_E = (uint8_t)min(bs_num_env, 4);
+      c.abs_bord_lead = 0;
+      c.abs_bord_trail = (uint8_t)bs_abs_bord;
+      break;
+    }
+    case SBR_VARFIX: {
+      int bs_abs_bord, bs_num_env;
+      GRID_RD(bs_abs_bord, 2);
+      GRID_RD(bs_num_env, 2);
+      bs_num_env += 1;
+      for (int rel = 0; rel < bs_num_env - 1; rel++) { GRID_RD(v, 2); c.bs_rel_bord[rel] = (uint8_t)(2 * v + 2); }
+      GRID_RD(v, sbr_log2(bs_num_env + 1));
+      c.bs_pointer = (uint8_t)v;
+      for (int env = 0; env < bs_num_env; env++) { GRID_RD(v, 1); c.f[env] = (uint8_t)v; }
+      c.L_E = (uint8_t)min(bs_num_env, 4);
+      c.abs_bord_lead = (uint8_t)bs_abs_bord;
+      c.abs_bord_trail = numTimeSlots;
+      break;
+    }
+    default: {
+      int bs_abs_bord, bs_abs_bord_1, n0, n1;
+      GRID_RD(bs_abs_bord, 2);
+      GRID_RD(bs_abs_bord_1, 2);
+      bs_abs_bord_1 += numTimeSlots;
+      GRID_RD(n0, 2);
+      c.bs_num_rel_0 = (uint8_t)n0;
+      GRID_RD(n1, 2);
+      c.bs_num_rel_1 = (uint8_t)n1;
+      const int bs_num_env = min(5, n0 + n1 + 1);
+      for (int rel = 0; rel < n0; rel++) { GRID_RD(v, 2); c.bs_rel_bord_0[rel] = (uint8_t)(2 * v + 2); }
+      for (int rel = 0; rel < n1; rel++) { GRID_RD(v, 2); c.bs_rel_bord_1[rel] = (uint8_t)(2 * v + 2); }
+      GRID_RD(v, sbr_log2(n0 + n1 + 2));
+      c.bs_pointer = (uint8_t)v;
+      for (int env = 0; env < bs_num_env; env++) { GRID_RD(v, 1); c.f[env] = (uint8_t)v; }
+      c.L_E = (uint8_t)min(bs_num_env, 5);
+      c.abs_bord_lead = (uint8_t)bs_abs_bord;
+      c.abs_bord_trail = (uint8_t)bs_abs_bord_1;
+      break;
+    }
+  }
+#undef GRID_RD
+  if (c.L_E <= 0) return 1;
+  c.L_Q = (c.L_E > 1) ? 2 : 1;
+  const int r = sbr_time_border_vector(c);
+  if (r != 0) {
+    if (r > 0) { c.frame_class = (uint8_t)saved_class; c.L_E = (uint8_t)saved_L_E; c.L_Q = (uint8_t)saved_L_Q; }
+    return r;
+  }
+  // noise_floor_time_border_vector (:529-541)
+  c.t_Q[0] = c.t_E[0];
+  if (c.L_E == 1) { c.t_Q[1] = c.t_E[1]; c.t_Q[2] = 0; }
+  else { const int index = sbr_middle_border(c); c.t_Q[1] = c.t_E[index]; c.t_Q[2] = c.t_E[c.L_E]; }
+  return 0;
+}
+
+__device__ inline int sbr_dtdf(SbrBits& ld, SbrChanParse& c) {  // :85-94
+  int v;
+  for (int i = 0; i < c.L_E; i++) { SBR_RD(v, 1); c.bs_df_env[i] = (uint8_t)v; }
+  for (int i = 0; i < c.L_Q; i++) { SBR_RD(v, 1); c.bs_df_noise[i] = (uint8_t)v; }
+  return 0;
+}
+
+__device__ inline int sbr_invf_mode(SbrBits& ld, SbrChanParse& c, int N_Q) {  // :97-101
+  int v;
+  for (int i = 0; i < N_Q; i++) { SBR_RD(v, 2); c.bs_invf_mode[i] = (uint8_t)v; }
+  return 0;
+}
+
+__device__ inline int sbr_huff(SbrBits& ld, const int16_t* __restrict__ t, int& out) {  // :280-289
+  int index = 0;
+  while (index >= 0) {
+    int bit;
+    SBR_RD(bit, 1);
+    index = t[index * 2 + bit];
+  }
+  out = index + 64;
+  return 0;
+}
+
+__device__ inline void sbr_extract_envelope(const SbrElemDev& S, SbrChanParse& c) {  // :192-240
+  for (int l = 0; l < c.L_E; l++) {
+    const int nb = S.n[c.f[l]];
+    if (c.bs_df_env[l] == 0) {
+      for (int k = 1; k < nb; k++) {
+        int v = c.E[k - 1][l] + c.E[k][l];
+        if (v < 0) v = 0;
+        c.E[k][l] = (int16_t)v;
+      }
+    } else {
+      const int g = (l == 0) ? c.f_prev : c.f[l - 1];
+      if (c.f[l] == g) {
+        for (int k = 0; k < nb; k++) {
+          const int prev = l == 0 ? c.E_prev[k] : c.E[k][l - 1];
+          c.E[k][l] = (int16_t)(prev + c.E[k][l]);
+        }
+      } else if ((g == 1) && (c.f[l] == 0)) {
+        for (int k = 0; k < nb; k++)
+          for (int i = 0; i < S.N_high; i++)
+            if (S.f_table_res[SBR_HI_RES][i] == S.f_table_res[SBR_LO_RES][k]) {
+              const int prev = l == 0 ? c.E_prev[i] : c.E[i][l - 1];
+              c.E[k][l] = (int16_t)(prev + c.E[k][l]);
+            }
+      } else if ((g == 0) && (c.f[l] == 1)) {
+        for (int k = 0; k < nb; k++)
+          for (int i = 0; i < S.N_low; i++)
+            if ((S.f_table_res[SBR_LO_RES][i] <= S.f_table_res[SBR_HI_RES][k]) &&
+                (S.f_table_res[SBR_HI_RES][k] < S.f_table_res[SBR_LO_RES][i + 1])) {
+              const int prev = l == 0 ? c.E_prev[i] : c.E[i][l - 1];
+              c.E[k][l] = (int16_t)(prev + c.E[k][l]);
+            }
+      }
+    }
+  }
+}
+
+__device__ inline int sbr_envelope(SbrBits& ld, const SbrCtx& C, SbrChanParse& c, bool coupled) {  // :126-190
+  const SbrElemDev& S = *C.S;
+  if ((c.L_E == 1) && (c.frame_class == SBR_FIXFIX)) c.amp_res = 0;
+  else c.amp_res = S.hdr.amp_res;
+  const int delta = coupled ? 1 : 0;
+  const int16_t *t_huff, *f_huff;
+  if (coupled) { t_huff = C.T->huff[c.amp_res ? 6 : 2]; f_huff = C.T->huff[c.amp_res ? 7 : 3]; }
+  else { t_huff = C.T->huff[c.amp_res ? 4 : 0]; f_huff = C.T->huff[c.amp_res ? 5 : 1]; }
+  for (int env = 0; env < c.L_E; env++) {
+    const int nb = S.n[c.f[env]];
+    int v;
+    if (c.bs_df_env[env] == 0) {
+      const int bits = coupled ? (c.amp_res ? 5 : 6) : (c.amp_res ? 6 : 7);
+      SBR_RD(v, bits);
+      c.E[0][env] = (int16_t)(v << delta);
+      for (int band = 1; band < nb; band++) { SBR_TRY(sbr_huff(ld, f_huff, v)); c.E[band][env] = (int16_t)(v << delta); }
+    } else {
+      for (int band = 0; band < nb; band++) { SBR_TRY(sbr_huff(ld, t_huff, v)); c.E[band][env] = (int16_t)(v << delta); }
+    }
+  }
+  sbr_extract_envelope(S, c);
+  return 0;
+}
+
+__device__ inline int sbr_noise(SbrBits& ld, const SbrCtx& C, SbrChanParse& c, bool coupled) {  // :243-312
+  const SbrElemDev& S = *C.S;
+  const int delta = coupled ? 1 : 0;
+  const int16_t* t_huff = C.T->huff[coupled ? 9 : 8];
+  const int16_t* f_huff = C.T->huff[coupled ? 7 : 5];
+  for (int noise = 0; noise < c.L_Q; noise++) {
+    int v;
+    if (c.bs_df_noise[noise] == 0) {
+      SBR_RD(v, 5);
+      c.Q[0][noise] = (int16_t)(v << delta);
+      for (int band = 1; band < S.N_Q; band++) { SBR_TRY(sbr_huff(ld, f_huff, v)); c.Q[band][noise] = (int16_t)(v << delta); }
+    } else {
+      for (int band = 0; band < S.N_Q; band++) { SBR_TRY(sbr_huff(ld, t_huff, v)); c.Q[band][noise] = (int16_t)(v << delta); }
+    }
+  }
+  for (int l = 0; l < c.L_Q; l++) {
+    if (c.bs_df_noise[l] == 0) {
+      for (int k = 1; k < S.N_Q; k++) c.Q[k][l] = (int16_t)(c.Q[k][l] + c.Q[k - 1][l]);
+    } else if (l == 0) {
+      for (int k = 0; k < S.N_Q; k++) c.Q[k][l] = (int16_t)(c.Q_prev[k] + c.Q[k][0]);
+    } else {
+      for (int k = 0; k < S.N_Q; k++) c.Q[k][l] = (int16_t)(c.Q[k][l - 1] + c.Q[k][l]);
+    }
+  }
+  return 0;
+}
+
+__device__ inline int sbr_sinusoidal(SbrBits& ld, SbrChanParse& c, int N_high) {  // SBR.java:249-254
+  int v;
+  for (int i = 0; i < N_high; i++) { SBR_RD(v, 1); c.bs_add_harmonic[i] = (uint8_t)v; }
+  return 0;
+}
+
+__device__ inline int sbr_harmonics(SbrBits& ld, SbrChanParse& c, int N_high) {
+  int v;
+  SBR_RD(v, 1);
+  c.add_harmonic_flag = (uint8_t)v;
+  if (v) SBR_TRY(sbr_sinusoidal(ld, c, N_high));
+  return 0;
+}
+
+// SBR.readExtendedData (:229-242).  Extension payloads (parametric stereo = id 2) are skipped in this build: the
+// engine refuses SBR+PS streams at open, and for plain SBR streams the reference's sbr_extension is a no-op that
+// re-reads 2-bit ids until fewer than 8 bits remain -- nothing observable.
+__device__ inline int sbr_extended_data(SbrBits& ld) {
+  int v;
+  SBR_RD(v, 1);
+  if (v) {
+    int cnt;
+    SBR_RD(cnt, 4);
+    if (cnt == 15) { SBR_RD(v, 8); cnt += v; }
+    if (ld.left() < (uint32_t)(8 * cnt)) return JAADB_ST_EOS;
+    ld.pos += 8 * cnt;
+  }
+  return 0;
+}
+
+// SBR1.sbr_data (:34-60) / SBR2.sbr_data (:35-135).  `valid` as SBR.decode sets it.
+__device__ inline int sbr_data(SbrBits& ld, const SbrCtx& C, bool stereo, int& result) {
+  SbrElemDev& S = *C.S;
+  SbrChanParse& c0 = S.ch[0];
+  SbrChanParse& c1 = S.ch[1];
+  int v, eos;
+  result = 0;
+  SBR_RD(v, 1);
+  if (v) { SBR_RD(v, 4); if (stereo) SBR_RD(v, 4); }
+  if (!stereo) {
+    int r = sbr_grid(ld, c0, eos);
+    if (r < 0) return -r;
+    if (r > 0) { result = r; return 0; }
+    SBR_TRY(sbr_dtdf(ld, c0));
+    SBR_TRY(sbr_invf_mode(ld, c0, S.N_Q));
+    SBR_TRY(sbr_envelope(ld, C, c0, false));
+    SBR_TRY(sbr_noise(ld, C, c0, false));
+    // NoiseEnvelope.dequantChannel happens here in the reference; the float tables are evaluated when the frame record
+    // is built (same inputs: E, Q, amp_res, f, n)
+    for (int i = 0; i < 64; ++i) c0.bs_add_harmonic[i] = 0;
+    SBR_TRY(sbr_harmonics(ld, c0, S.N_high));
+    SBR_TRY(sbr_extended_data(ld));
+    return 0;
+  }
+  SBR_RD(v, 1);
+  S.bs_coupling = (uint8_t)v;
+  if (S.bs_coupling) {
+    int r = sbr_grid(ld, c0, eos);
+    if (r < 0) return -r;
+    if (r > 0) { result = r; return 0; }
+    SBR_TRY(sbr_dtdf(ld, c0));
+    SBR_TRY(sbr_dtdf(ld, c1));          // with ch1's OLD L_E / L_Q: the grid is copied over only below
+    SBR_TRY(sbr_invf_mode(ld, c0, S.N_Q));
+    // Channel.couple (:103-122)
+    c1.frame_class = c0.frame_class;
+    c1.L_E = c0.L_E;
+    c1.L_Q = c0.L_Q;
+    c1.bs_pointer = c0.bs_pointer;
+    for (int i = 0; i <= c0.L_E; i++) { c1.t_E[i] = c0.t_E[i]; c1.f[i] = c0.f[i]; }
+    for (int i = 0; i <= c0.L_Q; i++) c1.t_Q[i] = c0.t_Q[i];
+    for (int i = 0; i < S.N_Q; i++) c1.bs_invf_mode[i] = c0.bs_invf_mode[i];
+    SBR_TRY(sbr_envelope(ld, C, c0, false));
+    SBR_TRY(sbr_noise(ld, C, c0, false));
+    SBR_TRY(sbr_envelope(ld, C, c1, true));
+    SBR_TRY(sbr_noise(ld, C, c1, true));
+    for (int i = 0; i < 64; ++i) { c0.bs_add_harmonic[i] = 0; c1.bs_add_harmonic[i] = 0; }
+    SBR_TRY(sbr_harmonics(ld, c0, S.N_high));
+    SBR_TRY(sbr_harmonics(ld, c1, S.N_high));
+  } else {
+    uint8_t saved_t_E[6] = {0, 0, 0, 0, 0, 0}, saved_t_Q[3] = {0, 0, 0};
+    const int saved_L_E = c0.L_E, saved_L_Q = c0.L_Q, saved_class = c0.frame_class;
+    for (int i = 0; i < saved_L_E && i < 6; i++) saved_t_E[i] = c0.t_E[i];
+    for (int i = 0; i < saved_L_Q && i < 3; i++) saved_t_Q[i] = c0.t_Q[i];
+    int r = sbr_grid(ld, c0, eos);
+    if (r < 0) return -r;
+    if (r > 0) { result = r; return 0; }
+    r = sbr_grid(ld, c1, eos);
+    if (r < 0) return -r;
+    if (r > 0) {
+      c0.frame_class = (uint8_t)saved_class;
+      c0.L_E = (uint8_t)saved_L_E;
+      c0.L_Q = (uint8_t)saved_L_Q;
+      for (int i = 0; i < 6; i++) c0.t_E[i] = saved_t_E[i];
+      for (int i = 0; i < 3; i++) c0.t_Q[i] = saved_t_Q[i];
+      result = r;
+      return 0;
+    }
+    SBR_TRY(sbr_dtdf(ld, c0));
+    SBR_TRY(sbr_dtdf(ld, c1));
+    SBR_TRY(sbr_invf_mode(ld, c0, S.N_Q));
+    SBR_TRY(sbr_invf_mode(ld, c1, S.N_Q));
+    SBR_TRY(sbr_envelope(ld, C, c0, false));
+    SBR_TRY(sbr_envelope(ld, C, c1, false));
+    SBR_TRY(sbr_noise(ld, C, c0, false));
+    SBR_TRY(sbr_noise(ld, C, c1, false));
+    for (int i = 0; i < 64; ++i) { c0.bs_add_harmonic[i] = 0; c1.bs_add_harmonic[i] = 0; }
+    SBR_TRY(sbr_harmonics(ld, c0, S.N_high));
+    SBR_TRY(sbr_harmonics(ld, c1, S.N_high));
+  }
+  SBR_TRY(sbr_extended_data(ld));
+  return 0;
+}
+
+// SBR.decode (:161-185).  Returns a frame status (0 = fine).
+__device__ inline int sbr_decode(SbrBits& ld, const SbrCtx& C, bool stereo, bool crc) {
+  SbrElemDev& S = *C.S;
+  int v;
+  if (crc) SBR_RD(v, 10);
+  // readHeader (:214-223)
+  SBR_RD(v, 1);
+  bool reset = false;
+  if (v) {
+    sbr_swap_headers(S);
+    SBR_TRY(sbr_header_decode(ld, S.hdr));
+    S.hdr.present = 1;
+    reset = sbr_header_differs(S.hdr, S.hdr_saved);
+  }
+  S.reset = reset ? 1 : 0;
+  if (reset) {
+    int rt = sbr_calc_tables(C);
+    if (rt < 0) return -rt;
+    if (rt > 0) {
+      sbr_swap_headers(S);
+      rt = sbr_calc_tables(C);
+      if (rt < 0) return -rt;
+    }
+  }
+  if (S.hdr.present) {
+    int result = 0;
+    SBR_TRY(sbr_data(ld, C, stereo, result));
+    S.valid = (result == 0) ? 1 : 0;
+  } else {
+    S.valid = 1;
+  }
+  return 0;
+}
+
+// ---- NoiseEnvelope.java: dequantisation of one (band, envelope) / (band, noise floor) entry ---------------------
+__device__ inline float sbr_e_orig(const SbrTablesDev& T, const SbrElemDev& S, bool stereo, int ch, int k, int l) {
+  if (stereo && S.bs_coupling) {
+    // unmap (:299-345)
+    const int amp0 = S.ch[0].amp_res ? 0 : 1, amp1 = S.ch[1].amp_res ? 0 : 1;
+    const int ch0E = S.ch[0].E[k][l];
+    const int exp0 = (ch0E >> amp0) + 1;
+    const int exp1 = (S.ch[1].E[k][l] >> amp1);
+    if ((exp0 < 0) || (exp0 >= 64) || (exp1 < 0) || (exp1 > 24)) return 0.f;
+    float tmp = T.e_deq[exp0];
+    if (amp0 != 0 && (ch0E & 1) != 0) tmp = (float)((double)tmp * 1.414213562);   // `tmp *= 1.414213562` (double literal)
+    return tmp * T.e_pan[ch == 0 ? exp1 : 24 - exp1];
+  }
+  // dequantChannel (:250-281)
+  const SbrChanParse& c = S.ch[ch];
+  const int amp = c.amp_res ? 0 : 1;
+  const int e = c.E[k][l];
+  const int exp = e >> amp;
+  if ((exp < 0) || (exp >= 64)) return 0.f;
+  float v = T.e_deq[exp];
+  if (amp != 0 && (e & 1) != 0) v = v * 1.414213562f;
+  return v;
+}
+
+__device__ inline void sbr_q_div(const SbrTablesDev& T, const SbrElemDev& S, bool stereo, int ch, int k, int l, float& qd, float& qd2) {
+  if (stereo && S.bs_coupling) {
+    const int q0 = S.ch[0].Q[k][l], q1 = S.ch[1].Q[k][l];
+    if ((q0 < 0 || q0 > 30) || (q1 < 0 || q1 > 24)) { qd = 0.f; qd2 = 0.f; return; }
+    qd = (ch == 0 ? T.q_div_left : T.q_div_right)[q0 * 13 + (q1 >> 1)];
+    qd2 = (ch == 0 ? T.q_div2_left : T.q_div2_right)[q0 * 13 + (q1 >> 1)];
+    return;
+  }
+  const int q = S.ch[ch].Q[k][l];
+  if (q < 0 || q > 30) { qd = 0.f; qd2 = 0.f; return; }
+  qd = T.q_div[q];
+  qd2 = T.q_div2[q];
+}
+
+struct SbrConstTables {
+  const int32_t *start_min, *offset_index, *offset, *stop_min, *stop_offset, *goal_sb;
+  const float* limiter_cmp;
+};
+
+constexpr int kK3WarpsPerBlock = 4;
+
+__global__ void __launch_bounds__(32 * kK3WarpsPerBlock)
+k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ frames, FrameSide* __restrict__ fside,
+                    const SbrRunDev* __restrict__ runs, uint32_t n_runs, const RunFrameDev* __restrict__ run_frames,
+                    SbrElemDev* __restrict__ elems, SbrFrameDev* __restrict__ out, SbrTablesDev T, SbrConstTables K) {
+  extern __shared__ __align__(16) uint8_t k3_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t r = blockIdx.x * kK3WarpsPerBlock + warp;
+  if (r >= n_runs) return;
+  const SbrRunDev run = runs[r];
+  SbrElemDev* S = reinterpret_cast<SbrElemDev*>(k3_smem) + warp;
+  SbrElemDev* G = elems + (size_t)run.stream_slot * 2 + run.element;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(G);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(S);
+    for (int i = lane; i < (int)(sizeof(SbrElemDev) / 4); i += 32) dst[i] = src[i];
+  }
+  __syncwarp();
+  SbrCtx C;
+  C.S = S; C.T = &T; C.start_min = K.start_min; C.offset_index = K.offset_index; C.offset = K.offset; C.stop_min = K.stop_min;
+  C.stop_offset = K.stop_offset; C.goal_sb = K.goal_sb; C.limiter_cmp = K.limiter_cmp; C.sr_index = run.sr_index;
+  const bool stereo = run.stereo != 0;
+  const int nch = stereo ? 2 : 1;
+
+  for (uint32_t it = 0; it < run.count; ++it) {
+    const uint32_t f = run_frames[run.first + it].frame;
+    int mode = 0;          // what K4 does with the frame (SbrFrameDev.mode)
+    int frame_status = 0;
+    if (lane == 0) {
+      const FrameDev fr = frames[f];
+      FrameSide fs = fside[f];
+      frame_status = fs.status;
+      // ChannelElement.decode invalidates the element's SBR at the start of every frame (ChannelElement.java:58-61);
+      // the element was reached iff K1 counted it
+      if (S->opened && run.element < fs.n_elements) S->valid = 0;
+      const uint32_t nbits = fs.sbr_bits[run.element];
+      if (nbits) {
+        // the FIL payload was seen by K1 (also in frames that failed later on): decodeSBR runs
+        S->opened = 1;
+        const uint64_t addr = reinterpret_cast<uint64_t>(blob) + fr.blob_off;
+        SbrBits ld;
+        ld.words = reinterpret_cast<const uint32_t*>(addr - (addr & 3u));
+        ld.pos = fs.sbr_bit_off[run.element];
+        ld.end = ld.pos + nbits;
+        int ext = 0;
+        ld.get(4, ext);
+        const int st = sbr_decode(ld, C, stereo, ext == 14);
+        if (st != 0 && frame_status == 0) {
+          // an exception inside SBR.decode fails the whole frame (EOS is swallowed by decodeFrame: no output)
+          frame_status = st;
+          fs.status = st;
+          fside[f].status = st;
+        }
+      }
+      if (frame_status == 0 && S->opened && S->valid) {
+        mode = S->hdr.present ? 2 : 1;
+        if (mode == 2) {
+          // hf_adjustment's l_A (HFAdjustment.java:24-38) for each channel
+          for (int c = 0; c < nch; ++c) {
+            SbrChanParse& cp = S->ch[c];
+            if (cp.frame_class == SBR_FIXFIX) cp.l_A = -1;
+            else if (cp.frame_class == SBR_VARFIX) cp.l_A = (cp.bs_pointer > 1) ? (int8_t)(cp.bs_pointer - 1) : (int8_t)-1;
+            else cp.l_A = (cp.bs_pointer == 0) ? (int8_t)-1 : (int8_t)(cp.L_E + 1 - cp.bs_pointer);
+          }
+          if (S->reset) {
+            // the reference builds patches and limiter bands inside the first hf_generation after a reset
+            const int pst = sbr_patch_construction(C);
+            if (pst != 0) { frame_status = pst; fside[f].status = pst; mode = 0; }
+            else sbr_limiter_table(C);
+          }
+        }
+      }
+    }
+    mode = __shfl_sync(0xFFFFFFFFu, mode, 0);
+    frame_status = __shfl_sync(0xFFFFFFFFu, frame_status, 0);
+    __syncwarp();
+    // ---- frame records (all lanes)
+    for (int c = 0; c < nch; ++c) {
+      SbrFrameDev* o = out + ((size_t)run.sbr_base + it) * 2 + c;
+      const SbrChanParse& cp = S->ch[c];
+      if (mode == 2) {
+        for (int i = lane; i < kSbrMaxLE * 64; i += 32) {
+          const int l = i >> 6, k = i & 63;
+          float v = 0.f;
+          if (l < cp.L_E && k < S->n[cp.f[l]]) v = sbr_e_orig(T, *S, stereo, c, k, l);
+          o->E_orig[l][k] = v;
+        }
+        if (lane < 16) {
+          const int l = lane >> 3, k = lane & 7;
+          float qd = 0.f, qd2 = 0.f;
+          if (l < cp.L_Q && k < S->N_Q) sbr_q_div(T, *S, stereo, c, k, l, qd, qd2);
+          o->Q_div[l][k] = qd;
+          o->Q_div2[l][k] = qd2;
+        }
+        for (int i = lane; i < 64; i += 32) {
+          o->f_table_res[0][i] = S->f_table_res[0][i];
+          o->f_table_res[1][i] = S->f_table_res[1][i];
+          o->f_table_lim[i] = S->f_table_lim[S->hdr.limiter_bands][i];
+          o->table_map_k_to_g[i] = S->table_map_k_to_g[i];
+          o->bs_add_harmonic[i] = cp.bs_add_harmonic[i];
+          o->bs_add_harmonic_prev[i] = cp.bs_add_harmonic_prev[i];
+        }
+        if (lane < 8) {
+          o->f_table_noise[lane] = S->f_table_noise[lane];
+          o->patchNoSubbands[lane] = S->patchNoSubbands[lane];
+          o->patchStartSubband[lane] = S->patchStartSubband[lane];
+        }
+        if (lane < 6) { o->t_E[lane] = cp.t_E[lane]; o->f[lane] = cp.f[lane]; }
+        if (lane < 3) o->t_Q[lane] = cp.t_Q[lane];
+        if (lane < 5) o->bs_invf_mode[lane] = cp.bs_invf_mode[lane];
+      }
+      if (lane == 0) {
+        o->mode = (uint8_t)mode;
+        o->frame_status = (uint8_t)frame_status;
+        // SBR2.process passes reset = false for the second channel's patch construction; the patches are built above once
+        o->reset = S->reset;
+        o->L_E = cp.L_E; o->L_Q = cp.L_Q; o->kx = S->kx; o->M = S->M; o->N_high = S->N_high; o->N_low = S->N_low; o->N_Q = S->N_Q;
+        o->N_L = S->N_L[S->hdr.limiter_bands]; o->kx_prev = S->kx_prev; o->M_prev = S->M_prev; o->noPatches = S->noPatches;
+        o->limiter_gains = S->hdr.limiter_gains; o->interpol_freq = S->hdr.interpol_freq; o->smoothing_mode = S->hdr.smoothing_mode;
+        o->add_harmonic_flag_prev = cp.add_harmonic_flag_prev;
+        o->l_A = cp.l_A; o->prevEnvIsShort = cp.prevEnvIsShort;
+      }
+    }
+    __syncwarp();
+    // ---- what SBR.process leaves behind for the next frame's parse (sbr_save_prev_data, SBR.java:256-284)
+    if (lane == 0 && mode == 2) {
+      for (int c = 0; c < nch; ++c) {
+        SbrChanParse& cp = S->ch[c];
+        S->kx_prev = S->kx;
+        S->M_prev = S->M;
+        cp.L_E_prev = cp.L_E;
+        cp.f_prev = cp.f[cp.L_E - 1];
+        for (int i = 0; i < kSbrMaxM; i++) { cp.E_prev[i] = cp.E[i][cp.L_E - 1]; cp.Q_prev[i] = cp.Q[i][cp.L_Q - 1]; }
+        for (int i = 0; i < kSbrMaxM; i++) cp.bs_add_harmonic_prev[i] = cp.bs_add_harmonic[i];
+        cp.add_harmonic_flag_prev = cp.add_harmonic_flag;
+        cp.prevEnvIsShort = (cp.l_A == cp.L_E) ? 0 : -1;
+      }
+    }
+    __syncwarp();
+  }
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(S);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(G);
+    for (int i = lane; i < (int)(sizeof(SbrElemDev) / 4); i += 32) dst[i] = src[i];
+  }
+}
+
+}  // namespace jaadb

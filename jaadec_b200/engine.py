@@ -143,6 +143,24 @@ class Batch:
         self.engine._check(self._lib.jaadb_batch_tap(self._h, frame, ch, _ptr(q), _ptr(sf), _ptr(cb), _ptr(spec), _ptr(info), _ptr(ms)), "batch_tap")
         return dict(q=q, sfidx=sf, sfbcb=cb, spec=spec, info=info, msused=ms)
 
+    SBR_FRAME_DTYPE = np.dtype([
+        ("E_orig", "<f4", (5, 64)), ("Q_div", "<f4", (2, 8)), ("Q_div2", "<f4", (2, 8)), ("f_table_res", "u1", (2, 64)),
+        ("f_table_noise", "u1", (8,)), ("f_table_lim", "i1", (64,)), ("table_map_k_to_g", "u1", (64,)),
+        ("bs_add_harmonic", "u1", (64,)), ("bs_add_harmonic_prev", "u1", (64,)), ("patchNoSubbands", "u1", (8,)),
+        ("patchStartSubband", "i1", (8,)), ("t_E", "u1", (6,)), ("t_Q", "u1", (3,)), ("f", "u1", (6,)), ("bs_invf_mode", "u1", (5,)),
+        ("mode", "u1"), ("reset", "u1"), ("L_E", "u1"), ("L_Q", "u1"), ("kx", "u1"), ("M", "u1"), ("N_high", "u1"), ("N_low", "u1"),
+        ("N_Q", "u1"), ("N_L", "u1"), ("kx_prev", "u1"), ("M_prev", "u1"), ("noPatches", "u1"), ("limiter_gains", "u1"),
+        ("interpol_freq", "u1"), ("smoothing_mode", "u1"), ("add_harmonic_flag_prev", "u1"), ("l_A", "i1"),
+        ("prevEnvIsShort", "i1"), ("frame_status", "u1"), ("pad", "u1", (16,))])
+
+    def tap_sbr(self, frame: int, ch: int):
+        """SBR record of frame `frame`, channel `ch` (None when the stream carries no SBR)."""
+        out = np.zeros(1, self.SBR_FRAME_DTYPE)
+        rc = self._lib.jaadb_batch_tap_sbr(self._h, frame, ch, out.ctypes.data, out.nbytes)
+        if rc < 0:
+            raise EngineError("batch_tap_sbr failed: %d" % rc)
+        return out[0] if rc > 0 else None
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.jaadb_batch_destroy(self._h)

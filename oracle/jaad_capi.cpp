@@ -160,6 +160,8 @@ int jo_tap_sbr(void* hv, int el, int ch, int32_t* out) {
   int32_t* x = out + 480;
   x[0] = s->kx; x[1] = s->M; x[2] = s->N_high; x[3] = s->N_low; x[4] = s->N_Q; x[5] = s->k0; x[6] = s->N_master;
   x[7] = s->noPatches; x[8] = s->reset ? 1 : 0; x[9] = s->isValid() ? 1 : 0;
+  if (s->hdr) { x[10] = s->hdr->bs_limiter_bands; x[11] = s->hdr->bs_limiter_gains; x[12] = s->hdr->bs_interpol_freq; x[13] = s->hdr->bs_smoothing_mode;
+                x[14] = s->hdr->bs_freq_scale; x[15] = s->hdr->bs_noise_bands; }
   for (int l = 0; l < 5; ++l) for (int k = 0; k < 64; ++k) memcpy(&x[16 + l * 64 + k], &c->E_orig[k][l], 4);
   for (int l = 0; l < 2; ++l) for (int k = 0; k < 64; ++k) memcpy(&x[16 + 320 + l * 64 + k], &c->Q_div[k][l], 4);
   return 0;

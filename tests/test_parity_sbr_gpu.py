@@ -1,0 +1,107 @@
+"""GPU parity tests for HE-AAC v1 (AAC-LC core + SBR): CUDA engine through the C ABI vs the CPU oracle.
+
+K1 parses the core, K3 the SBR payload (sequential per element: headers, delta-time coding), K2 produces the core PCM,
+K4 runs QMF analysis -> HF generation -> HF adjustment -> QMF synthesis.  Float PCM is compared bit for bit: the SBR
+kernels keep JAAD's operation order exactly like the AAC-LC ones.
+"""
+import numpy as np
+import pytest
+
+import gen
+from helpers import Workload, same_float_bits
+from jaadec_b200 import Engine, PCM_F32_PLANAR, PCM_S16BE, PCM_S16LE
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("c3_stereo_sbr", gen.config(3, n_frames=45), 6),
+    ("mono_sbr", gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=45, target_bytes=171, sbr_mode=1), 4),
+    ("stereo_sbr_32k", gen.GenConfig(sf_index=8, chan_cfg=2, n_frames=30, target_bytes=300, sbr_mode=1), 3),
+]
+
+
+@pytest.mark.parametrize("label,cfg,n_streams", CASES, ids=[c[0] for c in CASES])
+def test_sbr_float_pcm_bit_exact(label, cfg, n_streams):
+    wl = Workload(cfg, n_streams, base_seed=gen.seed_for(3, 40), with_truth=False)
+    decs = wl.oracle_decoders()
+    eng = Engine(max_streams=16, pcm_format=PCM_F32_PLANAR)
+    ids = [eng.open_adts(*wl.hdr, expect_sbr=1) for _ in range(n_streams)]
+    info = eng.stream_info(ids[0])
+    assert (info.channels, info.sample_length) == (2, 2048)
+    frames, index = wl.frame_table(ids)
+    pcm, res = eng.decode(wl.blob, frames)
+    per = 2 * 2048 * 4
+    worst = 0.0
+    for i, (s, f) in enumerate(index):
+        r = decs[s].decode_frame(wl.frame_bytes(s, f))
+        assert res["status"][i] == r["status"] == 0, (label, s, f, res["status"][i], r["status"])
+        assert (res["channels"][i], res["sample_length"][i], res["sample_rate"][i]) == (r["channels"], r["sample_length"], r["sample_rate"])
+        assert res["pcm_bytes"][i] == per
+        got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(2, 2048)
+        if not same_float_bits(got, r["f32"]):
+            worst = max(worst, float(np.abs(got - r["f32"]).max()))
+            bad = np.argwhere(got.view(np.uint32) != r["f32"].view(np.uint32))
+            raise AssertionError((label, s, f, "float pcm differs", worst, bad[:5].tolist()))
+    eng.close()
+
+
+@pytest.mark.parametrize("fmt,big", [(PCM_S16LE, False), (PCM_S16BE, True)])
+def test_sbr_s16_and_state_across_calls(fmt, big):
+    cfg = gen.config(3, n_frames=50)
+    wl = Workload(cfg, 3, base_seed=4711, with_truth=False)
+    decs = wl.oracle_decoders()
+    eng = Engine(max_streams=8, pcm_format=fmt, chunk_frames=16)
+    ids = [eng.open_adts(*wl.hdr, expect_sbr=1) for _ in range(3)]
+    per = 2 * 2048 * 2
+    for lo, hi in ((0, 1), (1, 22), (22, 50)):   # headers arrive at frames 0, 20, 40: state and tables carry across calls
+        frames, index = wl.frame_table(ids, lo, hi)
+        pcm, res = eng.decode(wl.blob, frames)
+        for i, (s, f) in enumerate(index):
+            r = decs[s].decode_frame(wl.frame_bytes(s, f), big_endian=big)
+            assert res["status"][i] == 0 and r["status"] == 0
+            got = pcm[i * per:(i + 1) * per].view(np.int16).reshape(2048, 2)
+            assert np.array_equal(got, r["s16"]), (s, f)
+    eng.close()
+
+
+def test_sbr_frames_without_payload_are_upsampled():
+    """A frame that carries no SBR fill element takes SBR.upsample (sample 1 keeps the core value) and leaves the
+    QMF state alone; bad frames yield no PCM and the stream continues."""
+    cfg = gen.config(3, n_frames=12)
+    wl = Workload(cfg, 2, base_seed=99, with_truth=False)
+    lc = Workload(gen.GenConfig(sf_index=6, chan_cfg=2, n_frames=12, target_bytes=300), 2, base_seed=199, with_truth=False)
+    # stream 0: frames 5 and 6 replaced by plain AAC-LC frames of the same layout (no fill element)
+    blob = np.concatenate([wl.blob, lc.blob])
+    frames, index = wl.frame_table([0, 1])
+    frames = frames.copy()
+    repl = {}
+    for i, (s, f) in enumerate(index):
+        if s == 0 and f in (5, 6):
+            st = lc.streams[0]
+            frames["offset"][i] = len(wl.blob) + lc.base[0] + st.offsets[f]
+            frames["nbytes"][i] = st.sizes[f]
+            repl[(s, f)] = lc.frame_bytes(0, f)
+        if s == 1 and f == 4:
+            frames["nbytes"][i] //= 3
+    decs = wl.oracle_decoders()
+    eng = Engine(max_streams=4, pcm_format=PCM_F32_PLANAR)
+    ids = [eng.open_adts(*wl.hdr, expect_sbr=1) for _ in range(2)]
+    assert ids == [0, 1]
+    pcm, res = eng.decode(blob, frames)
+    per = 2 * 2048 * 4
+    n_bad = 0
+    for i, (s, f) in enumerate(index):
+        data = repl.get((s, f))
+        if data is None:
+            o, n = int(frames["offset"][i]), int(frames["nbytes"][i])
+            data = blob[o:o + n]
+        r = decs[s].decode_frame(data)
+        assert res["status"][i] == r["status"], (s, f, res["status"][i], r["status"])
+        if r["status"] == 0:
+            got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(2, 2048)
+            assert same_float_bits(got, r["f32"]), (s, f)
+        else:
+            n_bad += 1
+            assert res["pcm_bytes"][i] == 0
+    assert n_bad >= 1
+    eng.close()
