@@ -27,7 +27,12 @@ sys.path.insert(0, ROOT)
 
 SF_FREQ = [96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000]
 # algorithmic bytes per frame: compressed in + s16 PCM out + overlap state read+write
-ALGO_BYTES = {1: lambda avg: avg + 4096 + 16384, 2: lambda avg: avg + 4096 + 16384, 5: lambda avg: avg + 12288 + 49152}
+# config 3 (HE-AAC v1 stereo): + 2048-sample stereo s16 out + this engine's SBR state read+write per frame
+# (2 x SbrChanDev 12480 B + SbrElemDev 3468 B, jaadec_b200/csrc/sbr_types.cuh)
+ALGO_BYTES = {1: lambda avg: avg + 4096 + 16384, 2: lambda avg: avg + 4096 + 16384, 5: lambda avg: avg + 12288 + 49152,
+              3: lambda avg: avg + 8192 + 16384 + 2 * (2 * 12480 + 3468)}
+OUT_SAMPLES = {1: 1024, 2: 1024, 5: 1024, 3: 2048}   # per frame and channel
+OUT_RATE_SHIFT = {1: 0, 2: 0, 5: 0, 3: 3}             # SBR doubles the rate: output sf index = core index - 3
 
 
 def read_peaks():
@@ -114,7 +119,7 @@ def cpu_baseline(cfg, blob, offs, sizes, asc, sample_streams, threads):
     first = np.arange(S + 1, dtype=np.int64) * F
     kw = dict(asc=asc) if asc is not None else dict(hdr=(2, cfg.sf_index, cfg.chan_cfg))
     sec, samples, errors = oracle.decode_streams(blob, first, offs[:S], sizes[:S], threads=threads, **kw)
-    rate = SF_FREQ[cfg.sf_index]
+    rate = SF_FREQ[cfg.sf_index - (3 if cfg.sbr_mode else 0)]
     return (samples / rate) / sec, sec, S, errors
 
 
@@ -150,6 +155,7 @@ def run_reference(args, rank, world):
 
 def workload_config(args, cfg, sizes):
     names = {1: "AAC-LC 44.1 kHz stereo ADTS, long windows only", 2: "AAC-LC 48 kHz stereo, mixed ONLY_LONG/EIGHT_SHORT, M/S, IS, TNS side info",
+             3: "HE-AAC v1 (SBR) 24 kHz core -> 48 kHz stereo: 32-band QMF analysis, HF generation/adjustment, 64-band synthesis",
              5: "AAC-LC 5.1 48 kHz raw frames (MP4 samples)"}
     return {"workload": "BASELINE config %d: %s" % (args.config, names.get(args.config, "?")), "streams_per_gpu": args.streams,
             "frames_per_stream": args.frames, "avg_frame_bytes": float(sizes.mean()), "pcm": "s16le interleaved",
@@ -162,7 +168,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 5])
     ap.add_argument("--streams", type=int, default=4096)
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--ref-streams", type=int, default=0)
@@ -172,7 +178,7 @@ def main():
     if args.config == 1 and args.streams == 4096:
         args.streams = 1
     if not args.frames:
-        args.frames = {1: 431, 2: 469, 5: 469}[args.config]
+        args.frames = {1: 431, 2: 469, 3: 235, 5: 469}[args.config]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,12 +203,12 @@ def main():
 
     cfg, blob, offs, sizes = make_workload(args.config, args.streams, args.frames, rank)
     S, F = offs.shape
-    rate = SF_FREQ[cfg.sf_index]
+    rate = SF_FREQ[cfg.sf_index - OUT_RATE_SHIFT[args.config]]
     asc = bytes([0x11, 0xB0]) if args.config == 5 else None
-    audio_s_per_step = S * F * 1024.0 / rate
+    audio_s_per_step = S * F * float(OUT_SAMPLES[args.config]) / rate
 
     eng = Engine(device=local_rank, max_streams=S, pcm_format=PCM_S16LE, flags=FLAG_PROFILE)
-    ids = [eng.open_asc(asc) if asc else eng.open_adts(2, cfg.sf_index, cfg.chan_cfg) for _ in range(S)]
+    ids = [eng.open_asc(asc) if asc else eng.open_adts(2, cfg.sf_index, cfg.chan_cfg, expect_sbr=cfg.sbr_mode) for _ in range(S)]
     frames = frame_table(offs, sizes, ids)
 
     # ---- value: kernels only, batch resident in HBM ------------------------------------------------
@@ -214,7 +220,7 @@ def main():
     batch.sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    parse_ms, fb_ms, dev_ms, launches = [], [], [], 0
+    parse_ms, fb_ms, sbr_ms, dev_ms, launches = [], [], [], [], 0
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -222,6 +228,7 @@ def main():
         t = batch.timings()   # CUDA events on the engine's stream (synchronises the step)
         parse_ms.append(t.parse_ms)
         fb_ms.append(t.filterbank_ms)
+        sbr_ms.append(t.sbr_ms)
         dev_ms.append(t.total_ms)
         launches += t.launches
     barrier()
@@ -267,12 +274,13 @@ def main():
     peak, peak_kind = read_peaks()
     avg_frame = float(sizes.mean())
     algo_bytes = ALGO_BYTES[args.config](avg_frame) * S * F
-    k1, k2 = float(np.mean(parse_ms)), float(np.mean(fb_ms))
-    dom_name, dom_ms = ("k1_parse_kernel", k1) if k1 >= k2 else ("k2_filterbank_kernel", k2)
+    k1, k2, k4 = float(np.mean(parse_ms)), float(np.mean(fb_ms)), float(np.mean(sbr_ms))
+    dom_name, dom_ms = max((("k1_parse_kernel" + ("+k3_sbr_parse_kernel" if cfg.sbr_mode else ""), k1), ("k2_filterbank_kernel", k2),
+                            ("k4_sbr_process_kernel", k4)), key=lambda kv: kv[1])
     achieved = algo_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (burst copy)", "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "algo_bytes_per_launch": algo_bytes,
-                "kernel_ms": {"k1_parse": k1, "k2_filterbank": k2, "step_device_total": float(np.mean(dev_ms))},
+                "kernel_ms": {"k1_parse(+k3_sbr_parse)": k1, "k2_filterbank": k2, "k4_sbr_process": k4, "step_device_total": float(np.mean(dev_ms))},
                 "whole_path_frac": algo_bytes / (float(np.mean(dev_ms)) * 1e-3) / 1e9 / peak}
 
     line = {

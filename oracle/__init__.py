@@ -127,6 +127,20 @@ class Decoder:
         return ms
 
 
+def qmf_roundtrip(x: np.ndarray):
+    """x [n_frames*1024] float32 -> (X [n_frames*32, 32] complex64, pcm [n_frames*2048] float32) through JAAD's 32-band
+    analysis and 64-band synthesis banks."""
+    x = np.ascontiguousarray(x, np.float32)
+    n = len(x) // 1024
+    X = np.zeros((n * 32, 32, 2), np.float32)
+    pcm = np.zeros(n * 2048, np.float32)
+    L = lib()
+    L.jo_qmf_roundtrip.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    if L.jo_qmf_roundtrip(x.ctypes.data, n, X.ctypes.data, pcm.ctypes.data) != 0:
+        raise RuntimeError("oracle built without SBR")
+    return X[..., 0] + 1j * X[..., 1], pcm
+
+
 def adts_index(data: np.ndarray, max_frames: int = 1 << 20):
     data = np.ascontiguousarray(data, np.uint8)
     offs = np.zeros(max_frames, np.int64)

@@ -171,6 +171,32 @@ int jo_tap_sbr(void* hv, int el, int ch, int32_t* out) {
 #endif
 }
 
+// QMF bank on its own (for the float64 direct-form check in tests/): n_frames x 1024 input samples -> 32-band analysis
+// (X_out [n_frames*32][32][2]) -> the low 32 bands through the 64-band synthesis (pcm_out n_frames x 2048).
+int jo_qmf_roundtrip(const float* in, int n_frames, float* X_out, float* pcm_out) {
+#ifdef JAAD_ORACLE_WITH_SBR
+  sbr::AnalysisFilterbank qa;
+  sbr::SynthesisFilterbank64 qs;
+  std::vector<float> xs((size_t)40 * 64 * 2, 0.f), X((size_t)32 * 64 * 2, 0.f);
+  sbr::Cpx (*Xs)[64] = reinterpret_cast<sbr::Cpx(*)[64]>(xs.data());
+  sbr::Cpx (*Xo)[64] = reinterpret_cast<sbr::Cpx(*)[64]>(X.data());
+  for (int f = 0; f < n_frames; ++f) {
+    qa.sbr_qmf_analysis_32(32, in + (size_t)f * 1024, Xs, 0, 32);
+    for (int l = 0; l < 32; ++l)
+      for (int k = 0; k < 64; ++k) {
+        Xo[l][k][0] = k < 32 ? Xs[l][k][0] : 0.f;
+        Xo[l][k][1] = k < 32 ? Xs[l][k][1] : 0.f;
+        if (k < 32) { X_out[(((size_t)f * 32 + l) * 32 + k) * 2] = Xs[l][k][0]; X_out[(((size_t)f * 32 + l) * 32 + k) * 2 + 1] = Xs[l][k][1]; }
+      }
+    qs.synthesis(32, Xo, pcm_out + (size_t)f * 2048);
+  }
+  return 0;
+#else
+  (void)in; (void)n_frames; (void)X_out; (void)pcm_out;
+  return -1;
+#endif
+}
+
 // ADTS index: payload offsets/sizes of up to `max` frames; hdr[0..2] = profile, sf_index, chan_cfg of the first frame.
 int jo_adts_index(const uint8_t* data, size_t n, int64_t* offsets, int32_t* sizes, int max, int* hdr) {
   ADTSDemultiplexer dm(data, n);

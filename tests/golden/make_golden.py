@@ -38,6 +38,9 @@ def cases():
         "lc_c2_mixed_48k": (gen.config(2, n_frames=12, p_transient=0.35), 3, None),
         "lc_mono_24k": (gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=8, target_bytes=171, p_transient=0.3), 2, None),
         "lc_c5_51_raw": (gen.config(5, n_frames=5, p_transient=0.3), 2, bytes([0x11, 0xB0])),
+        # HE-AAC v1: 24 kHz core + SBR, header at frame 0 and (possibly changed) at frame 20
+        "sbr_c3_stereo": (gen.config(3, n_frames=24), 2, None),
+        "sbr_mono": (gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=22, target_bytes=171, sbr_mode=1), 2, None),
     }
 
 
@@ -59,7 +62,11 @@ def build_case(name, cfg, n_streams, asc):
             assert r["status"] == 0, (name, s, f, r["status"])
             s16.append(r["s16"])
             f32_sha.update(np.ascontiguousarray(r["f32"], np.float32).tobytes())
+    extra = {}
+    if cfg.sbr_mode:
+        extra["truth_sbr"] = np.stack([s.truth["sbr"] for s in streams])
     out = dict(
+        sbr=np.array([cfg.sbr_mode], np.int32),
         blob=blob,
         frame_offset=np.array([r[0] for r in rows], np.int64),
         frame_nbytes=np.array([r[1] for r in rows], np.int32),
@@ -73,6 +80,7 @@ def build_case(name, cfg, n_streams, asc):
         truth_sfidx=np.stack([s.truth["sfidx"] for s in streams]),
         truth_sfbcb=np.stack([s.truth["sfbcb"] for s in streams]),
         truth_info=np.stack([s.truth["info"] for s in streams]),
+        **extra,
     )
     return out
 

@@ -1,0 +1,124 @@
+"""CPU tests that pin the SBR part of the oracle (C++ restatement of JAAD's sbr package).
+
+  1. integer stage: header -> band tables, grid, delta-decoded envelopes and noise floors against the generator's own
+     integer model (gen/aacgen_sbr.inc: independent band-table derivation and delta arithmetic, no decoder involved);
+  2. QMF banks: JAAD's 32-band analysis and 64-band synthesis against float64 direct-form evaluations of the
+     ISO 14496-3 4.6.18.4 definitions;
+  3. drift: committed fixtures (tests/golden/sbr_*.npz).
+"""
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gen
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def sbr_cfg(mono, n_frames):
+    if mono:
+        return gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=n_frames, target_bytes=171, sbr_mode=1)
+    return gen.config(3, n_frames=n_frames)
+
+
+@pytest.mark.parametrize("mono", [False, True], ids=["stereo", "mono"])
+def test_sbr_integer_stage_matches_generator_truth(mono):
+    n_checked = 0
+    classes, couplings, resets = set(), set(), 0
+    for seed in range(24):
+        cfg = sbr_cfg(mono, 64)   # headers at frames 0, 20, 40, 60 -- some with new contents (decoder reset)
+        st = gen.generate(cfg, 31000 + seed, with_truth=True)
+        dec = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)
+        for f in range(cfg.n_frames):
+            r = dec.decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
+            assert r["status"] == 0, (seed, f, r["status"])
+            assert (r["channels"], r["sample_length"], r["sample_rate"]) == (2, 2048, 48000)
+            assert np.abs(r["f32"]).max() < 32768.0   # the generator keeps PCM inside int16
+            for ch in range(1 if mono else 2):
+                t = dec.tap_sbr(0, ch)
+                tr = st.truth["sbr"][f, ch]
+                L_E, L_Q = int(t["ints"][0]), int(t["ints"][1])
+                assert np.array_equal(t["ints"][:3], tr[:3]), (seed, f, ch)
+                if t["ints"][2] != 0:
+                    assert t["ints"][3] == tr[3]                                    # bs_pointer (not sent for FIXFIX)
+                assert np.array_equal(t["ints"][4:5 + L_E], tr[4:5 + L_E])           # t_E
+                assert np.array_equal(t["ints"][10:10 + L_E], tr[10:10 + L_E])       # f
+                assert np.array_equal(t["ints"][16:18], tr[16:18])                   # amp_res, coupling
+                assert np.array_equal(t["extra"][:7], tr[18:25]), (seed, f, ch)      # kx, M, N_high, N_low, N_Q, k0, N_master
+                E_o, E_t = t["ints"][32:352].reshape(5, 64), tr[32:352].reshape(5, 64)
+                Q_o, Q_t = t["ints"][352:480].reshape(2, 64), tr[352:480].reshape(2, 64)
+                for l in range(L_E):
+                    nb = t["extra"][2] if t["ints"][10 + l] else t["extra"][3]
+                    assert np.array_equal(E_o[l, :nb], E_t[l, :nb]), (seed, f, ch, l)
+                assert np.array_equal(Q_o[:L_Q, :t["extra"][4]], Q_t[:L_Q, :t["extra"][4]]), (seed, f, ch)
+                classes.add(int(t["ints"][2]))
+                couplings.add(int(t["ints"][17]))
+                resets += int(t["extra"][8]) if ch == 0 and f > 0 else 0
+                n_checked += 1
+    assert n_checked == 24 * 64 * (1 if mono else 2)
+    assert classes == {0, 1, 2, 3}
+    assert couplings == ({0} if mono else {0, 1})
+    assert resets >= 1   # at least one mid-stream header change made the decoder rebuild its tables
+
+
+def _qmf_c():
+    txt = open(os.path.join(ROOT, "jaadec_b200", "csrc", "generated", "jaad_tables.h")).read()
+    m = re.search(r'JAAD_TABLE_F32\(SBR_QMF_C, 640, "\[640\]"\)(.*?)JAAD_TABLE_END', txt, re.S)
+    bits = np.array([int(t, 16) for t in re.findall(r"0x([0-9A-Fa-f]{8})u", m.group(1))], np.uint32)
+    assert len(bits) == 640
+    return bits.view(np.float32).astype(np.float64)
+
+
+def test_qmf_banks_match_direct_form():
+    rng = np.random.default_rng(7)
+    n = 3
+    x = (rng.standard_normal(n * 1024) * 2000).astype(np.float32)
+    X, pcm = oracle.qmf_roundtrip(x)
+    c = _qmf_c()
+    xx = np.concatenate([np.zeros(320), x.astype(np.float64)])
+    nn, kk = np.arange(64), np.arange(32)
+    A = 2 * np.exp(1j * np.pi / 64 * (kk[:, None] + 0.5) * (2 * nn[None, :] - 0.5))      # 4.6.18.4.1
+    Xd = np.zeros((n * 32, 32), complex)
+    for l in range(n * 32):
+        newest = 320 + 32 * l + 31
+        u = (xx[newest - np.arange(320)] * c[::2]).reshape(5, 64).sum(0)
+        Xd[l] = A @ u
+    assert np.abs(X - Xd).max() / np.abs(Xd).max() < 2e-6
+    n128, k64 = np.arange(128), np.arange(64)
+    S = np.exp(1j * np.pi / 128 * (k64[None, :] + 0.5) * (2 * n128[:, None] - 255)) / 64.0   # 4.6.18.4.2
+    v = np.zeros(1280)
+    out = np.zeros(n * 2048)
+    for l in range(n * 32):
+        Xl = np.zeros(64, complex)
+        Xl[:32] = Xd[l]
+        v = np.concatenate([(S @ Xl).real, v[:-128]])
+        g = np.zeros(640)
+        for j in range(5):
+            g[128 * j:128 * j + 64] = v[256 * j:256 * j + 64]
+            g[128 * j + 64:128 * j + 128] = v[256 * j + 192:256 * j + 256]
+        out[64 * l:64 * l + 64] = (g * c).reshape(10, 64).sum(0)
+    assert np.abs(out - pcm).max() / np.abs(pcm).max() < 2e-6
+    # and the chain reconstructs a low-pass input (x2 up-sampled, delayed): energy is preserved to a fraction of a dB
+    lp = np.convolve(rng.standard_normal(8 * 1024), np.ones(8) / 8, "same").astype(np.float32) * 3000
+    _, y = oracle.qmf_roundtrip(lp)
+    e_in, e_out = float((lp[2048:6144].astype(np.float64) ** 2).mean()), float((y[4096:12288].astype(np.float64) ** 2).mean())
+    assert abs(10 * np.log10(e_out / e_in)) < 0.5
+
+
+@pytest.mark.parametrize("name", ["sbr_c3_stereo", "sbr_mono"])
+def test_oracle_reproduces_sbr_golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    n_streams = int(g["frame_stream"].max()) + 1
+    decs = [oracle.Decoder.create_adts(*[int(x) for x in g["hdr"]]) for _ in range(n_streams)]
+    sha = hashlib.sha256()
+    for i, (o, n, s) in enumerate(zip(g["frame_offset"], g["frame_nbytes"], g["frame_stream"])):
+        r = decs[s].decode_frame(g["blob"][o:o + n])
+        assert r["status"] == 0
+        assert np.array_equal(r["s16"], g["s16"][i]), (name, i)
+        sha.update(np.ascontiguousarray(r["f32"], np.float32).tobytes())
+    assert sha.digest() == g["f32_sha256"].tobytes()
