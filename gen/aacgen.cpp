@@ -481,7 +481,8 @@ struct jg_config {
   int32_t ms_mode;        // 0: never, 1: random ms_mask_present in {0,1,2}
   int32_t sbr_mode;       // 0 none (LC); 1 SBR; 2 SBR+PS  (filled in by aacgen_sbr.inc when present)
   float target_rms;       // PCM rms target (default 2500)
-  int32_t reserved[3];
+  int32_t sbr_quirk;      // 1: also emit coupled SBR frames only the reference parses (aacgen_sbr.inc, SbrChanState)
+  int32_t reserved[2];
 };
 
 // Ground truth per ICS (element order, L before R); arrays may be NULL.
@@ -564,7 +565,8 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
         }
         if (cfg->sbr_mode && !el.lfe)
           sbrEmitFill(c, bw, sbrState[ei], false, f, sbrSrIndex, sbrSrFreq,
-                      (truth && truth->sbr) ? truth->sbr + ((size_t)f * nIcs + icsIdx) * kSbrTruthInts : nullptr, nullptr);
+                      (truth && truth->sbr) ? truth->sbr + ((size_t)f * nIcs + icsIdx) * kSbrTruthInts : nullptr, nullptr,
+                      cfg->sbr_quirk != 0);
         icsIdx += 1;
       } else {
         bool common = c.rng.chance(cfg->p_common_window);
@@ -646,7 +648,8 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
         }
         if (cfg->sbr_mode)
           sbrEmitFill(c, bw, sbrState[ei], true, f, sbrSrIndex, sbrSrFreq,
-                      (truth && truth->sbr) ? truth->sbr + ((size_t)f * nIcs + icsIdx) * kSbrTruthInts : nullptr, nullptr);
+                      (truth && truth->sbr) ? truth->sbr + ((size_t)f * nIcs + icsIdx) * kSbrTruthInts : nullptr, nullptr,
+                      cfg->sbr_quirk != 0);
         icsIdx += 2;
       }
     }

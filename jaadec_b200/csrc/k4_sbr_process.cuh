@@ -134,9 +134,17 @@ __device__ __forceinline__ void sbr_dct4_kernel(float (&in_real)[32], float (&in
 
 constexpr int kK4Threads = 64;
 // shared-memory carve (floats)
-constexpr int kK4Xs = 40 * 64 * 2;          // Xsbr
-constexpr int kK4In = 288 + 1024;           // analysis input: history + this frame's core PCM
-constexpr int kK4V = (9 + 32) * 128;        // synthesis v-vectors: 9 carried + 32 new
+// Row strides are odd so that the one-thread-per-time-slot phases (analysis, synthesis DCTs), where the 32 lanes of a
+// warp address the same column of 32 different rows, spread over all 32 banks.
+constexpr int kXsStride = 129;              // one Xsbr slot: 64 bands x (re, im) + 1
+constexpr int kVbStride = 129;              // one synthesis v-vector: 128 + 1
+constexpr int kK4Xs = 40 * kXsStride;       // Xsbr
+constexpr int kK4In = 288 + 1024 + 41 + 3;  // analysis input: history + this frame's core PCM, one pad float per 32 (+3: 16 B)
+constexpr int kK4V = (9 + 32) * kVbStride + 3;  // synthesis v-vectors: 9 carried + 32 new (+3: keeps what follows 16 B aligned)
+static_assert(kK4Xs % 4 == 0 && kK4In % 4 == 0 && kK4V % 4 == 0, "K4 shared-memory regions must stay 16-byte aligned");
+#define XS(l, k, c) xs[(l) * kXsStride + (k) * 2 + (c)]
+#define VB(s, r) vb[(s) * kVbStride + (r)]
+#define INB(i) inbuf[(i) + ((i) >> 5)]
 constexpr int kK4Adj = 3 * kSbrMaxLE * 64 + kSbrMaxLE * 64;   // G_lim_boost, Q_M_lim_boost, S_M_boost, E_curr
 __host__ __device__ constexpr size_t k4_smem_bytes() {
   return sizeof(float) * (kK4Xs + kK4In + kK4V + kK4Adj + 16) + sizeof(SbrFrameDev);
@@ -161,9 +169,9 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
                       uint8_t* __restrict__ pcm, const uint64_t* __restrict__ pcm_off, uint32_t* __restrict__ pcm_bytes_out,
                       SbrTablesDev T) {
   extern __shared__ __align__(16) float k4_smem[];
-  float (*xs)[64][2] = reinterpret_cast<float (*)[64][2]>(k4_smem);
+  float* xs = k4_smem;
   float* inbuf = k4_smem + kK4Xs;
-  float (*vb)[128] = reinterpret_cast<float (*)[128]>(inbuf + kK4In);
+  float* vb = inbuf + kK4In;
   float* adj = inbuf + kK4In + kK4V;
   float (*G_lim_boost)[64] = reinterpret_cast<float (*)[64]>(adj);
   float (*Q_M_lim_boost)[64] = reinterpret_cast<float (*)[64]>(adj + kSbrMaxLE * 64);
@@ -177,11 +185,11 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
   SbrChanDev* st = chans + (size_t)run.stream_slot * kSbrChansPerStream + run.ch_slot;
 
   // ---- persistent state in
-  for (int i = t; i < 288; i += kK4Threads) inbuf[i] = st->ana_hist[i];
-  for (int i = t; i < kSbrHfGen * 64 * 2; i += kK4Threads) (&xs[0][0][0])[i] = (&st->xsbr[0][0][0])[i];
-  for (int i = t; i < (40 - kSbrHfGen) * 64 * 2; i += kK4Threads) (&xs[kSbrHfGen][0][0])[i] = 0.f;
-  // carried v-vectors: vb[8] is the newest (slot -1), vb[0] the oldest (slot -9); syn_v[0] = newest
-  for (int i = t; i < 9 * 128; i += kK4Threads) vb[8 - i / 128][i % 128] = st->syn_v[i / 128][i % 128];
+  for (int i = t; i < 288; i += kK4Threads) INB(i) = st->ana_hist[i];
+  for (int i = t; i < kSbrHfGen * 128; i += kK4Threads) XS(i >> 7, 0, i & 127) = (&st->xsbr[0][0][0])[i];
+  for (int i = t; i < (40 - kSbrHfGen) * 128; i += kK4Threads) XS(kSbrHfGen + (i >> 7), 0, i & 127) = 0.f;
+  // carried v-vectors: row 8 is the newest (slot -1), row 0 the oldest (slot -9); syn_v[0] = newest
+  for (int i = t; i < 9 * 128; i += kK4Threads) VB(8 - i / 128, i % 128) = st->syn_v[i / 128][i % 128];
   float Gt[5], Qt[5];   // smoothing ring of band m = t
 #pragma unroll
   for (int n = 0; n < 5; ++n) { Gt[n] = st->G_temp_prev[n][t]; Qt[n] = st->Q_temp_prev[n][t]; }
@@ -204,8 +212,10 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
       uint4* dst = reinterpret_cast<uint4*>(fp);
       for (int i = t; i < (int)(sizeof(SbrFrameDev) / 16); i += kK4Threads) dst[i] = src[i];
       const float4* cs = reinterpret_cast<const float4*>(core + ((size_t)rf.ics_base + run.ch_slot) * 1024);
-      float4* cd = reinterpret_cast<float4*>(inbuf + 288);
-      for (int i = t; i < 256; i += kK4Threads) cd[i] = cs[i];
+      for (int i = t; i < 256; i += kK4Threads) {
+        const float4 v = cs[i];
+        INB(288 + 4 * i) = v.x; INB(288 + 4 * i + 1) = v.y; INB(288 + 4 * i + 2) = v.z; INB(288 + 4 * i + 3) = v.w;
+      }
     }
     __syncthreads();
     const int mode = fp->mode;
@@ -233,8 +243,7 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
 
     if (mode == 0) {
       // no valid SBR data in this frame: SBR.upsample (sbr/SBR.java:302-309; sample 1 keeps the core value)
-      const float* c = inbuf + 288;
-      for (int i = t; i < 2048; i += kK4Threads) put_sample(i, i < 2 ? c[i] : c[i >> 1]);
+      for (int i = t; i < 2048; i += kK4Threads) put_sample(i, i < 2 ? INB(288 + i) : INB(288 + (i >> 1)));
       __syncthreads();
       continue;
     }
@@ -242,13 +251,13 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
     const int kx = mode == 2 ? fp->kx : 32;
     // ---- 32-band QMF analysis: thread l < 32 computes time slot l
     if (t < 32) {
-      const float* x = inbuf + 288 + 32 * t + 31;   // newest sample of the slot; x[-j] = v[v_index + j] of the reference
+      const int xi = 288 + 32 * t + 31;   // newest sample of the slot; sample xi - j = v[v_index + j] of the reference
       float in_real[32], in_imag[32], out_real[32], out_imag[32];
 #pragma unroll
       for (int n = 0; n < 64; ++n) {
-        const float u = (x[-n] * c_sbr_qmf_c[2 * n]) + (x[-(n + 64)] * c_sbr_qmf_c[2 * (n + 64)]) +
-                        (x[-(n + 128)] * c_sbr_qmf_c[2 * (n + 128)]) + (x[-(n + 192)] * c_sbr_qmf_c[2 * (n + 192)]) +
-                        (x[-(n + 256)] * c_sbr_qmf_c[2 * (n + 256)]);
+        const float u = (INB(xi - n) * c_sbr_qmf_c[2 * n]) + (INB(xi - (n + 64)) * c_sbr_qmf_c[2 * (n + 64)]) +
+                        (INB(xi - (n + 128)) * c_sbr_qmf_c[2 * (n + 128)]) + (INB(xi - (n + 192)) * c_sbr_qmf_c[2 * (n + 192)]) +
+                        (INB(xi - (n + 256)) * c_sbr_qmf_c[2 * (n + 256)]);
         // reordering of AnalysisFilterbank.java:40-47
         if (n == 0) in_real[0] = u;
         else if (n == 1) in_imag[31] = u;
@@ -258,19 +267,19 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
         else in_real[64 - n] = -u;                      // in_real[m] = -u[64-m], m = 1..30
       }
       sbr_dct4_kernel(in_real, in_imag, out_real, out_imag);
-      float (*X)[2] = xs[t + kSbrHfGen];
+      const int xrow = t + kSbrHfGen;
 #pragma unroll
       for (int n = 0; n < 16; n++) {
         if (2 * n + 1 < kx) {
-          X[2 * n][0] = 2.0f * out_real[n];
-          X[2 * n][1] = 2.0f * out_imag[n];
-          X[2 * n + 1][0] = -2.0f * out_imag[31 - n];
-          X[2 * n + 1][1] = -2.0f * out_real[31 - n];
+          XS(xrow, 2 * n, 0) = 2.0f * out_real[n];
+          XS(xrow, 2 * n, 1) = 2.0f * out_imag[n];
+          XS(xrow, 2 * n + 1, 0) = -2.0f * out_imag[31 - n];
+          XS(xrow, 2 * n + 1, 1) = -2.0f * out_real[31 - n];
         } else {
-          if (2 * n < kx) { X[2 * n][0] = 2.0f * out_real[n]; X[2 * n][1] = 2.0f * out_imag[n]; }
-          else { X[2 * n][0] = 0; X[2 * n][1] = 0; }
-          X[2 * n + 1][0] = 0;
-          X[2 * n + 1][1] = 0;
+          if (2 * n < kx) { XS(xrow, 2 * n, 0) = 2.0f * out_real[n]; XS(xrow, 2 * n, 1) = 2.0f * out_imag[n]; }
+          else { XS(xrow, 2 * n, 0) = 0; XS(xrow, 2 * n, 1) = 0; }
+          XS(xrow, 2 * n + 1, 0) = 0;
+          XS(xrow, 2 * n + 1, 1) = 0;
         }
       }
     }
@@ -318,14 +327,14 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
             float r01r = 0, r01i = 0, r02r = 0, r02i = 0, r11r = 0;
             float temp1_r, temp1_i, temp2_r, temp2_i, temp3_r, temp3_i, temp4_r, temp4_i, temp5_r, temp5_i;
             const float rel = 1.0f / (1 + 1e-6f);
-            temp2_r = xs[offset - 2][p][0]; temp2_i = xs[offset - 2][p][1];
-            temp3_r = xs[offset - 1][p][0]; temp3_i = xs[offset - 1][p][1];
+            temp2_r = XS(offset - 2, p, 0); temp2_i = XS(offset - 2, p, 1);
+            temp3_r = XS(offset - 1, p, 0); temp3_i = XS(offset - 1, p, 1);
             temp4_r = temp2_r; temp4_i = temp2_i; temp5_r = temp3_r; temp5_i = temp3_i;
             temp1_r = 0; temp1_i = 0;
             for (int j = offset; j < kSbrSlots + 6 + offset; j++) {
               temp1_r = temp2_r; temp1_i = temp2_i;
               temp2_r = temp3_r; temp2_i = temp3_i;
-              temp3_r = xs[j][p][0]; temp3_i = xs[j][p][1];
+              temp3_r = XS(j, p, 0); temp3_i = XS(j, p, 1);
               r01r += temp3_r * temp2_r + temp3_i * temp2_i;
               r01i += temp3_i * temp2_r - temp3_r * temp2_i;
               r02r += temp3_r * temp1_r + temp3_i * temp1_i;
@@ -351,18 +360,18 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
             }
             if (((al0r * al0r) + (al0i * al0i) >= 16.0f) || ((al1r * al1r) + (al1i * al1i) >= 16.0f)) { al0r = 0; al0i = 0; al1r = 0; al1i = 0; }
             const float a0_r = (al0r * bw), a1_r = (al1r * bw2), a0_i = (al0i * bw), a1_i = (al1i * bw2);
-            temp2_r = xs[first_slot - 2 + offset][p][0]; temp3_r = xs[first_slot - 1 + offset][p][0];
-            temp2_i = xs[first_slot - 2 + offset][p][1]; temp3_i = xs[first_slot - 1 + offset][p][1];
+            temp2_r = XS(first_slot - 2 + offset, p, 0); temp3_r = XS(first_slot - 1 + offset, p, 0);
+            temp2_i = XS(first_slot - 2 + offset, p, 1); temp3_i = XS(first_slot - 1 + offset, p, 1);
             for (int l = first_slot; l < last_slot; l++) {
-              temp1_r = temp2_r; temp2_r = temp3_r; temp3_r = xs[l + offset][p][0];
-              temp1_i = temp2_i; temp2_i = temp3_i; temp3_i = xs[l + offset][p][1];
-              xs[l + offset][k][0] = temp3_r + ((a0_r * temp2_r) - (a0_i * temp2_i) + (a1_r * temp1_r) - (a1_i * temp1_i));
-              xs[l + offset][k][1] = temp3_i + ((a0_i * temp2_r) + (a0_r * temp2_i) + (a1_i * temp1_r) + (a1_r * temp1_i));
+              temp1_r = temp2_r; temp2_r = temp3_r; temp3_r = XS(l + offset, p, 0);
+              temp1_i = temp2_i; temp2_i = temp3_i; temp3_i = XS(l + offset, p, 1);
+              XS(l + offset, k, 0) = temp3_r + ((a0_r * temp2_r) - (a0_i * temp2_i) + (a1_r * temp1_r) - (a1_i * temp1_i));
+              XS(l + offset, k, 1) = temp3_i + ((a0_i * temp2_r) + (a0_r * temp2_i) + (a1_i * temp1_r) + (a1_r * temp1_i));
             }
           } else {
             for (int l = first_slot; l < last_slot; l++) {
-              xs[l + offset][k][0] = xs[l + offset][p][0];
-              xs[l + offset][k][1] = xs[l + offset][p][1];
+              XS(l + offset, k, 0) = XS(l + offset, p, 0);
+              XS(l + offset, k, 1) = XS(l + offset, p, 1);
             }
           }
         }
@@ -382,7 +391,7 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
             div = (float)(u_i - l_i);
             if (div == 0) div = 1;
             for (int i = l_i + kSbrHfAdj; i < u_i + kSbrHfAdj; i++)
-              nrg += (xs[i][t + kx][0] * xs[i][t + kx][0]) + (xs[i][t + kx][1] * xs[i][t + kx][1]);
+              nrg += (XS(i, t + kx, 0) * XS(i, t + kx, 0)) + (XS(i, t + kx, 1) * XS(i, t + kx, 1));
           } else {
             // the band of the envelope's resolution that holds k = t + kx
             const int res = fp->f[l], nb = res ? fp->N_high : fp->N_low;
@@ -392,7 +401,7 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
             div = (float)((u_i - l_i) * (k_h - k_l));
             if (div == 0) div = 1;
             for (int i = l_i + kSbrHfAdj; i < u_i + kSbrHfAdj; i++)
-              for (int j = k_l; j < k_h; j++) nrg += (xs[i][j][0] * xs[i][j][0]) + (xs[i][j][1] * xs[i][j][1]);
+              for (int j = k_l; j < k_h; j++) nrg += (XS(i, j, 0) * XS(i, j, 0)) + (XS(i, j, 1) * XS(i, j, 1));
           }
           E_curr[l][t] = nrg / div;
         }
@@ -529,7 +538,7 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
             Q_filt = (s_m != 0 || no_noise) ? 0 : Q_filt;
             if (active) {
               const int ni = (fIndexNoise + slots_done * M + t + 1) & 511;
-              float* x = xs[i + kSbrHfAdj][t + kx];
+              float* x = &XS(i + kSbrHfAdj, t + kx, 0);
               x[0] = G_filt * x[0] + (Q_filt * __ldg(T.noise_table + 2 * ni));
               x[1] = G_filt * x[1] + (Q_filt * __ldg(T.noise_table + 2 * ni + 1));
               const int rev = (((t + kx) & 1) != 0 ? -1 : 1);
@@ -557,10 +566,9 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
       int lim;
       if (mode == 2) lim = (l < first_slot) ? (fp->kx_prev + fp->M_prev) : (fp->kx + fp->M);
       else lim = 32;
-      const float (*pX)[2] = xs[l + kSbrHfAdj];
       const float scale = 1.f / 64.f;
-      auto Xr = [&](int k) -> float { return k < lim ? pX[k][0] : 0.f; };
-      auto Xi = [&](int k) -> float { return k < lim ? pX[k][1] : 0.f; };
+      auto Xr = [&](int k) -> float { return k < lim ? XS(l + kSbrHfAdj, k, 0) : 0.f; };
+      auto Xi = [&](int k) -> float { return k < lim ? XS(l + kSbrHfAdj, k, 1) : 0.f; };
       float in_r[32], in_i[32], o1r[32], o1i[32], o2r[32], o2i[32];
       in_i[31] = scale * Xr(1);
       in_r[0] = scale * Xr(0);
@@ -576,7 +584,7 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
       in_i[0] = scale * Xi(63 - 63);
       in_r[31] = scale * Xi(63 - 62);
       sbr_dct4_kernel(in_r, in_i, o2r, o2i);
-      float* v = vb[9 + l];
+      float* v = &VB(9 + l, 0);
 #pragma unroll
       for (int n = 0; n < 32; n++) {
         v[2 * n] = o2r[n] - o1r[n];
@@ -589,35 +597,35 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
     // window + output: thread k, all 32 slots
     for (int l = 0; l < 32; ++l) {
       const int cur = 9 + l;
-      float o = (vb[cur][t] * qc[0]);
+      float o = (VB(cur, t) * qc[0]);
 #pragma unroll
-      for (int j = 1; j < 10; ++j) o = o + (vb[cur - j][t + 64 * (j & 1)] * qc[j]);
+      for (int j = 1; j < 10; ++j) o = o + (VB(cur - j, t + 64 * (j & 1)) * qc[j]);
       put_sample(64 * l + t, o);
     }
     __syncthreads();
     // ---- carry: analysis history, the last 8 Xsbr slots (sbr_save_matrix), the last 9 v-vectors
-    for (int i = t; i < 288; i += kK4Threads) inbuf[i] = inbuf[1024 + i];   // disjoint ranges
+    for (int i = t; i < 288; i += kK4Threads) INB(i) = INB(1024 + i);   // disjoint ranges
     {
       float keep[kSbrHfGen * 2];
 #pragma unroll
-      for (int i = 0; i < kSbrHfGen; ++i) { keep[2 * i] = xs[i + kSbrSlots][t][0]; keep[2 * i + 1] = xs[i + kSbrSlots][t][1]; }
+      for (int i = 0; i < kSbrHfGen; ++i) { keep[2 * i] = XS(i + kSbrSlots, t, 0); keep[2 * i + 1] = XS(i + kSbrSlots, t, 1); }
       float vk[18];
 #pragma unroll
-      for (int s = 0; s < 9; ++s) { vk[2 * s] = vb[32 + s][t]; vk[2 * s + 1] = vb[32 + s][t + 64]; }
+      for (int s = 0; s < 9; ++s) { vk[2 * s] = VB(32 + s, t); vk[2 * s + 1] = VB(32 + s, t + 64); }
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < kSbrHfGen; ++i) { xs[i][t][0] = keep[2 * i]; xs[i][t][1] = keep[2 * i + 1]; }
-      for (int i = kSbrHfGen; i < 40; ++i) { xs[i][t][0] = 0.f; xs[i][t][1] = 0.f; }
+      for (int i = 0; i < kSbrHfGen; ++i) { XS(i, t, 0) = keep[2 * i]; XS(i, t, 1) = keep[2 * i + 1]; }
+      for (int i = kSbrHfGen; i < 40; ++i) { XS(i, t, 0) = 0.f; XS(i, t, 1) = 0.f; }
 #pragma unroll
-      for (int s = 0; s < 9; ++s) { vb[s][t] = vk[2 * s]; vb[s][t + 64] = vk[2 * s + 1]; }
+      for (int s = 0; s < 9; ++s) { VB(s, t) = vk[2 * s]; VB(s, t + 64) = vk[2 * s + 1]; }
     }
     __syncthreads();
   }
 
   // ---- persistent state out
-  for (int i = t; i < 288; i += kK4Threads) st->ana_hist[i] = inbuf[i];
-  for (int i = t; i < kSbrHfGen * 64 * 2; i += kK4Threads) (&st->xsbr[0][0][0])[i] = (&xs[0][0][0])[i];
-  for (int i = t; i < 9 * 128; i += kK4Threads) st->syn_v[i / 128][i % 128] = vb[8 - i / 128][i % 128];
+  for (int i = t; i < 288; i += kK4Threads) st->ana_hist[i] = INB(i);
+  for (int i = t; i < kSbrHfGen * 128; i += kK4Threads) (&st->xsbr[0][0][0])[i] = XS(i >> 7, 0, i & 127);
+  for (int i = t; i < 9 * 128; i += kK4Threads) st->syn_v[i / 128][i % 128] = VB(8 - i / 128, i % 128);
 #pragma unroll
   for (int n = 0; n < 5; ++n) { st->G_temp_prev[n][t] = Gt[n]; st->Q_temp_prev[n][t] = Qt[n]; }
   if (t < 8) { st->bwArray_prev[t] = bw_prev; st->bs_invf_mode_prev[t] = (uint8_t)invf_prev; }

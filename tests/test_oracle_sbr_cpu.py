@@ -32,6 +32,7 @@ def test_sbr_integer_stage_matches_generator_truth(mono):
     classes, couplings, resets = set(), set(), 0
     for seed in range(24):
         cfg = sbr_cfg(mono, 64)   # headers at frames 0, 20, 40, 60 -- some with new contents (decoder reset)
+        cfg.sbr_quirk = bool(seed & 1)   # odd seeds: coupled frames in the form only the reference parses
         st = gen.generate(cfg, 31000 + seed, with_truth=True)
         dec = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)
         for f in range(cfg.n_frames):

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 
 CASES = [
     ("c3_stereo_sbr", gen.config(3, n_frames=45), 6),
+    ("c3_stereo_sbr_jaad_coupling", gen.config(3, n_frames=45, sbr_quirk=True), 6),
     ("mono_sbr", gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=45, target_bytes=171, sbr_mode=1), 4),
     ("stereo_sbr_32k", gen.GenConfig(sf_index=8, chan_cfg=2, n_frames=30, target_bytes=300, sbr_mode=1), 3),
 ]

@@ -13,7 +13,7 @@ eng = Engine(max_streams=S, pcm_format=PCM_S16LE)
 ids = [eng.open_adts(2, 6, 2, expect_sbr=1) for _ in range(S)]
 fr = np.zeros(S * F, FRAME_DESC_DTYPE)
 fr["offset"] = offs.T.reshape(-1); fr["nbytes"] = sizes.T.reshape(-1); fr["stream_id"] = np.tile(np.asarray(ids, np.int32), F)
-b = eng.batch(fr, blob.nbytes); b.upload(blob); b.decode()
+b = eng.batch(fr, blob.nbytes); b.upload(blob); b.decode(); b.sync(); b.decode()
 pcm, res = b.download()
 bad = np.nonzero(res["status"])[0]
 print("bad", len(bad), "of", S * F)

@@ -10,7 +10,7 @@ from jaadec_b200 import Engine, PCM_F32_PLANAR
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 mono = len(sys.argv) > 2 and sys.argv[2] == "mono"
-cfg = gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=24, target_bytes=171, sbr_mode=1) if mono else gen.config(3, n_frames=24)
+cfg = gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=24, target_bytes=171, sbr_mode=1) if mono else gen.config(3, n_frames=24, sbr_quirk=True)
 wl = Workload(cfg, n, base_seed=int(sys.argv[3]) if len(sys.argv) > 3 else 70000, with_truth=False)
 decs = wl.oracle_decoders()
 eng = Engine(max_streams=n, pcm_format=PCM_F32_PLANAR)
