@@ -37,7 +37,7 @@ class _Cfg(C.Structure):
 
 class _Truth(C.Structure):
     _fields_ = [("q", C.c_void_p), ("sfidx", C.c_void_p), ("sfbcb", C.c_void_p), ("info", C.c_void_p), ("msused", C.c_void_p),
-                ("sbr", C.c_void_p)]
+                ("sbr", C.c_void_p), ("ps", C.c_void_p)]
 
 
 _lib = None
@@ -126,7 +126,11 @@ def generate(cfg: GenConfig, seed: int, with_truth: bool = False) -> Stream:
         if cfg.sbr_mode:
             truth["sbr"] = np.zeros((cfg.n_frames, nics, L.jg_sbr_truth_ints()), np.int32)
             sbr_p = truth["sbr"].ctypes.data
-        t = _Truth(*(truth[k].ctypes.data for k in ("q", "sfidx", "sfbcb", "info", "msused")), sbr_p)
+        ps_p = None
+        if cfg.sbr_mode > 1:
+            truth["ps"] = np.zeros((cfg.n_frames, L.jg_ps_truth_ints()), np.int32)
+            ps_p = truth["ps"].ctypes.data
+        t = _Truth(*(truth[k].ctypes.data for k in ("q", "sfidx", "sfbcb", "info", "msused")), sbr_p, ps_p)
         tp = C.byref(t)
     cc = cfg.c()
     n = L.jg_generate(C.byref(cc), seed, out.ctypes.data, cap, offs.ctypes.data, sizes.ctypes.data, tp)

@@ -462,6 +462,7 @@ void writeIcs(Ctx& c, BitWriter& bw, const IcsPlan& p, bool commonWindow) {
 }
 
 #include "aacgen_sbr.inc"
+#include "aacgen_ps.inc"
 
 }  // namespace
 
@@ -494,9 +495,11 @@ struct jg_truth {
   uint8_t* msused;   // [n_frames][n_elements][128]
   int32_t* sbr;      // [n_frames][n_ics][480] SBR streams only: L_E, L_Q, frame class, pointer, t_E[6], f[6], amp_res,
                      //   coupling, (pad to 32), E[5][64], Q[2][64] as a decoder reconstructs them (aacgen_sbr.inc)
+  int32_t* ps;       // [n_frames][348] SBR+PS streams only: num_env, border_position[6], pad, iid[5][34], icc[5][34]
 };
 
 int jg_sbr_truth_ints(void) { return kSbrTruthInts; }
+int jg_ps_truth_ints(void) { return kPsTruthInts; }
 
 int jg_ics_per_frame(int chan_cfg) { return chan_cfg == 6 ? 6 : chan_cfg; }
 int jg_elements_per_frame(int chan_cfg) { return chan_cfg == 6 ? 4 : 1; }
@@ -519,14 +522,15 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
   std::vector<int> wsState(els.size(), 0);  // 0 long, 1 start sent -> shorts, 2 in shorts
   std::vector<SbrElemState> sbrState(els.size());
   const int sbrSrIndex = cfg->sf_index - 3, sbrSrFreq = cfg->sf_index >= 3 ? T_SF_FREQ[cfg->sf_index - 3] : 0;
-  if (cfg->sbr_mode && (cfg->sf_index < 3 || cfg->sbr_mode > 1)) return -3;  // PS payloads: aacgen_ps.inc, not in this build
+  if (cfg->sbr_mode && (cfg->sf_index < 3 || (cfg->sbr_mode > 1 && cfg->chan_cfg != 1))) return -3;
+  PsState psState;
   const double targetRms = cfg->target_rms > 0 ? cfg->target_rms : 2500.0;
   int64_t pos = 0;
   for (int f = 0; f < cfg->n_frames; ++f) {
     BitWriter bw;
     int icsIdx = 0;
     int payloadBudget = cfg->target_bytes * 8 - 3 - 8;
-    if (cfg->sbr_mode) payloadBudget -= (cfg->chan_cfg == 2 ? 60 : 36) * 8;   // room for the SBR fill element
+    if (cfg->sbr_mode) payloadBudget -= (cfg->chan_cfg == 2 ? 60 : (cfg->sbr_mode > 1 ? 70 : 36)) * 8;   // room for the SBR fill element
     for (size_t ei = 0; ei < els.size(); ++ei) {
       const El& el = els[ei];
       // window sequence state machine (per element): ONLY_LONG -> LONG_START -> EIGHT_SHORT+ -> LONG_STOP -> ONLY_LONG
@@ -563,10 +567,13 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
             in[14] = 0; in[15] = 0;
           }
         }
-        if (cfg->sbr_mode && !el.lfe)
+        if (cfg->sbr_mode && !el.lfe) {
+          BitWriter psBits;
+          if (cfg->sbr_mode > 1) psBuild(c, psBits, psState, f, (truth && truth->ps) ? truth->ps + (size_t)f * kPsTruthInts : nullptr);
           sbrEmitFill(c, bw, sbrState[ei], false, f, sbrSrIndex, sbrSrFreq,
-                      (truth && truth->sbr) ? truth->sbr + ((size_t)f * nIcs + icsIdx) * kSbrTruthInts : nullptr, nullptr,
-                      cfg->sbr_quirk != 0);
+                      (truth && truth->sbr) ? truth->sbr + ((size_t)f * nIcs + icsIdx) * kSbrTruthInts : nullptr,
+                      cfg->sbr_mode > 1 ? &psBits : nullptr, cfg->sbr_quirk != 0);
+        }
         icsIdx += 1;
       } else {
         bool common = c.rng.chance(cfg->p_common_window);

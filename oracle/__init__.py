@@ -120,6 +120,15 @@ class Decoder:
         return dict(ints=out[:480].copy(), extra=out[480:496].copy(), e_orig=out[496:816].view(np.float32).reshape(5, 64).copy(),
                     q_div=out[816:944].view(np.float32).reshape(2, 64).copy())
 
+    def tap_ps(self, el: int = 0):
+        """PS state after the frame just decoded: dict(num_env, border[6], iid[5,34], icc[5,34], iid_mode, icc_mode)."""
+        out = np.zeros(350, np.int32)
+        lib().jo_tap_ps.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        if lib().jo_tap_ps(self._h, el, out.ctypes.data) < 0:
+            return None
+        return dict(num_env=int(out[0]), border=out[1:7].copy(), iid=out[8:178].reshape(5, 34).copy(),
+                    icc=out[178:348].reshape(5, 34).copy(), iid_mode=int(out[348]), icc_mode=int(out[349]), raw=out[:348].copy())
+
     def tap_msused(self, el: int):
         ms = np.zeros(128, np.uint8)
         if lib().jo_tap_msused(self._h, el, ms.ctypes.data) < 0:

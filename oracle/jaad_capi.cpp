@@ -13,6 +13,7 @@
 #include "jaad_lc.hpp"
 #ifdef JAAD_ORACLE_WITH_SBR
 #include "jaad_sbr.hpp"
+#include "jaad_ps.hpp"
 #endif
 
 using namespace jaad;
@@ -167,6 +168,30 @@ int jo_tap_sbr(void* hv, int el, int ch, int32_t* out) {
   return 0;
 #else
   (void)hv; (void)el; (void)ch; (void)out;
+  return -1;
+#endif
+}
+
+// PS parity tap of the frame just decoded (SCE element `el`): num_env, border_position[6], pad, iid[5][34], icc[5][34],
+// then (from out[348]) iid mode, icc mode (-1 = off).  Returns -1 if the element carries no PS.
+int jo_tap_ps(void* hv, int el, int32_t* out) {
+#ifdef JAAD_ORACLE_WITH_SBR
+  Handle* h = static_cast<Handle*>(hv);
+  auto& ae = h->dec->syn.audioElements;
+  if (el < 0 || el >= (int)ae.size() || !ae[el]->sbr || ae[el]->type == EL_CPE) return -1;
+  sbr::SBR1* s = static_cast<sbr::SBR1*>(ae[el]->sbr.get());
+  if (!s->ps) return -1;
+  ps::PSImpl* p = static_cast<ps::PSImpl*>(s->ps.get());
+  memset(out, 0, sizeof(int32_t) * 350);
+  out[0] = p->num_env;
+  for (int i = 0; i < 6; ++i) out[1 + i] = p->border_position[i];
+  for (int env = 0; env < 5; ++env)
+    for (int i = 0; i < 34; ++i) { out[8 + env * 34 + i] = p->iid.index[env][i]; out[8 + 170 + env * 34 + i] = p->icc.index[env][i]; }
+  out[348] = p->iid.mode;
+  out[349] = p->icc.mode;
+  return 0;
+#else
+  (void)hv; (void)el; (void)out;
   return -1;
 #endif
 }

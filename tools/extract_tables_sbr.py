@@ -38,3 +38,22 @@ def emit(em, ref, JavaFile, AAC):
                "T_HUFFMAN_ENV_3_0DB", "F_HUFFMAN_ENV_3_0DB", "T_HUFFMAN_ENV_BAL_3_0DB", "F_HUFFMAN_ENV_BAL_3_0DB",
                "T_HUFFMAN_NOISE_3_0DB", "T_HUFFMAN_NOISE_BAL_3_0DB"):
         em.i32("SBR_" + nm, ht.ints(nm), "int16_t", "sbr/HuffmanTables.java  binary tree, rows {next0, next1}, leaf = value-64 (<0)")
+    emit_ps(em, ref, JavaFile, AAC)
+
+
+def emit_ps(em, ref, JavaFile, AAC):
+    P = AAC + "ps/"
+    em.raw("/* ======================= PS tables (ps package) ======================= */")
+    t = JavaFile(ref, P + "PSTables.java")
+    em.f32("PS_FILTER_A", t.floats("filter_a"), "ps/PSTables.java:20")
+    for nm in ("Phi_Fract_Qmf", "Phi_Fract_SubQmf20", "Q_Fract_allpass_Qmf", "Q_Fract_allpass_SubQmf20", "cos_alphas", "sin_alphas",
+               "cos_betas_normal", "sin_betas_normal", "cos_betas_fine", "sin_betas_fine", "sincos_alphas_B_normal",
+               "sincos_alphas_B_fine", "cos_gammas_normal", "cos_gammas_fine", "sin_gammas_normal", "sin_gammas_fine",
+               "sf_iid_normal", "sf_iid_fine"):
+        em.f32("PS_" + nm.upper(), t.floats(nm), "ps/PSTables.java")
+    h = JavaFile(ref, P + "Huffman.java")
+    for nm in ("f_huff_iid_def", "t_huff_iid_def", "f_huff_iid_fine", "t_huff_iid_fine", "f_huff_icc", "t_huff_icc",
+               "f_huff_ipd", "t_huff_ipd", "f_huff_opd", "t_huff_opd"):
+        em.i32("PS_" + nm.upper(), h.ints(nm), "int16_t", "ps/Huffman.java  binary tree, rows {next0, next1}, leaf = value-31 (<0)")
+    em.f32("PS_P2_13_20", JavaFile(ref, P + "Filter2.java").floats("p2_13_20"), "ps/Filter2.java:15")
+    em.f32("PS_P8_13_20", JavaFile(ref, P + "Filter8.java").floats("p8_13_20"), "ps/Filter8.java:17")
