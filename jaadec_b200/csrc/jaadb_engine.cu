@@ -152,8 +152,8 @@ struct FrameIndex {
   uint32_t n_ics = 0;
   // SBR streams: one parse run per element (K3), one process run per channel (K4)
   std::vector<SbrRunDev> sbr_runs;
-  std::vector<K4RunDev> k4_runs;
-  uint32_t n_sbr_frames = 0;
+  std::vector<K4RunDev> k4_runs;      // plain SBR channels first, then the SBR+PS ones
+  uint32_t n_sbr_frames = 0, n_k4_plain = 0, n_ps_frames = 0;
   // when set, frames / run_frames are written here (pinned staging of the one-call path) instead of the vectors
   FrameDev* frames_out = nullptr;
   RunFrameDev* run_frames_out = nullptr;
@@ -201,6 +201,7 @@ struct jaadb_engine {
   bool sbr_ready = false;
   SbrElemDev* d_sbr_elem = nullptr;   // [max_streams][2]
   SbrChanDev* d_sbr_chan = nullptr;   // [max_streams][kSbrChansPerStream]
+  PsChanDev* d_ps_chan = nullptr;     // [max_streams]
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
   // workspace of the one-call path (jaadb_decode): grow-only, so a steady stream of calls allocates nothing.
@@ -221,6 +222,7 @@ struct jaadb_engine {
     DevBuf<SbrRunDev> sbr_runs;
     DevBuf<K4RunDev> k4_runs;
     DevBuf<SbrFrameDev> sbr_frames;
+    DevBuf<PsFrameDev> ps_frames;
     DevBuf<float> core;
     FrameSide* h_fside = nullptr;      // pinned
     uint32_t* h_pcm_bytes = nullptr;   // pinned
@@ -270,7 +272,8 @@ struct jaadb_batch {
   DevBuf<float> d_spec_tap;
   std::vector<SbrRunDev> sbr_runs;
   std::vector<K4RunDev> k4_runs;
-  uint32_t n_sbr_frames = 0;
+  uint32_t n_sbr_frames = 0, n_k4_plain = 0, n_ps_frames = 0;
+  DevBuf<PsFrameDev> d_ps_frames;
   DevBuf<SbrRunDev> d_sbr_runs;
   DevBuf<K4RunDev> d_k4_runs;
   DevBuf<SbrFrameDev> d_sbr_frames;
@@ -363,6 +366,38 @@ int init_sbr(jaadb_engine* e) {
   if ((rc = e->upload(JT(SBR_W_ARRAY_REAL), 16, &D.w_real))) return rc;
   if ((rc = e->upload(JT(SBR_W_ARRAY_IMAG), 16, &D.w_imag))) return rc;
   if ((rc = e->upload(JT(SBR_NOISE_TABLE), T::SBR_NOISE_TABLE_N, &D.noise_table))) return rc;
+  // parametric stereo
+  {
+    static const int16_t* ph[6] = {T::PS_F_HUFF_IID_DEF, T::PS_T_HUFF_IID_DEF, T::PS_F_HUFF_IID_FINE, T::PS_T_HUFF_IID_FINE,
+                                   T::PS_F_HUFF_ICC, T::PS_T_HUFF_ICC};
+    static const int ph_n[6] = {T::PS_F_HUFF_IID_DEF_N, T::PS_T_HUFF_IID_DEF_N, T::PS_F_HUFF_IID_FINE_N, T::PS_T_HUFF_IID_FINE_N,
+                                T::PS_F_HUFF_ICC_N, T::PS_T_HUFF_ICC_N};
+    for (int i = 0; i < 6; ++i)
+      if ((rc = e->upload(ph[i], ph_n[i], &D.ps_huff[i]))) return rc;
+    if ((rc = e->upload(JT(PS_FILTER_A), 3, &D.ps_filter_a))) return rc;
+    if ((rc = e->upload(JT(PS_PHI_FRACT_QMF), T::PS_PHI_FRACT_QMF_N, &D.ps_phi_qmf))) return rc;
+    if ((rc = e->upload(JT(PS_PHI_FRACT_SUBQMF20), T::PS_PHI_FRACT_SUBQMF20_N, &D.ps_phi_sub))) return rc;
+    if ((rc = e->upload(JT(PS_Q_FRACT_ALLPASS_QMF), T::PS_Q_FRACT_ALLPASS_QMF_N, &D.ps_q_qmf))) return rc;
+    if ((rc = e->upload(JT(PS_Q_FRACT_ALLPASS_SUBQMF20), T::PS_Q_FRACT_ALLPASS_SUBQMF20_N, &D.ps_q_sub))) return rc;
+    if ((rc = e->upload(JT(PS_COS_ALPHAS), 8, &D.ps_cos_alphas))) return rc;
+    if ((rc = e->upload(JT(PS_SIN_ALPHAS), 8, &D.ps_sin_alphas))) return rc;
+    if ((rc = e->upload(JT(PS_COS_BETAS_NORMAL), T::PS_COS_BETAS_NORMAL_N, &D.ps_cos_betas[0]))) return rc;
+    if ((rc = e->upload(JT(PS_COS_BETAS_FINE), T::PS_COS_BETAS_FINE_N, &D.ps_cos_betas[1]))) return rc;
+    if ((rc = e->upload(JT(PS_SIN_BETAS_NORMAL), T::PS_SIN_BETAS_NORMAL_N, &D.ps_sin_betas[0]))) return rc;
+    if ((rc = e->upload(JT(PS_SIN_BETAS_FINE), T::PS_SIN_BETAS_FINE_N, &D.ps_sin_betas[1]))) return rc;
+    // IIDMode hands (sin_gammas, cos_gammas) to constructor parameters named (cos_gammas, sin_gammas)
+    // (ps/IIDMode.java:16-28 vs ps/IIDTables.java:17-21): what the mixing code calls cos_gammas is the sin table
+    if ((rc = e->upload(JT(PS_SIN_GAMMAS_NORMAL), T::PS_SIN_GAMMAS_NORMAL_N, &D.ps_cos_gammas[0]))) return rc;
+    if ((rc = e->upload(JT(PS_SIN_GAMMAS_FINE), T::PS_SIN_GAMMAS_FINE_N, &D.ps_cos_gammas[1]))) return rc;
+    if ((rc = e->upload(JT(PS_COS_GAMMAS_NORMAL), T::PS_COS_GAMMAS_NORMAL_N, &D.ps_sin_gammas[0]))) return rc;
+    if ((rc = e->upload(JT(PS_COS_GAMMAS_FINE), T::PS_COS_GAMMAS_FINE_N, &D.ps_sin_gammas[1]))) return rc;
+    if ((rc = e->upload(JT(PS_SINCOS_ALPHAS_B_NORMAL), T::PS_SINCOS_ALPHAS_B_NORMAL_N, &D.ps_sincos_alphas_b[0]))) return rc;
+    if ((rc = e->upload(JT(PS_SINCOS_ALPHAS_B_FINE), T::PS_SINCOS_ALPHAS_B_FINE_N, &D.ps_sincos_alphas_b[1]))) return rc;
+    if ((rc = e->upload(JT(PS_SF_IID_NORMAL), T::PS_SF_IID_NORMAL_N, &D.ps_sf_iid[0]))) return rc;
+    if ((rc = e->upload(JT(PS_SF_IID_FINE), T::PS_SF_IID_FINE_N, &D.ps_sf_iid[1]))) return rc;
+    if ((rc = e->upload(JT(PS_P8_13_20), 7, &D.ps_p8))) return rc;
+    if ((rc = e->upload(JT(PS_P2_13_20), 7, &D.ps_p2))) return rc;
+  }
   // FBT.find_bands / find_initial_power (sbr/FBT.java:135-145) for every argument the band-table code can pass, evaluated
   // here on the host in double precision exactly as the Java expressions are
   {
@@ -400,10 +435,13 @@ int init_sbr(jaadb_engine* e) {
   const size_t ns = e->streams.size();
   CUDA_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->d_sbr_elem), sizeof(SbrElemDev) * ns * 2));
   CUDA_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->d_sbr_chan), sizeof(SbrChanDev) * ns * kSbrChansPerStream));
+  CUDA_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->d_ps_chan), sizeof(PsChanDev) * ns));
   cudaFuncSetAttribute(k3_sbr_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SbrElemDev) * kK3WarpsPerBlock));
-  cudaFuncSetAttribute(k4_sbr_process_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_bytes());
-  cudaFuncSetAttribute(k4_sbr_process_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_bytes());
-  cudaFuncSetAttribute(k4_sbr_process_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_bytes());
+#define K4_ATTR(FMT)                                                                                                       \
+  cudaFuncSetAttribute(k4_sbr_process_kernel<FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_bytes(false)); \
+  cudaFuncSetAttribute(k4_sbr_process_kernel<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_bytes(true))
+  K4_ATTR(0); K4_ATTR(1); K4_ATTR(2);
+#undef K4_ATTR
   e->sbr_ready = true;
   return 0;
 }
@@ -450,7 +488,7 @@ int finish_open(jaadb_engine* e, StreamHost& s, int32_t* stream_id) {
   s.n_slots = l.n_channels;
   s.out_channels = (s.chan_cfg == 1) ? 2 : l.n_channels;  // DecoderConfig.getChannelCount (DecoderConfig.java:108-115)
   s.profile_ok = profile_supported(s.profile);
-  if (s.sbr > 1) { e->set_error("parametric stereo (HE-AAC v2) streams are not implemented in this build"); return JAADB_E_CONFIG; }
+  if (s.sbr > 1 && s.chan_cfg != 1) { e->set_error("parametric stereo needs a mono core"); return JAADB_E_CONFIG; }
   if (s.sbr) {
     if (s.chan_cfg > 2) { e->set_error("SBR is implemented for mono and stereo streams only"); return JAADB_E_CONFIG; }
     if (s.sample_length != 2048) { e->set_error("down-sampled SBR (32-band synthesis) is not implemented"); return JAADB_E_CONFIG; }
@@ -468,9 +506,16 @@ int finish_open(jaadb_engine* e, StreamHost& s, int32_t* stream_id) {
     // a fresh SBR object per element: everything zero except Channel.prevEnvIsShort = -1 (Channel.java:51)
     static SbrElemDev fresh[2];
     memset(fresh, 0, sizeof fresh);
-    for (auto& el : fresh) { el.ch[0].prevEnvIsShort = -1; el.ch[1].prevEnvIsShort = -1; }
+    for (auto& el : fresh) { el.ch[0].prevEnvIsShort = -1; el.ch[1].prevEnvIsShort = -1; el.ps.iid.mode = -1; el.ps.icc.mode = -1; }
     CUDA_TRY(e, cudaMemcpyAsync(e->d_sbr_elem + (size_t)slot * 2, fresh, sizeof fresh, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemsetAsync(e->d_sbr_chan + (size_t)slot * kSbrChansPerStream, 0, sizeof(SbrChanDev) * kSbrChansPerStream, e->stream));
+    if (s.sbr > 1) {
+      // a fresh PSImpl (ps/PSImpl.java:64-94): everything zero except h11_prev = 1
+      static PsChanDev fresh_ps;
+      memset(&fresh_ps, 0, sizeof fresh_ps);
+      for (auto& h : fresh_ps.h_prev) h[0] = 1.0f;
+      CUDA_TRY(e, cudaMemcpyAsync(e->d_ps_chan + slot, &fresh_ps, sizeof fresh_ps, cudaMemcpyHostToDevice, e->stream));
+    }
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   }
   CUDA_TRY(e, cudaMemsetAsync(e->d_overlap + (size_t)slot * kMaxChannels * 1024, 0, sizeof(float) * kMaxChannels * 1024, e->stream));
@@ -530,6 +575,8 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
   ix.sbr_runs.clear();
   ix.k4_runs.clear();
   ix.n_sbr_frames = 0;
+  ix.n_k4_plain = 0;
+  ix.n_ps_frames = 0;
   // per-stream frame counts (counting sort keeps array order inside each stream)
   std::vector<uint32_t>& count = e->scratch_count;
   count.assign(e->streams.size(), 0);
@@ -577,36 +624,45 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
   }
   uint32_t acc = 0;
   for (auto& r : ix.runs) { r.first = acc; acc += r.count; }
-  for (const auto& r : ix.runs) {
-    if (!r.sbr) continue;
-    const StreamHost& sh = e->streams[r.stream_slot];
-    const bool stereo = sh.chan_cfg == 2;
-    SbrRunDev sr;
-    memset(&sr, 0, sizeof sr);
-    sr.stream_slot = r.stream_slot;
-    sr.first = r.first;
-    sr.count = r.count;
-    sr.sbr_base = ix.n_sbr_frames;
-    sr.element = 0;
-    sr.stereo = stereo ? 1 : 0;
-    sr.sr_index = (uint8_t)(sh.sf_index - 3);
-    sr.first_ch = 0;
-    ix.sbr_runs.push_back(sr);
-    for (int c = 0; c < (stereo ? 2 : 1); ++c) {
-      K4RunDev kr;
-      memset(&kr, 0, sizeof kr);
-      kr.stream_slot = r.stream_slot;
-      kr.first = r.first;
-      kr.count = r.count;
-      kr.sbr_base = sr.sbr_base;
-      kr.chan = (uint8_t)c;
-      kr.ch_slot = (uint8_t)c;
-      kr.out_ch = (uint8_t)c;
-      kr.n_out = 2;
-      kr.dup = stereo ? 0 : 1;
-      ix.k4_runs.push_back(kr);
+  for (int pass = 0; pass < 2; ++pass) {   // plain SBR first, SBR+PS second: K4 launches them as two grids
+    for (const auto& r : ix.runs) {
+      if (!r.sbr) continue;
+      const StreamHost& sh = e->streams[r.stream_slot];
+      const bool with_ps = sh.sbr > 1;
+      if (with_ps != (pass == 1)) continue;
+      const bool stereo = sh.chan_cfg == 2;
+      SbrRunDev sr;
+      memset(&sr, 0, sizeof sr);
+      sr.stream_slot = r.stream_slot;
+      sr.first = r.first;
+      sr.count = r.count;
+      sr.sbr_base = ix.n_sbr_frames;
+      sr.element = 0;
+      sr.stereo = stereo ? 1 : 0;
+      sr.sr_index = (uint8_t)(sh.sf_index - 3);
+      sr.first_ch = 0;
+      sr.ps = with_ps ? 1 : 0;
+      sr.ps_base = ix.n_ps_frames;
+      ix.sbr_runs.push_back(sr);
+      for (int c = 0; c < (stereo ? 2 : 1); ++c) {
+        K4RunDev kr;
+        memset(&kr, 0, sizeof kr);
+        kr.stream_slot = r.stream_slot;
+        kr.first = r.first;
+        kr.count = r.count;
+        kr.sbr_base = sr.sbr_base;
+        kr.chan = (uint8_t)c;
+        kr.ch_slot = (uint8_t)c;
+        kr.out_ch = (uint8_t)c;
+        kr.n_out = 2;
+        kr.dup = stereo ? 0 : 1;
+        kr.ps_base = sr.ps_base;
+        ix.k4_runs.push_back(kr);
+      }
+      ix.n_sbr_frames += r.count;
+      if (with_ps) ix.n_ps_frames += r.count;
     }
-    ix.n_sbr_frames += r.count;
+    if (pass == 0) ix.n_k4_plain = (uint32_t)ix.k4_runs.size();
   }
   if (!ix.run_frames_out) ix.run_frames.resize(n);
   RunFrameDev* const rout = ix.run_frames_out ? ix.run_frames_out : ix.run_frames.data();
@@ -637,6 +693,8 @@ struct DecodeBufs {
   const K4RunDev* k4_runs;
   SbrFrameDev* sbr_frames;
   float* core;
+  PsFrameDev* ps_frames;
+  uint32_t n_k4_plain;
 };
 
 // K1 (+ K3) + K2 (+ K4) over an indexed set of frames, everything already on the device.
@@ -653,7 +711,7 @@ void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_gr
     // SBR payload parse before the filterbank: an exception inside SBR.decode fails the whole frame
     const int blocks = (int)((n_sbr_runs + kK3WarpsPerBlock - 1) / kK3WarpsPerBlock);
     k3_sbr_parse_kernel<<<blocks, 32 * kK3WarpsPerBlock, sizeof(SbrElemDev) * kK3WarpsPerBlock, e->stream>>>(
-        B.blob, B.frames, B.fside, B.sbr_runs, n_sbr_runs, B.run_frames, e->d_sbr_elem, B.sbr_frames, e->sbr_tables, e->sbr_const);
+        B.blob, B.frames, B.fside, B.sbr_runs, n_sbr_runs, B.run_frames, e->d_sbr_elem, B.sbr_frames, B.ps_frames, e->sbr_tables, e->sbr_const);
     ++*launches;
   }
   if (after_k1) cudaEventRecord(after_k1, e->stream);
@@ -678,14 +736,25 @@ void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_gr
   }
   if (after_k2) cudaEventRecord(after_k2, e->stream);
   if (n_k4_runs) {
-#define LAUNCH_K4(FMT)                                                                                              \
-  k4_sbr_process_kernel<FMT><<<n_k4_runs, kK4Threads, k4_smem_bytes(), e->stream>>>(                                \
-      B.k4_runs, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, B.pcm, B.pcm_off, B.pcm_bytes, e->sbr_tables)
+    const uint32_t n_plain = B.n_k4_plain, n_ps = n_k4_runs - B.n_k4_plain;
+#define LAUNCH_K4(FMT)                                                                                                  \
+  do {                                                                                                                  \
+    if (n_plain) {                                                                                                      \
+      k4_sbr_process_kernel<FMT, false><<<n_plain, kK4Threads, k4_smem_bytes(false), e->stream>>>(                      \
+          B.k4_runs, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, B.pcm, B.pcm_off, B.pcm_bytes, e->sbr_tables, nullptr, nullptr); \
+      ++*launches;                                                                                                      \
+    }                                                                                                                   \
+    if (n_ps) {                                                                                                         \
+      k4_sbr_process_kernel<FMT, true><<<n_ps, kK4Threads, k4_smem_bytes(true), e->stream>>>(                           \
+          B.k4_runs + n_plain, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, B.pcm, B.pcm_off, B.pcm_bytes,        \
+          e->sbr_tables, B.ps_frames, e->d_ps_chan);                                                                    \
+      ++*launches;                                                                                                      \
+    }                                                                                                                   \
+  } while (0)
     if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K4(0);
     else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K4(1);
     else LAUNCH_K4(2);
 #undef LAUNCH_K4
-    ++*launches;
   }
 }
 
@@ -764,6 +833,7 @@ void jaadb_engine_destroy(jaadb_engine* e) {
   if (e->d_sstate) cudaFree(e->d_sstate);
   if (e->d_sbr_elem) cudaFree(e->d_sbr_elem);
   if (e->d_sbr_chan) cudaFree(e->d_sbr_chan);
+  if (e->d_ps_chan) cudaFree(e->d_ps_chan);
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);
   auto& W = e->ws;
@@ -779,7 +849,7 @@ void jaadb_engine_destroy(jaadb_engine* e) {
   }
   W.blob.release(); W.frames.release(); W.fside.release(); W.iside.release(); W.q.release(); W.runs.release();
   W.run_frames.release(); W.pcm_bytes.release(); W.pcm_off.release();
-  W.sbr_runs.release(); W.k4_runs.release(); W.sbr_frames.release(); W.core.release();
+  W.sbr_runs.release(); W.k4_runs.release(); W.sbr_frames.release(); W.core.release(); W.ps_frames.release();
   if (W.h_fside) cudaFreeHost(W.h_fside);
   if (W.h_pcm_bytes) cudaFreeHost(W.h_pcm_bytes);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -926,6 +996,8 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
   b->sbr_runs.swap(ix.sbr_runs);
   b->k4_runs.swap(ix.k4_runs);
   b->n_sbr_frames = ix.n_sbr_frames;
+  b->n_k4_plain = ix.n_k4_plain;
+  b->n_ps_frames = ix.n_ps_frames;
   const uint32_t ics = ix.n_ics;
   // device side
   cudaError_t ce = cudaSuccess;
@@ -946,6 +1018,7 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
     chk(b->d_k4_runs.ensure(b->k4_runs.size()));
     chk(b->d_sbr_frames.ensure((size_t)b->n_sbr_frames * 2));
     chk(b->d_core.ensure((size_t)ics * 1024));
+    if (b->n_ps_frames) chk(b->d_ps_frames.ensure(b->n_ps_frames));
   }
   if (ce != cudaSuccess) { e->set_error(std::string("batch allocation: ") + cudaGetErrorString(ce)); return fail(JAADB_E_NOMEM); }
   if (n) {
@@ -986,7 +1059,7 @@ int jaadb_batch_decode(jaadb_batch* b) {
   if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[0], e->stream));
   DecodeBufs B{b->d_blob.p, b->d_frames.p, b->d_fside.p, b->d_iside.p, b->d_q.p, b->d_runs.p, b->d_run_frames.p, b->d_pcm.p,
                b->d_pcm_off.p, b->d_pcm_bytes.p, (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) ? b->d_spec_tap.p : nullptr,
-               b->d_sbr_runs.p, b->d_k4_runs.p, b->d_sbr_frames.p, b->d_core.p};
+               b->d_sbr_runs.p, b->d_k4_runs.p, b->d_sbr_frames.p, b->d_core.p, b->d_ps_frames.p, b->n_k4_plain};
   launch_decode(e, b->groups.data(), b->groups.size(), b->n_frames, (uint32_t)b->sbr_runs.size(), (uint32_t)b->k4_runs.size(), B,
                 prof ? e->ev[1] : nullptr, prof ? e->ev[3] : nullptr, &launches);
   if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[2], e->stream));
@@ -1053,7 +1126,7 @@ void jaadb_batch_destroy(jaadb_batch* b) {
   b->d_blob.release(); b->d_pcm.release(); b->d_frames.release(); b->d_fside.release(); b->d_iside.release();
   b->d_q.release(); b->d_runs.release(); b->d_run_frames.release(); b->d_pcm_bytes.release(); b->d_pcm_off.release();
   b->d_spec_tap.release();
-  b->d_sbr_runs.release(); b->d_k4_runs.release(); b->d_sbr_frames.release(); b->d_core.release();
+  b->d_sbr_runs.release(); b->d_k4_runs.release(); b->d_sbr_frames.release(); b->d_core.release(); b->d_ps_frames.release();
   delete b;
 }
 
@@ -1126,6 +1199,7 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
     chk(W.sbr_runs.ensure(e->streams.size()));
     chk(W.k4_runs.ensure(e->streams.size() * 2));
     chk(W.sbr_frames.ensure((size_t)chunk * 2));
+    chk(W.ps_frames.ensure((size_t)chunk));
     chk(W.core.ensure(max_ics * 1024));
   }
   if (ce == cudaSuccess && (W.h_chunk_cap < chunk || W.h_runs_cap < e->streams.size())) {
@@ -1186,7 +1260,8 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
       CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     }
     DecodeBufs B{W.blob.p, W.frames.p, W.fside.p + r.i0, W.iside.p, W.q.p, W.runs.p, W.run_frames.p, W.pcm[pb].p - r.lo,
-                 W.pcm_off.p + r.i0, W.pcm_bytes.p + r.i0, nullptr, W.sbr_runs.p, W.k4_runs.p, W.sbr_frames.p, W.core.p};
+                 W.pcm_off.p + r.i0, W.pcm_bytes.p + r.i0, nullptr, W.sbr_runs.p, W.k4_runs.p, W.sbr_frames.p, W.core.p, W.ps_frames.p,
+                 ix.n_k4_plain};
     launch_decode(e, ix.groups.data(), ix.groups.size(), n, (uint32_t)ix.sbr_runs.size(), (uint32_t)ix.k4_runs.size(), B, nullptr,
                   nullptr, &launches);
     CUDA_TRY(e, cudaGetLastError());

@@ -649,10 +649,141 @@ __device__ inline int sbr_harmonics(SbrBits& ld, SbrChanParse& c, int N_high) {
   return 0;
 }
 
+// ---- parametric stereo payload (ps/PSImpl.java:103-135, ICData.java:21-32, EnvData.java:44-49, Envelope.java:24-30) --
+__device__ inline int ps_nr_par(int id) { return id % 3 == 0 ? 10 : (id % 3 == 1 ? 20 : 34); }
+__device__ inline int ps_stride(int id) { return (id % 3) == 0 ? 2 : 0; }   // ICMode.stride
+
+__device__ inline int ps_huff(SbrBits& ld, const int16_t* __restrict__ t, int& out) {  // ps/Huffman.java:264-276
+  int index = 0;
+  while (index >= 0) {
+    int bit;
+    SBR_RD(bit, 1);
+    index = t[index * 2 + bit];
+  }
+  out = index + 31;
+  return 0;
+}
+
+__device__ inline int ps_read_mode(SbrBits& ld, PsParamDev& p) {
+  int en, id;
+  SBR_RD(en, 1);
+  if (en) {
+    SBR_RD(id, 3);
+    if (id > 5) return JAADB_ST_ARRAY_BOUNDS;   // IID_MODES[id] / ICC_MODES[id]
+    p.mode = (int8_t)id;
+  } else p.mode = -1;
+  return 0;
+}
+
+__device__ inline int ps_read_data(SbrBits& ld, const SbrTablesDev& T, PsParamDev& p, bool icc, int num_env) {
+  if (p.mode < 0) return 0;
+  const int nr = ps_nr_par(p.mode);
+  for (int n = 0; n < num_env; n++) {
+    int dt, v;
+    SBR_RD(dt, 1);
+    p.dt[n] = (uint8_t)dt;
+    const int16_t* h = icc ? T.ps_huff[dt ? 5 : 4] : (p.mode < 3 ? T.ps_huff[dt ? 1 : 0] : T.ps_huff[dt ? 3 : 2]);
+    for (int i = 0; i < nr; i++) { SBR_TRY(ps_huff(ld, h, v)); p.index[n][i] = (int8_t)v; }
+  }
+  return 0;
+}
+
+// PSImpl.decode
+__device__ inline int ps_decode(SbrBits& ld, const SbrTablesDev& T, PsParseDev& P) {
+  int v;
+  SBR_RD(v, 1);
+  if (v) {
+    P.header_read = 1;
+    SBR_TRY(ps_read_mode(ld, P.iid));
+    SBR_TRY(ps_read_mode(ld, P.icc));
+    SBR_RD(v, 1);
+    P.ext_enabled = (uint8_t)v;
+    if (v) return JAADB_ST_UNSUPPORTED_ELEMENT;   // IPD/OPD extension: outside the engine's scope
+  }
+  SBR_RD(v, 1);
+  P.var_borders = (uint8_t)v;
+  int tmp;
+  SBR_RD(tmp, 2);
+  const int num_env = P.var_borders ? tmp + 1 : (tmp == 3 ? 4 : tmp);   // num_env_tab (PSTables.java:16-19)
+  P.num_env = (uint8_t)num_env;
+  if (P.var_borders)
+    for (int n = 1; n < num_env + 1; n++) { SBR_RD(v, 5); P.border_position[n] = (uint8_t)(v + 1); }
+  SBR_TRY(ps_read_data(ld, T, P.iid, false, num_env));
+  SBR_TRY(ps_read_data(ld, T, P.icc, true, num_env));
+  P.data_available = 1;
+  return 0;
+}
+
+// Envelope.decode (:45-74) for one envelope of one parameter set
+__device__ inline void ps_decode_env(PsParamDev& p, bool icc, int env) {
+  int8_t* ix = p.index[env];
+  if (p.mode < 0) { p.dt[env] = 0; for (int i = 0; i < 34; ++i) ix[i] = 0; return; }
+  const int st = ps_stride(p.mode), nr = ps_nr_par(p.mode);
+  const int lim = icc ? 7 : (p.mode < 3 ? 7 : 15);
+  const int lo = icc ? 0 : -lim;
+  const int8_t* prev = env == 0 ? p.first : p.index[env - 1];
+  if (p.dt[env]) {
+    for (int i = 0; i < nr; i++) ix[i] = (int8_t)min(max(prev[i * st] + ix[i], lo), lim);
+  } else {
+    int pc = ix[0];
+    for (int i = 1; i < nr; i++) { pc = min(max(pc + ix[i], lo), lim); ix[i] = (int8_t)pc; }
+  }
+  if (st > 1)
+    for (int i = st * nr - 1; i > 0; --i) ix[i] = ix[i / st];
+}
+
+// PSImpl.ps_data_decode (:137-199) -> the frame record K4 mixes with
+__device__ inline void ps_data_decode(PsParseDev& P, PsFrameDev& o) {
+  int num_env = P.data_available ? P.num_env : 0;
+  PsParamDev* ps[2] = {&P.iid, &P.icc};
+  for (int k = 0; k < 2; ++k) {
+    PsParamDev& p = *ps[k];
+    if (num_env == 0) {
+      if (p.mode >= 0) { for (int i = 0; i < 34; ++i) p.index[0][i] = p.first[i]; }
+      else { p.dt[0] = 0; for (int i = 0; i < 34; ++i) p.index[0][i] = 0; }
+    } else {
+      for (int env = 0; env < num_env; env++) ps_decode_env(p, k == 1, env);
+    }
+  }
+  if (num_env == 0) num_env = 1;
+  for (int k = 0; k < 2; ++k)
+    for (int i = 0; i < 34; ++i) ps[k]->first[i] = ps[k]->index[num_env - 1][i];
+  P.data_available = 0;
+  const int L = 32;
+  if (!P.var_borders) {
+    P.border_position[0] = 0;
+    for (int env = 1; env < num_env; env++) P.border_position[env] = (uint8_t)((env * L) / num_env);
+    P.border_position[num_env] = L;
+  } else {
+    P.border_position[0] = 0;
+    if (P.border_position[num_env] < L) {
+      for (int k = 0; k < 2; ++k)
+        for (int i = 0; i < 34; ++i) ps[k]->index[num_env][i] = ps[k]->index[num_env - 1][i];   // Envelope.restore
+      ++num_env;
+      P.border_position[num_env] = L;
+    }
+    int bpl = P.border_position[0];
+    for (int env = 1; env < num_env; env++) {
+      const int bp = P.border_position[env];
+      const int mx = L - (num_env - env);
+      bpl = min(max(bp, bpl + 1), mx);
+      if (bpl != bp) P.border_position[env] = (uint8_t)bpl;
+    }
+  }
+  P.num_env = (uint8_t)num_env;
+  o.use_ps = 1;
+  o.num_env = (uint8_t)num_env;
+  for (int i = 0; i < 6; ++i) o.border[i] = P.border_position[i];
+  o.iid_mode = P.iid.mode < 0 ? 0 : P.iid.mode;
+  o.icc_mode = P.icc.mode < 0 ? 1 : P.icc.mode;
+  for (int env = 0; env < 5; ++env)
+    for (int i = 0; i < 20; ++i) { o.iid[env][i] = P.iid.index[env][i]; o.icc[env][i] = P.icc.index[env][i]; }
+}
+
 // SBR.readExtendedData (:229-242).  Extension payloads (parametric stereo = id 2) are skipped in this build: the
 // engine refuses SBR+PS streams at open, and for plain SBR streams the reference's sbr_extension is a no-op that
 // re-reads 2-bit ids until fewer than 8 bits remain -- nothing observable.
-__device__ inline int sbr_extended_data(SbrBits& ld) {
+__device__ inline int sbr_extended_data(SbrBits& ld, const SbrTablesDev& T, PsParseDev* ps) {
   int v;
   SBR_RD(v, 1);
   if (v) {
@@ -660,13 +791,27 @@ __device__ inline int sbr_extended_data(SbrBits& ld) {
     SBR_RD(cnt, 4);
     if (cnt == 15) { SBR_RD(v, 8); cnt += v; }
     if (ld.left() < (uint32_t)(8 * cnt)) return JAADB_ST_EOS;
+    if (ps) {
+      // SBR1.sbr_extension (:62-73): extension id 2 is parametric stereo; everything else only consumes its 2-bit id
+      SbrBits sub = ld;
+      sub.end = ld.pos + 8 * cnt;
+      while (sub.left() > 7) {
+        int id;
+        if (!sub.get(2, id)) return JAADB_ST_EOS;
+        if (id == 2) {
+          ps->opened = 1;
+          const int st = ps_decode(sub, T, *ps);
+          if (st) return st;
+        }
+      }
+    }
     ld.pos += 8 * cnt;
   }
   return 0;
 }
 
 // SBR1.sbr_data (:34-60) / SBR2.sbr_data (:35-135).  `valid` as SBR.decode sets it.
-__device__ inline int sbr_data(SbrBits& ld, const SbrCtx& C, bool stereo, int& result) {
+__device__ inline int sbr_data(SbrBits& ld, const SbrCtx& C, bool stereo, bool with_ps, int& result) {
   SbrElemDev& S = *C.S;
   SbrChanParse& c0 = S.ch[0];
   SbrChanParse& c1 = S.ch[1];
@@ -686,7 +831,7 @@ __device__ inline int sbr_data(SbrBits& ld, const SbrCtx& C, bool stereo, int& r
     // is built (same inputs: E, Q, amp_res, f, n)
     for (int i = 0; i < 64; ++i) c0.bs_add_harmonic[i] = 0;
     SBR_TRY(sbr_harmonics(ld, c0, S.N_high));
-    SBR_TRY(sbr_extended_data(ld));
+    SBR_TRY(sbr_extended_data(ld, *C.T, with_ps ? &S.ps : nullptr));
     return 0;
   }
   SBR_RD(v, 1);
@@ -744,12 +889,12 @@ __device__ inline int sbr_data(SbrBits& ld, const SbrCtx& C, bool stereo, int& r
     SBR_TRY(sbr_harmonics(ld, c0, S.N_high));
     SBR_TRY(sbr_harmonics(ld, c1, S.N_high));
   }
-  SBR_TRY(sbr_extended_data(ld));
+  SBR_TRY(sbr_extended_data(ld, *C.T, nullptr));
   return 0;
 }
 
 // SBR.decode (:161-185).  Returns a frame status (0 = fine).
-__device__ inline int sbr_decode(SbrBits& ld, const SbrCtx& C, bool stereo, bool crc) {
+__device__ inline int sbr_decode(SbrBits& ld, const SbrCtx& C, bool stereo, bool with_ps, bool crc) {
   SbrElemDev& S = *C.S;
   int v;
   if (crc) SBR_RD(v, 10);
@@ -774,7 +919,7 @@ __device__ inline int sbr_decode(SbrBits& ld, const SbrCtx& C, bool stereo, bool
   }
   if (S.hdr.present) {
     int result = 0;
-    SBR_TRY(sbr_data(ld, C, stereo, result));
+    SBR_TRY(sbr_data(ld, C, stereo, with_ps, result));
     S.valid = (result == 0) ? 1 : 0;
   } else {
     S.valid = 1;
@@ -830,7 +975,8 @@ constexpr int kK3WarpsPerBlock = 4;
 __global__ void __launch_bounds__(32 * kK3WarpsPerBlock)
 k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ frames, FrameSide* __restrict__ fside,
                     const SbrRunDev* __restrict__ runs, uint32_t n_runs, const RunFrameDev* __restrict__ run_frames,
-                    SbrElemDev* __restrict__ elems, SbrFrameDev* __restrict__ out, SbrTablesDev T, SbrConstTables K) {
+                    SbrElemDev* __restrict__ elems, SbrFrameDev* __restrict__ out, PsFrameDev* __restrict__ ps_out,
+                    SbrTablesDev T, SbrConstTables K) {
   extern __shared__ __align__(16) uint8_t k3_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t r = blockIdx.x * kK3WarpsPerBlock + warp;
@@ -872,7 +1018,7 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
         ld.end = ld.pos + nbits;
         int ext = 0;
         ld.get(4, ext);
-        const int st = sbr_decode(ld, C, stereo, ext == 14);
+        const int st = sbr_decode(ld, C, stereo, run.ps != 0, ext == 14);
         if (st != 0 && frame_status == 0) {
           // an exception inside SBR.decode fails the whole frame (EOS is swallowed by decodeFrame: no output)
           frame_status = st;
@@ -898,6 +1044,12 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
           }
         }
       }
+    }
+    if (lane == 0 && run.ps) {
+      // SBR1.process: parametric stereo runs iff this frame brought ps_data (SBR1.isPSUsed); PSImpl.ps_data_decode
+      PsFrameDev* po = ps_out + run.ps_base + it;
+      po->use_ps = 0;
+      if (mode != 0 && S->ps.opened && S->ps.data_available) ps_data_decode(S->ps, *po);
     }
     mode = __shfl_sync(0xFFFFFFFFu, mode, 0);
     frame_status = __shfl_sync(0xFFFFFFFFu, frame_status, 0);

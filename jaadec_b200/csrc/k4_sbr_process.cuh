@@ -132,6 +132,16 @@ __device__ __forceinline__ void sbr_dct4_kernel(float (&in_real)[32], float (&in
   }
 }
 
+// ps/PSTables.java:26-45 (20-band configuration): group borders and the parameter band of each group
+__device__ __forceinline__ int ps_group_border(int gr) {
+  constexpr int gb[23] = {6, 7, 0, 1, 2, 3, 9, 8, 10, 11, 3, 4, 5, 6, 7, 8, 9, 11, 14, 18, 23, 35, 64};
+  int v = 64;
+#pragma unroll
+  for (int i = 0; i < 23; ++i) if (i == gr) v = gb[i];
+  return v;
+}
+__device__ __forceinline__ int ps_bk(int gr) { return gr == 0 ? 1 : (gr == 1 ? 0 : gr - 2); }   // map_group2bk20 & ~NEGATE_IPD_MASK
+
 constexpr int kK4Threads = 64;
 // shared-memory carve (floats)
 // Row strides are odd so that the one-thread-per-time-slot phases (analysis, synthesis DCTs), where the 32 lanes of a
@@ -146,8 +156,11 @@ static_assert(kK4Xs % 4 == 0 && kK4In % 4 == 0 && kK4V % 4 == 0, "K4 shared-memo
 #define VB(s, r) vb[(s) * kVbStride + (r)]
 #define INB(i) inbuf[(i) + ((i) >> 5)]
 constexpr int kK4Adj = 3 * kSbrMaxLE * 64 + kSbrMaxLE * 64;   // G_lim_boost, Q_M_lim_boost, S_M_boost, E_curr
-__host__ __device__ constexpr size_t k4_smem_bytes() {
-  return sizeof(float) * (kK4Xs + kK4In + kK4V + kK4Adj + 16) + sizeof(SbrFrameDev);
+constexpr int kK4PsFloats = 2 * 32 * kXsStride + 2 * 32 * 24 + 32 * 20 + 3 * 88 + 9 * kVbStride + 3;
+static_assert((2 * 32 * kXsStride + 2 * 32 * 24 + 32 * 20 + 3 * 88 + 9 * kVbStride + 3) % 4 == 0, "PsFrameDev must land 16-byte aligned");
+__host__ __device__ constexpr size_t k4_smem_bytes(bool with_ps = false) {
+  return sizeof(float) * (kK4Xs + kK4In + kK4V + kK4Adj + 16) + sizeof(SbrFrameDev) +
+         (with_ps ? sizeof(float) * kK4PsFloats + sizeof(PsFrameDev) : 0);
 }
 
 struct K4RunDev {
@@ -160,14 +173,17 @@ struct K4RunDev {
   uint8_t n_out;            // output channels of the stream
   uint8_t dup;              // mono element: copy the result to the second output channel (SBR1.process)
   uint8_t pad[3];
+  uint32_t ps_base;         // first PsFrameDev of the run (SBR+PS streams)
 };
 
-template <int PCM_FORMAT>
+// WITH_PS: the channel is the SCE of an SBR+PS stream; frames that carry ps_data go through the parametric-stereo tool
+// (hybrid analysis, decorrelator, mixing, hybrid synthesis; ps/PSImpl.java:685-707) and a second synthesis bank.
+template <int PCM_FORMAT, bool WITH_PS>
 __global__ void __launch_bounds__(kK4Threads)
 k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __restrict__ run_frames,
                       const SbrFrameDev* __restrict__ sframes, const float* __restrict__ core, SbrChanDev* __restrict__ chans,
                       uint8_t* __restrict__ pcm, const uint64_t* __restrict__ pcm_off, uint32_t* __restrict__ pcm_bytes_out,
-                      SbrTablesDev T) {
+                      SbrTablesDev T, const PsFrameDev* __restrict__ ps_frames, PsChanDev* __restrict__ ps_chans) {
   extern __shared__ __align__(16) float k4_smem[];
   float* xs = k4_smem;
   float* inbuf = k4_smem + kK4Xs;
@@ -179,6 +195,20 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
   float (*E_curr)[64] = reinterpret_cast<float (*)[64]>(adj + 3 * kSbrMaxLE * 64);   // [envelope][m]
   float* s_bw = adj + kK4Adj;                                                           // bwArray[8] (+8 spare)
   SbrFrameDev* fp = reinterpret_cast<SbrFrameDev*>(s_bw + 16);
+  // parametric stereo (WITH_PS only): left / right QMF matrices, hybrid sub-bands, energies, right-channel v history
+  float* ps_base = reinterpret_cast<float*>(fp + 1);
+  float* xl = ps_base;                                   // [32][kXsStride]
+  float* xr = xl + 32 * kXsStride;                       // [32][kXsStride]
+  float* hyl = xr + 32 * kXsStride;                      // [32][12][2]
+  float* hyr = hyl + 32 * 24;                            // [32][12][2]
+  float* pg = hyr + 32 * 24;                             // [32][20] band energies, then transient ratios
+  float* hwork = pg + 32 * 20;                           // [3][44][2] hybrid analysis input
+  float* vhr = hwork + 3 * 88;                           // [9][kVbStride] right channel's carried v-vectors
+  PsFrameDev* pp = reinterpret_cast<PsFrameDev*>(vhr + 9 * kVbStride + 3);
+#define XL(l, k, c) xl[(l) * kXsStride + (k) * 2 + (c)]
+#define XR(l, k, c) xr[(l) * kXsStride + (k) * 2 + (c)]
+#define HYL(n, k, c) hyl[((n) * 12 + (k)) * 2 + (c)]
+#define HYR(n, k, c) hyr[((n) * 12 + (k)) * 2 + (c)]
 
   const K4RunDev run = runs[blockIdx.x];
   const int t = threadIdx.x;
@@ -201,6 +231,11 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
   float qc[10];
 #pragma unroll
   for (int j = 0; j < 10; ++j) qc[j] = T.qmf_c[t + 64 * j];
+  PsChanDev* pst = nullptr;
+  if (WITH_PS) {
+    pst = ps_chans + run.stream_slot;
+    for (int i = t; i < 9 * 128; i += kK4Threads) vhr[(8 - i / 128) * kVbStride + (i % 128)] = pst->syn_v_right[i / 128][i % 128];
+  }
   __syncthreads();
 
   for (uint32_t it = 0; it < run.count; ++it) {
@@ -211,6 +246,10 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
       const uint4* src = reinterpret_cast<const uint4*>(sframes + ((size_t)run.sbr_base + it) * 2 + run.chan);
       uint4* dst = reinterpret_cast<uint4*>(fp);
       for (int i = t; i < (int)(sizeof(SbrFrameDev) / 16); i += kK4Threads) dst[i] = src[i];
+      if (WITH_PS) {
+        const uint4* psrc = reinterpret_cast<const uint4*>(ps_frames + run.ps_base + it);
+        if (t < (int)(sizeof(PsFrameDev) / 16)) reinterpret_cast<uint4*>(pp)[t] = psrc[t];
+      }
       const float4* cs = reinterpret_cast<const float4*>(core + ((size_t)rf.ics_base + run.ch_slot) * 1024);
       for (int i = t; i < 256; i += kK4Threads) {
         const float4 v = cs[i];
@@ -226,19 +265,22 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
       __syncthreads();
       continue;
     }
-    auto put_sample = [&](int i, float v) {
+    const bool use_ps = WITH_PS && mode != 0 && pp->use_ps != 0;
+    // och: output channel; dup: also write the next channel (mono element without parametric stereo in this frame)
+    auto put_sample_to = [&](int i, float v, int och, bool dup) {
       if (PCM_FORMAT == 2) {
         float* d = reinterpret_cast<float*>(dst);
-        d[(size_t)run.out_ch * 2048 + i] = v;
-        if (run.dup) d[(size_t)(run.out_ch + 1) * 2048 + i] = v;
+        d[(size_t)och * 2048 + i] = v;
+        if (dup) d[(size_t)(och + 1) * 2048 + i] = v;
       } else {
         uint32_t u = (uint32_t)pcm_round(v) & 0xFFFFu;
         if (PCM_FORMAT == 1) u = __byte_perm(u, 0, 0x4401);
         uint16_t* d = reinterpret_cast<uint16_t*>(dst);
-        d[(size_t)i * n_out + run.out_ch] = (uint16_t)u;
-        if (run.dup) d[(size_t)i * n_out + run.out_ch + 1] = (uint16_t)u;
+        d[(size_t)i * n_out + och] = (uint16_t)u;
+        if (dup) d[(size_t)i * n_out + och + 1] = (uint16_t)u;
       }
     };
+    auto put_sample = [&](int i, float v) { put_sample_to(i, v, run.out_ch, run.dup != 0 && !use_ps); };
     if (t == 0 && run.out_ch == 0) pcm_bytes_out[f] = (uint32_t)(2048 * n_out * (PCM_FORMAT == 2 ? 4 : 2));
 
     if (mode == 0) {
@@ -559,50 +601,356 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
       __syncthreads();
     }
 
-    // ---- 64-band QMF synthesis.  X[l][k] = Xsbr[l + tHFAdj][k] below kx + M of the slot's frame, 0 above
-    // (Channel.process_channel, :604-645)
-    if (t < 32) {
-      const int l = t;
-      int lim;
-      if (mode == 2) lim = (l < first_slot) ? (fp->kx_prev + fp->M_prev) : (fp->kx + fp->M);
-      else lim = 32;
-      const float scale = 1.f / 64.f;
-      auto Xr = [&](int k) -> float { return k < lim ? XS(l + kSbrHfAdj, k, 0) : 0.f; };
-      auto Xi = [&](int k) -> float { return k < lim ? XS(l + kSbrHfAdj, k, 1) : 0.f; };
-      float in_r[32], in_i[32], o1r[32], o1i[32], o2r[32], o2i[32];
-      in_i[31] = scale * Xr(1);
-      in_r[0] = scale * Xr(0);
+    // X[l][k] = Xsbr[l + tHFAdj][k] below kx + M of the slot's frame, 0 above (Channel.process_channel, :604-645)
+    auto x_limit = [&](int l) -> int {
+      if (mode == 2) return (l < first_slot) ? (fp->kx_prev + fp->M_prev) : (fp->kx + fp->M);
+      return 32;
+    };
+    // ---- 64-band QMF synthesis of one channel (sbr/SynthesisFilterbank64.java:9-79): the two DCT-IVs of slot l by thread l,
+    // then all 64 threads window.  src == nullptr: read Xsbr with the band limit; else a ready [32][kXsStride] matrix.
+    auto synthesis = [&](const float* src, int och, bool dup) {
+      if (t < 32) {
+        const int l = t;
+        const int lim = src ? 64 : x_limit(l);
+        const float* row = src ? src + l * kXsStride : xs + (l + kSbrHfAdj) * kXsStride;
+        const float scale = 1.f / 64.f;
+        auto Xr = [&](int k) -> float { return k < lim ? row[2 * k] : 0.f; };
+        auto Xi = [&](int k) -> float { return k < lim ? row[2 * k + 1] : 0.f; };
+        float in_r[32], in_i[32], o1r[32], o1i[32], o2r[32], o2i[32];
+        in_i[31] = scale * Xr(1);
+        in_r[0] = scale * Xr(0);
 #pragma unroll
-      for (int k = 1; k < 31; k++) { in_i[31 - k] = scale * Xr(2 * k + 1); in_r[k] = scale * Xr(2 * k); }
-      in_i[0] = scale * Xr(63);
-      in_r[31] = scale * Xr(62);
-      sbr_dct4_kernel(in_r, in_i, o1r, o1i);
-      in_i[31] = scale * Xi(63 - 1);
-      in_r[0] = scale * Xi(63 - 0);
+        for (int k = 1; k < 31; k++) { in_i[31 - k] = scale * Xr(2 * k + 1); in_r[k] = scale * Xr(2 * k); }
+        in_i[0] = scale * Xr(63);
+        in_r[31] = scale * Xr(62);
+        sbr_dct4_kernel(in_r, in_i, o1r, o1i);
+        in_i[31] = scale * Xi(63 - 1);
+        in_r[0] = scale * Xi(63 - 0);
 #pragma unroll
-      for (int k = 1; k < 31; k++) { in_i[31 - k] = scale * Xi(63 - (2 * k + 1)); in_r[k] = scale * Xi(63 - (2 * k)); }
-      in_i[0] = scale * Xi(63 - 63);
-      in_r[31] = scale * Xi(63 - 62);
-      sbr_dct4_kernel(in_r, in_i, o2r, o2i);
-      float* v = &VB(9 + l, 0);
+        for (int k = 1; k < 31; k++) { in_i[31 - k] = scale * Xi(63 - (2 * k + 1)); in_r[k] = scale * Xi(63 - (2 * k)); }
+        in_i[0] = scale * Xi(63 - 63);
+        in_r[31] = scale * Xi(63 - 62);
+        sbr_dct4_kernel(in_r, in_i, o2r, o2i);
+        float* v = &VB(9 + l, 0);
 #pragma unroll
-      for (int n = 0; n < 32; n++) {
-        v[2 * n] = o2r[n] - o1r[n];
-        v[127 - 2 * n] = o2r[n] + o1r[n];
-        v[2 * n + 1] = o2i[31 - n] + o1i[31 - n];
-        v[127 - (2 * n + 1)] = o2i[31 - n] - o1i[31 - n];
+        for (int n = 0; n < 32; n++) {
+          v[2 * n] = o2r[n] - o1r[n];
+          v[127 - 2 * n] = o2r[n] + o1r[n];
+          v[2 * n + 1] = o2i[31 - n] + o1i[31 - n];
+          v[127 - (2 * n + 1)] = o2i[31 - n] - o1i[31 - n];
+        }
       }
-    }
-    __syncthreads();
-    // window + output: thread k, all 32 slots
-    for (int l = 0; l < 32; ++l) {
-      const int cur = 9 + l;
-      float o = (VB(cur, t) * qc[0]);
+      __syncthreads();
+      // window + output: thread k, all 32 slots
+      for (int l = 0; l < 32; ++l) {
+        const int cur = 9 + l;
+        float o = (VB(cur, t) * qc[0]);
 #pragma unroll
-      for (int j = 1; j < 10; ++j) o = o + (VB(cur - j, t + 64 * (j & 1)) * qc[j]);
-      put_sample(64 * l + t, o);
+        for (int j = 1; j < 10; ++j) o = o + (VB(cur - j, t + 64 * (j & 1)) * qc[j]);
+        put_sample_to(64 * l + t, o, och, dup);
+      }
+      __syncthreads();
+    };
+
+    if (!use_ps) {
+      synthesis(nullptr, run.out_ch, run.dup != 0);
+    } else if (WITH_PS) {
+      // ================= parametric stereo (ps/PSImpl.java) =================
+      const int num_env = pp->num_env;
+      // X_left: the band-limited copy of Xsbr (SBR1.processPS); hybrid analysis input: QMF bands 0..2 of slots 6..37
+      for (int l = 0; l < 32; ++l) {
+        const int lim = x_limit(l);
+        XL(l, t, 0) = t < lim ? XS(l + kSbrHfAdj, t, 0) : 0.f;
+        XL(l, t, 1) = t < lim ? XS(l + kSbrHfAdj, t, 1) : 0.f;
+      }
+      for (int i = t; i < 3 * 44; i += kK4Threads) {
+        const int band = i / 44, j = i % 44;
+        // work[0..11] = history, work[12 + n] = X[n + 6][band]: rows 6..31 come from X_left, rows 32..37 straight
+        // from Xsbr (:108-113) -- for bands 0..2 both are the unmodified analysis output
+        hwork[(band * 44 + j) * 2] = j < 12 ? pst->hyb_buffer[band][j][0] : XS(j - 12 + 6 + kSbrHfAdj, band, 0);
+        hwork[(band * 44 + j) * 2 + 1] = j < 12 ? pst->hyb_buffer[band][j][1] : XS(j - 12 + 6 + kSbrHfAdj, band, 1);
+      }
+      __syncthreads();
+      if (t < 36) { const int band = t / 12, j = t % 12; pst->hyb_buffer[band][j][0] = hwork[(band * 44 + 32 + j) * 2]; pst->hyb_buffer[band][j][1] = hwork[(band * 44 + 32 + j) * 2 + 1]; }
+      // ---- hybrid analysis (ps/Filterbank.java:18-68): thread n
+      if (t < 32) {
+        const int i = t;
+        {
+          // Filter8 (ps/Filter8.java:53-122) on QMF band 0
+          const float* b = hwork;
+          float f[7];
+#pragma unroll
+          for (int z = 0; z < 7; ++z) f[z] = __ldg(T.ps_p8 + z);
+#define BR(k) b[((k) + i) * 2]
+#define BI(k) b[((k) + i) * 2 + 1]
+          auto dct3 = [](float (&y)[4], const float (&x)[4]) {   // DCT3_4_unscaled (:124-138)
+            const float f0 = (x[2] * 0.7071067811865476f);
+            const float f1 = x[0] - f0;
+            const float f2 = x[0] + f0;
+            const float f3 = x[1] + x[3];
+            const float f4 = (x[1] * 1.3065629648763766f);
+            const float f5 = (f3 * (-0.9238795325112866f));
+            const float f6 = (x[3] * (-0.5411961001461967f));
+            const float f7 = f4 + f5;
+            const float f8 = f6 - f5;
+            y[3] = f2 - f8; y[0] = f2 + f8; y[2] = f1 - f7; y[1] = f1 + f7;
+          };
+          float re1[4], im1[4], re2[4], im2[4], x[4], y[4];
+          re1[0] = (f[6] * BR(6));
+          re1[1] = (f[5] * (BR(5) + BR(7)));
+          re1[2] = -(f[0] * (BR(0) + BR(12))) + (f[4] * (BR(4) + BR(8)));
+          re1[3] = -(f[1] * (BR(1) + BR(11))) + (f[3] * (BR(3) + BR(9)));
+          im1[0] = (f[5] * (BI(7) - BI(5)));
+          im1[1] = (f[0] * (BI(12) - BI(0))) + (f[4] * (BI(8) - BI(4)));
+          im1[2] = (f[1] * (BI(11) - BI(1))) + (f[3] * (BI(9) - BI(3)));
+          im1[3] = (f[2] * (BI(10) - BI(2)));
+#pragma unroll
+          for (int n = 0; n < 4; n++) x[n] = re1[n] - im1[3 - n];
+          dct3(y, x);
+          HYL(i, 7, 0) = y[0]; HYL(i, 5, 0) = y[2]; HYL(i, 3, 0) = y[3]; HYL(i, 1, 0) = y[1];
+#pragma unroll
+          for (int n = 0; n < 4; n++) x[n] = re1[n] + im1[3 - n];
+          dct3(y, x);
+          HYL(i, 6, 0) = y[1]; HYL(i, 4, 0) = y[3]; HYL(i, 2, 0) = y[2]; HYL(i, 0, 0) = y[0];
+          im2[0] = (f[6] * BI(6));
+          im2[1] = (f[5] * (BI(5) + BI(7)));
+          im2[2] = -(f[0] * (BI(0) + BI(12))) + (f[4] * (BI(4) + BI(8)));
+          im2[3] = -(f[1] * (BI(1) + BI(11))) + (f[3] * (BI(3) + BI(9)));
+          re2[0] = (f[5] * (BR(7) - BR(5)));
+          re2[1] = (f[0] * (BR(12) - BR(0))) + (f[4] * (BR(8) - BR(4)));
+          re2[2] = (f[1] * (BR(11) - BR(1))) + (f[3] * (BR(9) - BR(3)));
+          re2[3] = (f[2] * (BR(10) - BR(2)));
+#pragma unroll
+          for (int n = 0; n < 4; n++) x[n] = im2[n] + re2[3 - n];
+          dct3(y, x);
+          HYL(i, 7, 1) = y[0]; HYL(i, 5, 1) = y[2]; HYL(i, 3, 1) = y[3]; HYL(i, 1, 1) = y[1];
+#pragma unroll
+          for (int n = 0; n < 4; n++) x[n] = im2[n] - re2[3 - n];
+          dct3(y, x);
+          HYL(i, 6, 1) = y[1]; HYL(i, 4, 1) = y[3]; HYL(i, 2, 1) = y[2]; HYL(i, 0, 1) = y[0];
+#undef BR
+#undef BI
+        }
+        for (int band = 1; band < 3; ++band) {
+          // Filter2 (ps/Filter2.java:40-68) on QMF bands 1 and 2
+          const float* b = hwork + band * 88;
+          float f[7];
+#pragma unroll
+          for (int z = 0; z < 7; ++z) f[z] = __ldg(T.ps_p2 + z);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const float r0 = (f[0] * (b[(0 + i) * 2 + c] + b[(12 + i) * 2 + c]));
+            const float r1 = (f[1] * (b[(1 + i) * 2 + c] + b[(11 + i) * 2 + c]));
+            const float r2 = (f[2] * (b[(2 + i) * 2 + c] + b[(10 + i) * 2 + c]));
+            const float r3 = (f[3] * (b[(3 + i) * 2 + c] + b[(9 + i) * 2 + c]));
+            const float r4 = (f[4] * (b[(4 + i) * 2 + c] + b[(8 + i) * 2 + c]));
+            const float r5 = (f[5] * (b[(5 + i) * 2 + c] + b[(7 + i) * 2 + c]));
+            const float r6 = (f[6] * b[(6 + i) * 2 + c]);
+            HYL(i, 8 + 2 * (band - 1), c) = r0 + r1 + r2 + r3 + r4 + r5 + r6;
+            HYL(i, 9 + 2 * (band - 1), c) = r0 - r1 + r2 - r3 + r4 - r5 + r6;
+          }
+        }
+        // group hybrid channels (:56-66)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          HYL(i, 3, c) += HYL(i, 4, c);
+          HYL(i, 4, c) = 0;
+          HYL(i, 2, c) += HYL(i, 5, c);
+          HYL(i, 5, c) = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { HYR(i, k, 0) = 0.f; HYR(i, k, 1) = 0.f; }
+        // ---- energy per parameter band (ps_decorrelate, :213-234): groups in order, sub-bands in order
+        float* P = pg + i * 20;
+#pragma unroll
+        for (int bk = 0; bk < 20; ++bk) P[bk] = 0.f;
+        for (int gr = 0; gr < 22; ++gr) {
+          const int bk = ps_bk(gr), lo = ps_group_border(gr), hi = gr < 10 ? lo + 1 : ps_group_border(gr + 1);
+          for (int sb = lo; sb < hi; ++sb) {
+            const float re = gr < 10 ? HYL(i, sb, 0) : XL(i, sb, 0);
+            const float im = gr < 10 ? HYL(i, sb, 1) : XL(i, sb, 1);
+            P[bk] += (re * re) + (im * im);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- transient reduction ratio (:236-264): thread bk, sequential in time
+      if (t < 20) {
+        float peak = pst->P_PeakDecayNrg[t], pprev = pst->P_prev[t], smooth_prev = pst->P_SmoothPeakDecayDiffNrg_prev[t];
+        for (int n = 0; n < 32; ++n) {
+          const float Pn = pg[n * 20 + t];
+          const float gamma = 1.5f;
+          peak = (peak * 0.76592833836465f);
+          if (peak < Pn) peak = Pn;
+          float sm = smooth_prev;
+          sm += ((peak - Pn - smooth_prev) * 0.25f);
+          smooth_prev = sm;
+          float nrg = pprev;
+          nrg += ((Pn - pprev) * 0.25f);
+          pprev = nrg;
+          pg[n * 20 + t] = ((sm * gamma) <= nrg) ? 1.0f : (nrg / (sm * gamma));
+        }
+        pst->P_PeakDecayNrg[t] = peak; pst->P_prev[t] = pprev; pst->P_SmoothPeakDecayDiffNrg_prev[t] = smooth_prev;
+      }
+      __syncthreads();
+      // ---- decorrelation (:266-396) + mixing (ps_mix_phase, :406-681), one band per thread: first the 10 hybrid
+      // sub-bands (threads 0..9), then QMF bands 3..63 (threads 3..63)
+      const int saved_delay = pst->saved_delay;
+      const int ser0 = pst->delay_buf_index_ser[0], ser1 = pst->delay_buf_index_ser[1], ser2 = pst->delay_buf_index_ser[2];
+      int td_end = saved_delay, s0_end = ser0, s1_end = ser1, s2_end = ser2;
+      const bool fine = pp->iid_mode >= 3;
+      const int num_steps = fine ? 15 : 7;
+      const float* sf_iid = T.ps_sf_iid[fine];
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const bool hyb = pass == 0;
+        const bool mine = hyb ? (t < 10) : (t >= 3);
+        if (mine) {
+          int gr, sb;
+          if (hyb) { gr = t; sb = ps_group_border(t); }
+          else { sb = t; gr = 10; while (ps_group_border(gr + 1) <= sb) ++gr; }
+          const int bk = ps_bk(gr);
+          const bool delay_band = !hyb && sb > 22;
+          float g_DecaySlope;
+          if (hyb || sb <= 3) g_DecaySlope = 1.0f;
+          else {
+            const int decay = 3 - sb;
+            g_DecaySlope = (decay <= -20) ? 0.f : 1.0f + 0.05f * (float)decay;
+          }
+          const float gf0 = g_DecaySlope * __ldg(T.ps_filter_a), gf1 = g_DecaySlope * __ldg(T.ps_filter_a + 1), gf2 = g_DecaySlope * __ldg(T.ps_filter_a + 2);
+          const float phi0 = __ldg((hyb ? T.ps_phi_sub : T.ps_phi_qmf) + 2 * sb), phi1 = __ldg((hyb ? T.ps_phi_sub : T.ps_phi_qmf) + 2 * sb + 1);
+          const float* qf = (hyb ? T.ps_q_sub : T.ps_q_qmf) + sb * 6;
+          const float q00 = __ldg(qf), q01 = __ldg(qf + 1), q10 = __ldg(qf + 2), q11 = __ldg(qf + 3), q20 = __ldg(qf + 4), q21 = __ldg(qf + 5);
+          float* d_in = hyb ? &pst->delay_sub[sb][0][0] : &pst->delay_qmf[sb][0][0];          // [slot][2]
+          float* d_ser = hyb ? &pst->delay_sub_ser[sb][0][0][0] : &pst->delay_qmf_ser[sb][0][0][0];   // [link][5][2]
+          int td = saved_delay, s0 = ser0, s1 = ser1, s2 = ser2;
+          int di = delay_band ? pst->delay_buf_index_delay[sb] : 0;
+          const int dD = sb < 35 ? 14 : 1;
+          // mixing state of the band's group
+          float H11 = pst->h_prev[gr][0], H12 = pst->h_prev[gr][1], H21 = pst->h_prev[gr][2], H22 = pst->h_prev[gr][3];
+          float hp11 = H11, hp12 = H12, hp21 = H21, hp22 = H22;
+          float dH11 = 0, dH12 = 0, dH21 = 0, dH22 = 0;
+          int env = -1, env_end = 0;
+          for (int n = 0; n < 32; ++n) {
+            if (n == env_end) {
+              // next envelope: target H from the IID / ICC indices (:424-478), linear interpolation over its length
+              do { ++env; env_end = pp->border[env + 1]; } while (env + 1 < num_env && env_end <= n);
+              int iid_index = pp->iid[env][bk];
+              const int iid_sign = iid_index < 0 ? -1 : 1;
+              iid_index = min(abs(iid_index), num_steps);
+              const int icc_index = min(max((int)pp->icc[env][bk], 0), 7);
+              float h11, h12, h21, h22;
+              if (pp->icc_mode < 3) {
+                const float c_1 = __ldg(sf_iid + num_steps + iid_index), c_2 = __ldg(sf_iid + num_steps - iid_index);
+                const float cosa = __ldg(T.ps_cos_alphas + icc_index), sina = __ldg(T.ps_sin_alphas + icc_index);
+                const float cosb = __ldg(T.ps_cos_betas[fine] + iid_index * 8 + icc_index);
+                const float sinb = __ldg(T.ps_sin_betas[fine] + iid_index * 8 + icc_index) * (float)iid_sign;
+                const float ab1 = (cosb * cosa), ab2 = (sinb * sina), ab3 = (sinb * cosa), ab4 = (cosb * sina);
+                h11 = (c_2 * (ab1 - ab2));
+                h12 = (c_1 * (ab1 + ab2));
+                h21 = (c_2 * (ab3 + ab4));
+                h22 = (c_1 * (ab3 - ab4));
+              } else {
+                const float cosa = __ldg(T.ps_sincos_alphas_b[fine] + (num_steps + iid_index) * 8 + icc_index);
+                const float sina = __ldg(T.ps_sincos_alphas_b[fine] + (2 * num_steps - (num_steps + iid_index)) * 8 + icc_index);
+                const float cosg = __ldg(T.ps_cos_gammas[fine] + iid_index * 8 + icc_index);
+                const float sing = __ldg(T.ps_sin_gammas[fine] + iid_index * 8 + icc_index);
+                h11 = (1.4142135623731f * (cosa * cosg));
+                h12 = (1.4142135623731f * (sina * cosg));
+                h21 = (1.4142135623731f * (-cosa * sing));
+                h22 = (1.4142135623731f * (sina * sing));
+              }
+              const float L = (float)(pp->border[env + 1] - pp->border[env]);
+              dH11 = (h11 - hp11) / L; dH12 = (h12 - hp12) / L; dH21 = (h21 - hp21) / L; dH22 = (h22 - hp22) / L;
+              H11 = hp11; H12 = hp12; H21 = hp21; H22 = hp22;
+              hp11 = h11; hp12 = h12; hp21 = h21; hp22 = h22;
+            }
+            // -- decorrelate
+            const float re = hyb ? HYL(n, sb, 0) : XL(n, sb, 0);
+            const float im = hyb ? HYL(n, sb, 1) : XL(n, sb, 1);
+            float r0Re, r0Im;
+            if (delay_band) {
+              float* d = d_in + 2 * di;
+              r0Re = d[0]; r0Im = d[1];
+              d[0] = re; d[1] = im;
+            } else {
+              float* d = d_in + 2 * td;
+              float tmp0Re = d[0], tmp0Im = d[1];
+              d[0] = re; d[1] = im;
+              r0Re = (tmp0Re * phi0) + (tmp0Im * phi1);
+              r0Im = (tmp0Im * phi0) - (tmp0Re * phi1);
+#pragma unroll
+              for (int m = 0; m < 3; ++m) {
+                const float qa = m == 0 ? q00 : (m == 1 ? q10 : q20), qb = m == 0 ? q01 : (m == 1 ? q11 : q21);
+                const float gf = m == 0 ? gf0 : (m == 1 ? gf1 : gf2);
+                float* dl = d_ser + (m * 5 + (m == 0 ? s0 : (m == 1 ? s1 : s2))) * 2;
+                tmp0Re = dl[0]; tmp0Im = dl[1];
+                float tmpRe = (tmp0Re * qa) + (tmp0Im * qb);
+                float tmpIm = (tmp0Im * qa) - (tmp0Re * qb);
+                tmpRe -= gf * r0Re;
+                tmpIm -= gf * r0Im;
+                dl[0] = r0Re + (gf * tmpRe);
+                dl[1] = r0Im + (gf * tmpIm);
+                r0Re = tmpRe;
+                r0Im = tmpIm;
+              }
+            }
+            const float G = pg[n * 20 + bk];
+            const float rRe = (G * r0Re), rIm = (G * r0Im);
+            if (++td >= 2) td = 0;
+            if (delay_band) { if (++di >= dD) di = 0; }
+            if (++s0 >= 3) s0 = 0;
+            if (++s1 >= 4) s1 = 0;
+            if (++s2 >= 5) s2 = 0;
+            // -- mix
+            H11 += dH11; H12 += dH12; H21 += dH21; H22 += dH22;
+            const float lRe = (H11 * re) + (H21 * rRe), lIm = (H11 * im) + (H21 * rIm);
+            const float oRe = (H12 * re) + (H22 * rRe), oIm = (H12 * im) + (H22 * rIm);
+            if (hyb) { HYL(n, sb, 0) = lRe; HYL(n, sb, 1) = lIm; HYR(n, sb, 0) = oRe; HYR(n, sb, 1) = oIm; }
+            else { XL(n, sb, 0) = lRe; XL(n, sb, 1) = lIm; XR(n, sb, 0) = oRe; XR(n, sb, 1) = oIm; }
+          }
+          if (delay_band) pst->delay_buf_index_delay[sb] = di;
+          if (sb == ps_group_border(gr)) { pst->h_prev[gr][0] = hp11; pst->h_prev[gr][1] = hp12; pst->h_prev[gr][2] = hp21; pst->h_prev[gr][3] = hp22; }
+          td_end = td; s0_end = s0; s1_end = s1; s2_end = s2;
+        }
+      }
+      __syncthreads();
+      if (t == 3) { pst->saved_delay = td_end; pst->delay_buf_index_ser[0] = s0_end; pst->delay_buf_index_ser[1] = s1_end; pst->delay_buf_index_ser[2] = s2_end; }
+      // ---- hybrid synthesis (ps/Filterbank.java:70-86) for both channels: thread n
+      if (t < 32) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float a0 = 0, b0 = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { a0 += HYL(t, k, c); b0 += HYR(t, k, c); }
+          XL(t, 0, c) = a0; XR(t, 0, c) = b0;
+          float a1 = 0, b1 = 0;
+          a1 += HYL(t, 8, c); a1 += HYL(t, 9, c); b1 += HYR(t, 8, c); b1 += HYR(t, 9, c);
+          XL(t, 1, c) = a1; XR(t, 1, c) = b1;
+          float a2 = 0, b2 = 0;
+          a2 += HYL(t, 10, c); a2 += HYL(t, 11, c); b2 += HYR(t, 10, c); b2 += HYR(t, 11, c);
+          XL(t, 2, c) = a2; XR(t, 2, c) = b2;
+        }
+      }
+      __syncthreads();
+      // ---- two synthesis banks (SBR1.processPS, :121-122): left with the channel's own history, right with its own
+      synthesis(xl, run.out_ch, false);
+      float vkl[18];
+#pragma unroll
+      for (int s2 = 0; s2 < 9; ++s2) { vkl[2 * s2] = VB(32 + s2, t); vkl[2 * s2 + 1] = VB(32 + s2, t + 64); }
+      __syncthreads();
+#pragma unroll
+      for (int s2 = 0; s2 < 9; ++s2) { VB(s2, t) = vhr[s2 * kVbStride + t]; VB(s2, t + 64) = vhr[s2 * kVbStride + t + 64]; }
+      __syncthreads();
+      synthesis(xr, run.out_ch + 1, false);
+#pragma unroll
+      for (int s2 = 0; s2 < 9; ++s2) { vhr[s2 * kVbStride + t] = VB(32 + s2, t); vhr[s2 * kVbStride + t + 64] = VB(32 + s2, t + 64); }
+      __syncthreads();
+      // put the left channel's newest nine vectors where the carry step below expects them
+#pragma unroll
+      for (int s2 = 0; s2 < 9; ++s2) { VB(32 + s2, t) = vkl[2 * s2]; VB(32 + s2, t + 64) = vkl[2 * s2 + 1]; }
+      __syncthreads();
     }
-    __syncthreads();
     // ---- carry: analysis history, the last 8 Xsbr slots (sbr_save_matrix), the last 9 v-vectors
     for (int i = t; i < 288; i += kK4Threads) INB(i) = INB(1024 + i);   // disjoint ranges
     {
@@ -630,6 +978,12 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
   for (int n = 0; n < 5; ++n) { st->G_temp_prev[n][t] = Gt[n]; st->Q_temp_prev[n][t] = Qt[n]; }
   if (t < 8) { st->bwArray_prev[t] = bw_prev; st->bs_invf_mode_prev[t] = (uint8_t)invf_prev; }
   if (t == 0) { st->GQ_ringbuf_index = ring_index; st->index_noise_prev = index_noise_prev; st->psi_is_prev = psi_is_prev; }
+  if (WITH_PS)
+    for (int i = t; i < 9 * 128; i += kK4Threads) pst->syn_v_right[i / 128][i % 128] = vhr[(8 - i / 128) * kVbStride + (i % 128)];
+#undef XL
+#undef XR
+#undef HYL
+#undef HYR
 }
 
 }  // namespace jaadb

@@ -46,6 +46,31 @@ struct SbrChanParse {
   uint8_t pad[3];
 };
 
+// Parametric stereo, parse side (ps/EnvData.java + Envelope.java for IID and ICC; ps/PSImpl.java:21-36)
+struct PsParamDev {
+  int8_t mode;            // -1: disabled (null)
+  uint8_t dt[5];
+  int8_t first[34];       // indices of the last envelope of the previous frame
+  int8_t index[5][34];
+};
+struct PsParseDev {
+  PsParamDev iid, icc;
+  uint8_t opened;         // SBR1.ps != null
+  uint8_t var_borders, num_env, data_available, header_read, ext_enabled;
+  uint8_t border_position[6];
+};
+
+// One frame of PS parameters as K4 consumes them (after PSImpl.ps_data_decode).
+struct __align__(16) PsFrameDev {
+  uint8_t use_ps;         // SBR1.isPSUsed() for this frame
+  uint8_t num_env;
+  uint8_t border[6];
+  int8_t iid_mode, icc_mode;   // as EnvData.mode() resolves them (IID null -> 0, ICC null -> 1)
+  int8_t iid[5][20], icc[5][20];
+  uint8_t pad[14];
+};
+static_assert(sizeof(PsFrameDev) == 224, "PsFrameDev layout");
+
 struct SbrElemDev {
   SbrHeaderDev hdr, hdr_saved;
   uint8_t opened;        // an SBR payload has been seen (ChannelElement.sbr != null)
@@ -63,7 +88,10 @@ struct SbrElemDev {
   int8_t patchStartSubband[64];
   uint8_t pad[3];
   SbrChanParse ch[2];
+  PsParseDev ps;          // mono element of an SBR+PS stream
+  uint8_t pad2[4];
 };
+static_assert(sizeof(SbrElemDev) % 4 == 0, "SbrElemDev is copied word-wise");
 
 // One channel of one SBR element frame, as K4 consumes it.
 struct __align__(16) SbrFrameDev {
@@ -87,6 +115,21 @@ struct __align__(16) SbrFrameDev {
   uint8_t pad[16];
 };
 static_assert(sizeof(SbrFrameDev) == 1872, "SbrFrameDev layout (mirrored by jaadec_b200/engine.py SBR_FRAME_DTYPE)");
+
+// Process-side persistent state of the parametric-stereo tool of one stream (ps/PSImpl.java:39-62, ps/Filterbank.java).
+// Delay lines are stored per band so that the thread that owns a band touches one contiguous piece.
+struct __align__(16) PsChanDev {
+  float hyb_buffer[3][12][2];        // hybrid analysis history of QMF bands 0..2
+  float delay_qmf[64][14][2];        // [band][slot]: 14-slot delay (bands > 22) or the 2-slot all-pass input delay
+  float delay_qmf_ser[64][3][5][2];  // [band][link][slot]
+  float delay_sub[12][2][2];         // hybrid sub-bands
+  float delay_sub_ser[12][3][5][2];
+  float P_PeakDecayNrg[20], P_prev[20], P_SmoothPeakDecayDiffNrg_prev[20];
+  float h_prev[22][4];               // h11, h12, h21, h22 (real parts) per group
+  float syn_v_right[9][128];         // right channel: the 9 most recent synthesis v-vectors ([0] = newest)
+  int32_t saved_delay, delay_buf_index_ser[3];
+  int32_t delay_buf_index_delay[64];
+};
 
 // Process-side persistent state of one SBR channel.
 struct __align__(16) SbrChanDev {
@@ -118,6 +161,23 @@ struct SbrTablesDev {
   const float* w_real;              // [16]
   const float* w_imag;              // [16]
   const float* noise_table;         // [512][2]
+  // parametric stereo
+  const int16_t* ps_huff[6];        // f_iid_def, t_iid_def, f_iid_fine, t_iid_fine, f_icc, t_icc
+  const float* ps_filter_a;         // [3]
+  const float* ps_phi_qmf;          // [64][2]
+  const float* ps_phi_sub;          // [12][2]
+  const float* ps_q_qmf;            // [64][3][2]
+  const float* ps_q_sub;            // [12][3][2]
+  const float* ps_cos_alphas;       // [8]
+  const float* ps_sin_alphas;
+  const float* ps_cos_betas[2];     // normal [8][8], fine [16][8]
+  const float* ps_sin_betas[2];
+  const float* ps_cos_gammas[2];    // as IIDTables names them (the reference swaps sin/cos here, IIDMode.java:16-28)
+  const float* ps_sin_gammas[2];
+  const float* ps_sincos_alphas_b[2];  // [15][8], [31][8]
+  const float* ps_sf_iid[2];        // [15], [31]
+  const float* ps_p8;               // [7] Filter8 prototype
+  const float* ps_p2;               // [7] Filter2 prototype
 };
 
 // One SBR element stream inside a batch: K3 walks `count` frames starting at run_frames[first].
@@ -129,6 +189,9 @@ struct SbrRunDev {
   uint8_t stereo;          // CPE
   uint8_t sr_index;        // output sampling-frequency index (FBT tables)
   uint8_t first_ch;        // channel slot of the element's first channel
+  uint8_t ps;              // the element may carry parametric stereo (mono SBR+PS stream)
+  uint8_t pad[3];
+  uint32_t ps_base;        // index of this run's first PsFrameDev
 };
 
 }  // namespace jaadb

@@ -18,6 +18,8 @@ CASES = [
     ("c3_stereo_sbr_jaad_coupling", gen.config(3, n_frames=45, sbr_quirk=True), 6),
     ("mono_sbr", gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=45, target_bytes=171, sbr_mode=1), 4),
     ("stereo_sbr_32k", gen.GenConfig(sf_index=8, chan_cfg=2, n_frames=30, target_bytes=300, sbr_mode=1), 3),
+    # HE-AAC v2: mono core + SBR + parametric stereo (hybrid filterbank, decorrelator, mixing, two synthesis banks)
+    ("c4_mono_sbr_ps", gen.config(4, n_frames=45), 8),
 ]
 
 
@@ -26,7 +28,7 @@ def test_sbr_float_pcm_bit_exact(label, cfg, n_streams):
     wl = Workload(cfg, n_streams, base_seed=gen.seed_for(3, 40), with_truth=False)
     decs = wl.oracle_decoders()
     eng = Engine(max_streams=16, pcm_format=PCM_F32_PLANAR)
-    ids = [eng.open_adts(*wl.hdr, expect_sbr=1) for _ in range(n_streams)]
+    ids = [eng.open_adts(*wl.hdr, expect_sbr=cfg.sbr_mode) for _ in range(n_streams)]
     info = eng.stream_info(ids[0])
     assert (info.channels, info.sample_length) == (2, 2048)
     frames, index = wl.frame_table(ids)

@@ -9,12 +9,13 @@ from helpers import Workload
 from jaadec_b200 import Engine, PCM_F32_PLANAR
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-mono = len(sys.argv) > 2 and sys.argv[2] == "mono"
-cfg = gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=24, target_bytes=171, sbr_mode=1) if mono else gen.config(3, n_frames=24, sbr_quirk=True)
+mono = len(sys.argv) > 2 and sys.argv[2] in ("mono", "ps")
+ps = len(sys.argv) > 2 and sys.argv[2] == "ps"
+cfg = gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=24, target_bytes=171, sbr_mode=2 if ps else 1) if mono else gen.config(3, n_frames=24, sbr_quirk=True)
 wl = Workload(cfg, n, base_seed=int(sys.argv[3]) if len(sys.argv) > 3 else 70000, with_truth=False)
 decs = wl.oracle_decoders()
 eng = Engine(max_streams=n, pcm_format=PCM_F32_PLANAR)
-ids = [eng.open_adts(*wl.hdr, expect_sbr=1) for _ in range(n)]
+ids = [eng.open_adts(*wl.hdr, expect_sbr=cfg.sbr_mode) for _ in range(n)]
 frames, index = wl.frame_table(ids)
 pcm, res = eng.decode(wl.blob, frames)
 per = 2 * 2048 * 4
