@@ -30,9 +30,11 @@ SF_FREQ = [96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000,
 # config 3 (HE-AAC v1 stereo): + 2048-sample stereo s16 out + this engine's SBR state read+write per frame
 # (2 x SbrChanDev 12480 B + SbrElemDev 3468 B, jaadec_b200/csrc/sbr_types.cuh)
 ALGO_BYTES = {1: lambda avg: avg + 4096 + 16384, 2: lambda avg: avg + 4096 + 16384, 5: lambda avg: avg + 12288 + 49152,
-              3: lambda avg: avg + 8192 + 16384 + 2 * (2 * 12480 + 3468)}
-OUT_SAMPLES = {1: 1024, 2: 1024, 5: 1024, 3: 2048}   # per frame and channel
-OUT_RATE_SHIFT = {1: 0, 2: 0, 5: 0, 3: 3}             # SBR doubles the rate: output sf index = core index - 3
+              3: lambda avg: avg + 8192 + 16384 + 2 * (2 * 12480 + 3904),
+              # config 4 (HE-AAC v2): mono core overlap + one SbrChanDev + SbrElemDev + PsChanDev (22 KB), read + write
+              4: lambda avg: avg + 8192 + 8192 + 2 * (12480 + 3904 + 22240)}
+OUT_SAMPLES = {1: 1024, 2: 1024, 5: 1024, 3: 2048, 4: 2048}   # per frame and channel
+OUT_RATE_SHIFT = {1: 0, 2: 0, 5: 0, 3: 3, 4: 3}               # SBR doubles the rate: output sf index = core index - 3
 
 
 def read_peaks():
@@ -156,6 +158,7 @@ def run_reference(args, rank, world):
 def workload_config(args, cfg, sizes):
     names = {1: "AAC-LC 44.1 kHz stereo ADTS, long windows only", 2: "AAC-LC 48 kHz stereo, mixed ONLY_LONG/EIGHT_SHORT, M/S, IS, TNS side info",
              3: "HE-AAC v1 (SBR) 24 kHz core -> 48 kHz stereo: 32-band QMF analysis, HF generation/adjustment, 64-band synthesis",
+             4: "HE-AAC v2 (SBR+PS) mono 24 kHz core -> 48 kHz stereo: PS hybrid filterbank + decorrelation + mixing",
              5: "AAC-LC 5.1 48 kHz raw frames (MP4 samples)"}
     return {"workload": "BASELINE config %d: %s" % (args.config, names.get(args.config, "?")), "streams_per_gpu": args.streams,
             "frames_per_stream": args.frames, "avg_frame_bytes": float(sizes.mean()), "pcm": "s16le interleaved",
@@ -168,7 +171,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--streams", type=int, default=4096)
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--ref-streams", type=int, default=0)
@@ -178,7 +181,9 @@ def main():
     if args.config == 1 and args.streams == 4096:
         args.streams = 1
     if not args.frames:
-        args.frames = {1: 431, 2: 469, 3: 235, 5: 469}[args.config]
+        args.frames = {1: 431, 2: 469, 3: 235, 4: 235, 5: 469}[args.config]
+    if args.config == 4 and args.streams == 4096:
+        args.streams = 8192
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

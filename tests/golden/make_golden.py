@@ -41,6 +41,8 @@ def cases():
         # HE-AAC v1: 24 kHz core + SBR, header at frame 0 and (possibly changed) at frame 20
         "sbr_c3_stereo": (gen.config(3, n_frames=24), 2, None),
         "sbr_mono": (gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=22, target_bytes=171, sbr_mode=1), 2, None),
+        # HE-AAC v2: mono core + SBR + parametric stereo
+        "ps_c4_mono": (gen.config(4, n_frames=24), 2, None),
     }
 
 
@@ -65,6 +67,8 @@ def build_case(name, cfg, n_streams, asc):
     extra = {}
     if cfg.sbr_mode:
         extra["truth_sbr"] = np.stack([s.truth["sbr"] for s in streams])
+    if cfg.sbr_mode > 1:
+        extra["truth_ps"] = np.stack([s.truth["ps"] for s in streams])
     out = dict(
         sbr=np.array([cfg.sbr_mode], np.int32),
         blob=blob,

@@ -67,6 +67,33 @@ def test_sbr_integer_stage_matches_generator_truth(mono):
     assert resets >= 1   # at least one mid-stream header change made the decoder rebuild its tables
 
 
+def test_ps_integer_stage_matches_generator_truth():
+    """HE-AAC v2: the parametric-stereo parameters the oracle reconstructs (envelope count and borders, IID / ICC indices
+    after delta decoding, clipping and stride expansion) against the generator's own index arithmetic."""
+    modes = set()
+    n_checked = 0
+    for seed in range(24):
+        cfg = gen.config(4, n_frames=40)
+        st = gen.generate(cfg, 52000 + seed, with_truth=True)
+        dec = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)
+        stereo_seen = False
+        for f in range(cfg.n_frames):
+            r = dec.decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
+            assert r["status"] == 0, (seed, f, r["status"])
+            assert (r["channels"], r["sample_length"], r["sample_rate"]) == (2, 2048, 48000)
+            stereo_seen |= not np.array_equal(r["f32"][0], r["f32"][1])
+            t, tr = dec.tap_ps(0), st.truth["ps"][f]
+            ne = t["num_env"]
+            assert ne == tr[0] and np.array_equal(t["border"][:ne + 1], tr[1:2 + ne]), (seed, f)
+            assert np.array_equal(t["iid"][:ne, :20], tr[8:178].reshape(5, 34)[:ne, :20]), (seed, f)
+            assert np.array_equal(t["icc"][:ne, :20], tr[178:348].reshape(5, 34)[:ne, :20]), (seed, f)
+            modes.add((t["iid_mode"], t["icc_mode"]))
+            n_checked += 1
+        assert stereo_seen
+    assert n_checked == 24 * 40
+    assert len(modes) >= 6   # default / fine IID, type-A / type-B mixing, 10- and 20-band, disabled
+
+
 def _qmf_c():
     txt = open(os.path.join(ROOT, "jaadec_b200", "csrc", "generated", "jaad_tables.h")).read()
     m = re.search(r'JAAD_TABLE_F32\(SBR_QMF_C, 640, "\[640\]"\)(.*?)JAAD_TABLE_END', txt, re.S)
@@ -111,7 +138,7 @@ def test_qmf_banks_match_direct_form():
     assert abs(10 * np.log10(e_out / e_in)) < 0.5
 
 
-@pytest.mark.parametrize("name", ["sbr_c3_stereo", "sbr_mono"])
+@pytest.mark.parametrize("name", ["sbr_c3_stereo", "sbr_mono", "ps_c4_mono"])
 def test_oracle_reproduces_sbr_golden(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     n_streams = int(g["frame_stream"].max()) + 1

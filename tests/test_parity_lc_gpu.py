@@ -169,7 +169,7 @@ def test_asc_open_5_1_raw_frames():
     eng.close()
 
 
-GOLDEN_CASES = ["lc_c1_long_44k", "lc_c2_mixed_48k", "lc_mono_24k", "lc_c5_51_raw", "sbr_c3_stereo", "sbr_mono"]
+GOLDEN_CASES = ["lc_c1_long_44k", "lc_c2_mixed_48k", "lc_mono_24k", "lc_c5_51_raw", "sbr_c3_stereo", "sbr_mono", "ps_c4_mono"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
