@@ -175,6 +175,49 @@ int jaadb_batch_tap(jaadb_batch* b, uint32_t frame, uint32_t ch, int16_t* q, int
  * sbr_types.cuh, SbrFrameDev); returns its size, 0 if the frame's stream carries no SBR, or a negative JAADB_E_* code. */
 int jaadb_batch_tap_sbr(jaadb_batch* b, uint32_t frame, uint32_t ch, void* out, uint32_t out_bytes);
 
+/* ---- container indexers (host side; frames for jaadb_decode) --------------
+ * The caller keeps whole ADTS streams / MP4 files in one blob; these calls produce the frame table.  A NULL `frames`
+ * (or a too small max_frames) only counts.  Return value: number of frames found, or a negative JAADB_E_* code.   */
+typedef struct jaadb_adts_info {   /* fields of the first frame's header, S/adts/ADTSFrame.java:68-100 */
+  int32_t profile;         /* audio object type (2-bit field + 1) */
+  int32_t sf_index;
+  int32_t channel_config;
+  int32_t sample_rate;
+  uint64_t n_frames;
+} jaadb_adts_info;
+
+typedef struct jaadb_mp4_track {   /* the first AAC audio track of a movie, M/api/AudioTrack.java, M/api/Track.java */
+  uint8_t asc[64];         /* DecoderSpecificInfo = AudioSpecificConfig for jaadb_stream_open_asc (M/api/Track.java:155-172) */
+  uint32_t asc_bytes;
+  int32_t track_id;
+  uint32_t timescale;      /* mdhd */
+  uint32_t channel_count;  /* AudioSampleEntry */
+  uint32_t sample_size_bits;
+  uint32_t sample_rate;
+  uint32_t object_type;    /* DecoderConfigDescriptor objectTypeIndication (0x40 = MPEG-4 audio) */
+  uint32_t max_bitrate, avg_bitrate;
+  uint32_t reserved;
+  uint64_t duration;       /* mdhd, in timescale units */
+  uint64_t n_frames;
+} jaadb_mp4_track;
+
+/* ADTSDemultiplexer: sync search + header + payload span of every frame   S/adts/ADTSDemultiplexer.java:26-74.
+ * frames[i].offset = blob_offset + position of the raw_data_block inside `data`. */
+int64_t jaadb_adts_index(const uint8_t* data, uint64_t nbytes, uint64_t blob_offset, int32_t stream_id,
+                         jaadb_frame_desc* frames, uint64_t max_frames, jaadb_adts_info* info);
+/* Stream s occupies blob[stream_begin[s], stream_begin[s+1]); indexed on `threads` host threads (0: all cores).
+ * frames are stream-major, first_frame[n_streams+1] receives each stream's first row; stream_ids NULL: 0..n-1. */
+int64_t jaadb_adts_index_many(const uint8_t* blob, const uint64_t* stream_begin, uint32_t n_streams,
+                              const int32_t* stream_ids, jaadb_frame_desc* frames, uint64_t max_frames,
+                              uint64_t* first_frame, jaadb_adts_info* infos, uint32_t threads);
+/* MP4Container + Movie.getTracks(AAC).get(0) + Track.parseSampleTable: stsz/stco|co64/stsc/stts -> frames in
+ * decoding-time order, esds -> AudioSpecificConfig      M/api/Track.java:90-172, M/boxes/BoxFactory.java:319-363 */
+int64_t jaadb_mp4_index(const uint8_t* file, uint64_t nbytes, uint64_t blob_offset, int32_t stream_id,
+                        jaadb_frame_desc* frames, uint64_t max_frames, jaadb_mp4_track* track);
+int64_t jaadb_mp4_index_many(const uint8_t* blob, const uint64_t* file_begin, uint32_t n_files, const int32_t* stream_ids,
+                             jaadb_frame_desc* frames, uint64_t max_frames, uint64_t* first_frame,
+                             jaadb_mp4_track* tracks, uint32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ def _sources():
     out = []
     for root, _, files in os.walk(CSRC):
         for f in files:
-            if f.endswith((".cu", ".cuh", ".h")):
+            if f.endswith((".cu", ".cuh", ".h", ".cpp")):
                 out.append(os.path.join(root, f))
     out.append(os.path.join(_HERE, "..", "include", "jaadb200.h"))
     return out
@@ -43,6 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc not found; cannot build libjaadb200.so")
     os.makedirs(OUT_DIR, exist_ok=True)
     extra = os.environ.get("JAADB200_NVCC_DEFS", "").split()   # tuning experiments only, e.g. -DK2_STEREO_MIN_BLOCKS=6
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "jaadb_engine.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "jaadb_engine.cu"),
+                                                                                  os.path.join(CSRC, "container_index.cpp")]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB

@@ -16,6 +16,7 @@ SYMBOLS = [
     "jaadb_stream_open_asc", "jaadb_stream_open_adts", "jaadb_stream_close", "jaadb_stream_get_info", "jaadb_decode",
     "jaadb_batch_create", "jaadb_batch_pcm_bytes", "jaadb_batch_upload", "jaadb_batch_decode", "jaadb_batch_sync",
     "jaadb_batch_download", "jaadb_batch_timings", "jaadb_batch_destroy", "jaadb_batch_tap", "jaadb_batch_tap_sbr",
+    "jaadb_adts_index", "jaadb_adts_index_many", "jaadb_mp4_index", "jaadb_mp4_index_many",
 ]
 
 
@@ -41,6 +42,18 @@ class StreamInfo(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("parse_ms", C.c_float), ("filterbank_ms", C.c_float), ("sbr_ms", C.c_float), ("total_ms", C.c_float),
                 ("launches", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
+class AdtsInfo(C.Structure):
+    _fields_ = [("profile", C.c_int32), ("sf_index", C.c_int32), ("channel_config", C.c_int32), ("sample_rate", C.c_int32),
+                ("n_frames", C.c_uint64)]
+
+
+class Mp4Track(C.Structure):
+    _fields_ = [("asc", C.c_uint8 * 64), ("asc_bytes", C.c_uint32), ("track_id", C.c_int32), ("timescale", C.c_uint32),
+                ("channel_count", C.c_uint32), ("sample_size_bits", C.c_uint32), ("sample_rate", C.c_uint32),
+                ("object_type", C.c_uint32), ("max_bitrate", C.c_uint32), ("avg_bitrate", C.c_uint32),
+                ("reserved", C.c_uint32), ("duration", C.c_uint64), ("n_frames", C.c_uint64)]
 
 
 _lib = None
@@ -83,5 +96,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.jaadb_batch_destroy.restype = None
     lib.jaadb_batch_tap.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp]
     lib.jaadb_batch_tap_sbr.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32]
+    for fn in (lib.jaadb_adts_index, lib.jaadb_mp4_index):
+        fn.restype = C.c_int64
+        fn.argtypes = [u8p, C.c_uint64, C.c_uint64, C.c_int32, vp, C.c_uint64, vp]
+    for fn in (lib.jaadb_adts_index_many, lib.jaadb_mp4_index_many):
+        fn.restype = C.c_int64
+        fn.argtypes = [u8p, vp, C.c_uint32, vp, vp, C.c_uint64, vp, vp, C.c_uint32]
     _lib = lib
     return lib

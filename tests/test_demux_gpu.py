@@ -1,0 +1,63 @@
+"""End-to-end container path on the GPU: MP4 files / ADTS streams -> native indexer -> engine -> PCM, against the
+oracle decoding the generator's raw frames (the way JAAD's Main walks a Track or an ADTSDemultiplexer)."""
+import numpy as np
+import pytest
+
+import gen
+import oracle
+from gen import mp4 as genmp4
+from jaadec_b200 import Engine, demux, PCM_S16LE
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mp4_files_decode_like_raw_frames():
+    asc = bytes([0x11, 0xB0])    # AAC-LC, 48 kHz, 5.1
+    cfg = gen.config(5, n_frames=14, p_transient=0.3)
+    layouts = [dict(), dict(chunk_pattern=(3, 1, 5), co64=True, large_mdat=True),
+               dict(decoy_track=True, moov_first=False, free_boxes=True, chunk_gap=7, long_descriptors=False)]
+    streams = [gen.generate(cfg, 3100 + s) for s in range(len(layouts))]
+    files = []
+    for st, kw in zip(streams, layouts):
+        raw = [st.data[o: o + n].tobytes() for o, n in zip(st.offsets, st.sizes)]
+        files.append(genmp4.write_mp4(raw, asc, 48000, 6, **kw)[0])
+    blob = np.concatenate(files)
+    begin = np.concatenate([[0], np.cumsum([len(f) for f in files])])
+    eng = Engine(max_streams=8, pcm_format=PCM_S16LE)
+    # index first to learn each file's AudioSpecificConfig, open the streams, then index with the engine's ids
+    _, _, tracks = demux.mp4_index_many(blob, begin)
+    ids = [eng.open_asc(demux.asc_of(t)) for t in tracks]
+    frames, first, _ = demux.mp4_index_many(blob, begin, ids)
+    frames = demux.interleave(frames, first)
+    pcm, res = eng.decode(blob, frames)
+    assert (res["status"] == 0).all()
+    per = 6 * 1024 * 2
+    pcm = np.frombuffer(pcm, np.int16).reshape(len(frames), 1024, 6)
+    assert pcm.nbytes == len(frames) * per
+    decs = [oracle.Decoder.create_asc(asc) for _ in streams]
+    k = 0
+    for f in range(cfg.n_frames):
+        for s, st in enumerate(streams):
+            r = decs[s].decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
+            assert r["status"] == 0 and frames["stream_id"][k] == ids[s]
+            assert np.array_equal(pcm[k], r["s16"]), (s, f)
+            k += 1
+
+
+def test_adts_streams_indexed_natively():
+    cfg = gen.config(2, n_frames=11, p_transient=0.3)
+    streams = [gen.generate(cfg, 5200 + s) for s in range(5)]
+    blob = np.concatenate([s.data for s in streams])
+    begin = np.concatenate([[0], np.cumsum([len(s.data) for s in streams])])
+    eng = Engine(max_streams=8, pcm_format=PCM_S16LE)
+    _, _, infos = demux.adts_index_many(blob, begin)
+    ids = [eng.open_adts(i.profile, i.sf_index, i.channel_config) for i in infos]
+    frames, first, _ = demux.adts_index_many(blob, begin, ids)
+    pcm, res = eng.decode(blob, frames)             # stream-major order this time
+    assert (res["status"] == 0).all()
+    pcm = np.frombuffer(pcm, np.int16).reshape(len(frames), 1024, 2)
+    for s, st in enumerate(streams):
+        dec = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)
+        for f in range(cfg.n_frames):
+            r = dec.decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
+            assert np.array_equal(pcm[first[s] + f], r["s16"]), (s, f)
