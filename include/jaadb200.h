@@ -77,7 +77,8 @@ typedef struct jaadb_options {
   int32_t tns_mode;      /* JAADB_TNS_* */
   uint32_t flags;        /* JAADB_FLAG_* */
   uint32_t chunk_frames; /* jaadb_decode pipelines chunks of this many consecutive frames (0: default, 131072) */
-  uint32_t reserved[2];
+  uint32_t sbr_tile_frames; /* SBR stages work on tiles of this many frames per stream (0: sized to the workspace budget) */
+  uint32_t reserved[1];
 } jaadb_options;
 
 /* One AAC frame (an ADTS payload or an MP4 sample) inside the caller's blob.

@@ -22,7 +22,7 @@ SYMBOLS = [
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_streams", C.c_uint32), ("pcm_format", C.c_int32), ("tns_mode", C.c_int32),
-                ("flags", C.c_uint32), ("chunk_frames", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+                ("flags", C.c_uint32), ("chunk_frames", C.c_uint32), ("sbr_tile_frames", C.c_uint32), ("reserved", C.c_uint32 * 1)]
 
 
 class FrameDesc(C.Structure):

@@ -153,7 +153,7 @@ struct FrameIndex {
   // SBR streams: one parse run per element (K3), one process run per channel (K4)
   std::vector<SbrRunDev> sbr_runs;
   std::vector<K4RunDev> k4_runs;      // plain SBR channels first, then the SBR+PS ones
-  uint32_t n_sbr_frames = 0, n_k4_plain = 0, n_ps_frames = 0;
+  uint32_t n_sbr_frames = 0, n_k4_plain = 0, n_ps_frames = 0, k4_max_count = 0;
   // when set, frames / run_frames are written here (pinned staging of the one-call path) instead of the vectors
   FrameDev* frames_out = nullptr;
   RunFrameDev* run_frames_out = nullptr;
@@ -201,6 +201,7 @@ struct jaadb_engine {
   bool sbr_ready = false;
   SbrElemDev* d_sbr_elem = nullptr;   // [max_streams][2]
   SbrChanDev* d_sbr_chan = nullptr;   // [max_streams][kSbrChansPerStream]
+  DevBuf<float> d_xg;                 // K4 tile workspace: the Xsbr matrices of one tile of frames (k4_sbr_process.cuh)
   PsChanDev* d_ps_chan = nullptr;     // [max_streams]
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
@@ -272,7 +273,7 @@ struct jaadb_batch {
   DevBuf<float> d_spec_tap;
   std::vector<SbrRunDev> sbr_runs;
   std::vector<K4RunDev> k4_runs;
-  uint32_t n_sbr_frames = 0, n_k4_plain = 0, n_ps_frames = 0;
+  uint32_t n_sbr_frames = 0, n_k4_plain = 0, n_ps_frames = 0, k4_max_count = 0;
   DevBuf<PsFrameDev> d_ps_frames;
   DevBuf<SbrRunDev> d_sbr_runs;
   DevBuf<K4RunDev> d_k4_runs;
@@ -442,6 +443,11 @@ int init_sbr(jaadb_engine* e) {
   cudaFuncSetAttribute(k4_sbr_process_kernel<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_bytes(true))
   K4_ATTR(0); K4_ATTR(1); K4_ATTR(2);
 #undef K4_ATTR
+  cudaFuncSetAttribute(k4a_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4a_smem_bytes());
+  cudaFuncSetAttribute(k4b_hf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4b_smem_bytes());
+  cudaFuncSetAttribute(k4c_synthesis_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes());
+  cudaFuncSetAttribute(k4c_synthesis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes());
+  cudaFuncSetAttribute(k4c_synthesis_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes());
   e->sbr_ready = true;
   return 0;
 }
@@ -576,6 +582,7 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
   ix.k4_runs.clear();
   ix.n_sbr_frames = 0;
   ix.n_k4_plain = 0;
+  ix.k4_max_count = 0;
   ix.n_ps_frames = 0;
   // per-stream frame counts (counting sort keeps array order inside each stream)
   std::vector<uint32_t>& count = e->scratch_count;
@@ -658,6 +665,7 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
         kr.dup = stereo ? 0 : 1;
         kr.ps_base = sr.ps_base;
         ix.k4_runs.push_back(kr);
+        if (!with_ps) ix.k4_max_count = std::max(ix.k4_max_count, r.count);
       }
       ix.n_sbr_frames += r.count;
       if (with_ps) ix.n_ps_frames += r.count;
@@ -695,10 +703,16 @@ struct DecodeBufs {
   float* core;
   PsFrameDev* ps_frames;
   uint32_t n_k4_plain;
+  uint32_t k4_max_count;   // longest plain-SBR run
 };
 
+#ifndef K4_TILE_BYTES
+#define K4_TILE_BYTES (1536ull << 20)
+#endif
+constexpr uint64_t kK4TileBytes = K4_TILE_BYTES;   // upper bound of the K4 tile workspace (Xsbr matrices of one tile)
+
 // K1 (+ K3) + K2 (+ K4) over an indexed set of frames, everything already on the device.
-void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_groups, uint32_t n_frames, uint32_t n_sbr_runs,
+cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_groups, uint32_t n_frames, uint32_t n_sbr_runs,
                    uint32_t n_k4_runs, const DecodeBufs& B, cudaEvent_t after_k1, cudaEvent_t after_k2, uint32_t* launches) {
   {
     const int threads = kK1Threads;
@@ -737,13 +751,32 @@ void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_gr
   if (after_k2) cudaEventRecord(after_k2, e->stream);
   if (n_k4_runs) {
     const uint32_t n_plain = B.n_k4_plain, n_ps = n_k4_runs - B.n_k4_plain;
+    if (n_plain) {
+      // frame-parallel pipeline over tiles of ft frames per run; the tile's Xsbr matrices stay within kK4TileBytes
+      const uint64_t per_frame = (uint64_t)n_plain * 32 * kXgRow * sizeof(float);
+      uint32_t ft = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(B.k4_max_count, kK4TileBytes / per_frame));
+      if (e->opts.sbr_tile_frames) ft = std::min(ft, e->opts.sbr_tile_frames);
+      const uint32_t rows = 8 + 32 * ft;
+      cudaError_t err = e->d_xg.ensure((size_t)n_plain * rows * kXgRow);
+      if (err != cudaSuccess) return err;
+      for (uint32_t lo = 0; lo < B.k4_max_count; lo += ft) {
+        const K4Tile tile{lo, ft, rows};
+        const uint32_t n_cf = n_plain * ft;
+        k4a_analysis_kernel<<<(n_cf + kK4aWarps - 1) / kK4aWarps, 32 * kK4aWarps, k4a_smem_bytes(), e->stream>>>(
+            B.k4_runs, n_plain, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, tile);
+        k4b_hf_kernel<<<(n_plain + kK4bWarps - 1) / kK4bWarps, 32 * kK4bWarps, k4b_smem_bytes(), e->stream>>>(
+            B.k4_runs, n_plain, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, e->sbr_tables, tile);
+#define K4C_ARGS B.k4_runs, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, B.pcm, B.pcm_off, B.pcm_bytes, e->sbr_tables, tile
+        if (e->opts.pcm_format == JAADB_PCM_S16LE) k4c_synthesis_kernel<0><<<n_cf, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS);
+        else if (e->opts.pcm_format == JAADB_PCM_S16BE) k4c_synthesis_kernel<1><<<n_cf, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS);
+        else k4c_synthesis_kernel<2><<<n_cf, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS);
+#undef K4C_ARGS
+        k4_commit_kernel<<<(n_plain + 255) / 256, 256, 0, e->stream>>>(B.k4_runs, n_plain, e->d_sbr_chan);
+        *launches += 4;
+      }
+    }
 #define LAUNCH_K4(FMT)                                                                                                  \
   do {                                                                                                                  \
-    if (n_plain) {                                                                                                      \
-      k4_sbr_process_kernel<FMT, false><<<n_plain, kK4Threads, k4_smem_bytes(false), e->stream>>>(                      \
-          B.k4_runs, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, B.pcm, B.pcm_off, B.pcm_bytes, e->sbr_tables, nullptr, nullptr); \
-      ++*launches;                                                                                                      \
-    }                                                                                                                   \
     if (n_ps) {                                                                                                         \
       k4_sbr_process_kernel<FMT, true><<<n_ps, kK4Threads, k4_smem_bytes(true), e->stream>>>(                           \
           B.k4_runs + n_plain, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, B.pcm, B.pcm_off, B.pcm_bytes,        \
@@ -756,6 +789,7 @@ void launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size_t n_gr
     else LAUNCH_K4(2);
 #undef LAUNCH_K4
   }
+  return cudaSuccess;
 }
 
 }  // namespace
@@ -833,6 +867,7 @@ void jaadb_engine_destroy(jaadb_engine* e) {
   if (e->d_sstate) cudaFree(e->d_sstate);
   if (e->d_sbr_elem) cudaFree(e->d_sbr_elem);
   if (e->d_sbr_chan) cudaFree(e->d_sbr_chan);
+  e->d_xg.release();
   if (e->d_ps_chan) cudaFree(e->d_ps_chan);
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);
@@ -997,6 +1032,7 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
   b->k4_runs.swap(ix.k4_runs);
   b->n_sbr_frames = ix.n_sbr_frames;
   b->n_k4_plain = ix.n_k4_plain;
+  b->k4_max_count = ix.k4_max_count;
   b->n_ps_frames = ix.n_ps_frames;
   const uint32_t ics = ix.n_ics;
   // device side
@@ -1059,9 +1095,10 @@ int jaadb_batch_decode(jaadb_batch* b) {
   if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[0], e->stream));
   DecodeBufs B{b->d_blob.p, b->d_frames.p, b->d_fside.p, b->d_iside.p, b->d_q.p, b->d_runs.p, b->d_run_frames.p, b->d_pcm.p,
                b->d_pcm_off.p, b->d_pcm_bytes.p, (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) ? b->d_spec_tap.p : nullptr,
-               b->d_sbr_runs.p, b->d_k4_runs.p, b->d_sbr_frames.p, b->d_core.p, b->d_ps_frames.p, b->n_k4_plain};
-  launch_decode(e, b->groups.data(), b->groups.size(), b->n_frames, (uint32_t)b->sbr_runs.size(), (uint32_t)b->k4_runs.size(), B,
-                prof ? e->ev[1] : nullptr, prof ? e->ev[3] : nullptr, &launches);
+               b->d_sbr_runs.p, b->d_k4_runs.p, b->d_sbr_frames.p, b->d_core.p, b->d_ps_frames.p, b->n_k4_plain,
+               b->k4_max_count};
+  CUDA_TRY(e, launch_decode(e, b->groups.data(), b->groups.size(), b->n_frames, (uint32_t)b->sbr_runs.size(), (uint32_t)b->k4_runs.size(), B,
+                prof ? e->ev[1] : nullptr, prof ? e->ev[3] : nullptr, &launches));
   if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[2], e->stream));
   CUDA_TRY(e, cudaGetLastError());
   b->timings.launches = launches;
@@ -1261,9 +1298,9 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
     }
     DecodeBufs B{W.blob.p, W.frames.p, W.fside.p + r.i0, W.iside.p, W.q.p, W.runs.p, W.run_frames.p, W.pcm[pb].p - r.lo,
                  W.pcm_off.p + r.i0, W.pcm_bytes.p + r.i0, nullptr, W.sbr_runs.p, W.k4_runs.p, W.sbr_frames.p, W.core.p, W.ps_frames.p,
-                 ix.n_k4_plain};
-    launch_decode(e, ix.groups.data(), ix.groups.size(), n, (uint32_t)ix.sbr_runs.size(), (uint32_t)ix.k4_runs.size(), B, nullptr,
-                  nullptr, &launches);
+                 ix.n_k4_plain, ix.k4_max_count};
+    CUDA_TRY(e, launch_decode(e, ix.groups.data(), ix.groups.size(), n, (uint32_t)ix.sbr_runs.size(), (uint32_t)ix.k4_runs.size(), B,
+                              nullptr, nullptr, &launches));
     CUDA_TRY(e, cudaGetLastError());
     CUDA_TRY(e, cudaEventRecord(W.k_done[pb], e->stream));
     CUDA_TRY(e, cudaStreamWaitEvent(W.copy_stream, W.k_done[pb], 0));

@@ -996,6 +996,9 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
   const bool stereo = run.stereo != 0;
   const int nch = stereo ? 2 : 1;
 
+  // bookkeeping for the frame-parallel K4: ordinal of / distances between the frames that run the QMF banks (and the PS tool)
+  uint32_t n_proc = 0;
+  int64_t last_proc = -1, last_ps = -1;
   for (uint32_t it = 0; it < run.count; ++it) {
     const uint32_t f = run_frames[run.first + it].frame;
     int mode = 0;          // what K4 does with the frame (SbrFrameDev.mode)
@@ -1045,14 +1048,18 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
         }
       }
     }
+    int use_ps = 0;
     if (lane == 0 && run.ps) {
       // SBR1.process: parametric stereo runs iff this frame brought ps_data (SBR1.isPSUsed); PSImpl.ps_data_decode
       PsFrameDev* po = ps_out + run.ps_base + it;
       po->use_ps = 0;
       if (mode != 0 && S->ps.opened && S->ps.data_available) ps_data_decode(S->ps, *po);
+      use_ps = po->use_ps;
     }
     mode = __shfl_sync(0xFFFFFFFFu, mode, 0);
     frame_status = __shfl_sync(0xFFFFFFFFu, frame_status, 0);
+    use_ps = __shfl_sync(0xFFFFFFFFu, use_ps, 0);
+    const bool processed = frame_status == 0 && mode != 0;
     __syncwarp();
     // ---- frame records (all lanes)
     for (int c = 0; c < nch; ++c) {
@@ -1099,8 +1106,16 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
         o->limiter_gains = S->hdr.limiter_gains; o->interpol_freq = S->hdr.interpol_freq; o->smoothing_mode = S->hdr.smoothing_mode;
         o->add_harmonic_flag_prev = cp.add_harmonic_flag_prev;
         o->l_A = cp.l_A; o->prevEnvIsShort = cp.prevEnvIsShort;
+        o->ord = n_proc;
+        o->back = last_proc < 0 ? 0u : (uint32_t)(it - last_proc);
+        o->fwd = 0;
+        o->back_ps = last_ps < 0 ? 0u : (uint32_t)(it - last_ps);
+        o->fwd_ps = 0;
+        if (processed && last_proc >= 0) out[((size_t)run.sbr_base + last_proc) * 2 + c].fwd = (uint32_t)(it - last_proc);
+        if (processed && use_ps && last_ps >= 0) out[((size_t)run.sbr_base + last_ps) * 2 + c].fwd_ps = (uint32_t)(it - last_ps);
       }
     }
+    if (processed) { last_proc = it; ++n_proc; if (use_ps) last_ps = it; }
     __syncwarp();
     // ---- what SBR.process leaves behind for the next frame's parse (sbr_save_prev_data, SBR.java:256-284)
     if (lane == 0 && mode == 2) {

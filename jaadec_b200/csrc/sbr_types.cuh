@@ -112,9 +112,15 @@ struct __align__(16) SbrFrameDev {
   uint8_t add_harmonic_flag_prev;
   int8_t l_A, prevEnvIsShort;
   uint8_t frame_status;             // the frame's final status != 0: nothing is processed
-  uint8_t pad[16];
+  // frame-parallel K4: a frame is "processed" when frame_status == 0 and mode != 0 (it runs the QMF banks and moves the
+  // channel's state); the others leave the state alone
+  uint32_t ord;                     // processed frames of this run (in this batch) before this one
+  uint32_t back;                    // distance (in run frames) to the previous processed frame, 0: none in this batch
+  uint32_t fwd;                     // distance to the next processed frame, 0: none in this batch
+  uint32_t back_ps, fwd_ps;         // the same over frames that run the parametric-stereo tool (use_ps)
+  uint8_t pad[12];
 };
-static_assert(sizeof(SbrFrameDev) == 1872, "SbrFrameDev layout (mirrored by jaadec_b200/engine.py SBR_FRAME_DTYPE)");
+static_assert(sizeof(SbrFrameDev) == 1888, "SbrFrameDev layout (mirrored by jaadec_b200/engine.py SBR_FRAME_DTYPE)");
 
 // Process-side persistent state of the parametric-stereo tool of one stream (ps/PSImpl.java:39-62, ps/Filterbank.java).
 // Delay lines are stored per band so that the thread that owns a band touches one contiguous piece.
@@ -135,13 +141,18 @@ struct __align__(16) PsChanDev {
 struct __align__(16) SbrChanDev {
   float ana_hist[288];              // the last 288 core samples (QMF analysis ring of sbr/AnalysisFilterbank.java)
   float xsbr[kSbrHfGen][64][2];     // Xsbr rows 0..7 (the last 8 slots of the previous frame, SBR.sbr_save_matrix)
-  float syn_v[9][128];              // the 9 most recent synthesis v-vectors ([0] = newest; sbr/SynthesisFilterbank64.java)
+  // the 9 most recent synthesis v-vectors ([0] = newest; sbr/SynthesisFilterbank64.java), double buffered: the synthesis
+  // kernel reads [v_sel] for the first frame of a tile while another CTA of the same launch stores the tile's last nine
+  // into [v_sel ^ 1]; k4_commit_kernel flips v_sel afterwards
+  float syn_v[2][9][128];
   float G_temp_prev[5][64], Q_temp_prev[5][64];
   float bwArray_prev[8];
   uint8_t bs_invf_mode_prev[8];
   int32_t GQ_ringbuf_index, index_noise_prev, psi_is_prev;
-  int32_t pad;
+  int32_t v_sel, v_flip;
+  int32_t pad[3];
 };
+static_assert(sizeof(SbrChanDev) % 16 == 0, "SbrChanDev is copied with 16-byte accesses");
 
 // Read-only tables of the SBR tool (engine-owned device memory).
 struct SbrTablesDev {

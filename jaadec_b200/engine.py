@@ -26,9 +26,9 @@ def _ptr(a):
 
 class Engine:
     def __init__(self, device: int = 0, max_streams: int = 4096, pcm_format: int = PCM_S16LE, flags: int = 0,
-                 chunk_frames: int = 0):
+                 chunk_frames: int = 0, sbr_tile_frames: int = 0):
         self._lib = _lib.load()
-        opts = Options(device, max_streams, pcm_format, 0, flags, chunk_frames, (C.c_uint32 * 2)(0, 0))
+        opts = Options(device, max_streams, pcm_format, 0, flags, chunk_frames, sbr_tile_frames, (C.c_uint32 * 1)(0))
         h = C.c_void_p()
         rc = self._lib.jaadb_engine_create(C.byref(opts), C.byref(h))
         if rc != 0:
@@ -151,7 +151,8 @@ class Batch:
         ("mode", "u1"), ("reset", "u1"), ("L_E", "u1"), ("L_Q", "u1"), ("kx", "u1"), ("M", "u1"), ("N_high", "u1"), ("N_low", "u1"),
         ("N_Q", "u1"), ("N_L", "u1"), ("kx_prev", "u1"), ("M_prev", "u1"), ("noPatches", "u1"), ("limiter_gains", "u1"),
         ("interpol_freq", "u1"), ("smoothing_mode", "u1"), ("add_harmonic_flag_prev", "u1"), ("l_A", "i1"),
-        ("prevEnvIsShort", "i1"), ("frame_status", "u1"), ("pad", "u1", (16,))])
+        ("prevEnvIsShort", "i1"), ("frame_status", "u1"), ("ord", "<u4"), ("back", "<u4"), ("fwd", "<u4"),
+        ("back_ps", "<u4"), ("fwd_ps", "<u4"), ("pad", "u1", (12,))])
 
     def tap_sbr(self, frame: int, ch: int):
         """SBR record of frame `frame`, channel `ch` (None when the stream carries no SBR)."""

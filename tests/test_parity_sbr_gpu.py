@@ -23,11 +23,13 @@ CASES = [
 ]
 
 
+# the SBR stages walk tiles of frames (0: one tile sized to the workspace budget); every tiling must give the same bits
+@pytest.mark.parametrize("tile", [0, 1, 7])
 @pytest.mark.parametrize("label,cfg,n_streams", CASES, ids=[c[0] for c in CASES])
-def test_sbr_float_pcm_bit_exact(label, cfg, n_streams):
+def test_sbr_float_pcm_bit_exact(label, cfg, n_streams, tile):
     wl = Workload(cfg, n_streams, base_seed=gen.seed_for(3, 40), with_truth=False)
     decs = wl.oracle_decoders()
-    eng = Engine(max_streams=16, pcm_format=PCM_F32_PLANAR)
+    eng = Engine(max_streams=16, pcm_format=PCM_F32_PLANAR, sbr_tile_frames=tile)
     ids = [eng.open_adts(*wl.hdr, expect_sbr=cfg.sbr_mode) for _ in range(n_streams)]
     info = eng.stream_info(ids[0])
     assert (info.channels, info.sample_length) == (2, 2048)
@@ -67,7 +69,8 @@ def test_sbr_s16_and_state_across_calls(fmt, big):
     eng.close()
 
 
-def test_sbr_frames_without_payload_are_upsampled():
+@pytest.mark.parametrize("tile", [0, 1, 3])
+def test_sbr_frames_without_payload_are_upsampled(tile):
     """A frame that carries no SBR fill element takes SBR.upsample (sample 1 keeps the core value) and leaves the
     QMF state alone; bad frames yield no PCM and the stream continues."""
     cfg = gen.config(3, n_frames=12)
@@ -87,7 +90,7 @@ def test_sbr_frames_without_payload_are_upsampled():
         if s == 1 and f == 4:
             frames["nbytes"][i] //= 3
     decs = wl.oracle_decoders()
-    eng = Engine(max_streams=4, pcm_format=PCM_F32_PLANAR)
+    eng = Engine(max_streams=4, pcm_format=PCM_F32_PLANAR, sbr_tile_frames=tile)
     ids = [eng.open_adts(*wl.hdr, expect_sbr=1) for _ in range(2)]
     assert ids == [0, 1]
     pcm, res = eng.decode(blob, frames)

@@ -14,7 +14,7 @@ ps = len(sys.argv) > 2 and sys.argv[2] == "ps"
 cfg = gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=24, target_bytes=171, sbr_mode=2 if ps else 1) if mono else gen.config(3, n_frames=24, sbr_quirk=True)
 wl = Workload(cfg, n, base_seed=int(sys.argv[3]) if len(sys.argv) > 3 else 70000, with_truth=False)
 decs = wl.oracle_decoders()
-eng = Engine(max_streams=n, pcm_format=PCM_F32_PLANAR)
+eng = Engine(max_streams=n, pcm_format=PCM_F32_PLANAR, sbr_tile_frames=int(os.environ.get('TILE', '0')))
 ids = [eng.open_adts(*wl.hdr, expect_sbr=cfg.sbr_mode) for _ in range(n)]
 frames, index = wl.frame_table(ids)
 pcm, res = eng.decode(wl.blob, frames)
