@@ -202,6 +202,7 @@ struct jaadb_engine {
   SbrElemDev* d_sbr_elem = nullptr;   // [max_streams][2]
   SbrChanDev* d_sbr_chan = nullptr;   // [max_streams][kSbrChansPerStream]
   DevBuf<float> d_xg;                 // K4 tile workspace: the Xsbr matrices of one tile of frames (k4_sbr_process.cuh)
+  DevBuf<float> d_xps;                // K5 -> K4c: left / right QMF matrices of the tile's parametric-stereo frames
   PsChanDev* d_ps_chan = nullptr;     // [max_streams]
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
@@ -438,16 +439,14 @@ int init_sbr(jaadb_engine* e) {
   CUDA_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->d_sbr_chan), sizeof(SbrChanDev) * ns * kSbrChansPerStream));
   CUDA_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->d_ps_chan), sizeof(PsChanDev) * ns));
   cudaFuncSetAttribute(k3_sbr_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SbrElemDev) * kK3WarpsPerBlock));
-#define K4_ATTR(FMT)                                                                                                       \
-  cudaFuncSetAttribute(k4_sbr_process_kernel<FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_bytes(false)); \
-  cudaFuncSetAttribute(k4_sbr_process_kernel<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_bytes(true))
-  K4_ATTR(0); K4_ATTR(1); K4_ATTR(2);
-#undef K4_ATTR
   cudaFuncSetAttribute(k4a_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4a_smem_bytes());
   cudaFuncSetAttribute(k4b_hf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4b_smem_bytes());
-  cudaFuncSetAttribute(k4c_synthesis_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes());
-  cudaFuncSetAttribute(k4c_synthesis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes());
-  cudaFuncSetAttribute(k4c_synthesis_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes());
+#define K4C_ATTR(FMT)                                                                                                        \
+  cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes()); \
+  cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes())
+  K4C_ATTR(0); K4C_ATTR(1); K4C_ATTR(2);
+#undef K4C_ATTR
+  cudaFuncSetAttribute(k5_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5_smem_bytes());
   e->sbr_ready = true;
   return 0;
 }
@@ -665,7 +664,7 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
         kr.dup = stereo ? 0 : 1;
         kr.ps_base = sr.ps_base;
         ix.k4_runs.push_back(kr);
-        if (!with_ps) ix.k4_max_count = std::max(ix.k4_max_count, r.count);
+        ix.k4_max_count = std::max(ix.k4_max_count, r.count);
       }
       ix.n_sbr_frames += r.count;
       if (with_ps) ix.n_ps_frames += r.count;
@@ -751,43 +750,48 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
   if (after_k2) cudaEventRecord(after_k2, e->stream);
   if (n_k4_runs) {
     const uint32_t n_plain = B.n_k4_plain, n_ps = n_k4_runs - B.n_k4_plain;
-    if (n_plain) {
-      // frame-parallel pipeline over tiles of ft frames per run; the tile's Xsbr matrices stay within kK4TileBytes
-      const uint64_t per_frame = (uint64_t)n_plain * 32 * kXgRow * sizeof(float);
-      uint32_t ft = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(B.k4_max_count, kK4TileBytes / per_frame));
-      if (e->opts.sbr_tile_frames) ft = std::min(ft, e->opts.sbr_tile_frames);
-      const uint32_t rows = 8 + 32 * ft;
-      cudaError_t err = e->d_xg.ensure((size_t)n_plain * rows * kXgRow);
+    // frame-parallel pipeline over tiles of ft frames per run; the tile's matrices stay within kK4TileBytes
+    const uint64_t per_frame = ((uint64_t)n_k4_runs * 32 + (uint64_t)n_ps * 64) * kXgRow * sizeof(float);
+    uint32_t ft = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(B.k4_max_count, kK4TileBytes / per_frame));
+    if (e->opts.sbr_tile_frames) ft = std::min(ft, e->opts.sbr_tile_frames);
+    const uint32_t rows = 8 + 32 * ft;
+    cudaError_t err = e->d_xg.ensure((size_t)n_k4_runs * rows * kXgRow);
+    if (err != cudaSuccess) return err;
+    if (n_ps) {
+      err = e->d_xps.ensure((size_t)n_ps * ft * 64 * kXgRow);
       if (err != cudaSuccess) return err;
-      for (uint32_t lo = 0; lo < B.k4_max_count; lo += ft) {
-        const K4Tile tile{lo, ft, rows};
-        const uint32_t n_cf = n_plain * ft;
-        k4a_analysis_kernel<<<(n_cf + kK4aWarps - 1) / kK4aWarps, 32 * kK4aWarps, k4a_smem_bytes(), e->stream>>>(
-            B.k4_runs, n_plain, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, tile);
-        k4b_hf_kernel<<<(n_plain + kK4bWarps - 1) / kK4bWarps, 32 * kK4bWarps, k4b_smem_bytes(), e->stream>>>(
-            B.k4_runs, n_plain, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, e->sbr_tables, tile);
-#define K4C_ARGS B.k4_runs, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, B.pcm, B.pcm_off, B.pcm_bytes, e->sbr_tables, tile
-        if (e->opts.pcm_format == JAADB_PCM_S16LE) k4c_synthesis_kernel<0><<<n_cf, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS);
-        else if (e->opts.pcm_format == JAADB_PCM_S16BE) k4c_synthesis_kernel<1><<<n_cf, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS);
-        else k4c_synthesis_kernel<2><<<n_cf, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS);
-#undef K4C_ARGS
-        k4_commit_kernel<<<(n_plain + 255) / 256, 256, 0, e->stream>>>(B.k4_runs, n_plain, e->d_sbr_chan);
-        *launches += 4;
-      }
     }
-#define LAUNCH_K4(FMT)                                                                                                  \
-  do {                                                                                                                  \
-    if (n_ps) {                                                                                                         \
-      k4_sbr_process_kernel<FMT, true><<<n_ps, kK4Threads, k4_smem_bytes(true), e->stream>>>(                           \
-          B.k4_runs + n_plain, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, B.pcm, B.pcm_off, B.pcm_bytes,        \
-          e->sbr_tables, B.ps_frames, e->d_ps_chan);                                                                    \
-      ++*launches;                                                                                                      \
-    }                                                                                                                   \
+    for (uint32_t lo = 0; lo < B.k4_max_count; lo += ft) {
+      const K4Tile tile{lo, ft, rows};
+      const uint32_t n_cf = n_k4_runs * ft;
+      k4a_analysis_kernel<<<(n_cf + kK4aWarps - 1) / kK4aWarps, 32 * kK4aWarps, k4a_smem_bytes(), e->stream>>>(
+          B.k4_runs, n_k4_runs, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, tile);
+      k4b_hf_kernel<<<(n_k4_runs + kK4bWarps - 1) / kK4bWarps, 32 * kK4bWarps, k4b_smem_bytes(), e->stream>>>(
+          B.k4_runs, n_k4_runs, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, e->sbr_tables, tile);
+      *launches += 2;
+      if (n_ps) {
+        k5_ps_kernel<<<n_ps, kK5Threads, k5_smem_bytes(), e->stream>>>(B.k4_runs, n_plain, B.sbr_frames, B.ps_frames, e->d_ps_chan,
+                                                                         e->d_xg.p, e->d_xps.p, e->sbr_tables, tile);
+        ++*launches;
+      }
+#define K4C_ARGS(R0) B.k4_runs, R0, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, B.pcm, B.pcm_off, B.pcm_bytes, \
+                     e->sbr_tables, tile, B.ps_frames, e->d_ps_chan, e->d_xps.p
+#define LAUNCH_K4C(FMT)                                                                                                        \
+  do {                                                                                                                         \
+    if (n_plain) { k4c_synthesis_kernel<FMT, false><<<n_plain * ft, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(0u)); ++*launches; } \
+    if (n_ps) {                                                                                                                \
+      k4c_synthesis_kernel<FMT, true><<<dim3(n_ps * ft, 2), kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(n_plain));    \
+      ++*launches;                                                                                                             \
+    }                                                                                                                          \
   } while (0)
-    if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K4(0);
-    else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K4(1);
-    else LAUNCH_K4(2);
-#undef LAUNCH_K4
+      if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K4C(0);
+      else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K4C(1);
+      else LAUNCH_K4C(2);
+#undef LAUNCH_K4C
+#undef K4C_ARGS
+      k4_commit_kernel<<<(n_k4_runs + 255) / 256, 256, 0, e->stream>>>(B.k4_runs, n_k4_runs, n_plain, e->d_sbr_chan, e->d_ps_chan);
+      ++*launches;
+    }
   }
   return cudaSuccess;
 }
@@ -868,6 +872,7 @@ void jaadb_engine_destroy(jaadb_engine* e) {
   if (e->d_sbr_elem) cudaFree(e->d_sbr_elem);
   if (e->d_sbr_chan) cudaFree(e->d_sbr_chan);
   e->d_xg.release();
+  e->d_xps.release();
   if (e->d_ps_chan) cudaFree(e->d_ps_chan);
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);

@@ -1,10 +1,9 @@
-// K4 -- SBR signal path.  One CTA (64 threads) owns one SBR channel of one stream and walks that stream's frames of the
-// batch in order, with the channel's persistent state (QMF analysis history, the last 8 slots of Xsbr, 9 synthesis
-// v-vectors, the gain smoothing ring) resident in shared memory for the whole run:
-//   32-band QMF analysis     sbr/AnalysisFilterbank.java:9-73   (one thread per time slot, DCT-IV in registers)
-//   HF generation            sbr/HFGeneration.java:17-245       (one thread per high band: covariance LPC + patching)
-//   HF adjustment            sbr/HFAdjustment.java:20-415       (envelope estimate per band, gains per envelope, assembly per band)
-//   64-band QMF synthesis    sbr/SynthesisFilterbank64.java:9-79 (one thread per slot for the two DCT-IVs, 64 threads window)
+// K4 / K5 -- SBR and parametric-stereo signal path (frame-parallel pipeline over tiles of frames, see below):
+//   32-band QMF analysis     sbr/AnalysisFilterbank.java:9-73
+//   HF generation            sbr/HFGeneration.java:17-245       (covariance LPC + patching)
+//   HF adjustment            sbr/HFAdjustment.java:20-415       (envelope estimate, gains, limiter, assembly)
+//   parametric stereo        ps/PSImpl.java:685-707, ps/Filterbank.java
+//   64-band QMF synthesis    sbr/SynthesisFilterbank64.java:9-79
 //   Math.round / clamp / interleave as S/SampleBuffer.java:168-209
 // Every floating-point operation is the binary32 operation of the Java code on the same operands in the same order
 // (this file is compiled with --fmad=false), so the PCM is bit-identical to the reference's, like the AAC-LC path.
@@ -143,26 +142,13 @@ __device__ __forceinline__ int ps_group_border(int gr) {
 __device__ __forceinline__ int ps_bk(int gr) { return gr == 0 ? 1 : (gr == 1 ? 0 : gr - 2); }   // map_group2bk20 & ~NEGATE_IPD_MASK
 
 constexpr int kK4Threads = 64;
-// shared-memory carve (floats)
-// Row strides are odd so that the one-thread-per-time-slot phases (analysis, synthesis DCTs), where the 32 lanes of a
-// warp address the same column of 32 different rows, spread over all 32 banks.
-constexpr int kXsStride = 129;              // one Xsbr slot: 64 bands x (re, im) + 1
+// Shared-memory row strides are odd so that the one-thread-per-time-slot phases (the DCTs), where the 32 lanes of a warp
+// address the same column of 32 different rows, spread over all 32 banks.
+constexpr int kXsStride = 129;              // one staged Xsbr slot: 128 + 1
 constexpr int kVbStride = 129;              // one synthesis v-vector: 128 + 1
-constexpr int kK4Xs = 40 * kXsStride;       // Xsbr
-constexpr int kK4In = 288 + 1024 + 41 + 3;  // analysis input: history + this frame's core PCM, one pad float per 32 (+3: 16 B)
-constexpr int kK4V = (9 + 32) * kVbStride + 3;  // synthesis v-vectors: 9 carried + 32 new (+3: keeps what follows 16 B aligned)
-static_assert(kK4Xs % 4 == 0 && kK4In % 4 == 0 && kK4V % 4 == 0, "K4 shared-memory regions must stay 16-byte aligned");
-#define XS(l, k, c) xs[(l) * kXsStride + (k) * 2 + (c)]
-#define VB(s, r) vb[(s) * kVbStride + (r)]
-#define INB(i) inbuf[(i) + ((i) >> 5)]
-constexpr int kK4Adj = 3 * kSbrMaxLE * 64 + kSbrMaxLE * 64;   // G_lim_boost, Q_M_lim_boost, S_M_boost, E_curr
-constexpr int kK4PsFloats = 2 * 32 * kXsStride + 2 * 32 * 24 + 32 * 20 + 3 * 88 + 9 * kVbStride + 3;
-static_assert((2 * 32 * kXsStride + 2 * 32 * 24 + 32 * 20 + 3 * 88 + 9 * kVbStride + 3) % 4 == 0, "PsFrameDev must land 16-byte aligned");
-__host__ __device__ constexpr size_t k4_smem_bytes(bool with_ps = false) {
-  return sizeof(float) * (kK4Xs + kK4In + kK4V + kK4Adj + 16) + sizeof(SbrFrameDev) +
-         (with_ps ? sizeof(float) * kK4PsFloats + sizeof(PsFrameDev) : 0);
-}
+#define INB(i) inbuf[(i) + ((i) >> 5)]      // analysis input: one pad float per 32
 
+// One SBR channel of one stream inside a batch.
 struct K4RunDev {
   int32_t stream_slot;
   uint32_t first, count;    // into run_frames
@@ -176,499 +162,1024 @@ struct K4RunDev {
   uint32_t ps_base;         // first PsFrameDev of the run (SBR+PS streams)
 };
 
-// WITH_PS: the channel is the SCE of an SBR+PS stream; frames that carry ps_data go through the parametric-stereo tool
-// (hybrid analysis, decorrelator, mixing, hybrid synthesis; ps/PSImpl.java:685-707) and a second synthesis bank.
-template <int PCM_FORMAT, bool WITH_PS>
-__global__ void __launch_bounds__(kK4Threads)
-k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __restrict__ run_frames,
-                      const SbrFrameDev* __restrict__ sframes, const float* __restrict__ core, SbrChanDev* __restrict__ chans,
-                      uint8_t* __restrict__ pcm, const uint64_t* __restrict__ pcm_off, uint32_t* __restrict__ pcm_bytes_out,
-                      SbrTablesDev T, const PsFrameDev* __restrict__ ps_frames, PsChanDev* __restrict__ ps_chans) {
-  extern __shared__ __align__(16) float k4_smem[];
-  float* xs = k4_smem;
-  float* inbuf = k4_smem + kK4Xs;
-  float* vb = inbuf + kK4In;
-  float* adj = inbuf + kK4In + kK4V;
-  float (*G_lim_boost)[64] = reinterpret_cast<float (*)[64]>(adj);
-  float (*Q_M_lim_boost)[64] = reinterpret_cast<float (*)[64]>(adj + kSbrMaxLE * 64);
-  float (*S_M_boost)[64] = reinterpret_cast<float (*)[64]>(adj + 2 * kSbrMaxLE * 64);
-  float (*E_curr)[64] = reinterpret_cast<float (*)[64]>(adj + 3 * kSbrMaxLE * 64);   // [envelope][m]
-  float* s_bw = adj + kK4Adj;                                                           // bwArray[8] (+8 spare)
-  SbrFrameDev* fp = reinterpret_cast<SbrFrameDev*>(s_bw + 16);
-  // parametric stereo (WITH_PS only): left / right QMF matrices, hybrid sub-bands, energies, right-channel v history
-  float* ps_base = reinterpret_cast<float*>(fp + 1);
-  float* xl = ps_base;                                   // [32][kXsStride]
-  float* xr = xl + 32 * kXsStride;                       // [32][kXsStride]
-  float* hyl = xr + 32 * kXsStride;                      // [32][12][2]
-  float* hyr = hyl + 32 * 24;                            // [32][12][2]
-  float* pg = hyr + 32 * 24;                             // [32][20] band energies, then transient ratios
-  float* hwork = pg + 32 * 20;                           // [3][44][2] hybrid analysis input
-  float* vhr = hwork + 3 * 88;                           // [9][kVbStride] right channel's carried v-vectors
-  PsFrameDev* pp = reinterpret_cast<PsFrameDev*>(vhr + 9 * kVbStride + 3);
-#define XL(l, k, c) xl[(l) * kXsStride + (k) * 2 + (c)]
-#define XR(l, k, c) xr[(l) * kXsStride + (k) * 2 + (c)]
-#define HYL(n, k, c) hyl[((n) * 12 + (k)) * 2 + (c)]
-#define HYR(n, k, c) hyr[((n) * 12 + (k)) * 2 + (c)]
+// =====================================================================================================================
+// Frame-parallel SBR pipeline.  The QMF banks are FIR structures: analysis slot l of a frame needs
+// the 320 newest core samples, synthesis slot l the ten newest v-vectors, so every (channel, frame) pair can run on its
+// own warp / CTA once the few truly recursive pieces are out of the way.  The Xsbr matrix of SBR.java lives in global
+// memory for a TILE of frames (ft consecutive frames of every run):
+//
+//   xg[run][8 + 32 * ft rows][64 bands][re, im]      row 32 * o + r = row r of Xsbr for the o-th processed frame
+//                                                    of the tile (rows 32..39 of a frame ARE rows 0..7 of the next one,
+//                                                    which is what SBR.sbr_save_matrix copies)
+//
+//   K4a  k4a_analysis_kernel   warp per (channel, frame): 32-band analysis, one time slot per lane       -> xg low band
+//   K4b  k4b_hf_kernel         warp per channel, frames of the tile in order (chirp factors, smoothing ring, noise and
+//                              sine phase are recursive): HF generation + HF adjustment, one band per lane -> xg high band
+//   K4c  k4c_synthesis_kernel  CTA per (channel, frame): 64-band synthesis; the nine v-vectors a frame inherits are
+//                              recomputed from the previous frame's rows (or come from the carried state at a tile start)
+//   k4_commit_kernel           flips the double-buffered v-vector state
+// Frames that do not run the SBR tool (mode 0, failed frames) take no rows: K3 numbers the processed frames (ord) and
+// links them (back / fwd).
+constexpr int kXgRow = 128;   // floats per row of xg
 
-  const K4RunDev run = runs[blockIdx.x];
-  const int t = threadIdx.x;
-  SbrChanDev* st = chans + (size_t)run.stream_slot * kSbrChansPerStream + run.ch_slot;
+struct K4Tile {
+  uint32_t lo, ft;    // frames [lo, lo + ft) of every run
+  uint32_t rows;      // rows per run in xg: 8 + 32 * ft
+};
 
-  // ---- persistent state in
-  for (int i = t; i < 288; i += kK4Threads) INB(i) = st->ana_hist[i];
-  for (int i = t; i < kSbrHfGen * 128; i += kK4Threads) XS(i >> 7, 0, i & 127) = (&st->xsbr[0][0][0])[i];
-  for (int i = t; i < (40 - kSbrHfGen) * 128; i += kK4Threads) XS(kSbrHfGen + (i >> 7), 0, i & 127) = 0.f;
-  // carried v-vectors: row 8 is the newest (slot -1), row 0 the oldest (slot -9); syn_v[0] = newest
-  for (int i = t; i < 9 * 128; i += kK4Threads) VB(8 - i / 128, i % 128) = st->syn_v[0][i / 128][i % 128];
-  float Gt[5], Qt[5];   // smoothing ring of band m = t
+__device__ __forceinline__ const SbrFrameDev* k4_frame(const SbrFrameDev* sframes, const K4RunDev& run, uint32_t it) {
+  return sframes + ((size_t)run.sbr_base + it) * 2 + run.chan;
+}
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+
+// ---- K4a: 32-band QMF analysis (sbr/AnalysisFilterbank.java:9-73)
+constexpr int kK4aWarps = 4;
+constexpr int kK4aStage = 32 * 65;   // floats per warp: the 1312 input samples first, then the [32 slots][64 + 1] output
+constexpr size_t k4a_smem_bytes() { return sizeof(float) * kK4aStage * kK4aWarps; }
+
+__global__ void __launch_bounds__(32 * kK4aWarps)
+k4a_analysis_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrameDev* __restrict__ run_frames,
+                    const SbrFrameDev* __restrict__ sframes, const float* __restrict__ core, const SbrChanDev* __restrict__ chans,
+                    float* __restrict__ xg, K4Tile tile) {
+  extern __shared__ __align__(16) float k4a_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w = blockIdx.x * kK4aWarps + warp;
+  if (w >= n_runs * tile.ft) return;
+  const uint32_t r = w / tile.ft, it = tile.lo + w % tile.ft;
+  const K4RunDev run = runs[r];
+  if (it >= run.count) return;
+  const SbrFrameDev* fp = k4_frame(sframes, run, it);
+  const int mode = fp->mode;
+  if (fp->frame_status != 0 || mode == 0) return;
+  const uint32_t o = fp->ord - k4_frame(sframes, run, tile.lo)->ord;
+  const int kx = mode == 2 ? fp->kx : 32;
+  const uint32_t back = fp->back;
+  float* X = xg + ((size_t)r * tile.rows + 32 * (size_t)o) * kXgRow;
+  const SbrChanDev* st = chans + (size_t)run.stream_slot * kSbrChansPerStream + run.ch_slot;
+  if (o == 0) {
+    // the rows the previous tile (or batch) left behind
+    const float4* s4 = reinterpret_cast<const float4*>(&st->xsbr[0][0][0]);
+    float4* d4 = reinterpret_cast<float4*>(X);
+    for (int i = lane; i < kSbrHfGen * 32; i += 32) d4[i] = s4[i];
+  }
+  float* inbuf = k4a_smem + warp * kK4aStage;
+  {
+    // all 17 loads of the lane are issued before the first one is consumed
+    const float* hist = back ? core + ((size_t)run_frames[run.first + it - back].ics_base + run.ch_slot) * 1024 + 736 : st->ana_hist;
+    const float4* cs = reinterpret_cast<const float4*>(core + ((size_t)run_frames[run.first + it].ics_base + run.ch_slot) * 1024);
+    float h[9];
+    float4 c[8];
 #pragma unroll
-  for (int n = 0; n < 5; ++n) { Gt[n] = st->G_temp_prev[n][t]; Qt[n] = st->Q_temp_prev[n][t]; }
+    for (int u = 0; u < 9; ++u) h[u] = hist[lane + 32 * u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c[u] = __ldg(cs + lane + 32 * u);
+#pragma unroll
+    for (int u = 0; u < 9; ++u) INB(lane + 32 * u) = h[u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = lane + 32 * u;
+      INB(288 + 4 * i) = c[u].x; INB(288 + 4 * i + 1) = c[u].y; INB(288 + 4 * i + 2) = c[u].z; INB(288 + 4 * i + 3) = c[u].w;
+    }
+  }
+  __syncwarp();
+  const int xi = 288 + 32 * lane + 31;   // newest sample of the slot; sample xi - j = v[v_index + j] of the reference
+  float in_real[32], in_imag[32], out_real[32], out_imag[32];
+#pragma unroll
+  for (int n = 0; n < 64; ++n) {
+    const float u = (INB(xi - n) * c_sbr_qmf_c[2 * n]) + (INB(xi - (n + 64)) * c_sbr_qmf_c[2 * (n + 64)]) +
+                    (INB(xi - (n + 128)) * c_sbr_qmf_c[2 * (n + 128)]) + (INB(xi - (n + 192)) * c_sbr_qmf_c[2 * (n + 192)]) +
+                    (INB(xi - (n + 256)) * c_sbr_qmf_c[2 * (n + 256)]);
+    // reordering of AnalysisFilterbank.java:40-47
+    if (n == 0) in_real[0] = u;
+    else if (n == 1) in_imag[31] = u;
+    else if (n <= 31) in_imag[32 - n] = u;
+    else if (n == 32) in_imag[0] = u;
+    else if (n == 33) in_real[31] = -u;
+    else in_real[64 - n] = -u;
+  }
+  sbr_dct4_kernel(in_real, in_imag, out_real, out_imag);
+  __syncwarp();   // every lane is done with the input samples: the region becomes the output stage
+  float* stage = inbuf + lane * 65;
+#pragma unroll
+  for (int n = 0; n < 16; n++) {
+    if (2 * n + 1 < kx) {
+      stage[4 * n] = 2.0f * out_real[n];
+      stage[4 * n + 1] = 2.0f * out_imag[n];
+      stage[4 * n + 2] = -2.0f * out_imag[31 - n];
+      stage[4 * n + 3] = -2.0f * out_real[31 - n];
+    } else {
+      if (2 * n < kx) { stage[4 * n] = 2.0f * out_real[n]; stage[4 * n + 1] = 2.0f * out_imag[n]; }
+      else { stage[4 * n] = 0; stage[4 * n + 1] = 0; }
+      stage[4 * n + 2] = 0;
+      stage[4 * n + 3] = 0;
+    }
+  }
+  __syncwarp();
+  // rows 8..39 of the frame: the low band, and zeros above it (what the reference's fresh / shifted matrix holds there)
+  for (int row = 0; row < 32; ++row) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < 16) {
+      const float* s = inbuf + row * 65 + 4 * lane;
+      v = make_float4(s[0], s[1], s[2], s[3]);
+    }
+    reinterpret_cast<float4*>(X + (size_t)(kSbrHfGen + row) * kXgRow)[lane] = v;
+  }
+}
+
+// ---- K4b: HF generation (sbr/HFGeneration.java:17-245) + HF adjustment (sbr/HFAdjustment.java:20-415)
+constexpr int kK4bWarps = 4;
+constexpr int kK4bMaxNL = 32;
+constexpr int kK4bPwCols = 50;   // >= SBR.MAX_M, even
+struct K4bGain {
+  float G[kSbrMaxLE][64], Q[kSbrMaxLE][64], S[kSbrMaxLE][64];   // G_lim_boost, Q_M_lim_boost, S_M_boost (contiguous)
+  float gmax[kSbrMaxLE][kK4bMaxNL], acc1[kSbrMaxLE][kK4bMaxNL], boost[kSbrMaxLE][kK4bMaxNL];
+  uint8_t rb[2][64];             // band of f_table_res[res] that holds k = m + kx
+  uint8_t nb[64], lb[64];        // noise-floor band, limiter band
+  uint8_t sflag[kSbrMaxLE][64];  // S_index_mapped != 0
+};
+struct __align__(16) K4bSmem {
+  SbrFrameDev fp;
+  float E_curr[kSbrMaxLE][64];
+  union {
+    K4bGain g;                   // calculate_gain's working set
+    float pw[38][kK4bPwCols];    // before that: |X|^2 of the generated band samples, [slot][m] (estimate_current_envelope)
+  };
+  float eband[64];               // envelope energy per frequency band (bs_interpol_freq == 0)
+  float bw[8];
+  float ringG[5][64], ringQ[5][64];   // G_temp_prev / Q_temp_prev: the smoothing ring, by ring position
+};
+constexpr size_t k4b_smem_bytes() { return sizeof(K4bSmem) * kK4bWarps; }
+
+__global__ void __launch_bounds__(32 * kK4bWarps)
+k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrameDev* __restrict__ run_frames,
+              const SbrFrameDev* __restrict__ sframes, const float* __restrict__ core, SbrChanDev* __restrict__ chans,
+              float* xg, SbrTablesDev T, K4Tile tile) {
+  extern __shared__ __align__(16) uint8_t k4b_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t r = blockIdx.x * kK4bWarps + warp;
+  if (r >= n_runs) return;
+  K4bSmem& W = reinterpret_cast<K4bSmem*>(k4b_raw)[warp];
+  const K4RunDev run = runs[r];
+  if (tile.lo >= run.count) return;
+  const uint32_t hi = min(run.count, tile.lo + tile.ft);
+  SbrChanDev* st = chans + (size_t)run.stream_slot * kSbrChansPerStream + run.ch_slot;
+  float* Xrun = xg + (size_t)r * tile.rows * kXgRow;
+
+  // ---- recursive state in: the smoothing ring, chirp factors (lanes < 8), phases
+  for (int i = lane; i < 5 * 64; i += 32) { (&W.ringG[0][0])[i] = (&st->G_temp_prev[0][0])[i]; (&W.ringQ[0][0])[i] = (&st->Q_temp_prev[0][0])[i]; }
   int ring_index = st->GQ_ringbuf_index;
   int index_noise_prev = st->index_noise_prev, psi_is_prev = st->psi_is_prev;
   float bw_prev = 0.f;
   int invf_prev = 0;
-  if (t < 8) { bw_prev = st->bwArray_prev[t]; invf_prev = st->bs_invf_mode_prev[t]; }
-  float qc[10];
-#pragma unroll
-  for (int j = 0; j < 10; ++j) qc[j] = T.qmf_c[t + 64 * j];
-  PsChanDev* pst = nullptr;
-  if (WITH_PS) {
-    pst = ps_chans + run.stream_slot;
-    for (int i = t; i < 9 * 128; i += kK4Threads) vhr[(8 - i / 128) * kVbStride + (i % 128)] = pst->syn_v_right[i / 128][i % 128];
-  }
-  __syncthreads();
+  if (lane < 8) { bw_prev = st->bwArray_prev[lane]; invf_prev = st->bs_invf_mode_prev[lane]; }
 
-  for (uint32_t it = 0; it < run.count; ++it) {
-    const RunFrameDev rf = run_frames[run.first + it];
-    const uint32_t f = rf.frame;
-    // frame record + core PCM -> shared
+  uint32_t n_done = 0;   // processed frames of the tile so far
+  int64_t last_it = -1;
+  const SbrFrameDev* fp = &W.fp;
+  // the frame records are fetched one frame ahead
+  constexpr int kRecVec = (int)(sizeof(SbrFrameDev) / 16);
+  uint4 rec[4];
+  auto fetch_record = [&](uint32_t it2) {
+    const uint4* src = reinterpret_cast<const uint4*>(k4_frame(sframes, run, it2));
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (lane + 32 * u < kRecVec) rec[u] = __ldg(src + lane + 32 * u);
+  };
+  fetch_record(tile.lo);
+  for (uint32_t it = tile.lo; it < hi; ++it) {
+    __syncwarp();
     {
-      const uint4* src = reinterpret_cast<const uint4*>(sframes + ((size_t)run.sbr_base + it) * 2 + run.chan);
-      uint4* dst = reinterpret_cast<uint4*>(fp);
-      for (int i = t; i < (int)(sizeof(SbrFrameDev) / 16); i += kK4Threads) dst[i] = src[i];
-      if (WITH_PS) {
-        const uint4* psrc = reinterpret_cast<const uint4*>(ps_frames + run.ps_base + it);
-        if (t < (int)(sizeof(PsFrameDev) / 16)) reinterpret_cast<uint4*>(pp)[t] = psrc[t];
-      }
-      const float4* cs = reinterpret_cast<const float4*>(core + ((size_t)rf.ics_base + run.ch_slot) * 1024);
-      for (int i = t; i < 256; i += kK4Threads) {
-        const float4 v = cs[i];
-        INB(288 + 4 * i) = v.x; INB(288 + 4 * i + 1) = v.y; INB(288 + 4 * i + 2) = v.z; INB(288 + 4 * i + 3) = v.w;
-      }
+      uint4* dst = reinterpret_cast<uint4*>(&W.fp);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (lane + 32 * u < kRecVec) dst[lane + 32 * u] = rec[u];
     }
-    __syncthreads();
+    if (it + 1 < hi) fetch_record(it + 1);
+    __syncwarp();
     const int mode = fp->mode;
-    uint8_t* dst = pcm + pcm_off[f];
-    const int n_out = run.n_out;
-    if (fp->frame_status != 0) {
-      if (t == 0 && run.out_ch == 0) pcm_bytes_out[f] = 0;
-      __syncthreads();
-      continue;
-    }
-    const bool use_ps = WITH_PS && mode != 0 && pp->use_ps != 0;
-    // och: output channel; dup: also write the next channel (mono element without parametric stereo in this frame)
-    auto put_sample_to = [&](int i, float v, int och, bool dup) {
-      if (PCM_FORMAT == 2) {
-        float* d = reinterpret_cast<float*>(dst);
-        d[(size_t)och * 2048 + i] = v;
-        if (dup) d[(size_t)(och + 1) * 2048 + i] = v;
-      } else {
-        uint32_t u = (uint32_t)pcm_round(v) & 0xFFFFu;
-        if (PCM_FORMAT == 1) u = __byte_perm(u, 0, 0x4401);
-        uint16_t* d = reinterpret_cast<uint16_t*>(dst);
-        d[(size_t)i * n_out + och] = (uint16_t)u;
-        if (dup) d[(size_t)i * n_out + och + 1] = (uint16_t)u;
+    if (fp->frame_status != 0 || mode == 0) continue;
+    float* X = Xrun + 32 * (size_t)n_done * kXgRow;   // row 0 of this frame's Xsbr
+    ++n_done;
+    last_it = it;
+    if (mode != 2) continue;
+    const int kx = fp->kx, M = fp->M, L_E = fp->L_E;
+    // (borders beyond the matrix can only come from a damaged grid, where the reference dies with an index error; the
+    // clamps keep the accesses inside the tile)
+    const int first_slot = min((int)fp->t_E[0], 38), last_slot = min((int)fp->t_E[L_E], 38);
+    bool grid_sorted = true;
+    for (int l = 0; l < L_E; ++l) grid_sorted = grid_sorted && fp->t_E[l + 1] >= fp->t_E[l] && fp->t_E[l + 1] <= 38;
+    // the frequency-band tables are strictly increasing from kx to at most kx + M (anything else takes the literal walks)
+    bool res_regular;
+    {
+      bool bad = fp->N_low < 1 || fp->N_high < 1 || fp->f_table_res[0][0] != kx || fp->f_table_res[1][0] != kx ||
+                 fp->f_table_res[0][fp->N_low] > kx + M || fp->f_table_res[1][fp->N_high] > kx + M || M > kK4bPwCols;
+      for (int i = lane; i < 64; i += 32) {
+        if (i < fp->N_low && fp->f_table_res[0][i + 1] <= fp->f_table_res[0][i]) bad = true;
+        if (i < fp->N_high && fp->f_table_res[1][i + 1] <= fp->f_table_res[1][i]) bad = true;
       }
-    };
-    auto put_sample = [&](int i, float v) { put_sample_to(i, v, run.out_ch, run.dup != 0 && !use_ps); };
-    if (t == 0 && run.out_ch == 0) pcm_bytes_out[f] = (uint32_t)(2048 * n_out * (PCM_FORMAT == 2 ? 4 : 2));
-
-    if (mode == 0) {
-      // no valid SBR data in this frame: SBR.upsample (sbr/SBR.java:302-309; sample 1 keeps the core value)
-      for (int i = t; i < 2048; i += kK4Threads) put_sample(i, i < 2 ? INB(288 + i) : INB(288 + (i >> 1)));
-      __syncthreads();
-      continue;
+      res_regular = !__any_sync(0xFFFFFFFFu, bad);
     }
-
-    const int kx = mode == 2 ? fp->kx : 32;
-    // ---- 32-band QMF analysis: thread l < 32 computes time slot l
-    if (t < 32) {
-      const int xi = 288 + 32 * t + 31;   // newest sample of the slot; sample xi - j = v[v_index + j] of the reference
-      float in_real[32], in_imag[32], out_real[32], out_imag[32];
-#pragma unroll
-      for (int n = 0; n < 64; ++n) {
-        const float u = (INB(xi - n) * c_sbr_qmf_c[2 * n]) + (INB(xi - (n + 64)) * c_sbr_qmf_c[2 * (n + 64)]) +
-                        (INB(xi - (n + 128)) * c_sbr_qmf_c[2 * (n + 128)]) + (INB(xi - (n + 192)) * c_sbr_qmf_c[2 * (n + 192)]) +
-                        (INB(xi - (n + 256)) * c_sbr_qmf_c[2 * (n + 256)]);
-        // reordering of AnalysisFilterbank.java:40-47
-        if (n == 0) in_real[0] = u;
-        else if (n == 1) in_imag[31] = u;
-        else if (n <= 31) in_imag[32 - n] = u;          // in_imag[31-(n-1)] = u[n]
-        else if (n == 32) in_imag[0] = u;
-        else if (n == 33) in_real[31] = -u;
-        else in_real[64 - n] = -u;                      // in_real[m] = -u[64-m], m = 1..30
-      }
-      sbr_dct4_kernel(in_real, in_imag, out_real, out_imag);
-      const int xrow = t + kSbrHfGen;
-#pragma unroll
-      for (int n = 0; n < 16; n++) {
-        if (2 * n + 1 < kx) {
-          XS(xrow, 2 * n, 0) = 2.0f * out_real[n];
-          XS(xrow, 2 * n, 1) = 2.0f * out_imag[n];
-          XS(xrow, 2 * n + 1, 0) = -2.0f * out_imag[31 - n];
-          XS(xrow, 2 * n + 1, 1) = -2.0f * out_real[31 - n];
-        } else {
-          if (2 * n < kx) { XS(xrow, 2 * n, 0) = 2.0f * out_real[n]; XS(xrow, 2 * n, 1) = 2.0f * out_imag[n]; }
-          else { XS(xrow, 2 * n, 0) = 0; XS(xrow, 2 * n, 1) = 0; }
-          XS(xrow, 2 * n + 1, 0) = 0;
-          XS(xrow, 2 * n + 1, 1) = 0;
+    const bool pw_ok = grid_sorted && res_regular;
+    // calc_chirp_factors (HFGeneration.java:230-245): lane i < N_Q
+    if (lane < 8) {
+      float bw = 0.f;
+      if (lane < fp->N_Q) {
+        const int mode_i = fp->bs_invf_mode[lane];
+        switch (mode_i) {
+          case 1: bw = (invf_prev == 0) ? 0.6f : 0.75f; break;
+          case 2: bw = 0.9f; break;
+          case 3: bw = 0.98f; break;
+          default: bw = (invf_prev == 1) ? 0.6f : 0.0f; break;
         }
+        if (bw < bw_prev) bw = (bw * 0.75f) + (bw_prev * 0.25f);
+        else bw = (bw * 0.90625f) + (bw_prev * 0.09375f);
+        if (bw < 0.015625f) bw = 0.0f;
+        if (bw >= 0.99609375f) bw = 0.99609375f;
+        bw_prev = bw;
+        invf_prev = mode_i;
       }
+      W.bw[lane] = bw;
     }
-    __syncthreads();
-
-    int first_slot = 0;   // t_E[0]
-    if (mode == 2) {
-      const int L_E = fp->L_E, M = fp->M;
-      first_slot = fp->t_E[0];
-      const int last_slot = fp->t_E[L_E];
-      // ---- HF generation (HFGeneration.java)
-      // calc_chirp_factors (:230-245): thread i < N_Q
-      if (t < 8) {
-        float bw = 0.f;
-        if (t < fp->N_Q) {
-          const int mode_i = fp->bs_invf_mode[t];
-          switch (mode_i) {
-            case 1: bw = (invf_prev == 0) ? 0.6f : 0.75f; break;
-            case 2: bw = 0.9f; break;
-            case 3: bw = 0.98f; break;
-            default: bw = (invf_prev == 1) ? 0.6f : 0.0f; break;
-          }
-          if (bw < bw_prev) bw = (bw * 0.75f) + (bw_prev * 0.25f);
-          else bw = (bw * 0.90625f) + (bw_prev * 0.09375f);
-          if (bw < 0.015625f) bw = 0.0f;
-          if (bw >= 0.99609375f) bw = 0.99609375f;
-          bw_prev = bw;
-          invf_prev = mode_i;
-        }
-        s_bw[t] = bw;
+    __syncwarp();
+    // ---- HF generation: one lane per generated band (band x of the concatenated patches).  Loops run in blocks of four
+    // slots whose loads are issued together (the next block's while the current one is worked on), rolled to stay small.
+    // |X|^2 of every generated sample is left in W.pw for the envelope estimate.
+    uint32_t not_generated = 0;   // bit pass: band lane + 32 * pass < M was not produced by any patch
+#pragma unroll 1
+    for (int x0 = 0; kx + x0 < 64; x0 += 32) {
+      const int k = kx + x0 + lane;
+      int i = 0, x = x0 + lane;
+      while (i < fp->noPatches && x >= fp->patchNoSubbands[i]) { x -= fp->patchNoSubbands[i]; ++i; }
+      if (k >= 64 || i >= fp->noPatches) {
+        if (k < kx + M) not_generated |= 1u << (x0 >> 5);
+        continue;
       }
-      __syncthreads();
-      // one thread per generated band: band x of the concatenated patches
-      if (kx + t < 64) {
-        int i = 0, x = t, k = kx + t;
-        while (i < fp->noPatches && x >= fp->patchNoSubbands[i]) { x -= fp->patchNoSubbands[i]; ++i; }
-        if (i < fp->noPatches) {
-          const int p = fp->patchStartSubband[i] + x;
-          const int g = fp->table_map_k_to_g[k];
-          const float bw = s_bw[g];
-          const float bw2 = bw * bw;
-          const int offset = kSbrHfAdj;
-          if (bw2 > 0) {
-            // calc_prediction_coef / auto_correlation (:100-204), len = numTimeSlotsRate + 6
-            float r01r = 0, r01i = 0, r02r = 0, r02i = 0, r11r = 0;
-            float temp1_r, temp1_i, temp2_r, temp2_i, temp3_r, temp3_i, temp4_r, temp4_i, temp5_r, temp5_i;
-            const float rel = 1.0f / (1 + 1e-6f);
-            temp2_r = XS(offset - 2, p, 0); temp2_i = XS(offset - 2, p, 1);
-            temp3_r = XS(offset - 1, p, 0); temp3_i = XS(offset - 1, p, 1);
-            temp4_r = temp2_r; temp4_i = temp2_i; temp5_r = temp3_r; temp5_i = temp3_i;
-            temp1_r = 0; temp1_i = 0;
-            for (int j = offset; j < kSbrSlots + 6 + offset; j++) {
+      const int p = fp->patchStartSubband[i] + x;
+      const float bw = W.bw[fp->table_map_k_to_g[k]];
+      const float bw2 = bw * bw;
+      const int offset = kSbrHfAdj;
+      const float* src = X + 2 * p;     // the source band is never written by this kernel
+      float* dst = X + 2 * k;
+      auto ld_src = [&](int row) -> float2 { return __ldg(reinterpret_cast<const float2*>(src + min(row, 39) * kXgRow)); };
+      float a0_r = 0, a1_r = 0, a0_i = 0, a1_i = 0;
+      if (bw2 > 0) {
+        // calc_prediction_coef / auto_correlation (:100-204), len = numTimeSlotsRate + 6
+        float r01r = 0, r01i = 0, r02r = 0, r02i = 0, r11r = 0;
+        float temp1_r, temp1_i, temp2_r, temp2_i, temp3_r, temp3_i, temp4_r, temp4_i, temp5_r, temp5_i;
+        const float rel = 1.0f / (1 + 1e-6f);
+        float2 v = ld_src(offset - 2);
+        temp2_r = v.x; temp2_i = v.y;
+        v = ld_src(offset - 1);
+        temp3_r = v.x; temp3_i = v.y;
+        temp4_r = temp2_r; temp4_i = temp2_i; temp5_r = temp3_r; temp5_i = temp3_i;
+        temp1_r = 0; temp1_i = 0;
+        float2 nxt[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nxt[u] = ld_src(offset + u);
+#pragma unroll 1
+        for (int j0 = offset; j0 < kSbrSlots + 6 + offset; j0 += 4) {
+          float2 cur[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { cur[u] = nxt[u]; nxt[u] = ld_src(j0 + 4 + u); }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (j0 + u < kSbrSlots + 6 + offset) {
               temp1_r = temp2_r; temp1_i = temp2_i;
               temp2_r = temp3_r; temp2_i = temp3_i;
-              temp3_r = XS(j, p, 0); temp3_i = XS(j, p, 1);
+              temp3_r = cur[u].x; temp3_i = cur[u].y;
               r01r += temp3_r * temp2_r + temp3_i * temp2_i;
               r01i += temp3_i * temp2_r - temp3_r * temp2_i;
               r02r += temp3_r * temp1_r + temp3_i * temp1_i;
               r02i += temp3_i * temp1_r - temp3_r * temp1_i;
               r11r += temp2_r * temp2_r + temp2_i * temp2_i;
             }
-            const float r12r = r01r - (temp3_r * temp2_r + temp3_i * temp2_i) + (temp5_r * temp4_r + temp5_i * temp4_i);
-            const float r12i = r01i - (temp3_i * temp2_r - temp3_r * temp2_i) + (temp5_i * temp4_r - temp5_r * temp4_i);
-            const float r22r = r11r - (temp2_r * temp2_r + temp2_i * temp2_i) + (temp4_r * temp4_r + temp4_i * temp4_i);
-            const float det = (r11r * r22r) - (rel * ((r12r * r12r) + (r12i * r12i)));
-            float al0r, al0i, al1r, al1i;
-            if (det == 0) { al1r = 0; al1i = 0; }
-            else {
-              const float tmp = 1.0f / det;
-              al1r = ((r01r * r12r) - (r01i * r12i) - (r02r * r11r)) * tmp;
-              al1i = ((r01i * r12r) + (r01r * r12i) - (r02i * r11r)) * tmp;
-            }
-            if (r11r == 0) { al0r = 0; al0i = 0; }
-            else {
-              const float tmp = 1.0f / r11r;
-              al0r = -(r01r + (al1r * r12r) + (al1i * r12i)) * tmp;
-              al0i = -(r01i + (al1i * r12r) - (al1r * r12i)) * tmp;
-            }
-            if (((al0r * al0r) + (al0i * al0i) >= 16.0f) || ((al1r * al1r) + (al1i * al1i) >= 16.0f)) { al0r = 0; al0i = 0; al1r = 0; al1i = 0; }
-            const float a0_r = (al0r * bw), a1_r = (al1r * bw2), a0_i = (al0i * bw), a1_i = (al1i * bw2);
-            temp2_r = XS(first_slot - 2 + offset, p, 0); temp3_r = XS(first_slot - 1 + offset, p, 0);
-            temp2_i = XS(first_slot - 2 + offset, p, 1); temp3_i = XS(first_slot - 1 + offset, p, 1);
-            for (int l = first_slot; l < last_slot; l++) {
-              temp1_r = temp2_r; temp2_r = temp3_r; temp3_r = XS(l + offset, p, 0);
-              temp1_i = temp2_i; temp2_i = temp3_i; temp3_i = XS(l + offset, p, 1);
-              XS(l + offset, k, 0) = temp3_r + ((a0_r * temp2_r) - (a0_i * temp2_i) + (a1_r * temp1_r) - (a1_i * temp1_i));
-              XS(l + offset, k, 1) = temp3_i + ((a0_i * temp2_r) + (a0_r * temp2_i) + (a1_i * temp1_r) + (a1_r * temp1_i));
-            }
-          } else {
-            for (int l = first_slot; l < last_slot; l++) {
-              XS(l + offset, k, 0) = XS(l + offset, p, 0);
-              XS(l + offset, k, 1) = XS(l + offset, p, 1);
-            }
+          }
+        }
+        const float r12r = r01r - (temp3_r * temp2_r + temp3_i * temp2_i) + (temp5_r * temp4_r + temp5_i * temp4_i);
+        const float r12i = r01i - (temp3_i * temp2_r - temp3_r * temp2_i) + (temp5_i * temp4_r - temp5_r * temp4_i);
+        const float r22r = r11r - (temp2_r * temp2_r + temp2_i * temp2_i) + (temp4_r * temp4_r + temp4_i * temp4_i);
+        const float det = (r11r * r22r) - (rel * ((r12r * r12r) + (r12i * r12i)));
+        float al0r, al0i, al1r, al1i;
+        if (det == 0) { al1r = 0; al1i = 0; }
+        else {
+          const float tmp = 1.0f / det;
+          al1r = ((r01r * r12r) - (r01i * r12i) - (r02r * r11r)) * tmp;
+          al1i = ((r01i * r12r) + (r01r * r12i) - (r02i * r11r)) * tmp;
+        }
+        if (r11r == 0) { al0r = 0; al0i = 0; }
+        else {
+          const float tmp = 1.0f / r11r;
+          al0r = -(r01r + (al1r * r12r) + (al1i * r12i)) * tmp;
+          al0i = -(r01i + (al1i * r12r) - (al1r * r12i)) * tmp;
+        }
+        if (((al0r * al0r) + (al0i * al0i) >= 16.0f) || ((al1r * al1r) + (al1i * al1i) >= 16.0f)) { al0r = 0; al0i = 0; al1r = 0; al1i = 0; }
+        a0_r = (al0r * bw); a1_r = (al1r * bw2); a0_i = (al0i * bw); a1_i = (al1i * bw2);
+      }
+      // patch the band (:60-97)
+      const bool keep_pw = k - kx < kK4bPwCols;
+      float2 t2 = ld_src(first_slot - 2 + offset), t3 = ld_src(first_slot - 1 + offset);
+      float2 nxt[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nxt[u] = ld_src(first_slot + u + offset);
+#pragma unroll 1
+      for (int l0 = first_slot; l0 < last_slot; l0 += 4) {
+        float2 cur[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { cur[u] = nxt[u]; nxt[u] = ld_src(l0 + 4 + u + offset); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int l = l0 + u;
+          if (l < last_slot) {
+            const float2 t1 = t2;
+            t2 = t3;
+            t3 = cur[u];
+            float o0, o1;
+            if (bw2 > 0) {
+              o0 = t3.x + ((a0_r * t2.x) - (a0_i * t2.y) + (a1_r * t1.x) - (a1_i * t1.y));
+              o1 = t3.y + ((a0_i * t2.x) + (a0_r * t2.y) + (a1_i * t1.x) + (a1_r * t1.y));
+            } else { o0 = t3.x; o1 = t3.y; }
+            st2(dst + (l + offset) * kXgRow, o0, o1);
+            if (keep_pw) W.pw[l][k - kx] = (o0 * o0) + (o1 * o1);
           }
         }
       }
-      __syncthreads();
+    }
+    __syncwarp();
 
-      // ---- HF adjustment (HFAdjustment.java)
-      // `new HFAdjustment()` per call: the boost arrays start from zero.  The limiter table does not always reach M
-      // (FBT.limiter_frequency_table sorts a shrinking prefix), and bands it leaves out keep gain 0.
-      for (int i = t; i < 3 * kSbrMaxLE * 64; i += kK4Threads) adj[i] = 0.f;
-      // estimate_current_envelope (:78-131): thread m
-      if (t < M) {
+    // ---- HF adjustment (HFAdjustment.java)
+    // estimate_current_envelope (:78-131).  With a sorted grid every sample it reads was produced just above and its
+    // |X|^2 sits in W.pw; the sums below add the same terms in the same order as the reference.
+    if (pw_ok) {
+      if (__any_sync(0xFFFFFFFFu, not_generated != 0)) {
+        // bands inside [kx, kx + M) that no patch covers keep whatever the matrix holds there
+        for (int m = lane; m < M; m += 32)
+          if ((not_generated >> (m >> 5)) & 1u)
+            for (int sl = first_slot; sl < last_slot; ++sl) {
+              const float2 v = ldg2(X + (size_t)(sl + kSbrHfAdj) * kXgRow + 2 * (m + kx));
+              W.pw[sl][m] = (v.x * v.x) + (v.y * v.y);
+            }
+        __syncwarp();
+      }
+      for (int l = 0; l < L_E; l++) {
+        const int l_i = fp->t_E[l], u_i = fp->t_E[l + 1];
+        if (fp->interpol_freq) {
+          float div = (float)(u_i - l_i);
+          if (div == 0) div = 1;
+          for (int m = lane; m < M; m += 32) {
+            float nrg = 0;
+            for (int sl = l_i; sl < u_i; ++sl) nrg += W.pw[sl][m];
+            W.E_curr[l][m] = nrg / div;
+          }
+        } else {
+          // one sum per frequency band of the envelope's resolution, taken by the lane of the band's first m
+          const int res = fp->f[l], nb = res ? fp->N_high : fp->N_low;
+          int pb[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int m = lane + 32 * q;
+            int pp = 0;
+            while (pp + 1 < nb && fp->f_table_res[res][pp + 1] <= m + kx) ++pp;
+            pb[q] = pp;
+          }
+          const int up0 = __shfl_up_sync(0xFFFFFFFFu, pb[0], 1), up1 = __shfl_up_sync(0xFFFFFFFFu, pb[1], 1);
+          const int last0 = __shfl_sync(0xFFFFFFFFu, pb[0], 31);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int m = lane + 32 * q;
+            const int before = q == 0 ? (lane == 0 ? -1 : up0) : (lane == 0 ? last0 : up1);   // the band of m - 1
+            if (m < M && before != pb[q]) {
+              const int k_l = fp->f_table_res[res][pb[q]], k_h = fp->f_table_res[res][pb[q] + 1];
+              float div = (float)((u_i - l_i) * (k_h - k_l));
+              if (div == 0) div = 1;
+              float nrg = 0;
+              for (int sl = l_i; sl < u_i; ++sl)
+                for (int j = k_l; j < k_h; j++) nrg += W.pw[sl][j - kx];
+              W.eband[pb[q]] = nrg / div;
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int m = lane + 32 * q;
+            if (m < M) W.E_curr[l][m] = W.eband[pb[q]];
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      for (int m = lane; m < M; m += 32) {
         for (int l = 0; l < L_E; l++) {
-          const int l_i = fp->t_E[l], u_i = fp->t_E[l + 1];
+          const int l_i = fp->t_E[l], u_i = min((int)fp->t_E[l + 1], 38);
           float nrg = 0, div;
           if (fp->interpol_freq) {
             div = (float)(u_i - l_i);
             if (div == 0) div = 1;
-            for (int i = l_i + kSbrHfAdj; i < u_i + kSbrHfAdj; i++)
-              nrg += (XS(i, t + kx, 0) * XS(i, t + kx, 0)) + (XS(i, t + kx, 1) * XS(i, t + kx, 1));
+            const float* col = X + 2 * (m + kx);
+            for (int i = l_i + kSbrHfAdj; i < u_i + kSbrHfAdj; i++) {
+              const float2 v = ldg2(col + i * kXgRow);
+              nrg += (v.x * v.x) + (v.y * v.y);
+            }
           } else {
-            // the band of the envelope's resolution that holds k = t + kx
+            // the band of the envelope's resolution that holds k = m + kx
             const int res = fp->f[l], nb = res ? fp->N_high : fp->N_low;
-            int p = 0;
-            while (p + 1 < nb && fp->f_table_res[res][p + 1] <= t + kx) ++p;
-            const int k_l = fp->f_table_res[res][p], k_h = fp->f_table_res[res][p + 1];
+            int pp = 0;
+            while (pp + 1 < nb && fp->f_table_res[res][pp + 1] <= m + kx) ++pp;
+            const int k_l = fp->f_table_res[res][pp], k_h = fp->f_table_res[res][pp + 1];
             div = (float)((u_i - l_i) * (k_h - k_l));
             if (div == 0) div = 1;
             for (int i = l_i + kSbrHfAdj; i < u_i + kSbrHfAdj; i++)
-              for (int j = k_l; j < k_h; j++) nrg += (XS(i, j, 0) * XS(i, j, 0)) + (XS(i, j, 1) * XS(i, j, 1));
-          }
-          E_curr[l][t] = nrg / div;
-        }
-      }
-      __syncthreads();
-      // calculate_gain (:242-415): thread l < L_E runs its envelope
-      if (t < L_E) {
-        const int l = t;
-        const float EPS = 1e-12f;
-        const int l_A = fp->l_A;
-        const int res = fp->f[l];
-        const bool flag_prev = fp->add_harmonic_flag_prev != 0;
-        auto get_S_mapped = [&](int current_band) -> int {   // :46-76
-          if (res == SBR_HI_RES) {
-            if ((l >= l_A) || (fp->bs_add_harmonic_prev[current_band] != 0 && flag_prev)) return fp->bs_add_harmonic[current_band];
-          } else {
-            const int odd = (fp->N_high & 1) ? 1 : 0;
-            const int lb = 2 * current_band - odd, ub = 2 * (current_band + 1) - odd;
-            for (int b = max(lb, 0); b < ub && b < 64; b++)
-              if ((l >= l_A) || (fp->bs_add_harmonic_prev[b] != 0 && flag_prev)) { if (fp->bs_add_harmonic[b] == 1) return 1; }
-          }
-          return 0;
-        };
-        // the noise-floor time band of envelope l: current_t_noise_band advances once per envelope whose end passes t_Q
-        int current_t_noise_band = 0;
-        for (int ll = 0; ll <= l; ++ll)
-          if (fp->t_E[ll + 1] > fp->t_Q[current_t_noise_band + 1]) current_t_noise_band++;
-        int current_f_noise_band = 0, current_res_band = 0, current_res_band2 = 0, current_hi_res_band = 0;
-        const float delta = (l == l_A || l == fp->prevEnvIsShort) ? 0.f : 1.f;
-        int S_mapped = get_S_mapped(current_res_band2);
-        float limg;
-        switch (fp->limiter_gains) { case 0: limg = 0.5f; break; case 1: limg = 1.0f; break; case 2: limg = 2.0f; break; default: limg = 1e10f; break; }
-        for (int k = 0; k < fp->N_L; k++) {
-          float den = 0, acc1 = 0, acc2 = 0;
-          const int ml1 = fp->f_table_lim[k], ml2 = fp->f_table_lim[k + 1];
-          for (int m = ml1; m < ml2; m++) {
-            if ((m + kx) == fp->f_table_res[res][current_res_band + 1]) current_res_band++;
-            acc1 += fp->E_orig[l][current_res_band];
-            acc2 += E_curr[l][m];
-          }
-          float G_max = ((EPS + acc1) / (EPS + acc2)) * limg;
-          G_max = fminf(G_max, 1e10f);
-          for (int m = ml1; m < ml2; m++) {
-            if ((m + kx) == fp->f_table_noise[current_f_noise_band + 1]) current_f_noise_band++;
-            if ((m + kx) == fp->f_table_res[res][current_res_band2 + 1]) {
-              current_res_band2++;
-              S_mapped = get_S_mapped(current_res_band2);
-            }
-            if ((m + kx) == fp->f_table_res[SBR_HI_RES][current_hi_res_band + 1]) current_hi_res_band++;
-            int S_index_mapped = 0;
-            if ((l >= l_A) || (fp->bs_add_harmonic_prev[current_hi_res_band] != 0 && flag_prev)) {
-              if ((m + kx) == (fp->f_table_res[SBR_HI_RES][current_hi_res_band + 1] + fp->f_table_res[SBR_HI_RES][current_hi_res_band]) >> 1)
-                S_index_mapped = fp->bs_add_harmonic[current_hi_res_band];
-            }
-            const float Q_div = fp->Q_div[current_t_noise_band][current_f_noise_band];
-            const float Q_div2 = fp->Q_div2[current_t_noise_band][current_f_noise_band];
-            const float E_o = fp->E_orig[l][current_res_band2];
-            const float Q_M = E_o * Q_div2;
-            float S_M;
-            if (S_index_mapped == 0) S_M = 0;
-            else { S_M = E_o * Q_div; den += S_M; }
-            float G = E_o / (1.0f + E_curr[l][m]);
-            if ((S_mapped == 0) && (delta == 1)) G *= Q_div;
-            else if (S_mapped == 1) G *= Q_div2;
-            float Q_M_lim, G_lim;
-            if (G_max > G) { Q_M_lim = Q_M; G_lim = G; }
-            else { Q_M_lim = Q_M * G_max / G; G_lim = G_max; }
-            den += E_curr[l][m] * G_lim;
-            if ((S_index_mapped == 0) && (l != l_A)) den += Q_M_lim;
-            // park the un-boosted values; the boost needs the whole limiter band's `den`
-            G_lim_boost[l][m] = G_lim;
-            Q_M_lim_boost[l][m] = Q_M_lim;
-            S_M_boost[l][m] = S_M;
-          }
-          float G_boost = (acc1 + EPS) / (den + EPS);
-          G_boost = fminf(G_boost, 2.51188643f);
-          for (int m = ml1; m < ml2; m++) {
-            // (float) Math.sqrt(float product): the double square root of a binary32 value, rounded to binary32, is the
-            // correctly rounded binary32 square root
-            G_lim_boost[l][m] = __fsqrt_rn(G_lim_boost[l][m] * G_boost);
-            Q_M_lim_boost[l][m] = __fsqrt_rn(Q_M_lim_boost[l][m] * G_boost);
-            const float sm = S_M_boost[l][m];
-            S_M_boost[l][m] = (sm != 0) ? __fsqrt_rn(sm * G_boost) : 0.f;
-          }
-        }
-      }
-      __syncthreads();
-      // hf_assembly (:133-240): thread m walks the slots; the 5-entry smoothing ring of its band lives in registers
-      {
-        const bool active = t < M;
-        int fIndexNoise = fp->reset ? 0 : index_noise_prev;
-        int fIndexSine = psi_is_prev;
-        bool assembly_reset = fp->reset != 0;
-        int slots_done = 0;
-        for (int l = 0; l < L_E; l++) {
-          const bool no_noise = (l == fp->l_A || l == fp->prevEnvIsShort);
-          int h_SL = fp->smoothing_mode ? 0 : 4;
-          h_SL = no_noise ? 0 : h_SL;
-          const float g_new = active ? G_lim_boost[l][t] : 0.f, q_new = active ? Q_M_lim_boost[l][t] : 0.f;
-          const float s_m = active ? S_M_boost[l][t] : 0.f;
-          // System.arraycopy(.., 0, .., 0, sbr.M): ring entries of bands >= M keep their old contents
-          if (assembly_reset) {
-            if (active) {
-#pragma unroll
-              for (int n = 0; n < 4; ++n) { Gt[n] = g_new; Qt[n] = q_new; }
-            }
-            ring_index = 4;
-            assembly_reset = false;
-          }
-          for (int i = fp->t_E[l]; i < fp->t_E[l + 1]; i++) {
-            if (active) {
-#pragma unroll
-              for (int n = 0; n < 5; ++n) if (n == ring_index) { Gt[n] = g_new; Qt[n] = q_new; }
-            }
-            float G_filt = 0, Q_filt = 0;
-            if (h_SL != 0) {
-              int ri = ring_index;
-#pragma unroll
-              for (int n = 0; n <= 4; n++) {
-                const float h = n == 0 ? 0.03183050093751f : n == 1 ? 0.11516383427084f : n == 2 ? 0.21816949906249f
-                              : n == 3 ? 0.30150283239582f : 0.33333333333333f;
-                ri++;
-                if (ri >= 5) ri -= 5;
-                float gv = Gt[0], qv = Qt[0];
-#pragma unroll
-                for (int z = 1; z < 5; ++z) if (z == ri) { gv = Gt[z]; qv = Qt[z]; }
-                G_filt += (gv * h);
-                Q_filt += (qv * h);
+              for (int j = k_l; j < k_h; j++) {
+                const float2 v = ldg2(X + i * kXgRow + 2 * j);
+                nrg += (v.x * v.x) + (v.y * v.y);
               }
-            } else {
+          }
+          W.E_curr[l][m] = nrg / div;
+        }
+      }
+    }
+    __syncwarp();
+    // `new HFAdjustment()` per call: the boost arrays start from zero; the limiter table does not always reach M
+    // (FBT.limiter_frequency_table sorts a shrinking prefix) and bands it leaves out keep gain 0.
+    for (int i = lane; i < 3 * kSbrMaxLE * 64; i += 32) (&W.g.G[0][0])[i] = 0.f;
+    __syncwarp();
+
+    // calculate_gain (:242-415)
+    const float EPS = 1e-12f;
+    const int l_A = fp->l_A;
+    const bool flag_prev = fp->add_harmonic_flag_prev != 0;
+    const int N_L = fp->N_L;
+    float limg;
+    switch (fp->limiter_gains) { case 0: limg = 0.5f; break; case 1: limg = 1.0f; break; case 2: limg = 2.0f; break; default: limg = 1e10f; break; }
+    auto get_S_mapped = [&](int l, int res, int current_band) -> int {   // :46-76
+      if (res == SBR_HI_RES) {
+        if ((l >= l_A) || (fp->bs_add_harmonic_prev[current_band] != 0 && flag_prev)) return fp->bs_add_harmonic[current_band];
+      } else {
+        const int odd = (fp->N_high & 1) ? 1 : 0;
+        const int lb = 2 * current_band - odd, ub = 2 * (current_band + 1) - odd;
+        for (int b = max(lb, 0); b < ub && b < 64; b++)
+          if ((l >= l_A) || (fp->bs_add_harmonic_prev[b] != 0 && flag_prev)) { if (fp->bs_add_harmonic[b] == 1) return 1; }
+      }
+      return 0;
+    };
+    auto t_noise_band = [&](int l) -> int {   // current_t_noise_band advances once per envelope whose end passes t_Q
+      int tb = 0;
+      for (int ll = 0; ll <= l; ++ll)
+        if (fp->t_E[ll + 1] > fp->t_Q[tb + 1]) tb++;
+      return tb;
+    };
+    // The reference walks m with running band counters; when every band table is strictly increasing and starts where
+    // it should, the counters equal plain lookups and the work splits over (envelope, band).  Anything else takes the
+    // literal walk below.
+    bool regular;
+    {
+      bool bad = N_L > kK4bMaxNL || N_L < 1 || !res_regular;
+      for (int i = lane; i < 64; i += 32) {
+        if (i < fp->N_Q && i < 7 && fp->f_table_noise[i + 1] <= fp->f_table_noise[i]) bad = true;
+        if (i < N_L && i < 63 && fp->f_table_lim[i + 1] <= fp->f_table_lim[i]) bad = true;
+      }
+      if (fp->f_table_noise[0] != kx || fp->f_table_lim[0] != 0) bad = true;
+      if (fp->N_Q > 7 || fp->N_Q < 1) bad = true;
+      if (N_L >= 1 && N_L <= kK4bMaxNL && fp->f_table_lim[N_L] > M) bad = true;
+      regular = !__any_sync(0xFFFFFFFFu, bad);
+    }
+    if (regular) {
+      const int mcov = fp->f_table_lim[N_L];
+      for (int m = lane; m < mcov; m += 32) {
+        const int k = m + kx;
+        int p = 0;
+        while (p + 1 < fp->N_low && fp->f_table_res[0][p + 1] <= k) ++p;
+        W.g.rb[0][m] = (uint8_t)p;
+        p = 0;
+        while (p + 1 < fp->N_high && fp->f_table_res[1][p + 1] <= k) ++p;
+        W.g.rb[1][m] = (uint8_t)p;
+        p = 0;
+        while (p + 1 < fp->N_Q && fp->f_table_noise[p + 1] <= k) ++p;
+        W.g.nb[m] = (uint8_t)p;
+        p = 0;
+        while (p + 1 < N_L && fp->f_table_lim[p + 1] <= m) ++p;
+        W.g.lb[m] = (uint8_t)p;
+      }
+      __syncwarp();
+      // limiter-band sums, in band order as the reference adds them
+      for (int task = lane; task < L_E * N_L; task += 32) {
+        const int l = task / N_L, kb = task - l * N_L, res = fp->f[l];
+        float acc1 = 0, acc2 = 0;
+        for (int m = fp->f_table_lim[kb]; m < fp->f_table_lim[kb + 1]; m++) {
+          acc1 += fp->E_orig[l][W.g.rb[res][m]];
+          acc2 += W.E_curr[l][m];
+        }
+        float G_max = ((EPS + acc1) / (EPS + acc2)) * limg;
+        G_max = fminf(G_max, 1e10f);
+        W.g.gmax[l][kb] = G_max;
+        W.g.acc1[l][kb] = acc1;
+      }
+      __syncwarp();
+      for (int m = lane; m < mcov; m += 32) {
+        const int k = m + kx;
+        const int hb = W.g.rb[1][m];
+        const bool centre = k == ((fp->f_table_res[SBR_HI_RES][hb + 1] + fp->f_table_res[SBR_HI_RES][hb]) >> 1);
+        for (int l = 0; l < L_E; ++l) {
+          const int res = fp->f[l];
+          const int rb = W.g.rb[res][m];
+          const int S_mapped = get_S_mapped(l, res, rb);
+          int S_index_mapped = 0;
+          if (((l >= l_A) || (fp->bs_add_harmonic_prev[hb] != 0 && flag_prev)) && centre) S_index_mapped = fp->bs_add_harmonic[hb];
+          const int tb = t_noise_band(l);
+          const float delta = (l == l_A || l == fp->prevEnvIsShort) ? 0.f : 1.f;
+          const float Q_div = fp->Q_div[tb][W.g.nb[m]];
+          const float Q_div2 = fp->Q_div2[tb][W.g.nb[m]];
+          const float E_o = fp->E_orig[l][rb];
+          const float Q_M = E_o * Q_div2;
+          const float S_M = (S_index_mapped == 0) ? 0.f : E_o * Q_div;
+          float G = E_o / (1.0f + W.E_curr[l][m]);
+          if ((S_mapped == 0) && (delta == 1)) G *= Q_div;
+          else if (S_mapped == 1) G *= Q_div2;
+          const float G_max = W.g.gmax[l][W.g.lb[m]];
+          float Q_M_lim, G_lim;
+          if (G_max > G) { Q_M_lim = Q_M; G_lim = G; }
+          else { Q_M_lim = Q_M * G_max / G; G_lim = G_max; }
+          W.g.G[l][m] = G_lim;
+          W.g.Q[l][m] = Q_M_lim;
+          W.g.S[l][m] = S_M;
+          W.g.sflag[l][m] = (uint8_t)(S_index_mapped != 0);
+        }
+      }
+      __syncwarp();
+      for (int task = lane; task < L_E * N_L; task += 32) {
+        const int l = task / N_L, kb = task - l * N_L;
+        float den = 0;
+        for (int m = fp->f_table_lim[kb]; m < fp->f_table_lim[kb + 1]; m++) {
+          const bool sf = W.g.sflag[l][m] != 0;
+          if (sf) den += W.g.S[l][m];
+          den += W.E_curr[l][m] * W.g.G[l][m];
+          if (!sf && (l != l_A)) den += W.g.Q[l][m];
+        }
+        float G_boost = (W.g.acc1[l][kb] + EPS) / (den + EPS);
+        G_boost = fminf(G_boost, 2.51188643f);
+        W.g.boost[l][kb] = G_boost;
+      }
+      __syncwarp();
+      for (int m = lane; m < mcov; m += 32) {
+        for (int l = 0; l < L_E; ++l) {
+          const float G_boost = W.g.boost[l][W.g.lb[m]];
+          // (float) Math.sqrt(float product): the double square root of a binary32 value, rounded to binary32, is the
+          // correctly rounded binary32 square root
+          W.g.G[l][m] = __fsqrt_rn(W.g.G[l][m] * G_boost);
+          W.g.Q[l][m] = __fsqrt_rn(W.g.Q[l][m] * G_boost);
+          const float sm = W.g.S[l][m];
+          W.g.S[l][m] = (sm != 0) ? __fsqrt_rn(sm * G_boost) : 0.f;
+        }
+      }
+    } else if (lane < L_E) {
+      // the reference's own loop, one lane per envelope
+      const int l = lane;
+      const int res = fp->f[l];
+      const int current_t_noise_band = t_noise_band(l);
+      int current_f_noise_band = 0, current_res_band = 0, current_res_band2 = 0, current_hi_res_band = 0;
+      const float delta = (l == l_A || l == fp->prevEnvIsShort) ? 0.f : 1.f;
+      int S_mapped = get_S_mapped(l, res, current_res_band2);
+      for (int k = 0; k < N_L; k++) {
+        float den = 0, acc1 = 0, acc2 = 0;
+        const int ml1 = fp->f_table_lim[k], ml2 = fp->f_table_lim[k + 1];
+        for (int m = ml1; m < ml2; m++) {
+          if ((m + kx) == fp->f_table_res[res][current_res_band + 1]) current_res_band++;
+          acc1 += fp->E_orig[l][current_res_band];
+          acc2 += W.E_curr[l][m];
+        }
+        float G_max = ((EPS + acc1) / (EPS + acc2)) * limg;
+        G_max = fminf(G_max, 1e10f);
+        for (int m = ml1; m < ml2; m++) {
+          if ((m + kx) == fp->f_table_noise[current_f_noise_band + 1]) current_f_noise_band++;
+          if ((m + kx) == fp->f_table_res[res][current_res_band2 + 1]) {
+            current_res_band2++;
+            S_mapped = get_S_mapped(l, res, current_res_band2);
+          }
+          if ((m + kx) == fp->f_table_res[SBR_HI_RES][current_hi_res_band + 1]) current_hi_res_band++;
+          int S_index_mapped = 0;
+          if ((l >= l_A) || (fp->bs_add_harmonic_prev[current_hi_res_band] != 0 && flag_prev)) {
+            if ((m + kx) == (fp->f_table_res[SBR_HI_RES][current_hi_res_band + 1] + fp->f_table_res[SBR_HI_RES][current_hi_res_band]) >> 1)
+              S_index_mapped = fp->bs_add_harmonic[current_hi_res_band];
+          }
+          const float Q_div = fp->Q_div[current_t_noise_band][current_f_noise_band];
+          const float Q_div2 = fp->Q_div2[current_t_noise_band][current_f_noise_band];
+          const float E_o = fp->E_orig[l][current_res_band2];
+          const float Q_M = E_o * Q_div2;
+          float S_M;
+          if (S_index_mapped == 0) S_M = 0;
+          else { S_M = E_o * Q_div; den += S_M; }
+          float G = E_o / (1.0f + W.E_curr[l][m]);
+          if ((S_mapped == 0) && (delta == 1)) G *= Q_div;
+          else if (S_mapped == 1) G *= Q_div2;
+          float Q_M_lim, G_lim;
+          if (G_max > G) { Q_M_lim = Q_M; G_lim = G; }
+          else { Q_M_lim = Q_M * G_max / G; G_lim = G_max; }
+          den += W.E_curr[l][m] * G_lim;
+          if ((S_index_mapped == 0) && (l != l_A)) den += Q_M_lim;
+          W.g.G[l][m] = G_lim;
+          W.g.Q[l][m] = Q_M_lim;
+          W.g.S[l][m] = S_M;
+        }
+        float G_boost = (acc1 + EPS) / (den + EPS);
+        G_boost = fminf(G_boost, 2.51188643f);
+        for (int m = ml1; m < ml2; m++) {
+          W.g.G[l][m] = __fsqrt_rn(W.g.G[l][m] * G_boost);
+          W.g.Q[l][m] = __fsqrt_rn(W.g.Q[l][m] * G_boost);
+          const float sm = W.g.S[l][m];
+          W.g.S[l][m] = (sm != 0) ? __fsqrt_rn(sm * G_boost) : 0.f;
+        }
+      }
+    }
+    __syncwarp();
+
+    // hf_assembly (:133-240): lane m walks the slots of its band.  The reference's 5-entry ring (written at
+    // GQ_ringbuf_index, read oldest to newest) is kept age-ordered in registers while a band is walked: A[0] = oldest ...
+    // A[4] = newest, and goes back to its ring positions afterwards.
+    {
+      const int fIndexNoise = fp->reset ? 0 : index_noise_prev;
+      const int ri0 = fp->reset ? 4 : ring_index;
+      int slots_total = 0;
+#pragma unroll 1
+      for (int m = lane; m < M; m += 32) {
+        // System.arraycopy(.., 0, .., 0, sbr.M) on a reset: positions 0..3 take the first envelope's values (bands < M only)
+        if (fp->reset) {
+          const float g0 = W.g.G[0][m], q0 = W.g.Q[0][m];
 #pragma unroll
-              for (int z = 0; z < 5; ++z) if (z == ring_index) { G_filt = Gt[z]; Q_filt = Qt[z]; }
+          for (int n = 0; n < 4; ++n) { W.ringG[n][m] = g0; W.ringQ[n][m] = q0; }
+        }
+        float Ag[5], Aq[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          int pos = ri0 + j;
+          if (pos >= 5) pos -= 5;
+          Ag[j] = W.ringG[pos][m];
+          Aq[j] = W.ringQ[pos][m];
+        }
+        int fIndexSine = psi_is_prev, slots_done = 0;
+        float* col = X + 2 * (m + kx);
+        const int rev = (((m + kx) & 1) != 0 ? -1 : 1);
+        // the reference's slot order: for every envelope l, slots t_E[l] .. t_E[l + 1] - 1; four at a time so that their
+        // loads are in flight together
+        int l = 0, i = fp->t_E[0];
+        auto env_end = [&](int e) -> int { return min((int)fp->t_E[e + 1], 38); };
+        while (l < L_E && i >= env_end(l)) { ++l; i = fp->t_E[min(l, kSbrMaxLE)]; }
+        int l_cached = -1;
+        float g_new = 0, q_new = 0, s_m = 0;
+        bool no_noise = false;
+        int h_SL = 0;
+        // block A is worked on while block B's loads are in flight
+        int al[4], ai[4], bl[4], bi[4];
+        float2 av[4], bv[4];
+        auto gather = [&](int (&gl)[4], int (&gi)[4], float2 (&gv)[4]) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            gl[u] = l < L_E ? l : -1;
+            gi[u] = i;
+            if (l < L_E) {
+              gv[u] = ldg2(col + (size_t)(i + kSbrHfAdj) * kXgRow);
+              ++i;
+              while (l < L_E && i >= env_end(l)) { ++l; i = fp->t_E[min(l, kSbrMaxLE)]; }
             }
-            Q_filt = (s_m != 0 || no_noise) ? 0 : Q_filt;
-            if (active) {
-              const int ni = (fIndexNoise + slots_done * M + t + 1) & 511;
-              float* x = &XS(i + kSbrHfAdj, t + kx, 0);
-              x[0] = G_filt * x[0] + (Q_filt * __ldg(T.noise_table + 2 * ni));
-              x[1] = G_filt * x[1] + (Q_filt * __ldg(T.noise_table + 2 * ni + 1));
-              const int rev = (((t + kx) & 1) != 0 ? -1 : 1);
+          }
+        };
+        gather(al, ai, av);
+#pragma unroll 1
+        while (al[0] >= 0) {
+          gather(bl, bi, bv);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (al[u] >= 0) {
+              if (al[u] != l_cached) {
+                l_cached = al[u];
+                no_noise = (l_cached == fp->l_A || l_cached == fp->prevEnvIsShort);
+                h_SL = (fp->smoothing_mode || no_noise) ? 0 : 4;
+                g_new = W.g.G[l_cached][m]; q_new = W.g.Q[l_cached][m]; s_m = W.g.S[l_cached][m];
+              }
+              // the slot's entry: the oldest leaves, the envelope's value comes in as the newest
+              Ag[0] = Ag[1]; Ag[1] = Ag[2]; Ag[2] = Ag[3]; Ag[3] = Ag[4]; Ag[4] = g_new;
+              Aq[0] = Aq[1]; Aq[1] = Aq[2]; Aq[2] = Aq[3]; Aq[3] = Aq[4]; Aq[4] = q_new;
+              float G_filt = 0, Q_filt = 0;
+              if (h_SL != 0) {
+#pragma unroll
+                for (int n = 0; n <= 4; n++) {
+                  const float h = n == 0 ? 0.03183050093751f : n == 1 ? 0.11516383427084f : n == 2 ? 0.21816949906249f
+                                : n == 3 ? 0.30150283239582f : 0.33333333333333f;
+                  G_filt += (Ag[n] * h);
+                  Q_filt += (Aq[n] * h);
+                }
+              } else { G_filt = g_new; Q_filt = q_new; }
+              Q_filt = (s_m != 0 || no_noise) ? 0 : Q_filt;
+              const int ni = (fIndexNoise + slots_done * M + m + 1) & 511;
+              const float2 nz = __ldg(reinterpret_cast<const float2*>(T.noise_table) + ni);
+              float x0 = G_filt * av[u].x + (Q_filt * nz.x);
+              float x1 = G_filt * av[u].y + (Q_filt * nz.y);
               const int phi_re = fIndexSine == 0 ? 1 : (fIndexSine == 2 ? -1 : 0);
               const int phi_im = fIndexSine == 1 ? 1 : (fIndexSine == 3 ? -1 : 0);
-              x[0] += s_m * (float)phi_re;
-              x[1] += (float)rev * s_m * (float)phi_im;
+              x0 += s_m * (float)phi_re;
+              x1 += (float)rev * s_m * (float)phi_im;
+              st2(col + (size_t)(ai[u] + kSbrHfAdj) * kXgRow, x0, x1);
+              ++slots_done;
+              fIndexSine = (fIndexSine + 1) & 3;
             }
-            ++slots_done;
-            fIndexSine = (fIndexSine + 1) & 3;
-            ring_index++;
-            if (ring_index >= 5) ring_index = 0;
           }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { al[u] = bl[u]; ai[u] = bi[u]; av[u] = bv[u]; }
         }
-        index_noise_prev = (fIndexNoise + slots_done * M) & 511;
-        psi_is_prev = fIndexSine;
+        // back to ring positions: after slots_done writes the next write position is ri0 + slots_done
+        int pos = (ri0 + slots_done) % 5;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          W.ringG[pos][m] = Ag[j];
+          W.ringQ[pos][m] = Aq[j];
+          if (++pos >= 5) pos = 0;
+        }
       }
-      __syncthreads();
+      for (int l = 0; l < L_E; ++l) slots_total += max(0, min((int)fp->t_E[l + 1], 38) - (int)fp->t_E[l]);
+      ring_index = (ri0 + slots_total) % 5;
+      index_noise_prev = (fIndexNoise + slots_total * M) & 511;
+      psi_is_prev = (psi_is_prev + slots_total) & 3;
     }
+  }
+  __syncwarp();
 
-    // X[l][k] = Xsbr[l + tHFAdj][k] below kx + M of the slot's frame, 0 above (Channel.process_channel, :604-645)
-    auto x_limit = [&](int l) -> int {
-      if (mode == 2) return (l < first_slot) ? (fp->kx_prev + fp->M_prev) : (fp->kx + fp->M);
-      return 32;
-    };
-    // ---- 64-band QMF synthesis of one channel (sbr/SynthesisFilterbank64.java:9-79): the two DCT-IVs of slot l by thread l,
-    // then all 64 threads window.  src == nullptr: read Xsbr with the band limit; else a ready [32][kXsStride] matrix.
-    auto synthesis = [&](const float* src, int och, bool dup) {
-      if (t < 32) {
-        const int l = t;
-        const int lim = src ? 64 : x_limit(l);
-        const float* row = src ? src + l * kXsStride : xs + (l + kSbrHfAdj) * kXsStride;
-        const float scale = 1.f / 64.f;
-        auto Xr = [&](int k) -> float { return k < lim ? row[2 * k] : 0.f; };
-        auto Xi = [&](int k) -> float { return k < lim ? row[2 * k + 1] : 0.f; };
-        float in_r[32], in_i[32], o1r[32], o1i[32], o2r[32], o2i[32];
-        in_i[31] = scale * Xr(1);
-        in_r[0] = scale * Xr(0);
+  // ---- recursive state out
+  for (int i = lane; i < 5 * 64; i += 32) { (&st->G_temp_prev[0][0])[i] = (&W.ringG[0][0])[i]; (&st->Q_temp_prev[0][0])[i] = (&W.ringQ[0][0])[i]; }
+  if (lane < 8) { st->bwArray_prev[lane] = bw_prev; st->bs_invf_mode_prev[lane] = (uint8_t)invf_prev; }
+  if (lane == 0) { st->GQ_ringbuf_index = ring_index; st->index_noise_prev = index_noise_prev; st->psi_is_prev = psi_is_prev; }
+  if (last_it >= 0) {
+    // what the next tile's analysis starts from: the last 288 core samples and rows 32..39 of the last processed frame
+    const float* cs = core + ((size_t)run_frames[run.first + last_it].ics_base + run.ch_slot) * 1024 + 736;
+    for (int i = lane; i < 288; i += 32) st->ana_hist[i] = cs[i];
+    const float4* s4 = reinterpret_cast<const float4*>(Xrun + 32 * (size_t)n_done * kXgRow);
+    float4* d4 = reinterpret_cast<float4*>(&st->xsbr[0][0][0]);
+    for (int i = lane; i < kSbrHfGen * 32; i += 32) d4[i] = __ldcg(s4 + i);
+  }
+}
+
+// ---- K4c: 64-band QMF synthesis (sbr/SynthesisFilterbank64.java:9-79) + PCM pack (S/SampleBuffer.java:168-209)
+constexpr int kK4cThreads = 64;
+constexpr int kK4cRows = 9 + 32;   // the nine inherited slots, then the frame's 32
+constexpr int kK4cXs = kK4cRows * kXsStride + 3, kK4cVb = kK4cRows * kVbStride + 3;
+static_assert(kK4cXs % 4 == 0 && kK4cVb % 4 == 0, "16-byte aligned regions");
+constexpr size_t k4c_smem_bytes() { return sizeof(float) * (kK4cXs + kK4cVb); }
+
+// The two DCT-IVs of one slot (SynthesisFilterbank64.java:27-60).  `row` holds the slot's band-limited QMF samples as
+// [Re X(0..63) | Im X(63..0)], so both transforms read their inputs the same way and ONE copy of the unrolled DCT serves
+// both (the kernel is instruction-fetch bound otherwise).  The first transform's output is parked in the cells its inputs
+// came from.  v = the slot's 128-entry v-vector.
+__device__ __forceinline__ void sbr_synth_slot(float* __restrict__ row, float* __restrict__ v) {
+  const float scale = 1.f / 64.f;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    float* b = row + 64 * pass;
+    float in_r[32], in_i[32], o_r[32], o_i[32];
+    in_i[31] = scale * b[1];
+    in_r[0] = scale * b[0];
 #pragma unroll
-        for (int k = 1; k < 31; k++) { in_i[31 - k] = scale * Xr(2 * k + 1); in_r[k] = scale * Xr(2 * k); }
-        in_i[0] = scale * Xr(63);
-        in_r[31] = scale * Xr(62);
-        sbr_dct4_kernel(in_r, in_i, o1r, o1i);
-        in_i[31] = scale * Xi(63 - 1);
-        in_r[0] = scale * Xi(63 - 0);
+    for (int k = 1; k < 31; k++) { in_i[31 - k] = scale * b[2 * k + 1]; in_r[k] = scale * b[2 * k]; }
+    in_i[0] = scale * b[63];
+    in_r[31] = scale * b[62];
+    sbr_dct4_kernel(in_r, in_i, o_r, o_i);
+    if (pass == 0) {
 #pragma unroll
-        for (int k = 1; k < 31; k++) { in_i[31 - k] = scale * Xi(63 - (2 * k + 1)); in_r[k] = scale * Xi(63 - (2 * k)); }
-        in_i[0] = scale * Xi(63 - 63);
-        in_r[31] = scale * Xi(63 - 62);
-        sbr_dct4_kernel(in_r, in_i, o2r, o2i);
-        float* v = &VB(9 + l, 0);
+      for (int n = 0; n < 32; n++) { b[n] = o_r[n]; b[32 + n] = o_i[n]; }
+    } else {
 #pragma unroll
-        for (int n = 0; n < 32; n++) {
-          v[2 * n] = o2r[n] - o1r[n];
-          v[127 - 2 * n] = o2r[n] + o1r[n];
-          v[2 * n + 1] = o2i[31 - n] + o1i[31 - n];
-          v[127 - (2 * n + 1)] = o2i[31 - n] - o1i[31 - n];
+      for (int n = 0; n < 32; n++) {
+        const float o1r = row[n], o1i = row[32 + 31 - n];
+        v[2 * n] = o_r[n] - o1r;
+        v[127 - 2 * n] = o_r[n] + o1r;
+        v[2 * n + 1] = o_i[31 - n] + o1i;
+        v[127 - (2 * n + 1)] = o_i[31 - n] - o1i;
+      }
+    }
+  }
+}
+
+// X[l][k] = Xsbr[l + tHFAdj][k] below kx + M of the slot's frame, 0 above (Channel.process_channel, SBR.java:604-645)
+__device__ __forceinline__ int k4_x_limit(const SbrFrameDev* fp, int mode, int l) {
+  if (mode == 2) return (l < fp->t_E[0]) ? (fp->kx_prev + fp->M_prev) : (fp->kx + fp->M);
+  return 32;
+}
+
+// PS: the runs are the SCEs of SBR+PS streams, blockIdx.y is the synthesis bank (SBR1.processPS, :121-122): 0 = left, fed
+// by K5's left matrix in frames that carry ps_data and by Xsbr (output duplicated) otherwise; 1 = right, which only exists
+// -- and only moves its history -- in frames that carry ps_data.
+template <int PCM_FORMAT, bool PS>
+__global__ void __launch_bounds__(kK4cThreads)
+k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const RunFrameDev* __restrict__ run_frames,
+                     const SbrFrameDev* __restrict__ sframes, const float* __restrict__ core, SbrChanDev* __restrict__ chans,
+                     const float* __restrict__ xg, uint8_t* __restrict__ pcm, const uint64_t* __restrict__ pcm_off,
+                     uint32_t* __restrict__ pcm_bytes_out, SbrTablesDev T, K4Tile tile,
+                     const PsFrameDev* __restrict__ ps_frames, PsChanDev* __restrict__ ps_chans, const float* __restrict__ xps) {
+  extern __shared__ __align__(16) float k4c_smem[];
+  float* xs = k4c_smem;            // [41][kXsStride]: rows 0..8 = slots -9..-1, rows 9..40 = slots 0..31; [Re 0..63 | Im 63..0]
+  float* vb = k4c_smem + kK4cXs;   // [41][kVbStride]
+  const int t = threadIdx.x;
+  const uint32_t rl = blockIdx.x / tile.ft, r = run0 + rl, it = tile.lo + blockIdx.x % tile.ft;
+  const int bank = PS ? (int)blockIdx.y : 0;
+  const K4RunDev run = runs[r];
+  if (it >= run.count) return;
+  const SbrFrameDev* fp = k4_frame(sframes, run, it);
+  const RunFrameDev rf = run_frames[run.first + it];
+  const uint32_t f = rf.frame;
+  const int mode = fp->mode;
+  const bool use_ps = PS && fp->frame_status == 0 && mode != 0 && ps_frames[run.ps_base + it].use_ps != 0;
+  if (PS && bank == 1 && !use_ps) return;
+  uint8_t* dst = pcm + pcm_off[f];
+  const int n_out = run.n_out;
+  const int out_ch = PS ? bank : run.out_ch;
+  if (fp->frame_status != 0) {
+    if (t == 0 && out_ch == 0) pcm_bytes_out[f] = 0;
+    return;
+  }
+  if (t == 0 && out_ch == 0) pcm_bytes_out[f] = (uint32_t)(2048 * n_out * (PCM_FORMAT == 2 ? 4 : 2));
+  const bool dup = run.dup != 0 && !use_ps;   // mono element: SBR1.process copies the channel unless PS makes the second one
+  const bool pair_store = dup && out_ch == 0 && n_out == 2 && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0;
+  auto put_sample = [&](int i, float v) {
+    if (PCM_FORMAT == 2) {
+      float* d = reinterpret_cast<float*>(dst);
+      d[(size_t)out_ch * 2048 + i] = v;
+      if (dup) d[(size_t)(out_ch + 1) * 2048 + i] = v;
+    } else {
+      uint32_t u = (uint32_t)pcm_round(v) & 0xFFFFu;
+      if (PCM_FORMAT == 1) u = __byte_perm(u, 0, 0x4401);
+      uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+      if (pair_store) reinterpret_cast<uint32_t*>(d)[i] = u | (u << 16);
+      else {
+        d[(size_t)i * n_out + out_ch] = (uint16_t)u;
+        if (dup) d[(size_t)i * n_out + out_ch + 1] = (uint16_t)u;
+      }
+    }
+  };
+  const float* cs = core + ((size_t)rf.ics_base + run.ch_slot) * 1024;
+  if (mode == 0) {
+    // no valid SBR data in this frame: SBR.upsample (sbr/SBR.java:302-309; sample 1 keeps the core value)
+    for (int i = t; i < 2048; i += kK4cThreads) put_sample(i, i < 2 ? cs[i] : cs[i >> 1]);
+    return;
+  }
+  const uint32_t o = fp->ord - k4_frame(sframes, run, tile.lo)->ord;
+  const float* X = xg + ((size_t)r * tile.rows + 32 * (size_t)o) * kXgRow;
+  SbrChanDev* st = chans + (size_t)run.stream_slot * kSbrChansPerStream + run.ch_slot;
+  PsChanDev* pst = PS ? ps_chans + run.stream_slot : nullptr;
+  const int sel = (PS && bank == 1) ? pst->v_sel : st->v_sel;
+  float* v_in = (PS && bank == 1) ? &pst->syn_v_right[sel][0][0] : &st->syn_v[sel][0][0];
+  float* v_out = (PS && bank == 1) ? &pst->syn_v_right[sel ^ 1][0][0] : &st->syn_v[sel ^ 1][0][0];
+  // K5's matrices of frame `fr` of this run: [left, right][32][kXgRow]
+  auto ps_matrix = [&](uint32_t fr) -> const float* { return xps + (((size_t)rl * tile.ft + (fr - tile.lo)) * 2 + bank) * 32 * kXgRow; };
+  // the frame whose last nine slots this bank inherits, and whether it lies inside the tile
+  const uint32_t back = (PS && bank == 1) ? fp->back_ps : fp->back;
+  const bool halo_in_tile = (PS && bank == 1) ? (back != 0 && it - back >= tile.lo && it >= back) : (o > 0);
+  // ---- stage the QMF rows (band limit applied); thread t = band t
+  {
+    if (use_ps) {
+      const float* P = ps_matrix(it);
+      for (int l = 0; l < 32; ++l) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(P + (size_t)l * kXgRow) + t);
+        xs[(9 + l) * kXsStride + t] = v.x;
+        xs[(9 + l) * kXsStride + 127 - t] = v.y;
+      }
+    } else {
+      const int lim_lo = k4_x_limit(fp, mode, 0), lim_hi = k4_x_limit(fp, mode, 31), first_slot = mode == 2 ? fp->t_E[0] : 0;
+      for (int l = 0; l < 32; ++l) {
+        const int lim = l < first_slot ? lim_lo : lim_hi;
+        float2 v = make_float2(0.f, 0.f);
+        if (t < lim) v = __ldg(reinterpret_cast<const float2*>(X + (size_t)(l + kSbrHfAdj) * kXgRow) + t);
+        xs[(9 + l) * kXsStride + t] = v.x;
+        xs[(9 + l) * kXsStride + 127 - t] = v.y;
+      }
+    }
+    if (halo_in_tile) {
+      const uint32_t q = it - back;
+      const bool q_ps = PS && (bank == 1 || ps_frames[run.ps_base + q].use_ps != 0);
+      if (q_ps) {
+        // the previous frame of this bank went through the PS tool: slots 23..31 of its matrix
+        const float* P = ps_matrix(q);
+        for (int h = 0; h < 9; ++h) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(P + (size_t)(23 + h) * kXgRow) + t);
+          xs[h * kXsStride + t] = v.x;
+          xs[h * kXsStride + 127 - t] = v.y;
+        }
+      } else {
+        // slots 23..31 of the previous processed frame: its rows 25..33 = rows -7..1 here
+        const SbrFrameDev* fq = k4_frame(sframes, run, q);
+        const int mq = fq->mode;
+        for (int h = 0; h < 9; ++h) {
+          const int lim = k4_x_limit(fq, mq, 23 + h);
+          float2 v = make_float2(0.f, 0.f);
+          if (t < lim) v = __ldg(reinterpret_cast<const float2*>(X + ((ptrdiff_t)h - 7) * kXgRow) + t);
+          xs[h * kXsStride + t] = v.x;
+          xs[h * kXsStride + 127 - t] = v.y;
         }
       }
-      __syncthreads();
-      // window + output: thread k, all 32 slots
-      for (int l = 0; l < 32; ++l) {
-        const int cur = 9 + l;
-        float o = (VB(cur, t) * qc[0]);
+    } else {
+      // carried v-vectors: row 8 is the newest (slot -1), row 0 the oldest (slot -9); [0] of the state = newest
+      for (int i = t; i < 9 * 128; i += kK4cThreads) vb[(8 - i / 128) * kVbStride + (i % 128)] = v_in[i];
+    }
+  }
+  __syncthreads();
+  {
+    const int srow = t < 32 ? 9 + t : t - 32;   // threads 32..40 take the nine inherited slots
+    if (t < 32 || (halo_in_tile && t < 41)) sbr_synth_slot(xs + srow * kXsStride, vb + srow * kVbStride);
+  }
+  __syncthreads();
+  // ---- window + output: thread k, all 32 slots
+  float qc[10];
 #pragma unroll
-        for (int j = 1; j < 10; ++j) o = o + (VB(cur - j, t + 64 * (j & 1)) * qc[j]);
-        put_sample_to(64 * l + t, o, och, dup);
-      }
-      __syncthreads();
-    };
+  for (int j = 0; j < 10; ++j) qc[j] = c_sbr_qmf_c[t + 64 * j];
+  for (int l = 0; l < 32; ++l) {
+    const int cur = 9 + l;
+    float ov = (vb[cur * kVbStride + t] * qc[0]);
+#pragma unroll
+    for (int j = 1; j < 10; ++j) ov = ov + (vb[(cur - j) * kVbStride + t + 64 * (j & 1)] * qc[j]);
+    put_sample(64 * l + t, ov);
+  }
+  // ---- the bank's last frame of the tile hands its nine newest v-vectors to the next tile
+  const uint32_t fwd = (PS && bank == 1) ? fp->fwd_ps : fp->fwd;
+  if (fwd == 0 || it + fwd >= tile.lo + tile.ft) {
+    for (int i = t; i < 9 * 128; i += kK4cThreads) v_out[i] = vb[(40 - i / 128) * kVbStride + (i % 128)];
+    if (t == 0) { if (PS && bank == 1) pst->v_flip = 1; else st->v_flip = 1; }
+  }
+}
 
-    if (!use_ps) {
-      synthesis(nullptr, run.out_ch, run.dup != 0);
-    } else if (WITH_PS) {
+__global__ void k4_commit_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, uint32_t n_plain, SbrChanDev* __restrict__ chans,
+                                 PsChanDev* __restrict__ ps_chans) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  SbrChanDev* st = chans + (size_t)runs[r].stream_slot * kSbrChansPerStream + runs[r].ch_slot;
+  if (st->v_flip) { st->v_sel ^= 1; st->v_flip = 0; }
+  if (r >= n_plain) {
+    PsChanDev* pst = ps_chans + runs[r].stream_slot;
+    if (pst->v_flip) { pst->v_sel ^= 1; pst->v_flip = 0; }
+  }
+}
+
+// ---- K5: parametric stereo (ps/PSImpl.java:685-707) for the frames of an SBR+PS stream that carry ps_data: hybrid
+// analysis, transient detection, all-pass decorrelation, H-matrix mixing, hybrid synthesis.  The decorrelator and the
+// transient detector are recursive in time, so one CTA (64 threads: one per QMF band / time slot) walks the frames of the
+// tile in order; input is the finished Xsbr matrix in xg, output the left / right QMF matrices the synthesis kernel reads:
+//   xps[ps run][frame of the tile][left, right][32 slots][64 bands][re, im]
+constexpr int kK5Threads = 64;
+constexpr int kK5Floats = 2 * 32 * kXsStride + 2 * 32 * 24 + 32 * 20 + 3 * 88;
+static_assert(kK5Floats % 4 == 0, "PsFrameDev must land 16-byte aligned");
+constexpr size_t k5_smem_bytes() { return sizeof(float) * kK5Floats + sizeof(PsFrameDev); }
+
+__global__ void __launch_bounds__(kK5Threads)
+k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev* __restrict__ sframes,
+             const PsFrameDev* __restrict__ ps_frames, PsChanDev* __restrict__ ps_chans, const float* __restrict__ xg,
+             float* __restrict__ xps, SbrTablesDev T, K4Tile tile) {
+  extern __shared__ __align__(16) float k5_smem[];
+  float* xl = k5_smem;                                   // [32][kXsStride]
+  float* xr = xl + 32 * kXsStride;                       // [32][kXsStride]
+  float* hyl = xr + 32 * kXsStride;                      // [32][12][2]
+  float* hyr = hyl + 32 * 24;                            // [32][12][2]
+  float* pg = hyr + 32 * 24;                             // [32][20] band energies, then transient ratios
+  float* hwork = pg + 32 * 20;                           // [3][44][2] hybrid analysis input
+  PsFrameDev* pp = reinterpret_cast<PsFrameDev*>(hwork + 3 * 88);
+#define XL(l, k, c) xl[(l) * kXsStride + (k) * 2 + (c)]
+#define XR(l, k, c) xr[(l) * kXsStride + (k) * 2 + (c)]
+#define HYL(n, k, c) hyl[((n) * 12 + (k)) * 2 + (c)]
+#define HYR(n, k, c) hyr[((n) * 12 + (k)) * 2 + (c)]
+  const int t = threadIdx.x;
+  const uint32_t r = run0 + blockIdx.x;
+  const K4RunDev run = runs[r];
+  if (tile.lo >= run.count) return;
+  const uint32_t hi = min(run.count, tile.lo + tile.ft);
+  PsChanDev* pst = ps_chans + run.stream_slot;
+  const float* Xrun = xg + (size_t)r * tile.rows * kXgRow;
+  const uint32_t ord_lo = k4_frame(sframes, run, tile.lo)->ord;
+  for (uint32_t it = tile.lo; it < hi; ++it) {
+    const SbrFrameDev* fp = k4_frame(sframes, run, it);
+    const int mode = fp->mode;
+    if (fp->frame_status != 0 || mode == 0) continue;
+    const PsFrameDev* pf = ps_frames + run.ps_base + it;
+    if (pf->use_ps == 0) continue;
+    __syncthreads();
+    if (t < (int)(sizeof(PsFrameDev) / 16)) reinterpret_cast<uint4*>(pp)[t] = reinterpret_cast<const uint4*>(pf)[t];
+    __syncthreads();
+    const float* X = Xrun + 32 * (size_t)(fp->ord - ord_lo) * kXgRow;
+    {
       // ================= parametric stereo (ps/PSImpl.java) =================
       const int num_env = pp->num_env;
       // X_left: the band-limited copy of Xsbr (SBR1.processPS); hybrid analysis input: QMF bands 0..2 of slots 6..37
-      for (int l = 0; l < 32; ++l) {
-        const int lim = x_limit(l);
-        XL(l, t, 0) = t < lim ? XS(l + kSbrHfAdj, t, 0) : 0.f;
-        XL(l, t, 1) = t < lim ? XS(l + kSbrHfAdj, t, 1) : 0.f;
+      {
+        const int lim_lo = k4_x_limit(fp, mode, 0), lim_hi = k4_x_limit(fp, mode, 31), fs = mode == 2 ? fp->t_E[0] : 0;
+        float2 xv[32];
+#pragma unroll
+        for (int l = 0; l < 32; ++l) xv[l] = __ldg(reinterpret_cast<const float2*>(X + (size_t)(l + kSbrHfAdj) * kXgRow) + t);
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+          const int lim = l < fs ? lim_lo : lim_hi;
+          XL(l, t, 0) = t < lim ? xv[l].x : 0.f;
+          XL(l, t, 1) = t < lim ? xv[l].y : 0.f;
+        }
       }
       for (int i = t; i < 3 * 44; i += kK4Threads) {
         const int band = i / 44, j = i % 44;
         // work[0..11] = history, work[12 + n] = X[n + 6][band]: rows 6..31 come from X_left, rows 32..37 straight
         // from Xsbr (:108-113) -- for bands 0..2 both are the unmodified analysis output
-        hwork[(band * 44 + j) * 2] = j < 12 ? pst->hyb_buffer[band][j][0] : XS(j - 12 + 6 + kSbrHfAdj, band, 0);
-        hwork[(band * 44 + j) * 2 + 1] = j < 12 ? pst->hyb_buffer[band][j][1] : XS(j - 12 + 6 + kSbrHfAdj, band, 1);
+        hwork[(band * 44 + j) * 2] = j < 12 ? pst->hyb_buffer[band][j][0] : __ldg(X + (size_t)(j - 12 + 6 + kSbrHfAdj) * kXgRow + 2 * band);
+        hwork[(band * 44 + j) * 2 + 1] = j < 12 ? pst->hyb_buffer[band][j][1] : __ldg(X + (size_t)(j - 12 + 6 + kSbrHfAdj) * kXgRow + 2 * band + 1);
       }
       __syncthreads();
       if (t < 36) { const int band = t / 12, j = t % 12; pst->hyb_buffer[band][j][0] = hwork[(band * 44 + 32 + j) * 2]; pst->hyb_buffer[band][j][1] = hwork[(band * 44 + 32 + j) * 2 + 1]; }
@@ -933,807 +1444,20 @@ k4_sbr_process_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __re
         }
       }
       __syncthreads();
-      // ---- two synthesis banks (SBR1.processPS, :121-122): left with the channel's own history, right with its own
-      synthesis(xl, run.out_ch, false);
-      float vkl[18];
-#pragma unroll
-      for (int s2 = 0; s2 < 9; ++s2) { vkl[2 * s2] = VB(32 + s2, t); vkl[2 * s2 + 1] = VB(32 + s2, t + 64); }
-      __syncthreads();
-#pragma unroll
-      for (int s2 = 0; s2 < 9; ++s2) { VB(s2, t) = vhr[s2 * kVbStride + t]; VB(s2, t + 64) = vhr[s2 * kVbStride + t + 64]; }
-      __syncthreads();
-      synthesis(xr, run.out_ch + 1, false);
-#pragma unroll
-      for (int s2 = 0; s2 < 9; ++s2) { vhr[s2 * kVbStride + t] = VB(32 + s2, t); vhr[s2 * kVbStride + t + 64] = VB(32 + s2, t + 64); }
-      __syncthreads();
-      // put the left channel's newest nine vectors where the carry step below expects them
-#pragma unroll
-      for (int s2 = 0; s2 < 9; ++s2) { VB(32 + s2, t) = vkl[2 * s2]; VB(32 + s2, t + 64) = vkl[2 * s2 + 1]; }
-      __syncthreads();
-    }
-    // ---- carry: analysis history, the last 8 Xsbr slots (sbr_save_matrix), the last 9 v-vectors
-    for (int i = t; i < 288; i += kK4Threads) INB(i) = INB(1024 + i);   // disjoint ranges
-    {
-      float keep[kSbrHfGen * 2];
-#pragma unroll
-      for (int i = 0; i < kSbrHfGen; ++i) { keep[2 * i] = XS(i + kSbrSlots, t, 0); keep[2 * i + 1] = XS(i + kSbrSlots, t, 1); }
-      float vk[18];
-#pragma unroll
-      for (int s = 0; s < 9; ++s) { vk[2 * s] = VB(32 + s, t); vk[2 * s + 1] = VB(32 + s, t + 64); }
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < kSbrHfGen; ++i) { XS(i, t, 0) = keep[2 * i]; XS(i, t, 1) = keep[2 * i + 1]; }
-      for (int i = kSbrHfGen; i < 40; ++i) { XS(i, t, 0) = 0.f; XS(i, t, 1) = 0.f; }
-#pragma unroll
-      for (int s = 0; s < 9; ++s) { VB(s, t) = vk[2 * s]; VB(s, t + 64) = vk[2 * s + 1]; }
-    }
-    __syncthreads();
-  }
 
-  // ---- persistent state out
-  for (int i = t; i < 288; i += kK4Threads) st->ana_hist[i] = INB(i);
-  for (int i = t; i < kSbrHfGen * 128; i += kK4Threads) (&st->xsbr[0][0][0])[i] = XS(i >> 7, 0, i & 127);
-  for (int i = t; i < 9 * 128; i += kK4Threads) st->syn_v[0][i / 128][i % 128] = VB(8 - i / 128, i % 128);
-#pragma unroll
-  for (int n = 0; n < 5; ++n) { st->G_temp_prev[n][t] = Gt[n]; st->Q_temp_prev[n][t] = Qt[n]; }
-  if (t < 8) { st->bwArray_prev[t] = bw_prev; st->bs_invf_mode_prev[t] = (uint8_t)invf_prev; }
-  if (t == 0) { st->GQ_ringbuf_index = ring_index; st->index_noise_prev = index_noise_prev; st->psi_is_prev = psi_is_prev; }
-  if (WITH_PS)
-    for (int i = t; i < 9 * 128; i += kK4Threads) pst->syn_v_right[i / 128][i % 128] = vhr[(8 - i / 128) * kVbStride + (i % 128)];
+    }
+    // ---- the two matrices go out: thread t = band
+    float* outl = xps + ((size_t)(blockIdx.x * tile.ft + (it - tile.lo)) * 2) * 32 * kXgRow;
+    float* outr = outl + 32 * kXgRow;
+    for (int l = 0; l < 32; ++l) {
+      reinterpret_cast<float2*>(outl + (size_t)l * kXgRow)[t] = make_float2(XL(l, t, 0), XL(l, t, 1));
+      reinterpret_cast<float2*>(outr + (size_t)l * kXgRow)[t] = make_float2(XR(l, t, 0), XR(l, t, 1));
+    }
+  }
 #undef XL
 #undef XR
 #undef HYL
 #undef HYR
-}
-
-// =====================================================================================================================
-// Frame-parallel SBR pipeline (plain SBR channels).  The QMF banks are FIR structures: analysis slot l of a frame needs
-// the 320 newest core samples, synthesis slot l the ten newest v-vectors, so every (channel, frame) pair can run on its
-// own warp / CTA once the few truly recursive pieces are out of the way.  The Xsbr matrix of SBR.java lives in global
-// memory for a TILE of frames (ft consecutive frames of every run):
-//
-//   xg[run][8 + 32 * ft rows][64 bands][re, im]      row 32 * o + r = row r of Xsbr for the o-th processed frame
-//                                                    of the tile (rows 32..39 of a frame ARE rows 0..7 of the next one,
-//                                                    which is what SBR.sbr_save_matrix copies)
-//
-//   K4a  k4a_analysis_kernel   warp per (channel, frame): 32-band analysis, one time slot per lane       -> xg low band
-//   K4b  k4b_hf_kernel         warp per channel, frames of the tile in order (chirp factors, smoothing ring, noise and
-//                              sine phase are recursive): HF generation + HF adjustment, one band per lane -> xg high band
-//   K4c  k4c_synthesis_kernel  CTA per (channel, frame): 64-band synthesis; the nine v-vectors a frame inherits are
-//                              recomputed from the previous frame's rows (or come from the carried state at a tile start)
-//   k4_commit_kernel           flips the double-buffered v-vector state
-// Frames that do not run the SBR tool (mode 0, failed frames) take no rows: K3 numbers the processed frames (ord) and
-// links them (back / fwd).
-constexpr int kXgRow = 128;   // floats per row of xg
-
-struct K4Tile {
-  uint32_t lo, ft;    // frames [lo, lo + ft) of every run
-  uint32_t rows;      // rows per run in xg: 8 + 32 * ft
-};
-
-__device__ __forceinline__ const SbrFrameDev* k4_frame(const SbrFrameDev* sframes, const K4RunDev& run, uint32_t it) {
-  return sframes + ((size_t)run.sbr_base + it) * 2 + run.chan;
-}
-__device__ __forceinline__ float2 ldg2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
-__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
-
-// ---- K4a: 32-band QMF analysis (sbr/AnalysisFilterbank.java:9-73)
-constexpr int kK4aWarps = 4;
-constexpr int kK4aStage = 32 * 65;   // floats per warp: the 1312 input samples first, then the [32 slots][64 + 1] output
-constexpr size_t k4a_smem_bytes() { return sizeof(float) * kK4aStage * kK4aWarps; }
-
-__global__ void __launch_bounds__(32 * kK4aWarps)
-k4a_analysis_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrameDev* __restrict__ run_frames,
-                    const SbrFrameDev* __restrict__ sframes, const float* __restrict__ core, const SbrChanDev* __restrict__ chans,
-                    float* __restrict__ xg, K4Tile tile) {
-  extern __shared__ __align__(16) float k4a_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t w = blockIdx.x * kK4aWarps + warp;
-  if (w >= n_runs * tile.ft) return;
-  const uint32_t r = w / tile.ft, it = tile.lo + w % tile.ft;
-  const K4RunDev run = runs[r];
-  if (it >= run.count) return;
-  const SbrFrameDev* fp = k4_frame(sframes, run, it);
-  const int mode = fp->mode;
-  if (fp->frame_status != 0 || mode == 0) return;
-  const uint32_t o = fp->ord - k4_frame(sframes, run, tile.lo)->ord;
-  const int kx = mode == 2 ? fp->kx : 32;
-  const uint32_t back = fp->back;
-  float* X = xg + ((size_t)r * tile.rows + 32 * (size_t)o) * kXgRow;
-  const SbrChanDev* st = chans + (size_t)run.stream_slot * kSbrChansPerStream + run.ch_slot;
-  if (o == 0) {
-    // the rows the previous tile (or batch) left behind
-    const float4* s4 = reinterpret_cast<const float4*>(&st->xsbr[0][0][0]);
-    float4* d4 = reinterpret_cast<float4*>(X);
-    for (int i = lane; i < kSbrHfGen * 32; i += 32) d4[i] = s4[i];
-  }
-  float* inbuf = k4a_smem + warp * kK4aStage;
-  {
-    const float* hist = back ? core + ((size_t)run_frames[run.first + it - back].ics_base + run.ch_slot) * 1024 + 736 : st->ana_hist;
-    for (int i = lane; i < 288; i += 32) INB(i) = hist[i];
-    const float4* cs = reinterpret_cast<const float4*>(core + ((size_t)run_frames[run.first + it].ics_base + run.ch_slot) * 1024);
-    for (int i = lane; i < 256; i += 32) {
-      const float4 v = cs[i];
-      INB(288 + 4 * i) = v.x; INB(288 + 4 * i + 1) = v.y; INB(288 + 4 * i + 2) = v.z; INB(288 + 4 * i + 3) = v.w;
-    }
-  }
-  __syncwarp();
-  const int xi = 288 + 32 * lane + 31;   // newest sample of the slot; sample xi - j = v[v_index + j] of the reference
-  float in_real[32], in_imag[32], out_real[32], out_imag[32];
-#pragma unroll
-  for (int n = 0; n < 64; ++n) {
-    const float u = (INB(xi - n) * c_sbr_qmf_c[2 * n]) + (INB(xi - (n + 64)) * c_sbr_qmf_c[2 * (n + 64)]) +
-                    (INB(xi - (n + 128)) * c_sbr_qmf_c[2 * (n + 128)]) + (INB(xi - (n + 192)) * c_sbr_qmf_c[2 * (n + 192)]) +
-                    (INB(xi - (n + 256)) * c_sbr_qmf_c[2 * (n + 256)]);
-    // reordering of AnalysisFilterbank.java:40-47
-    if (n == 0) in_real[0] = u;
-    else if (n == 1) in_imag[31] = u;
-    else if (n <= 31) in_imag[32 - n] = u;
-    else if (n == 32) in_imag[0] = u;
-    else if (n == 33) in_real[31] = -u;
-    else in_real[64 - n] = -u;
-  }
-  sbr_dct4_kernel(in_real, in_imag, out_real, out_imag);
-  __syncwarp();   // every lane is done with the input samples: the region becomes the output stage
-  float* stage = inbuf + lane * 65;
-#pragma unroll
-  for (int n = 0; n < 16; n++) {
-    if (2 * n + 1 < kx) {
-      stage[4 * n] = 2.0f * out_real[n];
-      stage[4 * n + 1] = 2.0f * out_imag[n];
-      stage[4 * n + 2] = -2.0f * out_imag[31 - n];
-      stage[4 * n + 3] = -2.0f * out_real[31 - n];
-    } else {
-      if (2 * n < kx) { stage[4 * n] = 2.0f * out_real[n]; stage[4 * n + 1] = 2.0f * out_imag[n]; }
-      else { stage[4 * n] = 0; stage[4 * n + 1] = 0; }
-      stage[4 * n + 2] = 0;
-      stage[4 * n + 3] = 0;
-    }
-  }
-  __syncwarp();
-  // rows 8..39 of the frame: the low band, and zeros above it (what the reference's fresh / shifted matrix holds there)
-  for (int row = 0; row < 32; ++row) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < 16) {
-      const float* s = inbuf + row * 65 + 4 * lane;
-      v = make_float4(s[0], s[1], s[2], s[3]);
-    }
-    reinterpret_cast<float4*>(X + (size_t)(kSbrHfGen + row) * kXgRow)[lane] = v;
-  }
-}
-
-// ---- K4b: HF generation (sbr/HFGeneration.java:17-245) + HF adjustment (sbr/HFAdjustment.java:20-415)
-constexpr int kK4bWarps = 4;
-constexpr int kK4bMaxNL = 32;
-struct __align__(16) K4bSmem {
-  SbrFrameDev fp;
-  float E_curr[kSbrMaxLE][64];
-  float G[kSbrMaxLE][64], Q[kSbrMaxLE][64], S[kSbrMaxLE][64];   // G_lim_boost, Q_M_lim_boost, S_M_boost (contiguous)
-  float gmax[kSbrMaxLE][kK4bMaxNL], acc1[kSbrMaxLE][kK4bMaxNL], boost[kSbrMaxLE][kK4bMaxNL];
-  float bw[8];
-  uint8_t rb[2][64];             // band of f_table_res[res] that holds k = m + kx
-  uint8_t nb[64], lb[64];        // noise-floor band, limiter band
-  uint8_t sflag[kSbrMaxLE][64];  // S_index_mapped != 0
-};
-constexpr size_t k4b_smem_bytes() { return sizeof(K4bSmem) * kK4bWarps; }
-
-__global__ void __launch_bounds__(32 * kK4bWarps)
-k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrameDev* __restrict__ run_frames,
-              const SbrFrameDev* __restrict__ sframes, const float* __restrict__ core, SbrChanDev* __restrict__ chans,
-              float* xg, SbrTablesDev T, K4Tile tile) {
-  extern __shared__ __align__(16) uint8_t k4b_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t r = blockIdx.x * kK4bWarps + warp;
-  if (r >= n_runs) return;
-  K4bSmem& W = reinterpret_cast<K4bSmem*>(k4b_raw)[warp];
-  const K4RunDev run = runs[r];
-  if (tile.lo >= run.count) return;
-  const uint32_t hi = min(run.count, tile.lo + tile.ft);
-  SbrChanDev* st = chans + (size_t)run.stream_slot * kSbrChansPerStream + run.ch_slot;
-  float* Xrun = xg + (size_t)r * tile.rows * kXgRow;
-
-  // ---- recursive state in: the smoothing ring of bands lane and lane + 32, chirp factors (lanes < 8), phases
-  float Gt[2][5], Qt[2][5];
-#pragma unroll
-  for (int p = 0; p < 2; ++p)
-#pragma unroll
-    for (int n = 0; n < 5; ++n) { Gt[p][n] = st->G_temp_prev[n][lane + 32 * p]; Qt[p][n] = st->Q_temp_prev[n][lane + 32 * p]; }
-  int ring_index = st->GQ_ringbuf_index;
-  int index_noise_prev = st->index_noise_prev, psi_is_prev = st->psi_is_prev;
-  float bw_prev = 0.f;
-  int invf_prev = 0;
-  if (lane < 8) { bw_prev = st->bwArray_prev[lane]; invf_prev = st->bs_invf_mode_prev[lane]; }
-
-  uint32_t n_done = 0;   // processed frames of the tile so far
-  int64_t last_it = -1;
-  const SbrFrameDev* fp = &W.fp;
-  for (uint32_t it = tile.lo; it < hi; ++it) {
-    const SbrFrameDev* g = k4_frame(sframes, run, it);
-    const int mode = g->mode;
-    if (g->frame_status != 0 || mode == 0) continue;
-    float* X = Xrun + 32 * (size_t)n_done * kXgRow;   // row 0 of this frame's Xsbr
-    ++n_done;
-    last_it = it;
-    if (mode != 2) continue;
-    __syncwarp();
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(g);
-      uint4* dst = reinterpret_cast<uint4*>(&W.fp);
-      for (int i = lane; i < (int)(sizeof(SbrFrameDev) / 16); i += 32) dst[i] = src[i];
-    }
-    __syncwarp();
-    const int kx = fp->kx, M = fp->M, L_E = fp->L_E;
-    const int first_slot = fp->t_E[0], last_slot = fp->t_E[L_E];
-    // calc_chirp_factors (HFGeneration.java:230-245): lane i < N_Q
-    if (lane < 8) {
-      float bw = 0.f;
-      if (lane < fp->N_Q) {
-        const int mode_i = fp->bs_invf_mode[lane];
-        switch (mode_i) {
-          case 1: bw = (invf_prev == 0) ? 0.6f : 0.75f; break;
-          case 2: bw = 0.9f; break;
-          case 3: bw = 0.98f; break;
-          default: bw = (invf_prev == 1) ? 0.6f : 0.0f; break;
-        }
-        if (bw < bw_prev) bw = (bw * 0.75f) + (bw_prev * 0.25f);
-        else bw = (bw * 0.90625f) + (bw_prev * 0.09375f);
-        if (bw < 0.015625f) bw = 0.0f;
-        if (bw >= 0.99609375f) bw = 0.99609375f;
-        bw_prev = bw;
-        invf_prev = mode_i;
-      }
-      W.bw[lane] = bw;
-    }
-    __syncwarp();
-    // ---- HF generation: one lane per generated band (band x of the concatenated patches)
-    for (int x0 = 0; kx + x0 < 64; x0 += 32) {
-      const int k = kx + x0 + lane;
-      if (k >= 64) continue;
-      int i = 0, x = x0 + lane;
-      while (i < fp->noPatches && x >= fp->patchNoSubbands[i]) { x -= fp->patchNoSubbands[i]; ++i; }
-      if (i >= fp->noPatches) continue;
-      const int p = fp->patchStartSubband[i] + x;
-      const float bw = W.bw[fp->table_map_k_to_g[k]];
-      const float bw2 = bw * bw;
-      const int offset = kSbrHfAdj;
-      const float* src = X + 2 * p;
-      float* dst = X + 2 * k;
-      if (bw2 > 0) {
-        // calc_prediction_coef / auto_correlation (:100-204), len = numTimeSlotsRate + 6
-        float r01r = 0, r01i = 0, r02r = 0, r02i = 0, r11r = 0;
-        float temp1_r, temp1_i, temp2_r, temp2_i, temp3_r, temp3_i, temp4_r, temp4_i, temp5_r, temp5_i;
-        const float rel = 1.0f / (1 + 1e-6f);
-        float2 v = ldg2(src + (offset - 2) * kXgRow);
-        temp2_r = v.x; temp2_i = v.y;
-        v = ldg2(src + (offset - 1) * kXgRow);
-        temp3_r = v.x; temp3_i = v.y;
-        temp4_r = temp2_r; temp4_i = temp2_i; temp5_r = temp3_r; temp5_i = temp3_i;
-        temp1_r = 0; temp1_i = 0;
-#pragma unroll 2
-        for (int j = offset; j < kSbrSlots + 6 + offset; j++) {
-          temp1_r = temp2_r; temp1_i = temp2_i;
-          temp2_r = temp3_r; temp2_i = temp3_i;
-          v = ldg2(src + j * kXgRow);
-          temp3_r = v.x; temp3_i = v.y;
-          r01r += temp3_r * temp2_r + temp3_i * temp2_i;
-          r01i += temp3_i * temp2_r - temp3_r * temp2_i;
-          r02r += temp3_r * temp1_r + temp3_i * temp1_i;
-          r02i += temp3_i * temp1_r - temp3_r * temp1_i;
-          r11r += temp2_r * temp2_r + temp2_i * temp2_i;
-        }
-        const float r12r = r01r - (temp3_r * temp2_r + temp3_i * temp2_i) + (temp5_r * temp4_r + temp5_i * temp4_i);
-        const float r12i = r01i - (temp3_i * temp2_r - temp3_r * temp2_i) + (temp5_i * temp4_r - temp5_r * temp4_i);
-        const float r22r = r11r - (temp2_r * temp2_r + temp2_i * temp2_i) + (temp4_r * temp4_r + temp4_i * temp4_i);
-        const float det = (r11r * r22r) - (rel * ((r12r * r12r) + (r12i * r12i)));
-        float al0r, al0i, al1r, al1i;
-        if (det == 0) { al1r = 0; al1i = 0; }
-        else {
-          const float tmp = 1.0f / det;
-          al1r = ((r01r * r12r) - (r01i * r12i) - (r02r * r11r)) * tmp;
-          al1i = ((r01i * r12r) + (r01r * r12i) - (r02i * r11r)) * tmp;
-        }
-        if (r11r == 0) { al0r = 0; al0i = 0; }
-        else {
-          const float tmp = 1.0f / r11r;
-          al0r = -(r01r + (al1r * r12r) + (al1i * r12i)) * tmp;
-          al0i = -(r01i + (al1i * r12r) - (al1r * r12i)) * tmp;
-        }
-        if (((al0r * al0r) + (al0i * al0i) >= 16.0f) || ((al1r * al1r) + (al1i * al1i) >= 16.0f)) { al0r = 0; al0i = 0; al1r = 0; al1i = 0; }
-        const float a0_r = (al0r * bw), a1_r = (al1r * bw2), a0_i = (al0i * bw), a1_i = (al1i * bw2);
-        v = ldg2(src + (first_slot - 2 + offset) * kXgRow);
-        temp2_r = v.x; temp2_i = v.y;
-        v = ldg2(src + (first_slot - 1 + offset) * kXgRow);
-        temp3_r = v.x; temp3_i = v.y;
-#pragma unroll 2
-        for (int l = first_slot; l < last_slot; l++) {
-          temp1_r = temp2_r; temp2_r = temp3_r;
-          temp1_i = temp2_i; temp2_i = temp3_i;
-          v = ldg2(src + (l + offset) * kXgRow);
-          temp3_r = v.x; temp3_i = v.y;
-          st2(dst + (l + offset) * kXgRow,
-              temp3_r + ((a0_r * temp2_r) - (a0_i * temp2_i) + (a1_r * temp1_r) - (a1_i * temp1_i)),
-              temp3_i + ((a0_i * temp2_r) + (a0_r * temp2_i) + (a1_i * temp1_r) + (a1_r * temp1_i)));
-        }
-      } else {
-        for (int l = first_slot; l < last_slot; l++) {
-          const float2 v = ldg2(src + (l + offset) * kXgRow);
-          st2(dst + (l + offset) * kXgRow, v.x, v.y);
-        }
-      }
-    }
-    __syncwarp();
-
-    // ---- HF adjustment.  `new HFAdjustment()` per call: the boost arrays start from zero; the limiter table does not
-    // always reach M (FBT.limiter_frequency_table sorts a shrinking prefix) and bands it leaves out keep gain 0.
-    for (int i = lane; i < 3 * kSbrMaxLE * 64; i += 32) (&W.G[0][0])[i] = 0.f;
-    // estimate_current_envelope (:78-131): lane per band m
-    for (int m = lane; m < M; m += 32) {
-      for (int l = 0; l < L_E; l++) {
-        const int l_i = fp->t_E[l], u_i = fp->t_E[l + 1];
-        float nrg = 0, div;
-        if (fp->interpol_freq) {
-          div = (float)(u_i - l_i);
-          if (div == 0) div = 1;
-          const float* col = X + 2 * (m + kx);
-#pragma unroll 4
-          for (int i = l_i + kSbrHfAdj; i < u_i + kSbrHfAdj; i++) {
-            const float2 v = ldg2(col + i * kXgRow);
-            nrg += (v.x * v.x) + (v.y * v.y);
-          }
-        } else {
-          // the band of the envelope's resolution that holds k = m + kx
-          const int res = fp->f[l], nb = res ? fp->N_high : fp->N_low;
-          int p = 0;
-          while (p + 1 < nb && fp->f_table_res[res][p + 1] <= m + kx) ++p;
-          const int k_l = fp->f_table_res[res][p], k_h = fp->f_table_res[res][p + 1];
-          div = (float)((u_i - l_i) * (k_h - k_l));
-          if (div == 0) div = 1;
-          for (int i = l_i + kSbrHfAdj; i < u_i + kSbrHfAdj; i++)
-            for (int j = k_l; j < k_h; j++) {
-              const float2 v = ldg2(X + i * kXgRow + 2 * j);
-              nrg += (v.x * v.x) + (v.y * v.y);
-            }
-        }
-        W.E_curr[l][m] = nrg / div;
-      }
-    }
-    __syncwarp();
-
-    // calculate_gain (:242-415)
-    const float EPS = 1e-12f;
-    const int l_A = fp->l_A;
-    const bool flag_prev = fp->add_harmonic_flag_prev != 0;
-    const int N_L = fp->N_L;
-    float limg;
-    switch (fp->limiter_gains) { case 0: limg = 0.5f; break; case 1: limg = 1.0f; break; case 2: limg = 2.0f; break; default: limg = 1e10f; break; }
-    auto get_S_mapped = [&](int l, int res, int current_band) -> int {   // :46-76
-      if (res == SBR_HI_RES) {
-        if ((l >= l_A) || (fp->bs_add_harmonic_prev[current_band] != 0 && flag_prev)) return fp->bs_add_harmonic[current_band];
-      } else {
-        const int odd = (fp->N_high & 1) ? 1 : 0;
-        const int lb = 2 * current_band - odd, ub = 2 * (current_band + 1) - odd;
-        for (int b = max(lb, 0); b < ub && b < 64; b++)
-          if ((l >= l_A) || (fp->bs_add_harmonic_prev[b] != 0 && flag_prev)) { if (fp->bs_add_harmonic[b] == 1) return 1; }
-      }
-      return 0;
-    };
-    auto t_noise_band = [&](int l) -> int {   // current_t_noise_band advances once per envelope whose end passes t_Q
-      int tb = 0;
-      for (int ll = 0; ll <= l; ++ll)
-        if (fp->t_E[ll + 1] > fp->t_Q[tb + 1]) tb++;
-      return tb;
-    };
-    // The reference walks m with running band counters; when every band table is strictly increasing and starts where
-    // it should, the counters equal plain lookups and the work splits over (envelope, band).  Anything else takes the
-    // literal walk below.
-    bool regular;
-    {
-      bool bad = N_L > kK4bMaxNL || N_L < 1;
-      for (int i = lane; i < 64; i += 32) {
-        if (i < fp->N_low && fp->f_table_res[0][i + 1] <= fp->f_table_res[0][i]) bad = true;
-        if (i < fp->N_high && fp->f_table_res[1][i + 1] <= fp->f_table_res[1][i]) bad = true;
-        if (i < fp->N_Q && i < 7 && fp->f_table_noise[i + 1] <= fp->f_table_noise[i]) bad = true;
-        if (i < N_L && i < 63 && fp->f_table_lim[i + 1] <= fp->f_table_lim[i]) bad = true;
-      }
-      if (fp->f_table_res[0][0] != kx || fp->f_table_res[1][0] != kx || fp->f_table_noise[0] != kx || fp->f_table_lim[0] != 0) bad = true;
-      if (fp->N_Q > 7 || fp->N_low < 1 || fp->N_high < 1 || fp->N_Q < 1) bad = true;
-      if (N_L >= 1 && N_L <= kK4bMaxNL && fp->f_table_lim[N_L] > M) bad = true;
-      regular = !__any_sync(0xFFFFFFFFu, bad);
-    }
-    if (regular) {
-      const int mcov = fp->f_table_lim[N_L];
-      for (int m = lane; m < mcov; m += 32) {
-        const int k = m + kx;
-        int p = 0;
-        while (p + 1 < fp->N_low && fp->f_table_res[0][p + 1] <= k) ++p;
-        W.rb[0][m] = (uint8_t)p;
-        p = 0;
-        while (p + 1 < fp->N_high && fp->f_table_res[1][p + 1] <= k) ++p;
-        W.rb[1][m] = (uint8_t)p;
-        p = 0;
-        while (p + 1 < fp->N_Q && fp->f_table_noise[p + 1] <= k) ++p;
-        W.nb[m] = (uint8_t)p;
-        p = 0;
-        while (p + 1 < N_L && fp->f_table_lim[p + 1] <= m) ++p;
-        W.lb[m] = (uint8_t)p;
-      }
-      __syncwarp();
-      // limiter-band sums, in band order as the reference adds them
-      for (int task = lane; task < L_E * N_L; task += 32) {
-        const int l = task / N_L, kb = task - l * N_L, res = fp->f[l];
-        float acc1 = 0, acc2 = 0;
-        for (int m = fp->f_table_lim[kb]; m < fp->f_table_lim[kb + 1]; m++) {
-          acc1 += fp->E_orig[l][W.rb[res][m]];
-          acc2 += W.E_curr[l][m];
-        }
-        float G_max = ((EPS + acc1) / (EPS + acc2)) * limg;
-        G_max = fminf(G_max, 1e10f);
-        W.gmax[l][kb] = G_max;
-        W.acc1[l][kb] = acc1;
-      }
-      __syncwarp();
-      for (int m = lane; m < mcov; m += 32) {
-        const int k = m + kx;
-        const int hb = W.rb[1][m];
-        const bool centre = k == ((fp->f_table_res[SBR_HI_RES][hb + 1] + fp->f_table_res[SBR_HI_RES][hb]) >> 1);
-        for (int l = 0; l < L_E; ++l) {
-          const int res = fp->f[l];
-          const int rb = W.rb[res][m];
-          const int S_mapped = get_S_mapped(l, res, rb);
-          int S_index_mapped = 0;
-          if (((l >= l_A) || (fp->bs_add_harmonic_prev[hb] != 0 && flag_prev)) && centre) S_index_mapped = fp->bs_add_harmonic[hb];
-          const int tb = t_noise_band(l);
-          const float delta = (l == l_A || l == fp->prevEnvIsShort) ? 0.f : 1.f;
-          const float Q_div = fp->Q_div[tb][W.nb[m]];
-          const float Q_div2 = fp->Q_div2[tb][W.nb[m]];
-          const float E_o = fp->E_orig[l][rb];
-          const float Q_M = E_o * Q_div2;
-          const float S_M = (S_index_mapped == 0) ? 0.f : E_o * Q_div;
-          float G = E_o / (1.0f + W.E_curr[l][m]);
-          if ((S_mapped == 0) && (delta == 1)) G *= Q_div;
-          else if (S_mapped == 1) G *= Q_div2;
-          const float G_max = W.gmax[l][W.lb[m]];
-          float Q_M_lim, G_lim;
-          if (G_max > G) { Q_M_lim = Q_M; G_lim = G; }
-          else { Q_M_lim = Q_M * G_max / G; G_lim = G_max; }
-          W.G[l][m] = G_lim;
-          W.Q[l][m] = Q_M_lim;
-          W.S[l][m] = S_M;
-          W.sflag[l][m] = (uint8_t)(S_index_mapped != 0);
-        }
-      }
-      __syncwarp();
-      for (int task = lane; task < L_E * N_L; task += 32) {
-        const int l = task / N_L, kb = task - l * N_L;
-        float den = 0;
-        for (int m = fp->f_table_lim[kb]; m < fp->f_table_lim[kb + 1]; m++) {
-          const bool sf = W.sflag[l][m] != 0;
-          if (sf) den += W.S[l][m];
-          den += W.E_curr[l][m] * W.G[l][m];
-          if (!sf && (l != l_A)) den += W.Q[l][m];
-        }
-        float G_boost = (W.acc1[l][kb] + EPS) / (den + EPS);
-        G_boost = fminf(G_boost, 2.51188643f);
-        W.boost[l][kb] = G_boost;
-      }
-      __syncwarp();
-      for (int m = lane; m < mcov; m += 32) {
-        for (int l = 0; l < L_E; ++l) {
-          const float G_boost = W.boost[l][W.lb[m]];
-          // (float) Math.sqrt(float product): the double square root of a binary32 value, rounded to binary32, is the
-          // correctly rounded binary32 square root
-          W.G[l][m] = __fsqrt_rn(W.G[l][m] * G_boost);
-          W.Q[l][m] = __fsqrt_rn(W.Q[l][m] * G_boost);
-          const float sm = W.S[l][m];
-          W.S[l][m] = (sm != 0) ? __fsqrt_rn(sm * G_boost) : 0.f;
-        }
-      }
-    } else if (lane < L_E) {
-      // the reference's own loop, one lane per envelope
-      const int l = lane;
-      const int res = fp->f[l];
-      const int current_t_noise_band = t_noise_band(l);
-      int current_f_noise_band = 0, current_res_band = 0, current_res_band2 = 0, current_hi_res_band = 0;
-      const float delta = (l == l_A || l == fp->prevEnvIsShort) ? 0.f : 1.f;
-      int S_mapped = get_S_mapped(l, res, current_res_band2);
-      for (int k = 0; k < N_L; k++) {
-        float den = 0, acc1 = 0, acc2 = 0;
-        const int ml1 = fp->f_table_lim[k], ml2 = fp->f_table_lim[k + 1];
-        for (int m = ml1; m < ml2; m++) {
-          if ((m + kx) == fp->f_table_res[res][current_res_band + 1]) current_res_band++;
-          acc1 += fp->E_orig[l][current_res_band];
-          acc2 += W.E_curr[l][m];
-        }
-        float G_max = ((EPS + acc1) / (EPS + acc2)) * limg;
-        G_max = fminf(G_max, 1e10f);
-        for (int m = ml1; m < ml2; m++) {
-          if ((m + kx) == fp->f_table_noise[current_f_noise_band + 1]) current_f_noise_band++;
-          if ((m + kx) == fp->f_table_res[res][current_res_band2 + 1]) {
-            current_res_band2++;
-            S_mapped = get_S_mapped(l, res, current_res_band2);
-          }
-          if ((m + kx) == fp->f_table_res[SBR_HI_RES][current_hi_res_band + 1]) current_hi_res_band++;
-          int S_index_mapped = 0;
-          if ((l >= l_A) || (fp->bs_add_harmonic_prev[current_hi_res_band] != 0 && flag_prev)) {
-            if ((m + kx) == (fp->f_table_res[SBR_HI_RES][current_hi_res_band + 1] + fp->f_table_res[SBR_HI_RES][current_hi_res_band]) >> 1)
-              S_index_mapped = fp->bs_add_harmonic[current_hi_res_band];
-          }
-          const float Q_div = fp->Q_div[current_t_noise_band][current_f_noise_band];
-          const float Q_div2 = fp->Q_div2[current_t_noise_band][current_f_noise_band];
-          const float E_o = fp->E_orig[l][current_res_band2];
-          const float Q_M = E_o * Q_div2;
-          float S_M;
-          if (S_index_mapped == 0) S_M = 0;
-          else { S_M = E_o * Q_div; den += S_M; }
-          float G = E_o / (1.0f + W.E_curr[l][m]);
-          if ((S_mapped == 0) && (delta == 1)) G *= Q_div;
-          else if (S_mapped == 1) G *= Q_div2;
-          float Q_M_lim, G_lim;
-          if (G_max > G) { Q_M_lim = Q_M; G_lim = G; }
-          else { Q_M_lim = Q_M * G_max / G; G_lim = G_max; }
-          den += W.E_curr[l][m] * G_lim;
-          if ((S_index_mapped == 0) && (l != l_A)) den += Q_M_lim;
-          W.G[l][m] = G_lim;
-          W.Q[l][m] = Q_M_lim;
-          W.S[l][m] = S_M;
-        }
-        float G_boost = (acc1 + EPS) / (den + EPS);
-        G_boost = fminf(G_boost, 2.51188643f);
-        for (int m = ml1; m < ml2; m++) {
-          W.G[l][m] = __fsqrt_rn(W.G[l][m] * G_boost);
-          W.Q[l][m] = __fsqrt_rn(W.Q[l][m] * G_boost);
-          const float sm = W.S[l][m];
-          W.S[l][m] = (sm != 0) ? __fsqrt_rn(sm * G_boost) : 0.f;
-        }
-      }
-    }
-    __syncwarp();
-
-    // hf_assembly (:133-240): lane m (and m + 32) walks the slots; the 5-entry smoothing rings live in registers
-    {
-      int fIndexNoise = fp->reset ? 0 : index_noise_prev;
-      int fIndexSine = psi_is_prev;
-      bool assembly_reset = fp->reset != 0;
-      int slots_done = 0;
-      for (int l = 0; l < L_E; l++) {
-        const bool no_noise = (l == fp->l_A || l == fp->prevEnvIsShort);
-        int h_SL = fp->smoothing_mode ? 0 : 4;
-        h_SL = no_noise ? 0 : h_SL;
-        float g_new[2], q_new[2], s_m[2];
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          const int m = lane + 32 * p;
-          const bool active = m < M;
-          g_new[p] = active ? W.G[l][m] : 0.f;
-          q_new[p] = active ? W.Q[l][m] : 0.f;
-          s_m[p] = active ? W.S[l][m] : 0.f;
-        }
-        // System.arraycopy(.., 0, .., 0, sbr.M): ring entries of bands >= M keep their old contents
-        if (assembly_reset) {
-#pragma unroll
-          for (int p = 0; p < 2; ++p)
-            if (lane + 32 * p < M) {
-#pragma unroll
-              for (int n = 0; n < 4; ++n) { Gt[p][n] = g_new[p]; Qt[p][n] = q_new[p]; }
-            }
-          ring_index = 4;
-          assembly_reset = false;
-        }
-        for (int i = fp->t_E[l]; i < fp->t_E[l + 1]; i++) {
-          const int phi_re = fIndexSine == 0 ? 1 : (fIndexSine == 2 ? -1 : 0);
-          const int phi_im = fIndexSine == 1 ? 1 : (fIndexSine == 3 ? -1 : 0);
-#pragma unroll
-          for (int p = 0; p < 2; ++p) {
-            const int m = lane + 32 * p;
-            if (m >= M) continue;
-#pragma unroll
-            for (int n = 0; n < 5; ++n) if (n == ring_index) { Gt[p][n] = g_new[p]; Qt[p][n] = q_new[p]; }
-            float G_filt = 0, Q_filt = 0;
-            if (h_SL != 0) {
-              int ri = ring_index;
-#pragma unroll
-              for (int n = 0; n <= 4; n++) {
-                const float h = n == 0 ? 0.03183050093751f : n == 1 ? 0.11516383427084f : n == 2 ? 0.21816949906249f
-                              : n == 3 ? 0.30150283239582f : 0.33333333333333f;
-                ri++;
-                if (ri >= 5) ri -= 5;
-                float gv = Gt[p][0], qv = Qt[p][0];
-#pragma unroll
-                for (int z = 1; z < 5; ++z) if (z == ri) { gv = Gt[p][z]; qv = Qt[p][z]; }
-                G_filt += (gv * h);
-                Q_filt += (qv * h);
-              }
-            } else {
-#pragma unroll
-              for (int z = 0; z < 5; ++z) if (z == ring_index) { G_filt = Gt[p][z]; Q_filt = Qt[p][z]; }
-            }
-            Q_filt = (s_m[p] != 0 || no_noise) ? 0 : Q_filt;
-            const int ni = (fIndexNoise + slots_done * M + m + 1) & 511;
-            float* x = X + (size_t)(i + kSbrHfAdj) * kXgRow + 2 * (m + kx);
-            const float2 xv = ldg2(x);
-            const float2 nz = __ldg(reinterpret_cast<const float2*>(T.noise_table) + ni);
-            float x0 = G_filt * xv.x + (Q_filt * nz.x);
-            float x1 = G_filt * xv.y + (Q_filt * nz.y);
-            const int rev = (((m + kx) & 1) != 0 ? -1 : 1);
-            x0 += s_m[p] * (float)phi_re;
-            x1 += (float)rev * s_m[p] * (float)phi_im;
-            st2(x, x0, x1);
-          }
-          ++slots_done;
-          fIndexSine = (fIndexSine + 1) & 3;
-          ring_index++;
-          if (ring_index >= 5) ring_index = 0;
-        }
-      }
-      index_noise_prev = (fIndexNoise + slots_done * M) & 511;
-      psi_is_prev = fIndexSine;
-    }
-  }
-  __syncwarp();
-
-  // ---- recursive state out
-#pragma unroll
-  for (int p = 0; p < 2; ++p)
-#pragma unroll
-    for (int n = 0; n < 5; ++n) { st->G_temp_prev[n][lane + 32 * p] = Gt[p][n]; st->Q_temp_prev[n][lane + 32 * p] = Qt[p][n]; }
-  if (lane < 8) { st->bwArray_prev[lane] = bw_prev; st->bs_invf_mode_prev[lane] = (uint8_t)invf_prev; }
-  if (lane == 0) { st->GQ_ringbuf_index = ring_index; st->index_noise_prev = index_noise_prev; st->psi_is_prev = psi_is_prev; }
-  if (last_it >= 0) {
-    // what the next tile's analysis starts from: the last 288 core samples and rows 32..39 of the last processed frame
-    const float* cs = core + ((size_t)run_frames[run.first + last_it].ics_base + run.ch_slot) * 1024 + 736;
-    for (int i = lane; i < 288; i += 32) st->ana_hist[i] = cs[i];
-    const float4* s4 = reinterpret_cast<const float4*>(Xrun + 32 * (size_t)n_done * kXgRow);
-    float4* d4 = reinterpret_cast<float4*>(&st->xsbr[0][0][0]);
-    for (int i = lane; i < kSbrHfGen * 32; i += 32) d4[i] = __ldcg(s4 + i);
-  }
-}
-
-// ---- K4c: 64-band QMF synthesis (sbr/SynthesisFilterbank64.java:9-79) + PCM pack (S/SampleBuffer.java:168-209)
-constexpr int kK4cThreads = 64;
-constexpr int kK4cRows = 9 + 32;   // the nine inherited slots, then the frame's 32
-constexpr int kK4cXs = kK4cRows * kXsStride + 3, kK4cVb = kK4cRows * kVbStride + 3;
-static_assert(kK4cXs % 4 == 0 && kK4cVb % 4 == 0, "16-byte aligned regions");
-constexpr size_t k4c_smem_bytes() { return sizeof(float) * (kK4cXs + kK4cVb); }
-
-// the two DCT-IVs of one slot: `row` = the slot's 64 complex QMF samples (band limit already applied), v = its 128-entry v-vector
-__device__ __forceinline__ void sbr_synth_slot(const float* __restrict__ row, float* __restrict__ v) {
-  const float scale = 1.f / 64.f;
-  float in_r[32], in_i[32], o1r[32], o1i[32], o2r[32], o2i[32];
-  in_i[31] = scale * row[2 * 1];
-  in_r[0] = scale * row[0];
-#pragma unroll
-  for (int k = 1; k < 31; k++) { in_i[31 - k] = scale * row[2 * (2 * k + 1)]; in_r[k] = scale * row[2 * (2 * k)]; }
-  in_i[0] = scale * row[2 * 63];
-  in_r[31] = scale * row[2 * 62];
-  sbr_dct4_kernel(in_r, in_i, o1r, o1i);
-  in_i[31] = scale * row[2 * (63 - 1) + 1];
-  in_r[0] = scale * row[2 * 63 + 1];
-#pragma unroll
-  for (int k = 1; k < 31; k++) { in_i[31 - k] = scale * row[2 * (63 - (2 * k + 1)) + 1]; in_r[k] = scale * row[2 * (63 - 2 * k) + 1]; }
-  in_i[0] = scale * row[1];
-  in_r[31] = scale * row[2 * (63 - 62) + 1];
-  sbr_dct4_kernel(in_r, in_i, o2r, o2i);
-#pragma unroll
-  for (int n = 0; n < 32; n++) {
-    v[2 * n] = o2r[n] - o1r[n];
-    v[127 - 2 * n] = o2r[n] + o1r[n];
-    v[2 * n + 1] = o2i[31 - n] + o1i[31 - n];
-    v[127 - (2 * n + 1)] = o2i[31 - n] - o1i[31 - n];
-  }
-}
-
-// X[l][k] = Xsbr[l + tHFAdj][k] below kx + M of the slot's frame, 0 above (Channel.process_channel, SBR.java:604-645)
-__device__ __forceinline__ int k4_x_limit(const SbrFrameDev* fp, int mode, int l) {
-  if (mode == 2) return (l < fp->t_E[0]) ? (fp->kx_prev + fp->M_prev) : (fp->kx + fp->M);
-  return 32;
-}
-
-template <int PCM_FORMAT>
-__global__ void __launch_bounds__(kK4cThreads)
-k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, const RunFrameDev* __restrict__ run_frames,
-                     const SbrFrameDev* __restrict__ sframes, const float* __restrict__ core, SbrChanDev* __restrict__ chans,
-                     const float* __restrict__ xg, uint8_t* __restrict__ pcm, const uint64_t* __restrict__ pcm_off,
-                     uint32_t* __restrict__ pcm_bytes_out, SbrTablesDev T, K4Tile tile) {
-  extern __shared__ __align__(16) float k4c_smem[];
-  float* xs = k4c_smem;            // [41][kXsStride]: rows 0..8 = slots -9..-1, rows 9..40 = slots 0..31
-  float* vb = k4c_smem + kK4cXs;   // [41][kVbStride]
-  const int t = threadIdx.x;
-  const uint32_t r = blockIdx.x / tile.ft, it = tile.lo + blockIdx.x % tile.ft;
-  const K4RunDev run = runs[r];
-  if (it >= run.count) return;
-  const SbrFrameDev* fp = k4_frame(sframes, run, it);
-  const RunFrameDev rf = run_frames[run.first + it];
-  const uint32_t f = rf.frame;
-  const int mode = fp->mode;
-  uint8_t* dst = pcm + pcm_off[f];
-  const int n_out = run.n_out;
-  if (fp->frame_status != 0) {
-    if (t == 0 && run.out_ch == 0) pcm_bytes_out[f] = 0;
-    return;
-  }
-  if (t == 0 && run.out_ch == 0) pcm_bytes_out[f] = (uint32_t)(2048 * n_out * (PCM_FORMAT == 2 ? 4 : 2));
-  const bool dup = run.dup != 0;
-  const bool pair_store = dup && run.out_ch == 0 && n_out == 2 && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0;
-  auto put_sample = [&](int i, float v) {
-    if (PCM_FORMAT == 2) {
-      float* d = reinterpret_cast<float*>(dst);
-      d[(size_t)run.out_ch * 2048 + i] = v;
-      if (dup) d[(size_t)(run.out_ch + 1) * 2048 + i] = v;
-    } else {
-      uint32_t u = (uint32_t)pcm_round(v) & 0xFFFFu;
-      if (PCM_FORMAT == 1) u = __byte_perm(u, 0, 0x4401);
-      uint16_t* d = reinterpret_cast<uint16_t*>(dst);
-      if (pair_store) reinterpret_cast<uint32_t*>(d)[i] = u | (u << 16);
-      else {
-        d[(size_t)i * n_out + run.out_ch] = (uint16_t)u;
-        if (dup) d[(size_t)i * n_out + run.out_ch + 1] = (uint16_t)u;
-      }
-    }
-  };
-  const float* cs = core + ((size_t)rf.ics_base + run.ch_slot) * 1024;
-  if (mode == 0) {
-    // no valid SBR data in this frame: SBR.upsample (sbr/SBR.java:302-309; sample 1 keeps the core value)
-    for (int i = t; i < 2048; i += kK4cThreads) put_sample(i, i < 2 ? cs[i] : cs[i >> 1]);
-    return;
-  }
-  const uint32_t o = fp->ord - k4_frame(sframes, run, tile.lo)->ord;
-  const float* X = xg + ((size_t)r * tile.rows + 32 * (size_t)o) * kXgRow;
-  SbrChanDev* st = chans + (size_t)run.stream_slot * kSbrChansPerStream + run.ch_slot;
-  const int sel = st->v_sel;
-  // ---- stage the QMF rows (band limit applied); thread t = band t
-  {
-    const int lim_lo = k4_x_limit(fp, mode, 0), lim_hi = k4_x_limit(fp, mode, 31), first_slot = mode == 2 ? fp->t_E[0] : 0;
-    for (int l = 0; l < 32; ++l) {
-      const int lim = l < first_slot ? lim_lo : lim_hi;
-      float2 v = make_float2(0.f, 0.f);
-      if (t < lim) v = __ldg(reinterpret_cast<const float2*>(X + (size_t)(l + kSbrHfAdj) * kXgRow) + t);
-      xs[(9 + l) * kXsStride + 2 * t] = v.x;
-      xs[(9 + l) * kXsStride + 2 * t + 1] = v.y;
-    }
-    if (o > 0) {
-      // slots 23..31 of the previous processed frame: its rows 25..33 = rows -7..1 here
-      const SbrFrameDev* fq = k4_frame(sframes, run, it - fp->back);
-      const int mq = fq->mode;
-      for (int h = 0; h < 9; ++h) {
-        const int lim = k4_x_limit(fq, mq, 23 + h);
-        float2 v = make_float2(0.f, 0.f);
-        if (t < lim) v = __ldg(reinterpret_cast<const float2*>(X + ((ptrdiff_t)h - 7) * kXgRow) + t);
-        xs[h * kXsStride + 2 * t] = v.x;
-        xs[h * kXsStride + 2 * t + 1] = v.y;
-      }
-    } else {
-      // carried v-vectors: row 8 is the newest (slot -1), row 0 the oldest (slot -9); syn_v[.][0] = newest
-      for (int i = t; i < 9 * 128; i += kK4cThreads) vb[(8 - i / 128) * kVbStride + (i % 128)] = st->syn_v[sel][i / 128][i % 128];
-    }
-  }
-  __syncthreads();
-  if (t < 32) sbr_synth_slot(xs + (9 + t) * kXsStride, vb + (9 + t) * kVbStride);
-  else if (o > 0 && t < 41) sbr_synth_slot(xs + (t - 32) * kXsStride, vb + (t - 32) * kVbStride);
-  __syncthreads();
-  // ---- window + output: thread k, all 32 slots
-  float qc[10];
-#pragma unroll
-  for (int j = 0; j < 10; ++j) qc[j] = c_sbr_qmf_c[t + 64 * j];
-  for (int l = 0; l < 32; ++l) {
-    const int cur = 9 + l;
-    float ov = (vb[cur * kVbStride + t] * qc[0]);
-#pragma unroll
-    for (int j = 1; j < 10; ++j) ov = ov + (vb[(cur - j) * kVbStride + t + 64 * (j & 1)] * qc[j]);
-    put_sample(64 * l + t, ov);
-  }
-  // ---- the tile's last processed frame hands its nine newest v-vectors to the next tile
-  const uint32_t fwd = fp->fwd;
-  if (fwd == 0 || it + fwd >= tile.lo + tile.ft) {
-    for (int i = t; i < 9 * 128; i += kK4cThreads) st->syn_v[sel ^ 1][i / 128][i % 128] = vb[(40 - i / 128) * kVbStride + (i % 128)];
-    if (t == 0) st->v_flip = 1;
-  }
-}
-
-__global__ void k4_commit_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, SbrChanDev* __restrict__ chans) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_runs) return;
-  SbrChanDev* st = chans + (size_t)runs[r].stream_slot * kSbrChansPerStream + runs[r].ch_slot;
-  if (st->v_flip) { st->v_sel ^= 1; st->v_flip = 0; }
 }
 
 }  // namespace jaadb

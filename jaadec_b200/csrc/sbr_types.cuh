@@ -132,10 +132,14 @@ struct __align__(16) PsChanDev {
   float delay_sub_ser[12][3][5][2];
   float P_PeakDecayNrg[20], P_prev[20], P_SmoothPeakDecayDiffNrg_prev[20];
   float h_prev[22][4];               // h11, h12, h21, h22 (real parts) per group
-  float syn_v_right[9][128];         // right channel: the 9 most recent synthesis v-vectors ([0] = newest)
+  float syn_v_right[2][9][128];      // right channel: the 9 most recent synthesis v-vectors ([.][0] = newest), double
+                                     // buffered like SbrChanDev::syn_v
   int32_t saved_delay, delay_buf_index_ser[3];
   int32_t delay_buf_index_delay[64];
+  int32_t v_sel, v_flip;
+  int32_t pad[2];
 };
+static_assert(sizeof(PsChanDev) % 16 == 0, "PsChanDev alignment");
 
 // Process-side persistent state of one SBR channel.
 struct __align__(16) SbrChanDev {
