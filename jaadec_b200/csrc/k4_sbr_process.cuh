@@ -1116,11 +1116,15 @@ __global__ void k4_commit_kernel(const K4RunDev* __restrict__ runs, uint32_t n_r
 
 // ---- K5: parametric stereo (ps/PSImpl.java:685-707) for the frames of an SBR+PS stream that carry ps_data: hybrid
 // analysis, transient detection, all-pass decorrelation, H-matrix mixing, hybrid synthesis.  The decorrelator and the
-// transient detector are recursive in time, so one CTA (64 threads: one per QMF band / time slot) walks the frames of the
-// tile in order; input is the finished Xsbr matrix in xg, output the left / right QMF matrices the synthesis kernel reads:
+// transient detector are recursive in time, so one CTA walks the frames of the tile in order with the delay lines in
+// shared memory for the whole tile (96 threads: one per time slot in the filterbank phases; one per band in the
+// decorrelator: threads 3..63 = QMF bands 3..63, threads 64..73 = the ten hybrid sub-bands).  Input is the finished
+// Xsbr matrix in xg, output the left / right QMF matrices the synthesis kernel reads:
 //   xps[ps run][frame of the tile][left, right][32 slots][64 bands][re, im]
-constexpr int kK5Threads = 64;
-constexpr int kK5Floats = 2 * 32 * kXsStride + 2 * 32 * 24 + 32 * 20 + 3 * 88;
+constexpr int kK5Threads = 96;
+constexpr int kK5Bands = 71;        // 10 hybrid sub-bands + QMF bands 3..63
+constexpr int kK5AllPass = 30;      // of which run the all-pass chain: the hybrid ones and QMF bands 3..22
+constexpr int kK5Floats = 2 * 32 * kXsStride + 2 * 32 * 24 + 32 * 20 + 3 * 88 + kK5Bands * 28 + kK5AllPass * 30 + 22 * 4 + 72;
 static_assert(kK5Floats % 4 == 0, "PsFrameDev must land 16-byte aligned");
 constexpr size_t k5_smem_bytes() { return sizeof(float) * kK5Floats + sizeof(PsFrameDev); }
 
@@ -1135,7 +1139,11 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
   float* hyr = hyl + 32 * 24;                            // [32][12][2]
   float* pg = hyr + 32 * 24;                             // [32][20] band energies, then transient ratios
   float* hwork = pg + 32 * 20;                           // [3][44][2] hybrid analysis input
-  PsFrameDev* pp = reinterpret_cast<PsFrameDev*>(hwork + 3 * 88);
+  float* dly = hwork + 3 * 88;                           // [71][14][2] input delay of every decorrelator band
+  float* ser = dly + kK5Bands * 28;                      // [30][3 links][5][2] all-pass delay lines
+  float* hprev = ser + kK5AllPass * 30;                  // [22][4] mixing matrix of the previous envelope, per group
+  float* hybuf = hprev + 22 * 4;                         // [3][12][2] hybrid analysis history
+  PsFrameDev* pp = reinterpret_cast<PsFrameDev*>(hybuf + 72);
 #define XL(l, k, c) xl[(l) * kXsStride + (k) * 2 + (c)]
 #define XR(l, k, c) xr[(l) * kXsStride + (k) * 2 + (c)]
 #define HYL(n, k, c) hyl[((n) * 12 + (k)) * 2 + (c)]
@@ -1148,6 +1156,55 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
   PsChanDev* pst = ps_chans + run.stream_slot;
   const float* Xrun = xg + (size_t)r * tile.rows * kXgRow;
   const uint32_t ord_lo = k4_frame(sframes, run, tile.lo)->ord;
+
+  // ---- the band this thread decorrelates, and its state
+  const bool hyb = t >= 64;
+  const bool band_task = (t >= 3 && t < 64) || (t >= 64 && t < 74);
+  int gr = 0, sb = 0;                                    // group; hybrid sub-band or QMF band
+  if (band_task) {
+    if (hyb) { gr = t - 64; sb = ps_group_border(gr); }
+    else { sb = t; gr = 10; while (ps_group_border(gr + 1) <= sb) ++gr; }
+  }
+  const int bslot = hyb ? gr : 10 + (sb - 3);
+  const bool delay_band = !hyb && sb > 22;
+  const bool allpass = band_task && !delay_band;
+  float* my_dly = dly + bslot * 28;
+  float* my_ser = ser + min(bslot, kK5AllPass - 1) * 30;
+  const int bk = ps_bk(gr);
+  int td = pst->saved_delay, s0 = pst->delay_buf_index_ser[0], s1 = pst->delay_buf_index_ser[1], s2 = pst->delay_buf_index_ser[2];
+  int di = 0;
+  const int dD = sb < 35 ? 14 : 1;
+  if (band_task) {
+    const float* gd = hyb ? &pst->delay_sub[sb][0][0] : &pst->delay_qmf[sb][0][0];
+    const int nd = hyb ? 4 : 28;
+    for (int i = 0; i < nd; ++i) my_dly[i] = gd[i];
+    if (allpass) {
+      const float* gs = hyb ? &pst->delay_sub_ser[sb][0][0][0] : &pst->delay_qmf_ser[sb][0][0][0];
+      for (int i = 0; i < 30; ++i) my_ser[i] = gs[i];
+    }
+    if (delay_band) di = pst->delay_buf_index_delay[sb];
+  }
+  if (t < 22)
+    for (int i = 0; i < 4; ++i) hprev[t * 4 + i] = pst->h_prev[t][i];
+  if (t < 72) hybuf[t] = (&pst->hyb_buffer[0][0][0])[t];
+  float peak = 0, pprev = 0, smooth_prev = 0;   // transient detector of parameter band t
+  if (t < 20) { peak = pst->P_PeakDecayNrg[t]; pprev = pst->P_prev[t]; smooth_prev = pst->P_SmoothPeakDecayDiffNrg_prev[t]; }
+  // per-band constants of the decorrelator (ps/PSImpl.java:266-396)
+  float gf0 = 0, gf1 = 0, gf2 = 0, phi0 = 0, phi1 = 0, q00 = 0, q01 = 0, q10 = 0, q11 = 0, q20 = 0, q21 = 0;
+  if (allpass) {
+    float g_DecaySlope;
+    if (hyb || sb <= 3) g_DecaySlope = 1.0f;
+    else {
+      const int decay = 3 - sb;
+      g_DecaySlope = (decay <= -20) ? 0.f : 1.0f + 0.05f * (float)decay;
+    }
+    gf0 = g_DecaySlope * __ldg(T.ps_filter_a); gf1 = g_DecaySlope * __ldg(T.ps_filter_a + 1); gf2 = g_DecaySlope * __ldg(T.ps_filter_a + 2);
+    phi0 = __ldg((hyb ? T.ps_phi_sub : T.ps_phi_qmf) + 2 * sb); phi1 = __ldg((hyb ? T.ps_phi_sub : T.ps_phi_qmf) + 2 * sb + 1);
+    const float* qf = (hyb ? T.ps_q_sub : T.ps_q_qmf) + sb * 6;
+    q00 = __ldg(qf); q01 = __ldg(qf + 1); q10 = __ldg(qf + 2); q11 = __ldg(qf + 3); q20 = __ldg(qf + 4); q21 = __ldg(qf + 5);
+  }
+  __syncthreads();
+
   for (uint32_t it = tile.lo; it < hi; ++it) {
     const SbrFrameDev* fp = k4_frame(sframes, run, it);
     const int mode = fp->mode;
@@ -1155,305 +1212,302 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
     const PsFrameDev* pf = ps_frames + run.ps_base + it;
     if (pf->use_ps == 0) continue;
     __syncthreads();
-    if (t < (int)(sizeof(PsFrameDev) / 16)) reinterpret_cast<uint4*>(pp)[t] = reinterpret_cast<const uint4*>(pf)[t];
-    __syncthreads();
+    if (t < (int)(sizeof(PsFrameDev) / 16)) reinterpret_cast<uint4*>(pp)[t] = __ldg(reinterpret_cast<const uint4*>(pf) + t);
     const float* X = Xrun + 32 * (size_t)(fp->ord - ord_lo) * kXgRow;
-    {
-      // ================= parametric stereo (ps/PSImpl.java) =================
-      const int num_env = pp->num_env;
-      // X_left: the band-limited copy of Xsbr (SBR1.processPS); hybrid analysis input: QMF bands 0..2 of slots 6..37
-      {
-        const int lim_lo = k4_x_limit(fp, mode, 0), lim_hi = k4_x_limit(fp, mode, 31), fs = mode == 2 ? fp->t_E[0] : 0;
-        float2 xv[32];
+    // X_left: the band-limited copy of Xsbr (SBR1.processPS); hybrid analysis input: QMF bands 0..2 of slots 6..37
+    if (t < 64) {
+      const int lim_lo = k4_x_limit(fp, mode, 0), lim_hi = k4_x_limit(fp, mode, 31), fs = mode == 2 ? fp->t_E[0] : 0;
+      float2 xv[32];
 #pragma unroll
-        for (int l = 0; l < 32; ++l) xv[l] = __ldg(reinterpret_cast<const float2*>(X + (size_t)(l + kSbrHfAdj) * kXgRow) + t);
+      for (int l = 0; l < 32; ++l) xv[l] = __ldg(reinterpret_cast<const float2*>(X + (size_t)(l + kSbrHfAdj) * kXgRow) + t);
 #pragma unroll
-        for (int l = 0; l < 32; ++l) {
-          const int lim = l < fs ? lim_lo : lim_hi;
-          XL(l, t, 0) = t < lim ? xv[l].x : 0.f;
-          XL(l, t, 1) = t < lim ? xv[l].y : 0.f;
-        }
+      for (int l = 0; l < 32; ++l) {
+        const int lim = l < fs ? lim_lo : lim_hi;
+        XL(l, t, 0) = t < lim ? xv[l].x : 0.f;
+        XL(l, t, 1) = t < lim ? xv[l].y : 0.f;
       }
-      for (int i = t; i < 3 * 44; i += kK4Threads) {
+    } else {
+      // work[0..11] = history, work[12 + n] = X[n + 6][band]: rows 6..31 come from X_left, rows 32..37 straight
+      // from Xsbr (:108-113) -- for bands 0..2 both are the unmodified analysis output
+      for (int i = t - 64; i < 3 * 44; i += 32) {
         const int band = i / 44, j = i % 44;
-        // work[0..11] = history, work[12 + n] = X[n + 6][band]: rows 6..31 come from X_left, rows 32..37 straight
-        // from Xsbr (:108-113) -- for bands 0..2 both are the unmodified analysis output
-        hwork[(band * 44 + j) * 2] = j < 12 ? pst->hyb_buffer[band][j][0] : __ldg(X + (size_t)(j - 12 + 6 + kSbrHfAdj) * kXgRow + 2 * band);
-        hwork[(band * 44 + j) * 2 + 1] = j < 12 ? pst->hyb_buffer[band][j][1] : __ldg(X + (size_t)(j - 12 + 6 + kSbrHfAdj) * kXgRow + 2 * band + 1);
+        float2 v;
+        if (j < 12) v = make_float2(hybuf[(band * 12 + j) * 2], hybuf[(band * 12 + j) * 2 + 1]);
+        else v = __ldg(reinterpret_cast<const float2*>(X + (size_t)(j - 12 + 6 + kSbrHfAdj) * kXgRow) + band);
+        hwork[(band * 44 + j) * 2] = v.x;
+        hwork[(band * 44 + j) * 2 + 1] = v.y;
       }
-      __syncthreads();
-      if (t < 36) { const int band = t / 12, j = t % 12; pst->hyb_buffer[band][j][0] = hwork[(band * 44 + 32 + j) * 2]; pst->hyb_buffer[band][j][1] = hwork[(band * 44 + 32 + j) * 2 + 1]; }
-      // ---- hybrid analysis (ps/Filterbank.java:18-68): thread n
-      if (t < 32) {
-        const int i = t;
-        {
-          // Filter8 (ps/Filter8.java:53-122) on QMF band 0
-          const float* b = hwork;
-          float f[7];
+    }
+    __syncthreads();
+    const int num_env = pp->num_env;
+    if (t >= 32 && t < 68) { const int u = t - 32, band = u / 12, j = u % 12; hybuf[(band * 12 + j) * 2] = hwork[(band * 44 + 32 + j) * 2]; hybuf[(band * 12 + j) * 2 + 1] = hwork[(band * 44 + 32 + j) * 2 + 1]; }
+    // ---- hybrid analysis (ps/Filterbank.java:18-68): thread n
+    if (t < 32) {
+      const int i = t;
+      {
+        // Filter8 (ps/Filter8.java:53-122) on QMF band 0
+        const float* b = hwork;
+        float f[7];
 #pragma unroll
-          for (int z = 0; z < 7; ++z) f[z] = __ldg(T.ps_p8 + z);
+        for (int z = 0; z < 7; ++z) f[z] = __ldg(T.ps_p8 + z);
 #define BR(k) b[((k) + i) * 2]
 #define BI(k) b[((k) + i) * 2 + 1]
-          auto dct3 = [](float (&y)[4], const float (&x)[4]) {   // DCT3_4_unscaled (:124-138)
-            const float f0 = (x[2] * 0.7071067811865476f);
-            const float f1 = x[0] - f0;
-            const float f2 = x[0] + f0;
-            const float f3 = x[1] + x[3];
-            const float f4 = (x[1] * 1.3065629648763766f);
-            const float f5 = (f3 * (-0.9238795325112866f));
-            const float f6 = (x[3] * (-0.5411961001461967f));
-            const float f7 = f4 + f5;
-            const float f8 = f6 - f5;
-            y[3] = f2 - f8; y[0] = f2 + f8; y[2] = f1 - f7; y[1] = f1 + f7;
-          };
-          float re1[4], im1[4], re2[4], im2[4], x[4], y[4];
-          re1[0] = (f[6] * BR(6));
-          re1[1] = (f[5] * (BR(5) + BR(7)));
-          re1[2] = -(f[0] * (BR(0) + BR(12))) + (f[4] * (BR(4) + BR(8)));
-          re1[3] = -(f[1] * (BR(1) + BR(11))) + (f[3] * (BR(3) + BR(9)));
-          im1[0] = (f[5] * (BI(7) - BI(5)));
-          im1[1] = (f[0] * (BI(12) - BI(0))) + (f[4] * (BI(8) - BI(4)));
-          im1[2] = (f[1] * (BI(11) - BI(1))) + (f[3] * (BI(9) - BI(3)));
-          im1[3] = (f[2] * (BI(10) - BI(2)));
+        auto dct3 = [](float (&y)[4], const float (&x)[4]) {   // DCT3_4_unscaled (:124-138)
+          const float f0 = (x[2] * 0.7071067811865476f);
+          const float f1 = x[0] - f0;
+          const float f2 = x[0] + f0;
+          const float f3 = x[1] + x[3];
+          const float f4 = (x[1] * 1.3065629648763766f);
+          const float f5 = (f3 * (-0.9238795325112866f));
+          const float f6 = (x[3] * (-0.5411961001461967f));
+          const float f7 = f4 + f5;
+          const float f8 = f6 - f5;
+          y[3] = f2 - f8; y[0] = f2 + f8; y[2] = f1 - f7; y[1] = f1 + f7;
+        };
+        float re1[4], im1[4], re2[4], im2[4], x[4], y[4];
+        re1[0] = (f[6] * BR(6));
+        re1[1] = (f[5] * (BR(5) + BR(7)));
+        re1[2] = -(f[0] * (BR(0) + BR(12))) + (f[4] * (BR(4) + BR(8)));
+        re1[3] = -(f[1] * (BR(1) + BR(11))) + (f[3] * (BR(3) + BR(9)));
+        im1[0] = (f[5] * (BI(7) - BI(5)));
+        im1[1] = (f[0] * (BI(12) - BI(0))) + (f[4] * (BI(8) - BI(4)));
+        im1[2] = (f[1] * (BI(11) - BI(1))) + (f[3] * (BI(9) - BI(3)));
+        im1[3] = (f[2] * (BI(10) - BI(2)));
 #pragma unroll
-          for (int n = 0; n < 4; n++) x[n] = re1[n] - im1[3 - n];
-          dct3(y, x);
-          HYL(i, 7, 0) = y[0]; HYL(i, 5, 0) = y[2]; HYL(i, 3, 0) = y[3]; HYL(i, 1, 0) = y[1];
+        for (int n = 0; n < 4; n++) x[n] = re1[n] - im1[3 - n];
+        dct3(y, x);
+        HYL(i, 7, 0) = y[0]; HYL(i, 5, 0) = y[2]; HYL(i, 3, 0) = y[3]; HYL(i, 1, 0) = y[1];
 #pragma unroll
-          for (int n = 0; n < 4; n++) x[n] = re1[n] + im1[3 - n];
-          dct3(y, x);
-          HYL(i, 6, 0) = y[1]; HYL(i, 4, 0) = y[3]; HYL(i, 2, 0) = y[2]; HYL(i, 0, 0) = y[0];
-          im2[0] = (f[6] * BI(6));
-          im2[1] = (f[5] * (BI(5) + BI(7)));
-          im2[2] = -(f[0] * (BI(0) + BI(12))) + (f[4] * (BI(4) + BI(8)));
-          im2[3] = -(f[1] * (BI(1) + BI(11))) + (f[3] * (BI(3) + BI(9)));
-          re2[0] = (f[5] * (BR(7) - BR(5)));
-          re2[1] = (f[0] * (BR(12) - BR(0))) + (f[4] * (BR(8) - BR(4)));
-          re2[2] = (f[1] * (BR(11) - BR(1))) + (f[3] * (BR(9) - BR(3)));
-          re2[3] = (f[2] * (BR(10) - BR(2)));
+        for (int n = 0; n < 4; n++) x[n] = re1[n] + im1[3 - n];
+        dct3(y, x);
+        HYL(i, 6, 0) = y[1]; HYL(i, 4, 0) = y[3]; HYL(i, 2, 0) = y[2]; HYL(i, 0, 0) = y[0];
+        im2[0] = (f[6] * BI(6));
+        im2[1] = (f[5] * (BI(5) + BI(7)));
+        im2[2] = -(f[0] * (BI(0) + BI(12))) + (f[4] * (BI(4) + BI(8)));
+        im2[3] = -(f[1] * (BI(1) + BI(11))) + (f[3] * (BI(3) + BI(9)));
+        re2[0] = (f[5] * (BR(7) - BR(5)));
+        re2[1] = (f[0] * (BR(12) - BR(0))) + (f[4] * (BR(8) - BR(4)));
+        re2[2] = (f[1] * (BR(11) - BR(1))) + (f[3] * (BR(9) - BR(3)));
+        re2[3] = (f[2] * (BR(10) - BR(2)));
 #pragma unroll
-          for (int n = 0; n < 4; n++) x[n] = im2[n] + re2[3 - n];
-          dct3(y, x);
-          HYL(i, 7, 1) = y[0]; HYL(i, 5, 1) = y[2]; HYL(i, 3, 1) = y[3]; HYL(i, 1, 1) = y[1];
+        for (int n = 0; n < 4; n++) x[n] = im2[n] + re2[3 - n];
+        dct3(y, x);
+        HYL(i, 7, 1) = y[0]; HYL(i, 5, 1) = y[2]; HYL(i, 3, 1) = y[3]; HYL(i, 1, 1) = y[1];
 #pragma unroll
-          for (int n = 0; n < 4; n++) x[n] = im2[n] - re2[3 - n];
-          dct3(y, x);
-          HYL(i, 6, 1) = y[1]; HYL(i, 4, 1) = y[3]; HYL(i, 2, 1) = y[2]; HYL(i, 0, 1) = y[0];
+        for (int n = 0; n < 4; n++) x[n] = im2[n] - re2[3 - n];
+        dct3(y, x);
+        HYL(i, 6, 1) = y[1]; HYL(i, 4, 1) = y[3]; HYL(i, 2, 1) = y[2]; HYL(i, 0, 1) = y[0];
 #undef BR
 #undef BI
-        }
-        for (int band = 1; band < 3; ++band) {
-          // Filter2 (ps/Filter2.java:40-68) on QMF bands 1 and 2
-          const float* b = hwork + band * 88;
-          float f[7];
+      }
+      for (int band = 1; band < 3; ++band) {
+        // Filter2 (ps/Filter2.java:40-68) on QMF bands 1 and 2
+        const float* b = hwork + band * 88;
+        float f[7];
 #pragma unroll
-          for (int z = 0; z < 7; ++z) f[z] = __ldg(T.ps_p2 + z);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const float r0 = (f[0] * (b[(0 + i) * 2 + c] + b[(12 + i) * 2 + c]));
-            const float r1 = (f[1] * (b[(1 + i) * 2 + c] + b[(11 + i) * 2 + c]));
-            const float r2 = (f[2] * (b[(2 + i) * 2 + c] + b[(10 + i) * 2 + c]));
-            const float r3 = (f[3] * (b[(3 + i) * 2 + c] + b[(9 + i) * 2 + c]));
-            const float r4 = (f[4] * (b[(4 + i) * 2 + c] + b[(8 + i) * 2 + c]));
-            const float r5 = (f[5] * (b[(5 + i) * 2 + c] + b[(7 + i) * 2 + c]));
-            const float r6 = (f[6] * b[(6 + i) * 2 + c]);
-            HYL(i, 8 + 2 * (band - 1), c) = r0 + r1 + r2 + r3 + r4 + r5 + r6;
-            HYL(i, 9 + 2 * (band - 1), c) = r0 - r1 + r2 - r3 + r4 - r5 + r6;
-          }
-        }
-        // group hybrid channels (:56-66)
+        for (int z = 0; z < 7; ++z) f[z] = __ldg(T.ps_p2 + z);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          HYL(i, 3, c) += HYL(i, 4, c);
-          HYL(i, 4, c) = 0;
-          HYL(i, 2, c) += HYL(i, 5, c);
-          HYL(i, 5, c) = 0;
+          const float r0 = (f[0] * (b[(0 + i) * 2 + c] + b[(12 + i) * 2 + c]));
+          const float r1 = (f[1] * (b[(1 + i) * 2 + c] + b[(11 + i) * 2 + c]));
+          const float r2 = (f[2] * (b[(2 + i) * 2 + c] + b[(10 + i) * 2 + c]));
+          const float r3 = (f[3] * (b[(3 + i) * 2 + c] + b[(9 + i) * 2 + c]));
+          const float r4 = (f[4] * (b[(4 + i) * 2 + c] + b[(8 + i) * 2 + c]));
+          const float r5 = (f[5] * (b[(5 + i) * 2 + c] + b[(7 + i) * 2 + c]));
+          const float r6 = (f[6] * b[(6 + i) * 2 + c]);
+          HYL(i, 8 + 2 * (band - 1), c) = r0 + r1 + r2 + r3 + r4 + r5 + r6;
+          HYL(i, 9 + 2 * (band - 1), c) = r0 - r1 + r2 - r3 + r4 - r5 + r6;
         }
+      }
+      // group hybrid channels (:56-66)
 #pragma unroll
-        for (int k = 0; k < 12; ++k) { HYR(i, k, 0) = 0.f; HYR(i, k, 1) = 0.f; }
-        // ---- energy per parameter band (ps_decorrelate, :213-234): groups in order, sub-bands in order
-        float* P = pg + i * 20;
+      for (int c = 0; c < 2; ++c) {
+        HYL(i, 3, c) += HYL(i, 4, c);
+        HYL(i, 4, c) = 0;
+        HYL(i, 2, c) += HYL(i, 5, c);
+        HYL(i, 5, c) = 0;
+      }
 #pragma unroll
-        for (int bk = 0; bk < 20; ++bk) P[bk] = 0.f;
-        for (int gr = 0; gr < 22; ++gr) {
-          const int bk = ps_bk(gr), lo = ps_group_border(gr), hi = gr < 10 ? lo + 1 : ps_group_border(gr + 1);
-          for (int sb = lo; sb < hi; ++sb) {
-            const float re = gr < 10 ? HYL(i, sb, 0) : XL(i, sb, 0);
-            const float im = gr < 10 ? HYL(i, sb, 1) : XL(i, sb, 1);
-            P[bk] += (re * re) + (im * im);
+      for (int k = 0; k < 12; ++k) { HYR(i, k, 0) = 0.f; HYR(i, k, 1) = 0.f; }
+      // ---- energy per parameter band (ps_decorrelate, :213-234): groups in order, sub-bands in order
+      {
+        constexpr int gb[23] = {6, 7, 0, 1, 2, 3, 9, 8, 10, 11, 3, 4, 5, 6, 7, 8, 9, 11, 14, 18, 23, 35, 64};
+        float P[20];
+#pragma unroll
+        for (int b2 = 0; b2 < 20; ++b2) P[b2] = 0.f;
+#pragma unroll
+        for (int g2 = 0; g2 < 22; ++g2) {
+          const int pb = g2 == 0 ? 1 : (g2 == 1 ? 0 : g2 - 2);
+          const int lo = gb[g2], hi2 = g2 < 10 ? gb[g2] + 1 : gb[g2 + 1];
+#pragma unroll
+          for (int s2 = lo; s2 < hi2; ++s2) {
+            const float re = g2 < 10 ? HYL(i, s2, 0) : XL(i, s2, 0);
+            const float im = g2 < 10 ? HYL(i, s2, 1) : XL(i, s2, 1);
+            P[pb] += (re * re) + (im * im);
           }
         }
+#pragma unroll
+        for (int b2 = 0; b2 < 20; ++b2) pg[i * 20 + b2] = P[b2];
       }
-      __syncthreads();
-      // ---- transient reduction ratio (:236-264): thread bk, sequential in time
-      if (t < 20) {
-        float peak = pst->P_PeakDecayNrg[t], pprev = pst->P_prev[t], smooth_prev = pst->P_SmoothPeakDecayDiffNrg_prev[t];
-        for (int n = 0; n < 32; ++n) {
-          const float Pn = pg[n * 20 + t];
-          const float gamma = 1.5f;
-          peak = (peak * 0.76592833836465f);
-          if (peak < Pn) peak = Pn;
-          float sm = smooth_prev;
-          sm += ((peak - Pn - smooth_prev) * 0.25f);
-          smooth_prev = sm;
-          float nrg = pprev;
-          nrg += ((Pn - pprev) * 0.25f);
-          pprev = nrg;
-          pg[n * 20 + t] = ((sm * gamma) <= nrg) ? 1.0f : (nrg / (sm * gamma));
-        }
-        pst->P_PeakDecayNrg[t] = peak; pst->P_prev[t] = pprev; pst->P_SmoothPeakDecayDiffNrg_prev[t] = smooth_prev;
+    }
+    __syncthreads();
+    // ---- transient reduction ratio (:236-264): thread bk, sequential in time
+    if (t < 20) {
+      for (int n = 0; n < 32; ++n) {
+        const float Pn = pg[n * 20 + t];
+        const float gamma = 1.5f;
+        peak = (peak * 0.76592833836465f);
+        if (peak < Pn) peak = Pn;
+        float sm = smooth_prev;
+        sm += ((peak - Pn - smooth_prev) * 0.25f);
+        smooth_prev = sm;
+        float nrg = pprev;
+        nrg += ((Pn - pprev) * 0.25f);
+        pprev = nrg;
+        pg[n * 20 + t] = ((sm * gamma) <= nrg) ? 1.0f : (nrg / (sm * gamma));
       }
-      __syncthreads();
-      // ---- decorrelation (:266-396) + mixing (ps_mix_phase, :406-681), one band per thread: first the 10 hybrid
-      // sub-bands (threads 0..9), then QMF bands 3..63 (threads 3..63)
-      const int saved_delay = pst->saved_delay;
-      const int ser0 = pst->delay_buf_index_ser[0], ser1 = pst->delay_buf_index_ser[1], ser2 = pst->delay_buf_index_ser[2];
-      int td_end = saved_delay, s0_end = ser0, s1_end = ser1, s2_end = ser2;
+    }
+    // the mixing matrices the groups ended the previous envelope with (read by every band of the group before any of
+    // them stores the new ones)
+    float hp11 = 1.f, hp12 = 0.f, hp21 = 0.f, hp22 = 0.f;
+    if (band_task) { hp11 = hprev[gr * 4]; hp12 = hprev[gr * 4 + 1]; hp21 = hprev[gr * 4 + 2]; hp22 = hprev[gr * 4 + 3]; }
+    __syncthreads();
+    // ---- decorrelation (:266-396) + mixing (ps_mix_phase, :406-681), one band per thread
+    if (band_task) {
       const bool fine = pp->iid_mode >= 3;
       const int num_steps = fine ? 15 : 7;
       const float* sf_iid = T.ps_sf_iid[fine];
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const bool hyb = pass == 0;
-        const bool mine = hyb ? (t < 10) : (t >= 3);
-        if (mine) {
-          int gr, sb;
-          if (hyb) { gr = t; sb = ps_group_border(t); }
-          else { sb = t; gr = 10; while (ps_group_border(gr + 1) <= sb) ++gr; }
-          const int bk = ps_bk(gr);
-          const bool delay_band = !hyb && sb > 22;
-          float g_DecaySlope;
-          if (hyb || sb <= 3) g_DecaySlope = 1.0f;
-          else {
-            const int decay = 3 - sb;
-            g_DecaySlope = (decay <= -20) ? 0.f : 1.0f + 0.05f * (float)decay;
+      float H11 = hp11, H12 = hp12, H21 = hp21, H22 = hp22;
+      float dH11 = 0, dH12 = 0, dH21 = 0, dH22 = 0;
+      int env = -1, env_end = 0;
+      for (int n = 0; n < 32; ++n) {
+        if (n == env_end) {
+          // next envelope: target H from the IID / ICC indices (:424-478), linear interpolation over its length
+          do { ++env; env_end = pp->border[env + 1]; } while (env + 1 < num_env && env_end <= n);
+          int iid_index = pp->iid[env][bk];
+          const int iid_sign = iid_index < 0 ? -1 : 1;
+          iid_index = min(abs(iid_index), num_steps);
+          const int icc_index = min(max((int)pp->icc[env][bk], 0), 7);
+          float h11, h12, h21, h22;
+          if (pp->icc_mode < 3) {
+            const float c_1 = __ldg(sf_iid + num_steps + iid_index), c_2 = __ldg(sf_iid + num_steps - iid_index);
+            const float cosa = __ldg(T.ps_cos_alphas + icc_index), sina = __ldg(T.ps_sin_alphas + icc_index);
+            const float cosb = __ldg(T.ps_cos_betas[fine] + iid_index * 8 + icc_index);
+            const float sinb = __ldg(T.ps_sin_betas[fine] + iid_index * 8 + icc_index) * (float)iid_sign;
+            const float ab1 = (cosb * cosa), ab2 = (sinb * sina), ab3 = (sinb * cosa), ab4 = (cosb * sina);
+            h11 = (c_2 * (ab1 - ab2));
+            h12 = (c_1 * (ab1 + ab2));
+            h21 = (c_2 * (ab3 + ab4));
+            h22 = (c_1 * (ab3 - ab4));
+          } else {
+            const float cosa = __ldg(T.ps_sincos_alphas_b[fine] + (num_steps + iid_index) * 8 + icc_index);
+            const float sina = __ldg(T.ps_sincos_alphas_b[fine] + (2 * num_steps - (num_steps + iid_index)) * 8 + icc_index);
+            const float cosg = __ldg(T.ps_cos_gammas[fine] + iid_index * 8 + icc_index);
+            const float sing = __ldg(T.ps_sin_gammas[fine] + iid_index * 8 + icc_index);
+            h11 = (1.4142135623731f * (cosa * cosg));
+            h12 = (1.4142135623731f * (sina * cosg));
+            h21 = (1.4142135623731f * (-cosa * sing));
+            h22 = (1.4142135623731f * (sina * sing));
           }
-          const float gf0 = g_DecaySlope * __ldg(T.ps_filter_a), gf1 = g_DecaySlope * __ldg(T.ps_filter_a + 1), gf2 = g_DecaySlope * __ldg(T.ps_filter_a + 2);
-          const float phi0 = __ldg((hyb ? T.ps_phi_sub : T.ps_phi_qmf) + 2 * sb), phi1 = __ldg((hyb ? T.ps_phi_sub : T.ps_phi_qmf) + 2 * sb + 1);
-          const float* qf = (hyb ? T.ps_q_sub : T.ps_q_qmf) + sb * 6;
-          const float q00 = __ldg(qf), q01 = __ldg(qf + 1), q10 = __ldg(qf + 2), q11 = __ldg(qf + 3), q20 = __ldg(qf + 4), q21 = __ldg(qf + 5);
-          float* d_in = hyb ? &pst->delay_sub[sb][0][0] : &pst->delay_qmf[sb][0][0];          // [slot][2]
-          float* d_ser = hyb ? &pst->delay_sub_ser[sb][0][0][0] : &pst->delay_qmf_ser[sb][0][0][0];   // [link][5][2]
-          int td = saved_delay, s0 = ser0, s1 = ser1, s2 = ser2;
-          int di = delay_band ? pst->delay_buf_index_delay[sb] : 0;
-          const int dD = sb < 35 ? 14 : 1;
-          // mixing state of the band's group
-          float H11 = pst->h_prev[gr][0], H12 = pst->h_prev[gr][1], H21 = pst->h_prev[gr][2], H22 = pst->h_prev[gr][3];
-          float hp11 = H11, hp12 = H12, hp21 = H21, hp22 = H22;
-          float dH11 = 0, dH12 = 0, dH21 = 0, dH22 = 0;
-          int env = -1, env_end = 0;
-          for (int n = 0; n < 32; ++n) {
-            if (n == env_end) {
-              // next envelope: target H from the IID / ICC indices (:424-478), linear interpolation over its length
-              do { ++env; env_end = pp->border[env + 1]; } while (env + 1 < num_env && env_end <= n);
-              int iid_index = pp->iid[env][bk];
-              const int iid_sign = iid_index < 0 ? -1 : 1;
-              iid_index = min(abs(iid_index), num_steps);
-              const int icc_index = min(max((int)pp->icc[env][bk], 0), 7);
-              float h11, h12, h21, h22;
-              if (pp->icc_mode < 3) {
-                const float c_1 = __ldg(sf_iid + num_steps + iid_index), c_2 = __ldg(sf_iid + num_steps - iid_index);
-                const float cosa = __ldg(T.ps_cos_alphas + icc_index), sina = __ldg(T.ps_sin_alphas + icc_index);
-                const float cosb = __ldg(T.ps_cos_betas[fine] + iid_index * 8 + icc_index);
-                const float sinb = __ldg(T.ps_sin_betas[fine] + iid_index * 8 + icc_index) * (float)iid_sign;
-                const float ab1 = (cosb * cosa), ab2 = (sinb * sina), ab3 = (sinb * cosa), ab4 = (cosb * sina);
-                h11 = (c_2 * (ab1 - ab2));
-                h12 = (c_1 * (ab1 + ab2));
-                h21 = (c_2 * (ab3 + ab4));
-                h22 = (c_1 * (ab3 - ab4));
-              } else {
-                const float cosa = __ldg(T.ps_sincos_alphas_b[fine] + (num_steps + iid_index) * 8 + icc_index);
-                const float sina = __ldg(T.ps_sincos_alphas_b[fine] + (2 * num_steps - (num_steps + iid_index)) * 8 + icc_index);
-                const float cosg = __ldg(T.ps_cos_gammas[fine] + iid_index * 8 + icc_index);
-                const float sing = __ldg(T.ps_sin_gammas[fine] + iid_index * 8 + icc_index);
-                h11 = (1.4142135623731f * (cosa * cosg));
-                h12 = (1.4142135623731f * (sina * cosg));
-                h21 = (1.4142135623731f * (-cosa * sing));
-                h22 = (1.4142135623731f * (sina * sing));
-              }
-              const float L = (float)(pp->border[env + 1] - pp->border[env]);
-              dH11 = (h11 - hp11) / L; dH12 = (h12 - hp12) / L; dH21 = (h21 - hp21) / L; dH22 = (h22 - hp22) / L;
-              H11 = hp11; H12 = hp12; H21 = hp21; H22 = hp22;
-              hp11 = h11; hp12 = h12; hp21 = h21; hp22 = h22;
-            }
-            // -- decorrelate
-            const float re = hyb ? HYL(n, sb, 0) : XL(n, sb, 0);
-            const float im = hyb ? HYL(n, sb, 1) : XL(n, sb, 1);
-            float r0Re, r0Im;
-            if (delay_band) {
-              float* d = d_in + 2 * di;
-              r0Re = d[0]; r0Im = d[1];
-              d[0] = re; d[1] = im;
-            } else {
-              float* d = d_in + 2 * td;
-              float tmp0Re = d[0], tmp0Im = d[1];
-              d[0] = re; d[1] = im;
-              r0Re = (tmp0Re * phi0) + (tmp0Im * phi1);
-              r0Im = (tmp0Im * phi0) - (tmp0Re * phi1);
+          const float L = (float)(pp->border[env + 1] - pp->border[env]);
+          dH11 = (h11 - hp11) / L; dH12 = (h12 - hp12) / L; dH21 = (h21 - hp21) / L; dH22 = (h22 - hp22) / L;
+          H11 = hp11; H12 = hp12; H21 = hp21; H22 = hp22;
+          hp11 = h11; hp12 = h12; hp21 = h21; hp22 = h22;
+        }
+        // -- decorrelate
+        const float re = hyb ? HYL(n, sb, 0) : XL(n, sb, 0);
+        const float im = hyb ? HYL(n, sb, 1) : XL(n, sb, 1);
+        float r0Re, r0Im;
+        if (delay_band) {
+          float* d = my_dly + 2 * di;
+          r0Re = d[0]; r0Im = d[1];
+          d[0] = re; d[1] = im;
+        } else {
+          float* d = my_dly + 2 * td;
+          float tmp0Re = d[0], tmp0Im = d[1];
+          d[0] = re; d[1] = im;
+          r0Re = (tmp0Re * phi0) + (tmp0Im * phi1);
+          r0Im = (tmp0Im * phi0) - (tmp0Re * phi1);
 #pragma unroll
-              for (int m = 0; m < 3; ++m) {
-                const float qa = m == 0 ? q00 : (m == 1 ? q10 : q20), qb = m == 0 ? q01 : (m == 1 ? q11 : q21);
-                const float gf = m == 0 ? gf0 : (m == 1 ? gf1 : gf2);
-                float* dl = d_ser + (m * 5 + (m == 0 ? s0 : (m == 1 ? s1 : s2))) * 2;
-                tmp0Re = dl[0]; tmp0Im = dl[1];
-                float tmpRe = (tmp0Re * qa) + (tmp0Im * qb);
-                float tmpIm = (tmp0Im * qa) - (tmp0Re * qb);
-                tmpRe -= gf * r0Re;
-                tmpIm -= gf * r0Im;
-                dl[0] = r0Re + (gf * tmpRe);
-                dl[1] = r0Im + (gf * tmpIm);
-                r0Re = tmpRe;
-                r0Im = tmpIm;
-              }
-            }
-            const float G = pg[n * 20 + bk];
-            const float rRe = (G * r0Re), rIm = (G * r0Im);
-            if (++td >= 2) td = 0;
-            if (delay_band) { if (++di >= dD) di = 0; }
-            if (++s0 >= 3) s0 = 0;
-            if (++s1 >= 4) s1 = 0;
-            if (++s2 >= 5) s2 = 0;
-            // -- mix
-            H11 += dH11; H12 += dH12; H21 += dH21; H22 += dH22;
-            const float lRe = (H11 * re) + (H21 * rRe), lIm = (H11 * im) + (H21 * rIm);
-            const float oRe = (H12 * re) + (H22 * rRe), oIm = (H12 * im) + (H22 * rIm);
-            if (hyb) { HYL(n, sb, 0) = lRe; HYL(n, sb, 1) = lIm; HYR(n, sb, 0) = oRe; HYR(n, sb, 1) = oIm; }
-            else { XL(n, sb, 0) = lRe; XL(n, sb, 1) = lIm; XR(n, sb, 0) = oRe; XR(n, sb, 1) = oIm; }
+          for (int m = 0; m < 3; ++m) {
+            const float qa = m == 0 ? q00 : (m == 1 ? q10 : q20), qb = m == 0 ? q01 : (m == 1 ? q11 : q21);
+            const float gf = m == 0 ? gf0 : (m == 1 ? gf1 : gf2);
+            float* dl = my_ser + (m * 5 + (m == 0 ? s0 : (m == 1 ? s1 : s2))) * 2;
+            tmp0Re = dl[0]; tmp0Im = dl[1];
+            float tmpRe = (tmp0Re * qa) + (tmp0Im * qb);
+            float tmpIm = (tmp0Im * qa) - (tmp0Re * qb);
+            tmpRe -= gf * r0Re;
+            tmpIm -= gf * r0Im;
+            dl[0] = r0Re + (gf * tmpRe);
+            dl[1] = r0Im + (gf * tmpIm);
+            r0Re = tmpRe;
+            r0Im = tmpIm;
           }
-          if (delay_band) pst->delay_buf_index_delay[sb] = di;
-          if (sb == ps_group_border(gr)) { pst->h_prev[gr][0] = hp11; pst->h_prev[gr][1] = hp12; pst->h_prev[gr][2] = hp21; pst->h_prev[gr][3] = hp22; }
-          td_end = td; s0_end = s0; s1_end = s1; s2_end = s2;
         }
+        const float G = pg[n * 20 + bk];
+        const float rRe = (G * r0Re), rIm = (G * r0Im);
+        if (++td >= 2) td = 0;
+        if (delay_band) { if (++di >= dD) di = 0; }
+        if (++s0 >= 3) s0 = 0;
+        if (++s1 >= 4) s1 = 0;
+        if (++s2 >= 5) s2 = 0;
+        // -- mix
+        H11 += dH11; H12 += dH12; H21 += dH21; H22 += dH22;
+        const float lRe = (H11 * re) + (H21 * rRe), lIm = (H11 * im) + (H21 * rIm);
+        const float oRe = (H12 * re) + (H22 * rRe), oIm = (H12 * im) + (H22 * rIm);
+        if (hyb) { HYL(n, sb, 0) = lRe; HYL(n, sb, 1) = lIm; HYR(n, sb, 0) = oRe; HYR(n, sb, 1) = oIm; }
+        else { XL(n, sb, 0) = lRe; XL(n, sb, 1) = lIm; XR(n, sb, 0) = oRe; XR(n, sb, 1) = oIm; }
       }
-      __syncthreads();
-      if (t == 3) { pst->saved_delay = td_end; pst->delay_buf_index_ser[0] = s0_end; pst->delay_buf_index_ser[1] = s1_end; pst->delay_buf_index_ser[2] = s2_end; }
-      // ---- hybrid synthesis (ps/Filterbank.java:70-86) for both channels: thread n
-      if (t < 32) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float a0 = 0, b0 = 0;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) { a0 += HYL(t, k, c); b0 += HYR(t, k, c); }
-          XL(t, 0, c) = a0; XR(t, 0, c) = b0;
-          float a1 = 0, b1 = 0;
-          a1 += HYL(t, 8, c); a1 += HYL(t, 9, c); b1 += HYR(t, 8, c); b1 += HYR(t, 9, c);
-          XL(t, 1, c) = a1; XR(t, 1, c) = b1;
-          float a2 = 0, b2 = 0;
-          a2 += HYL(t, 10, c); a2 += HYL(t, 11, c); b2 += HYR(t, 10, c); b2 += HYR(t, 11, c);
-          XL(t, 2, c) = a2; XR(t, 2, c) = b2;
-        }
-      }
-      __syncthreads();
-
+      if (sb == ps_group_border(gr)) { hprev[gr * 4] = hp11; hprev[gr * 4 + 1] = hp12; hprev[gr * 4 + 2] = hp21; hprev[gr * 4 + 3] = hp22; }
+    } else {
+      // every thread keeps the (uniform) ring positions in step: 32 slots per frame
+      td = (td + 32) % 2; s0 = (s0 + 32) % 3; s1 = (s1 + 32) % 4; s2 = (s2 + 32) % 5;
     }
+    __syncthreads();
+    // ---- hybrid synthesis (ps/Filterbank.java:70-86) for both channels: thread n
+    if (t < 32) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float a0 = 0, b0 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a0 += HYL(t, k, c); b0 += HYR(t, k, c); }
+        XL(t, 0, c) = a0; XR(t, 0, c) = b0;
+        float a1 = 0, b1 = 0;
+        a1 += HYL(t, 8, c); a1 += HYL(t, 9, c); b1 += HYR(t, 8, c); b1 += HYR(t, 9, c);
+        XL(t, 1, c) = a1; XR(t, 1, c) = b1;
+        float a2 = 0, b2 = 0;
+        a2 += HYL(t, 10, c); a2 += HYL(t, 11, c); b2 += HYR(t, 10, c); b2 += HYR(t, 11, c);
+        XL(t, 2, c) = a2; XR(t, 2, c) = b2;
+      }
+    }
+    __syncthreads();
     // ---- the two matrices go out: thread t = band
-    float* outl = xps + ((size_t)(blockIdx.x * tile.ft + (it - tile.lo)) * 2) * 32 * kXgRow;
-    float* outr = outl + 32 * kXgRow;
-    for (int l = 0; l < 32; ++l) {
-      reinterpret_cast<float2*>(outl + (size_t)l * kXgRow)[t] = make_float2(XL(l, t, 0), XL(l, t, 1));
-      reinterpret_cast<float2*>(outr + (size_t)l * kXgRow)[t] = make_float2(XR(l, t, 0), XR(l, t, 1));
+    if (t < 64) {
+      float* outl = xps + ((size_t)(blockIdx.x * tile.ft + (it - tile.lo)) * 2) * 32 * kXgRow;
+      float* outr = outl + 32 * kXgRow;
+      for (int l = 0; l < 32; ++l) {
+        reinterpret_cast<float2*>(outl + (size_t)l * kXgRow)[t] = make_float2(XL(l, t, 0), XL(l, t, 1));
+        reinterpret_cast<float2*>(outr + (size_t)l * kXgRow)[t] = make_float2(XR(l, t, 0), XR(l, t, 1));
+      }
     }
   }
+  __syncthreads();
+  // ---- state out
+  if (band_task) {
+    float* gd = hyb ? &pst->delay_sub[sb][0][0] : &pst->delay_qmf[sb][0][0];
+    const int nd = hyb ? 4 : 28;
+    for (int i = 0; i < nd; ++i) gd[i] = my_dly[i];
+    if (allpass) {
+      float* gs = hyb ? &pst->delay_sub_ser[sb][0][0][0] : &pst->delay_qmf_ser[sb][0][0][0];
+      for (int i = 0; i < 30; ++i) gs[i] = my_ser[i];
+    }
+    if (delay_band) pst->delay_buf_index_delay[sb] = di;
+  }
+  if (t == 3) { pst->saved_delay = td; pst->delay_buf_index_ser[0] = s0; pst->delay_buf_index_ser[1] = s1; pst->delay_buf_index_ser[2] = s2; }
+  if (t < 22)
+    for (int i = 0; i < 4; ++i) pst->h_prev[t][i] = hprev[t * 4 + i];
+  if (t < 72) (&pst->hyb_buffer[0][0][0])[t] = hybuf[t];
+  if (t < 20) { pst->P_PeakDecayNrg[t] = peak; pst->P_prev[t] = pprev; pst->P_SmoothPeakDecayDiffNrg_prev[t] = smooth_prev; }
 #undef XL
 #undef XR
 #undef HYL
