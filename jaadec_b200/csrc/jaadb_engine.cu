@@ -753,6 +753,7 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
     // frame-parallel pipeline over tiles of ft frames per run; the tile's matrices stay within kK4TileBytes
     const uint64_t per_frame = ((uint64_t)n_k4_runs * 32 + (uint64_t)n_ps * 64) * kXgRow * sizeof(float);
     uint32_t ft = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(B.k4_max_count, kK4TileBytes / per_frame));
+    if (ft > kK4cG) ft -= ft % kK4cG;   // the synthesis kernel takes kK4cG frames per CTA
     if (e->opts.sbr_tile_frames) ft = std::min(ft, e->opts.sbr_tile_frames);
     const uint32_t rows = 8 + 32 * ft;
     cudaError_t err = e->d_xg.ensure((size_t)n_k4_runs * rows * kXgRow);
@@ -763,7 +764,7 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
     }
     for (uint32_t lo = 0; lo < B.k4_max_count; lo += ft) {
       const K4Tile tile{lo, ft, rows};
-      const uint32_t n_cf = n_k4_runs * ft;
+      const uint32_t n_cf = n_k4_runs * ft, n_groups = (ft + kK4cG - 1) / kK4cG;
       k4a_analysis_kernel<<<(n_cf + kK4aWarps - 1) / kK4aWarps, 32 * kK4aWarps, k4a_smem_bytes(), e->stream>>>(
           B.k4_runs, n_k4_runs, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, tile);
       k4b_hf_kernel<<<(n_k4_runs + kK4bWarps - 1) / kK4bWarps, 32 * kK4bWarps, k4b_smem_bytes(), e->stream>>>(
@@ -778,9 +779,9 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
                      e->sbr_tables, tile, B.ps_frames, e->d_ps_chan, e->d_xps.p
 #define LAUNCH_K4C(FMT)                                                                                                        \
   do {                                                                                                                         \
-    if (n_plain) { k4c_synthesis_kernel<FMT, false><<<n_plain * ft, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(0u)); ++*launches; } \
+    if (n_plain) { k4c_synthesis_kernel<FMT, false><<<n_plain * n_groups, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(0u)); ++*launches; } \
     if (n_ps) {                                                                                                                \
-      k4c_synthesis_kernel<FMT, true><<<dim3(n_ps * ft, 2), kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(n_plain));    \
+      k4c_synthesis_kernel<FMT, true><<<dim3(n_ps * n_groups, 2), kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(n_plain));    \
       ++*launches;                                                                                                             \
     }                                                                                                                          \
   } while (0)

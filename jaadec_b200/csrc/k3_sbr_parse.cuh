@@ -1118,17 +1118,24 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
     if (processed) { last_proc = it; ++n_proc; if (use_ps) last_ps = it; }
     __syncwarp();
     // ---- what SBR.process leaves behind for the next frame's parse (sbr_save_prev_data, SBR.java:256-284)
-    if (lane == 0 && mode == 2) {
+    if (mode == 2) {
       for (int c = 0; c < nch; ++c) {
         SbrChanParse& cp = S->ch[c];
-        S->kx_prev = S->kx;
-        S->M_prev = S->M;
-        cp.L_E_prev = cp.L_E;
-        cp.f_prev = cp.f[cp.L_E - 1];
-        for (int i = 0; i < kSbrMaxM; i++) { cp.E_prev[i] = cp.E[i][cp.L_E - 1]; cp.Q_prev[i] = cp.Q[i][cp.L_Q - 1]; }
-        for (int i = 0; i < kSbrMaxM; i++) cp.bs_add_harmonic_prev[i] = cp.bs_add_harmonic[i];
-        cp.add_harmonic_flag_prev = cp.add_harmonic_flag;
-        cp.prevEnvIsShort = (cp.l_A == cp.L_E) ? 0 : -1;
+        const int le = cp.L_E - 1, lq = cp.L_Q - 1;
+        for (int i = lane; i < kSbrMaxM; i += 32) {
+          cp.E_prev[i] = cp.E[i][le];
+          cp.Q_prev[i] = cp.Q[i][lq];
+          cp.bs_add_harmonic_prev[i] = cp.bs_add_harmonic[i];
+        }
+        __syncwarp();
+        if (lane == 0) {
+          S->kx_prev = S->kx;
+          S->M_prev = S->M;
+          cp.L_E_prev = cp.L_E;
+          cp.f_prev = cp.f[cp.L_E - 1];
+          cp.add_harmonic_flag_prev = cp.add_harmonic_flag;
+          cp.prevEnvIsShort = (cp.l_A == cp.L_E) ? 0 : -1;
+        }
       }
     }
     __syncwarp();

@@ -917,21 +917,36 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
 }
 
 // ---- K4c: 64-band QMF synthesis (sbr/SynthesisFilterbank64.java:9-79) + PCM pack (S/SampleBuffer.java:168-209)
-constexpr int kK4cThreads = 64;
-constexpr int kK4cRows = 9 + 32;   // the nine inherited slots, then the frame's 32
-constexpr int kK4cXs = kK4cRows * kXsStride + 3, kK4cVb = kK4cRows * kVbStride + 3;
-static_assert(kK4cXs % 4 == 0 && kK4cVb % 4 == 0, "16-byte aligned regions");
-constexpr size_t k4c_smem_bytes() { return sizeof(float) * (kK4cXs + kK4cVb); }
+// One CTA takes kK4cG consecutive frames of one channel (bank): their 32 * G time slots plus the nine slots the first of
+// them inherits, one slot per thread for the two DCT-IVs, so the re-computation of inherited slots costs one partial warp
+// per G frames.  A slot's 64 complex QMF samples are staged in shared memory as [Re X(0..63) | Im X(63..0)] and replaced
+// in place by the slot's 128-entry v-vector.
+constexpr int kK4cG = 3;
+constexpr int kK4cThreads = 32 * (kK4cG + 1);
+constexpr int kK4cRows = 9 + 32 * kK4cG;   // the nine inherited slots, then the frames' slots
+constexpr int kK4cFloats = kK4cRows * kVbStride + 3;
+static_assert(kK4cFloats % 4 == 0, "16-byte aligned regions");
 
-// The two DCT-IVs of one slot (SynthesisFilterbank64.java:27-60).  `row` holds the slot's band-limited QMF samples as
-// [Re X(0..63) | Im X(63..0)], so both transforms read their inputs the same way and ONE copy of the unrolled DCT serves
-// both (the kernel is instruction-fetch bound otherwise).  The first transform's output is parked in the cells its inputs
-// came from.  v = the slot's 128-entry v-vector.
-__device__ __forceinline__ void sbr_synth_slot(float* __restrict__ row, float* __restrict__ v) {
+struct K4cFrame {        // what the CTA knows about one frame of its group
+  uint8_t* dst;          // the frame's PCM
+  const float* cs;       // core PCM of the channel (SBR.upsample)
+  const float* src;      // QMF matrix source: row of slot 0 (xg: row 2 of the frame; xps: row 0)
+  uint32_t it;
+  int16_t row0;          // first v row of the frame (synthesised frames)
+  uint8_t kind;          // 0: nothing to write, 1: SBR.upsample, 2: synthesise
+  uint8_t dup, pair_store, from_ps, last_in_tile, mode;
+  uint8_t lim_lo, lim_hi, first_slot;
+};
+constexpr size_t k4c_smem_bytes() { return sizeof(float) * kK4cFloats + sizeof(K4cFrame) * kK4cG + 16; }
+
+// The two DCT-IVs of one slot (SynthesisFilterbank64.java:27-60), in place.  ONE copy of the unrolled DCT serves both (the
+// kernel is instruction-fetch bound otherwise): pass 0 transforms the real parts and parks (o1r[n], o1i[31 - n]) in
+// cells (2n, 2n + 1), which pass 1 consumes exactly when it writes v[2n], v[2n + 1] there.
+__device__ __forceinline__ void sbr_synth_slot(float* __restrict__ row) {
   const float scale = 1.f / 64.f;
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
-    float* b = row + 64 * pass;
+    const float* b = row + 64 * pass;
     float in_r[32], in_i[32], o_r[32], o_i[32];
     in_i[31] = scale * b[1];
     in_r[0] = scale * b[0];
@@ -942,15 +957,15 @@ __device__ __forceinline__ void sbr_synth_slot(float* __restrict__ row, float* _
     sbr_dct4_kernel(in_r, in_i, o_r, o_i);
     if (pass == 0) {
 #pragma unroll
-      for (int n = 0; n < 32; n++) { b[n] = o_r[n]; b[32 + n] = o_i[n]; }
+      for (int n = 0; n < 32; n++) { row[2 * n] = o_r[n]; row[2 * n + 1] = o_i[31 - n]; }
     } else {
 #pragma unroll
       for (int n = 0; n < 32; n++) {
-        const float o1r = row[n], o1i = row[32 + 31 - n];
-        v[2 * n] = o_r[n] - o1r;
-        v[127 - 2 * n] = o_r[n] + o1r;
-        v[2 * n + 1] = o_i[31 - n] + o1i;
-        v[127 - (2 * n + 1)] = o_i[31 - n] - o1i;
+        const float o1r = row[2 * n], o1i = row[2 * n + 1];
+        row[2 * n] = o_r[n] - o1r;
+        row[127 - 2 * n] = o_r[n] + o1r;
+        row[2 * n + 1] = o_i[31 - n] + o1i;
+        row[127 - (2 * n + 1)] = o_i[31 - n] - o1i;
       }
     }
   }
@@ -973,53 +988,21 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
                      uint32_t* __restrict__ pcm_bytes_out, SbrTablesDev T, K4Tile tile,
                      const PsFrameDev* __restrict__ ps_frames, PsChanDev* __restrict__ ps_chans, const float* __restrict__ xps) {
   extern __shared__ __align__(16) float k4c_smem[];
-  float* xs = k4c_smem;            // [41][kXsStride]: rows 0..8 = slots -9..-1, rows 9..40 = slots 0..31; [Re 0..63 | Im 63..0]
-  float* vb = k4c_smem + kK4cXs;   // [41][kVbStride]
-  const int t = threadIdx.x;
-  const uint32_t rl = blockIdx.x / tile.ft, r = run0 + rl, it = tile.lo + blockIdx.x % tile.ft;
+  float* vb = k4c_smem;   // [kK4cRows][kVbStride]: rows 0..8 = the inherited slots, then 32 rows per synthesised frame
+  K4cFrame* info = reinterpret_cast<K4cFrame*>(k4c_smem + kK4cFloats);
+  __shared__ int s_nsyn, s_halo;   // synthesised frames of the group; 0: none, 1: v-vectors from the carried state, 2: recompute
+  __shared__ const float* s_halo_src;
+  __shared__ int s_halo_lim[9];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t n_groups = (tile.ft + kK4cG - 1) / kK4cG;
+  const uint32_t rl = blockIdx.x / n_groups, r = run0 + rl, it0 = tile.lo + (blockIdx.x % n_groups) * kK4cG;
   const int bank = PS ? (int)blockIdx.y : 0;
   const K4RunDev run = runs[r];
-  if (it >= run.count) return;
-  const SbrFrameDev* fp = k4_frame(sframes, run, it);
-  const RunFrameDev rf = run_frames[run.first + it];
-  const uint32_t f = rf.frame;
-  const int mode = fp->mode;
-  const bool use_ps = PS && fp->frame_status == 0 && mode != 0 && ps_frames[run.ps_base + it].use_ps != 0;
-  if (PS && bank == 1 && !use_ps) return;
-  uint8_t* dst = pcm + pcm_off[f];
+  if (it0 >= run.count) return;
+  const uint32_t it_end = min(min(run.count, tile.lo + tile.ft), it0 + kK4cG);
+  const int nfr = (int)(it_end - it0);
   const int n_out = run.n_out;
   const int out_ch = PS ? bank : run.out_ch;
-  if (fp->frame_status != 0) {
-    if (t == 0 && out_ch == 0) pcm_bytes_out[f] = 0;
-    return;
-  }
-  if (t == 0 && out_ch == 0) pcm_bytes_out[f] = (uint32_t)(2048 * n_out * (PCM_FORMAT == 2 ? 4 : 2));
-  const bool dup = run.dup != 0 && !use_ps;   // mono element: SBR1.process copies the channel unless PS makes the second one
-  const bool pair_store = dup && out_ch == 0 && n_out == 2 && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0;
-  auto put_sample = [&](int i, float v) {
-    if (PCM_FORMAT == 2) {
-      float* d = reinterpret_cast<float*>(dst);
-      d[(size_t)out_ch * 2048 + i] = v;
-      if (dup) d[(size_t)(out_ch + 1) * 2048 + i] = v;
-    } else {
-      uint32_t u = (uint32_t)pcm_round(v) & 0xFFFFu;
-      if (PCM_FORMAT == 1) u = __byte_perm(u, 0, 0x4401);
-      uint16_t* d = reinterpret_cast<uint16_t*>(dst);
-      if (pair_store) reinterpret_cast<uint32_t*>(d)[i] = u | (u << 16);
-      else {
-        d[(size_t)i * n_out + out_ch] = (uint16_t)u;
-        if (dup) d[(size_t)i * n_out + out_ch + 1] = (uint16_t)u;
-      }
-    }
-  };
-  const float* cs = core + ((size_t)rf.ics_base + run.ch_slot) * 1024;
-  if (mode == 0) {
-    // no valid SBR data in this frame: SBR.upsample (sbr/SBR.java:302-309; sample 1 keeps the core value)
-    for (int i = t; i < 2048; i += kK4cThreads) put_sample(i, i < 2 ? cs[i] : cs[i >> 1]);
-    return;
-  }
-  const uint32_t o = fp->ord - k4_frame(sframes, run, tile.lo)->ord;
-  const float* X = xg + ((size_t)r * tile.rows + 32 * (size_t)o) * kXgRow;
   SbrChanDev* st = chans + (size_t)run.stream_slot * kSbrChansPerStream + run.ch_slot;
   PsChanDev* pst = PS ? ps_chans + run.stream_slot : nullptr;
   const int sel = (PS && bank == 1) ? pst->v_sel : st->v_sel;
@@ -1027,50 +1010,111 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
   float* v_out = (PS && bank == 1) ? &pst->syn_v_right[sel ^ 1][0][0] : &st->syn_v[sel ^ 1][0][0];
   // K5's matrices of frame `fr` of this run: [left, right][32][kXgRow]
   auto ps_matrix = [&](uint32_t fr) -> const float* { return xps + (((size_t)rl * tile.ft + (fr - tile.lo)) * 2 + bank) * 32 * kXgRow; };
-  // the frame whose last nine slots this bank inherits, and whether it lies inside the tile
-  const uint32_t back = (PS && bank == 1) ? fp->back_ps : fp->back;
-  const bool halo_in_tile = (PS && bank == 1) ? (back != 0 && it - back >= tile.lo && it >= back) : (o > 0);
-  // ---- stage the QMF rows (band limit applied); thread t = band t
-  {
-    if (use_ps) {
-      const float* P = ps_matrix(it);
-      for (int l = 0; l < 32; ++l) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(P + (size_t)l * kXgRow) + t);
-        xs[(9 + l) * kXsStride + t] = v.x;
-        xs[(9 + l) * kXsStride + 127 - t] = v.y;
-      }
+  const uint32_t ord_lo = k4_frame(sframes, run, tile.lo)->ord;
+
+  // ---- what to do with each frame of the group (thread j), then the row plan (thread 0)
+  if (t < nfr) {
+    const uint32_t it = it0 + t;
+    const SbrFrameDev* fp = k4_frame(sframes, run, it);
+    const RunFrameDev rf = run_frames[run.first + it];
+    const int mode = fp->mode;
+    const bool ok = fp->frame_status == 0;
+    const bool use_ps = PS && ok && mode != 0 && ps_frames[run.ps_base + it].use_ps != 0;
+    K4cFrame f;
+    f.dst = pcm + pcm_off[rf.frame];
+    f.cs = core + ((size_t)rf.ics_base + run.ch_slot) * 1024;
+    f.it = it;
+    f.mode = (uint8_t)mode;
+    f.row0 = 0;
+    f.dup = (run.dup != 0 && !use_ps) ? 1 : 0;   // mono element: SBR1.process copies the channel unless PS makes the second one
+    f.pair_store = (f.dup && out_ch == 0 && n_out == 2 && (reinterpret_cast<uintptr_t>(f.dst) & 3u) == 0) ? 1 : 0;
+    f.from_ps = use_ps ? 1 : 0;
+    f.kind = 0;
+    f.last_in_tile = 0;
+    f.lim_lo = f.lim_hi = 64;
+    f.first_slot = 0;
+    f.src = nullptr;
+    if (PS && bank == 1) {
+      if (use_ps) f.kind = 2;
     } else {
-      const int lim_lo = k4_x_limit(fp, mode, 0), lim_hi = k4_x_limit(fp, mode, 31), first_slot = mode == 2 ? fp->t_E[0] : 0;
-      for (int l = 0; l < 32; ++l) {
-        const int lim = l < first_slot ? lim_lo : lim_hi;
-        float2 v = make_float2(0.f, 0.f);
-        if (t < lim) v = __ldg(reinterpret_cast<const float2*>(X + (size_t)(l + kSbrHfAdj) * kXgRow) + t);
-        xs[(9 + l) * kXsStride + t] = v.x;
-        xs[(9 + l) * kXsStride + 127 - t] = v.y;
+      if (ok) f.kind = mode == 0 ? 1 : 2;
+      if (out_ch == 0) pcm_bytes_out[rf.frame] = ok ? (uint32_t)(2048 * n_out * (PCM_FORMAT == 2 ? 4 : 2)) : 0u;
+    }
+    if (f.kind == 2) {
+      const uint32_t fwd = (PS && bank == 1) ? fp->fwd_ps : fp->fwd;
+      f.last_in_tile = (fwd == 0 || it + fwd >= tile.lo + tile.ft) ? 1 : 0;
+      if (use_ps) f.src = ps_matrix(it);
+      else {
+        f.src = xg + ((size_t)r * tile.rows + 32 * (size_t)(fp->ord - ord_lo) + kSbrHfAdj) * kXgRow;
+        f.lim_lo = (uint8_t)k4_x_limit(fp, mode, 0);
+        f.lim_hi = (uint8_t)k4_x_limit(fp, mode, 31);
+        f.first_slot = mode == 2 ? fp->t_E[0] : 0;
       }
     }
-    if (halo_in_tile) {
-      const uint32_t q = it - back;
-      const bool q_ps = PS && (bank == 1 || ps_frames[run.ps_base + q].use_ps != 0);
-      if (q_ps) {
-        // the previous frame of this bank went through the PS tool: slots 23..31 of its matrix
-        const float* P = ps_matrix(q);
-        for (int h = 0; h < 9; ++h) {
-          const float2 v = __ldg(reinterpret_cast<const float2*>(P + (size_t)(23 + h) * kXgRow) + t);
-          xs[h * kXsStride + t] = v.x;
-          xs[h * kXsStride + 127 - t] = v.y;
+    info[t] = f;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int n = 0, first = -1;
+    for (int j = 0; j < nfr; ++j)
+      if (info[j].kind == 2) { if (first < 0) first = j; info[j].row0 = (int16_t)(9 + 32 * n); ++n; }
+    s_nsyn = n;
+    s_halo = 0;
+    if (n) {
+      // the frame whose last nine slots the first synthesised frame inherits, and whether it lies inside the tile
+      const uint32_t it = info[first].it;
+      const SbrFrameDev* fp = k4_frame(sframes, run, it);
+      const uint32_t back = (PS && bank == 1) ? fp->back_ps : fp->back;
+      const bool in_tile = (PS && bank == 1) ? (back != 0 && it - back >= tile.lo) : (fp->ord > ord_lo);
+      s_halo = in_tile ? 2 : 1;
+      if (in_tile) {
+        const uint32_t q = it - back;
+        const bool q_ps = PS && (bank == 1 || ps_frames[run.ps_base + q].use_ps != 0);
+        if (q_ps) {
+          s_halo_src = ps_matrix(q) + 23 * kXgRow;   // slots 23..31 of the matrix K5 made of that frame
+          for (int h = 0; h < 9; ++h) s_halo_lim[h] = 64;
+        } else {
+          // slots 23..31 of the previous processed frame: its rows 25..33
+          const SbrFrameDev* fq = k4_frame(sframes, run, q);
+          s_halo_src = xg + ((size_t)r * tile.rows + 32 * (size_t)(fq->ord - ord_lo) + kSbrHfAdj + 23) * kXgRow;
+          for (int h = 0; h < 9; ++h) s_halo_lim[h] = k4_x_limit(fq, fq->mode, 23 + h);
         }
-      } else {
-        // slots 23..31 of the previous processed frame: its rows 25..33 = rows -7..1 here
-        const SbrFrameDev* fq = k4_frame(sframes, run, q);
-        const int mq = fq->mode;
-        for (int h = 0; h < 9; ++h) {
-          const int lim = k4_x_limit(fq, mq, 23 + h);
-          float2 v = make_float2(0.f, 0.f);
-          if (t < lim) v = __ldg(reinterpret_cast<const float2*>(X + ((ptrdiff_t)h - 7) * kXgRow) + t);
-          xs[h * kXsStride + t] = v.x;
-          xs[h * kXsStride + 127 - t] = v.y;
-        }
+      }
+    }
+  }
+  __syncthreads();
+  const int nsyn = s_nsyn, halo = s_halo;
+
+  // ---- stage the QMF rows (band limit applied): half a CTA per row, thread = band
+  if (nsyn) {
+    const int band = t & 63, rsel = t >> 6;   // kK4cThreads / 64 rows at a time
+    constexpr int kRowsPerIter = kK4cThreads / 64;
+    for (int j = 0; j < nfr; ++j) {
+      if (info[j].kind != 2) continue;
+      const float* src = info[j].src;
+      const int row0 = info[j].row0, lim_lo = info[j].lim_lo, lim_hi = info[j].lim_hi, fs = info[j].first_slot;
+      // all loads of the thread are issued before the first one is consumed
+      float2 v[32 / kRowsPerIter];
+#pragma unroll
+      for (int u = 0; u < 32 / kRowsPerIter; ++u) {
+        const int l = rsel + u * kRowsPerIter;
+        v[u] = make_float2(0.f, 0.f);
+        if (band < (l < fs ? lim_lo : lim_hi)) v[u] = __ldg(reinterpret_cast<const float2*>(src + (size_t)l * kXgRow) + band);
+      }
+#pragma unroll
+      for (int u = 0; u < 32 / kRowsPerIter; ++u) {
+        const int l = rsel + u * kRowsPerIter;
+        vb[(row0 + l) * kVbStride + band] = v[u].x;
+        vb[(row0 + l) * kVbStride + 127 - band] = v[u].y;
+      }
+    }
+    if (halo == 2) {
+      const float* src = s_halo_src;
+      for (int h = rsel; h < 9; h += kRowsPerIter) {
+        float2 v = make_float2(0.f, 0.f);
+        if (band < s_halo_lim[h]) v = __ldg(reinterpret_cast<const float2*>(src + (size_t)h * kXgRow) + band);
+        vb[h * kVbStride + band] = v.x;
+        vb[h * kVbStride + 127 - band] = v.y;
       }
     } else {
       // carried v-vectors: row 8 is the newest (slot -1), row 0 the oldest (slot -9); [0] of the state = newest
@@ -1078,27 +1122,64 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
     }
   }
   __syncthreads();
+  // ---- the DCTs: one slot per thread (the frames' slots first, then the nine inherited ones)
   {
-    const int srow = t < 32 ? 9 + t : t - 32;   // threads 32..40 take the nine inherited slots
-    if (t < 32 || (halo_in_tile && t < 41)) sbr_synth_slot(xs + srow * kXsStride, vb + srow * kVbStride);
+    const int n_main = 32 * nsyn;
+    int srow = -1;
+    if (t < n_main) srow = 9 + t;
+    else if (halo == 2 && t - n_main < 9) srow = t - n_main;
+    if (srow >= 0) sbr_synth_slot(vb + srow * kVbStride);
   }
   __syncthreads();
-  // ---- window + output: thread k, all 32 slots
-  float qc[10];
+  // ---- window + output: a warp per time slot, lanes take output samples lane and lane + 32
+  auto put_sample = [&](const K4cFrame& f, int i, float v) {
+    if (PCM_FORMAT == 2) {
+      float* d = reinterpret_cast<float*>(f.dst);
+      d[(size_t)out_ch * 2048 + i] = v;
+      if (f.dup) d[(size_t)(out_ch + 1) * 2048 + i] = v;
+    } else {
+      uint32_t u = (uint32_t)pcm_round(v) & 0xFFFFu;
+      if (PCM_FORMAT == 1) u = __byte_perm(u, 0, 0x4401);
+      uint16_t* d = reinterpret_cast<uint16_t*>(f.dst);
+      if (f.pair_store) reinterpret_cast<uint32_t*>(d)[i] = u | (u << 16);
+      else {
+        d[(size_t)i * n_out + out_ch] = (uint16_t)u;
+        if (f.dup) d[(size_t)i * n_out + out_ch + 1] = (uint16_t)u;
+      }
+    }
+  };
+  if (nsyn) {
+    float qc[2][10];
 #pragma unroll
-  for (int j = 0; j < 10; ++j) qc[j] = c_sbr_qmf_c[t + 64 * j];
-  for (int l = 0; l < 32; ++l) {
-    const int cur = 9 + l;
-    float ov = (vb[cur * kVbStride + t] * qc[0]);
+    for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-    for (int j = 1; j < 10; ++j) ov = ov + (vb[(cur - j) * kVbStride + t + 64 * (j & 1)] * qc[j]);
-    put_sample(64 * l + t, ov);
+      for (int j = 0; j < 10; ++j) qc[hf][j] = __ldg(T.qmf_c + lane + 32 * hf + 64 * j);   // (lane-dependent index: not the constant bank)
+    for (int j = 0; j < nfr; ++j) {
+      if (info[j].kind != 2) continue;
+      const K4cFrame f = info[j];
+      for (int l = warp; l < 32; l += kK4cThreads / 32) {
+        const int cur = f.row0 + l;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int k = lane + 32 * hf;
+          float ov = (vb[cur * kVbStride + k] * qc[hf][0]);
+#pragma unroll
+          for (int jj = 1; jj < 10; ++jj) ov = ov + (vb[(cur - jj) * kVbStride + k + 64 * (jj & 1)] * qc[hf][jj]);
+          put_sample(f, 64 * l + k, ov);
+        }
+      }
+      // ---- the bank's last frame of the tile hands its nine newest v-vectors to the next tile
+      if (f.last_in_tile) {
+        for (int i = t; i < 9 * 128; i += kK4cThreads) v_out[i] = vb[(f.row0 + 31 - i / 128) * kVbStride + (i % 128)];
+        if (t == 0) { if (PS && bank == 1) pst->v_flip = 1; else st->v_flip = 1; }
+      }
+    }
   }
-  // ---- the bank's last frame of the tile hands its nine newest v-vectors to the next tile
-  const uint32_t fwd = (PS && bank == 1) ? fp->fwd_ps : fp->fwd;
-  if (fwd == 0 || it + fwd >= tile.lo + tile.ft) {
-    for (int i = t; i < 9 * 128; i += kK4cThreads) v_out[i] = vb[(40 - i / 128) * kVbStride + (i % 128)];
-    if (t == 0) { if (PS && bank == 1) pst->v_flip = 1; else st->v_flip = 1; }
+  // ---- frames without valid SBR data: SBR.upsample (sbr/SBR.java:302-309; sample 1 keeps the core value)
+  for (int j = 0; j < nfr; ++j) {
+    if (info[j].kind != 1) continue;
+    const K4cFrame f = info[j];
+    for (int i = t; i < 2048; i += kK4cThreads) put_sample(f, i, i < 2 ? f.cs[i] : f.cs[i >> 1]);
   }
 }
 
