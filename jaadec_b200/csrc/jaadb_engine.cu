@@ -1184,12 +1184,20 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   cudaSetDevice(e->opts.device);
   if (n_frames == 0) return JAADB_OK;
   auto& W = e->ws;
+  // The compressed frames go first (one copy: frames of a chunk may sit anywhere in the caller's blob), so that the
+  // host-side layout work below runs while they are on the bus.
+  {
+    const cudaError_t be = W.blob.ensure(blob_bytes + 64);
+    if (be != cudaSuccess) { e->set_error(std::string("workspace allocation: ") + cudaGetErrorString(be)); return JAADB_E_NOMEM; }
+    if (blob_bytes) CUDA_TRY(e, cudaMemcpyAsync(W.blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemsetAsync(W.blob.p + blob_bytes, 0, 64, e->stream));
+  }
   std::vector<uint64_t>& off = e->scratch_off;
   std::vector<uint32_t>& size = e->scratch_size;
   uint64_t pcm_total = 0;
   int rc = layout_pcm(e, frames, n_frames, pcm_offsets, off, size, &pcm_total);
-  if (rc) return rc;
-  if (pcm_out && pcm_capacity < pcm_total) { e->set_error("pcm buffer too small"); return JAADB_E_CAPACITY; }
+  if (rc) { cudaStreamSynchronize(e->stream); return rc; }
+  if (pcm_out && pcm_capacity < pcm_total) { cudaStreamSynchronize(e->stream); e->set_error("pcm buffer too small"); return JAADB_E_CAPACITY; }
 
   // chunking: ~128 Ki frames per chunk, unless the caller's PCM placement is not monotonic over chunks
   uint32_t chunk = e->opts.chunk_frames ? e->opts.chunk_frames : 131072u;
@@ -1225,7 +1233,6 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   }
   cudaError_t ce = cudaSuccess;
   auto chk = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
-  chk(W.blob.ensure(blob_bytes + 64));
   chk(W.pcm[0].ensure(max_pcm));
   if (ranges.size() > 1) chk(W.pcm[1].ensure(max_pcm));
   chk(W.frames.ensure(chunk));
@@ -1269,13 +1276,14 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
     chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_pcm_bytes), sizeof(uint32_t) * (size_t)n_frames, cudaHostAllocDefault));
     if (ce == cudaSuccess) W.h_cap = n_frames;
   }
-  if (ce != cudaSuccess) { e->set_error(std::string("workspace allocation: ") + cudaGetErrorString(ce)); return JAADB_E_NOMEM; }
+  if (ce != cudaSuccess) {
+    cudaStreamSynchronize(e->stream);
+    e->set_error(std::string("workspace allocation: ") + cudaGetErrorString(ce));
+    return JAADB_E_NOMEM;
+  }
 
-  // PCM placement of every frame and the compressed frames (one copy each: frames of a chunk may sit anywhere
-  // in the caller's blob)
+  // PCM placement of every frame
   CUDA_TRY(e, cudaMemcpyAsync(W.pcm_off.p, off.data(), sizeof(uint64_t) * n_frames, cudaMemcpyHostToDevice, e->stream));
-  if (blob_bytes) CUDA_TRY(e, cudaMemcpyAsync(W.blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, e->stream));
-  CUDA_TRY(e, cudaMemsetAsync(W.blob.p + blob_bytes, 0, 64, e->stream));
 
   FrameIndex& ix = e->scratch_ix;
   uint32_t launches = 0;
