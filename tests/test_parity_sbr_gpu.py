@@ -111,3 +111,43 @@ def test_sbr_frames_without_payload_are_upsampled(tile):
             assert res["pcm_bytes"][i] == 0
     assert n_bad >= 1
     eng.close()
+
+
+@pytest.mark.parametrize("tile", [0, 2, 3])
+def test_sbr_ragged_streams_and_calls(tile):
+    """Streams of different lengths and kinds (HE-AAC v1 stereo, v1 mono, v2 mono+PS) in one engine, decoded in several
+    calls of uneven size: runs end inside tiles, tiles start inside runs, and every piece of carried state (QMF history,
+    Xsbr rows, v-vectors of both PS banks, decorrelator delay lines) crosses call and tile boundaries."""
+    kinds = [
+        (gen.config(3, n_frames=31), 1),
+        (gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=17, target_bytes=171, sbr_mode=1), 1),
+        (gen.config(4, n_frames=26), 2),
+        (gen.config(4, n_frames=9), 2),
+        (gen.config(3, n_frames=5), 1),
+    ]
+    streams = [gen.generate(cfg, 7700 + i) for i, (cfg, _) in enumerate(kinds)]
+    base = np.concatenate([[0], np.cumsum([len(s.data) for s in streams])]).astype(np.int64)
+    blob = np.concatenate([s.data for s in streams])
+    eng = Engine(max_streams=8, pcm_format=PCM_F32_PLANAR, sbr_tile_frames=tile)
+    ids = [eng.open_adts(2, cfg.sf_index, cfg.chan_cfg, expect_sbr=mode) for cfg, mode in kinds]
+    import oracle
+    decs = [oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg) for cfg, _ in kinds]
+    per = 2 * 2048 * 4
+    from jaadec_b200 import FRAME_DESC_DTYPE
+    for lo, hi in ((0, 4), (4, 5), (5, 16), (16, 40)):
+        rows, index = [], []
+        for f in range(lo, hi):
+            for s, (cfg, _) in enumerate(kinds):
+                if f < cfg.n_frames:
+                    rows.append((base[s] + streams[s].offsets[f], streams[s].sizes[f], ids[s]))
+                    index.append((s, f))
+        if not rows:
+            continue
+        pcm, res = eng.decode(blob, np.array(rows, FRAME_DESC_DTYPE))
+        for i, (s, f) in enumerate(index):
+            st = streams[s]
+            r = decs[s].decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
+            assert res["status"][i] == r["status"] == 0, (s, f, res["status"][i], r["status"])
+            got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(2, 2048)
+            assert same_float_bits(got, r["f32"]), (tile, s, f)
+    eng.close()
