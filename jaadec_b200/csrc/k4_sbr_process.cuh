@@ -308,6 +308,7 @@ struct __align__(16) K4bSmem {
   float eband[64];               // envelope energy per frequency band (bs_interpol_freq == 0)
   float bw[8];
   float ringG[5][64], ringQ[5][64];   // G_temp_prev / Q_temp_prev: the smoothing ring, by ring position
+  uint8_t seq_i[192], seq_l[192];     // hf_assembly's slot order: for every envelope l, slots t_E[l] .. t_E[l + 1] - 1
 };
 constexpr size_t k4b_smem_bytes() { return sizeof(K4bSmem) * kK4bWarps; }
 
@@ -799,6 +800,15 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
       const int fIndexNoise = fp->reset ? 0 : index_noise_prev;
       const int ri0 = fp->reset ? 4 : ring_index;
       int slots_total = 0;
+      // the slot order of the reference's loops, laid out once per frame
+      int n_seq = 0;
+      for (int l = 0; l < L_E; ++l) {
+        const int b0 = fp->t_E[l], b1 = min((int)fp->t_E[l + 1], 38);
+        for (int i = b0 + lane; i < b1; i += 32) { W.seq_i[n_seq + i - b0] = (uint8_t)i; W.seq_l[n_seq + i - b0] = (uint8_t)l; }
+        n_seq += max(0, b1 - b0);
+      }
+      for (int i = n_seq + lane; i < 192; i += 32) W.seq_i[i] = 0;   // (prefetches past the end read row tHFAdj)
+      __syncwarp();
 #pragma unroll 1
       for (int m = lane; m < M; m += 32) {
         // System.arraycopy(.., 0, .., 0, sbr.M) on a reset: positions 0..3 take the first envelope's values (bands < M only)
@@ -815,45 +825,34 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
           Ag[j] = W.ringG[pos][m];
           Aq[j] = W.ringQ[pos][m];
         }
-        int fIndexSine = psi_is_prev, slots_done = 0;
         float* col = X + 2 * (m + kx);
         const int rev = (((m + kx) & 1) != 0 ? -1 : 1);
-        // the reference's slot order: for every envelope l, slots t_E[l] .. t_E[l + 1] - 1; four at a time so that their
-        // loads are in flight together
-        int l = 0, i = fp->t_E[0];
-        auto env_end = [&](int e) -> int { return min((int)fp->t_E[e + 1], 38); };
-        while (l < L_E && i >= env_end(l)) { ++l; i = fp->t_E[min(l, kSbrMaxLE)]; }
         int l_cached = -1;
-        float g_new = 0, q_new = 0, s_m = 0;
+        float g_new = 0, q_new = 0, s_m = 0, rs_m = 0;
         bool no_noise = false;
         int h_SL = 0;
-        // block A is worked on while block B's loads are in flight
-        int al[4], ai[4], bl[4], bi[4];
-        float2 av[4], bv[4];
-        auto gather = [&](int (&gl)[4], int (&gi)[4], float2 (&gv)[4]) {
+        // four slots at a time; the next four are loaded while these are worked on
+        float2 nxt[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            gl[u] = l < L_E ? l : -1;
-            gi[u] = i;
-            if (l < L_E) {
-              gv[u] = ldg2(col + (size_t)(i + kSbrHfAdj) * kXgRow);
-              ++i;
-              while (l < L_E && i >= env_end(l)) { ++l; i = fp->t_E[min(l, kSbrMaxLE)]; }
-            }
-          }
-        };
-        gather(al, ai, av);
+        for (int u = 0; u < 4; ++u) nxt[u] = ldg2(col + (size_t)(W.seq_i[min(u, 191)] + kSbrHfAdj) * kXgRow);
 #pragma unroll 1
-        while (al[0] >= 0) {
-          gather(bl, bi, bv);
+        for (int n0 = 0; n0 < n_seq; n0 += 4) {
+          float2 cur[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { cur[u] = nxt[u]; nxt[u] = ldg2(col + (size_t)(W.seq_i[min(n0 + 4 + u, 191)] + kSbrHfAdj) * kXgRow); }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (al[u] >= 0) {
-              if (al[u] != l_cached) {
-                l_cached = al[u];
-                no_noise = (l_cached == fp->l_A || l_cached == fp->prevEnvIsShort);
+            const int n = n0 + u;
+            if (n < n_seq) {
+              const int i = W.seq_i[n], l = W.seq_l[n];
+              // (a damaged grid may visit a slot twice within the prefetch distance: read it when it is due)
+              if (!grid_sorted) cur[u] = ldg2(col + (size_t)(i + kSbrHfAdj) * kXgRow);
+              if (l != l_cached) {
+                l_cached = l;
+                no_noise = (l == fp->l_A || l == fp->prevEnvIsShort);
                 h_SL = (fp->smoothing_mode || no_noise) ? 0 : 4;
-                g_new = W.g.G[l_cached][m]; q_new = W.g.Q[l_cached][m]; s_m = W.g.S[l_cached][m];
+                g_new = W.g.G[l][m]; q_new = W.g.Q[l][m]; s_m = W.g.S[l][m];
+                rs_m = (float)rev * s_m;
               }
               // the slot's entry: the oldest leaves, the envelope's value comes in as the newest
               Ag[0] = Ag[1]; Ag[1] = Ag[2]; Ag[2] = Ag[3]; Ag[3] = Ag[4]; Ag[4] = g_new;
@@ -861,30 +860,26 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
               float G_filt = 0, Q_filt = 0;
               if (h_SL != 0) {
 #pragma unroll
-                for (int n = 0; n <= 4; n++) {
-                  const float h = n == 0 ? 0.03183050093751f : n == 1 ? 0.11516383427084f : n == 2 ? 0.21816949906249f
-                                : n == 3 ? 0.30150283239582f : 0.33333333333333f;
-                  G_filt += (Ag[n] * h);
-                  Q_filt += (Aq[n] * h);
+                for (int z = 0; z <= 4; z++) {
+                  const float h = z == 0 ? 0.03183050093751f : z == 1 ? 0.11516383427084f : z == 2 ? 0.21816949906249f
+                                : z == 3 ? 0.30150283239582f : 0.33333333333333f;
+                  G_filt += (Ag[z] * h);
+                  Q_filt += (Aq[z] * h);
                 }
               } else { G_filt = g_new; Q_filt = q_new; }
               Q_filt = (s_m != 0 || no_noise) ? 0 : Q_filt;
-              const int ni = (fIndexNoise + slots_done * M + m + 1) & 511;
+              const int ni = (fIndexNoise + n * M + m + 1) & 511;
               const float2 nz = __ldg(reinterpret_cast<const float2*>(T.noise_table) + ni);
-              float x0 = G_filt * av[u].x + (Q_filt * nz.x);
-              float x1 = G_filt * av[u].y + (Q_filt * nz.y);
-              const int phi_re = fIndexSine == 0 ? 1 : (fIndexSine == 2 ? -1 : 0);
-              const int phi_im = fIndexSine == 1 ? 1 : (fIndexSine == 3 ? -1 : 0);
-              x0 += s_m * (float)phi_re;
-              x1 += (float)rev * s_m * (float)phi_im;
-              st2(col + (size_t)(ai[u] + kSbrHfAdj) * kXgRow, x0, x1);
-              ++slots_done;
-              fIndexSine = (fIndexSine + 1) & 3;
+              float x0 = G_filt * cur[u].x + (Q_filt * nz.x);
+              float x1 = G_filt * cur[u].y + (Q_filt * nz.y);
+              const int fs = (psi_is_prev + n) & 3;   // fIndexSine
+              x0 += s_m * (fs == 0 ? 1.f : (fs == 2 ? -1.f : 0.f));
+              x1 += rs_m * (fs == 1 ? 1.f : (fs == 3 ? -1.f : 0.f));
+              st2(col + (size_t)(i + kSbrHfAdj) * kXgRow, x0, x1);
             }
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) { al[u] = bl[u]; ai[u] = bi[u]; av[u] = bv[u]; }
         }
+        const int slots_done = n_seq;
         // back to ring positions: after slots_done writes the next write position is ri0 + slots_done
         int pos = (ri0 + slots_done) % 5;
 #pragma unroll
@@ -894,7 +889,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
           if (++pos >= 5) pos = 0;
         }
       }
-      for (int l = 0; l < L_E; ++l) slots_total += max(0, min((int)fp->t_E[l + 1], 38) - (int)fp->t_E[l]);
+      slots_total = n_seq;
       ring_index = (ri0 + slots_total) % 5;
       index_noise_prev = (fIndexNoise + slots_total * M) & 511;
       psi_is_prev = (psi_is_prev + slots_total) & 3;
