@@ -288,7 +288,10 @@ k4a_analysis_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const Ru
 }
 
 // ---- K4b: HF generation (sbr/HFGeneration.java:17-245) + HF adjustment (sbr/HFAdjustment.java:20-415)
-constexpr int kK4bWarps = 4;
+#ifndef K4B_WARPS
+#define K4B_WARPS 4
+#endif
+constexpr int kK4bWarps = K4B_WARPS;
 constexpr int kK4bMaxNL = 32;
 constexpr int kK4bPwCols = 50;   // >= SBR.MAX_M, even
 struct K4bGain {
