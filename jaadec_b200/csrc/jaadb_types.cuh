@@ -43,8 +43,8 @@ struct FrameDev {
 struct FrameSide {
   int32_t status;
   uint16_t tags;          // 4-bit instance tag of up to 4 elements... (element i in bits 4i..4i+3)
-  uint8_t n_elements;
-  uint8_t pad;
+  uint8_t n_elements;     // SCE / CPE / LFE elements completely decoded
+  uint8_t n_started;      // ... whose element_instance_tag was read (a failing element counts here only)
   uint32_t sbr_bit_off[2];  // bit offset of an SBR FIL payload following element 0/1 (0 = none)
   uint32_t sbr_bits[2];
 };
@@ -70,8 +70,12 @@ static_assert(sizeof(IcsSide) == 400, "IcsSide layout");
 
 struct StreamState {
   uint8_t window_shape[kMaxChannels];  // windowShape[CURRENT] of each channel slot
-  uint16_t tags;                       // instance tags seen on the first frame
-  uint8_t tags_valid;
+  // JAAD keeps one element object per (type, element_instance_tag) (A/syntax/SyntacticElements.java, Element.java:36-38);
+  // the engine keeps the objects of the tags a stream uses first.  A frame that carries another tag addresses objects
+  // the engine does not have: it is reported as JAADB_ST_LAYOUT and leaves the stream's state alone (in JAAD it would
+  // decode against fresh objects and also leave these alone).
+  uint16_t tags;                       // expected instance tag of element i in bits 4i..4i+3
+  uint8_t tags_valid;                  // bit i: element i has been seen
   uint8_t pad[5];
 };
 

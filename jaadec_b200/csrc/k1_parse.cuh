@@ -98,6 +98,7 @@ __device__ __forceinline__ uint32_t huff_lookup(const uint32_t* lut, uint32_t ba
 
 struct IcsInfoRegs {
   int ws, shape, max_sfb, ngroups;
+  int shape_ok;          // the window_shape bit lay inside the frame: ICSInfo.decode got as far as storing it
   uint32_t glen_packed;  // 8 x 4 bits
   __device__ __forceinline__ int glen(int g) const { return (glen_packed >> (4 * g)) & 15; }
 };
@@ -107,6 +108,9 @@ __device__ __forceinline__ int parse_ics_info(BitReader& br, IcsInfoRegs& in) {
   br.skip(1);
   in.ws = (int)br.read(2);
   in.shape = (int)br.read(1);
+  // windowShape[CURRENT] = in.readBit() (ICSInfo.java:91) throws before the assignment when the frame ends here; the
+  // copy into windowShape[PREVIOUS] that precedes it is undone by the next frame's own copy
+  in.shape_ok = br.overrun() ? 0 : 1;
   in.ngroups = 1;
   in.glen_packed = 1u;
   if (in.ws == 2) {
@@ -127,7 +131,7 @@ __device__ __forceinline__ int parse_ics_info(BitReader& br, IcsInfoRegs& in) {
 
 __device__ __forceinline__ void store_ics_header(IcsSide* s, const IcsInfoRegs& in, int present, int info_decoded,
                                                  int ms_mask, int common) {
-  uint32_t h0 = (uint32_t)present | ((uint32_t)info_decoded << 8) | ((uint32_t)in.ws << 16) | ((uint32_t)in.shape << 24);
+  uint32_t h0 = (uint32_t)present | ((uint32_t)(info_decoded & in.shape_ok) << 8) | ((uint32_t)in.ws << 16) | ((uint32_t)in.shape << 24);
   uint32_t h1 = (uint32_t)in.max_sfb | ((uint32_t)in.ngroups << 8) | ((uint32_t)ms_mask << 16) | ((uint32_t)common << 24);
   uint32_t g0 = 0, g1 = 0;
 #pragma unroll
@@ -167,7 +171,9 @@ __device__ __forceinline__ void fail(int& status, bool& flag, int code) { status
 __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& status, const uint32_t* __restrict__ lut,
                                                const TablesDev& T, int sf_index, bool common, IcsInfoRegs& in,
                                                IcsSide* side, int16_t* __restrict__ q, int ms_mask,
-                                               uint8_t* __restrict__ cb_lane, const int16_t* __restrict__ s_swb) {
+                                               uint8_t* __restrict__ cb_lane, const int16_t* __restrict__ s_swb, bool discard) {
+  // discard: the element is not part of the stream's layout (see the element loop): it is parsed for its errors and its
+  // length only, nothing is stored
   // codebook per (group, sfb) of this lane's ICS: shared memory, one byte column per thread
 #define CB(i) cb_lane[(i) * kK1Threads]
   int global_gain = 0;
@@ -176,7 +182,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
     if (!common) {
       int st = parse_ics_info(br, in);
       // window_shape bookkeeping happens before predictor data is looked at (ICSInfo.java:90-91)
-      store_ics_header(side, in, 0, 1, 0, 0);
+      if (!discard) store_ics_header(side, in, 0, 1, 0, 0);
       if (st) fail(status, go, st);
     }
   }
@@ -252,7 +258,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
           }
         }
         if (sfa) {
-          sfo[idx] = (uint16_t)out;
+          if (!discard) sfo[idx] = (uint16_t)out;
           if (++idx == nbands) sfa = false;
         }
       }
@@ -307,12 +313,12 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
       }
     }
     if (go) {
-      side->tns_present = (uint8_t)tns_present;
+      if (!discard) side->tns_present = (uint8_t)tns_present;
       if (br.read1()) fail(status, go, JAADB_ST_UNSUPPORTED_ELEMENT);  // gain control: outside the engine's scope
     }
   }
   // section table out (K2 needs it for dequantisation / stereo tools)
-  if (go) {
+  if (go && !discard) {
     uint32_t* dst = reinterpret_cast<uint32_t*>(side->sfb_cb);
     for (int i = 0; i < (nbands + 3) / 4; ++i)
       dst[i] = (uint32_t)CB(4 * i) | ((uint32_t)CB(4 * i + 1) << 8) | ((uint32_t)CB(4 * i + 2) << 16) | ((uint32_t)CB(4 * i + 3) << 24);
@@ -403,10 +409,10 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
         if (sp) {
           const uint32_t lo32 = ((uint32_t)v0 & 0xFFFFu) | ((uint32_t)v1 << 16);
           if (quad) {
-            *reinterpret_cast<uint2*>(q + pos) = make_uint2(lo32, ((uint32_t)v2 & 0xFFFFu) | ((uint32_t)v3 << 16));
+            if (!discard) *reinterpret_cast<uint2*>(q + pos) = make_uint2(lo32, ((uint32_t)v2 & 0xFFFFu) | ((uint32_t)v3 << 16));
             pos += 4;
           } else {
-            *reinterpret_cast<uint32_t*>(q + pos) = lo32;
+            if (!discard) *reinterpret_cast<uint32_t*>(q + pos) = lo32;
             pos += 2;
           }
           --rem;
@@ -418,7 +424,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
     }
     if (status) go = false;
   }
-  if (go) store_ics_header(side, in, 1, 1, ms_mask, common ? 1 : 0);
+  if (go && !discard) store_ics_header(side, in, 1, 1, ms_mask, common ? 1 : 0);
   __syncwarp();
 #undef CB
 }
@@ -446,7 +452,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
   const int sf_index = fr.sf_index;
 
   FrameSide fs;
-  fs.pad = 0;
+  fs.n_started = 0;
   fs.tags = 0;
   fs.n_elements = 0;
   fs.sbr_bit_off[0] = fs.sbr_bit_off[1] = 0;
@@ -464,12 +470,13 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
     else if (!fr.profile_ok) fail(status, active, JAADB_ST_PROFILE);
   }
 
-  int el = 0;
+  int el = 0, n_good = 0;
+  bool layout_bad = false;
   bool pend_r = false;            // the right channel of the current CPE is next
   int ch0 = 0, ms_mask = 0;
   bool common = false;
   IcsInfoRegs in, in_r;
-  in.ws = 0; in.shape = 0; in.max_sfb = 0; in.ngroups = 1; in.glen_packed = 1;
+  in.ws = 0; in.shape = 0; in.shape_ok = 1; in.max_sfb = 0; in.ngroups = 1; in.glen_packed = 1;
   in_r = in;
 
   // one syntactic element (or one channel of a CPE) per iteration
@@ -481,7 +488,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
       if (pend_r) {
         pend_r = false;
         go = true;
-        ch = ch0 + 1;
+        ch = min(ch0 + 1, lay.n_channels - 1);
         in = in_r;
       } else if (br.overrun()) {
         fail(status, active, JAADB_ST_EOS);
@@ -491,12 +498,15 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
           active = false;
         } else if (type == EL_SCE || type == EL_LFE || type == EL_CPE) {
           const uint32_t tag = br.read(4);
-          if (el >= lay.n_elements || lay.el_type[el] != type) fail(status, active, JAADB_ST_LAYOUT);
-          else {
-            ch0 = lay.el_first_ch[el];
+          // An element the stream's channel layout does not have: JAAD decodes it all the same (and usually dies of
+          // something else further on), so the parse goes on -- into channel slots that exist -- and the frame ends as
+          // JAADB_ST_LAYOUT only if nothing else stops it first.
+          if (el >= lay.n_elements || lay.el_type[el] != type) layout_bad = true;
+          {
+            ch0 = layout_bad ? 0 : lay.el_first_ch[el];
             ch = ch0;
-            fs.tags |= (uint16_t)(tag << (4 * el));
-            in.ws = 0; in.shape = 0; in.max_sfb = 0; in.ngroups = 1; in.glen_packed = 1;
+            if (el < 4) { fs.tags |= (uint16_t)(tag << (4 * el)); fs.n_started = (uint8_t)(el + 1); }
+            in.ws = 0; in.shape = 0; in.shape_ok = 1; in.max_sfb = 0; in.ngroups = 1; in.glen_packed = 1;
             common = false;
             ms_mask = 0;
             go = true;
@@ -506,25 +516,25 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
               common = br.read1() != 0;
               if (common) {
                 const int st = parse_ics_info(br, in);
-                store_ics_header(iside + ch0, in, 0, 1, 0, 1);
+                if (!layout_bad) store_ics_header(iside + ch0, in, 0, 1, 0, 1);
                 if (st) { fail(status, active, st); go = false; }  // thrown inside infoL.decode: R's setCommonData never ran (CPE.java:95-96)
                 else {
-                  store_ics_header(iside + ch0 + 1, in, 0, 1, 0, 1);  // setCommonData updates R's window shape too
+                  if (!layout_bad) store_ics_header(iside + ch0 + 1, in, 0, 1, 0, 1);  // setCommonData updates R's window shape too
                   ms_mask = (int)br.read(2);
-                  uint32_t* ms = reinterpret_cast<uint32_t*>((iside + ch0)->ms_used);
+                  uint32_t msv[4] = {0u, 0u, 0u, 0u};
                   if (ms_mask == 1) {
                     const int n = in.ngroups * in.max_sfb;
                     for (int i = 0; i < 4; ++i) {
                       const int take = min(32, n - 32 * i);
-                      uint32_t v = 0;
-                      if (take > 0) v = __brev(br.read(take) << (32 - take));
-                      ms[i] = v;
+                      if (take > 0) msv[i] = __brev(br.read(take) << (32 - take));
                     }
                   } else if (ms_mask == 2) {
-                    ms[0] = ms[1] = ms[2] = ms[3] = 0xFFFFFFFFu;
-                  } else if (ms_mask == 0) {
-                    ms[0] = ms[1] = ms[2] = ms[3] = 0u;
-                  } else { fail(status, active, JAADB_ST_MS_RESERVED); go = false; }
+                    msv[0] = msv[1] = msv[2] = msv[3] = 0xFFFFFFFFu;
+                  } else if (ms_mask != 0) { fail(status, active, JAADB_ST_MS_RESERVED); go = false; }
+                  if (go && !layout_bad) {
+                    uint32_t* ms = reinterpret_cast<uint32_t*>((iside + ch0)->ms_used);
+                    ms[0] = msv[0]; ms[1] = msv[1]; ms[2] = msv[2]; ms[3] = msv[3];
+                  }
                 }
               }
               in_r = in;
@@ -548,7 +558,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
               const uint32_t ext = br.peek() >> 28;
               if (ext == 11) fail(status, active, JAADB_ST_UNSUPPORTED_ELEMENT);  // dynamic range info
               else {
-                if ((ext == 13 || ext == 14) && el > 0 && el <= 2) {
+                if ((ext == 13 || ext == 14) && el > 0 && el <= 2 && !layout_bad) {
                   fs.sbr_bit_off[el - 1] = br.pos;   // relative to the aligned word base of the frame
                   fs.sbr_bits[el - 1] = 8u * (uint32_t)count;
                 }
@@ -563,17 +573,17 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
     }
     __syncwarp();
     parse_ics_warp(go, br, status, s_lut, T, sf_index, common, in, iside + ch, qbase + ch * 1024, ms_mask,
-                   s_cb + threadIdx.x, s_swb);
+                   s_cb + threadIdx.x, s_swb, layout_bad);
     if (go) {
       if (status) active = false;
       else if (is_cpe_left) pend_r = true;
-      else ++el;
+      else { ++el; if (!layout_bad) n_good = el; }
     }
   }
-  fs.n_elements = (uint8_t)el;
+  fs.n_elements = (uint8_t)n_good;   // elements of the stream's layout that were decoded completely
   if (valid) {
     if (br.overrun()) status = JAADB_ST_EOS;
-    if (status == JAADB_ST_OK && el != lay.n_elements) status = JAADB_ST_LAYOUT;
+    if (status == JAADB_ST_OK && (layout_bad || el != lay.n_elements)) status = JAADB_ST_LAYOUT;
     fs.status = status;
     fside[f] = fs;
   }

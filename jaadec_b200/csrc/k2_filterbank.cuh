@@ -160,7 +160,7 @@ __device__ __forceinline__ void channel_barrier(int c) {
 template <int PCM_FORMAT, int MAX_THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
 k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restrict__ run_frames,
-                     const FrameSide* __restrict__ fside, const IcsSide* __restrict__ iside,
+                     FrameSide* __restrict__ fside, const IcsSide* __restrict__ iside,
                      const int16_t* __restrict__ qall, float* __restrict__ overlap_all, StreamState* __restrict__ sstate,
                      uint8_t* __restrict__ pcm, const uint64_t* __restrict__ pcm_off,
                      uint32_t* __restrict__ pcm_bytes_out, float* __restrict__ spec_tap, float* __restrict__ core, TablesDev T,
@@ -210,11 +210,11 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
   int shape_cur = sstate[run.stream_slot].window_shape[c];
 
   // element of this thread's channel
-  int el_first = c, el_nch = 1;
+  int el_first = c, el_nch = 1, my_el = 0;
   for (int e = 0; e < lay.n_elements; ++e) {
     int f0 = lay.el_first_ch[e];
     int n = lay.el_type[e] == EL_CPE ? 2 : 1;
-    if (c >= f0 && c < f0 + n) { el_first = f0; el_nch = n; }
+    if (c >= f0 && c < f0 + n) { el_first = f0; el_nch = n; my_el = e; }
   }
   // dequantisation work split: a CPE thread owns coefficients 8*et .. 8*et+7 of L and of R (M/S and IS are
   // element-wise across the pair); an SCE/LFE thread owns 16*et .. 16*et+15 of its channel.
@@ -227,7 +227,13 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
 
   // ---- software pipeline: descriptor, status, side information and q of the next frame live in registers
   RunFrameDev cur = run_frames[run.first];
-  int status = fside[cur.frame].status;
+  // status and the element instance tags of the frame: {status, tags | n_elements << 16 | n_started << 24}
+  uint2 fsw = *reinterpret_cast<const uint2*>(fside + cur.frame);
+  uint32_t exp_tags = sstate[run.stream_slot].tags, exp_mask = 0;
+  {
+    const uint32_t v = sstate[run.stream_slot].tags_valid;
+    for (int i = 0; i < 4; ++i) exp_mask |= ((v >> i) & 1u) ? (0xFu << (4 * i)) : 0u;
+  }
   uint4 side_pf = make_uint4(0, 0, 0, 0);
   const int side_vecs = nch * (int)(sizeof(IcsSide) / 16);
   if (tid < side_vecs) side_pf = reinterpret_cast<const uint4*>(iside + cur.ics_base)[tid];
@@ -247,13 +253,38 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
     if (tid < side_vecs) reinterpret_cast<uint4*>(s_side)[tid] = side_pf;
     __syncthreads();
     const IcsSide* sd = s_side + c;
+    // Element objects are per (type, instance tag) in JAAD (StreamState::tags).  An element that shows another tag, or
+    // that the layout does not have, addresses objects this stream does not own: it leaves them alone, the frame is
+    // reported as JAADB_ST_LAYOUT -- and the stream's own elements of that frame still go through the filterbank when
+    // the frame was parsed to its end, as they do in JAAD (SyntacticElements.process runs after the whole parse).
+    int frame_status = (int)fsw.x;
+    bool el_live;      // this thread's element belongs to the stream and was parsed completely
+    bool shape_ok;     // ... belongs to the stream (window-shape bookkeeping happens in failing frames too)
+    {
+      // nibble i of `started` / `exp_mask` = element i has shown its tag in this frame / earlier
+      const uint32_t tags = fsw.y & 0xFFFFu, started = (1u << (4 * min(fsw.y >> 24, 4u))) - 1u;
+      const uint32_t diff = (tags ^ exp_tags) & exp_mask & started;
+      const uint32_t fresh = started & ~exp_mask;
+      exp_tags |= tags & fresh;
+      exp_mask |= fresh;
+      const int n_good = (int)((fsw.y >> 16) & 0xFFu);
+      shape_ok = my_el >= 4 || ((diff >> (4 * my_el)) & 15u) == 0;
+      el_live = shape_ok && my_el < n_good;
+      if (diff != 0 && frame_status == 0) {
+        frame_status = JAADB_ST_LAYOUT;
+        if (tid == 0) fside[f].status = JAADB_ST_LAYOUT;
+      }
+    }
+    const bool emit = frame_status == 0;                                        // the frame yields PCM
+    const bool parsed = emit || frame_status == JAADB_ST_LAYOUT;                // JAAD reached SyntacticElements.process
+    // (SBR streams: the SBR stages only run for frames that yield PCM, so the core coder's state waits for them too)
+    const bool run_ch = parsed && el_live && (emit || !run.sbr);
     // window-shape bookkeeping of ICSInfo.decode / setCommonData (ICSInfo.java:90-91,196-197)
     int shape_prev = shape_cur;
-    if (sd->info_decoded) { shape_prev = shape_cur; shape_cur = sd->window_shape; }
+    if (sd->info_decoded && shape_ok) { shape_prev = shape_cur; shape_cur = sd->window_shape; }
     const int ws = sd->window_sequence;
-    const int frame_status = status;
 
-    if (frame_status == 0) {
+    if (run_ch) {
       // ---- phase 1: dequantise + M/S + IS into the element's spectra
       const int16_t* qL = qall + ((size_t)ics_base + chA) * 1024;
       const int16_t* qR = qall + ((size_t)ics_base + chB) * 1024;
@@ -311,7 +342,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
     }
     // ---- prefetch the next frame while this one is transformed
     if (have_next) {
-      status = fside[nxt.frame].status;
+      fsw = *reinterpret_cast<const uint2*>(fside + nxt.frame);
       if (tid < side_vecs) side_pf = reinterpret_cast<const uint4*>(iside + nxt.ics_base)[tid];
       qA = *reinterpret_cast<const uint4*>(qall + ((size_t)nxt.ics_base + chA) * 1024 + iA);
       qB = *reinterpret_cast<const uint4*>(qall + ((size_t)nxt.ics_base + chB) * 1024 + iB);
@@ -319,7 +350,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
     }
     cur = nxt;
     __syncthreads();
-    if (frame_status != 0) {
+    if (!parsed) {
       if (tid == 0 && !run.sbr) pcm_bytes_out[f] = 0;
       continue;  // the frame produced no PCM; overlap untouched (Decoder.java:96-98)
     }
@@ -549,8 +580,10 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
           }
           o0 = oo[0]; o1 = oo[1]; n0 = nn[0]; n1 = nn[1];
         }
-        *reinterpret_cast<float2*>(my_ovl + i) = make_float2(n0, n1);
-        if (run.sbr) {
+        if (run_ch) *reinterpret_cast<float2*>(my_ovl + i) = make_float2(n0, n1);
+        if (!emit) {
+          // a frame JAAD decodes against element objects this stream does not own: state only, no PCM
+        } else if (run.sbr) {
           // core-coder output of an SBR stream: K4 continues from here
           *reinterpret_cast<float2*>(core + ((size_t)ics_base + c) * 1024 + i) = make_float2(o0, o1);
         } else if (PCM_FORMAT == 2) {
@@ -569,7 +602,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
         }
       }
       __syncthreads();
-      if (PCM_FORMAT != 2 && !run.sbr) {
+      if (PCM_FORMAT != 2 && !run.sbr && emit) {
         // coalesced copy-out of the interleaved frame (pcm offsets are 4-byte aligned; 16 B when the caller packs)
         const int nwords = 1024 * out_ch / 2;   // 32-bit words
         const uint32_t* src = reinterpret_cast<const uint32_t*>(s_pcm);
@@ -581,7 +614,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
           for (int i = tid; i < nwords; i += nthreads) d[i] = src[i];
         }
       }
-      if (tid == 0 && !run.sbr) pcm_bytes_out[f] = (uint32_t)(1024 * out_ch * (PCM_FORMAT == 2 ? 4 : 2));
+      if (tid == 0 && !run.sbr) pcm_bytes_out[f] = emit ? (uint32_t)(1024 * out_ch * (PCM_FORMAT == 2 ? 4 : 2)) : 0u;
     }
   }
 
@@ -590,6 +623,12 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
   for (int i = t; i < 256; i += kThreadsPerChannel)
     reinterpret_cast<float4*>(g_ovl)[i] = reinterpret_cast<const float4*>(my_ovl)[i];
   if (t == 0) sstate[run.stream_slot].window_shape[c] = (uint8_t)shape_cur;
+  if (tid == 0) {
+    uint32_t v = 0;
+    for (int i = 0; i < 4; ++i) v |= ((exp_mask >> (4 * i)) & 1u) << i;
+    sstate[run.stream_slot].tags = (uint16_t)exp_tags;
+    sstate[run.stream_slot].tags_valid = (uint8_t)v;
+  }
 }
 
 }  // namespace jaadb

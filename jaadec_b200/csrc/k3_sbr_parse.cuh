@@ -1007,10 +1007,19 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
       const FrameDev fr = frames[f];
       FrameSide fs = fside[f];
       frame_status = fs.status;
+      // JAAD's element objects (and their SBR) are per instance tag: a frame that carries another tag does not touch
+      // this one (StreamState::tags; K2 applies the same rule to the core coder's state)
+      bool foreign = false;
+      if (run.element < fs.n_started && run.element < 4) {
+        const uint8_t tag = (uint8_t)((fs.tags >> (4 * run.element)) & 15u);
+        if (S->tag_valid) foreign = tag != S->tag;
+        else { S->tag = tag; S->tag_valid = 1; }
+      }
+      if (foreign && frame_status == 0) { frame_status = JAADB_ST_LAYOUT; fside[f].status = JAADB_ST_LAYOUT; }
       // ChannelElement.decode invalidates the element's SBR at the start of every frame (ChannelElement.java:58-61);
       // the element was reached iff K1 counted it
-      if (S->opened && run.element < fs.n_elements) S->valid = 0;
-      const uint32_t nbits = fs.sbr_bits[run.element];
+      if (!foreign && S->opened && run.element < fs.n_elements) S->valid = 0;
+      const uint32_t nbits = foreign ? 0u : fs.sbr_bits[run.element];
       if (nbits) {
         // the FIL payload was seen by K1 (also in frames that failed later on): decodeSBR runs
         S->opened = 1;

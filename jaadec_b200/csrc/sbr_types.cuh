@@ -86,7 +86,8 @@ struct SbrElemDev {
   uint8_t table_map_k_to_g[64];
   uint8_t patchNoSubbands[64];
   int8_t patchStartSubband[64];
-  uint8_t pad[3];
+  uint8_t tag_valid, tag;   // element_instance_tag of the element object this state belongs to (StreamState::tags)
+  uint8_t pad[1];
   SbrChanParse ch[2];
   PsParseDev ps;          // mono element of an SBR+PS stream
   uint8_t pad2[4];
