@@ -805,6 +805,10 @@ struct SCE : ChannelElement {
     target.push_back({dL, (int)dataL.size()});
     if (isSBRPresent() && config->sbrEnabled) {
       float* dR = getDataR();
+      // the element's buffers were created before the stream switched to SBR output: the Java code runs into an
+      // ArrayIndexOutOfBoundsException inside the synthesis filterbank (memory safety matters more here than the exact spot)
+      if ((int)dataL.size() < 2 * config->getFrameLength() || (!dataR.empty() && (int)dataR.size() < 2 * config->getFrameLength()))
+        throw AACException(ST_ARRAY_BOUNDS, "SBR output does not fit the element's buffers");
       sbr->process(dL, dR);
       target.push_back({dR, (int)dataR.size()});
     } else if ((int)dataL.size() != config->getFrameLength()) {
@@ -909,6 +913,10 @@ struct CPE : ChannelElement {
     icsL.process(dL, fb);
     icsR.process(dR, fb);
     if (isSBRPresent() && config->sbrEnabled) {
+      // the element's buffers were created before the stream switched to SBR output: the Java code runs into an
+      // ArrayIndexOutOfBoundsException inside the synthesis filterbank (memory safety matters more here than the exact spot)
+      if ((int)dataL.size() < 2 * config->getFrameLength() || (!dataR.empty() && (int)dataR.size() < 2 * config->getFrameLength()))
+        throw AACException(ST_ARRAY_BOUNDS, "SBR output does not fit the element's buffers");
       sbr->process(dL, dR);
     } else if ((int)dataL.size() != config->getFrameLength()) {
       sbrUpsample(dL, (int)dataL.size());
