@@ -47,7 +47,10 @@ extern "C" {
 #define JAADB_ST_TNS_ORDER 8          /* "TNS filter out of range"           A/tools/TNS.java:47 */
 #define JAADB_ST_LTP_PROFILE 9        /* "unexpected profile for LTP"        A/syntax/ICSInfo.java:139 */
 #define JAADB_ST_UNSUPPORTED_ELEMENT 10 /* CCE / PCE / SSR gain control / Main+LTP prediction / DRC / ADIF */
-#define JAADB_ST_LAYOUT 11            /* element sequence differs from the stream's channel layout */
+#define JAADB_ST_LAYOUT 11            /* the frame addresses element objects the stream does not own: an element the channel
+                                         layout does not have, or another element_instance_tag than the stream used before
+                                         (JAAD keeps one object per type and tag, A/syntax/Element.java:36-38, and would decode
+                                         such a frame against fresh ones); the stream's state is left as JAAD leaves it */
 #define JAADB_ST_PROFILE 12           /* "unsupported profile"               A/Decoder.java:110 */
 #define JAADB_ST_ARRAY_BOUNDS 13      /* a Java ArrayIndexOutOfBoundsException (IQ index > 8190, sf index < 0 ...) */
 #define JAADB_ST_SBR 14               /* AACException raised inside the SBR tool */
