@@ -1,0 +1,8 @@
+#!/bin/bash
+# aggregate D2H bandwidth with all GPUs copying at once (tools/pcie_peak.py per GPU)
+n=$(nvidia-smi -L | wc -l)
+for i in $(seq 0 $((n-1))); do
+  CUDA_VISIBLE_DEVICES=$i python tools/pcie_peak.py > /tmp/pcie_$i.log 2>&1 &
+done
+wait
+for i in $(seq 0 $((n-1))); do echo "gpu $i: $(tr '\n' ' ' < /tmp/pcie_$i.log)"; done
