@@ -1287,11 +1287,30 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
 
   FrameIndex& ix = e->scratch_ix;
   uint32_t launches = 0;
+  // per-frame results of frames [i0, i1) from the pinned copies of the device-side records
+  auto convert_results = [&](uint32_t i0, uint32_t i1) {
+    for (uint32_t i = i0; i < i1; ++i) {
+      const StreamHost& s = e->streams[frames[i].stream_id];
+      jaadb_frame_result& r = results[i];
+      r.status = W.h_fside[i].status;
+      r.pcm_bytes = W.h_pcm_bytes[i];
+      r.channels = r.status ? 0 : (uint16_t)s.out_channels;
+      r.sample_length = r.status ? 0 : (uint16_t)s.sample_length;
+      r.sample_rate = (uint32_t)s.sample_rate;
+    }
+  };
   for (size_t k = 0; k < ranges.size(); ++k) {
     const Range& r = ranges[k];
     const uint32_t n = r.i1 - r.i0;
     const int pb = (int)(k & 1);
-    if (k >= 2) CUDA_TRY(e, cudaEventSynchronize(W.desc_done[pb]));   // staging slot pb has been consumed
+    if (k >= 2) {
+      CUDA_TRY(e, cudaEventSynchronize(W.desc_done[pb]));   // staging slot pb has been consumed
+      // chunk k - 2 is back on the host: its results are converted while the GPU works on chunks k - 1 and k
+      if (results) {
+        CUDA_TRY(e, cudaEventSynchronize(W.d2h_done[pb]));
+        convert_results(ranges[k - 2].i0, ranges[k - 2].i1);
+      }
+    }
     ix.frames_out = W.h_frames[pb];
     ix.run_frames_out = W.h_run_frames[pb];
     rc = index_frames(e, frames + r.i0, n, blob_bytes, ix);
@@ -1328,17 +1347,7 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   }
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(W.copy_stream));
-  if (results) {
-    for (uint32_t i = 0; i < n_frames; ++i) {
-      const StreamHost& s = e->streams[frames[i].stream_id];
-      jaadb_frame_result& r = results[i];
-      r.status = W.h_fside[i].status;
-      r.pcm_bytes = W.h_pcm_bytes[i];
-      r.channels = r.status ? 0 : (uint16_t)s.out_channels;
-      r.sample_length = r.status ? 0 : (uint16_t)s.sample_length;
-      r.sample_rate = (uint32_t)s.sample_rate;
-    }
-  }
+  if (results) convert_results(ranges.size() >= 2 ? ranges[ranges.size() - 2].i0 : 0, n_frames);
   return JAADB_OK;
 }
 

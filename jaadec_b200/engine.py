@@ -71,11 +71,16 @@ class Engine:
         self._check(self._lib.jaadb_stream_get_info(self._h, sid, C.byref(info)), "stream_get_info")
         return info
 
-    def decode(self, blob: np.ndarray, frames: np.ndarray, pcm_out: np.ndarray | None = None, pcm_offsets: np.ndarray | None = None):
-        """One-call decode with host buffers. Returns (pcm uint8 array, results structured array)."""
+    def decode(self, blob: np.ndarray, frames: np.ndarray, pcm_out: np.ndarray | None = None, pcm_offsets: np.ndarray | None = None,
+               results: np.ndarray | None = None):
+        """One-call decode with host buffers. Returns (pcm uint8 array, results structured array).
+
+        `pcm_out` / `results` may be passed in to be reused across calls (every entry is overwritten)."""
         blob = np.ascontiguousarray(blob, np.uint8)
         frames = np.ascontiguousarray(frames, FRAME_DESC_DTYPE)
-        results = np.zeros(len(frames), FRAME_RESULT_DTYPE)
+        if results is None:
+            results = np.zeros(len(frames), FRAME_RESULT_DTYPE)
+        assert results.dtype == FRAME_RESULT_DTYPE and len(results) == len(frames) and results.flags.c_contiguous
         if pcm_out is None:
             need = self._packed_bytes(frames) if pcm_offsets is None else int(pcm_offsets.max(initial=0)) + 8 * 2048 * 4
             pcm_out = np.zeros(need, np.uint8)
