@@ -48,6 +48,55 @@ public final class NativeEngine implements AutoCloseable {
 	private static final MethodHandle STREAM_CLOSE = h("jaadb_stream_close", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
 	private static final MethodHandle DECODE = h("jaadb_decode", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS));
 
+	/** jaadb_adts_info { int32 profile, sf_index, channel_config, sample_rate; uint64 n_frames; } */
+	public static final StructLayout ADTS_INFO = MemoryLayout.structLayout(
+			JAVA_INT.withName("profile"), JAVA_INT.withName("sf_index"), JAVA_INT.withName("channel_config"),
+			JAVA_INT.withName("sample_rate"), JAVA_LONG.withName("n_frames"));
+	/** jaadb_mp4_track { uint8 asc[64]; uint32 asc_bytes; int32 track_id; uint32 timescale, channel_count, sample_size_bits,
+	 *  sample_rate, object_type, max_bitrate, avg_bitrate, reserved; uint64 duration, n_frames; } */
+	public static final StructLayout MP4_TRACK = MemoryLayout.structLayout(
+			MemoryLayout.sequenceLayout(64, JAVA_BYTE).withName("asc"), JAVA_INT.withName("asc_bytes"), JAVA_INT.withName("track_id"),
+			JAVA_INT.withName("timescale"), JAVA_INT.withName("channel_count"), JAVA_INT.withName("sample_size_bits"),
+			JAVA_INT.withName("sample_rate"), JAVA_INT.withName("object_type"), JAVA_INT.withName("max_bitrate"),
+			JAVA_INT.withName("avg_bitrate"), JAVA_INT.withName("reserved"), JAVA_LONG.withName("duration"),
+			JAVA_LONG.withName("n_frames"));
+	// int64 jaadb_{adts,mp4}_index(const uint8* data, uint64 nbytes, uint64 blob_offset, int32 stream_id,
+	//                              jaadb_frame_desc* frames, uint64 max_frames, info* out)
+	private static final FunctionDescriptor INDEX_FD =
+			FunctionDescriptor.of(JAVA_LONG, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS);
+	private static final MethodHandle ADTS_INDEX = h("jaadb_adts_index", INDEX_FD);
+	private static final MethodHandle MP4_INDEX = h("jaadb_mp4_index", INDEX_FD);
+
+	/**
+	 * The frame table of an ADTS stream held in native memory: what new ADTSDemultiplexer(in) + the readNextFrame() loop
+	 * of Main.decodeAAC produce (src/.../adts/ADTSDemultiplexer.java:26-74), without touching the payload bytes.
+	 * `frames` receives up to maxFrames jaadb_frame_desc rows (may be NULL to count), `info` an ADTS_INFO.
+	 */
+	public static long adtsIndex(MemorySegment data, long blobOffset, int streamId, MemorySegment frames, long maxFrames,
+								 MemorySegment info) {
+		try {
+			return (long) ADTS_INDEX.invokeExact(data, data.byteSize(), blobOffset, streamId,
+					frames == null ? MemorySegment.NULL : frames, maxFrames, info == null ? MemorySegment.NULL : info);
+		} catch (Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	/**
+	 * The sample table and AudioSpecificConfig of the first AAC track of an MP4 file held in native memory: what
+	 * new MP4Container(in).getMovie().getTracks(AudioTrack.AudioCodec.AAC).get(0) + getDecoderSpecificInfo() + the
+	 * readNextFrame() loop of Main.decodeMP4 produce (mp4/.../api/Track.java:90-172).  Negative: no AAC track / malformed.
+	 */
+	public static long mp4Index(MemorySegment file, long blobOffset, int streamId, MemorySegment frames, long maxFrames,
+								MemorySegment track) {
+		try {
+			return (long) MP4_INDEX.invokeExact(file, file.byteSize(), blobOffset, streamId,
+					frames == null ? MemorySegment.NULL : frames, maxFrames, track == null ? MemorySegment.NULL : track);
+		} catch (Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
 	private final MemorySegment engine;
 	public final int pcmFormat;
 
