@@ -20,6 +20,10 @@ CASES = [
     ("stereo_sbr_32k", gen.GenConfig(sf_index=8, chan_cfg=2, n_frames=30, target_bytes=300, sbr_mode=1), 3),
     # HE-AAC v2: mono core + SBR + parametric stereo (hybrid filterbank, decorrelator, mixing, two synthesis banks)
     ("c4_mono_sbr_ps", gen.config(4, n_frames=45), 8),
+    # other core rates: other master / derived band tables, patch layouts and limiter tables
+    ("stereo_sbr_22k", gen.GenConfig(sf_index=7, chan_cfg=2, n_frames=30, target_bytes=320, sbr_mode=1), 3),
+    ("mono_sbr_ps_16k", gen.GenConfig(sf_index=8, chan_cfg=1, n_frames=30, target_bytes=150, sbr_mode=2), 3),
+    ("mono_sbr_ps_32k", gen.GenConfig(sf_index=5, chan_cfg=1, n_frames=30, target_bytes=200, sbr_mode=2), 3),
 ]
 
 
@@ -150,4 +154,22 @@ def test_sbr_ragged_streams_and_calls(tile):
             assert res["status"][i] == r["status"] == 0, (s, f, res["status"][i], r["status"])
             got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(2, 2048)
             assert same_float_bits(got, r["f32"]), (tile, s, f)
+    eng.close()
+
+
+@pytest.mark.parametrize("cfg_no", [3, 4])
+def test_sbr_long_streams(cfg_no):
+    """The benchmark's stream length (235 frames, a header every 20): no drift, no rare-path surprises."""
+    cfg = gen.config(cfg_no, n_frames=235)
+    wl = Workload(cfg, 3, base_seed=gen.seed_for(cfg_no, 7), with_truth=False)
+    decs = wl.oracle_decoders()
+    eng = Engine(max_streams=4, pcm_format=PCM_S16LE)
+    ids = [eng.open_adts(*wl.hdr, expect_sbr=cfg.sbr_mode) for _ in range(3)]
+    frames, index = wl.frame_table(ids)
+    pcm, res = eng.decode(wl.blob, frames)
+    per = 2 * 2048 * 2
+    for i, (s, f) in enumerate(index):
+        r = decs[s].decode_frame(wl.frame_bytes(s, f))
+        assert res["status"][i] == r["status"] == 0, (s, f)
+        assert np.array_equal(pcm[i * per:(i + 1) * per].view(np.int16).reshape(2048, 2), r["s16"]), (s, f)
     eng.close()
