@@ -61,3 +61,48 @@ def test_adts_streams_indexed_natively():
         for f in range(cfg.n_frames):
             r = dec.decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
             assert np.array_equal(pcm[first[s] + f], r["s16"]), (s, f)
+
+
+def _asc(fields):
+    v = n = 0
+    for val, w in fields:
+        v = (v << w) | val
+        n += w
+    pad = (8 - n % 8) % 8
+    return (v << pad).to_bytes((n + pad) // 8, "big")
+
+
+def test_mp4_he_aac_tracks_with_explicit_signalling():
+    """HE-AAC v1 / v2 in MP4: the AudioSpecificConfig in esds says SBR (object type 5) or PS (29) with the extension
+    sampling rate (DecoderConfig.java:175-254); frames are raw_data_blocks.  Indexed natively, opened from the ASC."""
+    cases = [
+        (_asc([(5, 5), (6, 4), (2, 4), (3, 4), (2, 5), (0, 3)]), gen.config(3, n_frames=12, adts=False), 2, 48000),
+        (_asc([(29, 5), (6, 4), (1, 4), (3, 4), (2, 5), (0, 3)]), gen.config(4, n_frames=12, adts=False), 1, 48000),
+    ]
+    eng = Engine(max_streams=8, pcm_format=PCM_S16LE, sbr_tile_frames=5)
+    files, streams, ascs = [], [], []
+    for k, (asc, cfg, core_ch, rate) in enumerate(cases):
+        for j in range(2):
+            st = gen.generate(cfg, 6400 + 10 * k + j)
+            raw = [st.data[o: o + n].tobytes() for o, n in zip(st.offsets, st.sizes)]
+            files.append(genmp4.write_mp4(raw, asc, rate, core_ch, chunk_pattern=(2, 5), frame_duration=2048)[0])
+            streams.append(st)
+            ascs.append(asc)
+    blob = np.concatenate(files)
+    begin = np.concatenate([[0], np.cumsum([len(f) for f in files])])
+    _, _, tracks = demux.mp4_index_many(blob, begin)
+    assert [demux.asc_of(t) for t in tracks] == ascs
+    ids = [eng.open_asc(demux.asc_of(t)) for t in tracks]
+    for sid in ids:
+        info = eng.stream_info(sid)
+        assert (info.channels, info.sample_length, info.sample_rate, info.sbr != 0) == (2, 2048, 48000, True)
+    frames, first, _ = demux.mp4_index_many(blob, begin, ids)
+    pcm, res = eng.decode(blob, frames)
+    assert (res["status"] == 0).all()
+    pcm = np.frombuffer(pcm, np.int16).reshape(len(frames), 2048, 2)
+    for s, st in enumerate(streams):
+        dec = oracle.Decoder.create_asc(ascs[s])
+        for f in range(len(st.offsets)):
+            r = dec.decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
+            assert r["status"] == 0
+            assert np.array_equal(pcm[first[s] + f], r["s16"]), (s, f)

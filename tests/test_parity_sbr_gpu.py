@@ -54,13 +54,14 @@ def test_sbr_float_pcm_bit_exact(label, cfg, n_streams, tile):
     eng.close()
 
 
+@pytest.mark.parametrize("cfg_no", [3, 4])
 @pytest.mark.parametrize("fmt,big", [(PCM_S16LE, False), (PCM_S16BE, True)])
-def test_sbr_s16_and_state_across_calls(fmt, big):
-    cfg = gen.config(3, n_frames=50)
+def test_sbr_s16_and_state_across_calls(fmt, big, cfg_no):
+    cfg = gen.config(cfg_no, n_frames=50)
     wl = Workload(cfg, 3, base_seed=4711, with_truth=False)
     decs = wl.oracle_decoders()
     eng = Engine(max_streams=8, pcm_format=fmt, chunk_frames=16)
-    ids = [eng.open_adts(*wl.hdr, expect_sbr=1) for _ in range(3)]
+    ids = [eng.open_adts(*wl.hdr, expect_sbr=cfg.sbr_mode) for _ in range(3)]
     per = 2 * 2048 * 2
     for lo, hi in ((0, 1), (1, 22), (22, 50)):   # headers arrive at frames 0, 20, 40: state and tables carry across calls
         frames, index = wl.frame_table(ids, lo, hi)
