@@ -138,6 +138,13 @@ int jaadb_stream_open_asc(jaadb_engine* e, const uint8_t* asc, uint32_t asc_byte
  * open time (0 = plain AAC-LC, 1 = SBR, 2 = SBR+PS). */
 int jaadb_stream_open_adts(jaadb_engine* e, int32_t profile, int32_t sf_index, int32_t channel_config,
                            int32_t expect_sbr, int32_t* stream_id);
+/* What `expect_sbr` should be for a stream whose header does not say: JAAD learns that an LC-signalled stream is HE-AAC
+ * when the first SBR payload arrives (implicit signalling) and switches the decoder on the spot (A/sbr/SBR.java:98-101,
+ * A/syntax/ChannelElement.java:65-76); the batched engine needs the decision when the stream is opened.  Parses `frame`
+ * (the stream's first raw_data_block) on the GPU with a scratch stream and reports what it carries:
+ * 0 = no SBR payload, 1 = SBR, 2 = SBR + parametric stereo.  Needs one free slot of the stream table while it runs. */
+int jaadb_probe_sbr(jaadb_engine* e, int32_t profile, int32_t sf_index, int32_t channel_config, const uint8_t* frame,
+                    uint32_t nbytes, int32_t* expect_sbr);
 int jaadb_stream_close(jaadb_engine* e, int32_t stream_id);
 int jaadb_stream_get_info(const jaadb_engine* e, int32_t stream_id, jaadb_stream_info* info);
 

@@ -1422,4 +1422,38 @@ int jaadb_batch_tap_sbr(jaadb_batch* b, uint32_t frame, uint32_t ch, void* out, 
   return 0;
 }
 
+int jaadb_probe_sbr(jaadb_engine* e, int32_t profile, int32_t sf_index, int32_t channel_config, const uint8_t* frame,
+                    uint32_t nbytes, int32_t* expect_sbr) {
+  if (!e || !frame || !expect_sbr) return JAADB_E_INVALID;
+  *expect_sbr = 0;
+  // SBR is only implemented for one SCE or one CPE on a core rate of at most 48 kHz (jaadb_stream_open_*)
+  if (channel_config < 1 || channel_config > 2 || sf_index < 3) return JAADB_OK;
+  int32_t sid = -1;
+  int rc = jaadb_stream_open_adts(e, profile, sf_index, channel_config, channel_config == 1 ? 2 : 1, &sid);
+  if (rc) return rc;
+  jaadb_frame_desc fd{0, nbytes, sid};
+  jaadb_batch* b = nullptr;
+  rc = jaadb_batch_create(e, &fd, 1, nbytes, nullptr, &b);
+  if (rc == JAADB_OK) rc = jaadb_batch_upload(b, frame, nbytes);
+  if (rc == JAADB_OK) rc = jaadb_batch_decode(b);
+  if (rc == JAADB_OK) rc = jaadb_batch_sync(b);
+  if (rc == JAADB_OK) {
+    FrameSide fs;
+    memset(&fs, 0, sizeof fs);
+    if (cudaMemcpy(&fs, b->d_fside.p, sizeof fs, cudaMemcpyDeviceToHost) != cudaSuccess) rc = JAADB_E_CUDA;
+    else if (fs.sbr_bits[0] != 0) {
+      *expect_sbr = 1;
+      if (channel_config == 1 && b->d_ps_frames.p) {
+        PsFrameDev pf;
+        memset(&pf, 0, sizeof pf);
+        if (cudaMemcpy(&pf, b->d_ps_frames.p, sizeof pf, cudaMemcpyDeviceToHost) != cudaSuccess) rc = JAADB_E_CUDA;
+        else if (pf.use_ps) *expect_sbr = 2;
+      }
+    }
+  }
+  if (b) jaadb_batch_destroy(b);
+  jaadb_stream_close(e, sid);
+  return rc;
+}
+
 }  // extern "C"

@@ -57,6 +57,15 @@ class Engine:
         self._check(self._lib.jaadb_stream_open_adts(self._h, profile, sf_index, channel_config, expect_sbr, C.byref(sid)), "stream_open_adts")
         return sid.value
 
+    def probe_sbr(self, profile: int, sf_index: int, channel_config: int, frame) -> int:
+        """What expect_sbr should be for an LC-signalled stream, judged by its first frame: 0 = plain AAC-LC, 1 = SBR
+        payload present, 2 = SBR + parametric stereo (JAAD's implicit signalling, sbr/SBR.java:98-101)."""
+        buf = np.ascontiguousarray(frame, np.uint8)
+        out = C.c_int32(0)
+        self._check(self._lib.jaadb_probe_sbr(self._h, profile, sf_index, channel_config, _ptr(buf), buf.nbytes, C.byref(out)),
+                    "probe_sbr")
+        return int(out.value)
+
     def open_asc(self, asc: bytes) -> int:
         sid = C.c_int32(-1)
         buf = np.frombuffer(bytes(asc), np.uint8).copy()

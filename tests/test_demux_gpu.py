@@ -106,3 +106,24 @@ def test_mp4_he_aac_tracks_with_explicit_signalling():
             r = dec.decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
             assert r["status"] == 0
             assert np.array_equal(pcm[first[s] + f], r["s16"]), (s, f)
+
+
+def test_probe_sbr_tells_what_an_adts_stream_carries():
+    """ADTS says AAC-LC for HE-AAC streams too (implicit signalling): the engine looks at the first frame."""
+    eng = Engine(max_streams=4, pcm_format=PCM_S16LE)
+    cases = [
+        (gen.config(2, n_frames=2), 0),
+        (gen.config(3, n_frames=2), 1),
+        (gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=2, target_bytes=171, sbr_mode=1), 1),
+        (gen.config(4, n_frames=2), 2),
+        (gen.config(5, n_frames=2, adts=True), 0),
+    ]
+    for k, (cfg, want) in enumerate(cases):
+        st = gen.generate(cfg, 8800 + k)
+        frames, info = demux.adts_index(st.data)
+        f0 = st.data[int(frames["offset"][0]): int(frames["offset"][0]) + int(frames["nbytes"][0])]
+        assert eng.probe_sbr(info.profile, info.sf_index, info.channel_config, f0) == want, (k, want)
+    # the probe leaves no stream behind and the table is still usable
+    ids = [eng.open_adts(2, 3, 2) for _ in range(4)]
+    assert sorted(ids) == [0, 1, 2, 3]
+    eng.close()
