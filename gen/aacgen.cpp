@@ -483,7 +483,9 @@ struct jg_config {
   int32_t sbr_mode;       // 0 none (LC); 1 SBR; 2 SBR+PS  (filled in by aacgen_sbr.inc when present)
   float target_rms;       // PCM rms target (default 2500)
   int32_t sbr_quirk;      // 1: also emit coupled SBR frames only the reference parses (aacgen_sbr.inc, SbrChanState)
-  int32_t reserved[2];
+  int32_t sbr_downsampled; // 1: SBR band tables for the CORE rate (what JAAD uses when the stream is opened from an ASC that
+                          //    does not signal SBR: outputFrequency stays at the core rate, A/DecoderConfig.java:180, A/sbr/SBR.java:100-102)
+  int32_t reserved[1];
 };
 
 // Ground truth per ICS (element order, L before R); arrays may be NULL.
@@ -521,7 +523,8 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
   else return -2;
   std::vector<int> wsState(els.size(), 0);  // 0 long, 1 start sent -> shorts, 2 in shorts
   std::vector<SbrElemState> sbrState(els.size());
-  const int sbrSrIndex = cfg->sf_index - 3, sbrSrFreq = cfg->sf_index >= 3 ? T_SF_FREQ[cfg->sf_index - 3] : 0;
+  const int sbrSrIndex = cfg->sbr_downsampled ? cfg->sf_index : cfg->sf_index - 3;
+  const int sbrSrFreq = sbrSrIndex >= 0 ? T_SF_FREQ[sbrSrIndex] : 0;
   if (cfg->sbr_mode && (cfg->sf_index < 3 || (cfg->sbr_mode > 1 && cfg->chan_cfg != 1))) return -3;
   PsState psState;
   const double targetRms = cfg->target_rms > 0 ? cfg->target_rms : 2500.0;

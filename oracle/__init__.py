@@ -150,6 +150,19 @@ def qmf_roundtrip(x: np.ndarray):
     return X[..., 0] + 1j * X[..., 1], pcm
 
 
+def qmf_roundtrip32(x: np.ndarray):
+    """x [n_frames*1024] float32 -> pcm [n_frames*1024] float32 through JAAD's 32-band analysis bank and its 32-band
+    (down-sampled) synthesis bank (sbr/SynthesisFilterbank32.java)."""
+    x = np.ascontiguousarray(x, np.float32)
+    n = len(x) // 1024
+    pcm = np.zeros(n * 1024, np.float32)
+    L = lib()
+    L.jo_qmf_roundtrip32.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    if L.jo_qmf_roundtrip32(x.ctypes.data, n, pcm.ctypes.data) != 0:
+        raise RuntimeError("oracle built without SBR")
+    return pcm
+
+
 def adts_index(data: np.ndarray, max_frames: int = 1 << 20):
     data = np.ascontiguousarray(data, np.uint8)
     offs = np.zeros(max_frames, np.int64)

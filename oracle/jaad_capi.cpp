@@ -222,6 +222,24 @@ int jo_qmf_roundtrip(const float* in, int n_frames, float* X_out, float* pcm_out
 #endif
 }
 
+// The same through the 32-band (down-sampled) synthesis bank: pcm_out n_frames x 1024.
+int jo_qmf_roundtrip32(const float* in, int n_frames, float* pcm_out) {
+#ifdef JAAD_ORACLE_WITH_SBR
+  sbr::AnalysisFilterbank qa;
+  sbr::SynthesisFilterbank32 qs;
+  std::vector<float> xs((size_t)40 * 64 * 2, 0.f);
+  sbr::Cpx (*Xs)[64] = reinterpret_cast<sbr::Cpx(*)[64]>(xs.data());
+  for (int f = 0; f < n_frames; ++f) {
+    qa.sbr_qmf_analysis_32(32, in + (size_t)f * 1024, Xs, 0, 32);
+    qs.synthesis(32, Xs, pcm_out + (size_t)f * 1024);
+  }
+  return 0;
+#else
+  (void)in; (void)n_frames; (void)pcm_out;
+  return -1;
+#endif
+}
+
 // ADTS index: payload offsets/sizes of up to `max` frames; hdr[0..2] = profile, sf_index, chan_cfg of the first frame.
 int jo_adts_index(const uint8_t* data, size_t n, int64_t* offsets, int32_t* sizes, int max, int* hdr) {
   ADTSDemultiplexer dm(data, n);

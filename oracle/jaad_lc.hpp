@@ -745,6 +745,7 @@ struct ICStream {
 // ---------------------------------------------------------------------------
 struct SBRBase {
   bool valid = false;
+  bool downSampled = false;   // SBR.isSBRDownSampled (sbr/SBR.java:29-33): 32-band synthesis, output stays at the core's length
   virtual ~SBRBase() {}
   void invalidate() { valid = false; }
   bool isValid() const { return valid; }
@@ -807,7 +808,7 @@ struct SCE : ChannelElement {
       float* dR = getDataR();
       // the element's buffers were created before the stream switched to SBR output: the Java code runs into an
       // ArrayIndexOutOfBoundsException inside the synthesis filterbank (memory safety matters more here than the exact spot)
-      if ((int)dataL.size() < 2 * config->getFrameLength() || (!dataR.empty() && (int)dataR.size() < 2 * config->getFrameLength()))
+      if (!sbr->downSampled && ((int)dataL.size() < 2 * config->getFrameLength() || (!dataR.empty() && (int)dataR.size() < 2 * config->getFrameLength())))
         throw AACException(ST_ARRAY_BOUNDS, "SBR output does not fit the element's buffers");
       sbr->process(dL, dR);
       target.push_back({dR, (int)dataR.size()});
@@ -915,7 +916,7 @@ struct CPE : ChannelElement {
     if (isSBRPresent() && config->sbrEnabled) {
       // the element's buffers were created before the stream switched to SBR output: the Java code runs into an
       // ArrayIndexOutOfBoundsException inside the synthesis filterbank (memory safety matters more here than the exact spot)
-      if ((int)dataL.size() < 2 * config->getFrameLength() || (!dataR.empty() && (int)dataR.size() < 2 * config->getFrameLength()))
+      if (!sbr->downSampled && ((int)dataL.size() < 2 * config->getFrameLength() || (!dataR.empty() && (int)dataR.size() < 2 * config->getFrameLength())))
         throw AACException(ST_ARRAY_BOUNDS, "SBR output does not fit the element's buffers");
       sbr->process(dL, dR);
     } else if ((int)dataL.size() != config->getFrameLength()) {

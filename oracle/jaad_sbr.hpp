@@ -2,7 +2,7 @@
 //
 // CPU restatement of JAAD's SBR tool (aac/src/main/java/net/sourceforge/jaad/aac/sbr/):
 // payload parse (header, grid, dtdf, invf, envelope / noise Huffman), frequency band tables,
-// 32-band QMF analysis, HF generation, HF adjustment and the 64-band QMF synthesis.
+// 32-band QMF analysis, HF generation, HF adjustment, the 64-band QMF synthesis and the 32-band (down-sampled) one.
 // Same operation order and the same float/double promotion points as the Java code; tables
 // come verbatim from the reference through tools/extract_tables_sbr.py.
 // File:line references are relative to aac/src/main/java/net/sourceforge/jaad/aac/sbr/.
@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "jaad_lc.hpp"
+#include "../jaadec_b200/csrc/generated/jaad_dct32.h"   // operation lists of DCT4_32 / DST4_32 (tools/extract_dct32.py)
 
 namespace jaad {
 namespace sbr {
@@ -274,6 +275,74 @@ struct SynthesisFilterbank64 {
   }
 };
 
+// SynthesisFilterbank32.java:40-93 (down-sampled SBR: the low 32 QMF bands only, 32 output samples per slot)
+struct SynthesisFilterbank32 {
+  std::vector<float> v;
+  int v_index = 0;
+  SynthesisFilterbank32() : v(2 * 32 * 20, 0.f) {}
+
+#define JD_ADD(d, a, b) d = a + b;
+#define JD_SUB(d, a, b) d = a - b;
+#define JD_MUL(d, c, a) d = (c * a);
+  static void DCT4_32(float* x) {  // :95-534, called in place
+    JAAD_DCT4_32_TEMPS
+    JAAD_DCT4_32_OPS
+  }
+  static void DST4_32(float* x) {  // :536-940, called in place
+    JAAD_DST4_32_TEMPS
+    JAAD_DST4_32_OPS
+  }
+#undef JD_ADD
+#undef JD_SUB
+#undef JD_MUL
+
+  void synthesis(int numTimeSlotsRate, Cpx (*X)[64], float* output) {
+    const float* qmf_c = JT(SBR_QMF_C);
+    float tw[64];
+    memcpy(tw, JAAD_QMF32_PRE_TWIDDLE_BITS, sizeof tw);
+    float x1[32], x2[32];
+    const float scale = 1.f / 64.f;
+    int out = 0;
+    for (int l = 0; l < numTimeSlotsRate; l++) {
+      for (int k = 0; k < 32; k++) {
+        x1[k] = (X[l][k][0] * tw[2 * k]) - (X[l][k][1] * tw[2 * k + 1]);
+        x2[k] = (X[l][k][1] * tw[2 * k]) + (X[l][k][0] * tw[2 * k + 1]);
+        x1[k] *= scale;
+        x2[k] *= scale;
+      }
+      DCT4_32(x1);
+      DST4_32(x2);
+      for (int n = 0; n < 32; n++) {
+        v[v_index + n] = v[v_index + 640 + n] = -x1[n] + x2[n];
+        v[v_index + 63 - n] = v[v_index + 640 + 63 - n] = x1[n] + x2[n];
+      }
+      for (int k = 0; k < 32; k++) {
+        output[out++] = (v[v_index + k] * qmf_c[2 * k]) + (v[v_index + 96 + k] * qmf_c[64 + 2 * k]) +
+                        (v[v_index + 128 + k] * qmf_c[128 + 2 * k]) + (v[v_index + 224 + k] * qmf_c[192 + 2 * k]) +
+                        (v[v_index + 256 + k] * qmf_c[256 + 2 * k]) + (v[v_index + 352 + k] * qmf_c[320 + 2 * k]) +
+                        (v[v_index + 384 + k] * qmf_c[384 + 2 * k]) + (v[v_index + 480 + k] * qmf_c[448 + 2 * k]) +
+                        (v[v_index + 512 + k] * qmf_c[512 + 2 * k]) + (v[v_index + 608 + k] * qmf_c[576 + 2 * k]);
+      }
+      v_index -= 64;
+      if (v_index < 0) v_index = (640 - 64);
+    }
+  }
+};
+
+// SBR.openFilterbank (SBR.java:35-37): the bank an SBR element opens depends on whether the output rate could be doubled
+struct SynthesisFilterbank {
+  std::unique_ptr<SynthesisFilterbank64> f64;
+  std::unique_ptr<SynthesisFilterbank32> f32;
+  explicit SynthesisFilterbank(bool downSampled) {
+    if (downSampled) f32.reset(new SynthesisFilterbank32());
+    else f64.reset(new SynthesisFilterbank64());
+  }
+  void synthesis(int numTimeSlotsRate, Cpx (*X)[64], float* output) {
+    if (f32) f32->synthesis(numTimeSlotsRate, X, output);
+    else f64->synthesis(numTimeSlotsRate, X, output);
+  }
+};
+
 struct SBR;
 
 // Channel.java
@@ -372,7 +441,6 @@ struct Channel {
 // SBR.java (+ FBT.java, HFGeneration.java, HFAdjustment.java, NoiseEnvelope.java as members / friends)
 struct SBR : SBRBase {
   DecoderConfig* config;
-  bool downSampled;
   int sr_index, sr_freq;  // sample_rate = output frequency (nominal)
   int rate = 2;
   int k0 = 0, kx = 0, M = 0, N_master = 0, N_high = 0, N_low = 0, N_Q = 0;
@@ -400,7 +468,6 @@ struct SBR : SBRBase {
     sr_freq = SF_FREQ[out.index];
     memset(f_table_res, 0, sizeof f_table_res);
     memset(f_table_lim, 0, sizeof f_table_lim);
-    if (downSampled) throw AACException(ST_UNSUPPORTED_ELEMENT, "down-sampled SBR (32-band synthesis) is outside the engine's scope");
   }
 
   // ---- FBT.java ------------------------------------------------------------------------------------------
@@ -1353,10 +1420,10 @@ inline PSFactory& psFactory() { static PSFactory f = nullptr; return f; }
 // SBR1.java
 struct SBR1 : SBR {
   Channel ch0;
-  SynthesisFilterbank64 qmfs0;
-  std::unique_ptr<SynthesisFilterbank64> qmfs1;
+  SynthesisFilterbank qmfs0;
+  std::unique_ptr<SynthesisFilterbank> qmfs1;
   std::unique_ptr<PSBase> ps;
-  explicit SBR1(DecoderConfig& c) : SBR(c), ch0(this) {}
+  explicit SBR1(DecoderConfig& c) : SBR(c), ch0(this), qmfs0(downSampled) {}
 
   int sbr_data(BitStream& ld) override {  // :34-60
     int result;
@@ -1378,7 +1445,7 @@ struct SBR1 : SBR {
       if (!ps) {
         if (!psFactory()) throw AACException(ST_UNSUPPORTED_ELEMENT, "parametric stereo is not built into this oracle");
         ps.reset(psFactory()(numTimeSlotsRate));
-        qmfs1.reset(new SynthesisFilterbank64());
+        qmfs1.reset(new SynthesisFilterbank(downSampled));
       }
       ps->decode(ld);
     }
@@ -1409,7 +1476,7 @@ struct SBR1 : SBR {
       if (hdr) sbr_save_prev_data(ch0);
       sbr_save_matrix(ch0);
       frame++;
-      memcpy(right, left, sizeof(float) * 2048);
+      memcpy(right, left, sizeof(float) * (downSampled ? 1024 : 2048));   // right_chan.length (:80)
     }
   }
 };
@@ -1418,8 +1485,8 @@ struct SBR1 : SBR {
 struct SBR2 : SBR {
   Channel ch0, ch1;
   bool bs_coupling = false;
-  SynthesisFilterbank64 qmfs0, qmfs1;
-  explicit SBR2(DecoderConfig& c) : SBR(c), ch0(this), ch1(this) {}
+  SynthesisFilterbank qmfs0, qmfs1;
+  explicit SBR2(DecoderConfig& c) : SBR(c), ch0(this), ch1(this), qmfs0(downSampled), qmfs1(downSampled) {}
 
   float calc_Q_div_c(const Channel& ch, int m, int l) const {  // NoiseEnvelope.java:186-205
     if (bs_coupling) {
