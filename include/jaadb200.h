@@ -132,6 +132,12 @@ void jaadb_engine_destroy(jaadb_engine* e);
 /* ---- streams -------------------------------------------------------------- */
 /* Decoder.create(byte[] audioSpecificConfig)   A/Decoder.java:36-43, A/DecoderConfig.java:175-254 */
 int jaadb_stream_open_asc(jaadb_engine* e, const uint8_t* asc, uint32_t asc_bytes, int32_t* stream_id);
+/* The same for a stream whose ASC does not signal SBR but whose frames carry it (`expect_sbr` as below, e.g. from
+ * jaadb_probe_sbr): JAAD creates the SBR tool when the first payload arrives; the ASC has fixed the output rate by then
+ * (A/DecoderConfig.java:180), so the rate is NOT doubled and the stream runs the down-sampled SBR tool -- 32-band synthesis
+ * (A/sbr/SynthesisFilterbank32.java), 1024 samples per frame at the core rate (A/sbr/SBR.java:35-37,100, SURVEY A-20).
+ * An ASC with explicit signalling keeps what it says; expect_sbr = 2 then only adds parametric stereo. */
+int jaadb_stream_open_asc_sbr(jaadb_engine* e, const uint8_t* asc, uint32_t asc_bytes, int32_t expect_sbr, int32_t* stream_id);
 /* Decoder.create(AudioDecoderInfo) from an ADTS header   A/Decoder.java:45-48, S/adts/ADTSFrame.java:119-129
  * `expect_sbr`: JAAD switches a stream to 2048-sample output when the first SBR
  * payload arrives (A/sbr/SBR.java:98-101); the batched engine needs that decision at
@@ -145,6 +151,10 @@ int jaadb_stream_open_adts(jaadb_engine* e, int32_t profile, int32_t sf_index, i
  * 0 = no SBR payload, 1 = SBR, 2 = SBR + parametric stereo.  Needs one free slot of the stream table while it runs. */
 int jaadb_probe_sbr(jaadb_engine* e, int32_t profile, int32_t sf_index, int32_t channel_config, const uint8_t* frame,
                     uint32_t nbytes, int32_t* expect_sbr);
+/* The same for a stream described by an AudioSpecificConfig (MP4): the SBR band tables of a stream JAAD opens from an ASC
+ * follow the ASC's output rate (A/sbr/SBR.java:102), so the probe has to parse with those. */
+int jaadb_probe_sbr_asc(jaadb_engine* e, const uint8_t* asc, uint32_t asc_bytes, const uint8_t* frame, uint32_t nbytes,
+                        int32_t* expect_sbr);
 int jaadb_stream_close(jaadb_engine* e, int32_t stream_id);
 int jaadb_stream_get_info(const jaadb_engine* e, int32_t stream_id, jaadb_stream_info* info);
 

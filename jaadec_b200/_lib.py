@@ -13,10 +13,10 @@ from . import _build
 # symbols include/jaadb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "jaadb_abi_version", "jaadb_status_string", "jaadb_last_error", "jaadb_engine_create", "jaadb_engine_destroy",
-    "jaadb_stream_open_asc", "jaadb_stream_open_adts", "jaadb_stream_close", "jaadb_stream_get_info", "jaadb_decode",
+    "jaadb_stream_open_asc", "jaadb_stream_open_asc_sbr", "jaadb_stream_open_adts", "jaadb_stream_close", "jaadb_stream_get_info", "jaadb_decode",
     "jaadb_batch_create", "jaadb_batch_pcm_bytes", "jaadb_batch_upload", "jaadb_batch_decode", "jaadb_batch_sync",
     "jaadb_batch_download", "jaadb_batch_timings", "jaadb_batch_destroy", "jaadb_batch_tap", "jaadb_batch_tap_sbr",
-    "jaadb_adts_index", "jaadb_adts_index_many", "jaadb_mp4_index", "jaadb_mp4_index_many", "jaadb_probe_sbr",
+    "jaadb_adts_index", "jaadb_adts_index_many", "jaadb_mp4_index", "jaadb_mp4_index_many", "jaadb_probe_sbr", "jaadb_probe_sbr_asc",
 ]
 
 
@@ -80,9 +80,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.jaadb_engine_destroy.argtypes = [vp]
     lib.jaadb_engine_destroy.restype = None
     lib.jaadb_stream_open_asc.argtypes = [vp, u8p, C.c_uint32, C.POINTER(C.c_int32)]
+    lib.jaadb_stream_open_asc_sbr.argtypes = [vp, u8p, C.c_uint32, C.c_int32, C.POINTER(C.c_int32)]
     lib.jaadb_stream_open_adts.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     lib.jaadb_stream_close.argtypes = [vp, C.c_int32]
     lib.jaadb_probe_sbr.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, u8p, C.c_uint32, C.POINTER(C.c_int32)]
+    lib.jaadb_probe_sbr_asc.argtypes = [vp, u8p, C.c_uint32, u8p, C.c_uint32, C.POINTER(C.c_int32)]
     lib.jaadb_stream_get_info.argtypes = [vp, C.c_int32, C.POINTER(StreamInfo)]
     lib.jaadb_decode.argtypes = [vp, u8p, C.c_uint64, vp, C.c_uint32, vp, C.c_uint64, vp, vp]
     lib.jaadb_batch_create.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp, C.POINTER(vp)]

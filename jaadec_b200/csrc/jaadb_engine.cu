@@ -50,6 +50,8 @@ struct StreamHost {
   int out_channels = 0;   // DecoderConfig.getChannelCount()
   int sample_rate = 0, sample_length = 1024;
   int sbr = 0;
+  int sbr_sr_index = 0;   // SBR.sample_rate: index of the OUTPUT rate (A/sbr/SBR.java:102)
+  bool sbr_ds = false;    // SBR.isSBRDownSampled: the output rate could not be doubled (A/sbr/SBR.java:100, A/DecoderConfig.java:124-139)
   bool profile_ok = true;
 };
 
@@ -154,6 +156,7 @@ struct FrameIndex {
   std::vector<SbrRunDev> sbr_runs;
   std::vector<K4RunDev> k4_runs;      // plain SBR channels first, then the SBR+PS ones
   uint32_t n_sbr_frames = 0, n_k4_plain = 0, n_ps_frames = 0, k4_max_count = 0;
+  uint32_t k4_banks = 0;              // bit 0: some run uses the 64-band synthesis bank, bit 1: some run the down-sampled one
   // when set, frames / run_frames are written here (pinned staging of the one-call path) instead of the vectors
   FrameDev* frames_out = nullptr;
   RunFrameDev* run_frames_out = nullptr;
@@ -274,7 +277,7 @@ struct jaadb_batch {
   DevBuf<float> d_spec_tap;
   std::vector<SbrRunDev> sbr_runs;
   std::vector<K4RunDev> k4_runs;
-  uint32_t n_sbr_frames = 0, n_k4_plain = 0, n_ps_frames = 0, k4_max_count = 0;
+  uint32_t n_sbr_frames = 0, n_k4_plain = 0, n_ps_frames = 0, k4_max_count = 0, k4_banks = 0;
   DevBuf<PsFrameDev> d_ps_frames;
   DevBuf<SbrRunDev> d_sbr_runs;
   DevBuf<K4RunDev> d_k4_runs;
@@ -364,6 +367,7 @@ int init_sbr(jaadb_engine* e) {
   if ((rc = e->upload(JT(SBR_Q_DIV2_TAB_RIGHT), T::SBR_Q_DIV2_TAB_RIGHT_N, &D.q_div2_right))) return rc;
   if ((rc = e->upload(JT(SBR_E_PAN_TAB), T::SBR_E_PAN_TAB_N, &D.e_pan))) return rc;
   if ((rc = e->upload(JT(SBR_QMF_C), T::SBR_QMF_C_N, &D.qmf_c))) return rc;
+  if ((rc = e->upload(reinterpret_cast<const float*>(JAAD_QMF32_PRE_TWIDDLE_BITS), 64, &D.qmf32_tw))) return rc;
   if ((rc = e->upload(JT(SBR_DCT4_64_TAB), T::SBR_DCT4_64_TAB_N, &D.dct4_tab))) return rc;
   if ((rc = e->upload(JT(SBR_W_ARRAY_REAL), 16, &D.w_real))) return rc;
   if ((rc = e->upload(JT(SBR_W_ARRAY_IMAG), 16, &D.w_imag))) return rc;
@@ -442,8 +446,10 @@ int init_sbr(jaadb_engine* e) {
   cudaFuncSetAttribute(k4a_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4a_smem_bytes());
   cudaFuncSetAttribute(k4b_hf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4b_smem_bytes());
 #define K4C_ATTR(FMT)                                                                                                        \
-  cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes()); \
-  cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes())
+  cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes()); \
+  cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes()); \
+  cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes()); \
+  cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes())
   K4C_ATTR(0); K4C_ATTR(1); K4C_ATTR(2);
 #undef K4C_ATTR
   cudaFuncSetAttribute(k5_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5_smem_bytes());
@@ -496,8 +502,9 @@ int finish_open(jaadb_engine* e, StreamHost& s, int32_t* stream_id) {
   if (s.sbr > 1 && s.chan_cfg != 1) { e->set_error("parametric stereo needs a mono core"); return JAADB_E_CONFIG; }
   if (s.sbr) {
     if (s.chan_cfg > 2) { e->set_error("SBR is implemented for mono and stereo streams only"); return JAADB_E_CONFIG; }
-    if (s.sample_length != 2048) { e->set_error("down-sampled SBR (32-band synthesis) is not implemented"); return JAADB_E_CONFIG; }
-    if (s.sf_index < 3) { e->set_error("SBR core sampling rate too high"); return JAADB_E_CONFIG; }
+    s.sbr_ds = s.sample_length != 2048;
+    if (s.sbr_ds) s.sbr_sr_index = s.sf_index;
+    if (s.sbr_sr_index < 0 || s.sbr_sr_index > 11) { e->set_error("SBR core sampling rate too high"); return JAADB_E_CONFIG; }
     int rc = init_sbr(e);
     if (rc) return rc;
     s.out_channels = 2;   // SCE: SBR1.process fills a second channel (PS or a copy), CPE: two channels
@@ -582,6 +589,7 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
   ix.n_sbr_frames = 0;
   ix.n_k4_plain = 0;
   ix.k4_max_count = 0;
+  ix.k4_banks = 0;
   ix.n_ps_frames = 0;
   // per-stream frame counts (counting sort keeps array order inside each stream)
   std::vector<uint32_t>& count = e->scratch_count;
@@ -645,7 +653,7 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
       sr.sbr_base = ix.n_sbr_frames;
       sr.element = 0;
       sr.stereo = stereo ? 1 : 0;
-      sr.sr_index = (uint8_t)(sh.sf_index - 3);
+      sr.sr_index = (uint8_t)sh.sbr_sr_index;
       sr.first_ch = 0;
       sr.ps = with_ps ? 1 : 0;
       sr.ps_base = ix.n_ps_frames;
@@ -662,6 +670,8 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
         kr.out_ch = (uint8_t)c;
         kr.n_out = 2;
         kr.dup = stereo ? 0 : 1;
+        kr.ds = sh.sbr_ds ? 1 : 0;
+        ix.k4_banks |= sh.sbr_ds ? 2u : 1u;
         kr.ps_base = sr.ps_base;
         ix.k4_runs.push_back(kr);
         ix.k4_max_count = std::max(ix.k4_max_count, r.count);
@@ -703,6 +713,7 @@ struct DecodeBufs {
   PsFrameDev* ps_frames;
   uint32_t n_k4_plain;
   uint32_t k4_max_count;   // longest plain-SBR run
+  uint32_t k4_banks;       // FrameIndex::k4_banks
 };
 
 #ifndef K4_TILE_BYTES
@@ -777,18 +788,25 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
       }
 #define K4C_ARGS(R0) B.k4_runs, R0, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, B.pcm, B.pcm_off, B.pcm_bytes, \
                      e->sbr_tables, tile, B.ps_frames, e->d_ps_chan, e->d_xps.p
-#define LAUNCH_K4C(FMT)                                                                                                        \
+#define LAUNCH_K4C_BANK(FMT, DS)                                                                                                \
   do {                                                                                                                         \
-    if (n_plain) { k4c_synthesis_kernel<FMT, false><<<n_plain * n_groups, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(0u)); ++*launches; } \
+    if (n_plain) { k4c_synthesis_kernel<FMT, false, DS><<<n_plain * n_groups, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(0u)); ++*launches; } \
     if (n_ps) {                                                                                                                \
-      k4c_synthesis_kernel<FMT, true><<<dim3(n_ps * n_groups, 2), kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(n_plain));    \
+      k4c_synthesis_kernel<FMT, true, DS><<<dim3(n_ps * n_groups, 2), kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(n_plain));    \
       ++*launches;                                                                                                             \
     }                                                                                                                          \
+  } while (0)
+  // the two synthesis banks are two instantiations over the same grid; each leaves the other's runs alone
+#define LAUNCH_K4C(FMT)                                                                                                        \
+  do {                                                                                                                         \
+    if (B.k4_banks & 1u) LAUNCH_K4C_BANK(FMT, false);                                                                          \
+    if (B.k4_banks & 2u) LAUNCH_K4C_BANK(FMT, true);                                                                           \
   } while (0)
       if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K4C(0);
       else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K4C(1);
       else LAUNCH_K4C(2);
 #undef LAUNCH_K4C
+#undef LAUNCH_K4C_BANK
 #undef K4C_ARGS
       k4_commit_kernel<<<(n_k4_runs + 255) / 256, 256, 0, e->stream>>>(B.k4_runs, n_k4_runs, n_plain, e->d_sbr_chan, e->d_ps_chan);
       ++*launches;
@@ -914,12 +932,17 @@ int jaadb_stream_open_adts(jaadb_engine* e, int32_t profile, int32_t sf_index, i
   s.sbr = expect_sbr;
   if (s.sbr) {
     // DecoderConfig.setSBRPresent (A/DecoderConfig.java:124-135): ADTS streams have no output frequency yet
-    if (sf_index >= 3) { s.sample_rate = kSfFreq[sf_index - 3]; s.sample_length = 2048; }
+    // (rates above 48 kHz cannot be doubled: SampleRate.duplicated() is SF_NONE and the stream runs the down-sampled bank)
+    if (sf_index >= 3) { s.sample_rate = kSfFreq[sf_index - 3]; s.sample_length = 2048; s.sbr_sr_index = sf_index - 3; }
   }
   return finish_open(e, s, stream_id);
 }
 
 int jaadb_stream_open_asc(jaadb_engine* e, const uint8_t* asc, uint32_t n, int32_t* stream_id) {
+  return jaadb_stream_open_asc_sbr(e, asc, n, 0, stream_id);
+}
+
+int jaadb_stream_open_asc_sbr(jaadb_engine* e, const uint8_t* asc, uint32_t n, int32_t expect_sbr, int32_t* stream_id) {
   if (!e || !asc || !stream_id) return JAADB_E_INVALID;
   cudaSetDevice(e->opts.device);
   // DecoderConfig.decode (A/DecoderConfig.java:175-254)
@@ -936,7 +959,7 @@ int jaadb_stream_open_asc(jaadb_engine* e, const uint8_t* asc, uint32_t n, int32
   int profile = read_profile();
   int sf_index = -1, freq = 0;
   if (!read_rate(sf_index, freq)) { e->set_error("bad sampling frequency in AudioSpecificConfig"); return JAADB_E_CONFIG; }
-  int out_freq = freq;
+  int out_freq = freq, out_index = sf_index;
   int cc = (int)in.read(4);
   if (cc >= 7) ++cc;
   if (cc > 8 || cc == 7 || cc == 0) { e->set_error("unsupported channel configuration in AudioSpecificConfig"); return JAADB_E_CONFIG; }
@@ -949,6 +972,7 @@ int jaadb_stream_open_asc(jaadb_engine* e, const uint8_t* asc, uint32_t n, int32
       if (!read_rate(ext_index, ext_freq)) { e->set_error("bad extension sampling frequency"); return JAADB_E_CONFIG; }
       profile = read_profile();
       out_freq = ext_freq;
+      out_index = ext_index;
       break;
     }
     case 1: case 2: case 3: case 4: case 17: case 19: case 23: {
@@ -968,6 +992,7 @@ int jaadb_stream_open_asc(jaadb_engine* e, const uint8_t* asc, uint32_t n, int32
               int ext_index, ext_freq;
               if (!read_rate(ext_index, ext_freq)) { e->set_error("bad extension sampling frequency"); return JAADB_E_CONFIG; }
               out_freq = ext_freq;
+              out_index = ext_index;
               sbr = 1;
             }
             if (ext == 5 && in.left() > 12 && in.read(11) == 0x548 && in.read(1)) sbr = 2;
@@ -987,7 +1012,10 @@ int jaadb_stream_open_asc(jaadb_engine* e, const uint8_t* asc, uint32_t n, int32
   s.sample_rate = out_freq;
   // outputFrequency was set from the ASC: sample length doubles only if it differs (A/DecoderConfig.java:83-86)
   s.sample_length = (out_freq != freq) ? 2048 : 1024;
-  s.sbr = sbr;
+  // Implicit signalling: the ASC says nothing, the first SBR payload creates the tool (A/syntax/ChannelElement.java:65-76).
+  // outputFrequency is already set by then, so it is not doubled and the stream runs the down-sampled bank (SURVEY A-20).
+  s.sbr = std::max(sbr, std::max(expect_sbr, 0));
+  s.sbr_sr_index = out_index;
   return finish_open(e, s, stream_id);
 }
 
@@ -1039,6 +1067,7 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
   b->n_sbr_frames = ix.n_sbr_frames;
   b->n_k4_plain = ix.n_k4_plain;
   b->k4_max_count = ix.k4_max_count;
+  b->k4_banks = ix.k4_banks;
   b->n_ps_frames = ix.n_ps_frames;
   const uint32_t ics = ix.n_ics;
   // device side
@@ -1102,7 +1131,7 @@ int jaadb_batch_decode(jaadb_batch* b) {
   DecodeBufs B{b->d_blob.p, b->d_frames.p, b->d_fside.p, b->d_iside.p, b->d_q.p, b->d_runs.p, b->d_run_frames.p, b->d_pcm.p,
                b->d_pcm_off.p, b->d_pcm_bytes.p, (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) ? b->d_spec_tap.p : nullptr,
                b->d_sbr_runs.p, b->d_k4_runs.p, b->d_sbr_frames.p, b->d_core.p, b->d_ps_frames.p, b->n_k4_plain,
-               b->k4_max_count};
+               b->k4_max_count, b->k4_banks};
   CUDA_TRY(e, launch_decode(e, b->groups.data(), b->groups.size(), b->n_frames, (uint32_t)b->sbr_runs.size(), (uint32_t)b->k4_runs.size(), B,
                 prof ? e->ev[1] : nullptr, prof ? e->ev[3] : nullptr, &launches));
   if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[2], e->stream));
@@ -1331,7 +1360,7 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
     }
     DecodeBufs B{W.blob.p, W.frames.p, W.fside.p + r.i0, W.iside.p, W.q.p, W.runs.p, W.run_frames.p, W.pcm[pb].p - r.lo,
                  W.pcm_off.p + r.i0, W.pcm_bytes.p + r.i0, nullptr, W.sbr_runs.p, W.k4_runs.p, W.sbr_frames.p, W.core.p, W.ps_frames.p,
-                 ix.n_k4_plain, ix.k4_max_count};
+                 ix.n_k4_plain, ix.k4_max_count, ix.k4_banks};
     CUDA_TRY(e, launch_decode(e, ix.groups.data(), ix.groups.size(), n, (uint32_t)ix.sbr_runs.size(), (uint32_t)ix.k4_runs.size(), B,
                               nullptr, nullptr, &launches));
     CUDA_TRY(e, cudaGetLastError());
@@ -1422,18 +1451,12 @@ int jaadb_batch_tap_sbr(jaadb_batch* b, uint32_t frame, uint32_t ch, void* out, 
   return 0;
 }
 
-int jaadb_probe_sbr(jaadb_engine* e, int32_t profile, int32_t sf_index, int32_t channel_config, const uint8_t* frame,
-                    uint32_t nbytes, int32_t* expect_sbr) {
-  if (!e || !frame || !expect_sbr) return JAADB_E_INVALID;
-  *expect_sbr = 0;
-  // SBR is only implemented for one SCE or one CPE on a core rate of at most 48 kHz (jaadb_stream_open_*)
-  if (channel_config < 1 || channel_config > 2 || sf_index < 3) return JAADB_OK;
-  int32_t sid = -1;
-  int rc = jaadb_stream_open_adts(e, profile, sf_index, channel_config, channel_config == 1 ? 2 : 1, &sid);
-  if (rc) return rc;
+namespace {
+// decodes `frame` with the scratch stream `sid` (opened expecting SBR, and PS on a mono core) and reports what it carries
+int probe_with_stream(jaadb_engine* e, int32_t sid, bool mono, const uint8_t* frame, uint32_t nbytes, int32_t* expect_sbr) {
   jaadb_frame_desc fd{0, nbytes, sid};
   jaadb_batch* b = nullptr;
-  rc = jaadb_batch_create(e, &fd, 1, nbytes, nullptr, &b);
+  int rc = jaadb_batch_create(e, &fd, 1, nbytes, nullptr, &b);
   if (rc == JAADB_OK) rc = jaadb_batch_upload(b, frame, nbytes);
   if (rc == JAADB_OK) rc = jaadb_batch_decode(b);
   if (rc == JAADB_OK) rc = jaadb_batch_sync(b);
@@ -1443,7 +1466,7 @@ int jaadb_probe_sbr(jaadb_engine* e, int32_t profile, int32_t sf_index, int32_t 
     if (cudaMemcpy(&fs, b->d_fside.p, sizeof fs, cudaMemcpyDeviceToHost) != cudaSuccess) rc = JAADB_E_CUDA;
     else if (fs.sbr_bits[0] != 0) {
       *expect_sbr = 1;
-      if (channel_config == 1 && b->d_ps_frames.p) {
+      if (mono && b->d_ps_frames.p) {
         PsFrameDev pf;
         memset(&pf, 0, sizeof pf);
         if (cudaMemcpy(&pf, b->d_ps_frames.p, sizeof pf, cudaMemcpyDeviceToHost) != cudaSuccess) rc = JAADB_E_CUDA;
@@ -1454,6 +1477,37 @@ int jaadb_probe_sbr(jaadb_engine* e, int32_t profile, int32_t sf_index, int32_t 
   if (b) jaadb_batch_destroy(b);
   jaadb_stream_close(e, sid);
   return rc;
+}
+}  // namespace
+
+int jaadb_probe_sbr(jaadb_engine* e, int32_t profile, int32_t sf_index, int32_t channel_config, const uint8_t* frame,
+                    uint32_t nbytes, int32_t* expect_sbr) {
+  if (!e || !frame || !expect_sbr) return JAADB_E_INVALID;
+  *expect_sbr = 0;
+  // SBR is only implemented for one SCE or one CPE (jaadb_stream_open_*)
+  if (channel_config < 1 || channel_config > 2 || sf_index < 0 || sf_index > 11) return JAADB_OK;
+  int32_t sid = -1;
+  int rc = jaadb_stream_open_adts(e, profile, sf_index, channel_config, channel_config == 1 ? 2 : 1, &sid);
+  if (rc) return rc;
+  return probe_with_stream(e, sid, channel_config == 1, frame, nbytes, expect_sbr);
+}
+
+int jaadb_probe_sbr_asc(jaadb_engine* e, const uint8_t* asc, uint32_t asc_bytes, const uint8_t* frame, uint32_t nbytes,
+                        int32_t* expect_sbr) {
+  if (!e || !asc || !frame || !expect_sbr) return JAADB_E_INVALID;
+  *expect_sbr = 0;
+  int32_t sid = -1;
+  // the scratch stream expects everything a mono / stereo stream could carry; other layouts have no SBR in this engine
+  int rc = jaadb_stream_open_asc_sbr(e, asc, asc_bytes, 2, &sid);
+  if (rc == JAADB_E_CONFIG) rc = jaadb_stream_open_asc_sbr(e, asc, asc_bytes, 1, &sid);
+  if (rc == JAADB_E_CONFIG) {
+    rc = jaadb_stream_open_asc(e, asc, asc_bytes, &sid);   // a valid ASC the SBR tool does not apply to: no SBR
+    if (rc == JAADB_OK) jaadb_stream_close(e, sid);
+    return rc;
+  }
+  if (rc) return rc;
+  const bool mono = e->streams[sid].chan_cfg == 1;
+  return probe_with_stream(e, sid, mono, frame, nbytes, expect_sbr);
 }
 
 }  // extern "C"

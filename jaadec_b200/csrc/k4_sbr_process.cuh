@@ -11,6 +11,7 @@
 #include "jaadb_types.cuh"
 #include "k2_filterbank.cuh"
 #include "sbr_types.cuh"
+#include "generated/jaad_dct32.h"   // DCT4_32 / DST4_32 operation lists, qmf32_pre_twiddle (tools/extract_dct32.py)
 
 namespace jaadb {
 
@@ -158,7 +159,8 @@ struct K4RunDev {
   uint8_t out_ch;           // output channel index
   uint8_t n_out;            // output channels of the stream
   uint8_t dup;              // mono element: copy the result to the second output channel (SBR1.process)
-  uint8_t pad[3];
+  uint8_t ds;               // down-sampled SBR (SBR.isSBRDownSampled): 32-band synthesis, 1024 output samples per frame
+  uint8_t pad[2];
   uint32_t ps_base;         // first PsFrameDev of the run (SBR+PS streams)
 };
 
@@ -969,6 +971,41 @@ __device__ __forceinline__ void sbr_synth_slot(float* __restrict__ row) {
   }
 }
 
+// Down-sampled bank (sbr/SynthesisFilterbank32.java:57-77): the staged row holds the pre-twiddled, scaled x1[0..31] | x2[0..31];
+// DCT4_32 / DST4_32 are the reference's operation lists (generated/jaad_dct32.h), the row is replaced by the slot's 64-entry
+// v-vector.
+#define JD_ADD(d, a, b) d = a + b;
+#define JD_SUB(d, a, b) d = a - b;
+#define JD_MUL(d, c, a) d = (c * a);
+__device__ __forceinline__ void sbr_dct4_32(float (&x)[32]) {
+  JAAD_DCT4_32_TEMPS
+  JAAD_DCT4_32_OPS
+}
+__device__ __forceinline__ void sbr_dst4_32(float (&x)[32]) {
+  JAAD_DST4_32_TEMPS
+  JAAD_DST4_32_OPS
+}
+#undef JD_ADD
+#undef JD_SUB
+#undef JD_MUL
+__device__ __forceinline__ void sbr_synth_slot32(float* __restrict__ row) {
+  float x[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) x[k] = row[k];
+  sbr_dct4_32(x);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { const float t = row[32 + k]; row[32 + k] = x[k]; x[k] = t; }   // park x1', fetch x2
+  sbr_dst4_32(x);
+  float x1[32];
+#pragma unroll
+  for (int n = 0; n < 32; ++n) x1[n] = row[32 + n];
+#pragma unroll
+  for (int n = 0; n < 32; ++n) {   // :69-72
+    row[n] = -x1[n] + x[n];
+    row[63 - n] = x1[n] + x[n];
+  }
+}
+
 // X[l][k] = Xsbr[l + tHFAdj][k] below kx + M of the slot's frame, 0 above (Channel.process_channel, SBR.java:604-645)
 __device__ __forceinline__ int k4_x_limit(const SbrFrameDev* fp, int mode, int l) {
   if (mode == 2) return (l < fp->t_E[0]) ? (fp->kx_prev + fp->M_prev) : (fp->kx + fp->M);
@@ -978,7 +1015,7 @@ __device__ __forceinline__ int k4_x_limit(const SbrFrameDev* fp, int mode, int l
 // PS: the runs are the SCEs of SBR+PS streams, blockIdx.y is the synthesis bank (SBR1.processPS, :121-122): 0 = left, fed
 // by K5's left matrix in frames that carry ps_data and by Xsbr (output duplicated) otherwise; 1 = right, which only exists
 // -- and only moves its history -- in frames that carry ps_data.
-template <int PCM_FORMAT, bool PS>
+template <int PCM_FORMAT, bool PS, bool DS>
 __global__ void __launch_bounds__(kK4cThreads)
 k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const RunFrameDev* __restrict__ run_frames,
                      const SbrFrameDev* __restrict__ sframes, const float* __restrict__ core, SbrChanDev* __restrict__ chans,
@@ -996,7 +1033,9 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
   const uint32_t rl = blockIdx.x / n_groups, r = run0 + rl, it0 = tile.lo + (blockIdx.x % n_groups) * kK4cG;
   const int bank = PS ? (int)blockIdx.y : 0;
   const K4RunDev run = runs[r];
-  if (it0 >= run.count) return;
+  if (it0 >= run.count || (run.ds != 0) != DS) return;   // the two banks are two instantiations over the same grid
+  constexpr int kOutLen = DS ? 1024 : 2048;   // samples per frame and channel
+  constexpr int kVLen = DS ? 64 : 128;        // entries of one v-vector
   const uint32_t it_end = min(min(run.count, tile.lo + tile.ft), it0 + kK4cG);
   const int nfr = (int)(it_end - it0);
   const int n_out = run.n_out;
@@ -1036,7 +1075,7 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
       if (use_ps) f.kind = 2;
     } else {
       if (ok) f.kind = mode == 0 ? 1 : 2;
-      if (out_ch == 0) pcm_bytes_out[rf.frame] = ok ? (uint32_t)(2048 * n_out * (PCM_FORMAT == 2 ? 4 : 2)) : 0u;
+      if (out_ch == 0) pcm_bytes_out[rf.frame] = ok ? (uint32_t)(kOutLen * n_out * (PCM_FORMAT == 2 ? 4 : 2)) : 0u;
     }
     if (f.kind == 2) {
       const uint32_t fwd = (PS && bank == 1) ? fp->fwd_ps : fp->fwd;
@@ -1087,6 +1126,25 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
   if (nsyn) {
     const int band = t & 63, rsel = t >> 6;   // kK4cThreads / 64 rows at a time
     constexpr int kRowsPerIter = kK4cThreads / 64;
+    // one QMF sample into its staged row: [Re X(0..63) | Im X(63..0)] for the 64-band bank; the down-sampled bank keeps
+    // bands 0..31 only, pre-twiddled and scaled (SynthesisFilterbank32.java:57-64), as [x1(0..31) | x2(0..31)]
+    float tw0 = 0.f, tw1 = 0.f;
+    if (DS && band < 32) { tw0 = __ldg(T.qmf32_tw + 2 * band); tw1 = __ldg(T.qmf32_tw + 2 * band + 1); }
+    auto stage = [&](float* row, float2 x) {
+      if (DS) {
+        if (band < 32) {
+          float x1 = (x.x * tw0) - (x.y * tw1);
+          float x2 = (x.y * tw0) + (x.x * tw1);
+          x1 *= 1.f / 64.f;
+          x2 *= 1.f / 64.f;
+          row[band] = x1;
+          row[32 + band] = x2;
+        }
+      } else {
+        row[band] = x.x;
+        row[127 - band] = x.y;
+      }
+    };
     for (int j = 0; j < nfr; ++j) {
       if (info[j].kind != 2) continue;
       const float* src = info[j].src;
@@ -1102,8 +1160,7 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
 #pragma unroll
       for (int u = 0; u < 32 / kRowsPerIter; ++u) {
         const int l = rsel + u * kRowsPerIter;
-        vb[(row0 + l) * kVbStride + band] = v[u].x;
-        vb[(row0 + l) * kVbStride + 127 - band] = v[u].y;
+        stage(vb + (row0 + l) * kVbStride, v[u]);
       }
     }
     if (halo == 2) {
@@ -1111,12 +1168,12 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
       for (int h = rsel; h < 9; h += kRowsPerIter) {
         float2 v = make_float2(0.f, 0.f);
         if (band < s_halo_lim[h]) v = __ldg(reinterpret_cast<const float2*>(src + (size_t)h * kXgRow) + band);
-        vb[h * kVbStride + band] = v.x;
-        vb[h * kVbStride + 127 - band] = v.y;
+        stage(vb + h * kVbStride, v);
       }
     } else {
       // carried v-vectors: row 8 is the newest (slot -1), row 0 the oldest (slot -9); [0] of the state = newest
-      for (int i = t; i < 9 * 128; i += kK4cThreads) vb[(8 - i / 128) * kVbStride + (i % 128)] = v_in[i];
+      for (int i = t; i < 9 * 128; i += kK4cThreads)
+        if ((i % 128) < kVLen) vb[(8 - i / 128) * kVbStride + (i % 128)] = v_in[i];
     }
   }
   __syncthreads();
@@ -1126,15 +1183,15 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
     int srow = -1;
     if (t < n_main) srow = 9 + t;
     else if (halo == 2 && t - n_main < 9) srow = t - n_main;
-    if (srow >= 0) sbr_synth_slot(vb + srow * kVbStride);
+    if (srow >= 0) { if (DS) sbr_synth_slot32(vb + srow * kVbStride); else sbr_synth_slot(vb + srow * kVbStride); }
   }
   __syncthreads();
   // ---- window + output: a warp per time slot, lanes take output samples lane and lane + 32
   auto put_sample = [&](const K4cFrame& f, int i, float v) {
     if (PCM_FORMAT == 2) {
       float* d = reinterpret_cast<float*>(f.dst);
-      d[(size_t)out_ch * 2048 + i] = v;
-      if (f.dup) d[(size_t)(out_ch + 1) * 2048 + i] = v;
+      d[(size_t)out_ch * kOutLen + i] = v;
+      if (f.dup) d[(size_t)(out_ch + 1) * kOutLen + i] = v;
     } else {
       uint32_t u = (uint32_t)pcm_round(v) & 0xFFFFu;
       if (PCM_FORMAT == 1) u = __byte_perm(u, 0, 0x4401);
@@ -1147,28 +1204,31 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
     }
   };
   if (nsyn) {
-    float qc[2][10];
+    constexpr int kHalves = DS ? 1 : 2;   // output samples per lane and slot
+    float qc[kHalves][10];
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf)
+    for (int hf = 0; hf < kHalves; ++hf)
 #pragma unroll
-      for (int j = 0; j < 10; ++j) qc[hf][j] = __ldg(T.qmf_c + lane + 32 * hf + 64 * j);   // (lane-dependent index: not the constant bank)
+      for (int j = 0; j < 10; ++j)   // (lane-dependent index: not the constant bank); the 32-band bank takes every other tap (:80-89)
+        qc[hf][j] = DS ? __ldg(T.qmf_c + 2 * lane + 64 * j) : __ldg(T.qmf_c + lane + 32 * hf + 64 * j);
     for (int j = 0; j < nfr; ++j) {
       if (info[j].kind != 2) continue;
       const K4cFrame f = info[j];
       for (int l = warp; l < 32; l += kK4cThreads / 32) {
         const int cur = f.row0 + l;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+        for (int hf = 0; hf < kHalves; ++hf) {
           const int k = lane + 32 * hf;
           float ov = (vb[cur * kVbStride + k] * qc[hf][0]);
 #pragma unroll
-          for (int jj = 1; jj < 10; ++jj) ov = ov + (vb[(cur - jj) * kVbStride + k + 64 * (jj & 1)] * qc[hf][jj]);
-          put_sample(f, 64 * l + k, ov);
+          for (int jj = 1; jj < 10; ++jj) ov = ov + (vb[(cur - jj) * kVbStride + k + (kVLen / 2) * (jj & 1)] * qc[hf][jj]);
+          put_sample(f, (kVLen / 2) * l + k, ov);
         }
       }
       // ---- the bank's last frame of the tile hands its nine newest v-vectors to the next tile
       if (f.last_in_tile) {
-        for (int i = t; i < 9 * 128; i += kK4cThreads) v_out[i] = vb[(f.row0 + 31 - i / 128) * kVbStride + (i % 128)];
+        for (int i = t; i < 9 * 128; i += kK4cThreads)
+          if ((i % 128) < kVLen) v_out[i] = vb[(f.row0 + 31 - i / 128) * kVbStride + (i % 128)];
         if (t == 0) { if (PS && bank == 1) pst->v_flip = 1; else st->v_flip = 1; }
       }
     }
@@ -1177,7 +1237,8 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
   for (int j = 0; j < nfr; ++j) {
     if (info[j].kind != 1) continue;
     const K4cFrame f = info[j];
-    for (int i = t; i < 2048; i += kK4cThreads) put_sample(f, i, i < 2 ? f.cs[i] : f.cs[i >> 1]);
+    // (down-sampled streams keep the core's length: SCE/CPE.process leave the core PCM as it is)
+    for (int i = t; i < kOutLen; i += kK4cThreads) put_sample(f, i, DS ? f.cs[i] : (i < 2 ? f.cs[i] : f.cs[i >> 1]));
   }
 }
 

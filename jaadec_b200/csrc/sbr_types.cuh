@@ -173,6 +173,7 @@ struct SbrTablesDev {
   const uint8_t* find_bands;        // [2 warp][7 bands][65 a0][65 a1]   FBT.find_bands, evaluated on the host
   const float* init_power;          // [64 bands][65 a0][65 a1]          FBT.find_initial_power, evaluated on the host
   const float* qmf_c;               // [640]
+  const float* qmf32_tw;            // [32][2]  SynthesisFilterbank32.qmf32_pre_twiddle
   const float* dct4_tab;            // [192]
   const float* w_real;              // [16]
   const float* w_imag;              // [16]

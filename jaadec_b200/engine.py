@@ -66,10 +66,20 @@ class Engine:
                     "probe_sbr")
         return int(out.value)
 
-    def open_asc(self, asc: bytes) -> int:
+    def probe_sbr_asc(self, asc: bytes, frame) -> int:
+        """probe_sbr for a stream described by an AudioSpecificConfig (MP4 tracks); feeds open_asc(asc, expect_sbr)."""
+        a = np.frombuffer(bytes(asc), np.uint8).copy()
+        buf = np.ascontiguousarray(frame, np.uint8)
+        out = C.c_int32(0)
+        self._check(self._lib.jaadb_probe_sbr_asc(self._h, _ptr(a), a.nbytes, _ptr(buf), buf.nbytes, C.byref(out)), "probe_sbr_asc")
+        return int(out.value)
+
+    def open_asc(self, asc: bytes, expect_sbr: int = 0) -> int:
+        """Decoder.create(byte[] asc).  expect_sbr > 0 (see probe_sbr): the frames carry SBR (2: + PS) the ASC does not
+        signal -- JAAD then runs its down-sampled SBR tool, 1024 samples per frame at the core rate (SURVEY A-20)."""
         sid = C.c_int32(-1)
         buf = np.frombuffer(bytes(asc), np.uint8).copy()
-        self._check(self._lib.jaadb_stream_open_asc(self._h, buf.ctypes.data, len(buf), C.byref(sid)), "stream_open_asc")
+        self._check(self._lib.jaadb_stream_open_asc_sbr(self._h, buf.ctypes.data, len(buf), expect_sbr, C.byref(sid)), "stream_open_asc")
         return sid.value
 
     def close_stream(self, sid: int):

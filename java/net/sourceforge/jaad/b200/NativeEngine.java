@@ -44,6 +44,7 @@ public final class NativeEngine implements AutoCloseable {
 	private static final MethodHandle LAST_ERROR = h("jaadb_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
 	private static final MethodHandle STATUS_STRING = h("jaadb_status_string", FunctionDescriptor.of(ADDRESS, JAVA_INT));
 	private static final MethodHandle OPEN_ASC = h("jaadb_stream_open_asc", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+	private static final MethodHandle OPEN_ASC_SBR = h("jaadb_stream_open_asc_sbr", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
 	private static final MethodHandle OPEN_ADTS = h("jaadb_stream_open_adts", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS));
 	private static final MethodHandle STREAM_CLOSE = h("jaadb_stream_close", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
 	private static final MethodHandle DECODE = h("jaadb_decode", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS));
@@ -142,6 +143,21 @@ public final class NativeEngine implements AutoCloseable {
 			MemorySegment id = a.allocate(JAVA_INT);
 			int rc = (int) OPEN_ASC.invokeExact(engine, buf, asc.length, id);
 			if (rc != 0) throw new IllegalArgumentException("jaadb_stream_open_asc: " + lastError());
+			return id.get(JAVA_INT, 0);
+		} catch (RuntimeException e) {
+			throw e;
+		} catch (Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	/** Decoder.create(byte[] asc) for a track whose frames carry SBR (2: + PS) the ASC does not signal: JAAD's down-sampled SBR tool. */
+	public int openAsc(byte[] asc, int expectSbr) {
+		try (Arena a = Arena.ofConfined()) {
+			MemorySegment buf = a.allocateFrom(JAVA_BYTE, asc);
+			MemorySegment id = a.allocate(JAVA_INT);
+			int rc = (int) OPEN_ASC_SBR.invokeExact(engine, buf, asc.length, expectSbr, id);
+			if (rc != 0) throw new IllegalArgumentException("jaadb_stream_open_asc_sbr: " + lastError());
 			return id.get(JAVA_INT, 0);
 		} catch (RuntimeException e) {
 			throw e;

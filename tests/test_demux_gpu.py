@@ -108,6 +108,49 @@ def test_mp4_he_aac_tracks_with_explicit_signalling():
             assert np.array_equal(pcm[first[s] + f], r["s16"]), (s, f)
 
 
+def test_mp4_he_aac_tracks_with_implicit_signalling_run_the_downsampled_tool():
+    """HE-AAC in MP4 whose esds only says AAC-LC at the core rate: JAAD meets the SBR payload with the output rate already
+    fixed by the ASC and runs its down-sampled SBR tool (SURVEY A-20: 1024 samples per frame at the core rate, band tables
+    for the core rate).  The probe looks at the track's first sample; an LC-only track next to them stays plain."""
+    cases = [
+        (_asc([(2, 5), (6, 4), (2, 4), (0, 3)]), gen.GenConfig(sf_index=6, chan_cfg=2, n_frames=14, target_bytes=341, sbr_mode=1, adts=False, sbr_downsampled=True), 2, 1),
+        (_asc([(2, 5), (6, 4), (1, 4), (0, 3)]), gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=14, target_bytes=171, sbr_mode=2, adts=False, sbr_downsampled=True), 1, 2),
+        (_asc([(2, 5), (6, 4), (2, 4), (0, 3)]), gen.GenConfig(sf_index=6, chan_cfg=2, n_frames=14, target_bytes=300, adts=False), 2, 0),
+    ]
+    eng = Engine(max_streams=8, pcm_format=PCM_S16LE, sbr_tile_frames=4)
+    files, streams, ascs, want = [], [], [], []
+    for k, (asc, cfg, core_ch, mode) in enumerate(cases):
+        st = gen.generate(cfg, 7100 + k)
+        raw = [st.data[o: o + n].tobytes() for o, n in zip(st.offsets, st.sizes)]
+        files.append(genmp4.write_mp4(raw, asc, 24000, core_ch, chunk_pattern=(3, 4), frame_duration=1024)[0])
+        streams.append(st)
+        ascs.append(asc)
+        want.append(mode)
+    blob = np.concatenate(files)
+    begin = np.concatenate([[0], np.cumsum([len(f) for f in files])])
+    frames0, first0, tracks = demux.mp4_index_many(blob, begin)
+    ids = []
+    for s, t in enumerate(tracks):
+        o, n = int(frames0["offset"][first0[s]]), int(frames0["nbytes"][first0[s]])
+        mode = eng.probe_sbr_asc(demux.asc_of(t), blob[o:o + n])
+        assert mode == want[s]
+        ids.append(eng.open_asc(demux.asc_of(t), expect_sbr=mode))
+    for sid in ids:
+        info = eng.stream_info(sid)
+        assert (info.channels, info.sample_length, info.sample_rate) == (2, 1024, 24000)
+    frames, first, _ = demux.mp4_index_many(blob, begin, ids)
+    pcm, res = eng.decode(blob, frames)
+    assert (res["status"] == 0).all()
+    pcm = np.frombuffer(pcm, np.int16).reshape(len(frames), 1024, 2)
+    for s, st in enumerate(streams):
+        dec = oracle.Decoder.create_asc(ascs[s])
+        for f in range(len(st.offsets)):
+            r = dec.decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
+            assert r["status"] == 0 and r["sample_length"] == 1024
+            assert np.array_equal(pcm[first[s] + f], r["s16"]), (s, f)
+    eng.close()
+
+
 def test_probe_sbr_tells_what_an_adts_stream_carries():
     """ADTS says AAC-LC for HE-AAC streams too (implicit signalling): the engine looks at the first frame."""
     eng = Engine(max_streams=4, pcm_format=PCM_S16LE)
