@@ -43,6 +43,11 @@ def cases():
         "sbr_mono": (gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=22, target_bytes=171, sbr_mode=1), 2, None),
         # HE-AAC v2: mono core + SBR + parametric stereo
         "ps_c4_mono": (gen.config(4, n_frames=24), 2, None),
+        # down-sampled SBR (SURVEY A-20): opened from an AAC-LC ASC at the core rate, SBR / PS arrive implicitly
+        "sbr_ds_stereo": (gen.GenConfig(sf_index=6, chan_cfg=2, n_frames=22, target_bytes=341, sbr_mode=1, adts=False,
+                                        sbr_downsampled=True), 2, bytes([0x13, 0x10])),
+        "ps_ds_mono": (gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=22, target_bytes=171, sbr_mode=2, adts=False,
+                                     sbr_downsampled=True), 2, bytes([0x13, 0x08])),
     }
 
 
@@ -90,7 +95,10 @@ def build_case(name, cfg, n_streams, asc):
 
 
 def main():
+    only = set(sys.argv[1:])
     for name, (cfg, n, asc) in cases().items():
+        if only and name not in only:
+            continue
         data = build_case(name, cfg, n, asc)
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **data)

@@ -163,11 +163,12 @@ def test_downsampled_synthesis_bank_matches_direct_form():
     assert np.abs(pcm[289:] - x[:-289]).max() / np.abs(x).max() < 2e-3
 
 
-@pytest.mark.parametrize("name", ["sbr_c3_stereo", "sbr_mono", "ps_c4_mono"])
+@pytest.mark.parametrize("name", ["sbr_c3_stereo", "sbr_mono", "ps_c4_mono", "sbr_ds_stereo", "ps_ds_mono"])
 def test_oracle_reproduces_sbr_golden(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     n_streams = int(g["frame_stream"].max()) + 1
-    decs = [oracle.Decoder.create_adts(*[int(x) for x in g["hdr"]]) for _ in range(n_streams)]
+    asc = g["asc"].tobytes()
+    decs = [oracle.Decoder.create_asc(asc) if asc else oracle.Decoder.create_adts(*[int(x) for x in g["hdr"]]) for _ in range(n_streams)]
     sha = hashlib.sha256()
     for i, (o, n, s) in enumerate(zip(g["frame_offset"], g["frame_nbytes"], g["frame_stream"])):
         r = decs[s].decode_frame(g["blob"][o:o + n])

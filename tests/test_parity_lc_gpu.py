@@ -169,7 +169,8 @@ def test_asc_open_5_1_raw_frames():
     eng.close()
 
 
-GOLDEN_CASES = ["lc_c1_long_44k", "lc_c2_mixed_48k", "lc_mono_24k", "lc_c5_51_raw", "sbr_c3_stereo", "sbr_mono", "ps_c4_mono"]
+GOLDEN_CASES = ["lc_c1_long_44k", "lc_c2_mixed_48k", "lc_mono_24k", "lc_c5_51_raw", "sbr_c3_stereo", "sbr_mono", "ps_c4_mono",
+                "sbr_ds_stereo", "ps_ds_mono"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -186,7 +187,7 @@ def test_engine_reproduces_committed_golden(name):
     for fmt in (PCM_S16LE, PCM_F32_PLANAR):
         eng = Engine(max_streams=8, pcm_format=fmt, flags=FLAG_DEBUG_TAPS)
         sbr = int(g["sbr"][0]) if "sbr" in g.files else 0
-        ids = [eng.open_asc(asc) if len(asc) else eng.open_adts(*[int(x) for x in g["hdr"]], expect_sbr=sbr) for _ in range(n_streams)]
+        ids = [eng.open_asc(asc, expect_sbr=sbr) if len(asc) else eng.open_adts(*[int(x) for x in g["hdr"]], expect_sbr=sbr) for _ in range(n_streams)]
         frames["stream_id"] = np.asarray(ids)[g["frame_stream"]]
         b = eng.batch(frames, g["blob"].nbytes)
         b.upload(g["blob"])
