@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Attribute an .ncu-rep's per-SASS-instruction counters to CUDA source lines.
 
-    tools/nculine.py <report.ncu-rep> <library.so> <kernel-name-substring> [top N]
+    tools/nculine.py <report.ncu-rep> <library.so> <kernel-name-substring> [top N] [ncu -k filter]
 
 The SASS page of the report lists instructions in address order; nvdisasm -g on the cubin extracted from the
 .so lists the same instructions with //## File/line markers (needs -lineinfo).  The .so must be the build that was profiled.
@@ -45,7 +45,9 @@ def main():
     rep, so, kernel = sys.argv[1:4]
     topn = int(sys.argv[4]) if len(sys.argv) > 4 else 30
     lines = sass_lines(so, kernel)
-    txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    # a report with several kernels: name the one to read (ncu's -k matches the demangled base name), e.g. regex:k2_filterbank
+    kfilter = ['-k', sys.argv[5]] if len(sys.argv) > 5 else []
+    txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + kfilter, capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, data = None, []
     for r in rows:
