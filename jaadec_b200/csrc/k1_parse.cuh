@@ -43,12 +43,12 @@ struct BitReader {
   uint32_t end;                        // first bit after the frame
   uint32_t last_word;                  // index of the last word that holds frame bits
   uint32_t widx;
-  uint32_t w0, w1;
+  uint32_t w0, w1;                     // words widx, widx + 1 (big-endian order restored)
+  uint32_t w2;                         // word widx + 2 as loaded: requested a word ahead of its first use and not touched
+                                       // (no byte swap) until then, so the in-order pipe never waits on the request
 
-  __device__ __forceinline__ uint32_t load(uint32_t i) const {
-    uint32_t v = (i <= last_word) ? __ldg(words + i) : 0u;
-    return __byte_perm(v, 0, 0x0123);
-  }
+  __device__ __forceinline__ uint32_t load_raw(uint32_t i) const { return (i <= last_word) ? __ldg(words + i) : 0u; }
+  __device__ __forceinline__ uint32_t load(uint32_t i) const { return __byte_perm(load_raw(i), 0, 0x0123); }
   __device__ __forceinline__ void init(const uint8_t* blob, uint64_t off, uint32_t nbytes) {
     uint64_t addr = reinterpret_cast<uint64_t>(blob) + off;
     uint32_t mis = (uint32_t)(addr & 3u);
@@ -59,6 +59,7 @@ struct BitReader {
     widx = pos >> 5;
     w0 = load(widx);
     w1 = load(widx + 1);
+    w2 = load_raw(widx + 2);
 #pragma unroll
     for (uint32_t k = 8; k <= 64; k += 8)
       if (widx + k <= last_word) asm volatile("prefetch.global.L2 [%0];" ::"l"(words + widx + k));
@@ -67,8 +68,11 @@ struct BitReader {
   __device__ __forceinline__ uint32_t peek() {
     uint32_t wi = pos >> 5;
     if (wi != widx) {
-      w0 = (wi == widx + 1) ? w1 : load(wi);
-      w1 = load(wi + 1);
+      // sequential walk: the word that becomes w1 was requested a word ago, so its L2 latency (the frames of a warp's 32
+      // lanes thrash L1) is behind the decoding of the previous 32 bits instead of in front of the next funnel shift
+      if (wi == widx + 1) { w0 = w1; w1 = __byte_perm(w2, 0, 0x0123); }
+      else { w0 = load(wi); w1 = load(wi + 1); }
+      w2 = load_raw(wi + 2);
       widx = wi;
       // one 32-byte sector, 256 bytes ahead of the read position, per sector consumed: the compressed frame
       // streams through L2 ahead of the serial Huffman walk instead of stalling it on HBM
