@@ -208,6 +208,11 @@ struct jaadb_engine {
   DevBuf<float> d_xps;                // K5 -> K4c: left / right QMF matrices of the tile's parametric-stereo frames
   PsChanDev* d_ps_chan = nullptr;     // [max_streams]
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // the SBR / PS pipeline runs one half of a batch's runs on `stream` and the other on `k4_stream` (launch_decode)
+  static constexpr int kK4MaxParts = 8;
+  cudaStream_t k4_stream[kK4MaxParts - 1] = {};
+  cudaEvent_t k4_fork = nullptr, k4_join[kK4MaxParts - 1] = {};
+  int k4_parts = 2;
 
   // workspace of the one-call path (jaadb_decode): grow-only, so a steady stream of calls allocates nothing.
   // The call is cut into chunks of consecutive frames; chunk k's PCM goes out over PCIe on copy_stream while
@@ -773,26 +778,56 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
       err = e->d_xps.ensure((size_t)n_ps * ft * 64 * kXgRow);
       if (err != cudaSuccess) return err;
     }
+    // The runs are independent, and the pipeline mixes a latency-bound kernel (K4b: one warp per channel walking the
+    // tile's frames, a quarter of the SM's warp slots, whole waves of equal length) with throughput kernels (K4a, K4c).
+    // So the runs go down the pipeline in two halves on two CUDA streams: one half's K4b shares the SMs with the other
+    // half's analysis / synthesis, and the part-filled last wave of a K4b launch is filled from the other stream.
+    struct Part { uint32_t p0, pn, q0, qn; cudaStream_t st; };   // plain runs [p0, p0 + pn), SBR+PS runs [q0, q0 + qn)
+    Part parts[jaadb_engine::kK4MaxParts];
+    const int n_parts = (n_k4_runs >= 8u * (uint32_t)e->k4_parts) ? e->k4_parts : 1;
+    for (int i = 0; i < n_parts; ++i) {
+      // (cut between elements: a CPE's two channel runs are neighbours)
+      const uint32_t pa = (uint32_t)((uint64_t)n_plain * i / n_parts) & ~1u, pb = (i + 1 == n_parts) ? n_plain : ((uint32_t)((uint64_t)n_plain * (i + 1) / n_parts) & ~1u);
+      const uint32_t qa = (uint32_t)((uint64_t)n_ps * i / n_parts), qb = (uint32_t)((uint64_t)n_ps * (i + 1) / n_parts);
+      parts[i] = {pa, pb - pa, n_plain + qa, qb - qa, i == 0 ? e->stream : e->k4_stream[i - 1]};
+    }
+    if (n_parts > 1) {
+      if ((err = cudaEventRecord(e->k4_fork, e->stream)) != cudaSuccess) return err;
+      for (int i = 1; i < n_parts; ++i)
+        if ((err = cudaStreamWaitEvent(parts[i].st, e->k4_fork, 0)) != cudaSuccess) return err;
+    }
+    const size_t xg_run = (size_t)rows * kXgRow, xps_run = (size_t)ft * 64 * kXgRow;
     for (uint32_t lo = 0; lo < B.k4_max_count; lo += ft) {
       const K4Tile tile{lo, ft, rows};
-      const uint32_t n_cf = n_k4_runs * ft, n_groups = (ft + kK4cG - 1) / kK4cG;
-      k4a_analysis_kernel<<<(n_cf + kK4aWarps - 1) / kK4aWarps, 32 * kK4aWarps, k4a_smem_bytes(), e->stream>>>(
-          B.k4_runs, n_k4_runs, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, tile);
-      k4b_hf_kernel<<<(n_k4_runs + kK4bWarps - 1) / kK4bWarps, 32 * kK4bWarps, k4b_smem_bytes(), e->stream>>>(
-          B.k4_runs, n_k4_runs, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, e->sbr_tables, tile);
-      *launches += 2;
-      if (n_ps) {
-        k5_ps_kernel<<<n_ps, kK5Threads, k5_smem_bytes(), e->stream>>>(B.k4_runs, n_plain, B.sbr_frames, B.ps_frames, e->d_ps_chan,
-                                                                         e->d_xg.p, e->d_xps.p, e->sbr_tables, tile);
-        ++*launches;
-      }
+      const uint32_t n_groups = (ft + kK4cG - 1) / kK4cG;
+      for (int pi = 0; pi < n_parts; ++pi) {
+        const Part& P = parts[pi];
+        const cudaStream_t st = P.st;
+        // analysis + HF generation / adjustment over a contiguous range of runs (sub-ranges see their own slice of xg)
+        auto front = [&](uint32_t r0, uint32_t n) {
+          if (!n) return;
+          const uint32_t n_cf = n * ft;
+          k4a_analysis_kernel<<<(n_cf + kK4aWarps - 1) / kK4aWarps, 32 * kK4aWarps, k4a_smem_bytes(), st>>>(
+              B.k4_runs + r0, n, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p + r0 * xg_run, tile);
+          k4b_hf_kernel<<<(n + kK4bWarps - 1) / kK4bWarps, 32 * kK4bWarps, k4b_smem_bytes(), st>>>(
+              B.k4_runs + r0, n, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p + r0 * xg_run, e->sbr_tables, tile);
+          *launches += 2;
+        };
+        front(P.p0, P.pn);
+        front(P.q0, P.qn);
+        float* const xps_part = P.qn ? e->d_xps.p + (size_t)(P.q0 - n_plain) * xps_run : nullptr;
+        if (P.qn) {
+          k5_ps_kernel<<<P.qn, kK5Threads, k5_smem_bytes(), st>>>(B.k4_runs, P.q0, B.sbr_frames, B.ps_frames, e->d_ps_chan,
+                                                                   e->d_xg.p, xps_part, e->sbr_tables, tile);
+          ++*launches;
+        }
 #define K4C_ARGS(R0) B.k4_runs, R0, B.run_frames, B.sbr_frames, B.core, e->d_sbr_chan, e->d_xg.p, B.pcm, B.pcm_off, B.pcm_bytes, \
-                     e->sbr_tables, tile, B.ps_frames, e->d_ps_chan, e->d_xps.p
+                     e->sbr_tables, tile, B.ps_frames, e->d_ps_chan, xps_part
 #define LAUNCH_K4C_BANK(FMT, DS)                                                                                                \
   do {                                                                                                                         \
-    if (n_plain) { k4c_synthesis_kernel<FMT, false, DS><<<n_plain * n_groups, kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(0u)); ++*launches; } \
-    if (n_ps) {                                                                                                                \
-      k4c_synthesis_kernel<FMT, true, DS><<<dim3(n_ps * n_groups, 2), kK4cThreads, k4c_smem_bytes(), e->stream>>>(K4C_ARGS(n_plain));    \
+    if (P.pn) { k4c_synthesis_kernel<FMT, false, DS><<<P.pn * n_groups, kK4cThreads, k4c_smem_bytes(), st>>>(K4C_ARGS(P.p0)); ++*launches; } \
+    if (P.qn) {                                                                                                                \
+      k4c_synthesis_kernel<FMT, true, DS><<<dim3(P.qn * n_groups, 2), kK4cThreads, k4c_smem_bytes(), st>>>(K4C_ARGS(P.q0));     \
       ++*launches;                                                                                                             \
     }                                                                                                                          \
   } while (0)
@@ -802,14 +837,19 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
     if (B.k4_banks & 1u) LAUNCH_K4C_BANK(FMT, false);                                                                          \
     if (B.k4_banks & 2u) LAUNCH_K4C_BANK(FMT, true);                                                                           \
   } while (0)
-      if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K4C(0);
-      else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K4C(1);
-      else LAUNCH_K4C(2);
+        if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K4C(0);
+        else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K4C(1);
+        else LAUNCH_K4C(2);
 #undef LAUNCH_K4C
 #undef LAUNCH_K4C_BANK
 #undef K4C_ARGS
-      k4_commit_kernel<<<(n_k4_runs + 255) / 256, 256, 0, e->stream>>>(B.k4_runs, n_k4_runs, n_plain, e->d_sbr_chan, e->d_ps_chan);
-      ++*launches;
+        if (P.pn) { k4_commit_kernel<<<(P.pn + 255) / 256, 256, 0, st>>>(B.k4_runs + P.p0, P.pn, P.pn, e->d_sbr_chan, e->d_ps_chan); ++*launches; }
+        if (P.qn) { k4_commit_kernel<<<(P.qn + 255) / 256, 256, 0, st>>>(B.k4_runs + P.q0, P.qn, 0u, e->d_sbr_chan, e->d_ps_chan); ++*launches; }
+      }
+    }
+    for (int i = 1; i < n_parts; ++i) {
+      if ((err = cudaEventRecord(e->k4_join[i - 1], parts[i].st)) != cudaSuccess) return err;
+      if ((err = cudaStreamWaitEvent(e->stream, e->k4_join[i - 1], 0)) != cudaSuccess) return err;
     }
   }
   return cudaSuccess;
@@ -859,6 +899,12 @@ int jaadb_engine_create(const jaadb_options* opts, jaadb_engine** out) {
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(JAADB_E_CUDA);
   for (auto& ev : e->ev)
     if (cudaEventCreate(&ev) != cudaSuccess) return fail(JAADB_E_CUDA);
+  if (const char* v = getenv("JAADB200_K4_PARTS")) e->k4_parts = std::min(std::max(atoi(v), 1), (int)jaadb_engine::kK4MaxParts);   // tuning experiments only
+  if (cudaEventCreateWithFlags(&e->k4_fork, cudaEventDisableTiming) != cudaSuccess) return fail(JAADB_E_CUDA);
+  for (int i = 0; i + 1 < e->k4_parts; ++i) {
+    if (cudaStreamCreateWithFlags(&e->k4_stream[i], cudaStreamNonBlocking) != cudaSuccess) return fail(JAADB_E_CUDA);
+    if (cudaEventCreateWithFlags(&e->k4_join[i], cudaEventDisableTiming) != cudaSuccess) return fail(JAADB_E_CUDA);
+  }
   int rc = init_tables(e);
   if (rc) return fail(rc);
   e->streams.resize(opts->max_streams);
@@ -894,6 +940,11 @@ void jaadb_engine_destroy(jaadb_engine* e) {
   e->d_xps.release();
   if (e->d_ps_chan) cudaFree(e->d_ps_chan);
   for (auto& ev : e->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& st : e->k4_stream)
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  if (e->k4_fork) cudaEventDestroy(e->k4_fork);
+  for (auto& ev : e->k4_join)
     if (ev) cudaEventDestroy(ev);
   auto& W = e->ws;
   if (W.copy_stream) { cudaStreamSynchronize(W.copy_stream); cudaStreamDestroy(W.copy_stream); }
