@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -242,6 +243,8 @@ struct jaadb_engine {
     FrameDev* h_frames[2] = {nullptr, nullptr};
     RunFrameDev* h_run_frames[2] = {nullptr, nullptr};
     RunDev* h_runs[2] = {nullptr, nullptr};
+    SbrRunDev* h_sbr_runs[2] = {nullptr, nullptr};
+    K4RunDev* h_k4_runs[2] = {nullptr, nullptr};
     size_t h_chunk_cap = 0, h_runs_cap = 0;
   } ws;
 
@@ -955,6 +958,8 @@ void jaadb_engine_destroy(jaadb_engine* e) {
     if (W.h_frames[i]) cudaFreeHost(W.h_frames[i]);
     if (W.h_run_frames[i]) cudaFreeHost(W.h_run_frames[i]);
     if (W.h_runs[i]) cudaFreeHost(W.h_runs[i]);
+    if (W.h_sbr_runs[i]) cudaFreeHost(W.h_sbr_runs[i]);
+    if (W.h_k4_runs[i]) cudaFreeHost(W.h_k4_runs[i]);
     W.pcm[i].release();
   }
   W.blob.release(); W.frames.release(); W.fside.release(); W.iside.release(); W.q.release(); W.runs.release();
@@ -1264,6 +1269,10 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   cudaSetDevice(e->opts.device);
   if (n_frames == 0) return JAADB_OK;
   auto& W = e->ws;
+  // JAADB200_TRACE=1: host-side timeline of the call on stderr (tuning aid)
+  static const bool trace = getenv("JAADB200_TRACE") != nullptr;
+  const auto t_call = std::chrono::steady_clock::now();
+  auto ms_now = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
   // The compressed frames go first (one copy: frames of a chunk may sit anywhere in the caller's blob), so that the
   // host-side layout work below runs while they are on the bus.
   {
@@ -1284,10 +1293,17 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   if (n_frames <= chunk + chunk / 2) chunk = n_frames;
   struct Range { uint32_t i0, i1; uint64_t lo, hi; };
   std::vector<Range> ranges;
-  for (uint32_t i0 = 0; i0 < n_frames; i0 += chunk) {
-    Range r{i0, std::min(n_frames, i0 + chunk), ~0ull, 0};
+  // the first chunks are short (from 1/8 of a chunk, growing by a quarter each): the PCM download -- the long pole of the
+  // call -- starts after a fraction of a chunk's kernel time instead of a whole one, and stays fed while the chunks grow
+  // (a chunk's kernels take up to 3/4 of the time of its download, so faster growth would starve the copy engine)
+  const bool ramp = !e->opts.chunk_frames && n_frames >= 4 * chunk;
+  uint32_t step = ramp ? chunk / 8 : chunk;
+  for (uint32_t i0 = 0; i0 < n_frames;) {
+    Range r{i0, std::min(n_frames, i0 + step), ~0ull, 0};
     for (uint32_t i = r.i0; i < r.i1; ++i) { r.lo = std::min(r.lo, off[i]); r.hi = std::max(r.hi, off[i] + size[i]); }
     ranges.push_back(r);
+    i0 = r.i1;
+    step = std::min(chunk, step + step / 4);
   }
   bool monotonic = true;
   for (size_t k = 1; k < ranges.size(); ++k) monotonic = monotonic && ranges[k].lo >= ranges[k - 1].hi;
@@ -1337,7 +1353,9 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
       if (W.h_frames[i]) cudaFreeHost(W.h_frames[i]);
       if (W.h_run_frames[i]) cudaFreeHost(W.h_run_frames[i]);
       if (W.h_runs[i]) cudaFreeHost(W.h_runs[i]);
-      W.h_frames[i] = nullptr; W.h_run_frames[i] = nullptr; W.h_runs[i] = nullptr;
+      if (W.h_sbr_runs[i]) cudaFreeHost(W.h_sbr_runs[i]);
+      if (W.h_k4_runs[i]) cudaFreeHost(W.h_k4_runs[i]);
+      W.h_frames[i] = nullptr; W.h_run_frames[i] = nullptr; W.h_runs[i] = nullptr; W.h_sbr_runs[i] = nullptr; W.h_k4_runs[i] = nullptr;
     }
     W.h_chunk_cap = W.h_runs_cap = 0;
     const size_t cc = std::max<size_t>(chunk, W.h_chunk_cap), rr = e->streams.size();
@@ -1345,6 +1363,8 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
       chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_frames[i]), sizeof(FrameDev) * cc, cudaHostAllocDefault));
       chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_run_frames[i]), sizeof(RunFrameDev) * cc, cudaHostAllocDefault));
       chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_runs[i]), sizeof(RunDev) * rr, cudaHostAllocDefault));
+      chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_sbr_runs[i]), sizeof(SbrRunDev) * rr, cudaHostAllocDefault));
+      chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_k4_runs[i]), sizeof(K4RunDev) * rr * 2, cudaHostAllocDefault));
     }
     if (ce == cudaSuccess) { W.h_chunk_cap = cc; W.h_runs_cap = rr; }
   }
@@ -1383,32 +1403,27 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
     const Range& r = ranges[k];
     const uint32_t n = r.i1 - r.i0;
     const int pb = (int)(k & 1);
-    if (k >= 2) {
-      CUDA_TRY(e, cudaEventSynchronize(W.desc_done[pb]));   // staging slot pb has been consumed
-      // chunk k - 2 is back on the host: its results are converted while the GPU works on chunks k - 1 and k
-      if (results) {
-        CUDA_TRY(e, cudaEventSynchronize(W.d2h_done[pb]));
-        convert_results(ranges[k - 2].i0, ranges[k - 2].i1);
-      }
-    }
+    if (k >= 2) CUDA_TRY(e, cudaEventSynchronize(W.desc_done[pb]));   // staging slot pb has been consumed
+    const double t_wait = ms_now();
     ix.frames_out = W.h_frames[pb];
     ix.run_frames_out = W.h_run_frames[pb];
     rc = index_frames(e, frames + r.i0, n, blob_bytes, ix);
+    const double t_idx = ms_now();
     if (rc) { cudaStreamSynchronize(e->stream); cudaStreamSynchronize(W.copy_stream); return rc; }
     memcpy(W.h_runs[pb], ix.runs.data(), sizeof(RunDev) * ix.runs.size());
     // the device descriptor buffers are still being read by the previous chunk's kernels: stream order protects them
     CUDA_TRY(e, cudaMemcpyAsync(W.frames.p, W.h_frames[pb], sizeof(FrameDev) * n, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(W.runs.p, W.h_runs[pb], sizeof(RunDev) * ix.runs.size(), cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(W.run_frames.p, W.h_run_frames[pb], sizeof(RunFrameDev) * n, cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(e, cudaEventRecord(W.desc_done[pb], e->stream));
     if (k >= 2) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, W.d2h_done[pb], 0));   // PCM buffer pb is free again
     if (!ix.sbr_runs.empty()) {
-      // small and rare enough for pageable staging (the copies below synchronise the stream; SBR batches trade a little
-      // overlap for simplicity here)
-      CUDA_TRY(e, cudaMemcpyAsync(W.sbr_runs.p, ix.sbr_runs.data(), sizeof(SbrRunDev) * ix.sbr_runs.size(), cudaMemcpyHostToDevice, e->stream));
-      CUDA_TRY(e, cudaMemcpyAsync(W.k4_runs.p, ix.k4_runs.data(), sizeof(K4RunDev) * ix.k4_runs.size(), cudaMemcpyHostToDevice, e->stream));
-      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+      // (pinned, double buffered like the other descriptors: the host goes on to index the next chunk)
+      memcpy(W.h_sbr_runs[pb], ix.sbr_runs.data(), sizeof(SbrRunDev) * ix.sbr_runs.size());
+      memcpy(W.h_k4_runs[pb], ix.k4_runs.data(), sizeof(K4RunDev) * ix.k4_runs.size());
+      CUDA_TRY(e, cudaMemcpyAsync(W.sbr_runs.p, W.h_sbr_runs[pb], sizeof(SbrRunDev) * ix.sbr_runs.size(), cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(e, cudaMemcpyAsync(W.k4_runs.p, W.h_k4_runs[pb], sizeof(K4RunDev) * ix.k4_runs.size(), cudaMemcpyHostToDevice, e->stream));
     }
+    CUDA_TRY(e, cudaEventRecord(W.desc_done[pb], e->stream));   // staging slot pb is consumed once the copies above are done
     DecodeBufs B{W.blob.p, W.frames.p, W.fside.p + r.i0, W.iside.p, W.q.p, W.runs.p, W.run_frames.p, W.pcm[pb].p - r.lo,
                  W.pcm_off.p + r.i0, W.pcm_bytes.p + r.i0, nullptr, W.sbr_runs.p, W.k4_runs.p, W.sbr_frames.p, W.core.p, W.ps_frames.p,
                  ix.n_k4_plain, ix.k4_max_count, ix.k4_banks};
@@ -1423,10 +1438,21 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
       CUDA_TRY(e, cudaMemcpyAsync(W.h_fside + r.i0, W.fside.p + r.i0, sizeof(FrameSide) * n, cudaMemcpyDeviceToHost, W.copy_stream));
       CUDA_TRY(e, cudaMemcpyAsync(W.h_pcm_bytes + r.i0, W.pcm_bytes.p + r.i0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, W.copy_stream));
     }
+    // Chunk k is on its way; only now does the host wait for chunk k - 2 to be back (d2h_done[pb] still stands for it) and
+    // convert its results, while the GPU works on chunks k - 1 and k.  (Waiting before indexing chunk k left the compute
+    // stream idle for the host's indexing time once per chunk.)
+    if (k >= 2 && results) {
+      CUDA_TRY(e, cudaEventSynchronize(W.d2h_done[pb]));
+      convert_results(ranges[k - 2].i0, ranges[k - 2].i1);
+    }
     CUDA_TRY(e, cudaEventRecord(W.d2h_done[pb], W.copy_stream));
+    if (trace) fprintf(stderr, "[jaadb] chunk %zu: %u frames, waited until %.2f ms, indexed by %.2f, launched by %.2f\n", k, n, t_wait, t_idx, ms_now());
   }
+  if (trace) fprintf(stderr, "[jaadb] all chunks submitted at %.2f ms\n", ms_now());
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  if (trace) fprintf(stderr, "[jaadb] kernels done at %.2f ms\n", ms_now());
   CUDA_TRY(e, cudaStreamSynchronize(W.copy_stream));
+  if (trace) fprintf(stderr, "[jaadb] downloads done at %.2f ms\n", ms_now());
   if (results) convert_results(ranges.size() >= 2 ? ranges[ranges.size() - 2].i0 : 0, n_frames);
   return JAADB_OK;
 }
