@@ -40,6 +40,15 @@ public final class B200Decoder implements AutoCloseable {
 		return new B200Decoder(engine, engine.openAsc(audioSpecificConfig));
 	}
 
+	/**
+	 * Decoder.create(byte[]) for a track whose first sample is at hand: JAAD decides about implicit SBR / PS when the first
+	 * payload arrives (aac/.../syntax/ChannelElement.java:65-76), this engine when the stream is opened -- so the first sample
+	 * is probed.  An ASC that does not signal SBR then runs JAAD's down-sampled SBR tool (1024 samples per frame).
+	 */
+	public static B200Decoder create(NativeEngine engine, byte[] audioSpecificConfig, byte[] firstSample) {
+		return new B200Decoder(engine, engine.openAsc(audioSpecificConfig, engine.probeSbrAsc(audioSpecificConfig, firstSample)));
+	}
+
 	/** profileIndex/sfIndex/channelConfig exactly as ADTSFrame reports them (src/.../adts/ADTSFrame.java:119-129). */
 	public static B200Decoder create(NativeEngine engine, int profileIndex, int sfIndex, int channelConfig, int expectSbr) {
 		return new B200Decoder(engine, engine.openAdts(profileIndex, sfIndex, channelConfig, expectSbr));

@@ -46,6 +46,8 @@ public final class NativeEngine implements AutoCloseable {
 	private static final MethodHandle OPEN_ASC = h("jaadb_stream_open_asc", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
 	private static final MethodHandle OPEN_ASC_SBR = h("jaadb_stream_open_asc_sbr", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
 	private static final MethodHandle OPEN_ADTS = h("jaadb_stream_open_adts", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS));
+	private static final MethodHandle PROBE_SBR = h("jaadb_probe_sbr", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+	private static final MethodHandle PROBE_SBR_ASC = h("jaadb_probe_sbr_asc", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
 	private static final MethodHandle STREAM_CLOSE = h("jaadb_stream_close", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
 	private static final MethodHandle DECODE = h("jaadb_decode", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS));
 
@@ -173,6 +175,41 @@ public final class NativeEngine implements AutoCloseable {
 			int rc = (int) OPEN_ADTS.invokeExact(engine, profileIndex, sfIndex, channelConfig, expectSbr, id);
 			if (rc != 0) throw new IllegalArgumentException("jaadb_stream_open_adts: " + lastError());
 			return id.get(JAVA_INT, 0);
+		} catch (RuntimeException e) {
+			throw e;
+		} catch (Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	/**
+	 * What expectSbr should be for an LC-signalled ADTS stream, judged by its first raw_data_block: JAAD creates the SBR
+	 * (and PS) tool when the first payload arrives (aac/.../syntax/ChannelElement.java:65-76); the batched engine decides
+	 * when the stream is opened.  0 = plain AAC-LC, 1 = SBR, 2 = SBR + parametric stereo.
+	 */
+	public int probeSbr(int profileIndex, int sfIndex, int channelConfig, byte[] firstFrame) {
+		try (Arena a = Arena.ofConfined()) {
+			MemorySegment buf = a.allocateFrom(JAVA_BYTE, firstFrame);
+			MemorySegment out = a.allocate(JAVA_INT);
+			int rc = (int) PROBE_SBR.invokeExact(engine, profileIndex, sfIndex, channelConfig, buf, firstFrame.length, out);
+			if (rc != 0) throw new IllegalArgumentException("jaadb_probe_sbr: " + lastError());
+			return out.get(JAVA_INT, 0);
+		} catch (RuntimeException e) {
+			throw e;
+		} catch (Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	/** The same for an MP4 track described by its AudioSpecificConfig; feeds {@link #openAsc(byte[], int)}. */
+	public int probeSbrAsc(byte[] asc, byte[] firstSample) {
+		try (Arena a = Arena.ofConfined()) {
+			MemorySegment cfg = a.allocateFrom(JAVA_BYTE, asc);
+			MemorySegment buf = a.allocateFrom(JAVA_BYTE, firstSample);
+			MemorySegment out = a.allocate(JAVA_INT);
+			int rc = (int) PROBE_SBR_ASC.invokeExact(engine, cfg, asc.length, buf, firstSample.length, out);
+			if (rc != 0) throw new IllegalArgumentException("jaadb_probe_sbr_asc: " + lastError());
+			return out.get(JAVA_INT, 0);
 		} catch (RuntimeException e) {
 			throw e;
 		} catch (Throwable t) {
