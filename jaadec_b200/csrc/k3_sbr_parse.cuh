@@ -1031,8 +1031,11 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
         int ext = 0;
         ld.get(4, ext);
         const int st = sbr_decode(ld, C, stereo, run.ps != 0, ext == 14);
-        if (st != 0 && frame_status == 0) {
-          // an exception inside SBR.decode fails the whole frame (EOS is swallowed by decodeFrame: no output)
+        if (st != 0 && frame_status != JAADB_ST_LAYOUT) {
+          // an exception inside SBR.decode fails the whole frame (EOS is swallowed by decodeFrame: no output).  It also
+          // wins over an error K1 met: JAAD parses the payload when it reaches the fill element (decodeFIL,
+          // SyntacticElements.java:169-203), and K1, which stops at its first error, only records a payload it got past
+          // -- so whatever K1 reported happened later in the frame and JAAD never gets there.
           frame_status = st;
           fs.status = st;
           fside[f].status = st;

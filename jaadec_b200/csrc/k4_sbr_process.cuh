@@ -386,7 +386,11 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
       }
       res_regular = !__any_sync(0xFFFFFFFFu, bad);
     }
+#ifdef K4B_FORCE_LITERAL   // test builds: always take the literal walks (the paths damaged band tables fall back to)
+    const bool pw_ok = false;
+#else
     const bool pw_ok = grid_sorted && res_regular;
+#endif
     // calc_chirp_factors (HFGeneration.java:230-245): lane i < N_Q
     if (lane < 8) {
       float bw = 0.f;
@@ -648,6 +652,9 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
       if (fp->N_Q > 7 || fp->N_Q < 1) bad = true;
       if (N_L >= 1 && N_L <= kK4bMaxNL && fp->f_table_lim[N_L] > M) bad = true;
       regular = !__any_sync(0xFFFFFFFFu, bad);
+#ifdef K4B_FORCE_LITERAL
+      regular = false;
+#endif
     }
     if (regular) {
       const int mcov = fp->f_table_lim[N_L];

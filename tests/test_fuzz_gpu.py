@@ -31,10 +31,11 @@ def test_corrupted_lc_streams_match_the_oracle(cfg_no, streams, frames, seed, p)
     assert r["bad_pcm"] == [], r["bad_pcm"]
 
 
-@pytest.mark.parametrize("cfg_no,seed,tile", [(3, 5, 0), (4, 6, 3)])
-def test_corrupted_sbr_streams_do_not_derail_the_engine(cfg_no, seed, tile):
-    """HE-AAC: the same exercise.  A handful of frames per thousand end differently (index errors inside JAAD's SBR / PS
-    tools that the engine does not emulate); everything else must match bit for bit."""
-    r = fuzz_gpu.run(cfg_no, 24, 24, seed, 0.3, tile=tile, verbose=False)
+@pytest.mark.parametrize("cfg_no,seed,tile,ds", [(3, 5, 0, False), (4, 6, 3, False), (3, 15, 5, True), (4, 16, 0, True)])
+def test_corrupted_sbr_streams_do_not_derail_the_engine(cfg_no, seed, tile, ds):
+    """HE-AAC: the same exercise, also for ASC-opened streams on the down-sampled SBR tool.  A handful of frames per thousand
+    end differently (index errors inside JAAD's SBR / PS tools that the engine does not emulate, DESIGN.md section 7);
+    everything else must match bit for bit."""
+    r = fuzz_gpu.run(cfg_no, 24, 24, seed, 0.3, tile=tile, verbose=False, downsampled=ds)
     assert r["mutated"] > 100
     assert len(r["bad_status"]) + len(r["bad_pcm"]) <= 3, (r["bad_status"], r["bad_pcm"])

@@ -76,4 +76,21 @@ for i, (s, f) in enumerate(index):
             g = b.tap(i, c, want_spec=False)
             t = decs[s].tap_ics(0, c)
             line += ['tap', c, g['info'][:5].tolist(), t['info'][:5].tolist() if t else None]
+    if os.environ.get('SBRTAPS') and r["status"] == 0 and res["status"][i] == 0:
+        # engine's SBR frame record vs the oracle's SBR state after this frame
+        for ch in range(cfg.chan_cfg):
+            t = decs[s].tap_sbr(0, ch); g = b.tap_sbr(i, ch)
+            if t is None or g is None: continue
+            L_E, L_Q = int(t["ints"][0]), int(t["ints"][1]); ex = t["extra"]
+            hdr_g = [int(g[k]) for k in ("L_E", "L_Q", "kx", "M", "N_high", "N_low", "N_Q", "noPatches", "reset")]
+            hdr_t = [L_E, L_Q] + ex[:5].tolist() + [int(ex[7]), int(ex[8])]
+            if hdr_g != hdr_t: line += ["sbr hdr", ch, hdr_g, hdr_t]
+            if not np.array_equal(g["t_E"][:L_E + 1], t["ints"][4:5 + L_E]): line += ["t_E", ch, g["t_E"].tolist(), t["ints"][4:10].tolist()]
+            for l in range(min(L_E, 5)):
+                nb = ex[2] if t["ints"][10 + l] else ex[3]
+                if not np.array_equal(g["E_orig"][l, :nb].view(np.uint32), t["e_orig"][l, :nb].view(np.uint32)): line += ["E_orig differs", ch, l]
+            for l in range(min(L_Q, 2)):
+                if not np.array_equal(g["Q_div"][l, :ex[4]].view(np.uint32), t["q_div"][l, :ex[4]].view(np.uint32)): line += ["Q_div differs", ch, l]
+            line += ["rec", ch, {k: (g[k].tolist() if hasattr(g[k], "tolist") else g[k]) for k in ("mode", "reset", "L_E", "L_Q", "kx", "M", "kx_prev", "M_prev", "l_A", "prevEnvIsShort", "smoothing_mode", "interpol_freq", "limiter_gains", "add_harmonic_flag_prev", "t_E", "f", "bs_invf_mode")},
+                     "harm", int(g["bs_add_harmonic"].sum()), int(g["bs_add_harmonic_prev"].sum()), "oracle extra", ex.tolist()]
     print(line)
