@@ -827,8 +827,9 @@ __device__ inline int sbr_data(SbrBits& ld, const SbrCtx& C, bool stereo, bool w
     SBR_TRY(sbr_invf_mode(ld, c0, S.N_Q));
     SBR_TRY(sbr_envelope(ld, C, c0, false));
     SBR_TRY(sbr_noise(ld, C, c0, false));
-    // NoiseEnvelope.dequantChannel happens here in the reference; the float tables are evaluated when the frame record
-    // is built (same inputs: E, Q, amp_res, f, n)
+    // NoiseEnvelope.dequantChannel happens here in the reference; the float tables are evaluated by all lanes after the
+    // syntax (same inputs: E, Q, amp_res, f, n) -- also when the rest of the payload fails
+    S.dequant = 1;
     for (int i = 0; i < 64; ++i) c0.bs_add_harmonic[i] = 0;
     SBR_TRY(sbr_harmonics(ld, c0, S.N_high));
     SBR_TRY(sbr_extended_data(ld, *C.T, with_ps ? &S.ps : nullptr));
@@ -889,6 +890,7 @@ __device__ inline int sbr_data(SbrBits& ld, const SbrCtx& C, bool stereo, bool w
     SBR_TRY(sbr_harmonics(ld, c0, S.N_high));
     SBR_TRY(sbr_harmonics(ld, c1, S.N_high));
   }
+  S.dequant = 1;   // dequantChannel x 2 or unmap (SBR2.java:128-133)
   SBR_TRY(sbr_extended_data(ld, *C.T, nullptr));
   return 0;
 }
@@ -1003,10 +1005,12 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
     const uint32_t f = run_frames[run.first + it].frame;
     int mode = 0;          // what K4 does with the frame (SbrFrameDev.mode)
     int frame_status = 0;
+    int dequant = 0;       // NoiseEnvelope.dequantChannel / unmap ran for this frame (lane 0 decides, all lanes do it)
     if (lane == 0) {
       const FrameDev fr = frames[f];
       FrameSide fs = fside[f];
       frame_status = fs.status;
+      S->dequant = 0;
       // JAAD's element objects (and their SBR) are per instance tag: a frame that carries another tag does not touch
       // this one (StreamState::tags; K2 applies the same rule to the core coder's state)
       bool foreign = false;
@@ -1068,6 +1072,8 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
       if (mode != 0 && S->ps.opened && S->ps.data_available) ps_data_decode(S->ps, *po);
       use_ps = po->use_ps;
     }
+    if (lane == 0) dequant = S->dequant;
+    dequant = __shfl_sync(0xFFFFFFFFu, dequant, 0);
     mode = __shfl_sync(0xFFFFFFFFu, mode, 0);
     frame_status = __shfl_sync(0xFFFFFFFFu, frame_status, 0);
     use_ps = __shfl_sync(0xFFFFFFFFu, use_ps, 0);
@@ -1076,21 +1082,25 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
     // ---- frame records (all lanes)
     for (int c = 0; c < nch; ++c) {
       SbrFrameDev* o = out + ((size_t)run.sbr_base + it) * 2 + c;
-      const SbrChanParse& cp = S->ch[c];
-      if (mode == 2) {
+      SbrChanParse& cp = S->ch[c];
+      if (dequant || mode == 2) {
+        // NoiseEnvelope.dequantChannel / unmap (when this frame's sbr_data got there): the bands and envelopes of this
+        // frame; everything else keeps what an earlier frame put there (SbrChanParse::E_orig).  The record of a frame that
+        // runs the tool is a copy of the arrays as they stand now.
         for (int i = lane; i < kSbrMaxLE * 64; i += 32) {
           const int l = i >> 6, k = i & 63;
-          float v = 0.f;
-          if (l < cp.L_E && k < S->n[cp.f[l]]) v = sbr_e_orig(T, *S, stereo, c, k, l);
-          o->E_orig[l][k] = v;
+          float v = cp.E_orig[l][k];
+          if (dequant && l < cp.L_E && k < S->n[cp.f[l]]) { v = sbr_e_orig(T, *S, stereo, c, k, l); cp.E_orig[l][k] = v; }
+          if (mode == 2) o->E_orig[l][k] = v;
         }
         if (lane < 16) {
           const int l = lane >> 3, k = lane & 7;
-          float qd = 0.f, qd2 = 0.f;
-          if (l < cp.L_Q && k < S->N_Q) sbr_q_div(T, *S, stereo, c, k, l, qd, qd2);
-          o->Q_div[l][k] = qd;
-          o->Q_div2[l][k] = qd2;
+          float qd = cp.Q_div[l][k], qd2 = cp.Q_div2[l][k];
+          if (dequant && l < cp.L_Q && k < S->N_Q) { sbr_q_div(T, *S, stereo, c, k, l, qd, qd2); cp.Q_div[l][k] = qd; cp.Q_div2[l][k] = qd2; }
+          if (mode == 2) { o->Q_div[l][k] = qd; o->Q_div2[l][k] = qd2; }
         }
+      }
+      if (mode == 2) {
         for (int i = lane; i < 64; i += 32) {
           o->f_table_res[0][i] = S->f_table_res[0][i];
           o->f_table_res[1][i] = S->f_table_res[1][i];

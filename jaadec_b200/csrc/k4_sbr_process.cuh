@@ -334,6 +334,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
 
   // ---- recursive state in: the smoothing ring, chirp factors (lanes < 8), phases
   for (int i = lane; i < 5 * 64; i += 32) { (&W.ringG[0][0])[i] = (&st->G_temp_prev[0][0])[i]; (&W.ringQ[0][0])[i] = (&st->Q_temp_prev[0][0])[i]; }
+  for (int i = lane; i < kSbrMaxLE * 64; i += 32) (&W.E_curr[0][0])[i] = (&st->E_curr[0][0])[i];   // (see SbrChanDev::E_curr)
   int ring_index = st->GQ_ringbuf_index;
   int index_noise_prev = st->index_noise_prev, psi_is_prev = st->psi_is_prev;
   float bw_prev = 0.f;
@@ -911,6 +912,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
 
   // ---- recursive state out
   for (int i = lane; i < 5 * 64; i += 32) { (&st->G_temp_prev[0][0])[i] = (&W.ringG[0][0])[i]; (&st->Q_temp_prev[0][0])[i] = (&W.ringQ[0][0])[i]; }
+  for (int i = lane; i < kSbrMaxLE * 64; i += 32) (&st->E_curr[0][0])[i] = (&W.E_curr[0][0])[i];
   if (lane < 8) { st->bwArray_prev[lane] = bw_prev; st->bs_invf_mode_prev[lane] = (uint8_t)invf_prev; }
   if (lane == 0) { st->GQ_ringbuf_index = ring_index; st->index_noise_prev = index_noise_prev; st->psi_is_prev = psi_is_prev; }
   if (last_it >= 0) {

@@ -32,6 +32,12 @@ struct SbrHeaderDev {  // sbr/Header.java
 
 // Parse-side state of one channel (sbr/Channel.java fields the bitstream syntax reads or updates)
 struct SbrChanParse {
+  // Channel.E_orig / Q_div / Q_div2 (sbr/Channel.java): float arrays NoiseEnvelope.dequantChannel fills for the bands and
+  // envelopes of the current frame only and nothing ever clears.  HFAdjustment.calculate_gain walks them with band counters
+  // that run past the current tables when the limiter table is older than the band tables (a header change in a frame
+  // that failed: tables rebuilt, patches / limiter bands not) -- and then reads what an earlier frame left there.
+  float E_orig[kSbrMaxLE][64];
+  float Q_div[2][8], Q_div2[2][8];
   int16_t E[64][kSbrMaxLE];
   int16_t Q[64][2];
   int16_t E_prev[64], Q_prev[64];
@@ -87,7 +93,7 @@ struct SbrElemDev {
   uint8_t patchNoSubbands[64];
   int8_t patchStartSubband[64];
   uint8_t tag_valid, tag;   // element_instance_tag of the element object this state belongs to (StreamState::tags)
-  uint8_t pad[1];
+  uint8_t dequant;          // this frame's sbr_data got as far as NoiseEnvelope.dequantChannel / unmap (K3, per frame)
   SbrChanParse ch[2];
   PsParseDev ps;          // mono element of an SBR+PS stream
   uint8_t pad2[4];
@@ -151,6 +157,10 @@ struct __align__(16) SbrChanDev {
   // into [v_sel ^ 1]; k4_commit_kernel flips v_sel afterwards
   float syn_v[2][9][128];
   float G_temp_prev[5][64], Q_temp_prev[5][64];
+  // Channel.E_curr (sbr/Channel.java): a scratch array in JAAD, but one that is never cleared -- a limiter table that
+  // outlived a header change (the frame that carried the header failed, so the tables were rebuilt for the new kx / M while
+  // the patches and the limiter bands were not) makes calculate_gain read entries at or above M that an earlier frame wrote
+  float E_curr[kSbrMaxLE][64];
   float bwArray_prev[8];
   uint8_t bs_invf_mode_prev[8];
   int32_t GQ_ringbuf_index, index_noise_prev, psi_is_prev;

@@ -44,6 +44,10 @@ info = eng.stream_info(ids[0])
 nch, ln = info.channels, info.sample_length
 per = nch * ln * 4
 shown = 0
+if os.environ.get('DUMP'):   # engine output and the mutated input of stream S, for offline comparison against oracle variants
+    sel = [i for i, (s, f) in enumerate(index) if s == S]
+    np.savez_compressed(os.environ['DUMP'], pcm=np.stack([pcm[i * per:(i + 1) * per].view(np.float32).reshape(nch, ln) for i in sel]),
+                        status=res["status"][sel], frames=[blob[int(frames["offset"][i]):int(frames["offset"][i]) + int(frames["nbytes"][i])].tobytes() for i in sel])
 for i, (s, f) in enumerate(index):
     if s != S: continue
     o, nb = int(frames["offset"][i]), int(frames["nbytes"][i])
@@ -93,4 +97,9 @@ for i, (s, f) in enumerate(index):
                 if not np.array_equal(g["Q_div"][l, :ex[4]].view(np.uint32), t["q_div"][l, :ex[4]].view(np.uint32)): line += ["Q_div differs", ch, l]
             line += ["rec", ch, {k: (g[k].tolist() if hasattr(g[k], "tolist") else g[k]) for k in ("mode", "reset", "L_E", "L_Q", "kx", "M", "kx_prev", "M_prev", "l_A", "prevEnvIsShort", "smoothing_mode", "interpol_freq", "limiter_gains", "add_harmonic_flag_prev", "t_E", "f", "bs_invf_mode")},
                      "harm", int(g["bs_add_harmonic"].sum()), int(g["bs_add_harmonic_prev"].sum()), "oracle extra", ex.tolist()]
+            if os.environ.get('SBRTAPS') == '2':
+                line += ["Q_div", g["Q_div"].tolist(), "Q_div2", g["Q_div2"].tolist(), "lim", g["f_table_lim"][:12].tolist(), "noise", g["f_table_noise"].tolist(),
+                         "map", g["table_map_k_to_g"][:40].tolist(), "patches", g["patchNoSubbands"].tolist(), g["patchStartSubband"].tolist(),
+                         "res", g["f_table_res"][0][:12].tolist(), g["f_table_res"][1][:14].tolist(), "N_L", int(g["N_L"]), "t_Q", g["t_Q"].tolist(),
+                         "E_orig0", g["E_orig"][0][:10].tolist()]
     print(line)
