@@ -28,7 +28,9 @@ sys.path.insert(0, ROOT)
 SF_FREQ = [96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000]
 # algorithmic bytes per frame: compressed in + s16 PCM out + overlap state read+write
 # config 3 (HE-AAC v1 stereo): + 2048-sample stereo s16 out + this engine's SBR state read+write per frame
-# (2 x SbrChanDev 12480 B + SbrElemDev 3468 B, jaadec_b200/csrc/sbr_types.cuh)
+# (2 x SbrChanDev 12480 B + SbrElemDev 3904 B of LIVE decoder state, jaadec_b200/csrc/sbr_types.cuh: the second copy of the
+# double-buffered synthesis history and the reference's never-cleared scratch arrays, which the engine keeps only to match
+# corrupted streams, are not counted)
 ALGO_BYTES = {1: lambda avg: avg + 4096 + 16384, 2: lambda avg: avg + 4096 + 16384, 5: lambda avg: avg + 12288 + 49152,
               3: lambda avg: avg + 8192 + 16384 + 2 * (2 * 12480 + 3904),
               # config 4 (HE-AAC v2): mono core overlap + one SbrChanDev + SbrElemDev + PsChanDev (22 KB), read + write
