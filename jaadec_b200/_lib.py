@@ -15,7 +15,7 @@ SYMBOLS = [
     "jaadb_abi_version", "jaadb_status_string", "jaadb_last_error", "jaadb_engine_create", "jaadb_engine_destroy",
     "jaadb_stream_open_asc", "jaadb_stream_open_asc_sbr", "jaadb_stream_open_adts", "jaadb_stream_close", "jaadb_stream_get_info", "jaadb_decode",
     "jaadb_batch_create", "jaadb_batch_pcm_bytes", "jaadb_batch_upload", "jaadb_batch_decode", "jaadb_batch_sync",
-    "jaadb_batch_download", "jaadb_batch_timings", "jaadb_batch_destroy", "jaadb_batch_tap", "jaadb_batch_tap_sbr",
+    "jaadb_batch_download", "jaadb_batch_timings", "jaadb_batch_destroy", "jaadb_batch_tap", "jaadb_batch_tap_sbr", "jaadb_batch_tap_ps",
     "jaadb_adts_index", "jaadb_adts_index_many", "jaadb_mp4_index", "jaadb_mp4_index_many", "jaadb_probe_sbr", "jaadb_probe_sbr_asc",
 ]
 

@@ -1528,6 +1528,24 @@ int jaadb_batch_tap_sbr(jaadb_batch* b, uint32_t frame, uint32_t ch, void* out, 
   return 0;
 }
 
+int jaadb_batch_tap_ps(jaadb_batch* b, uint32_t frame, void* out, uint32_t out_bytes) {
+  if (!b || !b->decoded || frame >= b->n_frames || !out) return JAADB_E_INVALID;
+  jaadb_engine* e = b->e;
+  cudaSetDevice(e->opts.device);
+  const int32_t slot = b->frames[frame].stream_slot;
+  for (const SbrRunDev& r : b->sbr_runs) {
+    if (r.stream_slot != slot || !r.ps) continue;
+    for (uint32_t it = 0; it < r.count; ++it) {
+      if (b->run_frames[r.first + it].frame != frame) continue;
+      if (out_bytes < sizeof(PsFrameDev)) return JAADB_E_CAPACITY;
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+      CUDA_TRY(e, cudaMemcpy(out, b->d_ps_frames.p + (size_t)r.ps_base + it, sizeof(PsFrameDev), cudaMemcpyDeviceToHost));
+      return (int)sizeof(PsFrameDev);
+    }
+  }
+  return 0;
+}
+
 namespace {
 // decodes `frame` with the scratch stream `sid` (opened expecting SBR, and PS on a mono core) and reports what it carries
 int probe_with_stream(jaadb_engine* e, int32_t sid, bool mono, const uint8_t* frame, uint32_t nbytes, int32_t* expect_sbr) {

@@ -174,3 +174,44 @@ def test_sbr_long_streams(cfg_no):
         assert res["status"][i] == r["status"] == 0, (s, f)
         assert np.array_equal(pcm[i * per:(i + 1) * per].view(np.int16).reshape(2048, 2), r["s16"]), (s, f)
     eng.close()
+
+
+def test_ps_parameters_equal_generator_truth():
+    """Integer stage of parametric stereo on the GPU (K3: ps_data syntax, Huffman, delta decoding in frequency / time with
+    JAAD's stride quirk, envelope borders): the parameters the mixing stage receives are the generator's ground truth --
+    no decoder involved -- and the oracle's, for every frame."""
+    n_checked, modes = 0, set()
+    for seed in range(12):
+        cfg = gen.config(4, n_frames=20)
+        st = gen.generate(cfg, gen.seed_for(4, 600 + seed), with_truth=True)
+        dec = oracle_decoder(cfg)
+        eng = Engine(max_streams=2, pcm_format=PCM_S16LE, sbr_tile_frames=6)
+        sid = eng.open_adts(2, cfg.sf_index, cfg.chan_cfg, expect_sbr=2)
+        frames = np.zeros(cfg.n_frames, dtype=[("offset", "<u8"), ("nbytes", "<u4"), ("stream_id", "<i4")])
+        frames["offset"], frames["nbytes"], frames["stream_id"] = st.offsets, st.sizes, sid
+        b = eng.batch(frames, st.data.nbytes)
+        b.upload(st.data)
+        b.decode()
+        _, res = b.download()
+        assert (res["status"] == 0).all()
+        for f in range(cfg.n_frames):
+            r = dec.decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
+            assert r["status"] == 0
+            g, t, tr = b.tap_ps(f), dec.tap_ps(0), st.truth["ps"][f]
+            assert g is not None and g["use_ps"] == 1
+            ne = int(g["num_env"])
+            assert ne == tr[0] == t["num_env"], (seed, f)
+            assert np.array_equal(g["border"][:ne + 1], tr[1:2 + ne]) and np.array_equal(g["border"][:ne + 1], t["border"][:ne + 1]), (seed, f)
+            assert np.array_equal(g["iid"][:ne], tr[8:178].reshape(5, 34)[:ne, :20]), (seed, f)
+            assert np.array_equal(g["icc"][:ne], tr[178:348].reshape(5, 34)[:ne, :20]), (seed, f)
+            assert np.array_equal(g["iid"][:ne], t["iid"][:ne, :20]) and np.array_equal(g["icc"][:ne], t["icc"][:ne, :20]), (seed, f)
+            modes.add((int(g["iid_mode"]), int(g["icc_mode"])))
+            n_checked += 1
+        b.close()
+        eng.close()
+    assert n_checked == 12 * 20 and len(modes) >= 3
+
+
+def oracle_decoder(cfg):
+    import oracle
+    return oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)

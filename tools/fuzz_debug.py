@@ -37,7 +37,7 @@ for i, (s, f) in enumerate(index):
             b = int(rng.integers(0, min(nb, 8) * 8))
             blob[o + b // 8] ^= 1 << (7 - b % 8); mut[(s, f)] = [("hdrflip", b)]
 decs = wl.oracle_decoders()
-eng = Engine(max_streams=n, pcm_format=PCM_F32_PLANAR, flags=FLAG_DEBUG_TAPS)
+eng = Engine(max_streams=n, pcm_format=PCM_F32_PLANAR, flags=FLAG_DEBUG_TAPS, sbr_tile_frames=int(os.environ.get("TILE", "0")))
 ids = [eng.open_adts(*wl.hdr, expect_sbr=cfg.sbr_mode) for _ in range(n)]
 b = eng.batch(frames, blob.nbytes); b.upload(blob); b.decode(); pcm, res = b.download()
 info = eng.stream_info(ids[0])
@@ -102,4 +102,13 @@ for i, (s, f) in enumerate(index):
                          "map", g["table_map_k_to_g"][:40].tolist(), "patches", g["patchNoSubbands"].tolist(), g["patchStartSubband"].tolist(),
                          "res", g["f_table_res"][0][:12].tolist(), g["f_table_res"][1][:14].tolist(), "N_L", int(g["N_L"]), "t_Q", g["t_Q"].tolist(),
                          "E_orig0", g["E_orig"][0][:10].tolist()]
+    if os.environ.get('PSTAPS') and r["status"] == 0 and res["status"][i] == 0 and cfg.sbr_mode > 1:
+        g, t = b.tap_ps(i), decs[s].tap_ps(0)
+        if g is not None and t is not None:
+            ne = int(g["num_env"])
+            line += ["ps", "use", int(g["use_ps"]), "num_env", ne, int(t["num_env"]), "modes", (int(g["iid_mode"]), int(g["icc_mode"])), (t["iid_mode"], t["icc_mode"]),
+                     "border", g["border"][:ne + 1].tolist(), t["border"][:ne + 1].tolist(),
+                     "iid eq", bool(np.array_equal(g["iid"][:ne], t["iid"][:ne, :20])), "icc eq", bool(np.array_equal(g["icc"][:ne], t["icc"][:ne, :20]))]
+            if not np.array_equal(g["icc"][:ne], t["icc"][:ne, :20]): line += ["icc", g["icc"][:ne].tolist(), t["icc"][:ne, :20].tolist()]
+            if not np.array_equal(g["iid"][:ne], t["iid"][:ne, :20]): line += ["iid", g["iid"][:ne].tolist(), t["iid"][:ne, :20].tolist()]
     print(line)
