@@ -170,12 +170,23 @@ __host__ __device__ constexpr size_t k1_smem_bytes(uint32_t lut_entries) {
 
 __device__ __forceinline__ void fail(int& status, bool& flag, int code) { status = code; flag = false; }
 
+// one more window-shape update of a channel whose element object is decoded a second time in the same frame (IcsSide::dup_shapes)
+__device__ __forceinline__ void add_dup_shape(IcsSide* s, const IcsInfoRegs& in) {
+  if (!in.shape_ok) return;
+  const uint32_t d = s->dup_shapes, n = d & 3u;
+  if (n < 3u) {
+    s->dup_shapes = (uint8_t)((d & ~3u) | (n + 1u) | ((uint32_t)(in.shape & 1) << (2u + n)));
+    s->info_decoded |= 2u;   // (K2 looks at dup_shapes only when this bit is set)
+  }
+}
+
 // individual_channel_stream (ICStream.decode, ICStream.java:60-111) for the lanes with go == true.
 // `in` holds the shared ics_info when common_window is set.  Returns with status updated.
 __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& status, const uint32_t* __restrict__ lut,
                                                const TablesDev& T, int sf_index, bool common, IcsInfoRegs& in,
                                                IcsSide* side, int16_t* __restrict__ q, int ms_mask,
-                                               uint8_t* __restrict__ cb_lane, const int16_t* __restrict__ s_swb, bool discard) {
+                                               uint8_t* __restrict__ cb_lane, const int16_t* __restrict__ s_swb, bool discard,
+                                               IcsSide* dup_side) {
   // discard: the element is not part of the stream's layout (see the element loop): it is parsed for its errors and its
   // length only, nothing is stored
   // codebook per (group, sfb) of this lane's ICS: shared memory, one byte column per thread
@@ -187,6 +198,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
       int st = parse_ics_info(br, in);
       // window_shape bookkeeping happens before predictor data is looked at (ICSInfo.java:90-91)
       if (!discard) store_ics_header(side, in, 0, 1, 0, 0);
+      else if (dup_side) add_dup_shape(dup_side, in);
       if (st) fail(status, go, st);
     }
   }
@@ -433,7 +445,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
 #undef CB
 }
 
-__global__ void __launch_bounds__(kK1Threads)
+__global__ void __launch_bounds__(kK1Threads, 4)   // 64 registers: four CTAs per SM (the shared-memory limit)
 k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ frames, uint32_t n_frames,
                 FrameSide* __restrict__ fside, IcsSide* __restrict__ iside_all, int16_t* __restrict__ q_all, TablesDev T,
                 const LayoutDev* __restrict__ layouts) {
@@ -468,7 +480,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
   const uint32_t start = br.pos;
   if (valid) {
     // every channel slot starts out "absent"
-    for (int c = 0; c < lay.n_channels; ++c) *reinterpret_cast<uint4*>(iside + c) = make_uint4(0, 0, 0, 0);
+    for (int c = 0; c < lay.n_channels; ++c) { *reinterpret_cast<uint4*>(iside + c) = make_uint4(0, 0, 0, 0); iside[c].dup_shapes = 0; }
     if (fr.nbytes < 4) fail(status, active, JAADB_ST_EOS);  // ADIFHeader.isPresent peeks 32 bits (transport/ADIFHeader.java:18)
     else if (br.peek() == 0x41444946u) fail(status, active, JAADB_ST_UNSUPPORTED_ELEMENT);  // 'ADIF'
     else if (!fr.profile_ok) fail(status, active, JAADB_ST_PROFILE);
@@ -476,6 +488,8 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
 
   int el = 0, n_good = 0;
   bool layout_bad = false;
+  int n_in_layout = 0;            // elements parsed while the frame still followed the stream's layout
+  int dup_slot = -1;              // channel slot of the in-layout element whose object the current element addresses again
   bool pend_r = false;            // the right channel of the current CPE is next
   int ch0 = 0, ms_mask = 0;
   bool common = false;
@@ -506,6 +520,11 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
           // something else further on), so the parse goes on -- into channel slots that exist -- and the frame ends as
           // JAADB_ST_LAYOUT only if nothing else stops it first.
           if (el >= lay.n_elements || lay.el_type[el] != type) layout_bad = true;
+          if (!layout_bad) n_in_layout = el + 1;
+          dup_slot = -1;
+          if (layout_bad)
+            for (int j = 0; j < n_in_layout && j < 4; ++j)
+              if (lay.el_type[j] == type && ((uint32_t)(fs.tags >> (4 * j)) & 15u) == tag) dup_slot = lay.el_first_ch[j];
           {
             ch0 = layout_bad ? 0 : lay.el_first_ch[el];
             ch = ch0;
@@ -521,9 +540,11 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
               if (common) {
                 const int st = parse_ics_info(br, in);
                 if (!layout_bad) store_ics_header(iside + ch0, in, 0, 1, 0, 1);
+                else if (dup_slot >= 0) add_dup_shape(iside + dup_slot, in);
                 if (st) { fail(status, active, st); go = false; }  // thrown inside infoL.decode: R's setCommonData never ran (CPE.java:95-96)
                 else {
                   if (!layout_bad) store_ics_header(iside + ch0 + 1, in, 0, 1, 0, 1);  // setCommonData updates R's window shape too
+                  else if (dup_slot >= 0) add_dup_shape(iside + dup_slot + 1, in);
                   ms_mask = (int)br.read(2);
                   uint32_t msv[4] = {0u, 0u, 0u, 0u};
                   if (ms_mask == 1) {
@@ -577,7 +598,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
     }
     __syncwarp();
     parse_ics_warp(go, br, status, s_lut, T, sf_index, common, in, iside + ch, qbase + ch * 1024, ms_mask,
-                   s_cb + threadIdx.x, s_swb, layout_bad);
+                   s_cb + threadIdx.x, s_swb, layout_bad, (layout_bad && dup_slot >= 0) ? iside + dup_slot + (ch - ch0) : nullptr);
     if (go) {
       if (status) active = false;
       else if (is_cpe_left) pend_r = true;

@@ -76,7 +76,7 @@ for i, (s, f) in enumerate(index):
                     c += 1
                 el += 1
     if os.environ.get('ALLTAPS'):
-        for c in range(2):
+        for c in range(cfg.chan_cfg if cfg.chan_cfg <= 2 else 2):
             g = b.tap(i, c, want_spec=False)
             t = decs[s].tap_ics(0, c)
             line += ['tap', c, g['info'][:5].tolist(), t['info'][:5].tolist() if t else None]
