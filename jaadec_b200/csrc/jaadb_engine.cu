@@ -1470,7 +1470,7 @@ int jaadb_batch_tap(jaadb_batch* b, uint32_t frame, uint32_t ch, int16_t* q, int
   CUDA_TRY(e, cudaMemcpy(&side, b->d_iside.p + ics, sizeof side, cudaMemcpyDeviceToHost));
   const int nb = side.num_groups * side.max_sfb;
   if (info) {
-    info[0] = side.present; info[1] = side.window_sequence; info[2] = side.window_shape; info[3] = side.info_decoded & 1;
+    info[0] = side.present; info[1] = side.window_sequence; info[2] = side.window_shape; info[3] = side.info_decoded;
     info[4] = side.max_sfb; info[5] = side.num_groups;
     for (int i = 0; i < 8; ++i) info[6 + i] = i < side.num_groups ? side.group_len[i] : 0;
     info[14] = side.ms_mask; info[15] = side.common_window;

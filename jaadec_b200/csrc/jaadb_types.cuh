@@ -64,11 +64,7 @@ struct __align__(16) IcsSide {
   uint8_t sfb_cb[kMaxSfbEntries];
   uint16_t sf_idx[kMaxSfbEntries];  // SCALEFACTOR_TABLE index, 0xFFFF: scalefactor is 0.0f
   uint8_t tns_present;
-  // JAAD keeps ONE object per (element type, instance tag): an element that shows up again in the same frame -- only damaged
-  // frames do that -- is decoded into the same object, so its ics_info moves this channel's window shapes once more
-  // (ICSInfo.java:90-91) even though the frame is lost.  [1:0] number of such extra updates, [4:2] their window_shape bits.
-  uint8_t dup_shapes;
-  uint8_t pad[6];
+  uint8_t pad[7];
 };
 static_assert(sizeof(IcsSide) == 400, "IcsSide layout");
 

@@ -170,14 +170,17 @@ __host__ __device__ constexpr size_t k1_smem_bytes(uint32_t lut_entries) {
 
 __device__ __forceinline__ void fail(int& status, bool& flag, int code) { status = code; flag = false; }
 
-// one more window-shape update of a channel whose element object is decoded a second time in the same frame (IcsSide::dup_shapes)
-__device__ __forceinline__ void add_dup_shape(IcsSide* s, const IcsInfoRegs& in) {
-  if (!in.shape_ok) return;
-  const uint32_t d = s->dup_shapes, n = d & 3u;
-  if (n < 3u) {
-    s->dup_shapes = (uint8_t)((d & ~3u) | (n + 1u) | ((uint32_t)(in.shape & 1) << (2u + n)));
-    s->info_decoded |= 2u;   // (K2 looks at dup_shapes only when this bit is set)
-  }
+// JAAD keeps ONE object per (element type, instance tag) (SyntacticElements.java:39-41): an element that shows the type and
+// tag of an element this frame has already decoded -- only damaged frames do that -- is decoded into the same object, and
+// its ics_info moves that channel's window shapes once more (ICSInfo.java:90-91) before the frame dies further on.  Such a
+// frame is never transformed, so all that survives it is windowShape[CURRENT] = the LAST shape read: the updates are
+// collected here (up to four: [2:0] channel slot, [3] shape, [4] valid, five bits each) and, if the frame does end in an
+// error, written over the slot's header at the end of the parse -- K2 then does what it does for every frame.
+__device__ __forceinline__ void note_dup_shape(uint32_t& pend, int slot, const IcsInfoRegs& in) {
+  if (slot < 0 || !in.shape_ok) return;
+  int n = 0;
+  while (n < 4 && ((pend >> (5 * n + 4)) & 1u)) ++n;
+  if (n < 4) pend |= ((uint32_t)(slot & 7) | ((uint32_t)(in.shape & 1) << 3) | 16u) << (5 * n);
 }
 
 // individual_channel_stream (ICStream.decode, ICStream.java:60-111) for the lanes with go == true.
@@ -186,7 +189,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
                                                const TablesDev& T, int sf_index, bool common, IcsInfoRegs& in,
                                                IcsSide* side, int16_t* __restrict__ q, int ms_mask,
                                                uint8_t* __restrict__ cb_lane, const int16_t* __restrict__ s_swb, bool discard,
-                                               IcsSide* dup_side) {
+                                               int dup_ch, uint32_t& dup_pend) {
   // discard: the element is not part of the stream's layout (see the element loop): it is parsed for its errors and its
   // length only, nothing is stored
   // codebook per (group, sfb) of this lane's ICS: shared memory, one byte column per thread
@@ -198,7 +201,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
       int st = parse_ics_info(br, in);
       // window_shape bookkeeping happens before predictor data is looked at (ICSInfo.java:90-91)
       if (!discard) store_ics_header(side, in, 0, 1, 0, 0);
-      else if (dup_side) add_dup_shape(dup_side, in);
+      else note_dup_shape(dup_pend, dup_ch, in);
       if (st) fail(status, go, st);
     }
   }
@@ -480,7 +483,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
   const uint32_t start = br.pos;
   if (valid) {
     // every channel slot starts out "absent"
-    for (int c = 0; c < lay.n_channels; ++c) { *reinterpret_cast<uint4*>(iside + c) = make_uint4(0, 0, 0, 0); iside[c].dup_shapes = 0; }
+    for (int c = 0; c < lay.n_channels; ++c) *reinterpret_cast<uint4*>(iside + c) = make_uint4(0, 0, 0, 0);
     if (fr.nbytes < 4) fail(status, active, JAADB_ST_EOS);  // ADIFHeader.isPresent peeks 32 bits (transport/ADIFHeader.java:18)
     else if (br.peek() == 0x41444946u) fail(status, active, JAADB_ST_UNSUPPORTED_ELEMENT);  // 'ADIF'
     else if (!fr.profile_ok) fail(status, active, JAADB_ST_PROFILE);
@@ -489,7 +492,8 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
   int el = 0, n_good = 0;
   bool layout_bad = false;
   int n_in_layout = 0;            // elements parsed while the frame still followed the stream's layout
-  int dup_slot = -1;              // channel slot of the in-layout element whose object the current element addresses again
+  int dup_slot = -1;              // first channel slot of the in-layout element whose object the current element addresses again
+  uint32_t dup_pend = 0;          // note_dup_shape
   bool pend_r = false;            // the right channel of the current CPE is next
   int ch0 = 0, ms_mask = 0;
   bool common = false;
@@ -540,11 +544,11 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
               if (common) {
                 const int st = parse_ics_info(br, in);
                 if (!layout_bad) store_ics_header(iside + ch0, in, 0, 1, 0, 1);
-                else if (dup_slot >= 0) add_dup_shape(iside + dup_slot, in);
+                else note_dup_shape(dup_pend, dup_slot, in);
                 if (st) { fail(status, active, st); go = false; }  // thrown inside infoL.decode: R's setCommonData never ran (CPE.java:95-96)
                 else {
                   if (!layout_bad) store_ics_header(iside + ch0 + 1, in, 0, 1, 0, 1);  // setCommonData updates R's window shape too
-                  else if (dup_slot >= 0) add_dup_shape(iside + dup_slot + 1, in);
+                  else note_dup_shape(dup_pend, dup_slot >= 0 ? dup_slot + 1 : -1, in);
                   ms_mask = (int)br.read(2);
                   uint32_t msv[4] = {0u, 0u, 0u, 0u};
                   if (ms_mask == 1) {
@@ -598,7 +602,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
     }
     __syncwarp();
     parse_ics_warp(go, br, status, s_lut, T, sf_index, common, in, iside + ch, qbase + ch * 1024, ms_mask,
-                   s_cb + threadIdx.x, s_swb, layout_bad, (layout_bad && dup_slot >= 0) ? iside + dup_slot + (ch - ch0) : nullptr);
+                   s_cb + threadIdx.x, s_swb, layout_bad, (layout_bad && dup_slot >= 0) ? dup_slot + (ch - ch0) : -1, dup_pend);
     if (go) {
       if (status) active = false;
       else if (is_cpe_left) pend_r = true;
@@ -609,6 +613,13 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
   if (valid) {
     if (br.overrun()) status = JAADB_ST_EOS;
     if (status == JAADB_ST_OK && (layout_bad || el != lay.n_elements)) status = JAADB_ST_LAYOUT;
+    if (dup_pend && status != JAADB_ST_OK && status != JAADB_ST_LAYOUT) {
+      for (int n = 0; n < 4 && ((dup_pend >> (5 * n + 4)) & 1u); ++n) {
+        IcsSide* const s = iside + ((dup_pend >> (5 * n)) & 7u);
+        s->window_shape = (uint8_t)((dup_pend >> (5 * n + 3)) & 1u);
+        s->info_decoded = 1;
+      }
+    }
     fs.status = status;
     fside[f] = fs;
   }

@@ -281,10 +281,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
     const bool run_ch = parsed && el_live && (emit || !run.sbr);
     // window-shape bookkeeping of ICSInfo.decode / setCommonData (ICSInfo.java:90-91,196-197)
     int shape_prev = shape_cur;
-    const uint32_t info_dec = sd->info_decoded;   // bit 0: ics_info was read, bit 1: IcsSide::dup_shapes is not empty
-    if ((info_dec & 1u) && shape_ok) { shape_prev = shape_cur; shape_cur = sd->window_shape; }
-    if ((info_dec & 2u) && shape_ok)   // the same element object decoded again in this (damaged) frame
-      for (uint32_t d = sd->dup_shapes, k = 0; k < (d & 3u); ++k) { shape_prev = shape_cur; shape_cur = (int)((d >> (2u + k)) & 1u); }
+    if (sd->info_decoded && shape_ok) { shape_prev = shape_cur; shape_cur = sd->window_shape; }
     const int ws = sd->window_sequence;
 
     if (run_ch) {
