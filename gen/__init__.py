@@ -31,13 +31,13 @@ class _Cfg(C.Structure):
         ("sf_index", C.c_int32), ("chan_cfg", C.c_int32), ("n_frames", C.c_int32), ("target_bytes", C.c_int32),
         ("long_only", C.c_int32), ("adts", C.c_int32), ("p_transient", C.c_float), ("p_common_window", C.c_float),
         ("p_tns", C.c_float), ("p_is", C.c_float), ("ms_mode", C.c_int32), ("sbr_mode", C.c_int32),
-        ("target_rms", C.c_float), ("sbr_quirk", C.c_int32), ("sbr_downsampled", C.c_int32), ("reserved", C.c_int32 * 1),
+        ("target_rms", C.c_float), ("sbr_quirk", C.c_int32), ("sbr_downsampled", C.c_int32), ("p_pns", C.c_float), ("tns_mild", C.c_int32),
     ]
 
 
 class _Truth(C.Structure):
     _fields_ = [("q", C.c_void_p), ("sfidx", C.c_void_p), ("sfbcb", C.c_void_p), ("info", C.c_void_p), ("msused", C.c_void_p),
-                ("sbr", C.c_void_p), ("ps", C.c_void_p)]
+                ("sbr", C.c_void_p), ("ps", C.c_void_p), ("tns", C.c_void_p)]
 
 
 _lib = None
@@ -73,11 +73,13 @@ class GenConfig:
     target_rms: float = 2500.0
     sbr_quirk: bool = False   # also emit coupled SBR frames only the reference's parser reads (see gen/aacgen_sbr.inc)
     sbr_downsampled: bool = False   # SBR band tables for the core rate: streams JAAD opens from an ASC without SBR signalling
+    p_pns: float = 0.0        # share of the scalefactor bands coded as perceptual noise (codebook 13)
+    tns_mild: bool = False    # TNS filters an ISO decoder can apply: order <= 12 (long) / 7 (short), small coefficients
 
     def c(self) -> _Cfg:
         return _Cfg(self.sf_index, self.chan_cfg, self.n_frames, self.target_bytes, int(self.long_only), int(self.adts),
                     self.p_transient, self.p_common_window, self.p_tns, self.p_is, self.ms_mode, self.sbr_mode,
-                    self.target_rms, int(self.sbr_quirk), int(self.sbr_downsampled), (C.c_int32 * 1)(0))
+                    self.target_rms, int(self.sbr_quirk), int(self.sbr_downsampled), self.p_pns, int(self.tns_mild))
 
 
 # BASELINE.json configurations.  Seeds: 0xAAC0 + 1000*config + stream_id.
@@ -131,7 +133,8 @@ def generate(cfg: GenConfig, seed: int, with_truth: bool = False) -> Stream:
         if cfg.sbr_mode > 1:
             truth["ps"] = np.zeros((cfg.n_frames, L.jg_ps_truth_ints()), np.int32)
             ps_p = truth["ps"].ctypes.data
-        t = _Truth(*(truth[k].ctypes.data for k in ("q", "sfidx", "sfbcb", "info", "msused")), sbr_p, ps_p)
+        truth["tns"] = np.zeros((cfg.n_frames, nics, 600), np.int32)
+        t = _Truth(*(truth[k].ctypes.data for k in ("q", "sfidx", "sfbcb", "info", "msused")), sbr_p, ps_p, truth["tns"].ctypes.data)
         tp = C.byref(t)
     cc = cfg.c()
     n = L.jg_generate(C.byref(cc), seed, out.ctypes.data, cap, offs.ctypes.data, sizes.ctypes.data, tp)

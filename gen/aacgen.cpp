@@ -132,14 +132,17 @@ struct IcsPlan {
   int globalGain = 0;
   bool tns = false;
   BitWriter tnsBits;
+  int32_t tnsTruth[600];   // present, then per window {n_filt, coef_res, 3 x {length, order, direction, compress, coef[20] (signed)}}
   const int16_t* swb = nullptr;
   int nswb = 0;
-  IcsPlan() { memset(cb, 0, sizeof cb); memset(sf, 0, sizeof sf); memset(q, 0, sizeof q); }
+  IcsPlan() { memset(cb, 0, sizeof cb); memset(sf, 0, sizeof sf); memset(q, 0, sizeof q); memset(tnsTruth, 0, sizeof tnsTruth); }
 };
 
 struct Ctx {
   Rng rng;
   int sfIndex;
+  double pPns = 0;      // > 0: perceptual noise substitution (codebook 13) on that share of the bands
+  bool tnsMild = false; // TNS filters an ISO decoder can apply without blowing up: order <= 12 / 7, small reflection coefficients
   explicit Ctx(uint64_t seed, int sfi) : rng(seed), sfIndex(sfi) {}
 };
 
@@ -234,6 +237,7 @@ void planSpectrum(Ctx& c, IcsPlan& p, bool isAllowed, int budgetBits) {
   for (int i = 0; i < n; ++i) {
     int cb = c.rng.chance(0.45) ? prev : c.rng.range(0, 11);
     if (isAllowed && c.rng.chance(0.05)) cb = c.rng.chance(0.5) ? 14 : 15;
+    if (c.pPns > 0 && c.rng.chance(c.pPns)) cb = 13;   // (no draw when the knob is off: older seeds keep their streams)
     p.cb[i] = cb;
     if (cb <= 11) prev = cb;
   }
@@ -308,11 +312,20 @@ double planScalefactors(Ctx& c, IcsPlan& p, double targetRms, double extraGain) 
   int n = p.ngroups * p.maxSfb;
   // relative scalefactors: equalise band energies, add jitter, bound consecutive deltas
   int rel[120];
-  int prevSf = 0, prevIs = 0;
+  int prevSf = 0, prevIs = 0, prevNoise = -1000;
   bool first = true;
   for (int i = 0; i < n; ++i) {
     int cb = p.cb[i];
     if (cb == 0) { rel[i] = 0; continue; }
+    if (cb == 13) {
+      // noise energy: the band's L2 norm is 2^(sf/4) (ICStream.java:252); a few hundred per coefficient
+      const int lo = p.ws == 2 ? 4 : 24, hi = p.ws == 2 ? 36 : 56;
+      int v = c.rng.range(lo, hi);
+      if (prevNoise > -1000) v = std::min(std::max(v, prevNoise - 60), prevNoise + 60);
+      rel[i] = v;
+      prevNoise = v;
+      continue;
+    }
     if (cb >= 14) {
       int pos = prevIs + c.rng.range(-6, 6);
       pos = std::min(std::max(pos, -4), 24);
@@ -366,7 +379,7 @@ double planScalefactors(Ctx& c, IcsPlan& p, double targetRms, double extraGain) 
   for (int i = 0; i < n; ++i) {
     int cb = p.cb[i];
     if (cb == 0) p.sf[i] = 0;
-    else if (cb >= 14) p.sf[i] = rel[i];
+    else if (cb >= 13) p.sf[i] = rel[i];
     else p.sf[i] = std::min(std::max(base + rel[i], 0), 255);
   }
   // global_gain: the first spectral band's scalefactor plus a small offset the first delta undoes
@@ -383,22 +396,39 @@ void planTns(Ctx& c, IcsPlan& p) {
   BitWriter& bw = p.tnsBits;
   bool sh = p.ws == 2;
   int nwin = sh ? 8 : 1;
+  int32_t* tt = p.tnsTruth;
+  tt[0] = 1;
   for (int w = 0; w < nwin; ++w) {
+    int32_t* tw = tt + 1 + 74 * w;
     int nf = sh ? c.rng.range(0, 1) : c.rng.range(0, 3);
     bw.put(nf, sh ? 1 : 2);
+    tw[0] = nf;
     if (!nf) continue;
     int coefRes = c.rng.range(0, 1);
     bw.put(coefRes, 1);
+    tw[1] = coefRes;
     for (int f = 0; f < nf; ++f) {
-      bw.put(c.rng.range(0, sh ? 15 : 63), sh ? 4 : 6);
-      int order = sh ? c.rng.range(0, 7) : c.rng.range(0, 20);
+      int32_t* tf = tw + 2 + 24 * f;
+      tf[0] = c.rng.range(0, sh ? 15 : 63);
+      bw.put(tf[0], sh ? 4 : 6);
+      int order = sh ? c.rng.range(0, 7) : c.rng.range(0, c.tnsMild ? 12 : 20);
       bw.put(order, sh ? 3 : 5);
+      tf[1] = order;
       if (order) {
-        bw.put(c.rng.range(0, 1), 1);
+        tf[2] = c.rng.range(0, 1);
+        bw.put(tf[2], 1);
         int cc = c.rng.range(0, 1);
         bw.put(cc, 1);
+        tf[3] = cc;
         int len = coefRes + 3 - cc;
-        for (int i = 0; i < order; ++i) bw.put(c.rng.range(0, (1 << len) - 1), len);
+        for (int i = 0; i < order; ++i) {
+          // mild: reflection coefficients up to ~0.43 (index +-1 at 3-bit, +-2 at 4-bit resolution)
+          const int lim = coefRes ? 2 : 1;
+          uint32_t raw = c.tnsMild ? ((uint32_t)c.rng.range(-std::min(lim, 1 << (len - 1)), std::min(lim, (1 << (len - 1)) - 1)) & ((1u << len) - 1u))
+                                   : (uint32_t)c.rng.range(0, (1 << len) - 1);
+          bw.put(raw, len);
+          tf[4 + i] = ((int32_t)(raw << (32 - len))) >> (32 - len);   // the signed index of 14496-3 4.6.9.3
+        }
       }
     }
   }
@@ -443,10 +473,18 @@ void writeIcs(Ctx& c, BitWriter& bw, const IcsPlan& p, bool commonWindow) {
     }
   }
   // scale_factor_data
-  int cur = p.globalGain, curIs = 0;
+  int cur = p.globalGain, curIs = 0, curNoise = p.globalGain - 90;
+  bool noiseFirst = true;
   for (int i = 0; i < p.ngroups * p.maxSfb; ++i) {
     int cb = p.cb[i];
     if (cb == 0) continue;
+    if (cb == 13) {
+      // ICStream.java:199-208: the first noise energy is 9 bits (offset 256), the others are coded differentially
+      if (noiseFirst) { bw.put((uint32_t)(p.sf[i] - curNoise + 256), 9); noiseFirst = false; }
+      else { int d = p.sf[i] - curNoise; bw.put(g_sfCode[d + 60], g_sfLen[d + 60]); }
+      curNoise = p.sf[i];
+      continue;
+    }
     if (cb >= 14) { int d = p.sf[i] - curIs; bw.put(g_sfCode[d + 60], g_sfLen[d + 60]); curIs = p.sf[i]; }
     else { int d = p.sf[i] - cur; bw.put(g_sfCode[d + 60], g_sfLen[d + 60]); cur = p.sf[i]; }
   }
@@ -485,7 +523,8 @@ struct jg_config {
   int32_t sbr_quirk;      // 1: also emit coupled SBR frames only the reference parses (aacgen_sbr.inc, SbrChanState)
   int32_t sbr_downsampled; // 1: SBR band tables for the CORE rate (what JAAD uses when the stream is opened from an ASC that
                           //    does not signal SBR: outputFrequency stays at the core rate, A/DecoderConfig.java:180, A/sbr/SBR.java:100-102)
-  int32_t reserved[1];
+  float p_pns;            // > 0: share of the bands coded as perceptual noise (codebook 13)
+  int32_t tns_mild;       // 1: TNS filters an ISO decoder can apply (orders <= 12 / 7, small coefficients)
 };
 
 // Ground truth per ICS (element order, L before R); arrays may be NULL.
@@ -498,6 +537,8 @@ struct jg_truth {
   int32_t* sbr;      // [n_frames][n_ics][480] SBR streams only: L_E, L_Q, frame class, pointer, t_E[6], f[6], amp_res,
                      //   coupling, (pad to 32), E[5][64], Q[2][64] as a decoder reconstructs them (aacgen_sbr.inc)
   int32_t* ps;       // [n_frames][348] SBR+PS streams only: num_env, border_position[6], pad, iid[5][34], icc[5][34]
+  int32_t* tns;      // [n_frames][n_ics][600]: tns_data_present, then per window {n_filt, coef_res, 3 x {length, order,
+                     //   direction, coef_compress, coef[20] as signed indices}} (IcsPlan::tnsTruth)
 };
 
 int jg_sbr_truth_ints(void) { return kSbrTruthInts; }
@@ -512,6 +553,8 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
                     int32_t* frame_sizes, const jg_truth* truth) {
   initTables();
   Ctx c(seed, cfg->sf_index);
+  c.pPns = cfg->p_pns;
+  c.tnsMild = cfg->tns_mild != 0;
   const int nIcs = jg_ics_per_frame(cfg->chan_cfg);
   const int nEl = jg_elements_per_frame(cfg->chan_cfg);
   // element layout
@@ -561,8 +604,10 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
           if (truth->sfidx) {
             for (int i = 0; i < 120; ++i) truth->sfidx[o * 120 + i] = -1;
             for (int i = 0; i < p.ngroups * p.maxSfb; ++i)
-              truth->sfidx[o * 120 + i] = p.cb[i] == 0 ? -1 : (int16_t)(p.sf[i] + 100);
+              truth->sfidx[o * 120 + i] = p.cb[i] == 0 ? -1 : p.cb[i] == 13 ? (int16_t)((std::min(std::max(p.sf[i], -100), 155) + 200) | 0x4000)
+                                                                              : (int16_t)(p.sf[i] + 100);
           }
+          if (truth->tns) memcpy(truth->tns + o * 600, p.tnsTruth, sizeof p.tnsTruth);
           if (truth->info) {
             int32_t* in = truth->info + o * 16;
             in[0] = 1; in[1] = p.ws; in[2] = p.shape; in[3] = 0; in[4] = p.maxSfb; in[5] = p.ngroups;
@@ -643,10 +688,12 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
                 int cb = p.cb[i];
                 int16_t v = -1;
                 if (cb >= 14) v = (int16_t)(200 - std::min(std::max(p.sf[i], -155), 100));
+                else if (cb == 13) v = (int16_t)((std::min(std::max(p.sf[i], -100), 155) + 200) | 0x4000);
                 else if (cb != 0) v = (int16_t)(p.sf[i] + 100);
                 truth->sfidx[o * 120 + i] = v;
               }
             }
+            if (truth->tns) memcpy(truth->tns + o * 600, p.tnsTruth, sizeof p.tnsTruth);
             if (truth->info) {
               int32_t* in = truth->info + o * 16;
               in[0] = 1; in[1] = p.ws; in[2] = p.shape; in[3] = 0; in[4] = p.maxSfb; in[5] = p.ngroups;

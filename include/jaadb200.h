@@ -66,6 +66,10 @@ extern "C" {
 /* TNS modes.  JAAD parses TNS data and never applies it (A/tools/TNS.java:63-68);
  * JAADB_TNS_JAAD reproduces that and is the parity mode. */
 #define JAADB_TNS_JAAD 0
+/* JAADB_TNS_ISO applies the all-pole filter of ISO/IEC 14496-3 4.6.9.3 (tns_decode_frame / tns_decode_coef /
+ * tns_ar_filter) between the stereo tools and the filterbank, as A/syntax/CPE.java:177-178 and A/syntax/SCE.java:104 place
+ * the call JAAD never implemented.  Checked against the oracle's ISO restatement (bit-identical) and a float64 direct form. */
+#define JAADB_TNS_ISO 1
 
 #define JAADB_FLAG_PROFILE 1u   /* record per-kernel CUDA-event timings (jaadb_batch_timings) */
 #define JAADB_FLAG_DEBUG_TAPS 2u /* keep the dequantised spectra for jaadb_batch_tap (parity tests) */
@@ -81,7 +85,8 @@ typedef struct jaadb_options {
   uint32_t flags;        /* JAADB_FLAG_* */
   uint32_t chunk_frames; /* jaadb_decode pipelines chunks of this many consecutive frames (0: default, 131072) */
   uint32_t sbr_tile_frames; /* SBR stages work on tiles of this many frames per stream (0: sized to the workspace budget) */
-  uint32_t reserved[1];
+  uint32_t k2_segment_frames; /* filterbank kernel: cut every stream's frames into segments of this many frames, one CTA
+                                 each (0: decided from the number of streams; tests use it to force the segmented path) */
 } jaadb_options;
 
 /* One AAC frame (an ADTS payload or an MP4 sample) inside the caller's blob.

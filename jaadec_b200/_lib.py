@@ -22,7 +22,7 @@ SYMBOLS = [
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_streams", C.c_uint32), ("pcm_format", C.c_int32), ("tns_mode", C.c_int32),
-                ("flags", C.c_uint32), ("chunk_frames", C.c_uint32), ("sbr_tile_frames", C.c_uint32), ("reserved", C.c_uint32 * 1)]
+                ("flags", C.c_uint32), ("chunk_frames", C.c_uint32), ("sbr_tile_frames", C.c_uint32), ("k2_segment_frames", C.c_uint32)]
 
 
 class FrameDesc(C.Structure):
@@ -64,7 +64,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if build_if_missing and _build.stale():
+    if os.environ.get("JAADB200_LIB"):
+        path = os.environ["JAADB200_LIB"]   # tuning experiments only: another build of the same sources (tools/build_variants.sh)
+    elif build_if_missing and _build.stale():
         path = _build.build()
     if not os.path.exists(path):
         raise RuntimeError("libjaadb200.so is missing (%s): build it with __graft_entry__.build(); "

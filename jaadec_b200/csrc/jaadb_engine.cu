@@ -25,7 +25,7 @@
 #include "k4_sbr_process.cuh"
 
 #ifndef K2_STEREO_MIN_BLOCKS
-#define K2_STEREO_MIN_BLOCKS 4
+#define K2_STEREO_MIN_BLOCKS 5
 #endif
 
 namespace T = ::jaad_tables;
@@ -146,12 +146,15 @@ LayoutDev make_layout(int chan_cfg) {
   return l;
 }
 
+constexpr uint32_t kK2SegCtas = 148 * 6;   // K2 CTAs worth aiming for when a batch has few streams (SMs x resident CTAs)
+
 struct FrameIndex {
-  struct Group { int nch; uint32_t first_run, n_runs; };
+  struct Group { int nch; uint32_t first_run, n_runs, first_seg, n_segs; bool segmented; };
   std::vector<FrameDev> frames;          // in the caller's order
   std::vector<RunDev> runs;              // grouped by channel-slot count so every K2 launch has one block size
   std::vector<RunFrameDev> run_frames;   // per run, its frames in the caller's order
   std::vector<Group> groups;
+  std::vector<K2SegDev> segs;            // K2's CTAs: per group, the runs cut into segments (one per run when streams abound)
   uint32_t n_ics = 0;
   // SBR streams: one parse run per element (K3), one process run per channel (K4)
   std::vector<SbrRunDev> sbr_runs;
@@ -228,6 +231,9 @@ struct jaadb_engine {
     DevBuf<int16_t> q;
     DevBuf<RunDev> runs;
     DevBuf<RunFrameDev> run_frames;
+    DevBuf<K2FrameDev> k2frames;
+    DevBuf<K2SegDev> segs;
+    DevBuf<float> ovl_stage;
     DevBuf<uint32_t> pcm_bytes;
     DevBuf<uint64_t> pcm_off;
     DevBuf<SbrRunDev> sbr_runs;
@@ -243,6 +249,7 @@ struct jaadb_engine {
     FrameDev* h_frames[2] = {nullptr, nullptr};
     RunFrameDev* h_run_frames[2] = {nullptr, nullptr};
     RunDev* h_runs[2] = {nullptr, nullptr};
+    K2SegDev* h_segs[2] = {nullptr, nullptr};
     SbrRunDev* h_sbr_runs[2] = {nullptr, nullptr};
     K4RunDev* h_k4_runs[2] = {nullptr, nullptr};
     size_t h_chunk_cap = 0, h_runs_cap = 0;
@@ -280,6 +287,10 @@ struct jaadb_batch {
   DevBuf<int16_t> d_q;
   DevBuf<RunDev> d_runs;
   DevBuf<RunFrameDev> d_run_frames;
+  DevBuf<K2FrameDev> d_k2frames;
+  DevBuf<K2SegDev> d_segs;
+  DevBuf<float> d_ovl_stage;
+  std::vector<K2SegDev> segs;
   DevBuf<uint32_t> d_pcm_bytes;
   DevBuf<uint64_t> d_pcm_off;
   DevBuf<float> d_spec_tap;
@@ -343,6 +354,17 @@ int init_tables(jaadb_engine* e) {
   if ((rc = e->upload(JT(KBD_1024), 1024, &D.win_long[1]))) return rc;
   if ((rc = e->upload(JT(SINE_128), 128, &D.win_short[0]))) return rc;
   if ((rc = e->upload(JT(KBD_128), 128, &D.win_short[1]))) return rc;
+  {
+    // ISO TNS (JAADB_TNS_ISO): tools/TNSTables.java:10-25 in TNS_TABLES order, SampleFrequency.java:15-26 {long, short}
+    float tns[36];
+    memcpy(tns, JT(TNS_COEF_0_3), 8 * 4);
+    memcpy(tns + 8, JT(TNS_COEF_0_4), 16 * 4);
+    memcpy(tns + 24, JT(TNS_COEF_1_3), 4 * 4);
+    memcpy(tns + 28, JT(TNS_COEF_1_4), 8 * 4);
+    static const uint8_t max_sfb[24] = {31, 9, 31, 9, 34, 10, 40, 14, 42, 14, 51, 14, 46, 14, 46, 14, 42, 14, 42, 14, 42, 14, 39, 14};
+    CUDA_TRY(e, cudaMemcpyToSymbol(c_tns_coef, tns, sizeof tns));
+    CUDA_TRY(e, cudaMemcpyToSymbol(c_tns_max_sfb, max_sfb, sizeof max_sfb));
+  }
   for (int c = 0; c < 8; ++c) e->layouts[c] = make_layout(c);
   const LayoutDev* dl = nullptr;
   if ((rc = e->upload(e->layouts, 8, &dl))) return rc;
@@ -539,7 +561,13 @@ int finish_open(jaadb_engine* e, StreamHost& s, int32_t* stream_id) {
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   }
   CUDA_TRY(e, cudaMemsetAsync(e->d_overlap + (size_t)slot * kMaxChannels * 1024, 0, sizeof(float) * kMaxChannels * 1024, e->stream));
-  CUDA_TRY(e, cudaMemsetAsync(e->d_sstate + slot, 0, sizeof(StreamState), e->stream));
+  {
+    StreamState fresh_state;
+    memset(&fresh_state, 0, sizeof fresh_state);
+    fresh_state.pns_state = kPnsSeed;   // ICStream.randomState (ICStream.java:26), one generator per stream
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_sstate + slot, &fresh_state, sizeof fresh_state, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  }
   *stream_id = slot;
   return JAADB_OK;
 }
@@ -549,13 +577,6 @@ uint32_t frame_pcm_bytes(const jaadb_engine* e, const StreamHost& s) {
   return (uint32_t)s.out_channels * (uint32_t)s.sample_length * per;
 }
 
-size_t k2_smem_bytes(int nch, int out_ch) {
-  const int per_ch = kSpecStride + 1024 + 2 * kXchgStride;
-  size_t b = sizeof(float) * (2 * 256 + 2 * 32 + (size_t)nch * per_ch);
-  b += sizeof(IcsSide) * nch + 4 * 8 * kMaxChannels;
-  b += sizeof(int16_t) * 1024 * out_ch;
-  return (b + 15) & ~size_t(15);
-}
 
 // ---- host-side indexing shared by the staged and the one-call paths -----------------------------------------
 
@@ -627,7 +648,7 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
   std::vector<uint32_t>& run_of = e->scratch_run_of;
   run_of.assign(e->streams.size(), 0xFFFFFFFFu);
   for (int nch = 1; nch <= kMaxChannels; ++nch) {
-    FrameIndex::Group g{nch, (uint32_t)ix.runs.size(), 0};
+    FrameIndex::Group g{nch, (uint32_t)ix.runs.size(), 0, 0, 0, false};
     for (size_t s = 0; s < e->streams.size(); ++s) {
       if (!count[s] || e->streams[s].n_slots != nch) continue;
       RunDev r;
@@ -646,6 +667,25 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
   }
   uint32_t acc = 0;
   for (auto& r : ix.runs) { r.first = acc; acc += r.count; }
+  // K2's CTAs.  With plenty of streams one CTA walks a whole run; with few, runs are cut into segments of G frames so that
+  // the GPU fills up (each segment re-runs the frame before it for the overlap it starts from: 1/G extra work).
+  ix.segs.clear();
+  for (auto& g : ix.groups) {
+    uint64_t total = 0;
+    uint32_t longest = 0;
+    for (uint32_t r = g.first_run; r < g.first_run + g.n_runs; ++r) { total += ix.runs[r].count; longest = std::max(longest, ix.runs[r].count); }
+    uint32_t G = 0;
+    if (e->opts.k2_segment_frames) G = e->opts.k2_segment_frames;
+    else if (g.n_runs * 2 <= kK2SegCtas) G = (uint32_t)std::max<uint64_t>(2, (total + kK2SegCtas - 1) / kK2SegCtas);
+    if (G >= longest) G = 0;
+    g.first_seg = (uint32_t)ix.segs.size();
+    g.segmented = G != 0;
+    for (uint32_t r = g.first_run; r < g.first_run + g.n_runs; ++r) {
+      const uint32_t cnt = ix.runs[r].count, step = G ? G : cnt;
+      for (uint32_t f0 = 0; f0 < cnt; f0 += step) ix.segs.push_back(K2SegDev{r, f0, std::min(step, cnt - f0)});
+    }
+    g.n_segs = (uint32_t)ix.segs.size() - g.first_seg;
+  }
   for (int pass = 0; pass < 2; ++pass) {   // plain SBR first, SBR+PS second: K4 launches them as two grids
     for (const auto& r : ix.runs) {
       if (!r.sbr) continue;
@@ -708,7 +748,11 @@ struct DecodeBufs {
   IcsSide* iside;
   int16_t* q;
   const RunDev* runs;
+  uint32_t n_runs;
   const RunFrameDev* run_frames;
+  K2FrameDev* k2frames;
+  const K2SegDev* segs;
+  float* ovl_stage;
   uint8_t* pcm;
   const uint64_t* pcm_off;
   uint32_t* pcm_bytes;
@@ -747,24 +791,50 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
     ++*launches;
   }
   if (after_k1) cudaEventRecord(after_k1, e->stream);
+  {
+    // everything that depends on a stream's earlier frames, once per run
+    const int bps = e->opts.pcm_format == JAADB_PCM_F32_PLANAR ? 4 : 2;
+    k2_prepass_kernel<<<(B.n_runs + 127) / 128, 128, 0, e->stream>>>(B.runs, B.n_runs, B.run_frames, B.fside, B.iside, e->d_sstate,
+                                                                     e->d_layouts, B.k2frames, B.pcm_bytes, bps,
+                                                                     e->opts.tns_mode == JAADB_TNS_ISO ? 1 : 0);
+    ++*launches;
+  }
   for (size_t gi = 0; gi < n_groups; ++gi) {
     const FrameIndex::Group& g = groups[gi];
     const int threads = g.nch * kThreadsPerChannel;
     const int out_ch = (g.nch == 1) ? 2 : g.nch;
-    const size_t smem = k2_smem_bytes(g.nch, out_ch);
-    const RunDev* runs = B.runs + g.first_run;
-#define K2_ARGS runs, B.run_frames, B.fside, B.iside, B.q, e->d_overlap, e->d_sstate, B.pcm, B.pcm_off, B.pcm_bytes, B.tap, B.core, e->tables, e->d_layouts, g.nch
+    const size_t smem = k2_smem_bytes(g.nch, out_ch, threads <= 128);
+    K2Args A;
+    A.segs = B.segs + g.first_seg;
+    A.runs = B.runs;
+    A.k2frames = B.k2frames;
+    A.frames = B.frames;
+    A.blob = B.blob;
+    A.iside = B.iside;
+    A.qall = B.q;
+    A.overlap_all = e->d_overlap;
+    A.overlap_stage = g.segmented ? B.ovl_stage : nullptr;
+    A.pcm = B.pcm;
+    A.pcm_off = B.pcm_off;
+    A.spec_tap = B.tap;
+    A.core = B.core;
+    A.layouts = e->d_layouts;
+    A.nch = g.nch;
 #define LAUNCH_K2(FMT)                                                                                              \
   do {                                                                                                              \
-    if (threads <= 128) k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS><<<g.n_runs, threads, smem, e->stream>>>(K2_ARGS); \
-    else k2_filterbank_kernel<FMT, 512, 1><<<g.n_runs, threads, smem, e->stream>>>(K2_ARGS);                        \
+    if (threads <= 128) k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS><<<g.n_segs, threads, smem, e->stream>>>(A, e->tables); \
+    else k2_filterbank_kernel<FMT, 512, 1><<<g.n_segs, threads, smem, e->stream>>>(A, e->tables);                   \
   } while (0)
     if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K2(0);
     else if (e->opts.pcm_format == JAADB_PCM_S16BE) LAUNCH_K2(1);
     else LAUNCH_K2(2);
 #undef LAUNCH_K2
-#undef K2_ARGS
     ++*launches;
+    if (g.segmented) {
+      k2_commit_kernel<<<g.n_runs, 256, 0, e->stream>>>(B.runs + g.first_run, g.n_runs, g.nch, B.ovl_stage + (size_t)g.first_run * kMaxChannels * 1024,
+                                                        e->d_overlap);
+      ++*launches;
+    }
   }
   if (after_k2) cudaEventRecord(after_k2, e->stream);
   if (n_k4_runs) {
@@ -891,7 +961,7 @@ const char* jaadb_last_error(const jaadb_engine* e) { return e ? e->error.c_str(
 int jaadb_engine_create(const jaadb_options* opts, jaadb_engine** out) {
   if (!opts || !out) return JAADB_E_INVALID;
   *out = nullptr;
-  if (opts->pcm_format < 0 || opts->pcm_format > 2 || opts->tns_mode != JAADB_TNS_JAAD || opts->max_streams == 0)
+  if (opts->pcm_format < 0 || opts->pcm_format > 2 || (opts->tns_mode != JAADB_TNS_JAAD && opts->tns_mode != JAADB_TNS_ISO) || opts->max_streams == 0)
     return JAADB_E_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || opts->device < 0 || opts->device >= ndev) return JAADB_E_CUDA;
@@ -919,10 +989,12 @@ int jaadb_engine_create(const jaadb_options* opts, jaadb_engine** out) {
     return fail(JAADB_E_NOMEM);
   // opt in to the shared-memory sizes the kernels need
   cudaFuncSetAttribute(k1_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(e->lut_entries));
-  const int k2max = (int)k2_smem_bytes(kMaxChannels, kMaxChannels);
+  const int k2max = (int)k2_smem_bytes(kMaxChannels, kMaxChannels, false), k2max2 = (int)k2_smem_bytes(2, 2, true);
+  // (the one- / two-channel instantiation wants as many resident CTAs as its registers allow: all of the SM's shared memory)
 #define K2_ATTR(FMT)                                                                                                     \
   cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max);             \
-  cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max)
+  cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max2); \
+  cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
   K2_ATTR(0); K2_ATTR(1); K2_ATTR(2);
 #undef K2_ATTR
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) return fail(JAADB_E_CUDA);
@@ -958,12 +1030,13 @@ void jaadb_engine_destroy(jaadb_engine* e) {
     if (W.h_frames[i]) cudaFreeHost(W.h_frames[i]);
     if (W.h_run_frames[i]) cudaFreeHost(W.h_run_frames[i]);
     if (W.h_runs[i]) cudaFreeHost(W.h_runs[i]);
+    if (W.h_segs[i]) cudaFreeHost(W.h_segs[i]);
     if (W.h_sbr_runs[i]) cudaFreeHost(W.h_sbr_runs[i]);
     if (W.h_k4_runs[i]) cudaFreeHost(W.h_k4_runs[i]);
     W.pcm[i].release();
   }
   W.blob.release(); W.frames.release(); W.fside.release(); W.iside.release(); W.q.release(); W.runs.release();
-  W.run_frames.release(); W.pcm_bytes.release(); W.pcm_off.release();
+  W.run_frames.release(); W.pcm_bytes.release(); W.pcm_off.release(); W.k2frames.release(); W.segs.release(); W.ovl_stage.release();
   W.sbr_runs.release(); W.k4_runs.release(); W.sbr_frames.release(); W.core.release(); W.ps_frames.release();
   if (W.h_fside) cudaFreeHost(W.h_fside);
   if (W.h_pcm_bytes) cudaFreeHost(W.h_pcm_bytes);
@@ -1116,7 +1189,8 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
   b->frames.swap(ix.frames);
   b->runs.swap(ix.runs);
   b->run_frames.swap(ix.run_frames);
-  for (const auto& g : ix.groups) b->groups.push_back(jaadb_batch::Group{g.nch, g.first_run, g.n_runs});
+  b->groups = ix.groups;
+  b->segs.swap(ix.segs);
   b->n_ics = ix.n_ics;
   b->sbr_runs.swap(ix.sbr_runs);
   b->k4_runs.swap(ix.k4_runs);
@@ -1137,6 +1211,13 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
   chk(b->d_q.ensure(std::max<size_t>((size_t)ics * 1024, 16)));
   chk(b->d_runs.ensure(std::max<size_t>(b->runs.size(), 1)));
   chk(b->d_run_frames.ensure(std::max<uint32_t>(n, 1)));
+  chk(b->d_k2frames.ensure(std::max<uint32_t>(n, 1)));
+  chk(b->d_segs.ensure(std::max<size_t>(b->segs.size(), 1)));
+  {
+    bool segmented = false;
+    for (const auto& g : b->groups) segmented = segmented || g.segmented;
+    if (segmented) chk(b->d_ovl_stage.ensure(b->runs.size() * kMaxChannels * 1024));
+  }
   chk(b->d_pcm_bytes.ensure(std::max<uint32_t>(n, 1)));
   chk(b->d_pcm_off.ensure(std::max<uint32_t>(n, 1)));
   if (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) chk(b->d_spec_tap.ensure(std::max<size_t>((size_t)ics * 1024, 16)));
@@ -1152,6 +1233,7 @@ int jaadb_batch_create(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, 
     chk(cudaMemcpyAsync(b->d_frames.p, b->frames.data(), sizeof(FrameDev) * n, cudaMemcpyHostToDevice, e->stream));
     chk(cudaMemcpyAsync(b->d_runs.p, b->runs.data(), sizeof(RunDev) * b->runs.size(), cudaMemcpyHostToDevice, e->stream));
     chk(cudaMemcpyAsync(b->d_run_frames.p, b->run_frames.data(), sizeof(RunFrameDev) * n, cudaMemcpyHostToDevice, e->stream));
+    chk(cudaMemcpyAsync(b->d_segs.p, b->segs.data(), sizeof(K2SegDev) * b->segs.size(), cudaMemcpyHostToDevice, e->stream));
     chk(cudaMemcpyAsync(b->d_pcm_off.p, b->pcm_off.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream));
     chk(cudaMemsetAsync(b->d_blob.p + blob_bytes, 0, 64, e->stream));
     if (b->n_sbr_frames) {
@@ -1184,7 +1266,8 @@ int jaadb_batch_decode(jaadb_batch* b) {
   uint32_t launches = 0;
   if (b->n_frames == 0) { b->decoded = true; return JAADB_OK; }
   if (prof) CUDA_TRY(e, cudaEventRecord(e->ev[0], e->stream));
-  DecodeBufs B{b->d_blob.p, b->d_frames.p, b->d_fside.p, b->d_iside.p, b->d_q.p, b->d_runs.p, b->d_run_frames.p, b->d_pcm.p,
+  DecodeBufs B{b->d_blob.p, b->d_frames.p, b->d_fside.p, b->d_iside.p, b->d_q.p, b->d_runs.p, (uint32_t)b->runs.size(), b->d_run_frames.p,
+               b->d_k2frames.p, b->d_segs.p, b->d_ovl_stage.p, b->d_pcm.p,
                b->d_pcm_off.p, b->d_pcm_bytes.p, (e->opts.flags & JAADB_FLAG_DEBUG_TAPS) ? b->d_spec_tap.p : nullptr,
                b->d_sbr_runs.p, b->d_k4_runs.p, b->d_sbr_frames.p, b->d_core.p, b->d_ps_frames.p, b->n_k4_plain,
                b->k4_max_count, b->k4_banks};
@@ -1253,6 +1336,7 @@ void jaadb_batch_destroy(jaadb_batch* b) {
   cudaStreamSynchronize(b->e->stream);
   b->d_blob.release(); b->d_pcm.release(); b->d_frames.release(); b->d_fside.release(); b->d_iside.release();
   b->d_q.release(); b->d_runs.release(); b->d_run_frames.release(); b->d_pcm_bytes.release(); b->d_pcm_off.release();
+  b->d_k2frames.release(); b->d_segs.release(); b->d_ovl_stage.release();
   b->d_spec_tap.release();
   b->d_sbr_runs.release(); b->d_k4_runs.release(); b->d_sbr_frames.release(); b->d_core.release(); b->d_ps_frames.release();
   delete b;
@@ -1338,6 +1422,8 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   chk(W.q.ensure(max_ics * 1024));
   chk(W.runs.ensure(e->streams.size()));
   chk(W.run_frames.ensure(chunk));
+  chk(W.k2frames.ensure(chunk));
+  chk(W.segs.ensure((size_t)chunk + e->streams.size()));
   chk(W.pcm_off.ensure(n_frames));
   bool any_sbr = false;
   for (uint32_t i = 0; i < n_frames && !any_sbr; ++i) any_sbr = e->streams[frames[i].stream_id].sbr != 0;
@@ -1353,9 +1439,10 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
       if (W.h_frames[i]) cudaFreeHost(W.h_frames[i]);
       if (W.h_run_frames[i]) cudaFreeHost(W.h_run_frames[i]);
       if (W.h_runs[i]) cudaFreeHost(W.h_runs[i]);
+      if (W.h_segs[i]) cudaFreeHost(W.h_segs[i]);
       if (W.h_sbr_runs[i]) cudaFreeHost(W.h_sbr_runs[i]);
       if (W.h_k4_runs[i]) cudaFreeHost(W.h_k4_runs[i]);
-      W.h_frames[i] = nullptr; W.h_run_frames[i] = nullptr; W.h_runs[i] = nullptr; W.h_sbr_runs[i] = nullptr; W.h_k4_runs[i] = nullptr;
+      W.h_frames[i] = nullptr; W.h_run_frames[i] = nullptr; W.h_runs[i] = nullptr; W.h_segs[i] = nullptr; W.h_sbr_runs[i] = nullptr; W.h_k4_runs[i] = nullptr;
     }
     W.h_chunk_cap = W.h_runs_cap = 0;
     const size_t cc = std::max<size_t>(chunk, W.h_chunk_cap), rr = e->streams.size();
@@ -1363,6 +1450,7 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
       chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_frames[i]), sizeof(FrameDev) * cc, cudaHostAllocDefault));
       chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_run_frames[i]), sizeof(RunFrameDev) * cc, cudaHostAllocDefault));
       chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_runs[i]), sizeof(RunDev) * rr, cudaHostAllocDefault));
+      chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_segs[i]), sizeof(K2SegDev) * (cc + rr), cudaHostAllocDefault));
       chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_sbr_runs[i]), sizeof(SbrRunDev) * rr, cudaHostAllocDefault));
       chk(cudaHostAlloc(reinterpret_cast<void**>(&W.h_k4_runs[i]), sizeof(K4RunDev) * rr * 2, cudaHostAllocDefault));
     }
@@ -1411,10 +1499,20 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
     const double t_idx = ms_now();
     if (rc) { cudaStreamSynchronize(e->stream); cudaStreamSynchronize(W.copy_stream); return rc; }
     memcpy(W.h_runs[pb], ix.runs.data(), sizeof(RunDev) * ix.runs.size());
+    memcpy(W.h_segs[pb], ix.segs.data(), sizeof(K2SegDev) * ix.segs.size());
+    {
+      bool segmented = false;
+      for (const auto& g : ix.groups) segmented = segmented || g.segmented;
+      if (segmented) {
+        const cudaError_t se = W.ovl_stage.ensure(ix.runs.size() * kMaxChannels * 1024);
+        if (se != cudaSuccess) { cudaStreamSynchronize(e->stream); cudaStreamSynchronize(W.copy_stream); e->set_error("workspace allocation"); return JAADB_E_NOMEM; }
+      }
+    }
     // the device descriptor buffers are still being read by the previous chunk's kernels: stream order protects them
     CUDA_TRY(e, cudaMemcpyAsync(W.frames.p, W.h_frames[pb], sizeof(FrameDev) * n, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(W.runs.p, W.h_runs[pb], sizeof(RunDev) * ix.runs.size(), cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(W.run_frames.p, W.h_run_frames[pb], sizeof(RunFrameDev) * n, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(W.segs.p, W.h_segs[pb], sizeof(K2SegDev) * ix.segs.size(), cudaMemcpyHostToDevice, e->stream));
     if (k >= 2) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, W.d2h_done[pb], 0));   // PCM buffer pb is free again
     if (!ix.sbr_runs.empty()) {
       // (pinned, double buffered like the other descriptors: the host goes on to index the next chunk)
@@ -1424,7 +1522,8 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
       CUDA_TRY(e, cudaMemcpyAsync(W.k4_runs.p, W.h_k4_runs[pb], sizeof(K4RunDev) * ix.k4_runs.size(), cudaMemcpyHostToDevice, e->stream));
     }
     CUDA_TRY(e, cudaEventRecord(W.desc_done[pb], e->stream));   // staging slot pb is consumed once the copies above are done
-    DecodeBufs B{W.blob.p, W.frames.p, W.fside.p + r.i0, W.iside.p, W.q.p, W.runs.p, W.run_frames.p, W.pcm[pb].p - r.lo,
+    DecodeBufs B{W.blob.p, W.frames.p, W.fside.p + r.i0, W.iside.p, W.q.p, W.runs.p, (uint32_t)ix.runs.size(), W.run_frames.p,
+                 W.k2frames.p, W.segs.p, W.ovl_stage.p, W.pcm[pb].p - r.lo,
                  W.pcm_off.p + r.i0, W.pcm_bytes.p + r.i0, nullptr, W.sbr_runs.p, W.k4_runs.p, W.sbr_frames.p, W.core.p, W.ps_frames.p,
                  ix.n_k4_plain, ix.k4_max_count, ix.k4_banks};
     CUDA_TRY(e, launch_decode(e, ix.groups.data(), ix.groups.size(), n, (uint32_t)ix.sbr_runs.size(), (uint32_t)ix.k4_runs.size(), B,

@@ -40,14 +40,18 @@ struct FrameDev {
   uint8_t flags;
 };
 
-struct FrameSide {
+struct __align__(8) FrameSide {
   int32_t status;
   uint16_t tags;          // 4-bit instance tag of up to 4 elements... (element i in bits 4i..4i+3)
   uint8_t n_elements;     // SCE / CPE / LFE elements completely decoded
   uint8_t n_started;      // ... whose element_instance_tag was read (a failing element counts here only)
   uint32_t sbr_bit_off[2];  // bit offset of an SBR FIL payload following element 0/1 (0 = none)
   uint32_t sbr_bits[2];
+  uint32_t pns_draws;     // values the frame's parse took from the PNS generator (ICStream.java:241-257), also in frames
+                          // that failed later on: the generator has moved by then
+  uint32_t pad;
 };
+static_assert(sizeof(FrameSide) == 32, "FrameSide layout");
 
 // Side information of one individual_channel_stream (one channel of one frame).
 struct __align__(16) IcsSide {
@@ -64,7 +68,10 @@ struct __align__(16) IcsSide {
   uint8_t sfb_cb[kMaxSfbEntries];
   uint16_t sf_idx[kMaxSfbEntries];  // SCALEFACTOR_TABLE index, 0xFFFF: scalefactor is 0.0f
   uint8_t tns_present;
-  uint8_t pad[7];
+  uint8_t has_pns;          // some band uses codebook 13
+  uint16_t pns_base;        // generator values the frame's earlier channels took (draw offset of this channel's first noise band)
+  uint32_t tns_bit_off;     // position of tns_data (TNS.java:35-61) relative to the frame's aligned word base, like
+                            // FrameSide::sbr_bit_off; read again by K2 in JAADB_TNS_ISO mode
 };
 static_assert(sizeof(IcsSide) == 400, "IcsSide layout");
 
@@ -76,8 +83,25 @@ struct StreamState {
   // decode against fresh objects and also leave these alone).
   uint16_t tags;                       // expected instance tag of element i in bits 4i..4i+3
   uint8_t tags_valid;                  // bit i: element i has been seen
-  uint8_t pad[5];
+  uint8_t pad;
+  // PNS generator (ICStream.java:26,247).  JAAD has ONE static generator per JVM; the engine keeps one per stream, seeded like
+  // JAAD's, i.e. every stream decodes as it would alone in a fresh JVM.
+  uint32_t pns_state;
 };
+static_assert(sizeof(StreamState) == 16, "StreamState layout");
+constexpr uint32_t kPnsSeed = 0x1F2E3D4Cu;
+
+// n steps of the generator s -> 1664525 s + 1013904223 (mod 2^32) at once: f^2(x) = a^2 x + (a + 1) c
+__host__ __device__ inline uint32_t pns_jump(uint32_t s, uint32_t n) {
+  uint32_t a = 1664525u, c = 1013904223u;
+  while (n) {
+    if (n & 1u) s = a * s + c;
+    c = (a + 1u) * c;
+    a = a * a;
+    n >>= 1;
+  }
+  return s;
+}
 
 struct RunDev {
   int32_t stream_slot;
@@ -89,10 +113,31 @@ struct RunDev {
   uint8_t sbr;         // SBR stream: K2 hands the core PCM (float, 1024 per channel) to K4 instead of packing output
 };
 
-// One frame of a run, in decode order (what K2 walks).
+// One frame of a run, in decode order.
 struct RunFrameDev {
   uint32_t frame;      // index into frames / frame_side / pcm_off
   uint32_t ics_base;   // that frame's first channel slot in ics_side / q
+};
+
+// The same frame as K2 sees it: everything that depends on the stream's earlier frames is resolved by the pre-pass
+// (k2_prepass_kernel), so the filterbank kernel can start anywhere in a run.
+struct __align__(16) K2FrameDev {
+  uint32_t frame;
+  uint32_t ics_base;
+  // [7:0] channel slot c goes through the filterbank   [15:8] windowShape[PREVIOUS] of slot c   [23:16] windowShape[CURRENT]
+  // [24] the frame yields PCM   [25] JAAD reached SyntacticElements.process   [26] ISO TNS to apply   [27] noise bands present
+  uint32_t flags;
+  uint32_t pns_state;  // PNS generator state when the frame's parse starts
+};
+constexpr uint32_t kK2Emit = 1u << 24, kK2Parsed = 1u << 25, kK2Tns = 1u << 26, kK2Pns = 1u << 27;
+
+// A piece of a run for one K2 CTA: frames [first, first + count) of run `run` (positions inside the run).  One segment per
+// run when there are plenty of streams; several when there are few (the IMDCT overlap a segment starts from is recomputed
+// from the frames before it, see k2_filterbank_kernel).
+struct K2SegDev {
+  uint32_t run;
+  uint32_t first;
+  uint32_t count;
 };
 
 // Huffman LUT entry (uint32):

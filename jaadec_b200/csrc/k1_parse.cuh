@@ -13,7 +13,7 @@
 //   syntax/ICSInfo.java:86-119,193-211     ics_info
 //   syntax/ICStream.java:60-275            section / scalefactor / pulse / spectral data
 //   huffman/Huffman.java:15-84             codeword, sign bits, escape
-//   tools/TNS.java:35-61                   TNS side info (parsed, not applied)
+//   tools/TNS.java:35-61                   TNS side info (checked here; K2 reads the coefficients in JAADB_TNS_ISO mode)
 #pragma once
 #include "jaadb_types.cuh"
 
@@ -189,7 +189,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
                                                const TablesDev& T, int sf_index, bool common, IcsInfoRegs& in,
                                                IcsSide* side, int16_t* __restrict__ q, int ms_mask,
                                                uint8_t* __restrict__ cb_lane, const int16_t* __restrict__ s_swb, bool discard,
-                                               int dup_ch, uint32_t& dup_pend) {
+                                               int dup_ch, uint32_t& dup_pend, uint32_t& pns_draws) {
   // discard: the element is not part of the stream's layout (see the element loop): it is parsed for its errors and its
   // length only, nothing is stored
   // codebook per (group, sfb) of this lane's ICS: shared memory, one byte column per thread
@@ -241,9 +241,10 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
   }
 
   // ---- scale_factor_data (ICStream.java:172-220), one band per iteration
+  const uint32_t pns_base = pns_draws;   // what the frame's earlier channels took from the PNS generator
+  bool noise_flag = true;                // (false afterwards: the channel has noise bands)
   {
     int off0 = global_gain, off1 = global_gain - 90, off2 = 0;
-    bool noise_flag = true;
     const uint32_t sfbase = T.book_base[0];
     uint16_t* sfo = side->sf_idx;
     int idx = 0;
@@ -310,6 +311,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
   }
   if (go) {
     const uint32_t tns_present = br.read1();
+    const uint32_t tns_off = br.pos;
     if (tns_present) {
       const int nwin = is_short ? 8 : 1;
       const int b0 = is_short ? 1 : 2, b1 = is_short ? 4 : 6, b2 = is_short ? 3 : 5;
@@ -332,7 +334,9 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
       }
     }
     if (go) {
-      if (!discard) side->tns_present = (uint8_t)tns_present;
+      // tns_present | has_pns | pns_base, tns_bit_off (IcsSide): K2 reads tns_data again in JAADB_TNS_ISO mode
+      if (!discard)
+        *reinterpret_cast<uint2*>(&side->tns_present) = make_uint2(tns_present | (noise_flag ? 0u : 0x100u) | (pns_base << 16), tns_off);
       if (br.read1()) fail(status, go, JAADB_ST_UNSUPPORTED_ELEMENT);  // gain control: outside the engine's scope
     }
   }
@@ -361,8 +365,11 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
           if (sfb > swb_count) fail(status, sp, JAADB_ST_ARRAY_BOUNDS);          // offsets[sfb+1] past the table
           else if (hcb == 0 || hcb >= 14) {
             if (sfb == swb_count) fail(status, sp, JAADB_ST_ARRAY_BOUNDS);       // Arrays.fill with a negative range
-          } else if (hcb == 13) fail(status, sp, JAADB_ST_UNSUPPORTED_ELEMENT);  // PNS: JAAD's process-wide RNG, see DESIGN.md
-          else if (sfb < swb_count) {                                            // (== swb_count: negative width, body never runs)
+          } else if (hcb == 13) {
+            // PNS (ICStream.java:241-257): the band takes glen * width values from the generator while it is parsed; K2
+            // regenerates them from the draw offset (a band at the table's end has a negative width: nothing happens)
+            if (sfb < swb_count) pns_draws += (uint32_t)(glen * (swb[sfb + 1] - swb[sfb]));
+          } else if (sfb < swb_count) {                                            // (== swb_count: negative width, body never runs)
             const int lo = swb[sfb], width = swb[sfb + 1] - lo;
             pos = gbase + glen * lo;
             rem = (glen * width) >> (hcb < 5 ? 2 : 1);
@@ -476,6 +483,8 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
   fs.n_elements = 0;
   fs.sbr_bit_off[0] = fs.sbr_bit_off[1] = 0;
   fs.sbr_bits[0] = fs.sbr_bits[1] = 0;
+  fs.pad = 0;
+  uint32_t pns_draws = 0;
   int status = JAADB_ST_OK;
   bool active = valid;
   BitReader br;
@@ -602,7 +611,8 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
     }
     __syncwarp();
     parse_ics_warp(go, br, status, s_lut, T, sf_index, common, in, iside + ch, qbase + ch * 1024, ms_mask,
-                   s_cb + threadIdx.x, s_swb, layout_bad, (layout_bad && dup_slot >= 0) ? dup_slot + (ch - ch0) : -1, dup_pend);
+                   s_cb + threadIdx.x, s_swb, layout_bad, (layout_bad && dup_slot >= 0) ? dup_slot + (ch - ch0) : -1, dup_pend,
+                   pns_draws);
     if (go) {
       if (status) active = false;
       else if (is_cpe_left) pend_r = true;
@@ -621,6 +631,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
       }
     }
     fs.status = status;
+    fs.pns_draws = pns_draws;
     fside[f] = fs;
   }
 }

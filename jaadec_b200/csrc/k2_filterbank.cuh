@@ -1,32 +1,50 @@
-// K2 -- spectral processing.  One CTA owns one stream and walks that stream's
-// frames of the batch in decode order, 64 threads per channel.  The next frame's
-// descriptor, side information and quantised coefficients are fetched into
-// registers while the current frame is in its FFT, so HBM latency stays off the
-// per-frame critical path:
-//   dequantisation (|q|^(4/3) LUT x 2^((sf-100)/4) LUT, ICStream.java:264-269)
+// K2 -- spectral processing.
+//
+// k2_prepass_kernel: one thread per stream walks that stream's frames of the batch in decode order and resolves
+//   everything that depends on earlier frames -- window_shape[PREVIOUS] (ICSInfo.java:90-91,196-197), the element
+//   instance tags the stream owns (Element.java:36-38), which channels reach the filterbank, the state of the PNS
+//   generator at the start of each frame (ICStream.java:26,247) -- into one 16-byte K2FrameDev per frame.
+// k2_filterbank_kernel: one CTA per segment of a stream (the whole run when there are plenty of streams, a few
+//   frames when there are few), 64 threads per channel:
+//   dequantisation (|q|^(4/3) LUT x 2^((sf-100)/4) LUT, ICStream.java:264-269) + PNS (ICStream.java:241-257)
 //   -> M/S (tools/MS.java:17-41) -> intensity stereo (tools/IS.java:17-53)
+//   -> [JAADB_TNS_ISO: the all-pole filter of ISO/IEC 14496-3 4.6.9.3; JAAD's TNS.process is a stub]
 //   -> IMDCT as an N/4-point complex FFT in registers + shared memory
 //      (filterbank/MDCT.java:36-81, FFT.java:48-135)
 //   -> sine/KBD windowing + overlap-add (filterbank/FilterBank.java:39-123)
 //   -> Math.round / clamp / interleave to int16 (S/SampleBuffer.java:168-209).
-// The overlap buffers of the stream stay in shared memory for the whole run and
-// touch HBM once per call, window_shape[PREVIOUS] is carried in a register.
+// The next frame's quantised coefficients and side information come in by a TMA bulk copy (cp.async.bulk + mbarrier)
+// into a shared-memory stage while the current frame is transformed; the overlap buffers of the stream stay in shared
+// memory for the whole segment.  The overlap a frame leaves behind is a function of that frame alone (every window
+// sequence assigns all 1024 entries), so a segment that does not start its run first re-runs the frame(s) before it
+// without output to get the overlap it starts from: the same float operations in the same order, still bit-exact.
 //
-// Bit-exactness: every floating-point operation is the same binary32 operation,
-// on the same operands, as in the Java code (separate multiply and add, no FMA:
-// this file must be compiled with --fmad=false).  The FFT keeps JAAD's butterfly
-// graph -- bit reversal, one radix-4 stage without twiddles, then radix-2 stages --
-// and only changes which thread evaluates which butterfly, so the float PCM is
-// bit-identical to JAAD's, not merely within tolerance.
+// Bit-exactness: every floating-point operation is the same binary32 operation, on the same operands, as in the Java
+// code (separate multiply and add, no FMA: this file must be compiled with --fmad=false).  The FFT keeps JAAD's
+// butterfly graph -- bit reversal, one radix-4 stage without twiddles, then radix-2 stages -- and only changes which
+// thread evaluates which butterfly, so the float PCM is bit-identical to JAAD's, not merely within tolerance.
 #pragma once
 #include "jaadb_types.cuh"
 
 namespace jaadb {
 
 constexpr int kThreadsPerChannel = 64;
-// shared memory per channel (floats): spectrum / FFT exchange (1024 + pad), overlap (1024)
-constexpr int kSpecStride = 1024 + 32;  // one pad float per 32 keeps the bit-reversed gather conflict-free
-constexpr int kXchgStride = 8 * 72;     // 8 blocks of 8x8 complex, rows padded to 9 (re and im planes)
+// shared memory per channel (floats): spectrum (1024 + 1 pad per 32) / FFT exchange 2 (two planes of 576) / packed PCM,
+// overlap (1024), FFT exchange 1 + post-twiddled buffer (two planes of 576)
+constexpr int kSpecStride = 1152;
+constexpr int kXchgStride = 8 * 72;     // 8 blocks of 8x8 complex, rows padded to 9; 8 short windows of 64 + 8
+constexpr int kK2ChFloats = kSpecStride + 1024 + 2 * kXchgStride;
+constexpr int kK2StageBytesPerCh = 2048 + (int)sizeof(IcsSide);   // q[1024] int16 + IcsSide of the next frame
+
+__host__ __device__ constexpr size_t k2_smem_bytes(int nch, int out_ch, bool planar_pcm) {
+  return sizeof(float) * (2 * 256 + 2 * 32 + (size_t)nch * kK2ChFloats) + (size_t)nch * kK2StageBytesPerCh + 16 +
+         (planar_pcm ? 0 : sizeof(int16_t) * 1024 * (size_t)out_ch);
+}
+
+// ISO TNS tables (JAADB_TNS_ISO): tools/TNSTables.java:10-25 in TNS_TABLES order {0_3, 0_4, 1_3, 1_4}, and
+// SampleFrequency.getMaximalTNS_SFB (SampleFrequency.java:15-26) as [sf_index][long, short]
+__constant__ float c_tns_coef[36];
+__constant__ uint8_t c_tns_max_sfb[24];
 
 __device__ __forceinline__ int spec_addr(int i) { return i + (i >> 5); }
 __device__ __forceinline__ int brev3(int j) { return ((j & 1) << 2) | (j & 2) | ((j >> 2) & 1); }
@@ -79,13 +97,17 @@ __device__ __forceinline__ float mdct_out(const float* __restrict__ re, const fl
   }
 }
 
-// Java Math.round(float) + SampleBuffer clamp (S/SampleBuffer.java:193-205).
-// floor + exact fractional test is Math.round for every float: |x| >= 2^23 has no fraction, +-inf give a NaN
-// difference (test false) and saturate in the conversion, NaN converts to 0 -- the same values Java produces.
-__device__ __forceinline__ int pcm_round(float x) {
-  const float f = floorf(x);
-  const int r = __float2int_rz(f) + ((x - f) >= 0.5f ? 1 : 0);
-  return min(max(r, -32768), 32767);
+// Java Math.round(float) + SampleBuffer clamp (S/SampleBuffer.java:193-205) in two instructions.
+// Math.round(x) = floor(x + 0.5) evaluated exactly.  fma.rm(x, 1, 0.5) is the exact sum rounded toward -inf: the largest
+// float <= x + 0.5, which is never below floor(x + 0.5) (an integer that is a float itself whenever a fraction exists), so
+// its floor is the floor of the exact sum.  cvt.rmi.sat.s16 takes that floor and saturates to [-32768, 32767] -- Java
+// saturates at the int range first and SampleBuffer clamps to 16 bits, the same result -- and converts NaN to 0 like Java.
+__device__ __forceinline__ uint32_t pcm_round16(float x) {
+  float y;
+  asm("fma.rm.f32 %0, %1, 0f3F800000, 0f3F000000;" : "=f"(y) : "f"(x));
+  int16_t r;
+  asm("cvt.rmi.sat.s16.f32 %0, %1;" : "=h"(r) : "f"(y));
+  return (uint32_t)(uint16_t)r;
 }
 
 // Per-thread constants of one 4-coefficient sub-chunk (all SWB offsets are multiples of 4, so the four
@@ -102,47 +124,55 @@ __device__ __forceinline__ uint32_t subchunk_consts(const TablesDev& T, int sf_i
   return (uint32_t)sl | ((uint32_t)ss << 6) | ((uint32_t)lo << 10) | ((uint32_t)width << 18) | ((uint32_t)(i0 >> 7) << 24);
 }
 
+// Where short window w sits in the grouping of an EIGHT_SHORT channel: [3:0] group, [7:4] first window of the group,
+// [11:8] windows in the group.  Branch-free from the group-start mask (bit j: window j starts a group).
+__device__ __forceinline__ uint32_t short_group_of(const IcsSide* __restrict__ s, int w) {
+  uint32_t starts = 1u, acc = 0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    acc += s->group_len[k];
+    if (k + 1 < s->num_groups) starts |= 1u << acc;
+  }
+  const uint32_t below = starts & ((2u << w) - 1u);
+  const int gstart = 31 - __clz((int)below);
+  const int g = __popc(below) - 1;
+  const int next = w + 1 + (__ffs((int)((starts | 0x100u) >> (w + 1))) - 1);
+  return (uint32_t)g | ((uint32_t)gstart << 4) | ((uint32_t)(next - gstart) << 8);
+}
+
 // Dequantises coefficients i0..i0+3 of one channel (ICStream.java:264-269): v = +-IQ_TABLE[|q|] * scaleFactors[idx].
-// `qpre` holds q[i0..i0+3] as fetched at the natural position, which is where K1 put them for long windows; for
-// EIGHT_SHORT the bitstream position is computed from the grouping and the four values are re-read.
-// cb_out / idx_out: the band's codebook and its (group, sfb) index; cb_out = 0 for bands at or above max_sfb.
-__device__ __forceinline__ void dequant4(const IcsSide* __restrict__ s, const int16_t* __restrict__ q, uint2 qpre,
+// `q` is the channel's quantised spectrum as K1 wrote it (bitstream order, see k1_parse.cuh) in the shared-memory stage:
+// long windows sit at their natural position, for EIGHT_SHORT the position follows from the grouping (`grp`,
+// short_group_of of the chunk's window).  cb_out / idx_out: the band's codebook and its (group, sfb) index; cb_out = 0
+// for bands at or above max_sfb.
+__device__ __forceinline__ void dequant4(const IcsSide* __restrict__ s, const int16_t* __restrict__ q, uint32_t grp,
                                          uint32_t pk, int i0, const TablesDev& T, float v[4], int& cb_out, int& idx_out) {
   v[0] = v[1] = v[2] = v[3] = 0.f;
   cb_out = 0;
   idx_out = 0;
   const int max_sfb = s->max_sfb;
-  int sfb, idx;
+  int sfb, idx, qpos = i0;
   if (s->window_sequence == 2) {
     sfb = (int)((pk >> 6) & 15u);
     if (sfb >= max_sfb) return;
-    // window -> group: first window and length of the group that holds this window
     const int w = (int)((pk >> 24) & 7u);
-    int g = 0, gstart = 0, glen = s->group_len[0];
-    for (int k = 0, acc = 0; k < 7; ++k) {
-      acc += s->group_len[k];
-      if (w >= acc && k + 1 < s->num_groups) { g = k + 1; gstart = acc; glen = s->group_len[k + 1]; }
-    }
+    const int g = (int)(grp & 15u), gstart = (int)((grp >> 4) & 15u), glen = (int)((grp >> 8) & 15u);
     idx = g * max_sfb + sfb;
-    const int cb = s->sfb_cb[idx];
-    cb_out = cb;
-    idx_out = idx;
-    if (cb == 0 || cb > 11) return;
     const int lo = (int)((pk >> 10) & 255u), width = (int)((pk >> 18) & 63u);
-    const int qpos = 128 * gstart + glen * lo + (w - gstart) * width + ((i0 & 127) - lo);
-    qpre = *reinterpret_cast<const uint2*>(q + qpos);
+    qpos = 128 * gstart + glen * lo + (w - gstart) * width + ((i0 & 127) - lo);
   } else {
     sfb = (int)(pk & 63u);
     if (sfb >= max_sfb) return;
     idx = sfb;
-    const int cb = s->sfb_cb[idx];
-    cb_out = cb;
-    idx_out = idx;
-    if (cb == 0 || cb > 11) return;
   }
+  const int cb = s->sfb_cb[idx];
+  cb_out = cb;
+  idx_out = idx;
+  if (cb == 0 || cb > 11) return;
+  const uint2 qv = *reinterpret_cast<const uint2*>(q + qpos);
   const float sf = __ldg(T.sf + s->sf_idx[idx]);
-  const int q0 = (int)(int16_t)(qpre.x & 0xFFFFu), q1 = (int)qpre.x >> 16;
-  const int q2 = (int)(int16_t)(qpre.y & 0xFFFFu), q3 = (int)qpre.y >> 16;
+  const int q0 = (int)(int16_t)(qv.x & 0xFFFFu), q1 = (int)qv.x >> 16;
+  const int q2 = (int)(int16_t)(qv.y & 0xFFFFu), q3 = (int)qv.y >> 16;
   const float m0 = __ldg(T.iq + abs(q0)), m1 = __ldg(T.iq + abs(q1));
   const float m2 = __ldg(T.iq + abs(q2)), m3 = __ldg(T.iq + abs(q3));
   // iqData = (v>0) ? IQ[v] : -IQ[-v]; iqData *= scaleFactors[idx]   (ICStream.java:266-267)
@@ -152,40 +182,305 @@ __device__ __forceinline__ void dequant4(const IcsSide* __restrict__ s, const in
   v[3] = (q3 > 0 ? m3 : -m3) * sf;
 }
 
+// PNS (ICStream.java:241-257) for coefficients i0..i0+3 of a band with codebook 13.  While it parses, JAAD draws
+// width values per window of the band from the generator, sums their squares in float in index order and scales the
+// window's values by (float)(scaleFactors[idx] / Math.sqrt(energy)).  The draws are regenerated here: `state` is the
+// generator at the start of this channel's parse, the band's draw offset is the number of values the channel's
+// earlier noise bands took.  Rare path, kept out of line.
+__device__ __noinline__ float4 pns_fill4(const IcsSide* __restrict__ s, uint32_t grp, uint32_t pk, int i0, int idx, uint32_t state,
+                                         const int16_t* __restrict__ swb, const float* __restrict__ sf_table) {
+  const bool sh = s->window_sequence == 2;
+  const int max_sfb = s->max_sfb;
+  // draws of the bands before idx, in the order ICStream.decodeSpectralData walks them
+  uint32_t before = 0;
+  for (int j = 0, g = 0, sfb = 0; j < idx; ++j) {
+    if (s->sfb_cb[j] == 13) before += (uint32_t)(s->group_len[g] * (swb[sfb + 1] - swb[sfb]));
+    if (++sfb == max_sfb) { sfb = 0; ++g; }
+  }
+  int width, k0;
+  if (sh) {
+    const int w = (int)((pk >> 24) & 7u), gstart = (int)((grp >> 4) & 15u);
+    width = (int)((pk >> 18) & 63u);
+    before += (uint32_t)((w - gstart) * width);
+    k0 = (i0 & 127) - (int)((pk >> 10) & 255u);
+  } else {
+    const int sfb = (int)(pk & 63u);
+    width = swb[sfb + 1] - swb[sfb];
+    k0 = i0 - swb[sfb];
+  }
+  uint32_t r = pns_jump(state, before);
+  float energy = 0.f;
+  float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+  for (int k = 0; k < width; ++k) {
+    r = 1664525u * r + 1013904223u;
+    const float f = (float)(int32_t)r;
+    energy += f * f;
+    const int d = k - k0;
+    x0 = d == 0 ? f : x0; x1 = d == 1 ? f : x1; x2 = d == 2 ? f : x2; x3 = d == 3 ? f : x3;
+  }
+  const float sf = -__ldg(sf_table + (s->sf_idx[idx] & 0x3FFF));   // scaleFactors[idx] of a noise band is -2^(e/4) (ICStream.java:206)
+  const float scale = (float)((double)sf / sqrt((double)energy));
+  return make_float4(x0 * scale, x1 * scale, x2 * scale, x3 * scale);
+}
+
+// ISO/IEC 14496-3 4.6.9.3 (tns_decode_frame, tns_decode_coef, tns_ar_filter) for filter `filt` of window `w` of one channel,
+// in place on the channel's spectrum in shared memory.  The filter parameters are read again from the frame (K1 checked
+// them: TNS.java:35-61).  Same operations in the same order as the test oracle's ISO restatement.  Rare path, out of line.
+__device__ __noinline__ void tns_iso_filter(float* __restrict__ spec, const IcsSide* __restrict__ s, const uint32_t* __restrict__ words,
+                                            const int16_t* __restrict__ swb, int swb_count, int max_tns, int w, int filt) {
+  const bool sh = s->window_sequence == 2;
+  if (w >= (sh ? 8 : 1)) return;
+  uint32_t pos = s->tns_bit_off;
+  auto get = [&](int n) -> uint32_t {
+    const uint32_t wi = pos >> 5;
+    const uint32_t a = __byte_perm(__ldg(words + wi), 0, 0x0123), b = __byte_perm(__ldg(words + wi + 1), 0, 0x0123);
+    const uint32_t v = __funnelshift_l(b, a, pos & 31u) >> (32 - n);
+    pos += n;
+    return v;
+  };
+  const int b0 = sh ? 1 : 2, b1 = sh ? 4 : 6, b2 = sh ? 3 : 5;
+  int top = 0, bottom = 0, order = 0, direction = 0, table = 0, coef_len = 0;
+  uint32_t coef_pos = 0;
+  bool found = false;
+  for (int ww = 0; ww <= w && !found; ++ww) {
+    const int nf = (int)get(b0);
+    if (!nf) continue;
+    const int coef_res = (int)get(1);
+    bottom = swb_count;
+    for (int f = 0; f < nf; ++f) {
+      const int length = (int)get(b1);
+      const int ord = (int)get(b2);
+      top = bottom;
+      bottom = max(top - length, 0);
+      int dir = 0, compress = 0;
+      if (ord) { dir = (int)get(1); compress = (int)get(1); }
+      if (ww == w && f == filt) {
+        found = true;
+        order = ord; direction = dir; table = 2 * compress + coef_res; coef_len = coef_res + 3 - compress; coef_pos = pos;
+        break;
+      }
+      pos += (uint32_t)(ord * (coef_res + 3 - compress));
+    }
+  }
+  if (!found || order == 0) return;
+  // tns_decode_coef: TNSTables holds -sin(..), 4.6.9.3 has tmp2 = sin(coef / iqfac)
+  const int tab_off = table == 0 ? 0 : table == 1 ? 8 : table == 2 ? 24 : 28;
+  float lpc[21], b[21];
+  lpc[0] = 1.0f;
+  pos = coef_pos;
+  for (int m = 1; m <= order; ++m) {
+    const float t = -c_tns_coef[tab_off + (int)get(coef_len)];
+    for (int i = 1; i < m; ++i) b[i] = lpc[i] + (t * lpc[m - i]);
+    for (int i = 1; i < m; ++i) lpc[i] = b[i];
+    lpc[m] = t;
+  }
+  const int start = swb[min(min(bottom, max_tns), (int)s->max_sfb)];
+  const int end = swb[min(min(top, max_tns), (int)s->max_sfb)];
+  const int size = end - start;
+  if (size <= 0) return;
+  int p = w * 128 + start, inc = 1;
+  if (direction) { inc = -1; p = w * 128 + end - 1; }
+  float state[20];
+#pragma unroll
+  for (int j = 0; j < 20; ++j) state[j] = 0.f;
+  for (int i = 0; i < size; ++i, p += inc) {
+    float y = spec[spec_addr(p)];
+    for (int j = 0; j < order; ++j) y = y - (state[j] * lpc[j + 1]);
+    for (int j = order - 1; j > 0; --j) state[j] = state[j - 1];
+    state[0] = y;
+    spec[spec_addr(p)] = y;
+  }
+}
+
 __device__ __forceinline__ void channel_barrier(int c) {
   // the 64 threads (two warps) of one channel
   asm volatile("bar.sync %0, 64;" ::"r"(c + 1) : "memory");
 }
 
+// ---- mbarrier + TMA bulk copy (global -> shared::cta), one transaction barrier per CTA --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the TMA unit (async proxy) sees the initialised barrier
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pre-pass: the sequential part of a run, 16 bytes out per frame.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k2_prepass_kernel(const RunDev* __restrict__ runs, uint32_t n_runs, const RunFrameDev* __restrict__ run_frames,
+                  FrameSide* __restrict__ fside, const IcsSide* __restrict__ iside, StreamState* __restrict__ sstate,
+                  const LayoutDev* __restrict__ layouts, K2FrameDev* __restrict__ out, uint32_t* __restrict__ pcm_bytes_out,
+                  int bytes_per_sample, int tns_iso) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  const RunDev run = runs[r];
+  const LayoutDev lay = layouts[run.layout];
+  const int nch = lay.n_channels;
+  StreamState st = sstate[run.stream_slot];
+  // element of each channel slot, 3 bits each
+  uint32_t el_of = 0;
+  for (int e = 0; e < lay.n_elements; ++e) {
+    const int f0 = lay.el_first_ch[e], n = lay.el_type[e] == EL_CPE ? 2 : 1;
+    for (int c = f0; c < f0 + n; ++c) el_of |= (uint32_t)e << (3 * c);
+  }
+  uint32_t shape_cur = 0;
+  for (int c = 0; c < nch; ++c) shape_cur |= (uint32_t)(st.window_shape[c] & 1u) << c;
+  uint32_t exp_tags = st.tags, exp_mask = 0;
+  for (int i = 0; i < 4; ++i) exp_mask |= ((st.tags_valid >> i) & 1u) ? (0xFu << (4 * i)) : 0u;
+  uint32_t pns = st.pns_state;
+  const uint32_t frame_bytes = (uint32_t)(1024 * (run.mono_dup ? 2 : nch) * bytes_per_sample);
+
+  for (uint32_t it = 0; it < run.count; ++it) {
+    const RunFrameDev rf = run_frames[run.first + it];
+    const uint4 fsw = *reinterpret_cast<const uint4*>(fside + rf.frame);   // status, tags | n_elements | n_started, sbr_bit_off[2]
+    const uint32_t draws = fside[rf.frame].pns_draws;
+    int frame_status = (int)fsw.x;
+    // Element objects are per (type, instance tag) in JAAD (StreamState::tags).  An element that shows another tag, or
+    // that the layout does not have, addresses objects this stream does not own: it leaves them alone, the frame is
+    // reported as JAADB_ST_LAYOUT -- and the stream's own elements of that frame still go through the filterbank when
+    // the frame was parsed to its end, as they do in JAAD (SyntacticElements.process runs after the whole parse).
+    // nibble i of `started` / `exp_mask` = element i has shown its tag in this frame / earlier
+    const uint32_t tags = fsw.y & 0xFFFFu, started = (1u << (4 * min(fsw.y >> 24, 4u))) - 1u;
+    const uint32_t diff = (tags ^ exp_tags) & exp_mask & started;
+    const uint32_t fresh = started & ~exp_mask;
+    exp_tags |= tags & fresh;
+    exp_mask |= fresh;
+    const int n_good = (int)((fsw.y >> 16) & 0xFFu);
+    if (diff != 0 && frame_status == 0) {
+      frame_status = JAADB_ST_LAYOUT;
+      fside[rf.frame].status = JAADB_ST_LAYOUT;
+    }
+    const bool emit = frame_status == 0;                                        // the frame yields PCM
+    const bool parsed = emit || frame_status == JAADB_ST_LAYOUT;                // JAAD reached SyntacticElements.process
+    uint32_t flags = (emit ? kK2Emit : 0u) | (parsed ? kK2Parsed : 0u);
+    uint32_t shape_prev = shape_cur;
+    for (int c = 0; c < nch; ++c) {
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(iside + rf.ics_base + c);
+      const uint32_t h0 = sw[0];   // present | info_decoded << 8 | window_sequence << 16 | window_shape << 24
+      const int my_el = (int)((el_of >> (3 * c)) & 7u);
+      const bool shape_ok = my_el >= 4 || ((diff >> (4 * my_el)) & 15u) == 0;   // the element belongs to the stream
+      const bool el_live = shape_ok && my_el < n_good;                         // ... and was parsed completely
+      // window-shape bookkeeping of ICSInfo.decode / setCommonData (ICSInfo.java:90-91,196-197): in failing frames too
+      if (((h0 >> 8) & 0xFFu) && shape_ok) shape_cur = (shape_cur & ~(1u << c)) | (((h0 >> 24) & 1u) << c);
+      // (SBR streams: the SBR stages only run for frames that yield PCM, so the core coder's state waits for them too)
+      if (parsed && el_live && (emit || !run.sbr)) {
+        flags |= 1u << c;
+        const uint32_t tw = sw[98];   // tns_present | has_pns << 8 | pns_base << 16
+        if (tns_iso && (tw & 0xFFu)) flags |= kK2Tns;
+        if (tw & 0xFF00u) flags |= kK2Pns;
+      }
+    }
+    flags |= (shape_prev & 0xFFu) << 8 | (shape_cur & 0xFFu) << 16;
+    *reinterpret_cast<uint4*>(out + run.first + it) = make_uint4(rf.frame, rf.ics_base, flags, pns);
+    pns = pns_jump(pns, draws);
+    if (!run.sbr) pcm_bytes_out[rf.frame] = emit ? frame_bytes : 0u;
+  }
+  for (int c = 0; c < nch; ++c) st.window_shape[c] = (uint8_t)((shape_cur >> c) & 1u);
+  uint32_t v = 0;
+  for (int i = 0; i < 4; ++i) v |= ((exp_mask >> (4 * i)) & 1u) << i;
+  st.tags = (uint16_t)exp_tags;
+  st.tags_valid = (uint8_t)v;
+  st.pns_state = pns;
+  sstate[run.stream_slot] = st;
+}
+
+// Final overlap of segmented runs: the last segment of a run leaves it in a staging buffer (other segments of the run may
+// still be reading the persistent one), this kernel moves it into the stream's state.
+__global__ void k2_commit_kernel(const RunDev* __restrict__ runs, uint32_t n_runs, int nch, const float* __restrict__ stage,
+                                 float* __restrict__ overlap_all) {
+  const uint32_t r = blockIdx.x;
+  if (r >= n_runs) return;
+  const float4* src = reinterpret_cast<const float4*>(stage + (size_t)r * kMaxChannels * 1024);   // (stage: this group's first run)
+  float4* dst = reinterpret_cast<float4*>(overlap_all + (size_t)runs[r].stream_slot * kMaxChannels * 1024);
+  for (int i = threadIdx.x; i < nch * 256; i += blockDim.x) dst[i] = src[i];
+}
+
+struct K2Args {
+  const K2SegDev* segs;
+  const RunDev* runs;
+  const K2FrameDev* k2frames;
+  const FrameDev* frames;       // JAADB_TNS_ISO only: where a frame's bytes are
+  const uint8_t* blob;          // "
+  const IcsSide* iside;
+  const int16_t* qall;
+  float* overlap_all;
+  float* overlap_stage;         // segmented runs: [run][kMaxChannels][1024], moved into overlap_all by k2_commit_kernel; else null
+  uint8_t* pcm;
+  const uint64_t* pcm_off;
+  float* spec_tap;
+  float* core;
+  const LayoutDev* layouts;
+  int nch;
+};
+
 template <int PCM_FORMAT, int MAX_THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
-k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restrict__ run_frames,
-                     FrameSide* __restrict__ fside, const IcsSide* __restrict__ iside,
-                     const int16_t* __restrict__ qall, float* __restrict__ overlap_all, StreamState* __restrict__ sstate,
-                     uint8_t* __restrict__ pcm, const uint64_t* __restrict__ pcm_off,
-                     uint32_t* __restrict__ pcm_bytes_out, float* __restrict__ spec_tap, float* __restrict__ core, TablesDev T,
-                     const LayoutDev* __restrict__ layouts, int nch) {
+k2_filterbank_kernel(const K2Args A, const TablesDev T) {
+  // the 128-thread instantiation serves one- and two-channel streams: always two output channels (mono is duplicated,
+  // SyntacticElements.java:244-245), PCM packed per channel and interleaved on the way out
+  constexpr bool kPlanarPcm = MAX_THREADS == 128;
   extern __shared__ __align__(16) float smem[];
-  // carve: twiddles; per channel [spec kSpecStride][overlap 1024][xre kXchgStride][xim kXchgStride]; sides; pcm staging
-  const int per_ch = kSpecStride + 1024 + 2 * kXchgStride;
+  const int nch = A.nch;
+  // carve: twiddles; per channel [spec][overlap][xre][xim]; stage q[nch][1024], side[nch]; mbarrier; [pcm staging]
   float* s_fft_tw = smem;                         // fft512 re/im (inverse) [256][2] + fft64 [32][2]
   float* s_ch = s_fft_tw + 2 * 256 + 2 * 32;
-  IcsSide* s_side = reinterpret_cast<IcsSide*>(s_ch + nch * per_ch);
-  int16_t* s_pcm = reinterpret_cast<int16_t*>(s_side + nch);  // [1024][out_ch] (s16 formats)
+  int16_t* s_q = reinterpret_cast<int16_t*>(s_ch + nch * kK2ChFloats);
+  IcsSide* s_side = reinterpret_cast<IcsSide*>(s_q + nch * 1024);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_side + nch);
+  int16_t* s_pcm = reinterpret_cast<int16_t*>(s_bar + 2);  // [1024][out_ch] (s16 formats, more than two channels)
 
-  const RunDev run = runs[blockIdx.x];
-  const LayoutDev lay = layouts[run.layout];
+  const K2SegDev seg = A.segs[blockIdx.x];
+  const RunDev run = A.runs[seg.run];
+  const LayoutDev lay = A.layouts[run.layout];
   const int tid = threadIdx.x;
   const int c = tid / kThreadsPerChannel;         // channel slot of this thread
   const int t = tid - c * kThreadsPerChannel;
   const int nthreads = blockDim.x;
   const int out_ch = run.mono_dup ? 2 : nch;
   const int sf_index = run.sf_index;
+  const K2FrameDev* __restrict__ kf = A.k2frames + run.first;
 
-  float* my_spec = s_ch + c * per_ch;
+  float* my_spec = s_ch + c * kK2ChFloats;
   float* my_ovl = my_spec + kSpecStride;
   float* my_xre = my_ovl + 1024;
   float* my_xim = my_xre + kXchgStride;
+
+  // Where to start.  The overlap a channel holds after a frame depends on that frame alone, so a segment in the middle
+  // of a run first re-runs (without output) the frames before it, back to where every channel has been through the
+  // filterbank once; channels that never were keep the persistent overlap.
+  uint32_t it0 = seg.first;
+  if (it0 > 0) {
+    uint32_t have = 0;
+    const uint32_t all = (1u << nch) - 1u;
+    while (it0 > 0 && have != all) { --it0; have |= kf[it0].flags & 0xFFu; }
+  }
+  const uint32_t it_end = seg.first + seg.count;
+  const uint32_t stage_bytes = (uint32_t)nch * 2048u, side_bytes = (uint32_t)nch * (uint32_t)sizeof(IcsSide);
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    const K2FrameDev f0 = kf[it0];
+    mbar_expect_tx(s_bar, stage_bytes + side_bytes);
+    tma_bulk_g2s(s_q, A.qall + (size_t)f0.ics_base * 1024, stage_bytes, s_bar);
+    tma_bulk_g2s(s_side, A.iside + f0.ics_base, side_bytes, s_bar);
+  }
 
   // twiddles used by the radix-2 stages: roots[k*m] with k*m < length/2
   for (int i = tid; i < 256; i += nthreads) {
@@ -203,18 +498,17 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
   const float2* mdct_long2 = reinterpret_cast<const float2*>(T.mdct_long);
   const float2* mdct_short2 = reinterpret_cast<const float2*>(T.mdct_short);
 
-  // persistent state in: overlap + current window shapes
-  float* g_ovl = overlap_all + ((size_t)run.stream_slot * kMaxChannels + c) * 1024;
+  // persistent state in: overlap
+  float* g_ovl = A.overlap_all + ((size_t)run.stream_slot * kMaxChannels + c) * 1024;
   for (int i = t; i < 256; i += kThreadsPerChannel)
     reinterpret_cast<float4*>(my_ovl)[i] = reinterpret_cast<const float4*>(g_ovl)[i];
-  int shape_cur = sstate[run.stream_slot].window_shape[c];
 
   // element of this thread's channel
-  int el_first = c, el_nch = 1, my_el = 0;
+  int el_first = c, el_nch = 1;
   for (int e = 0; e < lay.n_elements; ++e) {
     int f0 = lay.el_first_ch[e];
     int n = lay.el_type[e] == EL_CPE ? 2 : 1;
-    if (c >= f0 && c < f0 + n) { el_first = f0; el_nch = n; my_el = e; }
+    if (c >= f0 && c < f0 + n) { el_first = f0; el_nch = n; }
   }
   // dequantisation work split: a CPE thread owns coefficients 8*et .. 8*et+7 of L and of R (M/S and IS are
   // element-wise across the pair); an SCE/LFE thread owns 16*et .. 16*et+15 of its channel.
@@ -225,79 +519,61 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
   const uint32_t pkA0 = subchunk_consts(T, sf_index, iA), pkA1 = subchunk_consts(T, sf_index, iA + 4);
   const uint32_t pkB0 = subchunk_consts(T, sf_index, iB), pkB1 = subchunk_consts(T, sf_index, iB + 4);
 
-  // ---- software pipeline: descriptor, status, side information and q of the next frame live in registers
-  RunFrameDev cur = run_frames[run.first];
-  // status and the element instance tags of the frame: {status, tags | n_elements << 16 | n_started << 24}
-  uint2 fsw = *reinterpret_cast<const uint2*>(fside + cur.frame);
-  uint32_t exp_tags = sstate[run.stream_slot].tags, exp_mask = 0;
-  {
-    const uint32_t v = sstate[run.stream_slot].tags_valid;
-    for (int i = 0; i < 4; ++i) exp_mask |= ((v >> i) & 1u) ? (0xFu << (4 * i)) : 0u;
-  }
-  uint4 side_pf = make_uint4(0, 0, 0, 0);
-  const int side_vecs = nch * (int)(sizeof(IcsSide) / 16);
-  if (tid < side_vecs) side_pf = reinterpret_cast<const uint4*>(iside + cur.ics_base)[tid];
-  uint4 qA = *reinterpret_cast<const uint4*>(qall + ((size_t)cur.ics_base + chA) * 1024 + iA);
-  uint4 qB = *reinterpret_cast<const uint4*>(qall + ((size_t)cur.ics_base + chB) * 1024 + iB);
-  uint64_t poff_pf = pcm_off[cur.frame];
-  __syncthreads();
+  K2FrameDev cur = kf[it0];
+  uint64_t poff_pf = A.pcm_off[cur.frame];
+  __syncthreads();   // twiddles, overlap and the barrier's initialisation are visible
 
-  for (uint32_t it = 0; it < run.count; ++it) {
+  for (uint32_t it = it0; it < it_end; ++it) {
     const uint32_t f = cur.frame;
     const uint32_t ics_base = cur.ics_base;
+    const uint32_t flags = cur.flags;
+    const uint32_t pns_state = cur.pns_state;
     const uint64_t poff = poff_pf;
-    const bool have_next = it + 1 < run.count;
-    RunFrameDev nxt = cur;
-    if (have_next) nxt = run_frames[run.first + it + 1];
-    // side info -> shared
-    if (tid < side_vecs) reinterpret_cast<uint4*>(s_side)[tid] = side_pf;
-    __syncthreads();
-    const IcsSide* sd = s_side + c;
-    // Element objects are per (type, instance tag) in JAAD (StreamState::tags).  An element that shows another tag, or
-    // that the layout does not have, addresses objects this stream does not own: it leaves them alone, the frame is
-    // reported as JAADB_ST_LAYOUT -- and the stream's own elements of that frame still go through the filterbank when
-    // the frame was parsed to its end, as they do in JAAD (SyntacticElements.process runs after the whole parse).
-    int frame_status = (int)fsw.x;
-    bool el_live;      // this thread's element belongs to the stream and was parsed completely
-    bool shape_ok;     // ... belongs to the stream (window-shape bookkeeping happens in failing frames too)
-    {
-      // nibble i of `started` / `exp_mask` = element i has shown its tag in this frame / earlier
-      const uint32_t tags = fsw.y & 0xFFFFu, started = (1u << (4 * min(fsw.y >> 24, 4u))) - 1u;
-      const uint32_t diff = (tags ^ exp_tags) & exp_mask & started;
-      const uint32_t fresh = started & ~exp_mask;
-      exp_tags |= tags & fresh;
-      exp_mask |= fresh;
-      const int n_good = (int)((fsw.y >> 16) & 0xFFu);
-      shape_ok = my_el >= 4 || ((diff >> (4 * my_el)) & 15u) == 0;
-      el_live = shape_ok && my_el < n_good;
-      if (diff != 0 && frame_status == 0) {
-        frame_status = JAADB_ST_LAYOUT;
-        if (tid == 0) fside[f].status = JAADB_ST_LAYOUT;
-      }
+    const bool have_next = it + 1 < it_end;
+    const bool warm = it < seg.first;                         // re-run for the overlap only
+    const bool emit = (flags & kK2Emit) != 0 && !warm;        // the frame yields PCM
+    const bool parsed = (flags & kK2Parsed) != 0;             // JAAD reached SyntacticElements.process
+    const bool run_ch = ((flags >> c) & 1u) != 0;             // this thread's channel goes through the filterbank
+    const int shape_prev = (int)((flags >> (8 + c)) & 1u), shape_cur = (int)((flags >> (16 + c)) & 1u);
+    if (have_next) {
+      cur = kf[it + 1];
+      poff_pf = A.pcm_off[cur.frame];
     }
-    const bool emit = frame_status == 0;                                        // the frame yields PCM
-    const bool parsed = emit || frame_status == JAADB_ST_LAYOUT;                // JAAD reached SyntacticElements.process
-    // (SBR streams: the SBR stages only run for frames that yield PCM, so the core coder's state waits for them too)
-    const bool run_ch = parsed && el_live && (emit || !run.sbr);
-    // window-shape bookkeeping of ICSInfo.decode / setCommonData (ICSInfo.java:90-91,196-197)
-    int shape_prev = shape_cur;
-    if (sd->info_decoded && shape_ok) { shape_prev = shape_cur; shape_cur = sd->window_shape; }
-    const int ws = sd->window_sequence;
+    // the frame's quantised coefficients and side information have landed in the stage
+    mbar_wait(s_bar, (it - it0) & 1u);
+    const int ws = s_side[c].window_sequence;
 
-    if (run_ch) {
+    if (run_ch) {   // (the channels of an element run together)
       // ---- phase 1: dequantise + M/S + IS into the element's spectra
-      const int16_t* qL = qall + ((size_t)ics_base + chA) * 1024;
-      const int16_t* qR = qall + ((size_t)ics_base + chB) * 1024;
+      const int16_t* qL = s_q + chA * 1024;
+      const int16_t* qR = s_q + chB * 1024;
       const IcsSide* sL = s_side + chA;
       const IcsSide* sR = s_side + chB;
-      float* specA = s_ch + chA * per_ch;
-      float* specB = s_ch + chB * per_ch;
+      float* specA = s_ch + chA * kK2ChFloats;
+      float* specB = s_ch + chB * kK2ChFloats;
       float a[8], b[8];
       int cbA0, cbA1, cbB0, cbB1, idxA0, idxA1, idxB0, idxB1;
-      dequant4(sL, qL, make_uint2(qA.x, qA.y), pkA0, iA, T, a, cbA0, idxA0);
-      dequant4(sL, qL, make_uint2(qA.z, qA.w), pkA1, iA + 4, T, a + 4, cbA1, idxA1);
-      dequant4(sR, qR, make_uint2(qB.x, qB.y), pkB0, iB, T, b, cbB0, idxB0);
-      dequant4(sR, qR, make_uint2(qB.z, qB.w), pkB1, iB + 4, T, b + 4, cbB1, idxB1);
+      // (the eight coefficients of a channel lie in one short window)
+      const uint32_t grpA = sL->window_sequence == 2 ? short_group_of(sL, (int)((pkA0 >> 24) & 7u)) : 0u;
+      const uint32_t grpB = sR->window_sequence == 2 ? short_group_of(sR, (int)((pkB0 >> 24) & 7u)) : 0u;
+      dequant4(sL, qL, grpA, pkA0, iA, T, a, cbA0, idxA0);
+      dequant4(sL, qL, grpA, pkA1, iA + 4, T, a + 4, cbA1, idxA1);
+      dequant4(sR, qR, grpB, pkB0, iB, T, b, cbB0, idxB0);
+      dequant4(sR, qR, grpB, pkB1, iB + 4, T, b + 4, cbB1, idxB1);
+      if (flags & kK2Pns) {
+        // generator state when this channel's parse began: the frame's + what the earlier channels took
+#define K2_PNS(S_, GRP, PK, I0, IDX, V, O)                                                                                        \
+  do {                                                                                                                           \
+    const int16_t* swb_ = (S_)->window_sequence == 2 ? (T.swb_short + sf_index * 17) : (T.swb_long + sf_index * 53);              \
+    const float4 n_ = pns_fill4(S_, GRP, PK, I0, IDX, pns_jump(pns_state, (S_)->pns_base), swb_, T.sf);                           \
+    V[O] = n_.x; V[O + 1] = n_.y; V[O + 2] = n_.z; V[O + 3] = n_.w;                                                               \
+  } while (0)
+        if (cbA0 == 13) K2_PNS(sL, grpA, pkA0, iA, idxA0, a, 0);
+        if (cbA1 == 13) K2_PNS(sL, grpA, pkA1, iA + 4, idxA1, a, 4);
+        if (cbB0 == 13) K2_PNS(sR, grpB, pkB0, iB, idxB0, b, 0);
+        if (cbB1 == 13) K2_PNS(sR, grpB, pkB1, iB + 4, idxB1, b, 4);
+#undef K2_PNS
+      }
       if (el_nch == 2) {
         const bool ms_on = sL->common_window && sL->ms_mask != 0;   // CPE.java:159-160
         const bool ms_present = sL->ms_mask != 0;                   // CPE.isMSMaskPresent
@@ -333,26 +609,43 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
         specA[spec_addr(iA + j)] = a[j];
         specB[spec_addr(iB + j)] = b[j];
       }
-      if (spec_tap) {
-        float* tA = spec_tap + ((size_t)ics_base + chA) * 1024 + iA;
-        float* tB = spec_tap + ((size_t)ics_base + chB) * 1024 + iB;
+      if (A.spec_tap && !warm && !(flags & kK2Tns)) {
+        float* tA = A.spec_tap + ((size_t)ics_base + chA) * 1024 + iA;
+        float* tB = A.spec_tap + ((size_t)ics_base + chB) * 1024 + iB;
 #pragma unroll
         for (int j = 0; j < 8; ++j) { tA[j] = a[j]; tB[j] = b[j]; }
       }
     }
-    // ---- prefetch the next frame while this one is transformed
-    if (have_next) {
-      fsw = *reinterpret_cast<const uint2*>(fside + nxt.frame);
-      if (tid < side_vecs) side_pf = reinterpret_cast<const uint4*>(iside + nxt.ics_base)[tid];
-      qA = *reinterpret_cast<const uint4*>(qall + ((size_t)nxt.ics_base + chA) * 1024 + iA);
-      qB = *reinterpret_cast<const uint4*>(qall + ((size_t)nxt.ics_base + chB) * 1024 + iB);
-      poff_pf = pcm_off[nxt.frame];
+    if (flags & kK2Tns) {
+      // ISO TNS between the stereo tools and the filterbank: one thread per (window, filter), in place on the spectrum
+      __syncthreads();
+      if (run_ch && s_side[c].tns_present && t < 32) {
+        const uint64_t addr = reinterpret_cast<uint64_t>(A.blob) + A.frames[f].blob_off;
+        const bool sh = ws == 2;
+        tns_iso_filter(my_spec, s_side + c, reinterpret_cast<const uint32_t*>(addr - (addr & 3u)),
+                       sh ? (T.swb_short + sf_index * 17) : (T.swb_long + sf_index * 53),
+                       sh ? T.swb_short_count[sf_index] : T.swb_long_count[sf_index], c_tns_max_sfb[sf_index * 2 + (sh ? 1 : 0)], t >> 2, t & 3);
+      }
+      if (A.spec_tap && !warm) {
+        __syncthreads();
+        if (run_ch)
+          for (int i = t; i < 1024; i += kThreadsPerChannel) A.spec_tap[((size_t)ics_base + c) * 1024 + i] = my_spec[spec_addr(i)];
+      }
     }
-    cur = nxt;
-    __syncthreads();
+    __syncthreads();   // spectra complete; every thread is done with the stage
+    // ---- the next frame comes in while this one is transformed
+    if (tid == 0 && have_next) {
+      mbar_expect_tx(s_bar, stage_bytes + side_bytes);
+      tma_bulk_g2s(s_q, A.qall + (size_t)cur.ics_base * 1024, stage_bytes, s_bar);
+      tma_bulk_g2s(s_side, A.iside + cur.ics_base, side_bytes, s_bar);
+    }
     if (!parsed) {
-      if (tid == 0 && !run.sbr) pcm_bytes_out[f] = 0;
-      continue;  // the frame produced no PCM; overlap untouched (Decoder.java:96-98)
+      // the frame produced no PCM; overlap untouched (Decoder.java:96-98).  Its slot of the output is zero-filled.
+      if (!warm && !run.sbr) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(A.pcm + poff);
+        for (int i = tid; i < 512 * out_ch * (PCM_FORMAT == 2 ? 2 : 1); i += nthreads) d[i] = 0u;
+      }
+      continue;
     }
 
     // ---- phase 2: IMDCT of this channel (thread t owns points 8t..8t+7 of the bit-reversed input)
@@ -429,29 +722,28 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
         bfly(a[j], a[j + 4], tw[2 * k * (mB >> 2)], tw[2 * k * (mB >> 2) + 1]);
       }
     }
-    // The spectrum was consumed before the channel barrier above, so its storage now carries exchange 2
-    // (planes re | im, 528 floats each); the post-twiddled buffer then goes where exchange 1 was.
+    // The spectrum was consumed before the channel barrier above, so its storage now carries exchange 2 (planes re | im,
+    // 576 floats each: 8 pad floats per 64 keep both the strided writes and the contiguous reads conflict-free); the
+    // post-twiddled buffer then goes where exchange 1 was.
     float* x2re = my_spec;
-    float* x2im = my_spec + 528;
-    float* bre = my_xre;               // post-twiddled buffer as planes re[512] | im[512]
+    float* x2im = my_spec + 576;
+    float* bre = my_xre;               // post-twiddled buffer as planes re[512] | im[512] (short: 8 windows of 64 at stride 72)
     float* bim = my_xim;
     if (!is_short) {
       // exchange 2: write n = 64*blk + col + 8*j, read n = t + 64*j
       const int blk = t >> 3, col = t & 7;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int n = 64 * blk + col + 8 * j;
-        x2re[n + (n >> 5)] = a[j].re;
-        x2im[n + (n >> 5)] = a[j].im;
+        x2re[72 * blk + col + 8 * j] = a[j].re;
+        x2im[72 * blk + col + 8 * j] = a[j].im;
       }
     }
     channel_barrier(c);   // also: every thread of the channel is done reading exchange 1
     if (!is_short) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int n = t + 64 * j;
-        a[j].re = x2re[n + (n >> 5)];
-        a[j].im = x2im[n + (n >> 5)];
+        a[j].re = x2re[t + 72 * j];
+        a[j].im = x2im[t + 72 * j];
       }
       // stage C: i = 64, 128, 256 on local index j
 #pragma unroll
@@ -485,8 +777,8 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
         const int nl = col + 8 * j;         // index inside the 64-point FFT of window blk
         const float2 cs = __ldg(mdct_short2 + nl);
         const float t0 = a[j].re, t1 = a[j].im;
-        bim[64 * blk + nl] = (t1 * cs.x) + (t0 * cs.y);
-        bre[64 * blk + nl] = (t0 * cs.x) - (t1 * cs.y);
+        bim[72 * blk + nl] = (t1 * cs.x) + (t0 * cs.y);
+        bre[72 * blk + nl] = (t0 * cs.x) - (t1 * cs.y);
       }
     }
     channel_barrier(c);
@@ -499,7 +791,8 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
       const float* __restrict__ LW = T.win_long[shape_cur];
       const float* __restrict__ SWp = T.win_short[shape_prev];
       const float* __restrict__ SW = T.win_short[shape_cur];
-      uint8_t* dst = pcm + poff;
+      uint8_t* dst = A.pcm + poff;
+      uint32_t* my_pk = reinterpret_cast<uint32_t*>(my_spec);   // kPlanarPcm: sample pairs (i, i+1) of this channel, word i/2
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int i = 2 * t + 128 * j;
@@ -540,7 +833,7 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
             n0 = x20 * w.y; n1 = x21 * w.x;
           }
         } else {
-          // EIGHT_SHORT: window w occupies b[256w .. 256w+255]; its samples come from FFT block w
+          // EIGHT_SHORT: window w occupies b[256w .. 256w+255]; its samples come from FFT block w (planes at stride 72)
           float oo[2], nn[2];
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
@@ -554,8 +847,8 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
                 o = ovp + (mdct_out(bre, bim, 64, 32, r) * __ldg(SWp + r));
               } else {
                 // second half of window s-1 + first half of window s (s = 1..4; s==4 only for r < 64)
-                const float a2 = mdct_out(bre + 64 * (s - 1), bim + 64 * (s - 1), 64, 32, 128 + r) * __ldg(SW + 127 - r);
-                const float b2 = mdct_out(bre + 64 * s, bim + 64 * s, 64, 32, r) * __ldg(SW + r);
+                const float a2 = mdct_out(bre + 72 * (s - 1), bim + 72 * (s - 1), 64, 32, 128 + r) * __ldg(SW + 127 - r);
+                const float b2 = mdct_out(bre + 72 * s, bim + 72 * s, 64, 32, r) * __ldg(SW + r);
                 o = (ovp + a2) + b2;
               }
             }
@@ -563,17 +856,17 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
             else if (ii < 64) {
               // overlap[i], i in [0,64): window 3 second half (r = 64+i) + window 4 first half
               const int r = 64 + ii;
-              nv = (mdct_out(bre + 64 * 3, bim + 64 * 3, 64, 32, 128 + r) * __ldg(SW + 127 - r)) +
-                   (mdct_out(bre + 64 * 4, bim + 64 * 4, 64, 32, r) * __ldg(SW + r));
+              nv = (mdct_out(bre + 72 * 3, bim + 72 * 3, 64, 32, 128 + r) * __ldg(SW + 127 - r)) +
+                   (mdct_out(bre + 72 * 4, bim + 72 * 4, 64, 32, r) * __ldg(SW + r));
             } else if (ii < 448) {
               // i = 64 + 128*u + r: window 4+u second half + window 5+u first half (u = 0..2)
               const int u = (ii - 64) >> 7, r = (ii - 64) & 127;
-              nv = (mdct_out(bre + 64 * (4 + u), bim + 64 * (4 + u), 64, 32, 128 + r) * __ldg(SW + 127 - r)) +
-                   (mdct_out(bre + 64 * (5 + u), bim + 64 * (5 + u), 64, 32, r) * __ldg(SW + r));
+              nv = (mdct_out(bre + 72 * (4 + u), bim + 72 * (4 + u), 64, 32, 128 + r) * __ldg(SW + 127 - r)) +
+                   (mdct_out(bre + 72 * (5 + u), bim + 72 * (5 + u), 64, 32, r) * __ldg(SW + r));
             } else {
               // i in [448,576): window 7 second half only
               const int r = ii - 448;
-              nv = mdct_out(bre + 64 * 7, bim + 64 * 7, 64, 32, 128 + r) * __ldg(SW + 127 - r);
+              nv = mdct_out(bre + 72 * 7, bim + 72 * 7, 64, 32, 128 + r) * __ldg(SW + 127 - r);
             }
             oo[p] = o;
             nn[p] = nv;
@@ -582,52 +875,66 @@ k2_filterbank_kernel(const RunDev* __restrict__ runs, const RunFrameDev* __restr
         }
         if (run_ch) *reinterpret_cast<float2*>(my_ovl + i) = make_float2(n0, n1);
         if (!emit) {
-          // a frame JAAD decodes against element objects this stream does not own: state only, no PCM
+          // a frame JAAD decodes against element objects this stream does not own, or a re-run: state only, no PCM
         } else if (run.sbr) {
           // core-coder output of an SBR stream: K4 continues from here
-          *reinterpret_cast<float2*>(core + ((size_t)ics_base + c) * 1024 + i) = make_float2(o0, o1);
+          *reinterpret_cast<float2*>(A.core + ((size_t)ics_base + c) * 1024 + i) = make_float2(o0, o1);
         } else if (PCM_FORMAT == 2) {
           float* d = reinterpret_cast<float*>(dst);
           *reinterpret_cast<float2*>(d + (size_t)c * 1024 + i) = make_float2(o0, o1);
           if (run.mono_dup) *reinterpret_cast<float2*>(d + 1024 + i) = make_float2(o0, o1);
         } else {
-          uint32_t u0 = (uint32_t)pcm_round(o0) & 0xFFFFu, u1 = (uint32_t)pcm_round(o1) & 0xFFFFu;
-          if (PCM_FORMAT == 1) { u0 = __byte_perm(u0, 0, 0x4401); u1 = __byte_perm(u1, 0, 0x4401); }
-          if (run.mono_dup) {
-            *reinterpret_cast<uint2*>(s_pcm + 2 * i) = make_uint2(u0 | (u0 << 16), u1 | (u1 << 16));
+          uint32_t pr = pcm_round16(o0) | (pcm_round16(o1) << 16);
+          if (PCM_FORMAT == 1) pr = __byte_perm(pr, 0, 0x2301);
+          if (kPlanarPcm) {
+            my_pk[t + 64 * j] = pr;   // (exchange 2 of this channel was consumed before the last channel barrier)
           } else {
-            s_pcm[i * out_ch + c] = (int16_t)u0;
-            s_pcm[(i + 1) * out_ch + c] = (int16_t)u1;
+            s_pcm[i * out_ch + c] = (int16_t)(pr & 0xFFFFu);
+            s_pcm[(i + 1) * out_ch + c] = (int16_t)(pr >> 16);
           }
         }
       }
       __syncthreads();
-      if (PCM_FORMAT != 2 && !run.sbr && emit) {
+      if (PCM_FORMAT != 2 && !run.sbr && (flags & kK2Emit) && !warm) {
         // coalesced copy-out of the interleaved frame (pcm offsets are 4-byte aligned; 16 B when the caller packs)
-        const int nwords = 1024 * out_ch / 2;   // 32-bit words
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(s_pcm);
         uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-          for (int i = tid; i < nwords / 4; i += nthreads)
-            reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(src)[i];
+        if (kPlanarPcm) {
+          // samples i..i+3 of both channels = words i/2, i/2+1 of the two planes (one plane twice when mono is duplicated)
+          const uint2* pl = reinterpret_cast<const uint2*>(s_ch);
+          const uint2* prr = reinterpret_cast<const uint2*>(s_ch + (nch == 2 ? kK2ChFloats : 0));
+          const bool al = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+          for (int i = tid; i < 256; i += nthreads) {
+            const uint2 l = pl[i], r = prr[i];
+            const uint4 o = make_uint4(__byte_perm(l.x, r.x, 0x5410), __byte_perm(l.x, r.x, 0x7632), __byte_perm(l.y, r.y, 0x5410),
+                                       __byte_perm(l.y, r.y, 0x7632));
+            if (al) reinterpret_cast<uint4*>(d)[i] = o;
+            else { d[4 * i] = o.x; d[4 * i + 1] = o.y; d[4 * i + 2] = o.z; d[4 * i + 3] = o.w; }
+          }
+          __syncthreads();   // the planes live where the next frame's spectrum goes
         } else {
-          for (int i = tid; i < nwords; i += nthreads) d[i] = src[i];
+          const int nwords = 1024 * out_ch / 2;   // 32-bit words
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(s_pcm);
+          if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+            for (int i = tid; i < nwords / 4; i += nthreads)
+              reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(src)[i];
+          } else {
+            for (int i = tid; i < nwords; i += nthreads) d[i] = src[i];
+          }
         }
+      } else if (!(flags & kK2Emit) && !warm && !run.sbr) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+        for (int i = tid; i < 512 * out_ch * (PCM_FORMAT == 2 ? 2 : 1); i += nthreads) d[i] = 0u;   // no PCM: the slot is zero-filled
       }
-      if (tid == 0 && !run.sbr) pcm_bytes_out[f] = emit ? (uint32_t)(1024 * out_ch * (PCM_FORMAT == 2 ? 4 : 2)) : 0u;
     }
   }
 
-  // persistent state out (the last frame's phase 3 wrote my_ovl; the loop's trailing barrier ordered it)
+  // persistent state out (the last frame's phase 3 wrote my_ovl; the loop's trailing barrier ordered it).  Only the
+  // run's last segment holds the final overlap.
   __syncthreads();
-  for (int i = t; i < 256; i += kThreadsPerChannel)
-    reinterpret_cast<float4*>(g_ovl)[i] = reinterpret_cast<const float4*>(my_ovl)[i];
-  if (t == 0) sstate[run.stream_slot].window_shape[c] = (uint8_t)shape_cur;
-  if (tid == 0) {
-    uint32_t v = 0;
-    for (int i = 0; i < 4; ++i) v |= ((exp_mask >> (4 * i)) & 1u) << i;
-    sstate[run.stream_slot].tags = (uint16_t)exp_tags;
-    sstate[run.stream_slot].tags_valid = (uint8_t)v;
+  if (it_end == run.count) {
+    float* o = A.overlap_stage ? A.overlap_stage + ((size_t)seg.run * kMaxChannels + c) * 1024 : g_ovl;
+    for (int i = t; i < 256; i += kThreadsPerChannel)
+      reinterpret_cast<float4*>(o)[i] = reinterpret_cast<const float4*>(my_ovl)[i];
   }
 }
 

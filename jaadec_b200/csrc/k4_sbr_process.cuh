@@ -1202,7 +1202,7 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
       d[(size_t)out_ch * kOutLen + i] = v;
       if (f.dup) d[(size_t)(out_ch + 1) * kOutLen + i] = v;
     } else {
-      uint32_t u = (uint32_t)pcm_round(v) & 0xFFFFu;
+      uint32_t u = pcm_round16(v);
       if (PCM_FORMAT == 1) u = __byte_perm(u, 0, 0x4401);
       uint16_t* d = reinterpret_cast<uint16_t*>(f.dst);
       if (f.pair_store) reinterpret_cast<uint32_t*>(d)[i] = u | (u << 16);

@@ -10,6 +10,7 @@ from ._lib import FrameDesc, FrameResult, Options, StreamInfo, Timings
 
 PCM_S16LE, PCM_S16BE, PCM_F32_PLANAR = 0, 1, 2
 FLAG_PROFILE, FLAG_DEBUG_TAPS = 1, 2
+TNS_JAAD, TNS_ISO = 0, 1
 
 FRAME_DESC_DTYPE = np.dtype([("offset", "<u8"), ("nbytes", "<u4"), ("stream_id", "<i4")])
 FRAME_RESULT_DTYPE = np.dtype([("status", "<i4"), ("channels", "<u2"), ("sample_length", "<u2"), ("sample_rate", "<u4"),
@@ -26,9 +27,9 @@ def _ptr(a):
 
 class Engine:
     def __init__(self, device: int = 0, max_streams: int = 4096, pcm_format: int = PCM_S16LE, flags: int = 0,
-                 chunk_frames: int = 0, sbr_tile_frames: int = 0):
+                 chunk_frames: int = 0, sbr_tile_frames: int = 0, tns_mode: int = TNS_JAAD, k2_segment_frames: int = 0):
         self._lib = _lib.load()
-        opts = Options(device, max_streams, pcm_format, 0, flags, chunk_frames, sbr_tile_frames, (C.c_uint32 * 1)(0))
+        opts = Options(device, max_streams, pcm_format, tns_mode, flags, chunk_frames, sbr_tile_frames, k2_segment_frames)
         h = C.c_void_p()
         rc = self._lib.jaadb_engine_create(C.byref(opts), C.byref(h))
         if rc != 0:

@@ -35,6 +35,7 @@ def lib():
         _lib.jo_open_asc.restype = C.c_void_p
         _lib.jo_open_asc.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         _lib.jo_close.argtypes = [C.c_void_p]
+        _lib.jo_set_tns_mode.argtypes = [C.c_void_p, C.c_int]
         _lib.jo_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.jo_tap_ics.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.jo_tap_msused.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -74,6 +75,11 @@ class Decoder:
         if not h:
             raise AACError(st.value)
         return cls(h)
+
+    def set_tns_mode(self, mode: int) -> "Decoder":
+        """0 = JAAD (TNS data parsed and ignored, tools/TNS.java:63-68), 1 = the ISO 14496-3 4.6.9 all-pole filter."""
+        lib().jo_set_tns_mode(self._h, int(mode))
+        return self
 
     def close(self):
         if self._h:

@@ -67,6 +67,9 @@ void* jo_open_asc(const uint8_t* asc, int n, int* status) {
 
 void jo_close(void* hv) { delete static_cast<Handle*>(hv); }
 
+// 0 = JAAD (TNS parsed, never applied), 1 = ISO/IEC 14496-3 4.6.9 filter (DecoderConfig::tnsMode)
+void jo_set_tns_mode(void* hv, int mode) { static_cast<Handle*>(hv)->dec->config.tnsMode = mode; }
+
 // meta[0..3] = status, channels, sampleLength, sampleRate.
 // pcm_f32: planar [channels][sampleLength] (may be NULL); pcm_s16: interleaved (may be NULL).
 int jo_decode_frame(void* hv, const uint8_t* data, int n, float* pcm_f32, int16_t* pcm_s16, int big_endian, int* meta) {

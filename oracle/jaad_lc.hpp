@@ -109,6 +109,12 @@ struct DecoderConfig {
   SampleRate outputFrequency;
   bool psEnabled = true, psPresent = false;
   bool sectionDataResilience = false, scalefactorResilience = false, spectralDataResilience = false;
+  // Not JAAD fields.  (1) JAAD's PNS generator is ONE static int for the whole JVM (ICStream.java:26), so its output depends
+  // on every decoder that ran before; the oracle (and the engine) give each Decoder its own generator with JAAD's seed,
+  // which is exactly "this stream decoded alone in a fresh JVM".  (2) tnsMode 0 = JAAD (TNS.process is a stub,
+  // tools/TNS.java:63-68), 1 = the ISO/IEC 14496-3 4.6.9 all-pole filter (TNS::process below).
+  mutable int32_t pnsState = 0x1F2E3D4C;
+  int tnsMode = 0;
 
   int getFrameLength() const { return frameLengthFlag ? 960 : 1024; }
   bool isUpSampled() const { return hasOutputFrequency && !outputFrequency.same(sampleFrequency); }
@@ -515,13 +521,63 @@ struct FilterBank {
 };
 
 // ---------------------------------------------------------------------------
-// TNS: parsed, never applied (tools/TNS.java:35-68)
+// TNS: parsed as JAAD does (tools/TNS.java:35-61).  JAAD never applies it (TNS.process is a stub, :63-68); process()
+// below is the tool as ISO/IEC 14496-3 4.6.9.3 defines it (tns_decode_frame / tns_decode_coef / tns_ar_filter) and runs
+// only in tnsMode 1.  Arithmetic: binary32, one rounding per operation, in the order written here (the engine's kernel
+// does the same operations in the same order, so the two agree bit for bit; the float64 direct form in
+// tests/test_oracle_cpu.py bounds the distance to the ideal filter).
 // ---------------------------------------------------------------------------
+// SampleFrequency.getMaximalTNS_SFB (SampleFrequency.java:15-26, second constructor array): {long, short}
+static const int TNS_MAX_SFB[12][2] = {{31, 9}, {31, 9}, {34, 10}, {40, 14}, {42, 14}, {51, 14},
+                                       {46, 14}, {46, 14}, {42, 14}, {42, 14}, {42, 14}, {39, 14}};
+
 struct TNS {
   int nFilt[8] = {0};
   int length[8][4] = {{0}}, order[8][4] = {{0}};
   bool direction[8][4] = {{false}};
   float coef[8][4][20] = {{{0}}};
+
+  // 4.6.9.3: spec is the channel's spectrum after M/S and intensity stereo, windows of 128 for EIGHT_SHORT
+  void process(const ICSInfo& info, float* spec) const {
+    const bool sh = info.isEightShortFrame();
+    const int maxTns = TNS_MAX_SFB[info.sfIndex][sh ? 1 : 0];
+    for (int w = 0; w < info.windowCount; w++) {
+      int bottom = info.swbCount;
+      for (int f = 0; f < nFilt[w]; f++) {
+        const int top = bottom;
+        bottom = std::max(top - length[w][f], 0);
+        const int ord = std::min(order[w][f], 20);
+        if (!ord) continue;
+        // tns_decode_coef.  TNSTables holds the NEGATED sin-mapped values (tools/TNSTables.java:10-25 has -sin(..) where
+        // 4.6.9.3 has tmp2 = sin(coef / iqfac)), so tmp2 = -coef, an exact operation.
+        float lpc[21], b[21];
+        lpc[0] = 1.0f;
+        for (int m = 1; m <= ord; m++) {
+          const float t = -coef[w][f][m - 1];
+          for (int i = 1; i < m; i++) b[i] = lpc[i] + (t * lpc[m - i]);
+          for (int i = 1; i < m; i++) lpc[i] = b[i];
+          lpc[m] = t;
+        }
+        const int start = info.swbOffsets[std::min(std::min(bottom, maxTns), info.maxSFB)];
+        const int end = info.swbOffsets[std::min(std::min(top, maxTns), info.maxSFB)];
+        const int size = end - start;
+        if (size <= 0) continue;
+        int pos = w * 128 + start, inc = 1;
+        if (direction[w][f]) { inc = -1; pos = w * 128 + end - 1; }
+        // tns_ar_filter: y(n) = x(n) - lpc[1] y(n-1) - ... - lpc[order] y(n-order), zero initial state
+        float state[20];
+        for (int j = 0; j < 20; j++) state[j] = 0.f;
+        for (int i = 0; i < size; i++, pos += inc) {
+          float y = spec[pos];
+          for (int j = 0; j < ord; j++) y = y - (state[j] * lpc[j + 1]);
+          for (int j = ord - 1; j > 0; j--) state[j] = state[j - 1];
+          state[0] = y;
+          spec[pos] = y;
+        }
+      }
+    }
+  }
+
   void decode(BitStream& in, const ICSInfo& info) {
     static const int SHORT_BITS[3] = {1, 4, 3}, LONG_BITS[3] = {2, 6, 5};
     const int* bits = info.isEightShortFrame() ? SHORT_BITS : LONG_BITS;
@@ -589,7 +645,12 @@ struct ICStream {
     gainControlPresent = in.readBool();
     if (gainControlPresent)
       throw AACException(ST_UNSUPPORTED_ELEMENT, "gain control (SSR) is outside the engine's scope");
-    decodeSpectralData(in);
+    decodeSpectralData(in, conf);
+  }
+
+  // ICStream.processTNS (:313-316) -> TNS.process
+  void processTNS(const DecoderConfig& conf) {
+    if (tnsDataPresent && conf.tnsMode == 1) tns.process(info, iqData);
   }
 
   void decodeSectionData(BitStream& in) {  // :113-146
@@ -676,10 +737,8 @@ struct ICStream {
     }
   }
 
-  // PNS random generator: one static LCG for the whole process (ICStream.java:26,247)
-  static int32_t& randomState() { static int32_t s = 0x1F2E3D4C; return s; }
-
-  void decodeSpectralData(BitStream& in) {  // :222-275
+  // PNS random generator (ICStream.java:26,247): static in JAAD, per Decoder here -- see DecoderConfig::pnsState
+  void decodeSpectralData(BitStream& in, const DecoderConfig& conf) {  // :222-275
     const float* IQ = JT(IQ_TABLE);
     std::fill(iqData, iqData + 1024, 0.f);
     std::fill(q, q + 1024, (int16_t)0);
@@ -700,10 +759,12 @@ struct ICStream {
           }
         } else if (hcb == 13) {
           for (int w = 0; w < groupLen; w++, off += 128) {
-            if (off < 0 || width < 0 || off + width > 1024) throw AACException(ST_ARRAY_BOUNDS, "band out of range");
+            // (a band at the end of the offset table has a negative width: the Java loops do not run, nothing is thrown)
+            if (width > 0 && (off < 0 || off + width > 1024)) throw AACException(ST_ARRAY_BOUNDS, "band out of range");
+            if (width <= 0) continue;
             float energy = 0;
             for (int k = 0; k < width; k++) {
-              int32_t& rs = randomState();
+              int32_t& rs = conf.pnsState;
               rs = (int32_t)(1664525u * (uint32_t)rs + 1013904223u);
               iqData[off + k] = (float)rs;
               energy += iqData[off + k] * iqData[off + k];
@@ -802,6 +863,7 @@ struct SCE : ChannelElement {
   }
   void process(FilterBank& fb, std::vector<std::pair<float*, int>>& target) override {  // SCE.java:90-133
     float* dL = getDataL();
+    ics.processTNS(*config);
     ics.process(dL, fb);
     target.push_back({dL, (int)dataL.size()});
     if (isSBRPresent() && config->sbrEnabled) {
@@ -910,7 +972,9 @@ struct CPE : ChannelElement {
     float* dR = getDataR();
     if (commonWindow & isMSMaskPresent()) processMS();
     processIS();
-    // TNS.process is a stub in JAAD (tools/TNS.java:63-68): nothing to do.
+    // TNS.process is a stub in JAAD (tools/TNS.java:63-68): nothing happens in tnsMode 0
+    icsL.processTNS(*config);
+    icsR.processTNS(*config);
     icsL.process(dL, fb);
     icsR.process(dR, fb);
     if (isSBRPresent() && config->sbrEnabled) {

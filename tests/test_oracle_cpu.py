@@ -226,3 +226,129 @@ def test_asc_parse():
     assert (r["status"], r["channels"], r["sample_rate"], r["sample_length"]) == (0, 6, 48000, 1024)
     with pytest.raises(oracle.AACError):
         oracle.Decoder.create_asc(bytes([0x11, 0xB4]))   # frameLengthFlag = 1 (960 samples) is rejected
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PNS and ISO TNS: the two tools the oracle restates beyond what the round-1 fixtures cover
+# ---------------------------------------------------------------------------------------------------------------------
+SWB_LONG_48 = [0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 48, 56, 64, 72, 80, 88, 96, 108, 120, 132, 144, 160, 176, 196, 216, 240, 264,
+               292, 320, 352, 384, 416, 448, 480, 512, 544, 576, 608, 640, 672, 704, 736, 768, 800, 832, 864, 896, 928, 1024]
+SWB_SHORT_48 = [0, 4, 8, 12, 16, 20, 28, 36, 44, 56, 68, 80, 96, 112, 128]
+
+
+def test_pns_matches_a_numpy_restatement_of_the_java_loop():
+    """Noise bands (codebook 13, ICStream.java:241-257) against a separate numpy model written from the Java lines:
+    int32 LCG 1664525 s + 1013904223 from 0x1F2E3D4C (one generator per Decoder = the stream alone in a fresh JVM),
+    (float) of each state, energy summed in float in index order, scale = (float)(sf / Math.sqrt(energy)) with sf =
+    -2^(e/4).  Draws follow bitstream order: channel L before R, group, band, window in the group.  Bit-exact."""
+    cfg = gen.config(2, n_frames=14, p_transient=0.4, p_pns=0.25)
+    st = gen.generate(cfg, gen.seed_for(2, 41), with_truth=True)
+    dec = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)
+    state = np.uint32(0x1F2E3D4C)
+    n_bands = 0
+    with np.errstate(over="ignore"):
+        for f in range(cfg.n_frames):
+            r = dec.decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
+            assert r["status"] == 0
+            taps = oracle_taps(dec)
+            # a noise band on the left channel feeds intensity stereo on the right, and M/S never touches noise bands
+            for c, t in enumerate(taps):
+                info, cb, sfidx = t["info"], t["sfbcb"], t["sfidx"]
+                short = info[1] == 2
+                swb = SWB_SHORT_48 if short else SWB_LONG_48
+                max_sfb, ngroups = int(info[4]), int(info[5])
+                glen = [int(x) for x in info[6:6 + ngroups]]
+                goff = 0
+                for g in range(ngroups):
+                    for sfb in range(max_sfb):
+                        idx = g * max_sfb + sfb
+                        if cb[idx] != 13:
+                            continue
+                        width = swb[sfb + 1] - swb[sfb]
+                        sf = -np.float32(2.0) ** np.float32(((int(sfidx[idx]) & 0x3FFF) - 200) / 4.0)
+                        for w in range(glen[g]):
+                            vals = np.zeros(width, np.float32)
+                            energy = np.float32(0)
+                            for k in range(width):
+                                state = np.uint32(np.uint32(1664525) * state + np.uint32(1013904223))
+                                vals[k] = np.float32(np.int32(state))
+                                energy = np.float32(energy + np.float32(vals[k] * vals[k]))
+                            scale = np.float32(np.float64(sf) / np.sqrt(np.float64(energy)))
+                            want = (vals * scale).astype(np.float32)
+                            off = goff + w * 128 + swb[sfb]
+                            got = t["spec"][off: off + width]
+                            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (f, c, g, sfb, w)
+                            n_bands += 1
+                    goff += glen[g] * 128
+    assert n_bands > 100
+
+
+def _tns_float64(spec, tns, ws, max_sfb, sf_index=3):
+    """ISO/IEC 14496-3 4.6.9.3 in float64, from the signed coefficient indices (generator truth), formula tables."""
+    out = spec.astype(np.float64).copy()
+    short = ws == 2
+    swb = SWB_SHORT_48 if short else SWB_LONG_48
+    n_swb = len(swb) - 1
+    max_tns = 14 if short else 40   # 48 kHz (SampleFrequency.java:18)
+    for w in range(8 if short else 1):
+        tw = tns[1 + 74 * w: 1 + 74 * (w + 1)]
+        nf, coef_res = int(tw[0]), int(tw[1])
+        bottom = n_swb
+        for f in range(nf):
+            tf = tw[2 + 24 * f: 2 + 24 * (f + 1)]
+            length, order, direction, compress = (int(x) for x in tf[:4])
+            top = bottom
+            bottom = max(top - length, 0)
+            if order == 0:
+                continue
+            bits = coef_res + 3
+            iqfac = ((1 << (bits - 1)) - 0.5) / (np.pi / 2)
+            iqfac_m = ((1 << (bits - 1)) + 0.5) / (np.pi / 2)
+            tmp2 = [np.sin(int(cf) / (iqfac if int(cf) >= 0 else iqfac_m)) for cf in tf[4:4 + order]]
+            a = [1.0] + [0.0] * order
+            for m in range(1, order + 1):
+                b = a[:]
+                for i in range(1, m):
+                    b[i] = a[i] + tmp2[m - 1] * a[m - i]
+                a = b
+                a[m] = tmp2[m - 1]
+            start = swb[min(bottom, max_tns, max_sfb)]
+            end = swb[min(top, max_tns, max_sfb)]
+            size = end - start
+            if size <= 0:
+                continue
+            pos, inc = (w * 128 + end - 1, -1) if direction else (w * 128 + start, 1)
+            state = [0.0] * order
+            for _ in range(size):
+                y = out[pos] - sum(state[j] * a[j + 1] for j in range(order))
+                state = [y] + state[:-1]
+                out[pos] = y
+                pos += inc
+    return out
+
+
+def test_iso_tns_matches_a_float64_direct_form():
+    """The oracle's ISO TNS mode (binary32, the order the engine's kernel uses) against the filter of 14496-3 4.6.9.3 in
+    float64 built from the coefficient INDICES the generator wrote (sin(coef / iqfac), not JAAD's table): pins the table
+    sign convention (TNSTables holds -sin), the LPC recursion, band limits, direction and the short-window layout.
+    JAAD mode on the same stream gives the spectrum before the filter."""
+    cfg = gen.config(2, n_frames=24, p_transient=0.4, p_tns=0.8, tns_mild=True)
+    st = gen.generate(cfg, gen.seed_for(2, 77), with_truth=True)
+    d_jaad = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)
+    d_iso = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg).set_tns_mode(1)
+    n_filtered, worst = 0, 0.0
+    for f in range(cfg.n_frames):
+        fr = st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]]
+        assert d_jaad.decode_frame(fr)["status"] == 0 and d_iso.decode_frame(fr)["status"] == 0
+        for c, (t0, t1) in enumerate(zip(oracle_taps(d_jaad), oracle_taps(d_iso))):
+            tns = st.truth["tns"][f, c]
+            if not tns[0]:
+                assert np.array_equal(t0["spec"], t1["spec"])
+                continue
+            want = _tns_float64(t0["spec"], tns, int(t0["info"][1]), int(t0["info"][4]))
+            scale = max(np.abs(want).max(), 1.0)
+            err = np.abs(t1["spec"].astype(np.float64) - want).max() / scale
+            worst = max(worst, err)
+            assert err < 2e-5, (f, c, err)
+            n_filtered += int(not np.array_equal(t0["spec"], t1["spec"]))
+    assert n_filtered > 10, n_filtered

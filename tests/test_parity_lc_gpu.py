@@ -237,3 +237,141 @@ def test_one_call_decode_pipelines_chunks_and_honours_pcm_offsets():
             got = pcm[o:o + per].view(np.int16).reshape(1024, 2)
             assert np.array_equal(got, ref[(s, f)]), (mode, s, f)
         eng.close()
+
+
+PNS_CASES = [
+    ("stereo_48k", gen.config(2, n_frames=36, p_transient=0.3, p_pns=0.2), 4),
+    ("stereo_48k_no_common", gen.config(2, n_frames=16, p_transient=0.4, p_common_window=0.0, p_pns=0.5), 2),
+    ("mono_24k", gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=20, target_bytes=171, p_transient=0.3, p_pns=0.3), 3),
+    ("c5_51_48k", gen.config(5, n_frames=12, adts=True, p_transient=0.3, p_pns=0.15), 2),
+    ("sf_8k", gen.GenConfig(sf_index=11, chan_cfg=2, n_frames=12, target_bytes=300, p_transient=0.3, p_pns=0.3), 2),
+]
+
+
+@pytest.mark.parametrize("label,cfg,n_streams", PNS_CASES, ids=[c[0] for c in PNS_CASES])
+@pytest.mark.parametrize("segment", [0, 3])
+def test_pns_bit_exact_in_one_batch_and_across_calls(label, cfg, n_streams, segment):
+    """Perceptual noise substitution (codebook 13, ICStream.java:241-257): every stream owns a generator seeded like
+    JAAD's static one, i.e. the oracle decoding that stream alone.  All streams in one batch (the frames of a stream are
+    parsed in parallel and the generator state of each frame comes from a prefix over the draw counts), then the same
+    streams again in three calls -- the generator state is carried in the stream's state."""
+    wl = Workload(cfg, n_streams, base_seed=gen.seed_for(2, 500))
+    assert sum(int((s.truth["sfbcb"] == 13).sum()) for s in wl.streams) > 50
+    ref = run_oracle(wl)
+    for calls in ([(0, cfg.n_frames)], [(0, 1), (1, 9), (9, cfg.n_frames)]):
+        eng = Engine(max_streams=64, pcm_format=PCM_F32_PLANAR, flags=FLAG_DEBUG_TAPS, k2_segment_frames=segment)
+        ids = [eng.open_adts(*wl.hdr) for _ in range(n_streams)]
+        info0 = eng.stream_info(ids[0])
+        ch, ln = info0.channels, info0.sample_length
+        per = ch * ln * 4
+        for lo, hi in calls:
+            frames, index = wl.frame_table(ids, lo, hi)
+            b = eng.batch(frames, wl.blob.nbytes)
+            b.upload(wl.blob)
+            b.decode()
+            pcm, res = b.download()
+            for i, (s, f) in enumerate(index):
+                r = ref[(s, f)]
+                assert res["status"][i] == 0 and r["status"] == 0, (label, s, f, res["status"][i])
+                truth = wl.streams[s].truth
+                for c, t in enumerate(r["taps"]):
+                    g = b.tap(i, c)
+                    assert np.array_equal(g["sfbcb"], t["sfbcb"]), (label, s, f, c, "sfbcb")
+                    assert np.array_equal(g["sfidx"], t["sfidx"]), (label, s, f, c, "sfidx")
+                    assert np.array_equal(g["sfidx"], truth["sfidx"][f, c]), (label, s, f, c, "sfidx vs generator")
+                    assert np.array_equal(g["q"], truth["q"][f, c]), (label, s, f, c, "q vs generator")
+                    assert same_float_bits(g["spec"], t["spec"]), (label, s, f, c, "spectrum", np.abs(g["spec"] - t["spec"]).max())
+                got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(ch, ln)
+                assert same_float_bits(got, r["f32"]), (label, s, f, "float pcm")
+            b.close()
+        eng.close()
+
+
+TNS_ISO_CASES = [
+    ("stereo_48k", gen.config(2, n_frames=30, p_transient=0.3, p_tns=0.7, tns_mild=True), 4),
+    ("stereo_48k_wild", gen.config(2, n_frames=16, p_transient=0.3, p_tns=1.0), 2),      # orders up to 20, any coefficient
+    ("mono_24k", gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=20, target_bytes=171, p_transient=0.3, p_tns=0.7, tns_mild=True), 2),
+    ("c5_51_48k", gen.config(5, n_frames=10, adts=True, p_transient=0.3, p_tns=0.7, tns_mild=True), 2),
+    ("sf_8k", gen.GenConfig(sf_index=11, chan_cfg=2, n_frames=12, target_bytes=300, p_transient=0.3, p_tns=0.7, tns_mild=True), 2),
+]
+
+
+@pytest.mark.parametrize("label,cfg,n_streams", TNS_ISO_CASES, ids=[c[0] for c in TNS_ISO_CASES])
+def test_tns_iso_mode_matches_the_oracle(label, cfg, n_streams):
+    """JAADB_TNS_ISO: the all-pole filter of 14496-3 4.6.9.3 between the stereo tools and the filterbank.  The oracle's
+    ISO restatement does the same binary32 operations in the same order, so spectrum and PCM are bit-identical (the
+    1e-5-of-full-scale budget of BASELINE.json is checked as well); JAAD mode on the same engine build stays JAAD's."""
+    from jaadec_b200 import TNS_ISO
+    wl = Workload(cfg, n_streams, base_seed=gen.seed_for(2, 900))
+    assert sum(int(s.truth["tns"][:, :, 0].sum()) for s in wl.streams) > 5
+    decs = [d.set_tns_mode(1) for d in wl.oracle_decoders()]
+    eng = Engine(max_streams=16, pcm_format=PCM_F32_PLANAR, flags=FLAG_DEBUG_TAPS, tns_mode=TNS_ISO)
+    ids = [eng.open_adts(*wl.hdr) for _ in range(n_streams)]
+    frames, index = wl.frame_table(ids)
+    b = eng.batch(frames, wl.blob.nbytes)
+    b.upload(wl.blob)
+    b.decode()
+    pcm, res = b.download()
+    info0 = eng.stream_info(ids[0])
+    ch, ln = info0.channels, info0.sample_length
+    per = ch * ln * 4
+    n_filtered = 0
+    for i, (s, f) in enumerate(index):
+        r = decs[s].decode_frame(wl.frame_bytes(s, f))
+        assert res["status"][i] == 0 and r["status"] == 0
+        nics = wl.streams[s].truth["q"].shape[1]
+        el = c_in = 0
+        for c in range(nics):
+            t = decs[s].tap_ics(el, c_in)
+            if t is None:
+                el, c_in = el + 1, 0
+                t = decs[s].tap_ics(el, 0)
+            c_in += 1
+            g = b.tap(i, c)
+            assert same_float_bits(g["spec"], t["spec"]), (label, s, f, c, "spectrum after TNS")
+            n_filtered += int(wl.streams[s].truth["tns"][f, c, 0])
+        got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(ch, ln)
+        ok = np.isfinite(r["f32"])
+        assert np.array_equal(ok, np.isfinite(got))
+        assert np.abs(got[ok] - r["f32"][ok]).max(initial=0.0) <= 1e-5 * 32768.0 * max(1.0, np.abs(r["f32"][ok]).max(initial=0.0) / 32768.0)
+        assert same_float_bits(got, r["f32"]), (label, s, f, "float pcm")
+    assert n_filtered > 5
+    b.close()
+    eng.close()
+
+
+SEGMENT_CASES = [("c1_long_only_44k", gen.config(1, n_frames=40), 1), ("c2_mixed_48k", gen.config(2, n_frames=33, p_transient=0.3), 3),
+                 ("mono_24k", gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=21, target_bytes=171, p_transient=0.3), 2),
+                 ("c5_51_48k", gen.config(5, n_frames=14, adts=True, p_transient=0.3), 2)]
+
+
+@pytest.mark.parametrize("label,cfg,n_streams", SEGMENT_CASES, ids=[c[0] for c in SEGMENT_CASES])
+@pytest.mark.parametrize("segment", [1, 2, 5])
+def test_segmented_filterbank_is_bit_identical(label, cfg, n_streams, segment):
+    """Few streams: the filterbank kernel cuts a stream's frames into segments, one CTA each; a segment re-runs the
+    frame before it for the overlap it starts from.  Same float PCM bits as the oracle, also across calls and around a
+    frame that fails (its channels keep the overlap of the frame before)."""
+    wl = Workload(cfg, n_streams, base_seed=gen.seed_for(2, 1300), with_truth=False)
+    blob = wl.blob.copy()
+    bad = (0, min(7, cfg.n_frames - 2))
+    decs = wl.oracle_decoders()
+    eng = Engine(max_streams=8, pcm_format=PCM_F32_PLANAR, k2_segment_frames=segment)
+    ids = [eng.open_adts(*wl.hdr) for _ in range(n_streams)]
+    info0 = eng.stream_info(ids[0])
+    per = info0.channels * info0.sample_length * 4
+    for lo, hi in ((0, 11), (11, cfg.n_frames)):
+        frames, index = wl.frame_table(ids, lo, hi)
+        frames = frames.copy()
+        for i, (s, f) in enumerate(index):
+            if (s, f) == bad:
+                frames["nbytes"][i] //= 2
+        pcm, res = eng.decode(blob, frames)
+        for i, (s, f) in enumerate(index):
+            r = decs[s].decode_frame(blob[int(frames["offset"][i]): int(frames["offset"][i]) + int(frames["nbytes"][i])])
+            assert res["status"][i] == r["status"], (label, s, f)
+            if r["status"] == 0:
+                got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(info0.channels, info0.sample_length)
+                assert same_float_bits(got, r["f32"]), (label, segment, s, f)
+            else:
+                assert (s, f) == bad and res["pcm_bytes"][i] == 0 and not pcm[i * per:(i + 1) * per].any()
+    eng.close()
