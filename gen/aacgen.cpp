@@ -142,6 +142,7 @@ struct Ctx {
   Rng rng;
   int sfIndex;
   double pPns = 0;      // > 0: perceptual noise substitution (codebook 13) on that share of the bands
+  double psExt = 0;     // > 0: PS headers enable the IPD/OPD extension with this probability
   bool tnsMild = false; // TNS filters an ISO decoder can apply without blowing up: order <= 12 / 7, small reflection coefficients
   explicit Ctx(uint64_t seed, int sfi) : rng(seed), sfIndex(sfi) {}
 };
@@ -525,6 +526,8 @@ struct jg_config {
                           //    does not signal SBR: outputFrequency stays at the core rate, A/DecoderConfig.java:180, A/sbr/SBR.java:100-102)
   float p_pns;            // > 0: share of the bands coded as perceptual noise (codebook 13)
   int32_t tns_mild;       // 1: TNS filters an ISO decoder can apply (orders <= 12 / 7, small coefficients)
+  float ps_ext;           // > 0: probability that a PS header enables the IPD/OPD extension (ps/Extension.java)
+  int32_t reserved2;
 };
 
 // Ground truth per ICS (element order, L before R); arrays may be NULL.
@@ -536,7 +539,8 @@ struct jg_truth {
   uint8_t* msused;   // [n_frames][n_elements][128]
   int32_t* sbr;      // [n_frames][n_ics][480] SBR streams only: L_E, L_Q, frame class, pointer, t_E[6], f[6], amp_res,
                      //   coupling, (pad to 32), E[5][64], Q[2][64] as a decoder reconstructs them (aacgen_sbr.inc)
-  int32_t* ps;       // [n_frames][348] SBR+PS streams only: num_env, border_position[6], pad, iid[5][34], icc[5][34]
+  int32_t* ps;       // [n_frames][jg_ps_truth_ints()] SBR+PS streams only: num_env, border_position[6], pad, iid[5][34], icc[5][34],
+                     //   ipd[5][17], nr_ipdopd_par, enable_ipdopd (aacgen_ps.inc)
   int32_t* tns;      // [n_frames][n_ics][600]: tns_data_present, then per window {n_filt, coef_res, 3 x {length, order,
                      //   direction, coef_compress, coef[20] as signed indices}} (IcsPlan::tnsTruth)
 };
@@ -555,6 +559,7 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
   Ctx c(seed, cfg->sf_index);
   c.pPns = cfg->p_pns;
   c.tnsMild = cfg->tns_mild != 0;
+  c.psExt = cfg->ps_ext;
   const int nIcs = jg_ics_per_frame(cfg->chan_cfg);
   const int nEl = jg_elements_per_frame(cfg->chan_cfg);
   // element layout

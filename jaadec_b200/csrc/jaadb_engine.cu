@@ -404,12 +404,14 @@ int init_sbr(jaadb_engine* e) {
   if ((rc = e->upload(JT(SBR_NOISE_TABLE), T::SBR_NOISE_TABLE_N, &D.noise_table))) return rc;
   // parametric stereo
   {
-    static const int16_t* ph[6] = {T::PS_F_HUFF_IID_DEF, T::PS_T_HUFF_IID_DEF, T::PS_F_HUFF_IID_FINE, T::PS_T_HUFF_IID_FINE,
-                                   T::PS_F_HUFF_ICC, T::PS_T_HUFF_ICC};
-    static const int ph_n[6] = {T::PS_F_HUFF_IID_DEF_N, T::PS_T_HUFF_IID_DEF_N, T::PS_F_HUFF_IID_FINE_N, T::PS_T_HUFF_IID_FINE_N,
-                                T::PS_F_HUFF_ICC_N, T::PS_T_HUFF_ICC_N};
-    for (int i = 0; i < 6; ++i)
+    static const int16_t* ph[10] = {T::PS_F_HUFF_IID_DEF, T::PS_T_HUFF_IID_DEF, T::PS_F_HUFF_IID_FINE, T::PS_T_HUFF_IID_FINE,
+                                    T::PS_F_HUFF_ICC, T::PS_T_HUFF_ICC, T::PS_F_HUFF_IPD, T::PS_T_HUFF_IPD, T::PS_F_HUFF_OPD, T::PS_T_HUFF_OPD};
+    static const int ph_n[10] = {T::PS_F_HUFF_IID_DEF_N, T::PS_T_HUFF_IID_DEF_N, T::PS_F_HUFF_IID_FINE_N, T::PS_T_HUFF_IID_FINE_N,
+                                 T::PS_F_HUFF_ICC_N, T::PS_T_HUFF_ICC_N, T::PS_F_HUFF_IPD_N, T::PS_T_HUFF_IPD_N, T::PS_F_HUFF_OPD_N, T::PS_T_HUFF_OPD_N};
+    for (int i = 0; i < 10; ++i)
       if ((rc = e->upload(ph[i], ph_n[i], &D.ps_huff[i]))) return rc;
+    if ((rc = e->upload(JT(PS_IPDOPD_COS_TAB), 9, &D.ps_ipdopd_cos))) return rc;
+    if ((rc = e->upload(JT(PS_IPDOPD_SIN_TAB), 9, &D.ps_ipdopd_sin))) return rc;
     if ((rc = e->upload(JT(PS_FILTER_A), 3, &D.ps_filter_a))) return rc;
     if ((rc = e->upload(JT(PS_PHI_FRACT_QMF), T::PS_PHI_FRACT_QMF_N, &D.ps_phi_qmf))) return rc;
     if ((rc = e->upload(JT(PS_PHI_FRACT_SUBQMF20), T::PS_PHI_FRACT_SUBQMF20_N, &D.ps_phi_sub))) return rc;
@@ -552,10 +554,11 @@ int finish_open(jaadb_engine* e, StreamHost& s, int32_t* stream_id) {
     CUDA_TRY(e, cudaMemcpyAsync(e->d_sbr_elem + (size_t)slot * 2, fresh, sizeof fresh, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemsetAsync(e->d_sbr_chan + (size_t)slot * kSbrChansPerStream, 0, sizeof(SbrChanDev) * kSbrChansPerStream, e->stream));
     if (s.sbr > 1) {
-      // a fresh PSImpl (ps/PSImpl.java:64-94): everything zero except h11_prev = 1
+      // a fresh PSImpl (ps/PSImpl.java:64-94): everything zero except h11_prev = 1 and -- the constructor sets
+      // h12_prev[i][1] where it means h12_prev[i][0] (SURVEY A-14) -- the imaginary part of h12_prev = 1
       static PsChanDev fresh_ps;
       memset(&fresh_ps, 0, sizeof fresh_ps);
-      for (auto& h : fresh_ps.h_prev) h[0] = 1.0f;
+      for (auto& h : fresh_ps.h_prev) { h[0] = 1.0f; h[5] = 1.0f; }
       CUDA_TRY(e, cudaMemcpyAsync(e->d_ps_chan + slot, &fresh_ps, sizeof fresh_ps, cudaMemcpyHostToDevice, e->stream));
     }
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -794,7 +797,7 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
   {
     // everything that depends on a stream's earlier frames, once per run
     const int bps = e->opts.pcm_format == JAADB_PCM_F32_PLANAR ? 4 : 2;
-    k2_prepass_kernel<<<(B.n_runs + 127) / 128, 128, 0, e->stream>>>(B.runs, B.n_runs, B.run_frames, B.fside, B.iside, e->d_sstate,
+    k2_prepass_kernel<<<(B.n_runs + kK2PreWarps - 1) / kK2PreWarps, 32 * kK2PreWarps, 0, e->stream>>>(B.runs, B.n_runs, B.run_frames, B.fside, B.iside, e->d_sstate,
                                                                      e->d_layouts, B.k2frames, B.pcm_bytes, bps,
                                                                      e->opts.tns_mode == JAADB_TNS_ISO ? 1 : 0);
     ++*launches;

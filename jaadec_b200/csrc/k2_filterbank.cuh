@@ -292,9 +292,26 @@ __device__ __noinline__ void tns_iso_filter(float* __restrict__ spec, const IcsS
   }
 }
 
+// The 64 threads (two warps) of one channel.  The barrier number is an immediate: with a register operand ptxas reserves all
+// 16 named barriers for the CTA, and an SM only has 64 -- four resident CTAs, whatever registers and shared memory allow
+// (launch__occupancy_limit_barriers in the round-1 profiles).
+template <int MAX_CH>
 __device__ __forceinline__ void channel_barrier(int c) {
-  // the 64 threads (two warps) of one channel
-  asm volatile("bar.sync %0, 64;" ::"r"(c + 1) : "memory");
+  if (MAX_CH <= 2) {
+    if (c == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+    else asm volatile("bar.sync 2, 64;" ::: "memory");
+  } else {
+    switch (c) {
+      case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+      case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+      case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+      case 3: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+      case 4: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+      case 5: asm volatile("bar.sync 6, 64;" ::: "memory"); break;
+      case 6: asm volatile("bar.sync 7, 64;" ::: "memory"); break;
+      default: asm volatile("bar.sync 8, 64;" ::: "memory"); break;
+    }
+  }
 }
 
 // ---- mbarrier + TMA bulk copy (global -> shared::cta), one transaction barrier per CTA --------------------------------
@@ -322,14 +339,21 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Pre-pass: the sequential part of a run, 16 bytes out per frame.
+// Pre-pass: the sequential part of a run, 16 bytes out per frame.  One warp per run, 32 frames per step: each lane loads
+// its frame's status words and channel headers, and the three things that depend on earlier frames are resolved with
+// warp votes / scans instead of a serial walk -- the instance tag an element showed first (first lane that starts it),
+// windowShape[CURRENT] of each channel (last lane below that decoded an ics_info), the PNS generator (prefix sum of the
+// draw counts, then an O(log n) jump).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int kK2PreWarps = 4;
+
+__global__ void __launch_bounds__(32 * kK2PreWarps)
 k2_prepass_kernel(const RunDev* __restrict__ runs, uint32_t n_runs, const RunFrameDev* __restrict__ run_frames,
                   FrameSide* __restrict__ fside, const IcsSide* __restrict__ iside, StreamState* __restrict__ sstate,
                   const LayoutDev* __restrict__ layouts, K2FrameDev* __restrict__ out, uint32_t* __restrict__ pcm_bytes_out,
                   int bytes_per_sample, int tns_iso) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t r = blockIdx.x * kK2PreWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (r >= n_runs) return;
   const RunDev run = runs[r];
   const LayoutDev lay = layouts[run.layout];
@@ -341,65 +365,103 @@ k2_prepass_kernel(const RunDev* __restrict__ runs, uint32_t n_runs, const RunFra
     const int f0 = lay.el_first_ch[e], n = lay.el_type[e] == EL_CPE ? 2 : 1;
     for (int c = f0; c < f0 + n; ++c) el_of |= (uint32_t)e << (3 * c);
   }
+  // carried along the run (the same in every lane)
   uint32_t shape_cur = 0;
   for (int c = 0; c < nch; ++c) shape_cur |= (uint32_t)(st.window_shape[c] & 1u) << c;
   uint32_t exp_tags = st.tags, exp_mask = 0;
   for (int i = 0; i < 4; ++i) exp_mask |= ((st.tags_valid >> i) & 1u) ? (0xFu << (4 * i)) : 0u;
   uint32_t pns = st.pns_state;
   const uint32_t frame_bytes = (uint32_t)(1024 * (run.mono_dup ? 2 : nch) * bytes_per_sample);
+  const uint32_t lt_mask = (1u << lane) - 1u;
 
-  for (uint32_t it = 0; it < run.count; ++it) {
-    const RunFrameDev rf = run_frames[run.first + it];
-    const uint4 fsw = *reinterpret_cast<const uint4*>(fside + rf.frame);   // status, tags | n_elements | n_started, sbr_bit_off[2]
-    const uint32_t draws = fside[rf.frame].pns_draws;
+  for (uint32_t base = 0; base < run.count; base += 32) {
+    const uint32_t it = base + (uint32_t)lane;
+    const bool valid = it < run.count;
+    RunFrameDev rf{0u, 0u};
+    uint4 fsw = make_uint4(0, 0, 0, 0);   // status, tags | n_elements << 16 | n_started << 24, sbr_bit_off[2]
+    uint32_t draws = 0;
+    if (valid) {
+      rf = run_frames[run.first + it];
+      fsw = *reinterpret_cast<const uint4*>(fside + rf.frame);
+      draws = fside[rf.frame].pns_draws;
+    }
+    // Element objects are per (type, instance tag) in JAAD (StreamState::tags).  An element that shows another tag than
+    // the stream's first one for that element, or that the layout does not have, addresses objects this stream does not
+    // own: it leaves them alone, the frame is reported as JAADB_ST_LAYOUT -- and the stream's own elements of that frame
+    // still go through the filterbank when the frame was parsed to its end, as they do in JAAD
+    // (SyntacticElements.process runs after the whole parse).
+    const uint32_t tags = fsw.y & 0xFFFFu;
+    const int n_started = (int)min(fsw.y >> 24, 4u), n_good = (int)((fsw.y >> 16) & 0xFFu);
+    uint32_t diff = 0;   // nibble e set: element e shows a tag that is not the stream's
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool started = valid && e < n_started;
+      const uint32_t who = __ballot_sync(0xFFFFFFFFu, started);
+      const bool known = ((exp_mask >> (4 * e)) & 1u) != 0;
+      const uint32_t tag = (tags >> (4 * e)) & 15u;
+      const int first = who ? __ffs((int)who) - 1 : 0;
+      const uint32_t first_tag = __shfl_sync(0xFFFFFFFFu, tag, first);
+      const uint32_t expect = known ? ((exp_tags >> (4 * e)) & 15u) : first_tag;
+      if (started && (known || lane > first) && tag != expect) diff |= 0xFu << (4 * e);
+      if (!known && who) { exp_tags |= first_tag << (4 * e); exp_mask |= 0xFu << (4 * e); }
+    }
     int frame_status = (int)fsw.x;
-    // Element objects are per (type, instance tag) in JAAD (StreamState::tags).  An element that shows another tag, or
-    // that the layout does not have, addresses objects this stream does not own: it leaves them alone, the frame is
-    // reported as JAADB_ST_LAYOUT -- and the stream's own elements of that frame still go through the filterbank when
-    // the frame was parsed to its end, as they do in JAAD (SyntacticElements.process runs after the whole parse).
-    // nibble i of `started` / `exp_mask` = element i has shown its tag in this frame / earlier
-    const uint32_t tags = fsw.y & 0xFFFFu, started = (1u << (4 * min(fsw.y >> 24, 4u))) - 1u;
-    const uint32_t diff = (tags ^ exp_tags) & exp_mask & started;
-    const uint32_t fresh = started & ~exp_mask;
-    exp_tags |= tags & fresh;
-    exp_mask |= fresh;
-    const int n_good = (int)((fsw.y >> 16) & 0xFFu);
-    if (diff != 0 && frame_status == 0) {
+    if (valid && diff != 0 && frame_status == 0) {
       frame_status = JAADB_ST_LAYOUT;
       fside[rf.frame].status = JAADB_ST_LAYOUT;
     }
     const bool emit = frame_status == 0;                                        // the frame yields PCM
     const bool parsed = emit || frame_status == JAADB_ST_LAYOUT;                // JAAD reached SyntacticElements.process
     uint32_t flags = (emit ? kK2Emit : 0u) | (parsed ? kK2Parsed : 0u);
-    uint32_t shape_prev = shape_cur;
     for (int c = 0; c < nch; ++c) {
-      const uint32_t* sw = reinterpret_cast<const uint32_t*>(iside + rf.ics_base + c);
-      const uint32_t h0 = sw[0];   // present | info_decoded << 8 | window_sequence << 16 | window_shape << 24
+      uint32_t h0 = 0, tw = 0;
+      if (valid) {
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(iside + rf.ics_base + c);
+        h0 = sw[0];    // present | info_decoded << 8 | window_sequence << 16 | window_shape << 24
+        tw = sw[98];   // tns_present | has_pns << 8 | pns_base << 16
+      }
       const int my_el = (int)((el_of >> (3 * c)) & 7u);
       const bool shape_ok = my_el >= 4 || ((diff >> (4 * my_el)) & 15u) == 0;   // the element belongs to the stream
       const bool el_live = shape_ok && my_el < n_good;                         // ... and was parsed completely
       // window-shape bookkeeping of ICSInfo.decode / setCommonData (ICSInfo.java:90-91,196-197): in failing frames too
-      if (((h0 >> 8) & 0xFFu) && shape_ok) shape_cur = (shape_cur & ~(1u << c)) | (((h0 >> 24) & 1u) << c);
+      const bool upd = valid && ((h0 >> 8) & 0xFFu) != 0 && shape_ok;
+      const uint32_t sbit = (h0 >> 24) & 1u;
+      const uint32_t U = __ballot_sync(0xFFFFFFFFu, upd), S = __ballot_sync(0xFFFFFFFFu, upd && sbit);
+      const uint32_t below = U & lt_mask;
+      const uint32_t prev = below ? ((S >> (31 - __clz((int)below))) & 1u) : ((shape_cur >> c) & 1u);
+      const uint32_t cur = upd ? sbit : prev;
+      flags |= prev << (8 + c) | cur << (16 + c);
+      if (U) shape_cur = (shape_cur & ~(1u << c)) | (((S >> (31 - __clz((int)U))) & 1u) << c);
       // (SBR streams: the SBR stages only run for frames that yield PCM, so the core coder's state waits for them too)
-      if (parsed && el_live && (emit || !run.sbr)) {
+      if (valid && parsed && el_live && (emit || !run.sbr)) {
         flags |= 1u << c;
-        const uint32_t tw = sw[98];   // tns_present | has_pns << 8 | pns_base << 16
         if (tns_iso && (tw & 0xFFu)) flags |= kK2Tns;
         if (tw & 0xFF00u) flags |= kK2Pns;
       }
     }
-    flags |= (shape_prev & 0xFFu) << 8 | (shape_cur & 0xFFu) << 16;
-    *reinterpret_cast<uint4*>(out + run.first + it) = make_uint4(rf.frame, rf.ics_base, flags, pns);
-    pns = pns_jump(pns, draws);
-    if (!run.sbr) pcm_bytes_out[rf.frame] = emit ? frame_bytes : 0u;
+    // PNS generator at the start of each frame: prefix sum of the draws, then jump
+    uint32_t incl = draws;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (valid) {
+      *reinterpret_cast<uint4*>(out + run.first + it) = make_uint4(rf.frame, rf.ics_base, flags, total ? pns_jump(pns, incl - draws) : pns);
+      if (!run.sbr) pcm_bytes_out[rf.frame] = emit ? frame_bytes : 0u;
+    }
+    if (total) pns = pns_jump(pns, total);
   }
-  for (int c = 0; c < nch; ++c) st.window_shape[c] = (uint8_t)((shape_cur >> c) & 1u);
-  uint32_t v = 0;
-  for (int i = 0; i < 4; ++i) v |= ((exp_mask >> (4 * i)) & 1u) << i;
-  st.tags = (uint16_t)exp_tags;
-  st.tags_valid = (uint8_t)v;
-  st.pns_state = pns;
-  sstate[run.stream_slot] = st;
+  if (lane == 0) {
+    for (int c = 0; c < nch; ++c) st.window_shape[c] = (uint8_t)((shape_cur >> c) & 1u);
+    uint32_t v = 0;
+    for (int i = 0; i < 4; ++i) v |= ((exp_mask >> (4 * i)) & 1u) << i;
+    st.tags = (uint16_t)exp_tags;
+    st.tags_valid = (uint8_t)v;
+    st.pns_state = pns;
+    sstate[run.stream_slot] = st;
+  }
 }
 
 // Final overlap of segmented runs: the last segment of a run leaves it in a staging buffer (other segments of the run may
@@ -694,7 +756,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
         }
       }
     }
-    channel_barrier(c);
+    channel_barrier<MAX_THREADS / kThreadsPerChannel>(c);
     {
       const int blk = t >> 3, col = t & 7;
 #pragma unroll
@@ -738,7 +800,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
         x2im[72 * blk + col + 8 * j] = a[j].im;
       }
     }
-    channel_barrier(c);   // also: every thread of the channel is done reading exchange 1
+    channel_barrier<MAX_THREADS / kThreadsPerChannel>(c);   // also: every thread of the channel is done reading exchange 1
     if (!is_short) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -781,7 +843,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
         bre[72 * blk + nl] = (t0 * cs.x) - (t1 * cs.y);
       }
     }
-    channel_barrier(c);
+    channel_barrier<MAX_THREADS / kThreadsPerChannel>(c);
 
     // ---- phase 3: windowing + overlap-add (FilterBank.java:39-123) + PCM.  Thread t owns the sample pairs
     // i = 2t + 128j, i+1 (j = 0..7): the MDCT reorder (MDCT.java:60-80) then reads mirrored positions of the two

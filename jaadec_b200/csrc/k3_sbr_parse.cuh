@@ -688,6 +688,22 @@ __device__ inline int ps_read_data(SbrBits& ld, const SbrTablesDev& T, PsParamDe
   return 0;
 }
 
+__device__ inline int ps_pd_nr_par(int id) { return id % 3 == 0 ? 5 : (id % 3 == 1 ? 11 : 17); }   // PDMode.java:50-57
+
+// EnvData.readData for IPD / OPD
+__device__ inline int ps_read_pd(SbrBits& ld, const SbrTablesDev& T, PsPdDev& p, bool opd, int num_env) {
+  if (p.mode < 0) return 0;
+  const int nr = ps_pd_nr_par(p.mode);
+  for (int n = 0; n < num_env; n++) {
+    int dt, v;
+    SBR_RD(dt, 1);
+    p.dt[n] = (uint8_t)dt;
+    const int16_t* h = T.ps_huff[(opd ? 8 : 6) + (dt ? 1 : 0)];
+    for (int i = 0; i < nr; i++) { SBR_TRY(ps_huff(ld, h, v)); p.index[n][i] = (int8_t)v; }
+  }
+  return 0;
+}
+
 // PSImpl.decode
 __device__ inline int ps_decode(SbrBits& ld, const SbrTablesDev& T, PsParseDev& P) {
   int v;
@@ -696,9 +712,11 @@ __device__ inline int ps_decode(SbrBits& ld, const SbrTablesDev& T, PsParseDev& 
     P.header_read = 1;
     SBR_TRY(ps_read_mode(ld, P.iid));
     SBR_TRY(ps_read_mode(ld, P.icc));
+    // Extension.readMode (ps/Extension.java:31-38)
     SBR_RD(v, 1);
     P.ext_enabled = (uint8_t)v;
-    if (v) return JAADB_ST_UNSUPPORTED_ELEMENT;   // IPD/OPD extension: outside the engine's scope
+    if (v) P.ext_has_data = 1;
+    if (P.ext_has_data) P.ipd.mode = P.opd.mode = v ? P.iid.mode : (int8_t)-1;   // ExtData.setMode(enabled ? parent.mode : null)
   }
   SBR_RD(v, 1);
   P.var_borders = (uint8_t)v;
@@ -710,6 +728,30 @@ __device__ inline int ps_decode(SbrBits& ld, const SbrTablesDev& T, PsParseDev& 
     for (int n = 1; n < num_env + 1; n++) { SBR_RD(v, 5); P.border_position[n] = (uint8_t)(v + 1); }
   SBR_TRY(ps_read_data(ld, T, P.iid, false, num_env));
   SBR_TRY(ps_read_data(ld, T, P.icc, true, num_env));
+  if (P.ext_enabled) {
+    // Extension.readData (ps/Extension.java:40-59): cnt bytes in a sub-stream; extension id 0 is ExtData.readData
+    // (ps/ExtData.java:17-25), every other id only consumes its two bits
+    int cnt;
+    SBR_RD(cnt, 4);
+    if (cnt == 15) { SBR_RD(v, 8); cnt += v; }
+    if (ld.left() < (uint32_t)(8 * cnt)) return JAADB_ST_EOS;
+    SbrBits sub = ld;
+    sub.end = ld.pos + 8 * cnt;
+    while (sub.left() > 7) {
+      int id;
+      if (!sub.get(2, id)) return JAADB_ST_EOS;
+      if (id == 0 && P.ext_has_data) {
+        if (!sub.get(1, v)) return JAADB_ST_EOS;
+        P.ext_data_enabled = (uint8_t)v;
+        if (v) {
+          SBR_TRY(ps_read_pd(sub, T, P.ipd, false, num_env));
+          SBR_TRY(ps_read_pd(sub, T, P.opd, true, num_env));
+        }
+        if (!sub.get(1, v)) return JAADB_ST_EOS;
+      }
+    }
+    ld.pos += 8 * cnt;
+  }
   P.data_available = 1;
   return 0;
 }
@@ -745,9 +787,39 @@ __device__ inline void ps_data_decode(PsParseDev& P, PsFrameDev& o) {
       for (int env = 0; env < num_env; env++) ps_decode_env(p, k == 1, env);
     }
   }
+  // Extension.decode / ExtData.decode (ps/Extension.java:61-64, ExtData.java:27-32) with PDMode: stride 1, clip = idx & 7
+  const bool ext_live = P.ext_enabled && P.ext_has_data;
+  PsPdDev* pd[2] = {&P.ipd, &P.opd};
+  if (ext_live && P.ext_data_enabled) {
+    for (int k = 0; k < 2; ++k) {
+      PsPdDev& p = *pd[k];
+      if (num_env == 0) {
+        if (p.mode >= 0) { for (int i = 0; i < 17; ++i) p.index[0][i] = p.first[i]; }
+        else { p.dt[0] = 0; for (int i = 0; i < 17; ++i) p.index[0][i] = 0; }
+      } else {
+        for (int env = 0; env < num_env; env++) {
+          int8_t* ix = p.index[env];
+          if (p.mode < 0) { p.dt[env] = 0; for (int i = 0; i < 17; ++i) ix[i] = 0; continue; }
+          const int nr = ps_pd_nr_par(p.mode);
+          const int8_t* prev = env == 0 ? p.first : p.index[env - 1];
+          if (p.dt[env]) {
+            for (int i = 0; i < nr; i++) ix[i] = (int8_t)((prev[i] + ix[i]) & 7);
+          } else {
+            int pc = ix[0];
+            for (int i = 1; i < nr; i++) { pc = (pc + ix[i]) & 7; ix[i] = (int8_t)pc; }
+          }
+        }
+      }
+    }
+  }
   if (num_env == 0) num_env = 1;
   for (int k = 0; k < 2; ++k)
     for (int i = 0; i < 34; ++i) ps[k]->first[i] = ps[k]->index[num_env - 1][i];
+  // ExtData.update runs whether or not the frame carried phase data (ps/ExtData.java:34-37); ExtData.restore in the
+  // variable-border branch below calls update as well (:39-42), i.e. changes nothing more
+  if (ext_live)
+    for (int k = 0; k < 2; ++k)
+      for (int i = 0; i < 17; ++i) pd[k]->first[i] = pd[k]->index[num_env - 1][i];
   P.data_available = 0;
   const int L = 32;
   if (!P.var_borders) {
@@ -778,6 +850,12 @@ __device__ inline void ps_data_decode(PsParseDev& P, PsFrameDev& o) {
   o.icc_mode = P.icc.mode < 0 ? 1 : P.icc.mode;
   for (int env = 0; env < 5; ++env)
     for (int i = 0; i < 20; ++i) { o.iid[env][i] = P.iid.index[env][i]; o.icc[env][i] = P.icc.index[env][i]; }
+  // Extension.nr_par (ps/Extension.java:81-86, ExtData.java:49-54).  255: the extension is on while IID is off -- JAAD
+  // dereferences the null PDMode (NullPointerException); the caller fails the frame
+  o.nr_ipdopd_par = !ext_live ? 0 : (P.ipd.mode < 0 ? 255 : (uint8_t)max(ps_pd_nr_par(P.ipd.mode), 11));
+  o.enable_ipdopd = P.ext_data_enabled;
+  for (int env = 0; env < 5; ++env)
+    for (int i = 0; i < 17; ++i) o.ipd[env][i] = P.ipd.index[env][i];
 }
 
 // SBR.readExtendedData (:229-242).  Extension payloads (parametric stereo = id 2) are skipped in this build: the
@@ -1070,6 +1148,12 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
       PsFrameDev* po = ps_out + run.ps_base + it;
       po->use_ps = 0;
       if (mode != 0 && S->ps.opened && S->ps.data_available) ps_data_decode(S->ps, *po);
+      if (po->use_ps && po->nr_ipdopd_par == 255) {
+        // JAAD dies of a NullPointerException inside ps_mix_phase (see ps_data_decode): the frame fails
+        po->use_ps = 0;
+        if (frame_status == 0) { frame_status = JAADB_ST_ARRAY_BOUNDS; fside[f].status = JAADB_ST_ARRAY_BOUNDS; }
+        mode = 0;
+      }
       use_ps = po->use_ps;
     }
     if (lane == 0) dequant = S->dequant;

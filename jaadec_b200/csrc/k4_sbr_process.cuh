@@ -1271,9 +1271,10 @@ __global__ void k4_commit_kernel(const K4RunDev* __restrict__ runs, uint32_t n_r
 // Xsbr matrix in xg, output the left / right QMF matrices the synthesis kernel reads:
 //   xps[ps run][frame of the tile][left, right][32 slots][64 bands][re, im]
 constexpr int kK5Threads = 96;
+constexpr int kK5PhaseThread = 80;  // an otherwise idle thread: the sequential IPD/OPD phase bookkeeping
 constexpr int kK5Bands = 71;        // 10 hybrid sub-bands + QMF bands 3..63
 constexpr int kK5AllPass = 30;      // of which run the all-pass chain: the hybrid ones and QMF bands 3..22
-constexpr int kK5Floats = 2 * 32 * kXsStride + 2 * 32 * 24 + 32 * 20 + 3 * 88 + kK5Bands * 28 + kK5AllPass * 30 + 22 * 4 + 72;
+constexpr int kK5Floats = 2 * 32 * kXsStride + 2 * 32 * 24 + 32 * 20 + 3 * 88 + kK5Bands * 28 + kK5AllPass * 30 + 22 * 8 + 72 + 22 * 5 * 4 + 80;
 static_assert(kK5Floats % 4 == 0, "PsFrameDev must land 16-byte aligned");
 constexpr size_t k5_smem_bytes() { return sizeof(float) * kK5Floats + sizeof(PsFrameDev); }
 
@@ -1290,9 +1291,11 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
   float* hwork = pg + 32 * 20;                           // [3][44][2] hybrid analysis input
   float* dly = hwork + 3 * 88;                           // [71][14][2] input delay of every decorrelator band
   float* ser = dly + kK5Bands * 28;                      // [30][3 links][5][2] all-pass delay lines
-  float* hprev = ser + kK5AllPass * 30;                  // [22][4] mixing matrix of the previous envelope, per group
-  float* hybuf = hprev + 22 * 4;                         // [3][12][2] hybrid analysis history
-  PsFrameDev* pp = reinterpret_cast<PsFrameDev*>(hybuf + 72);
+  float* hprev = ser + kK5AllPass * 30;                  // [22][8] mixing matrix of the previous envelope, per group (re x4, im x4)
+  float* hybuf = hprev + 22 * 8;                         // [3][12][2] hybrid analysis history
+  float* phases = hybuf + 72;                            // [22][5][4] IPD/OPD: phaseLeft, phaseRight per (group, envelope)
+  float* pdprev = phases + 22 * 5 * 4;                   // [20][2][2] PDData.prev
+  PsFrameDev* pp = reinterpret_cast<PsFrameDev*>(pdprev + 80);
 #define XL(l, k, c) xl[(l) * kXsStride + (k) * 2 + (c)]
 #define XR(l, k, c) xr[(l) * kXsStride + (k) * 2 + (c)]
 #define HYL(n, k, c) hyl[((n) * 12 + (k)) * 2 + (c)]
@@ -1334,8 +1337,10 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
     if (delay_band) di = pst->delay_buf_index_delay[sb];
   }
   if (t < 22)
-    for (int i = 0; i < 4; ++i) hprev[t * 4 + i] = pst->h_prev[t][i];
+    for (int i = 0; i < 8; ++i) hprev[t * 8 + i] = pst->h_prev[t][i];
   if (t < 72) hybuf[t] = (&pst->hyb_buffer[0][0][0])[t];
+  if (t < 80) pdprev[t] = (&pst->pd_prev[0][0][0])[t];
+  int phase_hist = pst->phase_hist;             // (thread kK5PhaseThread carries it)
   float peak = 0, pprev = 0, smooth_prev = 0;   // transient detector of parameter band t
   if (t < 20) { peak = pst->P_PeakDecayNrg[t]; pprev = pst->P_prev[t]; smooth_prev = pst->P_SmoothPeakDecayDiffNrg_prev[t]; }
   // per-band constants of the decorrelator (ps/PSImpl.java:266-396)
@@ -1516,10 +1521,46 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
         pg[n * 20 + t] = ((sm * gamma) <= nrg) ? 1.0f : (nrg / (sm * gamma));
       }
     }
+    // ---- IPD/OPD phase rotation parameters (ps_mix_phase, :488-560), thread kK5PhaseThread alongside the transient
+    // detector: sequential over (group, envelope) in the reference's order, because phase_hist moves once per pair and the
+    // groups 0/3 and 1/2 share a parameter band's history.  Quirks kept (SURVEY A-15): opd_index is read from ipd -- so
+    // ipd.prev and opd.prev always hold the same values (pdprev) -- and the value "before previous" comes from opd.prev for both.
+    const int nr_ipdopd_par = pp->nr_ipdopd_par;
+    if (t == kK5PhaseThread && nr_ipdopd_par) {
+      for (int g2 = 0; g2 < 22; ++g2) {
+        const int b2 = ps_bk(g2);
+        if (b2 >= nr_ipdopd_par) continue;
+        for (int env = 0; env < num_env; ++env) {
+          float* pv = pdprev + (b2 * 2 + phase_hist) * 2;
+          float tl0 = (pv[0] * 0.25f), tl1 = (pv[1] * 0.25f), tr0 = (pv[0] * 0.25f), tr1 = (pv[1] * 0.25f);
+          const int ix = min(abs((int)pp->ipd[env][b2]), 8);
+          const float c0 = __ldg(T.ps_ipdopd_cos + ix), s0v = __ldg(T.ps_ipdopd_sin + ix);
+          pv[0] = c0; pv[1] = s0v;
+          tl0 += c0; tl1 += s0v; tr0 += c0; tr1 += s0v;
+          phase_hist = (phase_hist + 1) % 2;
+          const float* pb = pdprev + (b2 * 2 + phase_hist) * 2;
+          tl0 += (pb[0] * 0.5f); tl1 += (pb[1] * 0.5f); tr0 += (pb[0] * 0.5f); tr1 += (pb[1] * 0.5f);
+          // magnitude_c (:402-404): (float) Math.sqrt of a float sum of squares -- a correctly rounded float sqrt is the same value
+          const float xy = __fsqrt_rn((tr0 * tr0) + (tr1 * tr1)), pq = __fsqrt_rn((tl0 * tl0) + (tl1 * tl1));
+          float pl0 = 0.f, pl1 = 0.f, pr0 = 0.f, pr1 = 0.f;
+          if (xy != 0.f) { pl0 = __fdiv_rn(tr0, xy); pl1 = __fdiv_rn(tr1, xy); }
+          const float xypq = (xy * pq);
+          if (xypq != 0.f) {
+            const float tmp1 = (tr0 * tl0) + (tr1 * tl1), tmp2 = (tr1 * tl0) - (tr0 * tl1);
+            pr0 = __fdiv_rn(tmp1, xypq); pr1 = __fdiv_rn(tmp2, xypq);
+          }
+          float* ph = phases + (g2 * 5 + env) * 4;
+          ph[0] = pl0; ph[1] = pl1; ph[2] = pr0; ph[3] = pr1;
+        }
+      }
+    }
     // the mixing matrices the groups ended the previous envelope with (read by every band of the group before any of
     // them stores the new ones)
-    float hp11 = 1.f, hp12 = 0.f, hp21 = 0.f, hp22 = 0.f;
-    if (band_task) { hp11 = hprev[gr * 4]; hp12 = hprev[gr * 4 + 1]; hp21 = hprev[gr * 4 + 2]; hp22 = hprev[gr * 4 + 3]; }
+    float hp11 = 1.f, hp12 = 0.f, hp21 = 0.f, hp22 = 0.f, hq11 = 0.f, hq12 = 0.f, hq21 = 0.f, hq22 = 0.f;
+    if (band_task) {
+      hp11 = hprev[gr * 8]; hp12 = hprev[gr * 8 + 1]; hp21 = hprev[gr * 8 + 2]; hp22 = hprev[gr * 8 + 3];
+      hq11 = hprev[gr * 8 + 4]; hq12 = hprev[gr * 8 + 5]; hq21 = hprev[gr * 8 + 6]; hq22 = hprev[gr * 8 + 7];
+    }
     __syncthreads();
     // ---- decorrelation (:266-396) + mixing (ps_mix_phase, :406-681), one band per thread
     if (band_task) {
@@ -1528,6 +1569,10 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
       const float* sf_iid = T.ps_sf_iid[fine];
       float H11 = hp11, H12 = hp12, H21 = hp21, H22 = hp22;
       float dH11 = 0, dH12 = 0, dH21 = 0, dH22 = 0;
+      // imaginary parts: only for the parameter bands the IPD/OPD extension covers (bk < nr_ipdopd_par)
+      const bool rot = bk < nr_ipdopd_par;
+      const bool bkm = bk != 0;   // FBType.bkm tests `& ~NEGATE_IPD_MASK` (FBType.java:71-73, A-13): true for every bk != 0
+      float G11 = 0, G12 = 0, G21 = 0, G22 = 0, dG11 = 0, dG12 = 0, dG21 = 0, dG22 = 0;
       int env = -1, env_end = 0;
       for (int n = 0; n < 32; ++n) {
         if (n == env_end) {
@@ -1558,10 +1603,22 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
             h21 = (1.4142135623731f * (-cosa * sing));
             h22 = (1.4142135623731f * (sina * sing));
           }
+          float g11 = 0, g12 = 0, g21 = 0, g22 = 0;
+          if (rot) {
+            const float* ph = phases + (gr * 5 + env) * 4;   // phaseLeft, phaseRight (:562-571)
+            g11 = (h11 * ph[1]); g12 = (h12 * ph[3]); g21 = (h21 * ph[1]); g22 = (h22 * ph[3]);
+            h11 = (h11 * ph[0]); h12 = (h12 * ph[2]); h21 = (h21 * ph[0]); h22 = (h22 * ph[2]);
+          }
           const float L = (float)(pp->border[env + 1] - pp->border[env]);
           dH11 = (h11 - hp11) / L; dH12 = (h12 - hp12) / L; dH21 = (h21 - hp21) / L; dH22 = (h22 - hp22) / L;
           H11 = hp11; H12 = hp12; H21 = hp21; H22 = hp22;
           hp11 = h11; hp12 = h12; hp21 = h21; hp22 = h22;
+          if (rot) {
+            dG11 = (g11 - hq11) / L; dG12 = (g12 - hq12) / L; dG21 = (g21 - hq21) / L; dG22 = (g22 - hq22) / L;
+            G11 = hq11; G12 = hq12; G21 = hq21; G22 = hq22;
+            if (bkm) { dG11 = -dG11; dG12 = -dG12; dG21 = -dG21; dG22 = -dG22; G11 = -G11; G12 = -G12; G21 = -G21; G22 = -G22; }
+            hq11 = g11; hq12 = g12; hq21 = g21; hq22 = g22;
+          }
         }
         // -- decorrelate
         const float re = hyb ? HYL(n, sb, 0) : XL(n, sb, 0);
@@ -1602,12 +1659,23 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
         if (++s2 >= 5) s2 = 0;
         // -- mix
         H11 += dH11; H12 += dH12; H21 += dH21; H22 += dH22;
-        const float lRe = (H11 * re) + (H21 * rRe), lIm = (H11 * im) + (H21 * rIm);
-        const float oRe = (H12 * re) + (H22 * rRe), oIm = (H12 * im) + (H22 * rIm);
+        float lRe = (H11 * re) + (H21 * rRe), lIm = (H11 * im) + (H21 * rIm);
+        float oRe = (H12 * re) + (H22 * rRe), oIm = (H12 * im) + (H22 * rIm);
+        if (rot) {
+          // apply rotation (:650-656)
+          G11 += dG11; G12 += dG12; G21 += dG21; G22 += dG22;
+          lRe -= (G11 * im) + (G21 * rIm);
+          lIm += (G11 * re) + (G21 * rRe);
+          oRe -= (G12 * im) + (G22 * rIm);
+          oIm += (G12 * re) + (G22 * rRe);
+        }
         if (hyb) { HYL(n, sb, 0) = lRe; HYL(n, sb, 1) = lIm; HYR(n, sb, 0) = oRe; HYR(n, sb, 1) = oIm; }
         else { XL(n, sb, 0) = lRe; XL(n, sb, 1) = lIm; XR(n, sb, 0) = oRe; XR(n, sb, 1) = oIm; }
       }
-      if (sb == ps_group_border(gr)) { hprev[gr * 4] = hp11; hprev[gr * 4 + 1] = hp12; hprev[gr * 4 + 2] = hp21; hprev[gr * 4 + 3] = hp22; }
+      if (sb == ps_group_border(gr)) {
+        hprev[gr * 8] = hp11; hprev[gr * 8 + 1] = hp12; hprev[gr * 8 + 2] = hp21; hprev[gr * 8 + 3] = hp22;
+        hprev[gr * 8 + 4] = hq11; hprev[gr * 8 + 5] = hq12; hprev[gr * 8 + 6] = hq21; hprev[gr * 8 + 7] = hq22;
+      }
     } else {
       // every thread keeps the (uniform) ring positions in step: 32 slots per frame
       td = (td + 32) % 2; s0 = (s0 + 32) % 3; s1 = (s1 + 32) % 4; s2 = (s2 + 32) % 5;
@@ -1654,8 +1722,10 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
   }
   if (t == 3) { pst->saved_delay = td; pst->delay_buf_index_ser[0] = s0; pst->delay_buf_index_ser[1] = s1; pst->delay_buf_index_ser[2] = s2; }
   if (t < 22)
-    for (int i = 0; i < 4; ++i) pst->h_prev[t][i] = hprev[t * 4 + i];
+    for (int i = 0; i < 8; ++i) pst->h_prev[t][i] = hprev[t * 8 + i];
   if (t < 72) (&pst->hyb_buffer[0][0][0])[t] = hybuf[t];
+  if (t < 80) (&pst->pd_prev[0][0][0])[t] = pdprev[t];
+  if (t == kK5PhaseThread) pst->phase_hist = phase_hist;
   if (t < 20) { pst->P_PeakDecayNrg[t] = peak; pst->P_prev[t] = pprev; pst->P_SmoothPeakDecayDiffNrg_prev[t] = smooth_prev; }
 #undef XL
 #undef XR

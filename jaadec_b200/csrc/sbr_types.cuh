@@ -59,10 +59,21 @@ struct PsParamDev {
   int8_t first[34];       // indices of the last envelope of the previous frame
   int8_t index[5][34];
 };
+// IPD / OPD (ps/PDData.java, PDMode.java): 17 entries, stride 1, indices modulo 8
+struct PsPdDev {
+  int8_t mode;            // PDMode id = the IID mode's id, -1: null
+  uint8_t dt[5];
+  int8_t first[17];
+  int8_t index[5][17];
+};
 struct PsParseDev {
   PsParamDev iid, icc;
+  PsPdDev ipd, opd;       // the IPD/OPD extension (ps/Extension.java, ExtData.java)
   uint8_t opened;         // SBR1.ps != null
-  uint8_t var_borders, num_env, data_available, header_read, ext_enabled;
+  uint8_t var_borders, num_env, data_available, header_read;
+  uint8_t ext_enabled;    // Extension.enabled (enable_ext of the PS header)
+  uint8_t ext_has_data;   // Extension.data != null: created when a header first enables the extension, never dropped
+  uint8_t ext_data_enabled;   // ExtData.enabled (enable_ipdopd of the last ps_extension read)
   uint8_t border_position[6];
 };
 
@@ -73,9 +84,13 @@ struct __align__(16) PsFrameDev {
   uint8_t border[6];
   int8_t iid_mode, icc_mode;   // as EnvData.mode() resolves them (IID null -> 0, ICC null -> 1)
   int8_t iid[5][20], icc[5][20];
-  uint8_t pad[14];
+  uint8_t nr_ipdopd_par;  // Extension.nr_par(): parameter bands below it get the IPD/OPD phase rotation (0: extension off)
+  uint8_t enable_ipdopd;  // ExtData.enabled of this frame (parity tap only; the rotation runs without it, as in JAAD)
+  uint8_t pad[12];
+  int8_t ipd[5][17];      // IPD indices as PSImpl.ps_mix_phase reads them (opd_index is read from the same array, A-15)
+  uint8_t pad2[11];
 };
-static_assert(sizeof(PsFrameDev) == 224, "PsFrameDev layout");
+static_assert(sizeof(PsFrameDev) == 320, "PsFrameDev layout (mirrored by jaadec_b200/engine.py PS_FRAME_DTYPE)");
 
 struct SbrElemDev {
   SbrHeaderDev hdr, hdr_saved;
@@ -96,7 +111,7 @@ struct SbrElemDev {
   uint8_t dequant;          // this frame's sbr_data got as far as NoiseEnvelope.dequantChannel / unmap (K3, per frame)
   SbrChanParse ch[2];
   PsParseDev ps;          // mono element of an SBR+PS stream
-  uint8_t pad2[4];
+  uint8_t pad2[2];
 };
 static_assert(sizeof(SbrElemDev) % 4 == 0, "SbrElemDev is copied word-wise");
 
@@ -138,7 +153,12 @@ struct __align__(16) PsChanDev {
   float delay_sub[12][2][2];         // hybrid sub-bands
   float delay_sub_ser[12][3][5][2];
   float P_PeakDecayNrg[20], P_prev[20], P_SmoothPeakDecayDiffNrg_prev[20];
-  float h_prev[22][4];               // h11, h12, h21, h22 (real parts) per group
+  float h_prev[22][8];               // h11, h12, h21, h22 per group: real parts, then imaginary parts (IPD/OPD rotation)
+  // PDData.prev (ps/PDData.java:13) of ipd AND opd: ps_mix_phase stores the same value into both at the same place
+  // (opd_index is read from ipd, ps/PSImpl.java:503-504), so the two arrays are always equal and one copy serves
+  float pd_prev[20][2][2];
+  int32_t phase_hist;
+  int32_t pad3[3];
   float syn_v_right[2][9][128];      // right channel: the 9 most recent synthesis v-vectors ([.][0] = newest), double
                                      // buffered like SbrChanDev::syn_v
   int32_t saved_delay, delay_buf_index_ser[3];
@@ -189,7 +209,9 @@ struct SbrTablesDev {
   const float* w_imag;              // [16]
   const float* noise_table;         // [512][2]
   // parametric stereo
-  const int16_t* ps_huff[6];        // f_iid_def, t_iid_def, f_iid_fine, t_iid_fine, f_icc, t_icc
+  const int16_t* ps_huff[10];       // f_iid_def, t_iid_def, f_iid_fine, t_iid_fine, f_icc, t_icc, f_ipd, t_ipd, f_opd, t_opd
+  const float* ps_ipdopd_cos;       // [9]
+  const float* ps_ipdopd_sin;       // [9]
   const float* ps_filter_a;         // [3]
   const float* ps_phi_qmf;          // [64][2]
   const float* ps_phi_sub;          // [12][2]

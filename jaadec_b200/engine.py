@@ -188,10 +188,12 @@ class Batch:
         return out[0] if rc > 0 else None
 
     PS_FRAME_DTYPE = np.dtype([("use_ps", "u1"), ("num_env", "u1"), ("border", "u1", (6,)), ("iid_mode", "i1"), ("icc_mode", "i1"),
-                               ("iid", "i1", (5, 20)), ("icc", "i1", (5, 20)), ("pad", "u1", (14,))])
+                               ("iid", "i1", (5, 20)), ("icc", "i1", (5, 20)), ("nr_ipdopd_par", "u1"), ("enable_ipdopd", "u1"),
+                               ("pad", "u1", (12,)), ("ipd", "i1", (5, 17)), ("pad2", "u1", (11,))])
 
     def tap_ps(self, frame: int):
         """Parametric-stereo parameters of frame `frame` after ps_data_decode (None when the stream carries no PS)."""
+        assert self.PS_FRAME_DTYPE.itemsize == 320
         out = np.zeros(1, self.PS_FRAME_DTYPE)
         self._lib.jaadb_batch_tap_ps.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         rc = self._lib.jaadb_batch_tap_ps(self._h, frame, out.ctypes.data, out.nbytes)

@@ -127,13 +127,15 @@ class Decoder:
                     q_div=out[816:944].view(np.float32).reshape(2, 64).copy())
 
     def tap_ps(self, el: int = 0):
-        """PS state after the frame just decoded: dict(num_env, border[6], iid[5,34], icc[5,34], iid_mode, icc_mode)."""
-        out = np.zeros(350, np.int32)
+        """PS state after the frame just decoded: dict(num_env, border[6], iid[5,34], icc[5,34], iid_mode, icc_mode, ipd[5,17],
+        nr_ipdopd_par (Extension.nr_par), enable_ipdopd (ExtData.enabled))."""
+        out = np.zeros(440, np.int32)
         lib().jo_tap_ps.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         if lib().jo_tap_ps(self._h, el, out.ctypes.data) < 0:
             return None
         return dict(num_env=int(out[0]), border=out[1:7].copy(), iid=out[8:178].reshape(5, 34).copy(),
-                    icc=out[178:348].reshape(5, 34).copy(), iid_mode=int(out[348]), icc_mode=int(out[349]), raw=out[:348].copy())
+                    icc=out[178:348].reshape(5, 34).copy(), iid_mode=int(out[348]), icc_mode=int(out[349]), raw=out[:348].copy(),
+                    ipd=out[350:435].reshape(5, 17).copy(), nr_ipdopd_par=int(out[435]), enable_ipdopd=int(out[436]))
 
     def tap_msused(self, el: int):
         ms = np.zeros(128, np.uint8)

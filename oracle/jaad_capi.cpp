@@ -185,7 +185,12 @@ int jo_tap_ps(void* hv, int el, int32_t* out) {
   sbr::SBR1* s = static_cast<sbr::SBR1*>(ae[el]->sbr.get());
   if (!s->ps) return -1;
   ps::PSImpl* p = static_cast<ps::PSImpl*>(s->ps.get());
-  memset(out, 0, sizeof(int32_t) * 350);
+  memset(out, 0, sizeof(int32_t) * 440);
+  // [350..434]: ipd.index[5][17]; [435]: Extension.nr_par(); [436]: ExtData.enabled
+  for (int env = 0; env < 5; ++env)
+    for (int i = 0; i < 17; ++i) out[350 + env * 17 + i] = p->ext.ipd.index[env][i];
+  out[435] = p->ext.nr_par();
+  out[436] = p->ext.data_enabled ? 1 : 0;
   out[0] = p->num_env;
   for (int i = 0; i < 6; ++i) out[1 + i] = p->border_position[i];
   for (int env = 0; env < 5; ++env)

@@ -4,8 +4,8 @@
 // (IID / ICC modes, envelopes, Huffman delta coding), hybrid analysis / synthesis filterbank, all-pass decorrelator
 // with transient ducking and the H-matrix mixing.  Same operation order and the same quirks (SURVEY.md A-12..A-16,
 // A-31); tables come verbatim from the reference through tools/extract_tables_sbr.py.
-// The IPD/OPD extension (Extension / ExtData / PDData) is outside the engine's scope: a header that enables it is
-// reported as ST_UNSUPPORTED_ELEMENT.  The 34-band configuration is dead code in the reference (FBType.max returns the
+// The IPD/OPD extension (Extension / ExtData / PDData / PDMode and the phase rotation in ps_mix_phase) is restated with
+// its quirks.  The 34-band configuration is dead code in the reference (FBType.max returns the
 // smaller type, ps/FBType.java:17-19), so only the 20-band hybrid structure exists here.
 // File:line references are relative to aac/src/main/java/net/sourceforge/jaad/aac/ps/.
 #pragma once
@@ -107,6 +107,96 @@ struct ParamData {
   void update(int num_env) {  // :64-69
     if (num_env == 0) memset(first, 0, sizeof first);
     else memcpy(first, index[num_env - 1], sizeof first);
+  }
+};
+
+// PDData (PDData.java, PDMode.java): one phase parameter set (IPD or OPD), 17 entries, stride 1, indices modulo 8
+struct PdData {
+  bool isOpd;
+  int first[17];
+  int index[MAX_PS_ENVELOPES][17];
+  bool dt[MAX_PS_ENVELOPES];
+  int mode = -1;             // PDMode id = the IID mode's id (PDData.setMode, :19-21); -1 = null
+  float prev[20][2][2];      // PDData.prev (:13)
+  explicit PdData(bool opd) : isOpd(opd) {
+    memset(first, 0, sizeof first); memset(index, 0, sizeof index); memset(dt, 0, sizeof dt); memset(prev, 0, sizeof prev);
+  }
+  static int nrPar(int id) { static const int n[6] = {5, 11, 17, 5, 11, 17}; return n[id]; }   // PDMode.java:50-57
+  const int16_t* table(bool dtFlag) const {
+    if (isOpd) return dtFlag ? T::PS_T_HUFF_OPD : T::PS_F_HUFF_OPD;
+    return dtFlag ? T::PS_T_HUFF_IPD : T::PS_F_HUFF_IPD;
+  }
+  const int* prevOf(int env) const { return env == 0 ? first : index[env - 1]; }
+  void readData(BitStream& ld, int num_env) {  // EnvData.readData (:44-49)
+    if (mode < 0) return;
+    for (int n = 0; n < num_env; n++) {
+      dt[n] = ld.readBool();
+      const int16_t* h = table(dt[n]);
+      for (int i = 0; i < nrPar(mode); i++) index[n][i] = huffRead(ld, h);
+    }
+  }
+  void decodeEnv(int env) {  // Envelope.decode (:45-74) with PDMode.stride() = 1, clip = idx & 7
+    if (mode < 0) { dt[env] = false; memset(index[env], 0, sizeof index[env]); return; }
+    const int nr = nrPar(mode);
+    int* ix = index[env];
+    const int* pv = prevOf(env);
+    if (dt[env]) {
+      for (int i = 0; i < nr; i++) ix[i] = (pv[i] + ix[i]) & 7;
+    } else {
+      int p = ix[0];
+      for (int i = 1; i < nr; i++) { p = (p + ix[i]) & 7; ix[i] = p; }
+    }
+  }
+  void decode(int num_env) {  // EnvData.decode (:51-62)
+    if (num_env == 0) {
+      if (mode >= 0) memcpy(index[0], first, sizeof first);
+      else { dt[0] = false; memset(index[0], 0, sizeof index[0]); }
+    } else {
+      for (int env = 0; env < num_env; env++) decodeEnv(env);
+    }
+  }
+  void update(int num_env) {  // :64-69
+    if (num_env == 0) memset(first, 0, sizeof first);
+    else memcpy(first, index[num_env - 1], sizeof first);
+  }
+};
+
+// Extension.java + ExtData.java: the IPD/OPD extension of ps_data
+struct PsExtension {
+  bool enabled = false;       // Extension.enabled: enable_ext of the PS header
+  bool has_data = false;      // Extension.data != null (created the first time a header enables the extension, never dropped)
+  bool data_enabled = false;  // ExtData.enabled: enable_ipdopd of the last ps_extension(0) read
+  PdData ipd{false}, opd{true};
+
+  void readMode(BitStream& ld, int iidMode) {  // Extension.readMode (:31-38)
+    enabled = ld.readBool();
+    if (enabled) has_data = true;
+    if (has_data) ipd.mode = opd.mode = enabled ? iidMode : -1;   // ExtData.setMode(enabled ? parent.mode : null)
+  }
+  void readData(BitStream& ld0, int num_env) {  // Extension.readData (:40-59)
+    if (!enabled) return;
+    int cnt = ld0.readBits(4);
+    if (cnt == 15) cnt += ld0.readBits(8);
+    BitStream ld = ld0.readSubStream(8 * cnt);
+    while (ld.getBitsLeft() > 7) {
+      const int ps_extension_id = ld.readBits(2);
+      if (ps_extension_id == 0 && has_data) {
+        // ExtData.readData (ExtData.java:17-25)
+        data_enabled = ld.readBool();
+        if (data_enabled) { ipd.readData(ld, num_env); opd.readData(ld, num_env); }
+        ld.readBit();
+      }
+    }
+  }
+  void decode(int num_env) { if (enabled && has_data && data_enabled) { ipd.decode(num_env); opd.decode(num_env); } }   // :61-64, ExtData :27-32
+  void update(int num_env) { if (enabled && has_data) { ipd.update(num_env); opd.update(num_env); } }                  // :66-69, ExtData :34-37
+  void restore(int num_env) { update(num_env); }   // ExtData.restore calls update (ExtData.java:39-42)
+  // Extension.nr_par (:81-86) -> ExtData.nr_par (ExtData.java:49-54).  -1: JAAD dereferences the null PDMode of an extension
+  // that was enabled while IID is off (NullPointerException)
+  int nr_par() const {
+    if (!(enabled && has_data)) return 0;
+    if (ipd.mode < 0) return -1;
+    return std::max(PdData::nrPar(ipd.mode), 11);
   }
 };
 
@@ -233,7 +323,7 @@ struct HybridFilterbank {
 // PSImpl.java
 struct PSImpl : sbr::PSBase {
   ParamData iid{false}, icc{true};
-  bool ext_enabled = false;
+  PsExtension ext;
   bool var_borders = false;
   int num_env = 0;
   int border_position[MAX_PS_ENVELOPES + 1] = {0};
@@ -272,8 +362,7 @@ struct PSImpl : sbr::PSBase {
       header_read = true;
       iid.readMode(ld);
       icc.readMode(ld);
-      ext_enabled = ld.readBool();
-      if (ext_enabled) throw AACException(ST_UNSUPPORTED_ELEMENT, "PS IPD/OPD extension is outside the engine's scope");
+      ext.readMode(ld, iid.mode);
     }
     var_borders = ld.readBit() != 0;
     int tmp = ld.readBits(2);
@@ -283,7 +372,7 @@ struct PSImpl : sbr::PSBase {
       for (int n = 1; n < num_env + 1; n++) border_position[n] = ld.readBits(5) + 1;
     iid.readData(ld, num_env);
     icc.readData(ld, num_env);
-    // ext.readData: nothing is read while the extension is disabled (Extension.java:40-41)
+    ext.readData(ld, num_env);
     ps_data_available = true;
   }
 
@@ -291,9 +380,11 @@ struct PSImpl : sbr::PSBase {
     if (!ps_data_available) num_env = 0;
     iid.decode(num_env);
     icc.decode(num_env);
+    ext.decode(num_env);
     if (num_env == 0) num_env = 1;
     iid.update(num_env);
     icc.update(num_env);
+    ext.update(num_env);
     ps_data_available = false;
     const int L = HybridFilterbank::len;
     if (!var_borders) {
@@ -305,6 +396,7 @@ struct PSImpl : sbr::PSBase {
       if (border_position[num_env] < L) {
         iid.restoreEnv(num_env);
         icc.restoreEnv(num_env);
+        ext.restore(num_env);
         ++num_env;
         border_position[num_env] = L;
       }
@@ -435,9 +527,16 @@ struct PSImpl : sbr::PSBase {
     const float* sincos_alphas_b = fine ? JT(PS_SINCOS_ALPHAS_B_FINE) : JT(PS_SINCOS_ALPHAS_B_NORMAL);
     const float* cos_alphas = JT(PS_COS_ALPHAS);
     const float* sin_alphas = JT(PS_SIN_ALPHAS);
+    const float* ipdopd_cos_tab = JT(PS_IPDOPD_COS_TAB);
+    const float* ipdopd_sin_tab = JT(PS_IPDOPD_SIN_TAB);
     float h11, h12, h21, h22, H11, H12, H21, H22, dH11, dH12, dH21, dH22;
+    float h11i = 0, h12i = 0, h21i = 0, h22i = 0, H11i = 0, H12i = 0, H21i = 0, H22i = 0, dH11i = 0, dH12i = 0, dH21i = 0, dH22i = 0;
+    const int nr_ipdopd_par = ext.nr_par();
     for (int gr = 0; gr < NUM_GROUPS; gr++) {
       const int bk = bk_of(gr);
+      const bool rot = bk < nr_ipdopd_par;
+      // FBType.bkm tests `& ~NEGATE_IPD_MASK` instead of `& NEGATE_IPD_MASK` (FBType.java:71-73): true for every bk != 0
+      const bool bkm = (map_group2bk20[gr] & ~NEGATE_IPD_MASK) != 0;
       const bool hyb = gr < NUM_HYBRID_GROUPS;
       const int maxsb = hyb ? group_border20[gr] + 1 : group_border20[gr + 1];
       for (int env = 0; env < num_env; env++) {
@@ -469,6 +568,55 @@ struct PSImpl : sbr::PSBase {
           h21 = (COEF_SQRT2 * (-cosa * sing));
           h22 = (COEF_SQRT2 * (sina * sing));
         }
+        if (rot) {
+          // phase rotation parameters (:488-560), quirks kept: opd_index is read from ipd, the value "before previous" comes
+          // from opd.prev for both, phase_hist moves once per (group, envelope)
+          float* ipd_prev = ext.ipd.prev[bk][phase_hist];
+          float* opd_prev = ext.opd.prev[bk][phase_hist];
+          float tempLeft[2], tempRight[2], phaseLeft[2], phaseRight[2];
+          tempLeft[0] = (ipd_prev[0] * 0.25f);
+          tempLeft[1] = (ipd_prev[1] * 0.25f);
+          tempRight[0] = (opd_prev[0] * 0.25f);
+          tempRight[1] = (opd_prev[1] * 0.25f);
+          const int ipd_index = std::abs(ext.ipd.index[env][bk]);
+          const int opd_index = std::abs(ext.ipd.index[env][bk]);
+          if (ipd_index > 8) throw AACException(ST_ARRAY_BOUNDS, "PS phase index out of bounds");
+          ipd_prev[0] = ipdopd_cos_tab[ipd_index];
+          ipd_prev[1] = ipdopd_sin_tab[ipd_index];
+          opd_prev[0] = ipdopd_cos_tab[opd_index];
+          opd_prev[1] = ipdopd_sin_tab[opd_index];
+          tempLeft[0] += ipd_prev[0];
+          tempLeft[1] += ipd_prev[1];
+          tempRight[0] += opd_prev[0];
+          tempRight[1] += opd_prev[1];
+          ++phase_hist;
+          phase_hist %= 2;
+          ipd_prev = ext.opd.prev[bk][phase_hist];
+          opd_prev = ext.opd.prev[bk][phase_hist];
+          tempLeft[0] += (ipd_prev[0] * 0.5f);
+          tempLeft[1] += (ipd_prev[1] * 0.5f);
+          tempRight[0] += (opd_prev[0] * 0.5f);
+          tempRight[1] += (opd_prev[1] * 0.5f);
+          const float xy = (float)std::sqrt((double)(tempRight[0] * tempRight[0] + tempRight[1] * tempRight[1]));   // magnitude_c (:402-404)
+          const float pq = (float)std::sqrt((double)(tempLeft[0] * tempLeft[0] + tempLeft[1] * tempLeft[1]));
+          if (xy != 0) { phaseLeft[0] = (tempRight[0] / xy); phaseLeft[1] = (tempRight[1] / xy); }
+          else { phaseLeft[0] = 0; phaseLeft[1] = 0; }
+          const float xypq = (xy * pq);
+          if (xypq != 0) {
+            const float tmp1 = (tempRight[0] * tempLeft[0]) + (tempRight[1] * tempLeft[1]);
+            const float tmp2 = (tempRight[1] * tempLeft[0]) - (tempRight[0] * tempLeft[1]);
+            phaseRight[0] = (tmp1 / xypq);
+            phaseRight[1] = (tmp2 / xypq);
+          } else { phaseRight[0] = 0; phaseRight[1] = 0; }
+          h11i = (h11 * phaseLeft[1]);
+          h12i = (h12 * phaseRight[1]);
+          h21i = (h21 * phaseLeft[1]);
+          h22i = (h22 * phaseRight[1]);
+          h11 = (h11 * phaseLeft[0]);
+          h12 = (h12 * phaseRight[0]);
+          h21 = (h21 * phaseLeft[0]);
+          h22 = (h22 * phaseRight[0]);
+        }
         const float L = (float)(border_position[env + 1] - border_position[env]);
         dH11 = (h11 - h11_prev[gr][0]) / L;
         dH12 = (h12 - h12_prev[gr][0]) / L;
@@ -476,16 +624,36 @@ struct PSImpl : sbr::PSBase {
         dH22 = (h22 - h22_prev[gr][0]) / L;
         H11 = h11_prev[gr][0]; H12 = h12_prev[gr][0]; H21 = h21_prev[gr][0]; H22 = h22_prev[gr][0];
         h11_prev[gr][0] = h11; h12_prev[gr][0] = h12; h21_prev[gr][0] = h21; h22_prev[gr][0] = h22;
+        if (rot) {
+          dH11i = (h11i - h11_prev[gr][1]) / L;
+          dH12i = (h12i - h12_prev[gr][1]) / L;
+          dH21i = (h21i - h21_prev[gr][1]) / L;
+          dH22i = (h22i - h22_prev[gr][1]) / L;
+          H11i = h11_prev[gr][1]; H12i = h12_prev[gr][1]; H21i = h21_prev[gr][1]; H22i = h22_prev[gr][1];
+          if (bkm) {
+            dH11i = -dH11i; dH12i = -dH12i; dH21i = -dH21i; dH22i = -dH22i;
+            H11i = -H11i; H12i = -H12i; H21i = -H21i; H22i = -H22i;
+          }
+          h11_prev[gr][1] = h11i; h12_prev[gr][1] = h12i; h21_prev[gr][1] = h21i; h22_prev[gr][1] = h22i;
+        }
         for (int n = border_position[env]; n < border_position[env + 1]; n++) {
           H11 += dH11; H12 += dH12; H21 += dH21; H22 += dH22;
+          if (rot) { H11i += dH11i; H12i += dH12i; H21i += dH21i; H22i += dH22i; }
           for (int sb = group_border20[gr]; sb < maxsb; sb++) {
             float* l = hyb ? X_hybrid_left[n][sb] : X_left[n][sb];
             float* r = hyb ? X_hybrid_right[n][sb] : X_right[n][sb];
             const float inL0 = l[0], inL1 = l[1], inR0 = r[0], inR1 = r[1];
-            l[0] = (H11 * inL0) + (H21 * inR0);
-            l[1] = (H11 * inL1) + (H21 * inR1);
-            r[0] = (H12 * inL0) + (H22 * inR0);
-            r[1] = (H12 * inL1) + (H22 * inR1);
+            float tL0 = (H11 * inL0) + (H21 * inR0);
+            float tL1 = (H11 * inL1) + (H21 * inR1);
+            float tR0 = (H12 * inL0) + (H22 * inR0);
+            float tR1 = (H12 * inL1) + (H22 * inR1);
+            if (rot) {
+              tL0 -= (H11i * inL1) + (H21i * inR1);
+              tL1 += (H11i * inL0) + (H21i * inR0);
+              tR0 -= (H12i * inL1) + (H22i * inR1);
+              tR1 += (H12i * inL0) + (H22i * inR0);
+            }
+            l[0] = tL0; l[1] = tL1; r[0] = tR0; r[1] = tR1;
           }
         }
       }
@@ -497,6 +665,9 @@ struct PSImpl : sbr::PSBase {
     memset(X_hybrid_left, 0, sizeof X_hybrid_left);
     memset(X_hybrid_right, 0, sizeof X_hybrid_right);
     ps_data_decode();
+    // JAAD runs into a NullPointerException inside ps_mix_phase (ExtData.nr_par on a null mode) when a header enables the
+    // extension while IID is off; reported here before the frame's processing starts
+    if (ext.nr_par() < 0) throw AACException(ST_ARRAY_BOUNDS, "PS extension enabled without IID (NullPointerException in JAAD)");
     fb.hybrid_analysis(X_left, X_hybrid_left);
     ps_decorrelate(X_left, X_right, X_hybrid_left, X_hybrid_right);
     ps_mix_phase(X_left, X_right, X_hybrid_left, X_hybrid_right);

@@ -176,3 +176,30 @@ def test_oracle_reproduces_sbr_golden(name):
         assert np.array_equal(r["s16"], g["s16"][i]), (name, i)
         sha.update(np.ascontiguousarray(r["f32"], np.float32).tobytes())
     assert sha.digest() == g["f32_sha256"].tobytes()
+
+
+def test_ps_ipdopd_extension_parse_matches_generator_truth():
+    """IPD/OPD extension of parametric stereo (ps/Extension.java, ExtData.java, PDData.java, PDMode.java): the oracle's
+    ps_extension parse and modulo-8 delta decoding against the generator's own bookkeeping (no decoder involved), including
+    Extension.nr_par -- which decides the parameter bands that get the phase rotation -- and frames whose extension carries
+    no phase data (enable_ipdopd = 0: the rotation still runs on the indices an earlier frame left, as in JAAD)."""
+    import gen
+    import oracle
+    n_rot = n_stale = 0
+    for seed in range(8):
+        cfg = gen.config(4, n_frames=50, ps_ext=0.7)
+        st = gen.generate(cfg, gen.seed_for(4, 300 + seed), with_truth=True)
+        dec = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)
+        for f in range(cfg.n_frames):
+            r = dec.decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
+            assert r["status"] == 0, (seed, f)
+            t, tr = dec.tap_ps(0), st.truth["ps"][f]
+            ne = t["num_env"]
+            assert ne == tr[0] and np.array_equal(t["border"][:ne + 1], tr[1:2 + ne]), (seed, f)
+            assert np.array_equal(t["iid"][:ne], tr[8:178].reshape(5, 34)[:ne]) and np.array_equal(t["icc"][:ne], tr[178:348].reshape(5, 34)[:ne])
+            assert t["nr_ipdopd_par"] == tr[433], (seed, f)
+            assert np.array_equal(t["ipd"], tr[348:433].reshape(5, 17)), (seed, f)
+            n_rot += int(tr[433] > 0)
+            n_stale += int(tr[433] > 0 and tr[434] == 0)
+            assert np.isfinite(r["f32"]).all()
+    assert n_rot > 100 and n_stale > 5, (n_rot, n_stale)

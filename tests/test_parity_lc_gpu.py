@@ -319,14 +319,18 @@ def test_tns_iso_mode_matches_the_oracle(label, cfg, n_streams):
     for i, (s, f) in enumerate(index):
         r = decs[s].decode_frame(wl.frame_bytes(s, f))
         assert res["status"][i] == 0 and r["status"] == 0
-        nics = wl.streams[s].truth["q"].shape[1]
-        el = c_in = 0
-        for c in range(nics):
-            t = decs[s].tap_ics(el, c_in)
+        taps, el = [], 0
+        while True:
+            t = decs[s].tap_ics(el, 0)
             if t is None:
-                el, c_in = el + 1, 0
-                t = decs[s].tap_ics(el, 0)
-            c_in += 1
+                break
+            taps.append(t)
+            t2 = decs[s].tap_ics(el, 1)
+            if t2 is not None:
+                taps.append(t2)
+            el += 1
+        assert len(taps) == wl.streams[s].truth["q"].shape[1]
+        for c, t in enumerate(taps):
             g = b.tap(i, c)
             assert same_float_bits(g["spec"], t["spec"]), (label, s, f, c, "spectrum after TNS")
             n_filtered += int(wl.streams[s].truth["tns"][f, c, 0])

@@ -24,6 +24,9 @@ CASES = [
     ("stereo_sbr_22k", gen.GenConfig(sf_index=7, chan_cfg=2, n_frames=30, target_bytes=320, sbr_mode=1), 3),
     ("mono_sbr_ps_16k", gen.GenConfig(sf_index=8, chan_cfg=1, n_frames=30, target_bytes=150, sbr_mode=2), 3),
     ("mono_sbr_ps_32k", gen.GenConfig(sf_index=5, chan_cfg=1, n_frames=30, target_bytes=200, sbr_mode=2), 3),
+    # the IPD/OPD extension of parametric stereo (ps/Extension.java, the phase rotation of ps/PSImpl.java:488-660)
+    ("c4_mono_sbr_ps_ipdopd", gen.config(4, n_frames=60, ps_ext=0.7), 8),
+    ("mono_sbr_ps_ipdopd_16k", gen.GenConfig(sf_index=8, chan_cfg=1, n_frames=40, target_bytes=170, sbr_mode=2, ps_ext=1.0), 3),
 ]
 
 
@@ -215,3 +218,41 @@ def test_ps_parameters_equal_generator_truth():
 def oracle_decoder(cfg):
     import oracle
     return oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)
+
+
+def test_ps_ipdopd_parameters_equal_generator_truth_and_state_crosses_calls():
+    """The IPD/OPD extension: K3 reads ps_extension (ps/Extension.java:40-59, ExtData.java:17-25), decodes the phase
+    indices modulo 8 (PDMode) and hands ps_mix_phase the number of parameter bands that rotate; the values equal the
+    generator's ground truth and the oracle's.  Then the same streams in three calls: the phase history (PDData.prev,
+    phase_hist) and the imaginary parts of the previous mixing matrices cross call boundaries -- float PCM bit-exact."""
+    n_rot = 0
+    for seed in range(6):
+        cfg = gen.config(4, n_frames=40, ps_ext=0.8)
+        st = gen.generate(cfg, gen.seed_for(4, 900 + seed), with_truth=True)
+        dec = oracle_decoder(cfg)
+        eng = Engine(max_streams=2, pcm_format=PCM_F32_PLANAR, sbr_tile_frames=5)
+        sid = eng.open_adts(2, cfg.sf_index, cfg.chan_cfg, expect_sbr=2)
+        per = 2 * 2048 * 4
+        for lo, hi in ((0, 3), (3, 19), (19, 40)):
+            n = hi - lo
+            frames = np.zeros(n, dtype=[("offset", "<u8"), ("nbytes", "<u4"), ("stream_id", "<i4")])
+            frames["offset"], frames["nbytes"], frames["stream_id"] = st.offsets[lo:hi], st.sizes[lo:hi], sid
+            b = eng.batch(frames, st.data.nbytes)
+            b.upload(st.data)
+            b.decode()
+            pcm, res = b.download()
+            assert (res["status"] == 0).all()
+            for i, f in enumerate(range(lo, hi)):
+                r = dec.decode_frame(st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]])
+                assert r["status"] == 0
+                g, t, tr = b.tap_ps(i), dec.tap_ps(0), st.truth["ps"][f]
+                assert g is not None and g["use_ps"] == 1
+                assert int(g["nr_ipdopd_par"]) == tr[433] == t["nr_ipdopd_par"], (seed, f)
+                if tr[433]:
+                    assert np.array_equal(g["ipd"], tr[348:433].reshape(5, 17)) and np.array_equal(g["ipd"], t["ipd"]), (seed, f)
+                    n_rot += 1
+                got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(2, 2048)
+                assert same_float_bits(got, r["f32"]), (seed, f, float(np.abs(got - r["f32"]).max()))
+            b.close()
+        eng.close()
+    assert n_rot > 60

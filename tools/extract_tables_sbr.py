@@ -49,7 +49,7 @@ def emit_ps(em, ref, JavaFile, AAC):
     for nm in ("Phi_Fract_Qmf", "Phi_Fract_SubQmf20", "Q_Fract_allpass_Qmf", "Q_Fract_allpass_SubQmf20", "cos_alphas", "sin_alphas",
                "cos_betas_normal", "sin_betas_normal", "cos_betas_fine", "sin_betas_fine", "sincos_alphas_B_normal",
                "sincos_alphas_B_fine", "cos_gammas_normal", "cos_gammas_fine", "sin_gammas_normal", "sin_gammas_fine",
-               "sf_iid_normal", "sf_iid_fine"):
+               "sf_iid_normal", "sf_iid_fine", "ipdopd_cos_tab", "ipdopd_sin_tab"):
         em.f32("PS_" + nm.upper(), t.floats(nm), "ps/PSTables.java")
     h = JavaFile(ref, P + "Huffman.java")
     for nm in ("f_huff_iid_def", "t_huff_iid_def", "f_huff_iid_fine", "t_huff_iid_fine", "f_huff_icc", "t_huff_icc",
