@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -206,6 +207,9 @@ int parse_stbl(Reader& r, const Box& stbl, std::vector<Sample>& out) {
 
   uint64_t fixed = r.be(stsz.body + 4, 4), n_samples = r.be(stsz.body + 8, 4);
   if (!r.ok || (fixed == 0 && stsz.body + 12 + 4 * n_samples > stsz.end)) return JAADB_E_CONFIG;
+  // A sample table cannot describe more samples than the file has bytes for: with a fixed sample size the count is not
+  // backed by a table, so a crafted header must not size the allocations below (JAAD would die of OutOfMemoryError)
+  if (n_samples > r.n / std::max<uint64_t>(fixed, 1)) return JAADB_E_CONFIG;
   auto sample_size = [&](uint64_t i) -> uint32_t { return fixed ? (uint32_t)fixed : (uint32_t)r.be(stsz.body + 12 + 4 * i, 4); };
 
   uint64_t n_chunks = r.be(stco.body + 4, 4);
@@ -223,8 +227,8 @@ int parse_stbl(Reader& r, const Box& stbl, std::vector<Sample>& out) {
     uint64_t t = 0, k = 0;
     for (uint64_t i = 0; i < n_tt; ++i) {
       uint64_t cnt = r.be(stts.body + 8 + 8 * i, 4), delta = r.be(stts.body + 12 + 8 * i, 4);
+      if (cnt > n_samples - k) return JAADB_E_CONFIG;   // ArrayIndexOutOfBoundsException in JAAD
       for (uint64_t j = 0; j < cnt; ++j) {
-        if (k >= n_samples) return JAADB_E_CONFIG;   // ArrayIndexOutOfBoundsException in JAAD
         times[k++] = t;
         t += delta;
       }
@@ -240,8 +244,8 @@ int parse_stbl(Reader& r, const Box& stbl, std::vector<Sample>& out) {
     if (first == 0 || last > n_chunks) return JAADB_E_CONFIG;
     for (uint64_t j = first - 1; j < last; ++j) {
       uint64_t off = chunk_offset(j);
+      if (per > n_samples - cur) return JAADB_E_CONFIG;
       for (uint64_t k = 0; k < per; ++k) {
-        if (cur >= n_samples) return JAADB_E_CONFIG;
         uint32_t sz = sample_size(cur);
         out.push_back(Sample{off, times[cur], sz});
         off += sz;
@@ -297,7 +301,7 @@ int64_t mp4_index(const uint8_t* file, uint64_t nbytes, uint64_t blob_offset, in
     if (rc != JAADB_OK) return rc;
     int64_t cnt = 0;
     for (const Sample& s : samples) {
-      if (s.offset + s.size > nbytes) break;   // EOFException while reading the frame: the stream ends here
+      if (s.size > nbytes || s.offset > nbytes - s.size) break;   // EOFException while reading the frame: the stream ends here
       if (frames && (uint64_t)cnt < max_frames) {
         frames[cnt].offset = blob_offset + s.offset;
         frames[cnt].nbytes = s.size;
@@ -317,6 +321,7 @@ void parallel_streams(uint32_t n_streams, uint32_t threads, F&& fn) {
   if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
   threads = std::min(threads, std::max(1u, n_streams));
   std::atomic<uint32_t> next(0);
+  // (fn never throws: the per-stream indexers catch everything themselves -- an exception leaving a std::thread is std::terminate)
   auto worker = [&]() {
     for (;;) {
       uint32_t s = next.fetch_add(1);
@@ -326,7 +331,13 @@ void parallel_streams(uint32_t n_streams, uint32_t threads, F&& fn) {
   };
   if (threads == 1) { worker(); return; }
   std::vector<std::thread> pool;
-  for (uint32_t i = 0; i < threads; ++i) pool.emplace_back(worker);
+  pool.reserve(threads);
+  try {
+    for (uint32_t i = 0; i < threads; ++i) pool.emplace_back(worker);
+  } catch (...) {
+    // the host refused another thread: the ones that exist (and this one) finish the work
+  }
+  worker();
   for (auto& th : pool) th.join();
 }
 
@@ -338,11 +349,17 @@ int64_t index_many(const uint8_t* blob, const uint64_t* stream_begin, uint32_t n
   if (!blob || !stream_begin) return JAADB_E_INVALID;
   for (uint32_t s = 0; s < n_streams; ++s)
     if (stream_begin[s + 1] < stream_begin[s]) return JAADB_E_INVALID;
+  // no exception crosses the C ABI or leaves a worker thread: allocation failures inside one stream's indexer fail that stream
+  auto one_safe = [&one](const uint8_t* d, uint64_t n, uint64_t off, int32_t id, jaadb_frame_desc* fr, uint64_t mx, Info* info) -> int64_t {
+    try { return one(d, n, off, id, fr, mx, info); }
+    catch (const std::bad_alloc&) { return JAADB_E_NOMEM; }
+    catch (...) { return JAADB_E_INVALID; }
+  };
   std::vector<int64_t> count(n_streams, 0);
   std::vector<Info> local(n_streams);
   parallel_streams(n_streams, threads, [&](uint32_t s) {
-    count[s] = one(blob + stream_begin[s], stream_begin[s + 1] - stream_begin[s], stream_begin[s],
-                   stream_ids ? stream_ids[s] : (int32_t)s, nullptr, 0, &local[s]);
+    count[s] = one_safe(blob + stream_begin[s], stream_begin[s + 1] - stream_begin[s], stream_begin[s],
+                        stream_ids ? stream_ids[s] : (int32_t)s, nullptr, 0, &local[s]);
   });
   std::vector<uint64_t> first(n_streams + 1, 0);
   for (uint32_t s = 0; s < n_streams; ++s) first[s + 1] = first[s] + (uint64_t)std::max<int64_t>(count[s], 0);
@@ -355,8 +372,8 @@ int64_t index_many(const uint8_t* blob, const uint64_t* stream_begin, uint32_t n
   if (frames && first[n_streams] <= max_frames)
     parallel_streams(n_streams, threads, [&](uint32_t s) {
       if (count[s] > 0)
-        one(blob + stream_begin[s], stream_begin[s + 1] - stream_begin[s], stream_begin[s],
-            stream_ids ? stream_ids[s] : (int32_t)s, frames + first[s], (uint64_t)count[s], nullptr);
+        one_safe(blob + stream_begin[s], stream_begin[s + 1] - stream_begin[s], stream_begin[s],
+                 stream_ids ? stream_ids[s] : (int32_t)s, frames + first[s], (uint64_t)count[s], nullptr);
     });
   return (int64_t)first[n_streams];
 }
@@ -368,25 +385,33 @@ extern "C" {
 int64_t jaadb_adts_index(const uint8_t* data, uint64_t nbytes, uint64_t blob_offset, int32_t stream_id,
                          jaadb_frame_desc* frames, uint64_t max_frames, jaadb_adts_info* info) {
   if (!data && nbytes) return JAADB_E_INVALID;
-  return adts_index(data, nbytes, blob_offset, stream_id, frames, max_frames, info);
+  try { return adts_index(data, nbytes, blob_offset, stream_id, frames, max_frames, info); }
+  catch (const std::bad_alloc&) { return JAADB_E_NOMEM; }
+  catch (...) { return JAADB_E_INVALID; }
 }
 
 int64_t jaadb_mp4_index(const uint8_t* file, uint64_t nbytes, uint64_t blob_offset, int32_t stream_id,
                         jaadb_frame_desc* frames, uint64_t max_frames, jaadb_mp4_track* track) {
   if (!file) return JAADB_E_INVALID;
-  return mp4_index(file, nbytes, blob_offset, stream_id, frames, max_frames, track);
+  try { return mp4_index(file, nbytes, blob_offset, stream_id, frames, max_frames, track); }
+  catch (const std::bad_alloc&) { return JAADB_E_NOMEM; }
+  catch (...) { return JAADB_E_INVALID; }
 }
 
 int64_t jaadb_adts_index_many(const uint8_t* blob, const uint64_t* stream_begin, uint32_t n_streams,
                               const int32_t* stream_ids, jaadb_frame_desc* frames, uint64_t max_frames,
                               uint64_t* first_frame, jaadb_adts_info* infos, uint32_t threads) {
-  return index_many(blob, stream_begin, n_streams, stream_ids, frames, max_frames, first_frame, infos, threads, adts_index);
+  try { return index_many(blob, stream_begin, n_streams, stream_ids, frames, max_frames, first_frame, infos, threads, adts_index); }
+  catch (const std::bad_alloc&) { return JAADB_E_NOMEM; }
+  catch (...) { return JAADB_E_INVALID; }
 }
 
 int64_t jaadb_mp4_index_many(const uint8_t* blob, const uint64_t* file_begin, uint32_t n_files, const int32_t* stream_ids,
                              jaadb_frame_desc* frames, uint64_t max_frames, uint64_t* first_frame,
                              jaadb_mp4_track* tracks, uint32_t threads) {
-  return index_many(blob, file_begin, n_files, stream_ids, frames, max_frames, first_frame, tracks, threads, mp4_index);
+  try { return index_many(blob, file_begin, n_files, stream_ids, frames, max_frames, first_frame, tracks, threads, mp4_index); }
+  catch (const std::bad_alloc&) { return JAADB_E_NOMEM; }
+  catch (...) { return JAADB_E_INVALID; }
 }
 
 }  // extern "C"

@@ -27,6 +27,11 @@
 #ifndef K2_STEREO_MIN_BLOCKS
 #define K2_STEREO_MIN_BLOCKS 5
 #endif
+// shared-memory carve-out preference of the one- / two-channel filterbank kernel in percent (-1: the driver's choice).  The
+// kernel's table look-ups (IQ, windows, twiddles) live in what is left of the 256 KB for L1.
+#ifndef K2_CARVEOUT
+#define K2_CARVEOUT 100
+#endif
 
 namespace T = ::jaad_tables;
 using namespace jaadb;
@@ -206,6 +211,8 @@ struct jaadb_engine {
   SbrTablesDev sbr_tables;
   SbrConstTables sbr_const;
   bool sbr_ready = false;
+  std::vector<SbrElemDev> fresh_sbr_elem;   // a freshly constructed SBR object per element (init_sbr)
+  std::vector<PsChanDev> fresh_ps;          // a freshly constructed PSImpl
   SbrElemDev* d_sbr_elem = nullptr;   // [max_streams][2]
   SbrChanDev* d_sbr_chan = nullptr;   // [max_streams][kSbrChansPerStream]
   DevBuf<float> d_xg;                 // K4 tile workspace: the Xsbr matrices of one tile of frames (k4_sbr_process.cuh)
@@ -348,6 +355,28 @@ int init_tables(jaadb_engine* e) {
   if ((rc = e->upload(sfbs.data(), sfbs.size(), &D.sfb_of_short))) return rc;
   if ((rc = e->upload(JT(MDCT_TABLE_2048), T::MDCT_TABLE_2048_N, &D.mdct_long))) return rc;
   if ((rc = e->upload(JT(MDCT_TABLE_128), T::MDCT_TABLE_128_N, &D.mdct_short))) return rc;
+  {
+    // the pre-IFFT twiddles in the order the kernel's bit-reversed gather reads them (TablesDev::mdct_long_gather)
+    auto brev3 = [](int j) { return ((j & 1) << 2) | (j & 2) | ((j >> 2) & 1); };
+    auto brev6 = [](int t) { int r = 0; for (int b = 0; b < 6; ++b) r |= ((t >> b) & 1) << (5 - b); return r; };
+    const float* ml = JT(MDCT_TABLE_2048);
+    const float* ms = JT(MDCT_TABLE_128);
+    std::vector<float> gl(8 * 64 * 2), gs(8 * 8 * 2);
+    for (int j = 0; j < 8; ++j) {
+      for (int t = 0; t < 64; ++t) {
+        const int k = brev6(t) + 64 * brev3(j);
+        gl[(j * 64 + t) * 2] = ml[2 * k];
+        gl[(j * 64 + t) * 2 + 1] = ml[2 * k + 1];
+      }
+      for (int u = 0; u < 8; ++u) {
+        const int k = brev3(u) + 8 * brev3(j);
+        gs[(j * 8 + u) * 2] = ms[2 * k];
+        gs[(j * 8 + u) * 2 + 1] = ms[2 * k + 1];
+      }
+    }
+    if ((rc = e->upload(gl.data(), gl.size(), &D.mdct_long_gather))) return rc;
+    if ((rc = e->upload(gs.data(), gs.size(), &D.mdct_short_gather))) return rc;
+  }
   if ((rc = e->upload(JT(FFT_TABLE_512), T::FFT_TABLE_512_N, &D.fft512))) return rc;
   if ((rc = e->upload(JT(FFT_TABLE_64), T::FFT_TABLE_64_N, &D.fft64))) return rc;
   if ((rc = e->upload(JT(SINE_1024), 1024, &D.win_long[0]))) return rc;
@@ -485,6 +514,18 @@ int init_sbr(jaadb_engine* e) {
   K4C_ATTR(0); K4C_ATTR(1); K4C_ATTR(2);
 #undef K4C_ATTR
   cudaFuncSetAttribute(k5_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5_smem_bytes());
+  // a fresh SBR object per element: everything zero except Channel.prevEnvIsShort = -1 (Channel.java:51) and the null modes
+  e->fresh_sbr_elem.resize(2);
+  memset(e->fresh_sbr_elem.data(), 0, sizeof(SbrElemDev) * 2);
+  for (auto& el : e->fresh_sbr_elem) {
+    el.ch[0].prevEnvIsShort = -1; el.ch[1].prevEnvIsShort = -1;
+    el.ps.iid.mode = -1; el.ps.icc.mode = -1; el.ps.ipd.mode = -1; el.ps.opd.mode = -1;
+  }
+  // a fresh PSImpl (ps/PSImpl.java:64-94): everything zero except h11_prev = 1 and -- the constructor sets
+  // h12_prev[i][1] where it means h12_prev[i][0] (SURVEY A-14) -- the imaginary part of h12_prev = 1
+  e->fresh_ps.resize(1);
+  memset(e->fresh_ps.data(), 0, sizeof(PsChanDev));
+  for (auto& h : e->fresh_ps[0].h_prev) { h[0] = 1.0f; h[5] = 1.0f; }
   e->sbr_ready = true;
   return 0;
 }
@@ -542,35 +583,29 @@ int finish_open(jaadb_engine* e, StreamHost& s, int32_t* stream_id) {
     s.out_channels = 2;   // SCE: SBR1.process fills a second channel (PS or a copy), CPE: two channels
   }
   if (e->free_slots.empty()) { e->set_error("stream table full"); return JAADB_E_CAPACITY; }
-  int32_t slot = e->free_slots.back();
+  const int32_t slot = e->free_slots.back();
+  // fresh decoder state for the slot; the slot is only taken once all of it is in place
+  cudaError_t ce = cudaSuccess;
+  auto chk = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
+  if (s.sbr) {
+    // engine-owned templates (built once in init_sbr, read-only afterwards: engines on different threads share nothing)
+    chk(cudaMemcpyAsync(e->d_sbr_elem + (size_t)slot * 2, e->fresh_sbr_elem.data(), sizeof(SbrElemDev) * 2, cudaMemcpyHostToDevice, e->stream));
+    chk(cudaMemsetAsync(e->d_sbr_chan + (size_t)slot * kSbrChansPerStream, 0, sizeof(SbrChanDev) * kSbrChansPerStream, e->stream));
+    if (s.sbr > 1) chk(cudaMemcpyAsync(e->d_ps_chan + slot, e->fresh_ps.data(), sizeof(PsChanDev), cudaMemcpyHostToDevice, e->stream));
+  }
+  chk(cudaMemsetAsync(e->d_overlap + (size_t)slot * kMaxChannels * 1024, 0, sizeof(float) * kMaxChannels * 1024, e->stream));
+  StreamState fresh_state;
+  memset(&fresh_state, 0, sizeof fresh_state);
+  fresh_state.pns_state = kPnsSeed;   // ICStream.randomState (ICStream.java:26), one generator per stream
+  chk(cudaMemcpyAsync(e->d_sstate + slot, &fresh_state, sizeof fresh_state, cudaMemcpyHostToDevice, e->stream));
+  chk(cudaStreamSynchronize(e->stream));
+  if (ce != cudaSuccess) {
+    e->set_error(std::string("stream open: ") + cudaGetErrorString(ce));
+    return JAADB_E_CUDA;   // the slot stays in the free list
+  }
   e->free_slots.pop_back();
   s.open = true;
   e->streams[slot] = s;
-  if (s.sbr) {
-    // a fresh SBR object per element: everything zero except Channel.prevEnvIsShort = -1 (Channel.java:51)
-    static SbrElemDev fresh[2];
-    memset(fresh, 0, sizeof fresh);
-    for (auto& el : fresh) { el.ch[0].prevEnvIsShort = -1; el.ch[1].prevEnvIsShort = -1; el.ps.iid.mode = -1; el.ps.icc.mode = -1; }
-    CUDA_TRY(e, cudaMemcpyAsync(e->d_sbr_elem + (size_t)slot * 2, fresh, sizeof fresh, cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(e, cudaMemsetAsync(e->d_sbr_chan + (size_t)slot * kSbrChansPerStream, 0, sizeof(SbrChanDev) * kSbrChansPerStream, e->stream));
-    if (s.sbr > 1) {
-      // a fresh PSImpl (ps/PSImpl.java:64-94): everything zero except h11_prev = 1 and -- the constructor sets
-      // h12_prev[i][1] where it means h12_prev[i][0] (SURVEY A-14) -- the imaginary part of h12_prev = 1
-      static PsChanDev fresh_ps;
-      memset(&fresh_ps, 0, sizeof fresh_ps);
-      for (auto& h : fresh_ps.h_prev) { h[0] = 1.0f; h[5] = 1.0f; }
-      CUDA_TRY(e, cudaMemcpyAsync(e->d_ps_chan + slot, &fresh_ps, sizeof fresh_ps, cudaMemcpyHostToDevice, e->stream));
-    }
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  }
-  CUDA_TRY(e, cudaMemsetAsync(e->d_overlap + (size_t)slot * kMaxChannels * 1024, 0, sizeof(float) * kMaxChannels * 1024, e->stream));
-  {
-    StreamState fresh_state;
-    memset(&fresh_state, 0, sizeof fresh_state);
-    fresh_state.pns_state = kPnsSeed;   // ICStream.randomState (ICStream.java:26), one generator per stream
-    CUDA_TRY(e, cudaMemcpyAsync(e->d_sstate + slot, &fresh_state, sizeof fresh_state, cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  }
   *stream_id = slot;
   return JAADB_OK;
 }
@@ -599,6 +634,7 @@ int layout_pcm(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, const ui
     size[i] = sz;
     if (pcm_offsets) {
       if (pcm_offsets[i] & 3u) { e->set_error("pcm offsets must be 4-byte aligned"); return JAADB_E_INVALID; }
+      if (pcm_offsets[i] > UINT64_MAX - sz) { e->set_error("pcm offset out of range"); return JAADB_E_INVALID; }
       off[i] = pcm_offsets[i];
     } else {
       off[i] = pos;
@@ -633,7 +669,11 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
       e->set_error("frame refers to an unknown stream");
       return JAADB_E_NOSTREAM;
     }
-    if (d.offset + d.nbytes > blob_bytes) { e->set_error("frame exceeds the blob"); return JAADB_E_INVALID; }
+    // (overflow-safe: an offset close to 2^64 must not wrap past the test; 2^29 bytes keeps the bit positions in 32 bits)
+    if (d.nbytes > blob_bytes || d.offset > blob_bytes - d.nbytes || d.nbytes >= (1u << 29)) {
+      e->set_error("frame exceeds the blob");
+      return JAADB_E_INVALID;
+    }
     const StreamHost& s = e->streams[d.stream_id];
     FrameDev& f = fout[i];
     f.blob_off = d.offset;
@@ -798,7 +838,7 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
     // everything that depends on a stream's earlier frames, once per run
     const int bps = e->opts.pcm_format == JAADB_PCM_F32_PLANAR ? 4 : 2;
     k2_prepass_kernel<<<(B.n_runs + kK2PreWarps - 1) / kK2PreWarps, 32 * kK2PreWarps, 0, e->stream>>>(B.runs, B.n_runs, B.run_frames, B.fside, B.iside, e->d_sstate,
-                                                                     e->d_layouts, B.k2frames, B.pcm_bytes, bps,
+                                                                     e->d_layouts, B.pcm_off, B.k2frames, B.pcm_bytes, bps,
                                                                      e->opts.tns_mode == JAADB_TNS_ISO ? 1 : 0);
     ++*launches;
   }
@@ -818,7 +858,6 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
     A.overlap_all = e->d_overlap;
     A.overlap_stage = g.segmented ? B.ovl_stage : nullptr;
     A.pcm = B.pcm;
-    A.pcm_off = B.pcm_off;
     A.spec_tap = B.tap;
     A.core = B.core;
     A.layouts = e->d_layouts;
@@ -997,7 +1036,7 @@ int jaadb_engine_create(const jaadb_options* opts, jaadb_engine** out) {
 #define K2_ATTR(FMT)                                                                                                     \
   cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max);             \
   cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max2); \
-  cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+  if (K2_CARVEOUT >= 0) cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS>, cudaFuncAttributePreferredSharedMemoryCarveout, K2_CARVEOUT)
   K2_ATTR(0); K2_ATTR(1); K2_ATTR(2);
 #undef K2_ATTR
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) return fail(JAADB_E_CUDA);
@@ -1374,6 +1413,16 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   int rc = layout_pcm(e, frames, n_frames, pcm_offsets, off, size, &pcm_total);
   if (rc) { cudaStreamSynchronize(e->stream); return rc; }
   if (pcm_out && pcm_capacity < pcm_total) { cudaStreamSynchronize(e->stream); e->set_error("pcm buffer too small"); return JAADB_E_CAPACITY; }
+  // every descriptor is checked before the first kernel: a bad one in a later chunk must not leave the streams of the
+  // earlier chunks half-way through the call
+  for (uint32_t i = 0; i < n_frames; ++i) {
+    const jaadb_frame_desc& d = frames[i];
+    if (d.nbytes > blob_bytes || d.offset > blob_bytes - d.nbytes || d.nbytes >= (1u << 29)) {
+      cudaStreamSynchronize(e->stream);
+      e->set_error("frame exceeds the blob");
+      return JAADB_E_INVALID;
+    }
+  }
 
   // chunking: ~128 Ki frames per chunk, unless the caller's PCM placement is not monotonic over chunks
   uint32_t chunk = e->opts.chunk_frames ? e->opts.chunk_frames : 131072u;
@@ -1490,11 +1539,22 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
       r.sample_rate = (uint32_t)s.sample_rate;
     }
   };
+  // an error inside the pipelined loop: nothing may still be writing the caller's buffers when the call returns
+#define CUDA_TRY_SYNC(e, expr)                                                                 \
+  do {                                                                                         \
+    cudaError_t _err = (expr);                                                                 \
+    if (_err != cudaSuccess) {                                                                 \
+      (e)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_err));                    \
+      cudaStreamSynchronize((e)->stream);                                                      \
+      cudaStreamSynchronize(W.copy_stream);                                                    \
+      return JAADB_E_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
   for (size_t k = 0; k < ranges.size(); ++k) {
     const Range& r = ranges[k];
     const uint32_t n = r.i1 - r.i0;
     const int pb = (int)(k & 1);
-    if (k >= 2) CUDA_TRY(e, cudaEventSynchronize(W.desc_done[pb]));   // staging slot pb has been consumed
+    if (k >= 2) CUDA_TRY_SYNC(e, cudaEventSynchronize(W.desc_done[pb]));   // staging slot pb has been consumed
     const double t_wait = ms_now();
     ix.frames_out = W.h_frames[pb];
     ix.run_frames_out = W.h_run_frames[pb];
@@ -1512,44 +1572,45 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
       }
     }
     // the device descriptor buffers are still being read by the previous chunk's kernels: stream order protects them
-    CUDA_TRY(e, cudaMemcpyAsync(W.frames.p, W.h_frames[pb], sizeof(FrameDev) * n, cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(W.runs.p, W.h_runs[pb], sizeof(RunDev) * ix.runs.size(), cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(W.run_frames.p, W.h_run_frames[pb], sizeof(RunFrameDev) * n, cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(W.segs.p, W.h_segs[pb], sizeof(K2SegDev) * ix.segs.size(), cudaMemcpyHostToDevice, e->stream));
-    if (k >= 2) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, W.d2h_done[pb], 0));   // PCM buffer pb is free again
+    CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.frames.p, W.h_frames[pb], sizeof(FrameDev) * n, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.runs.p, W.h_runs[pb], sizeof(RunDev) * ix.runs.size(), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.run_frames.p, W.h_run_frames[pb], sizeof(RunFrameDev) * n, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.segs.p, W.h_segs[pb], sizeof(K2SegDev) * ix.segs.size(), cudaMemcpyHostToDevice, e->stream));
+    if (k >= 2) CUDA_TRY_SYNC(e, cudaStreamWaitEvent(e->stream, W.d2h_done[pb], 0));   // PCM buffer pb is free again
     if (!ix.sbr_runs.empty()) {
       // (pinned, double buffered like the other descriptors: the host goes on to index the next chunk)
       memcpy(W.h_sbr_runs[pb], ix.sbr_runs.data(), sizeof(SbrRunDev) * ix.sbr_runs.size());
       memcpy(W.h_k4_runs[pb], ix.k4_runs.data(), sizeof(K4RunDev) * ix.k4_runs.size());
-      CUDA_TRY(e, cudaMemcpyAsync(W.sbr_runs.p, W.h_sbr_runs[pb], sizeof(SbrRunDev) * ix.sbr_runs.size(), cudaMemcpyHostToDevice, e->stream));
-      CUDA_TRY(e, cudaMemcpyAsync(W.k4_runs.p, W.h_k4_runs[pb], sizeof(K4RunDev) * ix.k4_runs.size(), cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.sbr_runs.p, W.h_sbr_runs[pb], sizeof(SbrRunDev) * ix.sbr_runs.size(), cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.k4_runs.p, W.h_k4_runs[pb], sizeof(K4RunDev) * ix.k4_runs.size(), cudaMemcpyHostToDevice, e->stream));
     }
-    CUDA_TRY(e, cudaEventRecord(W.desc_done[pb], e->stream));   // staging slot pb is consumed once the copies above are done
+    CUDA_TRY_SYNC(e, cudaEventRecord(W.desc_done[pb], e->stream));   // staging slot pb is consumed once the copies above are done
     DecodeBufs B{W.blob.p, W.frames.p, W.fside.p + r.i0, W.iside.p, W.q.p, W.runs.p, (uint32_t)ix.runs.size(), W.run_frames.p,
                  W.k2frames.p, W.segs.p, W.ovl_stage.p, W.pcm[pb].p - r.lo,
                  W.pcm_off.p + r.i0, W.pcm_bytes.p + r.i0, nullptr, W.sbr_runs.p, W.k4_runs.p, W.sbr_frames.p, W.core.p, W.ps_frames.p,
                  ix.n_k4_plain, ix.k4_max_count, ix.k4_banks};
-    CUDA_TRY(e, launch_decode(e, ix.groups.data(), ix.groups.size(), n, (uint32_t)ix.sbr_runs.size(), (uint32_t)ix.k4_runs.size(), B,
+    CUDA_TRY_SYNC(e, launch_decode(e, ix.groups.data(), ix.groups.size(), n, (uint32_t)ix.sbr_runs.size(), (uint32_t)ix.k4_runs.size(), B,
                               nullptr, nullptr, &launches));
-    CUDA_TRY(e, cudaGetLastError());
-    CUDA_TRY(e, cudaEventRecord(W.k_done[pb], e->stream));
-    CUDA_TRY(e, cudaStreamWaitEvent(W.copy_stream, W.k_done[pb], 0));
+    CUDA_TRY_SYNC(e, cudaGetLastError());
+    CUDA_TRY_SYNC(e, cudaEventRecord(W.k_done[pb], e->stream));
+    CUDA_TRY_SYNC(e, cudaStreamWaitEvent(W.copy_stream, W.k_done[pb], 0));
     if (pcm_out && r.hi > r.lo)
-      CUDA_TRY(e, cudaMemcpyAsync(static_cast<uint8_t*>(pcm_out) + r.lo, W.pcm[pb].p, r.hi - r.lo, cudaMemcpyDeviceToHost, W.copy_stream));
+      CUDA_TRY_SYNC(e, cudaMemcpyAsync(static_cast<uint8_t*>(pcm_out) + r.lo, W.pcm[pb].p, r.hi - r.lo, cudaMemcpyDeviceToHost, W.copy_stream));
     if (results) {
-      CUDA_TRY(e, cudaMemcpyAsync(W.h_fside + r.i0, W.fside.p + r.i0, sizeof(FrameSide) * n, cudaMemcpyDeviceToHost, W.copy_stream));
-      CUDA_TRY(e, cudaMemcpyAsync(W.h_pcm_bytes + r.i0, W.pcm_bytes.p + r.i0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, W.copy_stream));
+      CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.h_fside + r.i0, W.fside.p + r.i0, sizeof(FrameSide) * n, cudaMemcpyDeviceToHost, W.copy_stream));
+      CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.h_pcm_bytes + r.i0, W.pcm_bytes.p + r.i0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, W.copy_stream));
     }
     // Chunk k is on its way; only now does the host wait for chunk k - 2 to be back (d2h_done[pb] still stands for it) and
     // convert its results, while the GPU works on chunks k - 1 and k.  (Waiting before indexing chunk k left the compute
     // stream idle for the host's indexing time once per chunk.)
     if (k >= 2 && results) {
-      CUDA_TRY(e, cudaEventSynchronize(W.d2h_done[pb]));
+      CUDA_TRY_SYNC(e, cudaEventSynchronize(W.d2h_done[pb]));
       convert_results(ranges[k - 2].i0, ranges[k - 2].i1);
     }
-    CUDA_TRY(e, cudaEventRecord(W.d2h_done[pb], W.copy_stream));
+    CUDA_TRY_SYNC(e, cudaEventRecord(W.d2h_done[pb], W.copy_stream));
     if (trace) fprintf(stderr, "[jaadb] chunk %zu: %u frames, waited until %.2f ms, indexed by %.2f, launched by %.2f\n", k, n, t_wait, t_idx, ms_now());
   }
+#undef CUDA_TRY_SYNC
   if (trace) fprintf(stderr, "[jaadb] all chunks submitted at %.2f ms\n", ms_now());
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   if (trace) fprintf(stderr, "[jaadb] kernels done at %.2f ms\n", ms_now());

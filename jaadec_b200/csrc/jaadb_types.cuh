@@ -121,14 +121,17 @@ struct RunFrameDev {
 
 // The same frame as K2 sees it: everything that depends on the stream's earlier frames is resolved by the pre-pass
 // (k2_prepass_kernel), so the filterbank kernel can start anywhere in a run.
-struct __align__(16) K2FrameDev {
+struct __align__(32) K2FrameDev {
   uint32_t frame;
   uint32_t ics_base;
   // [7:0] channel slot c goes through the filterbank   [15:8] windowShape[PREVIOUS] of slot c   [23:16] windowShape[CURRENT]
   // [24] the frame yields PCM   [25] JAAD reached SyntacticElements.process   [26] ISO TNS to apply   [27] noise bands present
   uint32_t flags;
   uint32_t pns_state;  // PNS generator state when the frame's parse starts
+  uint64_t pcm_off;    // where the frame's PCM goes (a copy of pcm_off[frame]: one load level instead of two in K2's loop)
+  uint64_t pad;
 };
+static_assert(sizeof(K2FrameDev) == 32, "K2FrameDev layout");
 constexpr uint32_t kK2Emit = 1u << 24, kK2Parsed = 1u << 25, kK2Tns = 1u << 26, kK2Pns = 1u << 27;
 
 // A piece of a run for one K2 CTA: frames [first, first + count) of run `run` (positions inside the run).  One segment per
@@ -161,6 +164,11 @@ struct TablesDev {
   const uint8_t* sfb_of_short;   // [12][128]
   const float* mdct_long;        // [512][2]
   const float* mdct_short;       // [64][2]
+  // the same twiddles in the order K2's pre-IFFT gather reads them (bit-reversed, FFT.java:51-61): entry [j * 64 + t] of
+  // the long table = mdct_long[bitrev6(t) + 64 * brev3(j)], entry [j * 8 + u] of the short one = mdct_short[brev3(u) + 8 * brev3(j)]
+  // -- the 64 threads of a channel then read consecutive 8-byte entries instead of one 32-byte sector each
+  const float* mdct_long_gather;   // [8][64][2]
+  const float* mdct_short_gather;  // [8][8][2]
   const float* fft512;           // [512][3]
   const float* fft64;            // [64][2]
   const float* win_long[2];      // sine, kbd [1024]

@@ -38,7 +38,7 @@ constexpr int kK2StageBytesPerCh = 2048 + (int)sizeof(IcsSide);   // q[1024] int
 
 __host__ __device__ constexpr size_t k2_smem_bytes(int nch, int out_ch, bool planar_pcm) {
   return sizeof(float) * (2 * 256 + 2 * 32 + (size_t)nch * kK2ChFloats) + (size_t)nch * kK2StageBytesPerCh + 16 +
-         (planar_pcm ? 0 : sizeof(int16_t) * 1024 * (size_t)out_ch);
+         (planar_pcm ? sizeof(uint32_t) * 512 * (size_t)nch : sizeof(int16_t) * 1024 * (size_t)out_ch);
 }
 
 // ISO TNS tables (JAADB_TNS_ISO): tools/TNSTables.java:10-25 in TNS_TABLES order {0_3, 0_4, 1_3, 1_4}, and
@@ -350,8 +350,8 @@ constexpr int kK2PreWarps = 4;
 __global__ void __launch_bounds__(32 * kK2PreWarps)
 k2_prepass_kernel(const RunDev* __restrict__ runs, uint32_t n_runs, const RunFrameDev* __restrict__ run_frames,
                   FrameSide* __restrict__ fside, const IcsSide* __restrict__ iside, StreamState* __restrict__ sstate,
-                  const LayoutDev* __restrict__ layouts, K2FrameDev* __restrict__ out, uint32_t* __restrict__ pcm_bytes_out,
-                  int bytes_per_sample, int tns_iso) {
+                  const LayoutDev* __restrict__ layouts, const uint64_t* __restrict__ pcm_off, K2FrameDev* __restrict__ out,
+                  uint32_t* __restrict__ pcm_bytes_out, int bytes_per_sample, int tns_iso) {
   const uint32_t r = blockIdx.x * kK2PreWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= n_runs) return;
@@ -380,10 +380,12 @@ k2_prepass_kernel(const RunDev* __restrict__ runs, uint32_t n_runs, const RunFra
     RunFrameDev rf{0u, 0u};
     uint4 fsw = make_uint4(0, 0, 0, 0);   // status, tags | n_elements << 16 | n_started << 24, sbr_bit_off[2]
     uint32_t draws = 0;
+    uint64_t poff = 0;
     if (valid) {
       rf = run_frames[run.first + it];
       fsw = *reinterpret_cast<const uint4*>(fside + rf.frame);
       draws = fside[rf.frame].pns_draws;
+      poff = pcm_off[rf.frame];
     }
     // Element objects are per (type, instance tag) in JAAD (StreamState::tags).  An element that shows another tag than
     // the stream's first one for that element, or that the layout does not have, addresses objects this stream does not
@@ -448,7 +450,9 @@ k2_prepass_kernel(const RunDev* __restrict__ runs, uint32_t n_runs, const RunFra
     }
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
     if (valid) {
-      *reinterpret_cast<uint4*>(out + run.first + it) = make_uint4(rf.frame, rf.ics_base, flags, total ? pns_jump(pns, incl - draws) : pns);
+      uint4* o = reinterpret_cast<uint4*>(out + run.first + it);
+      o[0] = make_uint4(rf.frame, rf.ics_base, flags, total ? pns_jump(pns, incl - draws) : pns);
+      o[1] = make_uint4((uint32_t)poff, (uint32_t)(poff >> 32), 0u, 0u);
       if (!run.sbr) pcm_bytes_out[rf.frame] = emit ? frame_bytes : 0u;
     }
     if (total) pns = pns_jump(pns, total);
@@ -486,7 +490,6 @@ struct K2Args {
   float* overlap_all;
   float* overlap_stage;         // segmented runs: [run][kMaxChannels][1024], moved into overlap_all by k2_commit_kernel; else null
   uint8_t* pcm;
-  const uint64_t* pcm_off;
   float* spec_tap;
   float* core;
   const LayoutDev* layouts;
@@ -507,7 +510,8 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
   int16_t* s_q = reinterpret_cast<int16_t*>(s_ch + nch * kK2ChFloats);
   IcsSide* s_side = reinterpret_cast<IcsSide*>(s_q + nch * 1024);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_side + nch);
-  int16_t* s_pcm = reinterpret_cast<int16_t*>(s_bar + 2);  // [1024][out_ch] (s16 formats, more than two channels)
+  int16_t* s_pcm = reinterpret_cast<int16_t*>(s_bar + 2);  // s16 formats: [1024][out_ch] interleaved (more than two channels)
+                                                           // or, kPlanarPcm, [nch][512] words = sample pairs (i, i+1) of a channel
 
   const K2SegDev seg = A.segs[blockIdx.x];
   const RunDev run = A.runs[seg.run];
@@ -559,6 +563,8 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
   // to give nothing and costs a resident CTA per SM
   const float2* mdct_long2 = reinterpret_cast<const float2*>(T.mdct_long);
   const float2* mdct_short2 = reinterpret_cast<const float2*>(T.mdct_short);
+  const float2* mdct_long_g = reinterpret_cast<const float2*>(T.mdct_long_gather);
+  const float2* mdct_short_g = reinterpret_cast<const float2*>(T.mdct_short_gather);
 
   // persistent state in: overlap
   float* g_ovl = A.overlap_all + ((size_t)run.stream_slot * kMaxChannels + c) * 1024;
@@ -582,7 +588,6 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
   const uint32_t pkB0 = subchunk_consts(T, sf_index, iB), pkB1 = subchunk_consts(T, sf_index, iB + 4);
 
   K2FrameDev cur = kf[it0];
-  uint64_t poff_pf = A.pcm_off[cur.frame];
   __syncthreads();   // twiddles, overlap and the barrier's initialisation are visible
 
   for (uint32_t it = it0; it < it_end; ++it) {
@@ -590,17 +595,14 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
     const uint32_t ics_base = cur.ics_base;
     const uint32_t flags = cur.flags;
     const uint32_t pns_state = cur.pns_state;
-    const uint64_t poff = poff_pf;
+    const uint64_t poff = cur.pcm_off;
     const bool have_next = it + 1 < it_end;
     const bool warm = it < seg.first;                         // re-run for the overlap only
     const bool emit = (flags & kK2Emit) != 0 && !warm;        // the frame yields PCM
     const bool parsed = (flags & kK2Parsed) != 0;             // JAAD reached SyntacticElements.process
     const bool run_ch = ((flags >> c) & 1u) != 0;             // this thread's channel goes through the filterbank
     const int shape_prev = (int)((flags >> (8 + c)) & 1u), shape_cur = (int)((flags >> (16 + c)) & 1u);
-    if (have_next) {
-      cur = kf[it + 1];
-      poff_pf = A.pcm_off[cur.frame];
-    }
+    if (have_next) cur = kf[it + 1];
     // the frame's quantised coefficients and side information have landed in the stage
     mbar_wait(s_bar, (it - it0) & 1u);
     const int ws = s_side[c].window_sequence;
@@ -722,7 +724,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
           const int k = kb + 64 * brev3(j);
           const float x0 = my_spec[spec_addr(2 * k)];
           const float x1 = my_spec[spec_addr(1023 - 2 * k)];
-          const float2 cs = __ldg(mdct_long2 + k);
+          const float2 cs = __ldg(mdct_long_g + j * 64 + t);   // = mdct_long2[k]
           a[j].im = (x0 * cs.x) + (x1 * cs.y);
           a[j].re = (x1 * cs.x) - (x0 * cs.y);
         }
@@ -734,7 +736,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
           const int k = kb + 8 * brev3(j);                     // bitrev6(8*(t&7)+j)
           const float x0 = my_spec[spec_addr(128 * w + 2 * k)];
           const float x1 = my_spec[spec_addr(128 * w + 127 - 2 * k)];
-          const float2 cs = __ldg(mdct_short2 + k);
+          const float2 cs = __ldg(mdct_short_g + j * 8 + (t & 7));   // = mdct_short2[k]
           a[j].im = (x0 * cs.x) + (x1 * cs.y);
           a[j].re = (x1 * cs.x) - (x0 * cs.y);
         }
@@ -854,7 +856,21 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
       const float* __restrict__ SWp = T.win_short[shape_prev];
       const float* __restrict__ SW = T.win_short[shape_cur];
       uint8_t* dst = A.pcm + poff;
-      uint32_t* my_pk = reinterpret_cast<uint32_t*>(my_spec);   // kPlanarPcm: sample pairs (i, i+1) of this channel, word i/2
+      uint32_t* my_pk = reinterpret_cast<uint32_t*>(s_pcm) + 512 * c;   // kPlanarPcm: sample pairs (i, i+1) of this channel, word i/2
+      // the long windows of the frame, requested together ahead of the loop (their L1 / L2 latency was the largest single
+      // stall of the kernel when each load sat right in front of its use): rising half for every long sequence but
+      // LONG_STOP, falling half for every one but LONG_START
+#ifndef K2_WIN_PREFETCH
+#define K2_WIN_PREFETCH 1
+#endif
+      const bool pre_rise = K2_WIN_PREFETCH && !is_short && ws != 3, pre_fall = K2_WIN_PREFETCH && !is_short && ws != 1;
+      float2 w_rise[8], w_fall[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = 2 * t + 128 * j;
+        if (pre_rise) w_rise[j] = __ldg(reinterpret_cast<const float2*>(LWp + i));
+        if (pre_fall) w_fall[j] = __ldg(reinterpret_cast<const float2*>(LW + 1022 - i));
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int i = 2 * t + 128 * j;
@@ -880,7 +896,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
               o0 = ov.x + (x10 * w.x); o1 = ov.y + (x11 * w.y);
             } else { o0 = ov.x + x10; o1 = ov.y + x11; }
           } else {
-            const float2 w = __ldg(reinterpret_cast<const float2*>(LWp + i));
+            const float2 w = K2_WIN_PREFETCH ? w_rise[j] : __ldg(reinterpret_cast<const float2*>(LWp + i));
             o0 = ov.x + (x10 * w.x); o1 = ov.y + (x11 * w.y);
           }
           if (ws == 1) {
@@ -891,7 +907,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
               n0 = x20 * w.y; n1 = x21 * w.x;
             } else { n0 = 0.f; n1 = 0.f; }
           } else {
-            const float2 w = __ldg(reinterpret_cast<const float2*>(LW + 1022 - i));
+            const float2 w = K2_WIN_PREFETCH ? w_fall[j] : __ldg(reinterpret_cast<const float2*>(LW + 1022 - i));
             n0 = x20 * w.y; n1 = x21 * w.x;
           }
         } else {
@@ -949,7 +965,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
           uint32_t pr = pcm_round16(o0) | (pcm_round16(o1) << 16);
           if (PCM_FORMAT == 1) pr = __byte_perm(pr, 0, 0x2301);
           if (kPlanarPcm) {
-            my_pk[t + 64 * j] = pr;   // (exchange 2 of this channel was consumed before the last channel barrier)
+            my_pk[t + 64 * j] = pr;   // (the copy-out of the previous frame finished before this frame's phase-1 barrier)
           } else {
             s_pcm[i * out_ch + c] = (int16_t)(pr & 0xFFFFu);
             s_pcm[(i + 1) * out_ch + c] = (int16_t)(pr >> 16);
@@ -962,8 +978,8 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
         uint32_t* d = reinterpret_cast<uint32_t*>(dst);
         if (kPlanarPcm) {
           // samples i..i+3 of both channels = words i/2, i/2+1 of the two planes (one plane twice when mono is duplicated)
-          const uint2* pl = reinterpret_cast<const uint2*>(s_ch);
-          const uint2* prr = reinterpret_cast<const uint2*>(s_ch + (nch == 2 ? kK2ChFloats : 0));
+          const uint2* pl = reinterpret_cast<const uint2*>(s_pcm);
+          const uint2* prr = pl + (nch == 2 ? 256 : 0);
           const bool al = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
           for (int i = tid; i < 256; i += nthreads) {
             const uint2 l = pl[i], r = prr[i];
@@ -972,7 +988,6 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
             if (al) reinterpret_cast<uint4*>(d)[i] = o;
             else { d[4 * i] = o.x; d[4 * i + 1] = o.y; d[4 * i + 2] = o.z; d[4 * i + 3] = o.w; }
           }
-          __syncthreads();   // the planes live where the next frame's spectrum goes
         } else {
           const int nwords = 1024 * out_ch / 2;   // 32-bit words
           const uint32_t* src = reinterpret_cast<const uint32_t*>(s_pcm);

@@ -1100,6 +1100,14 @@ k4c_synthesis_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const Run
     info[t] = f;
   }
   __syncthreads();
+  // a frame that failed yields no PCM: its slot of the output is zero-filled (first output channel's CTA, left bank)
+  if (!(PS && bank == 1) && out_ch == 0) {
+    for (int j = 0; j < nfr; ++j) {
+      if (info[j].kind != 0) continue;
+      uint32_t* d = reinterpret_cast<uint32_t*>(info[j].dst);
+      for (int i = t; i < kOutLen * n_out * (PCM_FORMAT == 2 ? 4 : 2) / 4; i += kK4cThreads) d[i] = 0u;
+    }
+  }
   if (t == 0) {
     int n = 0, first = -1;
     for (int j = 0; j < nfr; ++j)
