@@ -163,12 +163,19 @@ int jaadb_probe_sbr_asc(jaadb_engine* e, const uint8_t* asc, uint32_t asc_bytes,
 int jaadb_stream_close(jaadb_engine* e, int32_t stream_id);
 int jaadb_stream_get_info(const jaadb_engine* e, int32_t stream_id, jaadb_stream_info* info);
 
-/* ---- one-call decode: host buffers in, host PCM out ----------------------
+/* ---- one-call decode ------------------------------------------------------
  * Batched Decoder.decodeFrame (A/Decoder.java:89-121) + SampleBuffer.accept
  * (S/SampleBuffer.java:168-209).  Frames of one stream are applied in array
  * order; different streams are independent.  pcm_offsets[i] is the byte offset
  * of frame i's PCM inside pcm_out (NULL: frames are packed back to back in
- * array order, every frame taking its stream's full frame size).            */
+ * array order, every frame taking its stream's full frame size).
+ * `blob` and `pcm_out` may each be host memory (pinned or pageable) or memory of
+ * the engine's GPU (cudaMalloc / managed; detected with cudaPointerGetAttributes).
+ * A device pcm_out (4-byte aligned) is written by the kernels in place: the PCM
+ * never crosses PCIe, which is the mode for GPU-side consumers (resamplers,
+ * feature extraction, encoders).  `frames`, `pcm_offsets` and `results` are host
+ * arrays.  A frame that fails (results[i].status != 0) has pcm_bytes 0 and its
+ * slot zero-filled.                                                          */
 int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const jaadb_frame_desc* frames,
                  uint32_t n_frames, void* pcm_out, uint64_t pcm_capacity, const uint64_t* pcm_offsets,
                  jaadb_frame_result* results);
@@ -247,6 +254,13 @@ int64_t jaadb_mp4_index(const uint8_t* file, uint64_t nbytes, uint64_t blob_offs
 int64_t jaadb_mp4_index_many(const uint8_t* blob, const uint64_t* file_begin, uint32_t n_files, const int32_t* stream_ids,
                              jaadb_frame_desc* frames, uint64_t max_frames, uint64_t* first_frame,
                              jaadb_mp4_track* tracks, uint32_t threads);
+
+/* Reorders the stream-major table of the *_index_many calls frame-major: frame 0 of every stream, frame 1 of every stream,
+ * ... -- the order a live batch of concurrent streams arrives in, and the one that gives every chunk of jaadb_decode all
+ * streams to work on.  Per-stream order is kept, so both orders decode identically.  `out` has first_frame[n_streams] rows.
+ * Returns the number of rows, or a negative JAADB_E_* code.  (S/Main.java reads one file at a time; this is the batch glue.) */
+int64_t jaadb_frames_interleave(const jaadb_frame_desc* frames, const uint64_t* first_frame, uint32_t n_streams,
+                                jaadb_frame_desc* out, uint32_t threads);
 
 #ifdef __cplusplus
 }

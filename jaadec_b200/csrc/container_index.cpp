@@ -378,9 +378,43 @@ int64_t index_many(const uint8_t* blob, const uint64_t* stream_begin, uint32_t n
   return (int64_t)first[n_streams];
 }
 
+// Stream-major frame table -> frame-major ("tick") order: frame 0 of every stream, frame 1 of every stream, ...; a stream
+// that has ended simply drops out.  Rows of the result are independent, so they are filled on host threads.
+int64_t frames_interleave(const jaadb_frame_desc* in, const uint64_t* first_frame, uint32_t n_streams, jaadb_frame_desc* out,
+                          uint32_t threads) {
+  uint64_t longest = 0;
+  for (uint32_t s = 0; s < n_streams; ++s) {
+    if (first_frame[s + 1] < first_frame[s]) return JAADB_E_INVALID;
+    longest = std::max(longest, first_frame[s + 1] - first_frame[s]);
+  }
+  // row_start[f] = frames in rows before f = sum over streams of min(len, f)
+  std::vector<uint64_t> alive(longest + 1, 0), row_start(longest + 1, 0);
+  for (uint32_t s = 0; s < n_streams; ++s) alive[first_frame[s + 1] - first_frame[s]]++;   // histogram of lengths
+  uint64_t ge = n_streams;   // streams with len > f
+  for (uint64_t f = 0; f < longest; ++f) {
+    ge -= alive[f];          // streams of length exactly f are gone in row f
+    row_start[f + 1] = row_start[f] + ge;
+  }
+  const uint32_t n_rows = (uint32_t)std::min<uint64_t>(longest, 0xFFFFFFFFu);
+  parallel_streams(n_rows, threads, [&](uint32_t f) {
+    uint64_t pos = row_start[f];
+    for (uint32_t s = 0; s < n_streams; ++s)
+      if (first_frame[s + 1] - first_frame[s] > f) out[pos++] = in[first_frame[s] + f];
+  });
+  return (int64_t)row_start[longest];
+}
+
 }  // namespace
 
 extern "C" {
+
+int64_t jaadb_frames_interleave(const jaadb_frame_desc* frames, const uint64_t* first_frame, uint32_t n_streams,
+                                jaadb_frame_desc* out, uint32_t threads) {
+  if (!frames || !first_frame || !out) return JAADB_E_INVALID;
+  try { return frames_interleave(frames, first_frame, n_streams, out, threads); }
+  catch (const std::bad_alloc&) { return JAADB_E_NOMEM; }
+  catch (...) { return JAADB_E_INVALID; }
+}
 
 int64_t jaadb_adts_index(const uint8_t* data, uint64_t nbytes, uint64_t blob_offset, int32_t stream_id,
                          jaadb_frame_desc* frames, uint64_t max_frames, jaadb_adts_info* info) {

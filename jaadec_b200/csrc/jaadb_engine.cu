@@ -24,13 +24,15 @@
 #include "k3_sbr_parse.cuh"
 #include "k4_sbr_process.cuh"
 
+// resident CTAs per SM the one- / two-channel filterbank kernel is compiled for.  Measured on B200 (config 2): 4 (128
+// registers, no spills) 19.7 ms; 5 (96 registers, ~40 bytes of spills) 21.2 ms; 6 (80 registers) 29 ms.
 #ifndef K2_STEREO_MIN_BLOCKS
-#define K2_STEREO_MIN_BLOCKS 5
+#define K2_STEREO_MIN_BLOCKS 4
 #endif
 // shared-memory carve-out preference of the one- / two-channel filterbank kernel in percent (-1: the driver's choice).  The
 // kernel's table look-ups (IQ, windows, twiddles) live in what is left of the 256 KB for L1.
 #ifndef K2_CARVEOUT
-#define K2_CARVEOUT 100
+#define K2_CARVEOUT -1
 #endif
 
 namespace T = ::jaad_tables;
@@ -1296,7 +1298,7 @@ int jaadb_batch_upload(jaadb_batch* b, const uint8_t* blob, uint64_t blob_bytes)
   if (!b || (!blob && blob_bytes) || blob_bytes != b->blob_bytes) return JAADB_E_INVALID;
   jaadb_engine* e = b->e;
   cudaSetDevice(e->opts.device);
-  if (blob_bytes) CUDA_TRY(e, cudaMemcpyAsync(b->d_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, e->stream));
+  if (blob_bytes) CUDA_TRY(e, cudaMemcpyAsync(b->d_blob.p, blob, blob_bytes, cudaMemcpyDefault, e->stream));   // host or device source
   return JAADB_OK;
 }
 
@@ -1404,8 +1406,18 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   {
     const cudaError_t be = W.blob.ensure(blob_bytes + 64);
     if (be != cudaSuccess) { e->set_error(std::string("workspace allocation: ") + cudaGetErrorString(be)); return JAADB_E_NOMEM; }
-    if (blob_bytes) CUDA_TRY(e, cudaMemcpyAsync(W.blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, e->stream));
+    // (host or device source: a device blob is copied once inside HBM, which gives it the padding the bit readers rely on)
+    if (blob_bytes) CUDA_TRY(e, cudaMemcpyAsync(W.blob.p, blob, blob_bytes, cudaMemcpyDefault, e->stream));
     CUDA_TRY(e, cudaMemsetAsync(W.blob.p + blob_bytes, 0, 64, e->stream));
+  }
+  // A pcm_out in device memory (of this engine's GPU) is written by the kernels directly: no staging buffers, nothing on
+  // PCIe but the descriptors in and the per-frame results out.
+  bool out_dev = false;
+  if (pcm_out) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, pcm_out) == cudaSuccess) out_dev = pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged;
+    else cudaGetLastError();
+    if (out_dev && (reinterpret_cast<uintptr_t>(pcm_out) & 3u)) { cudaStreamSynchronize(e->stream); e->set_error("device pcm_out must be 4-byte aligned"); return JAADB_E_INVALID; }
   }
   std::vector<uint64_t>& off = e->scratch_off;
   std::vector<uint32_t>& size = e->scratch_size;
@@ -1443,7 +1455,7 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   }
   bool monotonic = true;
   for (size_t k = 1; k < ranges.size(); ++k) monotonic = monotonic && ranges[k].lo >= ranges[k - 1].hi;
-  if (!monotonic) { ranges.assign(1, Range{0, n_frames, 0, pcm_total}); chunk = n_frames; }
+  if (!monotonic && !out_dev) { ranges.assign(1, Range{0, n_frames, 0, pcm_total}); chunk = n_frames; }   // (device output needs no byte ranges)
   uint64_t max_pcm = 16;
   for (const auto& r : ranges) max_pcm = std::max(max_pcm, r.hi - r.lo);
 
@@ -1465,8 +1477,10 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   }
   cudaError_t ce = cudaSuccess;
   auto chk = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
-  chk(W.pcm[0].ensure(max_pcm));
-  if (ranges.size() > 1) chk(W.pcm[1].ensure(max_pcm));
+  if (!out_dev) {
+    chk(W.pcm[0].ensure(max_pcm));
+    if (ranges.size() > 1) chk(W.pcm[1].ensure(max_pcm));
+  }
   chk(W.frames.ensure(chunk));
   chk(W.fside.ensure(n_frames));
   chk(W.pcm_bytes.ensure(n_frames));
@@ -1576,7 +1590,7 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
     CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.runs.p, W.h_runs[pb], sizeof(RunDev) * ix.runs.size(), cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.run_frames.p, W.h_run_frames[pb], sizeof(RunFrameDev) * n, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.segs.p, W.h_segs[pb], sizeof(K2SegDev) * ix.segs.size(), cudaMemcpyHostToDevice, e->stream));
-    if (k >= 2) CUDA_TRY_SYNC(e, cudaStreamWaitEvent(e->stream, W.d2h_done[pb], 0));   // PCM buffer pb is free again
+    if (k >= 2 && !out_dev) CUDA_TRY_SYNC(e, cudaStreamWaitEvent(e->stream, W.d2h_done[pb], 0));   // PCM buffer pb is free again
     if (!ix.sbr_runs.empty()) {
       // (pinned, double buffered like the other descriptors: the host goes on to index the next chunk)
       memcpy(W.h_sbr_runs[pb], ix.sbr_runs.data(), sizeof(SbrRunDev) * ix.sbr_runs.size());
@@ -1586,7 +1600,7 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
     }
     CUDA_TRY_SYNC(e, cudaEventRecord(W.desc_done[pb], e->stream));   // staging slot pb is consumed once the copies above are done
     DecodeBufs B{W.blob.p, W.frames.p, W.fside.p + r.i0, W.iside.p, W.q.p, W.runs.p, (uint32_t)ix.runs.size(), W.run_frames.p,
-                 W.k2frames.p, W.segs.p, W.ovl_stage.p, W.pcm[pb].p - r.lo,
+                 W.k2frames.p, W.segs.p, W.ovl_stage.p, out_dev ? static_cast<uint8_t*>(pcm_out) : W.pcm[pb].p - r.lo,
                  W.pcm_off.p + r.i0, W.pcm_bytes.p + r.i0, nullptr, W.sbr_runs.p, W.k4_runs.p, W.sbr_frames.p, W.core.p, W.ps_frames.p,
                  ix.n_k4_plain, ix.k4_max_count, ix.k4_banks};
     CUDA_TRY_SYNC(e, launch_decode(e, ix.groups.data(), ix.groups.size(), n, (uint32_t)ix.sbr_runs.size(), (uint32_t)ix.k4_runs.size(), B,
@@ -1594,7 +1608,7 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
     CUDA_TRY_SYNC(e, cudaGetLastError());
     CUDA_TRY_SYNC(e, cudaEventRecord(W.k_done[pb], e->stream));
     CUDA_TRY_SYNC(e, cudaStreamWaitEvent(W.copy_stream, W.k_done[pb], 0));
-    if (pcm_out && r.hi > r.lo)
+    if (pcm_out && !out_dev && r.hi > r.lo)
       CUDA_TRY_SYNC(e, cudaMemcpyAsync(static_cast<uint8_t*>(pcm_out) + r.lo, W.pcm[pb].p, r.hi - r.lo, cudaMemcpyDeviceToHost, W.copy_stream));
     if (results) {
       CUDA_TRY_SYNC(e, cudaMemcpyAsync(W.h_fside + r.i0, W.fside.p + r.i0, sizeof(FrameSide) * n, cudaMemcpyDeviceToHost, W.copy_stream));

@@ -615,46 +615,45 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
       const IcsSide* sR = s_side + chB;
       float* specA = s_ch + chA * kK2ChFloats;
       float* specB = s_ch + chB * kK2ChFloats;
-      float a[8], b[8];
-      int cbA0, cbA1, cbB0, cbB1, idxA0, idxA1, idxB0, idxB1;
       // (the eight coefficients of a channel lie in one short window)
       const uint32_t grpA = sL->window_sequence == 2 ? short_group_of(sL, (int)((pkA0 >> 24) & 7u)) : 0u;
       const uint32_t grpB = sR->window_sequence == 2 ? short_group_of(sR, (int)((pkB0 >> 24) & 7u)) : 0u;
-      dequant4(sL, qL, grpA, pkA0, iA, T, a, cbA0, idxA0);
-      dequant4(sL, qL, grpA, pkA1, iA + 4, T, a + 4, cbA1, idxA1);
-      dequant4(sR, qR, grpB, pkB0, iB, T, b, cbB0, idxB0);
-      dequant4(sR, qR, grpB, pkB1, iB + 4, T, b + 4, cbB1, idxB1);
-      if (flags & kK2Pns) {
-        // generator state when this channel's parse began: the frame's + what the earlier channels took
-#define K2_PNS(S_, GRP, PK, I0, IDX, V, O)                                                                                        \
-  do {                                                                                                                           \
-    const int16_t* swb_ = (S_)->window_sequence == 2 ? (T.swb_short + sf_index * 17) : (T.swb_long + sf_index * 53);              \
-    const float4 n_ = pns_fill4(S_, GRP, PK, I0, IDX, pns_jump(pns_state, (S_)->pns_base), swb_, T.sf);                           \
-    V[O] = n_.x; V[O + 1] = n_.y; V[O + 2] = n_.z; V[O + 3] = n_.w;                                                               \
-  } while (0)
-        if (cbA0 == 13) K2_PNS(sL, grpA, pkA0, iA, idxA0, a, 0);
-        if (cbA1 == 13) K2_PNS(sL, grpA, pkA1, iA + 4, idxA1, a, 4);
-        if (cbB0 == 13) K2_PNS(sR, grpB, pkB0, iB, idxB0, b, 0);
-        if (cbB1 == 13) K2_PNS(sR, grpB, pkB1, iB + 4, idxB1, b, 4);
-#undef K2_PNS
-      }
-      if (el_nch == 2) {
-        const bool ms_on = sL->common_window && sL->ms_mask != 0;   // CPE.java:159-160
-        const bool ms_present = sL->ms_mask != 0;                   // CPE.isMSMaskPresent
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int cbL = h ? cbA1 : cbA0, cbR = h ? cbB1 : cbB0;
-          const int idxL = h ? idxA1 : idxA0, idxR = h ? idxB1 : idxB0;
+      const bool ms_on = el_nch == 2 && sL->common_window && sL->ms_mask != 0;   // CPE.java:159-160
+      const bool ms_present = sL->ms_mask != 0;                                   // CPE.isMSMaskPresent
+      // two rounds of four coefficients per channel, as a real loop: the kernel's instruction footprint per frame is what
+      // the instruction caches see (32 KB of L1.5), and this phase was a third of it when unrolled
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t pkA = h ? pkA1 : pkA0, pkB = h ? pkB1 : pkB0;
+        const int i0A = iA + 4 * h, i0B = iB + 4 * h;
+        float a[4], b[4];
+        int cbL, cbR, idxL, idxR;
+        dequant4(sL, qL, grpA, pkA, i0A, T, a, cbL, idxL);
+        dequant4(sR, qR, grpB, pkB, i0B, T, b, cbR, idxR);
+        if (flags & kK2Pns) {
+          // generator state when this channel's parse began: the frame's + what the earlier channels took
+          if (cbL == 13) {
+            const int16_t* swb_ = sL->window_sequence == 2 ? (T.swb_short + sf_index * 17) : (T.swb_long + sf_index * 53);
+            const float4 n_ = pns_fill4(sL, grpA, pkA, i0A, idxL, pns_jump(pns_state, sL->pns_base), swb_, T.sf);
+            a[0] = n_.x; a[1] = n_.y; a[2] = n_.z; a[3] = n_.w;
+          }
+          if (cbR == 13) {
+            const int16_t* swb_ = sR->window_sequence == 2 ? (T.swb_short + sf_index * 17) : (T.swb_long + sf_index * 53);
+            const float4 n_ = pns_fill4(sR, grpB, pkB, i0B, idxR, pns_jump(pns_state, sR->pns_base), swb_, T.sf);
+            b[0] = n_.x; b[1] = n_.y; b[2] = n_.z; b[3] = n_.w;
+          }
+        }
+        if (el_nch == 2) {
           // MS.process: both codebooks < NOISE_HCB, band flagged (MS.java:28-36).  Bands at or above max_sfb have
           // cb_out 0 and idx 0: they hold zeros, for which the butterfly is the identity up to the sign of zero --
           // JAAD never touches them, so they are excluded through the left channel's band test.
-          const bool in_band = ((sL->window_sequence == 2) ? (int)(((h ? pkA1 : pkA0) >> 6) & 15u) : (int)((h ? pkA1 : pkA0) & 63u)) < sL->max_sfb;
+          const bool in_band = ((sL->window_sequence == 2) ? (int)((pkA >> 6) & 15u) : (int)(pkA & 63u)) < sL->max_sfb;
           if (ms_on && cbL < 13 && cbR < 13 && in_band && ((sL->ms_used[idxL >> 3] >> (idxL & 7)) & 1)) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float l = a[4 * h + j], r = b[4 * h + j];
-              a[4 * h + j] = l + r;
-              b[4 * h + j] = l - r;
+              const float l = a[j], r = b[j];
+              a[j] = l + r;
+              b[j] = l - r;
             }
           }
           // IS.process: right channel bands with codebook 14/15 (IS.java:29-44)
@@ -664,20 +663,20 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
             float scale = __ldg(T.sf + sR->sf_idx[idxR]);
             if (sgn < 0) scale = -scale;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[4 * h + j] = a[4 * h + j] * scale;
+            for (int j = 0; j < 4; ++j) b[j] = a[j] * scale;
           }
         }
-      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        specA[spec_addr(iA + j)] = a[j];
-        specB[spec_addr(iB + j)] = b[j];
-      }
-      if (A.spec_tap && !warm && !(flags & kK2Tns)) {
-        float* tA = A.spec_tap + ((size_t)ics_base + chA) * 1024 + iA;
-        float* tB = A.spec_tap + ((size_t)ics_base + chB) * 1024 + iB;
+        for (int j = 0; j < 4; ++j) {
+          specA[spec_addr(i0A + j)] = a[j];
+          specB[spec_addr(i0B + j)] = b[j];
+        }
+        if (A.spec_tap && !warm && !(flags & kK2Tns)) {
+          float* tA = A.spec_tap + ((size_t)ics_base + chA) * 1024 + i0A;
+          float* tB = A.spec_tap + ((size_t)ics_base + chB) * 1024 + i0B;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { tA[j] = a[j]; tB[j] = b[j]; }
+          for (int j = 0; j < 4; ++j) { tA[j] = a[j]; tB[j] = b[j]; }
+        }
       }
     }
     if (flags & kK2Tns) {
@@ -857,21 +856,13 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
       const float* __restrict__ SW = T.win_short[shape_cur];
       uint8_t* dst = A.pcm + poff;
       uint32_t* my_pk = reinterpret_cast<uint32_t*>(s_pcm) + 512 * c;   // kPlanarPcm: sample pairs (i, i+1) of this channel, word i/2
-      // the long windows of the frame, requested together ahead of the loop (their L1 / L2 latency was the largest single
-      // stall of the kernel when each load sat right in front of its use): rising half for every long sequence but
-      // LONG_STOP, falling half for every one but LONG_START
-#ifndef K2_WIN_PREFETCH
-#define K2_WIN_PREFETCH 1
+      // (requesting all of a frame's window values ahead of this loop was measured: the 32 extra registers cost more -- spills at
+      //  96 registers, instruction-cache misses at 128 -- than the L1 latency they hide)
+#ifndef K2_P3_UNROLL
+#define K2_P3_UNROLL 8
 #endif
-      const bool pre_rise = K2_WIN_PREFETCH && !is_short && ws != 3, pre_fall = K2_WIN_PREFETCH && !is_short && ws != 1;
-      float2 w_rise[8], w_fall[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = 2 * t + 128 * j;
-        if (pre_rise) w_rise[j] = __ldg(reinterpret_cast<const float2*>(LWp + i));
-        if (pre_fall) w_fall[j] = __ldg(reinterpret_cast<const float2*>(LW + 1022 - i));
-      }
-#pragma unroll
+      constexpr int kP3Unroll = K2_P3_UNROLL;
+#pragma unroll kP3Unroll
       for (int j = 0; j < 8; ++j) {
         const int i = 2 * t + 128 * j;
         const float2 ov = *reinterpret_cast<const float2*>(my_ovl + i);
@@ -896,7 +887,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
               o0 = ov.x + (x10 * w.x); o1 = ov.y + (x11 * w.y);
             } else { o0 = ov.x + x10; o1 = ov.y + x11; }
           } else {
-            const float2 w = K2_WIN_PREFETCH ? w_rise[j] : __ldg(reinterpret_cast<const float2*>(LWp + i));
+            const float2 w = __ldg(reinterpret_cast<const float2*>(LWp + i));
             o0 = ov.x + (x10 * w.x); o1 = ov.y + (x11 * w.y);
           }
           if (ws == 1) {
@@ -907,7 +898,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
               n0 = x20 * w.y; n1 = x21 * w.x;
             } else { n0 = 0.f; n1 = 0.f; }
           } else {
-            const float2 w = K2_WIN_PREFETCH ? w_fall[j] : __ldg(reinterpret_cast<const float2*>(LW + 1022 - i));
+            const float2 w = __ldg(reinterpret_cast<const float2*>(LW + 1022 - i));
             n0 = x20 * w.y; n1 = x21 * w.x;
           }
         } else {

@@ -80,12 +80,14 @@ def mp4_index_many(blob, file_begin, stream_ids=None, threads: int = 0):
     return _many("jaadb_mp4_index_many", _lib.Mp4Track, blob, file_begin, stream_ids, threads)
 
 
-def interleave(frames: np.ndarray, first_frame: np.ndarray) -> np.ndarray:
+def interleave(frames: np.ndarray, first_frame: np.ndarray, out: np.ndarray | None = None, threads: int = 0) -> np.ndarray:
     """Reorder a stream-major frame table frame-major (frame 0 of every stream, frame 1 of every stream ...), the
     order a live batch of concurrent streams arrives in.  Per-stream order is preserved, so both decode identically."""
-    n = len(first_frame) - 1
-    cnt = np.diff(first_frame)
-    sid = np.repeat(np.arange(n), cnt)
-    k = np.arange(len(frames)) - np.repeat(first_frame[:-1], cnt)
-    order = np.lexsort((sid, k))
-    return frames[order]
+    lib = _lib.load()
+    frames = np.ascontiguousarray(frames, FRAME_DESC_DTYPE)
+    first = np.ascontiguousarray(first_frame, np.uint64)
+    out = np.empty(len(frames), FRAME_DESC_DTYPE) if out is None else out
+    n = lib.jaadb_frames_interleave(frames.ctypes.data, first.ctypes.data, len(first) - 1, out.ctypes.data, threads)
+    if n != len(frames):
+        raise EngineError("jaadb_frames_interleave failed: %d" % n)
+    return out

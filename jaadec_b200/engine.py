@@ -110,6 +110,24 @@ class Engine:
                                            pcm_out.nbytes, _ptr(pcm_offsets), _ptr(results)), "decode")
         return pcm_out, results
 
+    def decode_ptr(self, blob_ptr: int, blob_bytes: int, frames: np.ndarray, pcm_ptr: int, pcm_capacity: int,
+                   pcm_offsets: np.ndarray | None = None, results: np.ndarray | None = None):
+        """jaadb_decode on raw addresses: `blob_ptr` / `pcm_ptr` may point to host memory or to memory of the engine's GPU
+        (e.g. torch tensors' data_ptr()).  With a device pcm_ptr the kernels write the PCM in place and nothing but the
+        frame table and the per-frame results crosses PCIe.  Returns the results array."""
+        frames = np.ascontiguousarray(frames, FRAME_DESC_DTYPE)
+        if results is None:
+            results = np.zeros(len(frames), FRAME_RESULT_DTYPE)
+        if pcm_offsets is not None:
+            pcm_offsets = np.ascontiguousarray(pcm_offsets, np.uint64)
+        self._check(self._lib.jaadb_decode(self._h, blob_ptr, blob_bytes, _ptr(frames), len(frames), pcm_ptr, pcm_capacity,
+                                           _ptr(pcm_offsets), _ptr(results)), "decode")
+        return results
+
+    def packed_bytes(self, frames) -> int:
+        """Size of the PCM buffer jaadb_decode fills for `frames` when pcm_offsets is None."""
+        return self._packed_bytes(np.ascontiguousarray(frames, FRAME_DESC_DTYPE))
+
     def _packed_bytes(self, frames) -> int:
         per = 4 if self.pcm_format == PCM_F32_PLANAR else 2
         total = 0

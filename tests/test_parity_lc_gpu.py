@@ -379,3 +379,35 @@ def test_segmented_filterbank_is_bit_identical(label, cfg, n_streams, segment):
             else:
                 assert (s, f) == bad and res["pcm_bytes"][i] == 0 and not pcm[i * per:(i + 1) * per].any()
     eng.close()
+
+
+@pytest.mark.parametrize("cfg_no,n_frames", [(2, 30), (3, 20), (4, 20)])
+def test_device_resident_blob_and_pcm(cfg_no, n_frames):
+    """jaadb_decode with the blob and the PCM buffer in device memory (torch tensors): the kernels write the PCM in place
+    (no staging buffer, no PCIe transfer of PCM); same bytes as the host-buffer call and as the oracle, chunked
+    (chunks of 16 frames) and across two calls."""
+    import torch
+    cfg = gen.config(cfg_no, n_frames=n_frames, p_transient=0.3)
+    wl = Workload(cfg, 4, base_seed=gen.seed_for(cfg_no, 321), with_truth=False)
+    decs = wl.oracle_decoders()
+    engs = [Engine(max_streams=8, pcm_format=PCM_S16LE, chunk_frames=16) for _ in range(2)]
+    ids = [[e.open_adts(*wl.hdr, expect_sbr=cfg.sbr_mode) for _ in range(4)] for e in engs]
+    info = engs[0].stream_info(ids[0][0])
+    per = info.channels * info.sample_length * 2
+    d_blob = torch.from_numpy(wl.blob).cuda()
+    for lo, hi in ((0, 7), (7, n_frames)):
+        frames, index = wl.frame_table(ids[0], lo, hi)
+        n = len(frames)
+        d_pcm = torch.full((n * per,), 0x55, dtype=torch.uint8, device="cuda")
+        res_d = engs[0].decode_ptr(d_blob.data_ptr(), wl.blob.nbytes, frames, d_pcm.data_ptr(), d_pcm.numel())
+        torch.cuda.synchronize()
+        got_d = d_pcm.cpu().numpy()
+        frames_h, _ = wl.frame_table(ids[1], lo, hi)
+        got_h, res_h = engs[1].decode(wl.blob, frames_h)
+        assert np.array_equal(res_d["status"], res_h["status"]) and (res_d["status"] == 0).all()
+        assert np.array_equal(got_d, got_h)
+        for i, (s, f) in enumerate(index):
+            r = decs[s].decode_frame(wl.frame_bytes(s, f))
+            assert np.array_equal(got_d[i * per:(i + 1) * per].view(np.int16).reshape(info.sample_length, info.channels), r["s16"]), (s, f)
+    for e in engs:
+        e.close()
