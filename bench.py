@@ -1,23 +1,28 @@
 #!/usr/bin/env python3
 """Throughput benchmark of the batched AAC decode hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2] [--no-extras]
 
-A "step" is one pass of the hot path over one batch: every frame of S independent
-streams (default: BASELINE config 2, 4096 AAC-LC 48 kHz stereo streams x 469 frames = 10 s
-each).  `value` times the kernels with the batch resident in HBM; `e2e` times the public
-one-call API with host buffers (indexing + H2D + kernels + D2H inside the region).
-One process per GPU; streams shard across GPUs with no collective (weak scaling: S per GPU).
+A "step" is one pass of the hot path over one batch: every frame of S independent streams (default: BASELINE config 2,
+4096 AAC-LC 48 kHz stereo streams x 469 frames = 10 s each).
+  value       kernels only, batch resident in HBM (CUDA events on the engine's stream)
+  e2e         the public one-call API from container bytes in pinned host memory to PCM in pinned host memory: container
+              indexing (jaadb_adts_index_many / jaadb_mp4_index_many + jaadb_frames_interleave, reported as index_ms),
+              H2D, kernels, D2H, all inside the timed region
+  e2e_device  the same call with the container bytes and the PCM buffer in device memory (PCM never crosses PCIe)
+The default run (N = 1) appends a `configs` array with the other BASELINE configurations (1, 3, 4, 5) measured the same
+way, each for a few steps.  One process per GPU; streams shard across GPUs with no collective (weak scaling: S per GPU);
+with --gpus N > 1 the line also carries config 5 strong-scaled (16384 MP4 streams / N per GPU).
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -26,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SF_FREQ = [96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000]
-# algorithmic bytes per frame (SURVEY.md §8d): compressed in + s16 PCM out + overlap state read+write
+# algorithmic bytes per frame (SURVEY.md section 8d): compressed in + s16 PCM out + overlap state read+write
 # config 3 (HE-AAC v1 stereo): + 2048-sample stereo s16 out + this engine's SBR state read+write per frame
 # (2 x SbrChanDev 12480 B + SbrElemDev 3904 B of LIVE decoder state, jaadec_b200/csrc/sbr_types.cuh: the second copy of the
 # double-buffered synthesis history and the reference's never-cleared scratch arrays, which the engine keeps only to match
@@ -37,6 +42,20 @@ ALGO_BYTES = {1: lambda avg: avg + 4096 + 16384, 2: lambda avg: avg + 4096 + 163
               4: lambda avg: avg + 8192 + 8192 + 2 * (12480 + 3904 + 22240)}
 OUT_SAMPLES = {1: 1024, 2: 1024, 5: 1024, 3: 2048, 4: 2048}   # per frame and channel
 OUT_RATE_SHIFT = {1: 0, 2: 0, 5: 0, 3: 3, 4: 3}               # SBR doubles the rate: output sf index = core index - 3
+DEFAULT_STREAMS = {1: 1, 2: 4096, 3: 4096, 4: 8192, 5: 4096}
+DEFAULT_FRAMES = {1: 431, 2: 469, 3: 235, 4: 235, 5: 469}
+ASC_51 = bytes([0x11, 0xB0])
+NAMES = {1: "AAC-LC 44.1 kHz stereo ADTS, one 10 s stream, long windows only",
+         2: "AAC-LC 48 kHz stereo ADTS, mixed ONLY_LONG/EIGHT_SHORT, M/S, IS, TNS side info",
+         3: "HE-AAC v1 (SBR) ADTS 24 kHz core -> 48 kHz stereo: 32-band QMF analysis, HF generation/adjustment, 64-band synthesis",
+         4: "HE-AAC v2 (SBR+PS) ADTS mono 24 kHz core -> 48 kHz stereo: PS hybrid filterbank + decorrelation + mixing",
+         5: "AAC-LC 5.1 48 kHz MP4 files (mp4 demux path)"}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch at the default sizes, from the committed
+# `ncu --set full` captures (profiles/README.md names the file per entry); None where no capture exists
+NCU_TRAFFIC = {(2, "k2_filterbank_kernel"): 9.711e9 + 7.894e9}
+# what limits the dominant kernel according to those captures (issue-slot utilisation of the SM sub-partitions)
+NCU_LIMITER = {(2, "k2_filterbank_kernel"): {"limiter": "issue/latency (instruction fetch + L1 table look-ups), not HBM",
+                                             "issue_slot_frac": 0.52, "dram_frac": 0.10, "source": "profiles/r2_k2_filterbank_ncu_raw.txt"}}
 
 
 def read_peaks():
@@ -99,6 +118,7 @@ class ClockSampler:
 
 
 def make_workload(config_no, n_streams, n_frames, rank):
+    """The raw generator output (tests/test_full_size_gpu.py shares seeds and sizes with the benchmark through this)."""
     import gen
     cfg = gen.config(config_no, n_frames=n_frames)
     blob, offs, sizes, _ = gen.generate_many(cfg, gen.seed_for(config_no, rank * n_streams), n_streams)
@@ -116,15 +136,70 @@ def frame_table(offs, sizes, ids):
     return fr
 
 
-def cpu_baseline(cfg, blob, offs, sizes, asc, sample_streams, threads):
+class Workload:
+    """S synthetic streams of one BASELINE configuration as the container files a caller would hold: ADTS streams
+    (configs 1-4) or MP4 files (config 5) back to back in one blob."""
+
+    def __init__(self, config_no, n_streams, n_frames, seed_offset):
+        import gen
+        self.config_no = config_no
+        self.cfg = cfg = gen.config(config_no, n_frames=n_frames)
+        blob, offs, sizes, sb = gen.generate_many(cfg, gen.seed_for(config_no, seed_offset), n_streams)
+        self.n_streams, self.n_frames = offs.shape
+        self.sizes = sizes
+        self.asc = ASC_51 if config_no == 5 else None
+        starts = np.concatenate([[0], np.cumsum(sb)]).astype(np.int64)
+        if config_no == 5:
+            # the generator's raw frames (MP4 samples) of every stream wrapped into an MP4 file: moov (stsd/esds, stts, stsc,
+            # stsz, stco) + mdat, chunks of four samples
+            from gen import mp4 as genmp4
+            files = []
+            for s in range(self.n_streams):
+                files.append(genmp4.write_mp4((blob[starts[s]: starts[s + 1]], sizes[s]), ASC_51, 48000, 6)[0])
+            self.begin = np.concatenate([[0], np.cumsum([len(f) for f in files])]).astype(np.uint64)
+            self.blob = np.concatenate(files)
+            # for the CPU arm (which reads raw frames): where the samples sit inside the container blob
+            self.raw_blob, self.raw_offs = blob, offs
+        else:
+            self.begin = starts.astype(np.uint64)
+            self.blob = blob
+            self.raw_blob, self.raw_offs = blob, offs
+        self.out_rate = SF_FREQ[cfg.sf_index - OUT_RATE_SHIFT[config_no]]
+        self.audio_s = self.n_streams * self.n_frames * float(OUT_SAMPLES[config_no]) / self.out_rate
+
+    def index(self, ids, threads=0, out=None, scratch=None):
+        """Container bytes -> frame table in frame-major (tick) order, with the product's native indexers."""
+        from jaadec_b200 import demux
+        if self.config_no == 5:
+            frames, first, _ = demux.mp4_index_many(self.blob, self.begin, ids, threads, out=scratch)
+        else:
+            frames, first, _ = demux.adts_index_many(self.blob, self.begin, ids, threads, out=scratch)
+        return demux.interleave(frames, first, out=out, threads=threads)
+
+    def open_streams(self, eng):
+        cfg = self.cfg
+        if self.asc is not None:
+            return [eng.open_asc(self.asc) for _ in range(self.n_streams)]
+        return [eng.open_adts(2, cfg.sf_index, cfg.chan_cfg, expect_sbr=cfg.sbr_mode) for _ in range(self.n_streams)]
+
+
+def cpu_baseline(wl, sample_streams, threads):
+    """The CPU arm: the C++ restatement of JAAD (oracle/, kind "port"), one Decoder per stream on `threads` host threads."""
     import oracle
-    S = min(sample_streams, offs.shape[0])
-    F = offs.shape[1]
+    S = min(sample_streams, wl.n_streams)
+    F = wl.n_frames
     first = np.arange(S + 1, dtype=np.int64) * F
-    kw = dict(asc=asc) if asc is not None else dict(hdr=(2, cfg.sf_index, cfg.chan_cfg))
-    sec, samples, errors = oracle.decode_streams(blob, first, offs[:S], sizes[:S], threads=threads, **kw)
-    rate = SF_FREQ[cfg.sf_index - (3 if cfg.sbr_mode else 0)]
-    return (samples / rate) / sec, sec, S, errors
+    kw = dict(asc=wl.asc) if wl.asc is not None else dict(hdr=(2, wl.cfg.sf_index, wl.cfg.chan_cfg))
+    sec, samples, errors = oracle.decode_streams(wl.raw_blob, first, wl.raw_offs[:S], wl.sizes[:S], threads=threads, **kw)
+    return (samples / wl.out_rate) / sec, sec, S, errors
+
+
+def workload_config(config_no, wl, streams_per_gpu):
+    return {"workload": "BASELINE config %d: %s" % (config_no, NAMES[config_no]), "streams_per_gpu": int(streams_per_gpu),
+            "frames_per_stream": int(wl.n_frames), "avg_frame_bytes": float(wl.sizes.mean()), "pcm": "s16le interleaved",
+            "container": "mp4" if config_no == 5 else "adts",
+            "l2_policy": "inputs+outputs per step far larger than the 126 MB L2 (no flush needed)" if wl.n_streams >= 1024
+            else "L2 flushed between steps (256 MB memset)", "parallelism": "streams sharded, no collective"}
 
 
 def run_reference(args, rank, world):
@@ -133,23 +208,25 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    cfg, blob, offs, sizes = make_workload(args.config, min(args.streams, args.ref_streams or 64 * cores), args.frames, 0)
-    asc = bytes([0x11, 0xB0]) if args.config == 5 else None
+    n_streams = min(args.streams, args.ref_streams or 64 * cores)
+    wl = Workload(args.config, n_streams, args.frames, 0)
     vals = []
     for _ in range(args.warmup):
-        cpu_baseline(cfg, blob, offs, sizes, asc, max(8, offs.shape[0] // 8), cores)
+        cpu_baseline(wl, max(8, wl.n_streams // 8), cores)
     t_all = 0.0
     for _ in range(args.steps):
-        v, sec, S, err = cpu_baseline(cfg, blob, offs, sizes, asc, offs.shape[0], cores)
+        v, sec, S, err = cpu_baseline(wl, wl.n_streams, cores)
         vals.append(v)
         t_all += sec
     value = float(np.mean(vals))
-    sample = "%d streams x %d frames of config %d per step" % (offs.shape[0], args.frames, args.config)
+    sample = "%d streams x %d frames of config %d per step (a bounded sample of the %d-stream workload: per-stream work is the same)" % (
+        wl.n_streams, args.frames, args.config, args.streams)
+    cfg_out = workload_config(args.config, wl, wl.n_streams)
+    cfg_out["streams_in_full_workload"] = int(args.streams)
     line = {
         "impl": "reference", "metric": "decoded audio-sec/sec (x realtime)", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_all / max(args.steps, 1), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, cfg, sizes),
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_out,
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -157,14 +234,136 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, cfg, sizes):
-    names = {1: "AAC-LC 44.1 kHz stereo ADTS, long windows only", 2: "AAC-LC 48 kHz stereo, mixed ONLY_LONG/EIGHT_SHORT, M/S, IS, TNS side info",
-             3: "HE-AAC v1 (SBR) 24 kHz core -> 48 kHz stereo: 32-band QMF analysis, HF generation/adjustment, 64-band synthesis",
-             4: "HE-AAC v2 (SBR+PS) mono 24 kHz core -> 48 kHz stereo: PS hybrid filterbank + decorrelation + mixing",
-             5: "AAC-LC 5.1 48 kHz raw frames (MP4 samples)"}
-    return {"workload": "BASELINE config %d: %s" % (args.config, names.get(args.config, "?")), "streams_per_gpu": args.streams,
-            "frames_per_stream": args.frames, "avg_frame_bytes": float(sizes.mean()), "pcm": "s16le interleaved",
-            "l2_policy": "inputs+outputs per step far larger than the 126 MB L2 (no flush needed)", "parallelism": "streams sharded, no collective"}
+def measure(config_no, n_streams, n_frames, steps, warmup, local_rank, rank, world, *, want_e2e=True, want_clocks=False, barrier=None,
+            allreduce_max=None, seed_offset=None):
+    """One configuration on this rank's GPU: value (resident), e2e (host buffers, indexing inside), e2e_device, roofline."""
+    import torch
+
+    from jaadec_b200 import Engine, FLAG_PROFILE, FRAME_RESULT_DTYPE, PCM_S16LE
+
+    barrier = barrier or (lambda: torch.cuda.synchronize())
+    allreduce_max = allreduce_max or (lambda x: x)
+    wl = Workload(config_no, n_streams, n_frames, rank * n_streams if seed_offset is None else seed_offset)
+    S, F = wl.n_streams, wl.n_frames
+    eng = Engine(device=local_rank, max_streams=S, pcm_format=PCM_S16LE, flags=FLAG_PROFILE)
+    ids = np.asarray(wl.open_streams(eng), np.int32)
+    frames = wl.index(ids)
+    assert len(frames) == S * F, "the indexer must find every generated frame"
+    flush = None
+    if S < 1024:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # small batches: L2 flushed between steps
+
+    # ---- value: kernels only, batch resident in HBM ------------------------------------------------
+    batch = eng.batch(frames, wl.blob.nbytes)
+    batch.upload(wl.blob)
+    batch.sync()
+    for _ in range(warmup):
+        batch.decode()
+    batch.sync()
+    sampler = ClockSampler(local_rank) if want_clocks else None
+    if sampler:
+        sampler.start()
+    parse_ms, fb_ms, sbr_ms, dev_ms, launches = [], [], [], [], 0
+    barrier()
+    t0 = time.perf_counter()
+    flush_s = 0.0
+    for _ in range(steps):
+        if flush is not None:
+            tf = time.perf_counter()
+            flush.zero_()
+            torch.cuda.synchronize()
+            flush_s += time.perf_counter() - tf
+        batch.decode()
+        t = batch.timings()   # CUDA events on the engine's stream (synchronises the step)
+        parse_ms.append(t.parse_ms)
+        fb_ms.append(t.filterbank_ms)
+        sbr_ms.append(t.sbr_ms)
+        dev_ms.append(t.total_ms)
+        launches += t.launches
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop() if sampler else None
+    elapsed = allreduce_max(t1 - t0 - flush_s)
+    value = world * wl.audio_s * steps / elapsed
+    _, results = batch.download(want_results=True)
+    n_bad = int((results["status"] != 0).sum())
+    pcm_bytes = batch.pcm_bytes
+    batch.close()
+
+    out = {"value": value, "ms_per_step": 1000.0 * elapsed / steps, "gpu_launches": int(launches), "bad_frames": n_bad, "clocks": clocks,
+           "device_ms_per_step": float(np.mean(dev_ms))}
+
+    # ---- e2e: container bytes in pinned host memory -> index -> one-call decode -> PCM in pinned host memory -----------
+    if want_e2e:
+        blob_pin = torch.empty(wl.blob.nbytes, dtype=torch.uint8, pin_memory=True)
+        blob_pin.numpy()[:] = wl.blob
+        pcm_pin = torch.empty(pcm_bytes, dtype=torch.uint8, pin_memory=True)
+        bp, pp = blob_pin.numpy(), pcm_pin.numpy()
+        wl_blob_saved, wl.blob = wl.blob, bp            # the indexer reads the same (pinned) bytes the engine uploads
+        res_buf = np.zeros(len(frames), FRAME_RESULT_DTYPE)   # reused across calls, like the PCM and the frame-table buffers
+        tbl, scratch = np.empty(len(frames), frames.dtype), np.empty(len(frames), frames.dtype)
+        for _ in range(min(warmup, 2)):
+            eng.decode(bp, wl.index(ids, out=tbl, scratch=scratch), pcm_out=pp, results=res_buf)
+        barrier()
+        idx_s = 0.0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ti = time.perf_counter()
+            fr = wl.index(ids, out=tbl, scratch=scratch)
+            idx_s += time.perf_counter() - ti
+            _, res = eng.decode(bp, fr, pcm_out=pp, results=res_buf)
+            chk = int(res["status"][0])  # read the step's result on the host
+        barrier()
+        t1 = time.perf_counter()
+        e_elapsed = allreduce_max(t1 - t0)
+        out["e2e"] = {"value": world * wl.audio_s * steps / e_elapsed, "unit": "audio-s/s",
+                      "h2d_bytes_per_step": int(wl.blob.nbytes + frames.nbytes * 3), "d2h_bytes_per_step": int(pcm_bytes + len(frames) * 36),
+                      "ms_per_step": 1000.0 * e_elapsed / steps, "index_ms": 1000.0 * idx_s / steps,
+                      "indexer": "jaadb_mp4_index_many" if config_no == 5 else "jaadb_adts_index_many"}
+        # ---- e2e_device: the same call, container bytes and PCM in device memory (results still come back to the host)
+        d_blob = torch.from_numpy(wl_blob_saved).cuda()
+        d_pcm = torch.empty(pcm_bytes, dtype=torch.uint8, device="cuda")
+        for _ in range(min(warmup, 2)):
+            eng.decode_ptr(d_blob.data_ptr(), d_blob.numel(), fr, d_pcm.data_ptr(), d_pcm.numel(), results=res_buf)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = eng.decode_ptr(d_blob.data_ptr(), d_blob.numel(), fr, d_pcm.data_ptr(), d_pcm.numel(), results=res_buf)
+            chk = int(res["status"][0])
+        barrier()
+        t1 = time.perf_counter()
+        d_elapsed = allreduce_max(t1 - t0)
+        out["e2e_device"] = {"value": world * wl.audio_s * steps / d_elapsed, "unit": "audio-s/s", "ms_per_step": 1000.0 * d_elapsed / steps,
+                             "h2d_bytes_per_step": int(frames.nbytes * 3), "d2h_bytes_per_step": int(len(frames) * 36),
+                             "note": "container bytes and PCM stay in HBM (jaadb_decode with device pointers)"}
+        wl.blob = wl_blob_saved
+        del blob_pin, pcm_pin, d_blob, d_pcm, bp, pp
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------------
+    peak, peak_kind = read_peaks()
+    avg_frame = float(wl.sizes.mean())
+    algo_bytes = ALGO_BYTES[config_no](avg_frame) * S * F
+    k1, k2, k4 = float(np.mean(parse_ms)), float(np.mean(fb_ms)), float(np.mean(sbr_ms))
+    k4_name = "k4 pipeline, tiled: k4a_analysis + k4b_hf" + (" + k5_ps" if wl.cfg.sbr_mode > 1 else "") + " + k4c_synthesis"
+    dom_name, dom_ms = max((("k1_parse_kernel" + ("+k3_sbr_parse_kernel" if wl.cfg.sbr_mode else ""), k1), ("k2_filterbank_kernel", k2),
+                            (k4_name, k4)), key=lambda kv: kv[1])
+    achieved = algo_bytes / (dom_ms * 1e-3) / 1e9
+    full_size = S == DEFAULT_STREAMS[config_no] and F == DEFAULT_FRAMES[config_no]
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (burst copy)", "unit": "GB/s",
+                "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((config_no, dom_name)) if full_size else None,
+                "algo_bytes_per_launch": algo_bytes,
+                "kernel_ms": {"k1_parse(+k3_sbr_parse)": k1, "k2_prepass+k2_filterbank": k2, "k4_k5_sbr_ps_pipeline": k4,
+                              "step_device_total": float(np.mean(dev_ms))},
+                "whole_path_frac": algo_bytes / (float(np.mean(dev_ms)) * 1e-3) / 1e9 / peak}
+    if (config_no, dom_name) in NCU_LIMITER:
+        roofline["ncu"] = NCU_LIMITER[(config_no, dom_name)]
+    out["roofline"] = roofline
+    out["config"] = workload_config(config_no, wl, S)
+    eng.close()
+    del flush
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out, wl
 
 
 def main():
@@ -174,18 +373,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
-    ap.add_argument("--streams", type=int, default=4096)
+    ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--ref-streams", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `configs` array (the other BASELINE configurations)")
     args = ap.parse_args()
-    if args.config == 1 and args.streams == 4096:
-        args.streams = 1
+    if not args.streams:
+        args.streams = DEFAULT_STREAMS[args.config]
     if not args.frames:
-        args.frames = {1: 431, 2: 469, 3: 235, 4: 235, 5: 469}[args.config]
-    if args.config == 4 and args.streams == 4096:
-        args.streams = 8192
+        args.frames = DEFAULT_FRAMES[args.config]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,8 +395,6 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from jaadec_b200 import Engine, FLAG_PROFILE, FRAME_RESULT_DTYPE, PCM_S16LE
-
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -208,110 +404,57 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    cfg, blob, offs, sizes = make_workload(args.config, args.streams, args.frames, rank)
-    S, F = offs.shape
-    rate = SF_FREQ[cfg.sf_index - OUT_RATE_SHIFT[args.config]]
-    asc = bytes([0x11, 0xB0]) if args.config == 5 else None
-    audio_s_per_step = S * F * float(OUT_SAMPLES[args.config]) / rate
-
-    eng = Engine(device=local_rank, max_streams=S, pcm_format=PCM_S16LE, flags=FLAG_PROFILE)
-    ids = [eng.open_asc(asc) if asc else eng.open_adts(2, cfg.sf_index, cfg.chan_cfg, expect_sbr=cfg.sbr_mode) for _ in range(S)]
-    frames = frame_table(offs, sizes, ids)
-
-    # ---- value: kernels only, batch resident in HBM ------------------------------------------------
-    batch = eng.batch(frames, blob.nbytes)
-    batch.upload(blob)
-    batch.sync()
-    for _ in range(args.warmup):
-        batch.decode()
-    batch.sync()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    parse_ms, fb_ms, sbr_ms, dev_ms, launches = [], [], [], [], 0
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        batch.decode()
-        t = batch.timings()   # CUDA events on the engine's stream (synchronises the step)
-        parse_ms.append(t.parse_ms)
-        fb_ms.append(t.filterbank_ms)
-        sbr_ms.append(t.sbr_ms)
-        dev_ms.append(t.total_ms)
-        launches += t.launches
-    barrier()
-    t1 = time.perf_counter()
-    clocks = sampler.stop()
-    elapsed = t1 - t0
-    if world > 1:
-        tt = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed = float(tt.item())
-    value = world * audio_s_per_step * args.steps / elapsed
-    _, results = batch.download(want_results=True)
-    n_bad = int((results["status"] != 0).sum())
-    pcm_bytes = batch.pcm_bytes
-    batch.close()
-
-    # ---- e2e: the public one-call API with pinned host buffers, copies inside the timed region --------
-    e2e = None
-    if not args.no_e2e:
-        blob_pin = torch.empty(blob.nbytes, dtype=torch.uint8, pin_memory=True)
-        blob_pin.numpy()[:] = blob
-        pcm_pin = torch.empty(pcm_bytes, dtype=torch.uint8, pin_memory=True)
-        bp, pp = blob_pin.numpy(), pcm_pin.numpy()
-        res_buf = np.zeros(len(frames), FRAME_RESULT_DTYPE)   # reused across calls, like the PCM buffer
-        for _ in range(min(args.warmup, 2)):
-            eng.decode(bp, frames, pcm_out=pp, results=res_buf)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            _, res = eng.decode(bp, frames, pcm_out=pp, results=res_buf)
-            chk = int(res["status"][0])  # read the step's result on the host
-        barrier()
-        t1 = time.perf_counter()
-        e_elapsed = t1 - t0
+    def allreduce_max(x):
         if world > 1:
-            tt = torch.tensor([e_elapsed], device="cuda", dtype=torch.float64)
+            tt = torch.tensor([x], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e_elapsed = float(tt.item())
-        e2e = {"value": world * audio_s_per_step * args.steps / e_elapsed, "unit": "audio-s/s",
-               "h2d_bytes_per_step": int(blob.nbytes + frames.nbytes * 3), "d2h_bytes_per_step": int(pcm_bytes + len(frames) * 24),
-               "ms_per_step": 1000.0 * e_elapsed / args.steps}
+            return float(tt.item())
+        return x
 
-    # ---- roofline of the dominant kernel ----------------------------------------------------------------
-    peak, peak_kind = read_peaks()
-    avg_frame = float(sizes.mean())
-    algo_bytes = ALGO_BYTES[args.config](avg_frame) * S * F
-    k1, k2, k4 = float(np.mean(parse_ms)), float(np.mean(fb_ms)), float(np.mean(sbr_ms))
-    k4_name = "k4 pipeline, tiled: k4a_analysis + k4b_hf" + (" + k5_ps" if cfg.sbr_mode > 1 else "") + " + k4c_synthesis"
-    dom_name, dom_ms = max((("k1_parse_kernel" + ("+k3_sbr_parse_kernel" if cfg.sbr_mode else ""), k1), ("k2_filterbank_kernel", k2),
-                            (k4_name, k4)), key=lambda kv: kv[1])
-    achieved = algo_bytes / (dom_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch, from the committed ncu --set full capture
-    # of this very workload (profiles/r1_k1_k2_final_ncu_raw.txt); only known for the default size of config 2
-    traffic = None
-    if args.config == 2 and S == 4096 and F == 469 and dom_name == "k2_filterbank_kernel":
-        traffic = 9.531168e9 + 7.880068e9
-    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (burst copy)", "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "algo_bytes_per_launch": algo_bytes,
-                "kernel_ms": {"k1_parse(+k3_sbr_parse)": k1, "k2_filterbank": k2, "k4_k5_sbr_ps_pipeline": k4, "step_device_total": float(np.mean(dev_ms))},
-                "whole_path_frac": algo_bytes / (float(np.mean(dev_ms)) * 1e-3) / 1e9 / peak}
-
+    kw = dict(barrier=barrier, allreduce_max=allreduce_max)
+    head, wl = measure(args.config, args.streams, args.frames, args.steps, args.warmup, local_rank, rank, world,
+                       want_e2e=not args.no_e2e, want_clocks=True, **kw)
     line = {
-        "metric": "decoded audio-sec/sec (x realtime)", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, sizes), "clocks": clocks,
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "bad_frames": n_bad,
+        "metric": "decoded audio-sec/sec (x realtime)", "value": head["value"], "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": head["config"], "clocks": head["clocks"],
+        "e2e": head.get("e2e"), "e2e_device": head.get("e2e_device"), "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
+        "bad_frames": head["bad_frames"],
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample_streams = min(S, 96 * cores)
-        v, sec, Ss, err = cpu_baseline(cfg, blob, offs, sizes, asc, sample_streams, cores)
+        sample_streams = min(wl.n_streams, 96 * cores)
+        v, sec, Ss, err = cpu_baseline(wl, sample_streams, cores)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                "sample": "%d of the %d streams x %d frames, %.1f s wall, C++ restatement of JAAD (no JVM in the image)" % (Ss, S, F, sec)}
+                                "sample": "%d of the %d streams x %d frames, %.1f s wall, C++ restatement of JAAD (no JVM in the image)" % (
+                                    Ss, wl.n_streams, wl.n_frames, sec)}
+    del wl
+    gc.collect()
+
+    # ---- the other BASELINE configurations, a few steps each (N = 1 only: their pinned PCM buffers are tens of GB) ------
+    if not args.no_extras and args.config == 2 and args.streams == DEFAULT_STREAMS[2]:
+        extras = []
+        if world == 1:
+            for c in (1, 3, 4, 5):
+                r, _ = measure(c, DEFAULT_STREAMS[c], DEFAULT_FRAMES[c], 3, 3, local_rank, rank, world, want_e2e=not args.no_e2e, **kw)
+                extras.append({"config_no": c, "config": r["config"], "value": r["value"], "unit": "audio-s/s", "ms_per_step": r["ms_per_step"],
+                               "device_ms_per_step": r["device_ms_per_step"],
+                               "e2e": r.get("e2e"), "e2e_device": r.get("e2e_device"), "roofline": r["roofline"], "bad_frames": r["bad_frames"],
+                               "gpu_launches": r["gpu_launches"], "steps": 3, "warmup": 3})
+                _ = None
+                gc.collect()
+        else:
+            # BASELINE config 5 as it is stated: 16384 MP4 streams in total, sharded over the GPUs (strong scaling), kernels only
+            total = 16384
+            per = total // world
+            if per <= 8192:
+                r, _ = measure(5, per, DEFAULT_FRAMES[5], 2, 3, local_rank, rank, world, want_e2e=False, seed_offset=rank * per, **kw)
+                extras.append({"config_no": 5, "scaling": "strong", "total_streams": total, "config": r["config"], "value": r["value"],
+                               "unit": "audio-s/s", "ms_per_step": r["ms_per_step"], "roofline": r["roofline"], "bad_frames": r["bad_frames"],
+                               "steps": 2, "warmup": 3})
+        line["configs"] = extras
     if rank == 0:
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

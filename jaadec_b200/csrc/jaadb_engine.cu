@@ -24,10 +24,10 @@
 #include "k3_sbr_parse.cuh"
 #include "k4_sbr_process.cuh"
 
-// resident CTAs per SM the one- / two-channel filterbank kernel is compiled for.  Measured on B200 (config 2): 4 (128
-// registers, no spills) 19.7 ms; 5 (96 registers, ~40 bytes of spills) 21.2 ms; 6 (80 registers) 29 ms.
+// resident CTAs per SM the one- / two-channel filterbank kernel is compiled for.  Measured on B200 (config 2, round 2
+// session D): 5 (96 registers, 12 bytes of spills) 18.9 ms; 4 (128 registers) 19.6 ms; 6 does not fit the shared memory.
 #ifndef K2_STEREO_MIN_BLOCKS
-#define K2_STEREO_MIN_BLOCKS 4
+#define K2_STEREO_MIN_BLOCKS 5
 #endif
 // shared-memory carve-out preference of the one- / two-channel filterbank kernel in percent (-1: the driver's choice).  The
 // kernel's table look-ups (IQ, windows, twiddles) live in what is left of the 256 KB for L1.

@@ -128,8 +128,10 @@ struct __align__(32) K2FrameDev {
   // [24] the frame yields PCM   [25] JAAD reached SyntacticElements.process   [26] ISO TNS to apply   [27] noise bands present
   uint32_t flags;
   uint32_t pns_state;  // PNS generator state when the frame's parse starts
-  uint64_t pcm_off;    // where the frame's PCM goes (a copy of pcm_off[frame]: one load level instead of two in K2's loop)
-  uint64_t pad;
+  uint64_t pcm_off;    // where the frame's PCM goes (a copy of pcm_off[frame])
+  uint32_t next_ics_base;  // ics_base of the run's next frame: K2 asks the TMA unit for that frame's coefficients while this
+                           // record is all it holds
+  uint32_t pad;
 };
 static_assert(sizeof(K2FrameDev) == 32, "K2FrameDev layout");
 constexpr uint32_t kK2Emit = 1u << 24, kK2Parsed = 1u << 25, kK2Tns = 1u << 26, kK2Pns = 1u << 27;

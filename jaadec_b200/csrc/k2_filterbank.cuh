@@ -34,10 +34,10 @@ constexpr int kThreadsPerChannel = 64;
 constexpr int kSpecStride = 1152;
 constexpr int kXchgStride = 8 * 72;     // 8 blocks of 8x8 complex, rows padded to 9; 8 short windows of 64 + 8
 constexpr int kK2ChFloats = kSpecStride + 1024 + 2 * kXchgStride;
-constexpr int kK2StageBytesPerCh = 2048 + (int)sizeof(IcsSide);   // q[1024] int16 + IcsSide of the next frame
+constexpr int kK2StageBytesPerCh = 2048 + (int)sizeof(IcsSide);   // q[1024] int16 + IcsSide of the next frame (+ its K2FrameDev, once)
 
 __host__ __device__ constexpr size_t k2_smem_bytes(int nch, int out_ch, bool planar_pcm) {
-  return sizeof(float) * (2 * 256 + 2 * 32 + (size_t)nch * kK2ChFloats) + (size_t)nch * kK2StageBytesPerCh + 16 +
+  return sizeof(float) * (2 * 256 + 2 * 32 + (size_t)nch * kK2ChFloats) + (size_t)nch * kK2StageBytesPerCh + sizeof(K2FrameDev) + 16 +
          (planar_pcm ? sizeof(uint32_t) * 512 * (size_t)nch : sizeof(int16_t) * 1024 * (size_t)out_ch);
 }
 
@@ -387,6 +387,7 @@ k2_prepass_kernel(const RunDev* __restrict__ runs, uint32_t n_runs, const RunFra
       draws = fside[rf.frame].pns_draws;
       poff = pcm_off[rf.frame];
     }
+    const uint32_t next_ics = (it + 1 < run.count) ? run_frames[run.first + it + 1].ics_base : 0u;
     // Element objects are per (type, instance tag) in JAAD (StreamState::tags).  An element that shows another tag than
     // the stream's first one for that element, or that the layout does not have, addresses objects this stream does not
     // own: it leaves them alone, the frame is reported as JAADB_ST_LAYOUT -- and the stream's own elements of that frame
@@ -452,7 +453,7 @@ k2_prepass_kernel(const RunDev* __restrict__ runs, uint32_t n_runs, const RunFra
     if (valid) {
       uint4* o = reinterpret_cast<uint4*>(out + run.first + it);
       o[0] = make_uint4(rf.frame, rf.ics_base, flags, total ? pns_jump(pns, incl - draws) : pns);
-      o[1] = make_uint4((uint32_t)poff, (uint32_t)(poff >> 32), 0u, 0u);
+      o[1] = make_uint4((uint32_t)poff, (uint32_t)(poff >> 32), next_ics, 0u);
       if (!run.sbr) pcm_bytes_out[rf.frame] = emit ? frame_bytes : 0u;
     }
     if (total) pns = pns_jump(pns, total);
@@ -509,7 +510,8 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
   float* s_ch = s_fft_tw + 2 * 256 + 2 * 32;
   int16_t* s_q = reinterpret_cast<int16_t*>(s_ch + nch * kK2ChFloats);
   IcsSide* s_side = reinterpret_cast<IcsSide*>(s_q + nch * 1024);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_side + nch);
+  K2FrameDev* s_kf = reinterpret_cast<K2FrameDev*>(s_side + nch);   // the staged frame's record (16-byte aligned: 400 B per side)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_kf + 1);
   int16_t* s_pcm = reinterpret_cast<int16_t*>(s_bar + 2);  // s16 formats: [1024][out_ch] interleaved (more than two channels)
                                                            // or, kPlanarPcm, [nch][512] words = sample pairs (i, i+1) of a channel
 
@@ -540,12 +542,14 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
   }
   const uint32_t it_end = seg.first + seg.count;
   const uint32_t stage_bytes = (uint32_t)nch * 2048u, side_bytes = (uint32_t)nch * (uint32_t)sizeof(IcsSide);
+  constexpr uint32_t kf_bytes = (uint32_t)sizeof(K2FrameDev);
   if (tid == 0) {
     mbar_init(s_bar, 1);
-    const K2FrameDev f0 = kf[it0];
-    mbar_expect_tx(s_bar, stage_bytes + side_bytes);
-    tma_bulk_g2s(s_q, A.qall + (size_t)f0.ics_base * 1024, stage_bytes, s_bar);
-    tma_bulk_g2s(s_side, A.iside + f0.ics_base, side_bytes, s_bar);
+    const uint32_t ics0 = kf[it0].ics_base;
+    mbar_expect_tx(s_bar, stage_bytes + side_bytes + kf_bytes);
+    tma_bulk_g2s(s_q, A.qall + (size_t)ics0 * 1024, stage_bytes, s_bar);
+    tma_bulk_g2s(s_side, A.iside + ics0, side_bytes, s_bar);
+    tma_bulk_g2s(s_kf, kf + it0, kf_bytes, s_bar);
   }
 
   // twiddles used by the radix-2 stages: roots[k*m] with k*m < length/2
@@ -587,24 +591,24 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
   const uint32_t pkA0 = subchunk_consts(T, sf_index, iA), pkA1 = subchunk_consts(T, sf_index, iA + 4);
   const uint32_t pkB0 = subchunk_consts(T, sf_index, iB), pkB1 = subchunk_consts(T, sf_index, iB + 4);
 
-  K2FrameDev cur = kf[it0];
   __syncthreads();   // twiddles, overlap and the barrier's initialisation are visible
 
   for (uint32_t it = it0; it < it_end; ++it) {
-    const uint32_t f = cur.frame;
-    const uint32_t ics_base = cur.ics_base;
-    const uint32_t flags = cur.flags;
-    const uint32_t pns_state = cur.pns_state;
-    const uint64_t poff = cur.pcm_off;
+    // the frame's record, quantised coefficients and side information have landed in the stage
+    mbar_wait(s_bar, (it - it0) & 1u);
+    const uint4 kf0 = reinterpret_cast<const uint4*>(s_kf)[0], kf1 = reinterpret_cast<const uint4*>(s_kf)[1];
+    const uint32_t f = kf0.x;
+    const uint32_t ics_base = kf0.y;
+    const uint32_t flags = kf0.z;
+    const uint32_t pns_state = kf0.w;
+    const uint64_t poff = (uint64_t)kf1.x | ((uint64_t)kf1.y << 32);
+    const uint32_t next_ics_base = kf1.z;
     const bool have_next = it + 1 < it_end;
     const bool warm = it < seg.first;                         // re-run for the overlap only
     const bool emit = (flags & kK2Emit) != 0 && !warm;        // the frame yields PCM
     const bool parsed = (flags & kK2Parsed) != 0;             // JAAD reached SyntacticElements.process
     const bool run_ch = ((flags >> c) & 1u) != 0;             // this thread's channel goes through the filterbank
     const int shape_prev = (int)((flags >> (8 + c)) & 1u), shape_cur = (int)((flags >> (16 + c)) & 1u);
-    if (have_next) cur = kf[it + 1];
-    // the frame's quantised coefficients and side information have landed in the stage
-    mbar_wait(s_bar, (it - it0) & 1u);
     const int ws = s_side[c].window_sequence;
 
     if (run_ch) {   // (the channels of an element run together)
@@ -698,9 +702,10 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
     __syncthreads();   // spectra complete; every thread is done with the stage
     // ---- the next frame comes in while this one is transformed
     if (tid == 0 && have_next) {
-      mbar_expect_tx(s_bar, stage_bytes + side_bytes);
-      tma_bulk_g2s(s_q, A.qall + (size_t)cur.ics_base * 1024, stage_bytes, s_bar);
-      tma_bulk_g2s(s_side, A.iside + cur.ics_base, side_bytes, s_bar);
+      mbar_expect_tx(s_bar, stage_bytes + side_bytes + kf_bytes);
+      tma_bulk_g2s(s_q, A.qall + (size_t)next_ics_base * 1024, stage_bytes, s_bar);
+      tma_bulk_g2s(s_side, A.iside + next_ics_base, side_bytes, s_bar);
+      tma_bulk_g2s(s_kf, kf + it + 1, kf_bytes, s_bar);
     }
     if (!parsed) {
       // the frame produced no PCM; overlap untouched (Decoder.java:96-98).  Its slot of the output is zero-filled.
@@ -862,9 +867,20 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
 #define K2_P3_UNROLL 8
 #endif
       constexpr int kP3Unroll = K2_P3_UNROLL;
+      // long windows: the values of round j + 1 are requested before round j computes (the loads sat right in front of their
+      // use behind the sequence branches: the largest long-scoreboard stall of the kernel)
+      const bool pre_rise = !is_short && ws != 3, pre_fall = !is_short && ws != 1;
+      float2 w_rise_n = make_float2(0.f, 0.f), w_fall_n = make_float2(0.f, 0.f);
+      if (pre_rise) w_rise_n = __ldg(reinterpret_cast<const float2*>(LWp + 2 * t));
+      if (pre_fall) w_fall_n = __ldg(reinterpret_cast<const float2*>(LW + 1022 - 2 * t));
 #pragma unroll kP3Unroll
       for (int j = 0; j < 8; ++j) {
         const int i = 2 * t + 128 * j;
+        const float2 w_rise = w_rise_n, w_fall = w_fall_n;
+        if (j < 7) {
+          if (pre_rise) w_rise_n = __ldg(reinterpret_cast<const float2*>(LWp + i + 128));
+          if (pre_fall) w_fall_n = __ldg(reinterpret_cast<const float2*>(LW + 1022 - i - 128));
+        }
         const float2 ov = *reinterpret_cast<const float2*>(my_ovl + i);
         float o0, o1, n0, n1;
         if (!is_short) {
@@ -887,7 +903,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
               o0 = ov.x + (x10 * w.x); o1 = ov.y + (x11 * w.y);
             } else { o0 = ov.x + x10; o1 = ov.y + x11; }
           } else {
-            const float2 w = __ldg(reinterpret_cast<const float2*>(LWp + i));
+            const float2 w = w_rise;
             o0 = ov.x + (x10 * w.x); o1 = ov.y + (x11 * w.y);
           }
           if (ws == 1) {
@@ -898,7 +914,7 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
               n0 = x20 * w.y; n1 = x21 * w.x;
             } else { n0 = 0.f; n1 = 0.f; }
           } else {
-            const float2 w = __ldg(reinterpret_cast<const float2*>(LW + 1022 - i));
+            const float2 w = w_fall;
             n0 = x20 * w.y; n1 = x21 * w.x;
           }
         } else {

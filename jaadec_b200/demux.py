@@ -50,7 +50,7 @@ def asc_of(track: _lib.Mp4Track) -> bytes:
     return bytes(track.asc[: track.asc_bytes])
 
 
-def _many(fn, info_cls, blob, begin, stream_ids, threads):
+def _many(fn, info_cls, blob, begin, stream_ids, threads, out=None):
     lib = _lib.load()
     a = _u8(blob)
     begin = np.ascontiguousarray(begin, np.uint64)
@@ -60,6 +60,12 @@ def _many(fn, info_cls, blob, begin, stream_ids, threads):
     infos = (info_cls * max(n_streams, 1))()
     f = getattr(lib, fn)
     idp = None if ids is None else ids.ctypes.data
+    if out is not None:
+        # a caller-owned table (steady-state use: the frame count of a batch is known): one call counts and fills
+        total = f(a.ctypes.data, begin.ctypes.data, n_streams, idp, out.ctypes.data, len(out), first.ctypes.data, infos, threads)
+        if total < 0 or total > len(out):
+            raise EngineError("%s failed: %d (table holds %d rows)" % (fn, total, len(out)))
+        return out[:total], first.astype(np.int64), infos
     total = f(a.ctypes.data, begin.ctypes.data, n_streams, idp, None, 0, first.ctypes.data, infos, threads)
     if total < 0:
         raise EngineError("%s failed: %d" % (fn, total))
@@ -69,15 +75,15 @@ def _many(fn, info_cls, blob, begin, stream_ids, threads):
     return frames, first.astype(np.int64), list(infos)[:n_streams]
 
 
-def adts_index_many(blob, stream_begin, stream_ids=None, threads: int = 0):
+def adts_index_many(blob, stream_begin, stream_ids=None, threads: int = 0, out=None):
     """Index n ADTS streams stored back to back in `blob` (stream s = blob[begin[s]:begin[s+1]]) on host threads.
 
-    Returns (frames stream-major, first_frame[n+1], infos)."""
-    return _many("jaadb_adts_index_many", _lib.AdtsInfo, blob, stream_begin, stream_ids, threads)
+    Returns (frames stream-major, first_frame[n+1], infos).  `out`: a FRAME_DESC_DTYPE array to fill instead of a new one."""
+    return _many("jaadb_adts_index_many", _lib.AdtsInfo, blob, stream_begin, stream_ids, threads, out)
 
 
-def mp4_index_many(blob, file_begin, stream_ids=None, threads: int = 0):
-    return _many("jaadb_mp4_index_many", _lib.Mp4Track, blob, file_begin, stream_ids, threads)
+def mp4_index_many(blob, file_begin, stream_ids=None, threads: int = 0, out=None):
+    return _many("jaadb_mp4_index_many", _lib.Mp4Track, blob, file_begin, stream_ids, threads, out)
 
 
 def interleave(frames: np.ndarray, first_frame: np.ndarray, out: np.ndarray | None = None, threads: int = 0) -> np.ndarray:

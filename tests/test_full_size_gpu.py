@@ -25,6 +25,8 @@ pytestmark = pytest.mark.gpu
 
 # (BASELINE config, streams, frames per stream, staged-call cuts, SBR tile of the staged engine)
 FULL = [
+    # config 1: ONE 10 s stream -- the filterbank kernel cuts its 431 frames into segments of a few frames, one CTA each
+    (1, 1, 431, (0, 100, 101, 431), 0),
     (2, 4096, 469, (0, 131, 300, 469), 0),
     (3, 4096, 235, (0, 37, 150, 235), 5),
     (4, 8192, 235, (0, 100, 101, 235), 7),
@@ -32,7 +34,7 @@ FULL = [
     # is 24 GB of PCM twice over in host memory; bench.py --config 5 runs that size)
     (5, 4096, 469, (0, 200, 469), 0),
 ]
-IDS = ["config2_lc_4096x469", "config3_sbr_4096x235", "config4_sbr_ps_8192x235", "config5_lc_51_4096x469"]
+IDS = ["config1_lc_1x431", "config2_lc_4096x469", "config3_sbr_4096x235", "config4_sbr_ps_8192x235", "config5_lc_51_4096x469"]
 
 
 @pytest.mark.parametrize("config_no,n_streams,n_frames,cuts,tile", FULL, ids=IDS)
