@@ -143,6 +143,7 @@ struct Ctx {
   int sfIndex;
   double pPns = 0;      // > 0: perceptual noise substitution (codebook 13) on that share of the bands
   double psExt = 0;     // > 0: PS headers enable the IPD/OPD extension with this probability
+  bool psIso = false;   // PS modes restricted to the ones JAAD decodes like ISO/IEC 14496-3 (aacgen_ps.inc)
   bool tnsMild = false; // TNS filters an ISO decoder can apply without blowing up: order <= 12 / 7, small reflection coefficients
   explicit Ctx(uint64_t seed, int sfi) : rng(seed), sfIndex(sfi) {}
 };
@@ -527,7 +528,7 @@ struct jg_config {
   float p_pns;            // > 0: share of the bands coded as perceptual noise (codebook 13)
   int32_t tns_mild;       // 1: TNS filters an ISO decoder can apply (orders <= 12 / 7, small coefficients)
   float ps_ext;           // > 0: probability that a PS header enables the IPD/OPD extension (ps/Extension.java)
-  int32_t reserved2;
+  int32_t ps_iso;         // 1: only the PS modes on which JAAD and ISO/IEC 14496-3 agree (cross-checks against other decoders)
 };
 
 // Ground truth per ICS (element order, L before R); arrays may be NULL.
@@ -560,6 +561,7 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
   c.pPns = cfg->p_pns;
   c.tnsMild = cfg->tns_mild != 0;
   c.psExt = cfg->ps_ext;
+  c.psIso = cfg->ps_iso != 0;
   const int nIcs = jg_ics_per_frame(cfg->chan_cfg);
   const int nEl = jg_elements_per_frame(cfg->chan_cfg);
   // element layout
