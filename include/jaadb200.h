@@ -255,6 +255,21 @@ int64_t jaadb_mp4_index_many(const uint8_t* blob, const uint64_t* file_begin, ui
                              jaadb_frame_desc* frames, uint64_t max_frames, uint64_t* first_frame,
                              jaadb_mp4_track* tracks, uint32_t threads);
 
+/* ---- containers in, PCM out ------------------------------------------------
+ * S/Main.java:49-111 for a whole batch in one call: n_streams ADTS streams (S/adts/ADTSDemultiplexer.java) or MP4 files
+ * (M/MP4Container.java, M/api/Track.java) stored back to back in `blob` (host memory; container s = blob[stream_begin[s],
+ * stream_begin[s+1]), stream_begin[0] = 0) are indexed on `threads` host threads (0: all cores) WHILE the bytes are already on
+ * their way to the GPU, the frames are put in frame-major order (jaadb_frames_interleave) and decoded like jaadb_decode
+ * does, PCM packed in that order.  stream_ids[s] (NULL: 0..n-1) names the open stream container s belongs to.
+ * Returns the number of frames decoded, or a negative JAADB_E_* code.  `results` / `frames_out` (either may be NULL) receive
+ * one row per frame and must hold max_frames rows (JAADB_E_CAPACITY if the containers hold more); pcm_out may be host or
+ * device memory as for jaadb_decode.                                          */
+#define JAADB_CONTAINER_ADTS 0
+#define JAADB_CONTAINER_MP4 1
+int64_t jaadb_decode_containers(jaadb_engine* e, int32_t kind, const uint8_t* blob, const uint64_t* stream_begin, uint32_t n_streams,
+                                const int32_t* stream_ids, void* pcm_out, uint64_t pcm_capacity, jaadb_frame_result* results,
+                                uint64_t max_frames, jaadb_frame_desc* frames_out, uint32_t threads);
+
 /* Reorders the stream-major table of the *_index_many calls frame-major: frame 0 of every stream, frame 1 of every stream,
  * ... -- the order a live batch of concurrent streams arrives in, and the one that gives every chunk of jaadb_decode all
  * streams to work on.  Per-stream order is kept, so both orders decode identically.  `out` has first_frame[n_streams] rows.

@@ -17,7 +17,7 @@ SYMBOLS = [
     "jaadb_batch_create", "jaadb_batch_pcm_bytes", "jaadb_batch_upload", "jaadb_batch_decode", "jaadb_batch_sync",
     "jaadb_batch_download", "jaadb_batch_timings", "jaadb_batch_destroy", "jaadb_batch_tap", "jaadb_batch_tap_sbr", "jaadb_batch_tap_ps",
     "jaadb_adts_index", "jaadb_adts_index_many", "jaadb_mp4_index", "jaadb_mp4_index_many", "jaadb_probe_sbr", "jaadb_probe_sbr_asc",
-    "jaadb_frames_interleave",
+    "jaadb_frames_interleave", "jaadb_decode_containers",
 ]
 
 
@@ -108,6 +108,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     for fn in (lib.jaadb_adts_index_many, lib.jaadb_mp4_index_many):
         fn.restype = C.c_int64
         fn.argtypes = [u8p, vp, C.c_uint32, vp, vp, C.c_uint64, vp, vp, C.c_uint32]
+    lib.jaadb_decode_containers.restype = C.c_int64
+    lib.jaadb_decode_containers.argtypes = [vp, C.c_int32, u8p, vp, C.c_uint32, vp, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint32]
     lib.jaadb_frames_interleave.restype = C.c_int64
     lib.jaadb_frames_interleave.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32]
     _lib = lib

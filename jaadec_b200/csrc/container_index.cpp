@@ -341,7 +341,9 @@ void parallel_streams(uint32_t n_streams, uint32_t threads, F&& fn) {
   for (auto& th : pool) th.join();
 }
 
-// Shared driver of the two *_index_many calls: pass 1 counts (in parallel), prefix sum, pass 2 fills (in parallel).
+// Shared driver of the two *_index_many calls.  One pass over the containers (the sync search / sample tables are the
+// expensive part: a cache miss per frame): every stream's frames go into a per-stream vector, then a prefix sum places
+// them in the caller's table.
 template <typename Info, typename One>
 int64_t index_many(const uint8_t* blob, const uint64_t* stream_begin, uint32_t n_streams, const int32_t* stream_ids,
                           jaadb_frame_desc* frames, uint64_t max_frames, uint64_t* first_frame, Info* infos,
@@ -357,9 +359,20 @@ int64_t index_many(const uint8_t* blob, const uint64_t* stream_begin, uint32_t n
   };
   std::vector<int64_t> count(n_streams, 0);
   std::vector<Info> local(n_streams);
+  std::vector<std::vector<jaadb_frame_desc>> found(frames ? n_streams : 0);
   parallel_streams(n_streams, threads, [&](uint32_t s) {
-    count[s] = one_safe(blob + stream_begin[s], stream_begin[s + 1] - stream_begin[s], stream_begin[s],
-                        stream_ids ? stream_ids[s] : (int32_t)s, nullptr, 0, &local[s]);
+    const uint64_t bytes = stream_begin[s + 1] - stream_begin[s];
+    jaadb_frame_desc* tmp = nullptr;
+    uint64_t cap = 0;
+    if (frames) {
+      try { found[s].resize((size_t)std::min<uint64_t>(bytes / 64 + 16, 1u << 20)); tmp = found[s].data(); cap = found[s].size(); }
+      catch (...) { tmp = nullptr; cap = 0; }
+    }
+    count[s] = one_safe(blob + stream_begin[s], bytes, stream_begin[s], stream_ids ? stream_ids[s] : (int32_t)s, tmp, cap, &local[s]);
+    if (frames && count[s] > (int64_t)cap) {   // more frames than the guess: index once more into a table of the right size
+      try { found[s].resize((size_t)count[s]); one_safe(blob + stream_begin[s], bytes, stream_begin[s], stream_ids ? stream_ids[s] : (int32_t)s, found[s].data(), (uint64_t)count[s], nullptr); }
+      catch (...) { count[s] = JAADB_E_NOMEM; }
+    }
   });
   std::vector<uint64_t> first(n_streams + 1, 0);
   for (uint32_t s = 0; s < n_streams; ++s) first[s + 1] = first[s] + (uint64_t)std::max<int64_t>(count[s], 0);
@@ -371,9 +384,7 @@ int64_t index_many(const uint8_t* blob, const uint64_t* stream_begin, uint32_t n
     }
   if (frames && first[n_streams] <= max_frames)
     parallel_streams(n_streams, threads, [&](uint32_t s) {
-      if (count[s] > 0)
-        one_safe(blob + stream_begin[s], stream_begin[s + 1] - stream_begin[s], stream_begin[s],
-                 stream_ids ? stream_ids[s] : (int32_t)s, frames + first[s], (uint64_t)count[s], nullptr);
+      if (count[s] > 0) std::memcpy(frames + first[s], found[s].data(), (size_t)count[s] * sizeof(jaadb_frame_desc));
     });
   return (int64_t)first[n_streams];
 }
@@ -405,6 +416,32 @@ int64_t frames_interleave(const jaadb_frame_desc* in, const uint64_t* first_fram
 }
 
 }  // namespace
+
+// Used by jaadb_decode_containers (jaadb_engine.cu): containers -> frame table in frame-major order, `frames` resized to fit.
+// kind 0: ADTS streams, 1: MP4 files.  Returns the number of frames or a negative JAADB_E_* code; never throws.
+int64_t jaadb_internal_index_interleaved(int kind, const uint8_t* blob, const uint64_t* begin, uint32_t n_streams, const int32_t* stream_ids,
+                                         std::vector<jaadb_frame_desc>& scratch, std::vector<jaadb_frame_desc>& frames, uint32_t threads) {
+  try {
+    std::vector<uint64_t> first(n_streams + 1, 0);
+    // a first call that only counts would cost a second pass over the containers: guess, and grow if the guess was short
+    uint64_t guess = scratch.size() ? scratch.size() : (begin[n_streams] - begin[0]) / 256 + 1024;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      scratch.resize((size_t)guess);
+      const int64_t n = kind == 1
+          ? index_many(blob, begin, n_streams, stream_ids, scratch.data(), (uint64_t)scratch.size(), first.data(), (jaadb_mp4_track*)nullptr, threads, mp4_index)
+          : index_many(blob, begin, n_streams, stream_ids, scratch.data(), (uint64_t)scratch.size(), first.data(), (jaadb_adts_info*)nullptr, threads, adts_index);
+      if (n < 0) return n;
+      if ((uint64_t)n <= scratch.size()) {
+        frames.resize((size_t)n);
+        if (n == 0) return 0;
+        return frames_interleave(scratch.data(), first.data(), n_streams, frames.data(), threads);
+      }
+      guess = (uint64_t)n;
+    }
+    return JAADB_E_INVALID;
+  } catch (const std::bad_alloc&) { return JAADB_E_NOMEM; }
+  catch (...) { return JAADB_E_INVALID; }
+}
 
 extern "C" {
 

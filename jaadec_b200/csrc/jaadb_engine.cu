@@ -198,6 +198,7 @@ struct jaadb_engine {
   std::vector<StreamHost> streams;
   std::vector<int32_t> free_slots;
   std::vector<uint32_t> scratch_count, scratch_run_of, scratch_fill, scratch_size;
+  std::vector<jaadb_frame_desc> scratch_frames, scratch_frames_sm;   // jaadb_decode_containers: frame-major table, stream-major scratch
   std::vector<uint64_t> scratch_off;
   FrameIndex scratch_ix;
   // device tables
@@ -1390,12 +1391,80 @@ void jaadb_batch_destroy(jaadb_batch* b) {
 // host, upload descriptors, K1, K2 into one of two device PCM buffers, then the chunk's PCM byte range and result
 // words go back over PCIe on a second stream while the next chunk is decoded.  Frames of a stream stay in array
 // order across chunks because chunks run in order on one stream and the overlap state lives in HBM in between.
+}  // extern "C"
+
+// container_index.cpp
+int64_t jaadb_internal_index_interleaved(int kind, const uint8_t* blob, const uint64_t* begin, uint32_t n_streams, const int32_t* stream_ids,
+                                         std::vector<jaadb_frame_desc>& scratch, std::vector<jaadb_frame_desc>& frames, uint32_t threads);
+
+namespace {
+
+// the compressed bytes go on the bus (or across HBM) first, so that host-side work runs while they travel
+int start_blob_upload(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes) {
+  auto& W = e->ws;
+  const cudaError_t be = W.blob.ensure(blob_bytes + 64);
+  if (be != cudaSuccess) { e->set_error(std::string("workspace allocation: ") + cudaGetErrorString(be)); return JAADB_E_NOMEM; }
+  // (host or device source: a device blob is copied once inside HBM, which gives it the padding the bit readers rely on)
+  if (blob_bytes) CUDA_TRY(e, cudaMemcpyAsync(W.blob.p, blob, blob_bytes, cudaMemcpyDefault, e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(W.blob.p + blob_bytes, 0, 64, e->stream));
+  return JAADB_OK;
+}
+
+int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const jaadb_frame_desc* frames, uint32_t n_frames,
+                void* pcm_out, uint64_t pcm_capacity, const uint64_t* pcm_offsets, jaadb_frame_result* results, bool blob_in_flight);
+
+}  // namespace
+
+extern "C" {
+
 int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const jaadb_frame_desc* frames,
                  uint32_t n_frames, void* pcm_out, uint64_t pcm_capacity, const uint64_t* pcm_offsets,
                  jaadb_frame_result* results) {
   if (!e || (n_frames && !frames) || (!blob && blob_bytes)) return JAADB_E_INVALID;
   cudaSetDevice(e->opts.device);
   if (n_frames == 0) return JAADB_OK;
+  return decode_impl(e, blob, blob_bytes, frames, n_frames, pcm_out, pcm_capacity, pcm_offsets, results, false);
+}
+
+int64_t jaadb_decode_containers(jaadb_engine* e, int32_t kind, const uint8_t* blob, const uint64_t* stream_begin, uint32_t n_streams,
+                                const int32_t* stream_ids, void* pcm_out, uint64_t pcm_capacity, jaadb_frame_result* results,
+                                uint64_t max_frames, jaadb_frame_desc* frames_out, uint32_t threads) {
+  if (!e || !blob || !stream_begin || (kind != JAADB_CONTAINER_ADTS && kind != JAADB_CONTAINER_MP4)) return JAADB_E_INVALID;
+  cudaSetDevice(e->opts.device);
+  if (n_streams == 0) return 0;
+  if (stream_begin[0] != 0) { e->set_error("stream_begin[0] must be 0: the blob starts with the first container"); return JAADB_E_INVALID; }
+  const uint64_t blob_bytes = stream_begin[n_streams];
+  // the containers travel to the GPU while the host threads index them (both read the same bytes)
+  {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, blob) == cudaSuccess && pa.type == cudaMemoryTypeDevice) {
+      e->set_error("jaadb_decode_containers indexes on the host: the containers must be in host memory");
+      return JAADB_E_INVALID;
+    }
+    cudaGetLastError();
+  }
+  int rc = start_blob_upload(e, blob, blob_bytes);
+  if (rc) return rc;
+  const int64_t n = jaadb_internal_index_interleaved(kind, blob, stream_begin, n_streams, stream_ids, e->scratch_frames_sm, e->scratch_frames, threads);
+  if (n < 0 || (uint64_t)n > 0xFFFFFFFFull) { cudaStreamSynchronize(e->stream); e->set_error("container indexing failed"); return n < 0 ? n : JAADB_E_CAPACITY; }
+  if ((results || frames_out) && (uint64_t)n > max_frames) {
+    cudaStreamSynchronize(e->stream);
+    e->set_error("the containers hold more frames than max_frames");
+    return JAADB_E_CAPACITY;
+  }
+  if (frames_out && n) memcpy(frames_out, e->scratch_frames.data(), (size_t)n * sizeof(jaadb_frame_desc));
+  if (n == 0) { cudaStreamSynchronize(e->stream); return 0; }
+  rc = decode_impl(e, blob, blob_bytes, e->scratch_frames.data(), (uint32_t)n, pcm_out, pcm_capacity, nullptr, results, true);
+  return rc ? rc : n;
+}
+
+}  // extern "C"
+
+namespace {
+
+// One-call decode, pipelined (see jaadb_decode below for the contract).
+int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const jaadb_frame_desc* frames, uint32_t n_frames,
+                void* pcm_out, uint64_t pcm_capacity, const uint64_t* pcm_offsets, jaadb_frame_result* results, bool blob_in_flight) {
   auto& W = e->ws;
   // JAADB200_TRACE=1: host-side timeline of the call on stderr (tuning aid)
   static const bool trace = getenv("JAADB200_TRACE") != nullptr;
@@ -1403,12 +1472,9 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   auto ms_now = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
   // The compressed frames go first (one copy: frames of a chunk may sit anywhere in the caller's blob), so that the
   // host-side layout work below runs while they are on the bus.
-  {
-    const cudaError_t be = W.blob.ensure(blob_bytes + 64);
-    if (be != cudaSuccess) { e->set_error(std::string("workspace allocation: ") + cudaGetErrorString(be)); return JAADB_E_NOMEM; }
-    // (host or device source: a device blob is copied once inside HBM, which gives it the padding the bit readers rely on)
-    if (blob_bytes) CUDA_TRY(e, cudaMemcpyAsync(W.blob.p, blob, blob_bytes, cudaMemcpyDefault, e->stream));
-    CUDA_TRY(e, cudaMemsetAsync(W.blob.p + blob_bytes, 0, 64, e->stream));
+  if (!blob_in_flight) {
+    const int urc = start_blob_upload(e, blob, blob_bytes);
+    if (urc) return urc;
   }
   // A pcm_out in device memory (of this engine's GPU) is written by the kernels directly: no staging buffers, nothing on
   // PCIe but the descriptors in and the per-frame results out.
@@ -1438,13 +1504,20 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
 
   // chunking: ~128 Ki frames per chunk, unless the caller's PCM placement is not monotonic over chunks
   uint32_t chunk = e->opts.chunk_frames ? e->opts.chunk_frames : 131072u;
+  if (out_dev && !e->opts.chunk_frames) {
+    // nothing to overlap with when the PCM stays in HBM: chunks only bound the workspace (quantised coefficients and side
+    // information, 2448 bytes per channel-frame), 16 GB of it
+    int slots = 1;
+    for (uint32_t i = 0; i < n_frames; ++i) slots = std::max(slots, e->streams[frames[i].stream_id].n_slots);
+    chunk = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, (16ull << 30) / ((uint64_t)slots * 2448ull));
+  }
   if (n_frames <= chunk + chunk / 2) chunk = n_frames;
   struct Range { uint32_t i0, i1; uint64_t lo, hi; };
   std::vector<Range> ranges;
   // the first chunks are short (from 1/8 of a chunk, growing by a quarter each): the PCM download -- the long pole of the
   // call -- starts after a fraction of a chunk's kernel time instead of a whole one, and stays fed while the chunks grow
   // (a chunk's kernels take up to 3/4 of the time of its download, so faster growth would starve the copy engine)
-  const bool ramp = !e->opts.chunk_frames && n_frames >= 4 * chunk;
+  const bool ramp = !e->opts.chunk_frames && !out_dev && n_frames >= 4 * chunk;
   uint32_t step = ramp ? chunk / 8 : chunk;
   for (uint32_t i0 = 0; i0 < n_frames;) {
     Range r{i0, std::min(n_frames, i0 + step), ~0ull, 0};
@@ -1633,6 +1706,10 @@ int jaadb_decode(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, cons
   if (results) convert_results(ranges.size() >= 2 ? ranges[ranges.size() - 2].i0 : 0, n_frames);
   return JAADB_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 int jaadb_batch_tap(jaadb_batch* b, uint32_t frame, uint32_t ch, int16_t* q, int16_t* sfidx, uint8_t* sfbcb, float* spec,
                     int32_t* info, uint8_t* ms_used128) {

@@ -11,6 +11,7 @@ from ._lib import FrameDesc, FrameResult, Options, StreamInfo, Timings
 PCM_S16LE, PCM_S16BE, PCM_F32_PLANAR = 0, 1, 2
 FLAG_PROFILE, FLAG_DEBUG_TAPS = 1, 2
 TNS_JAAD, TNS_ISO = 0, 1
+CONTAINER_ADTS, CONTAINER_MP4 = 0, 1
 
 FRAME_DESC_DTYPE = np.dtype([("offset", "<u8"), ("nbytes", "<u4"), ("stream_id", "<i4")])
 FRAME_RESULT_DTYPE = np.dtype([("status", "<i4"), ("channels", "<u2"), ("sample_length", "<u2"), ("sample_rate", "<u4"),
@@ -123,6 +124,26 @@ class Engine:
         self._check(self._lib.jaadb_decode(self._h, blob_ptr, blob_bytes, _ptr(frames), len(frames), pcm_ptr, pcm_capacity,
                                            _ptr(pcm_offsets), _ptr(results)), "decode")
         return results
+
+    def decode_containers(self, kind: int, blob: np.ndarray, stream_begin: np.ndarray, stream_ids, pcm_out, results: np.ndarray,
+                          frames_out: np.ndarray | None = None, threads: int = 0, pcm_capacity: int | None = None) -> int:
+        """Container bytes in, PCM out (jaadb_decode_containers): `blob` holds ADTS streams (kind CONTAINER_ADTS) or MP4 files
+        (CONTAINER_MP4) back to back; they are indexed on host threads while the bytes are on their way to the GPU, then
+        decoded in frame-major order.  `pcm_out`: a numpy array, or a device address (int) together with pcm_capacity.
+        Returns the number of frames; results[:n] (and frames_out[:n]) are filled."""
+        blob = np.ascontiguousarray(blob, np.uint8)
+        begin = np.ascontiguousarray(stream_begin, np.uint64)
+        ids = None if stream_ids is None else np.ascontiguousarray(stream_ids, np.int32)
+        assert results.dtype == FRAME_RESULT_DTYPE and results.flags.c_contiguous
+        if isinstance(pcm_out, np.ndarray):
+            pcm_ptr, cap = pcm_out.ctypes.data, pcm_out.nbytes
+        else:
+            pcm_ptr, cap = pcm_out, int(pcm_capacity)
+        n = self._lib.jaadb_decode_containers(self._h, kind, _ptr(blob), _ptr(begin), len(begin) - 1, _ptr(ids), pcm_ptr, cap,
+                                              _ptr(results), len(results), _ptr(frames_out), threads)
+        if n < 0:
+            raise EngineError("decode_containers failed: %d (%s)" % (n, self._lib.jaadb_last_error(self._h).decode()))
+        return int(n)
 
     def packed_bytes(self, frames) -> int:
         """Size of the PCM buffer jaadb_decode fills for `frames` when pcm_offsets is None."""

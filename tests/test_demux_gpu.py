@@ -170,3 +170,55 @@ def test_probe_sbr_tells_what_an_adts_stream_carries():
     ids = [eng.open_adts(2, 3, 2) for _ in range(4)]
     assert sorted(ids) == [0, 1, 2, 3]
     eng.close()
+
+
+@pytest.mark.parametrize("kind", ["adts", "mp4"])
+def test_decode_containers_one_call(kind):
+    """jaadb_decode_containers: container bytes in, PCM out -- host-side indexing overlapped with the upload, frames in
+    frame-major order.  Same frame table and the same PCM bytes as indexing + interleaving + jaadb_decode done by hand, for
+    ragged streams, with the PCM in host memory and in device memory; a table that is too small is refused."""
+    import torch
+    from jaadec_b200 import CONTAINER_ADTS, CONTAINER_MP4, FRAME_RESULT_DTYPE, FRAME_DESC_DTYPE, EngineError
+    lens = [9, 14, 5, 14]
+    if kind == "adts":
+        cfgs = [gen.config(2, n_frames=n, p_transient=0.3) for n in lens]
+        streams = [gen.generate(c, 8100 + i) for i, c in enumerate(cfgs)]
+        files = [s.data for s in streams]
+    else:
+        cfgs = [gen.config(5, n_frames=n, p_transient=0.3) for n in lens]
+        streams = [gen.generate(c, 8200 + i) for i, c in enumerate(cfgs)]
+        files = [genmp4.write_mp4((s.data, s.sizes), bytes([0x11, 0xB0]), 48000, 6, chunk_pattern=(3, 2))[0] for s in streams]
+    begin = np.concatenate([[0], np.cumsum([len(f) for f in files])]).astype(np.uint64)
+    blob = np.concatenate(files)
+    ck = CONTAINER_ADTS if kind == "adts" else CONTAINER_MP4
+
+    def open_all(e):
+        if kind == "adts":
+            return [e.open_adts(2, cfgs[0].sf_index, cfgs[0].chan_cfg) for _ in lens]
+        return [e.open_asc(bytes([0x11, 0xB0])) for _ in lens]
+
+    e1, e2, e3 = (Engine(max_streams=8, pcm_format=PCM_S16LE, chunk_frames=16) for _ in range(3))
+    ids = np.asarray(open_all(e1), np.int32)
+    assert list(open_all(e2)) == list(ids) and list(open_all(e3)) == list(ids)
+    # by hand
+    fr, first, _ = (demux.adts_index_many if kind == "adts" else demux.mp4_index_many)(blob, begin, ids)
+    fr = demux.interleave(fr, first)
+    want_pcm, want_res = e1.decode(blob, fr)
+    assert (want_res["status"] == 0).all() and len(fr) == sum(lens)
+    # one call, host PCM
+    n_max = sum(lens)
+    res = np.zeros(n_max, FRAME_RESULT_DTYPE)
+    tbl = np.zeros(n_max, FRAME_DESC_DTYPE)
+    pcm = np.zeros(want_pcm.nbytes, np.uint8)
+    assert e2.decode_containers(ck, blob, begin, ids, pcm, res, frames_out=tbl) == n_max
+    assert np.array_equal(tbl, fr) and np.array_equal(res, want_res) and np.array_equal(pcm, want_pcm)
+    # one call, device PCM
+    d_pcm = torch.zeros(want_pcm.nbytes, dtype=torch.uint8, device="cuda")
+    res3 = np.zeros(n_max, FRAME_RESULT_DTYPE)
+    assert e3.decode_containers(ck, blob, begin, ids, d_pcm.data_ptr(), res3, pcm_capacity=d_pcm.numel()) == n_max
+    torch.cuda.synchronize()
+    assert np.array_equal(d_pcm.cpu().numpy(), want_pcm) and np.array_equal(res3, want_res)
+    with pytest.raises(EngineError):
+        e3.decode_containers(ck, blob, begin, ids, pcm, np.zeros(n_max - 1, FRAME_RESULT_DTYPE))
+    for e in (e1, e2, e3):
+        e.close()
