@@ -25,11 +25,11 @@ public final class NativeEngine implements AutoCloseable {
 			JAVA_INT.withName("status"), JAVA_SHORT.withName("channels"), JAVA_SHORT.withName("sample_length"),
 			JAVA_INT.withName("sample_rate"), JAVA_INT.withName("pcm_bytes"));
 	/** jaadb_options { int32 device; uint32 max_streams; int32 pcm_format; int32 tns_mode; uint32 flags; uint32 chunk_frames;
-	 *  uint32 sbr_tile_frames; uint32 reserved[1]; } -- the two tuning knobs stay 0 (defaults) here */
+	 *  uint32 sbr_tile_frames; uint32 k2_segment_frames; } -- the three tuning knobs stay 0 (defaults) here */
 	static final StructLayout OPTIONS = MemoryLayout.structLayout(
 			JAVA_INT.withName("device"), JAVA_INT.withName("max_streams"), JAVA_INT.withName("pcm_format"),
 			JAVA_INT.withName("tns_mode"), JAVA_INT.withName("flags"), JAVA_INT.withName("chunk_frames"),
-			JAVA_INT.withName("sbr_tile_frames"), MemoryLayout.sequenceLayout(1, JAVA_INT));
+			JAVA_INT.withName("sbr_tile_frames"), JAVA_INT.withName("k2_segment_frames"));
 
 	private static final Linker LINKER = Linker.nativeLinker();
 	private static final SymbolLookup LIB = SymbolLookup.libraryLookup(

@@ -48,6 +48,10 @@ def cases():
                                         sbr_downsampled=True), 2, bytes([0x13, 0x10])),
         "ps_ds_mono": (gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=22, target_bytes=171, sbr_mode=2, adts=False,
                                      sbr_downsampled=True), 2, bytes([0x13, 0x08])),
+        # round 2: perceptual noise substitution (every stream decoded by its own Decoder = alone in a fresh JVM, which is
+        # how tools/jaad_verify runs JAAD: one process per file) and the IPD/OPD extension of parametric stereo
+        "lc_pns_48k": (gen.config(2, n_frames=12, p_transient=0.35, p_pns=0.25), 3, None),
+        "ps_ipdopd_mono": (gen.config(4, n_frames=30, ps_ext=0.8), 2, None),
     }
 
 

@@ -163,7 +163,7 @@ def test_downsampled_synthesis_bank_matches_direct_form():
     assert np.abs(pcm[289:] - x[:-289]).max() / np.abs(x).max() < 2e-3
 
 
-@pytest.mark.parametrize("name", ["sbr_c3_stereo", "sbr_mono", "ps_c4_mono", "sbr_ds_stereo", "ps_ds_mono"])
+@pytest.mark.parametrize("name", ["sbr_c3_stereo", "sbr_mono", "ps_c4_mono", "sbr_ds_stereo", "ps_ds_mono", "ps_ipdopd_mono"])
 def test_oracle_reproduces_sbr_golden(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     n_streams = int(g["frame_stream"].max()) + 1
