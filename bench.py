@@ -84,6 +84,12 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def n_samples(self):
+        try:
+            return sum(1 for _ in open(self.path))
+        except OSError:
+            return 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
@@ -257,12 +263,19 @@ def measure(config_no, n_streams, n_frames, steps, warmup, local_rank, rank, wor
     batch = eng.batch(frames, wl.blob.nbytes)
     batch.upload(wl.blob)
     batch.sync()
-    for _ in range(warmup):
-        batch.decode()
-    batch.sync()
     sampler = ClockSampler(local_rank) if want_clocks else None
     if sampler:
         sampler.start()
+    for _ in range(warmup):
+        batch.decode()
+    batch.sync()
+    if sampler:
+        # nvidia-smi needs a moment to deliver its first line: the GPU stays under the same load (more untimed warm-up steps)
+        # until it has, so that the samples -- one per 100 ms from here to the end of the timed region -- are taken under load
+        t_dead = time.perf_counter() + 5.0
+        while sampler.n_samples() < 2 and time.perf_counter() < t_dead:
+            batch.decode()
+            batch.sync()
     parse_ms, fb_ms, sbr_ms, dev_ms, launches = [], [], [], [], 0
     barrier()
     t0 = time.perf_counter()

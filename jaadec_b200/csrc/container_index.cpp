@@ -13,8 +13,10 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/jaadb200.h"
@@ -344,6 +346,44 @@ void parallel_streams(uint32_t n_streams, uint32_t threads, F&& fn) {
 // Shared driver of the two *_index_many calls.  One pass over the containers (the sync search / sample tables are the
 // expensive part: a cache miss per frame): every stream's frames go into a per-stream vector, then a prefix sum places
 // them in the caller's table.
+// ADTS streams, eight at a time per host thread: every frame header is a cache miss (frames are a few hundred bytes apart in
+// blobs far larger than the caches), and a stream's next header is only known once the current one is parsed -- so one
+// walker has one miss in flight.  Stepping eight independent walkers in turn, each prefetching its next header before the
+// others take their step, keeps eight in flight (measured: 125 ns -> ~25 ns per frame and thread).
+constexpr uint32_t kAdtsGroup = 8;
+void adts_index_group(const uint8_t* blob, const uint64_t* stream_begin, const int32_t* stream_ids, uint32_t s0, uint32_t s1,
+                      jaadb_frame_desc* stage, const uint64_t* at, int64_t* count, jaadb_adts_info* local) {
+  AdtsWalker w[kAdtsGroup];
+  bool alive[kAdtsGroup];
+  const uint32_t n = s1 - s0;
+  for (uint32_t j = 0; j < n; ++j) {
+    w[j] = AdtsWalker{blob + stream_begin[s0 + j], stream_begin[s0 + j + 1] - stream_begin[s0 + j]};
+    alive[j] = true;
+    count[s0 + j] = 0;
+    std::memset(&local[s0 + j], 0, sizeof(jaadb_adts_info));
+  }
+  for (bool any = true; any;) {
+    any = false;
+    for (uint32_t j = 0; j < n; ++j) {
+      if (!alive[j]) continue;
+      const uint32_t s = s0 + j;
+      uint64_t off;
+      uint32_t len;
+      if (!w[j].next(off, len, count[s] == 0 ? &local[s] : nullptr)) { alive[j] = false; continue; }
+      any = true;
+      if (stage && (uint64_t)count[s] < at[s + 1] - at[s]) {
+        jaadb_frame_desc& f = stage[at[s] + (uint64_t)count[s]];
+        f.offset = stream_begin[s] + off;
+        f.nbytes = len;
+        f.stream_id = stream_ids ? stream_ids[s] : (int32_t)s;
+      }
+      ++count[s];
+      if (w[j].pos + 8 <= w[j].n) __builtin_prefetch(w[j].d + w[j].pos);
+    }
+  }
+  for (uint32_t j = 0; j < n; ++j) local[s0 + j].n_frames = (uint64_t)count[s0 + j];
+}
+
 template <typename Info, typename One>
 int64_t index_many(const uint8_t* blob, const uint64_t* stream_begin, uint32_t n_streams, const int32_t* stream_ids,
                           jaadb_frame_desc* frames, uint64_t max_frames, uint64_t* first_frame, Info* infos,
@@ -359,21 +399,37 @@ int64_t index_many(const uint8_t* blob, const uint64_t* stream_begin, uint32_t n
   };
   std::vector<int64_t> count(n_streams, 0);
   std::vector<Info> local(n_streams);
-  std::vector<std::vector<jaadb_frame_desc>> found(frames ? n_streams : 0);
-  parallel_streams(n_streams, threads, [&](uint32_t s) {
+  // staging rows: stream s may write cap[s] = bytes / 64 + 16 rows at stage + at[s] (one uninitialised allocation: only the
+  // rows that are written are ever touched); a stream with more frames than that is indexed again into its own table
+  std::vector<uint64_t> at(n_streams + 1, 0);
+  std::unique_ptr<jaadb_frame_desc[]> stage;
+  std::vector<std::vector<jaadb_frame_desc>> big(frames ? n_streams : 0);
+  if (frames) {
+    for (uint32_t s = 0; s < n_streams; ++s) at[s + 1] = at[s] + std::min<uint64_t>((stream_begin[s + 1] - stream_begin[s]) / 64 + 16, 1u << 22);
+    stage.reset(new jaadb_frame_desc[at[n_streams]]);
+  }
+  auto redo_big = [&](uint32_t s) {   // more frames than the staging guess: once more, into a table of the right size
     const uint64_t bytes = stream_begin[s + 1] - stream_begin[s];
-    jaadb_frame_desc* tmp = nullptr;
-    uint64_t cap = 0;
-    if (frames) {
-      try { found[s].resize((size_t)std::min<uint64_t>(bytes / 64 + 16, 1u << 20)); tmp = found[s].data(); cap = found[s].size(); }
-      catch (...) { tmp = nullptr; cap = 0; }
-    }
-    count[s] = one_safe(blob + stream_begin[s], bytes, stream_begin[s], stream_ids ? stream_ids[s] : (int32_t)s, tmp, cap, &local[s]);
-    if (frames && count[s] > (int64_t)cap) {   // more frames than the guess: index once more into a table of the right size
-      try { found[s].resize((size_t)count[s]); one_safe(blob + stream_begin[s], bytes, stream_begin[s], stream_ids ? stream_ids[s] : (int32_t)s, found[s].data(), (uint64_t)count[s], nullptr); }
-      catch (...) { count[s] = JAADB_E_NOMEM; }
-    }
-  });
+    try { big[s].resize((size_t)count[s]); one_safe(blob + stream_begin[s], bytes, stream_begin[s], stream_ids ? stream_ids[s] : (int32_t)s, big[s].data(), (uint64_t)count[s], nullptr); }
+    catch (...) { count[s] = JAADB_E_NOMEM; }
+  };
+  if constexpr (std::is_same<Info, jaadb_adts_info>::value) {
+    const uint32_t n_groups = (n_streams + kAdtsGroup - 1) / kAdtsGroup;
+    parallel_streams(n_groups, threads, [&](uint32_t g) {
+      const uint32_t s0 = g * kAdtsGroup, s1 = std::min(n_streams, s0 + kAdtsGroup);
+      adts_index_group(blob, stream_begin, stream_ids, s0, s1, stage.get(), at.data(), count.data(), local.data());
+      for (uint32_t s = s0; s < s1; ++s)
+        if (frames && count[s] > (int64_t)(at[s + 1] - at[s])) redo_big(s);
+    });
+  } else {
+    parallel_streams(n_streams, threads, [&](uint32_t s) {
+      const uint64_t bytes = stream_begin[s + 1] - stream_begin[s];
+      const uint64_t cap = frames ? at[s + 1] - at[s] : 0;
+      count[s] = one_safe(blob + stream_begin[s], bytes, stream_begin[s], stream_ids ? stream_ids[s] : (int32_t)s,
+                          frames ? stage.get() + at[s] : nullptr, cap, &local[s]);
+      if (frames && count[s] > (int64_t)cap) redo_big(s);
+    });
+  }
   std::vector<uint64_t> first(n_streams + 1, 0);
   for (uint32_t s = 0; s < n_streams; ++s) first[s + 1] = first[s] + (uint64_t)std::max<int64_t>(count[s], 0);
   if (first_frame) std::memcpy(first_frame, first.data(), (n_streams + 1) * sizeof(uint64_t));
@@ -384,7 +440,8 @@ int64_t index_many(const uint8_t* blob, const uint64_t* stream_begin, uint32_t n
     }
   if (frames && first[n_streams] <= max_frames)
     parallel_streams(n_streams, threads, [&](uint32_t s) {
-      if (count[s] > 0) std::memcpy(frames + first[s], found[s].data(), (size_t)count[s] * sizeof(jaadb_frame_desc));
+      if (count[s] > 0)
+        std::memcpy(frames + first[s], big[s].empty() ? stage.get() + at[s] : big[s].data(), (size_t)count[s] * sizeof(jaadb_frame_desc));
     });
   return (int64_t)first[n_streams];
 }

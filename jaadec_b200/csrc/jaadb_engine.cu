@@ -1443,6 +1443,8 @@ int64_t jaadb_decode_containers(jaadb_engine* e, int32_t kind, const uint8_t* bl
     }
     cudaGetLastError();
   }
+  static const bool trace = getenv("JAADB200_TRACE") != nullptr;
+  const auto t_call = std::chrono::steady_clock::now();
   int rc = start_blob_upload(e, blob, blob_bytes);
   if (rc) return rc;
   const int64_t n = jaadb_internal_index_interleaved(kind, blob, stream_begin, n_streams, stream_ids, e->scratch_frames_sm, e->scratch_frames, threads);
@@ -1454,6 +1456,8 @@ int64_t jaadb_decode_containers(jaadb_engine* e, int32_t kind, const uint8_t* bl
   }
   if (frames_out && n) memcpy(frames_out, e->scratch_frames.data(), (size_t)n * sizeof(jaadb_frame_desc));
   if (n == 0) { cudaStreamSynchronize(e->stream); return 0; }
+  if (trace) fprintf(stderr, "[jaadb] containers indexed (%lld frames) at %.2f ms\n", (long long)n,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count());
   rc = decode_impl(e, blob, blob_bytes, e->scratch_frames.data(), (uint32_t)n, pcm_out, pcm_capacity, nullptr, results, true);
   return rc ? rc : n;
 }
@@ -1487,29 +1491,57 @@ int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const
   }
   std::vector<uint64_t>& off = e->scratch_off;
   std::vector<uint32_t>& size = e->scratch_size;
+  // One pass over the frame table: PCM placement (the caller's offsets, or frames packed back to back in array order), the
+  // checks of every descriptor -- before the first kernel: a bad one in a later chunk must not leave the streams of the
+  // earlier chunks half-way through the call -- and what the workspace sizing needs.  (This runs while the compressed bytes
+  // are on the bus; it used to be five passes.)
   uint64_t pcm_total = 0;
-  int rc = layout_pcm(e, frames, n_frames, pcm_offsets, off, size, &pcm_total);
+  int max_slots = 1;
+  bool any_sbr = false;
+  int rc = JAADB_OK;
+  {
+    off.resize(n_frames);
+    size.resize(n_frames);
+    const size_t n_streams = e->streams.size();
+    const uint32_t per = (e->opts.pcm_format == JAADB_PCM_F32_PLANAR) ? 4u : 2u;
+    uint64_t pos = 0, end = 0;
+    for (uint32_t i = 0; i < n_frames && rc == JAADB_OK; ++i) {
+      const jaadb_frame_desc& d = frames[i];
+      if (d.stream_id < 0 || (size_t)d.stream_id >= n_streams || !e->streams[d.stream_id].open) {
+        e->set_error("frame refers to an unknown stream");
+        rc = JAADB_E_NOSTREAM;
+        break;
+      }
+      if (d.nbytes > blob_bytes || d.offset > blob_bytes - d.nbytes || d.nbytes >= (1u << 29)) {
+        e->set_error("frame exceeds the blob");
+        rc = JAADB_E_INVALID;
+        break;
+      }
+      const StreamHost& sh = e->streams[d.stream_id];
+      const uint32_t sz = (uint32_t)sh.out_channels * (uint32_t)sh.sample_length * per;
+      size[i] = sz;
+      if (pcm_offsets) {
+        if ((pcm_offsets[i] & 3u) || pcm_offsets[i] > UINT64_MAX - sz) { e->set_error("pcm offsets must be 4-byte aligned and in range"); rc = JAADB_E_INVALID; break; }
+        off[i] = pcm_offsets[i];
+      } else {
+        off[i] = pos;
+        pos += sz;
+      }
+      end = std::max(end, off[i] + sz);
+      max_slots = std::max(max_slots, sh.n_slots);
+      any_sbr = any_sbr || sh.sbr != 0;
+    }
+    pcm_total = end;
+  }
   if (rc) { cudaStreamSynchronize(e->stream); return rc; }
   if (pcm_out && pcm_capacity < pcm_total) { cudaStreamSynchronize(e->stream); e->set_error("pcm buffer too small"); return JAADB_E_CAPACITY; }
-  // every descriptor is checked before the first kernel: a bad one in a later chunk must not leave the streams of the
-  // earlier chunks half-way through the call
-  for (uint32_t i = 0; i < n_frames; ++i) {
-    const jaadb_frame_desc& d = frames[i];
-    if (d.nbytes > blob_bytes || d.offset > blob_bytes - d.nbytes || d.nbytes >= (1u << 29)) {
-      cudaStreamSynchronize(e->stream);
-      e->set_error("frame exceeds the blob");
-      return JAADB_E_INVALID;
-    }
-  }
 
   // chunking: ~128 Ki frames per chunk, unless the caller's PCM placement is not monotonic over chunks
   uint32_t chunk = e->opts.chunk_frames ? e->opts.chunk_frames : 131072u;
   if (out_dev && !e->opts.chunk_frames) {
     // nothing to overlap with when the PCM stays in HBM: chunks only bound the workspace (quantised coefficients and side
     // information, 2448 bytes per channel-frame), 16 GB of it
-    int slots = 1;
-    for (uint32_t i = 0; i < n_frames; ++i) slots = std::max(slots, e->streams[frames[i].stream_id].n_slots);
-    chunk = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, (16ull << 30) / ((uint64_t)slots * 2448ull));
+    chunk = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, (16ull << 30) / ((uint64_t)max_slots * 2448ull));
   }
   if (n_frames <= chunk + chunk / 2) chunk = n_frames;
   struct Range { uint32_t i0, i1; uint64_t lo, hi; };
@@ -1541,13 +1573,7 @@ int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const
       CUDA_TRY(e, cudaEventCreateWithFlags(&W.desc_done[i], cudaEventDisableTiming));
     }
   }
-  size_t max_ics = 0;
-  {
-    // worst case channel slots per frame in this call
-    int slots = 1;
-    for (uint32_t i = 0; i < n_frames; ++i) slots = std::max(slots, e->streams[frames[i].stream_id].n_slots);
-    max_ics = (size_t)chunk * slots;
-  }
+  const size_t max_ics = (size_t)chunk * max_slots;   // worst case channel slots per frame in this call
   cudaError_t ce = cudaSuccess;
   auto chk = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
   if (!out_dev) {
@@ -1564,8 +1590,6 @@ int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const
   chk(W.k2frames.ensure(chunk));
   chk(W.segs.ensure((size_t)chunk + e->streams.size()));
   chk(W.pcm_off.ensure(n_frames));
-  bool any_sbr = false;
-  for (uint32_t i = 0; i < n_frames && !any_sbr; ++i) any_sbr = e->streams[frames[i].stream_id].sbr != 0;
   if (any_sbr) {
     chk(W.sbr_runs.ensure(e->streams.size()));
     chk(W.k4_runs.ensure(e->streams.size() * 2));
