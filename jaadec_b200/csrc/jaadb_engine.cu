@@ -15,6 +15,8 @@
 #include <chrono>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/jaadb200.h"
@@ -1500,36 +1502,65 @@ int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const
   bool any_sbr = false;
   int rc = JAADB_OK;
   {
-    off.resize(n_frames);
-    size.resize(n_frames);
+    if (off.size() < n_frames) off.resize(n_frames);
+    if (size.size() < n_frames) size.resize(n_frames);
     const size_t n_streams = e->streams.size();
     const uint32_t per = (e->opts.pcm_format == JAADB_PCM_F32_PLANAR) ? 4u : 2u;
-    uint64_t pos = 0, end = 0;
-    for (uint32_t i = 0; i < n_frames && rc == JAADB_OK; ++i) {
-      const jaadb_frame_desc& d = frames[i];
-      if (d.stream_id < 0 || (size_t)d.stream_id >= n_streams || !e->streams[d.stream_id].open) {
-        e->set_error("frame refers to an unknown stream");
-        rc = JAADB_E_NOSTREAM;
-        break;
+    // slices of the table on host threads; packed placement is a prefix sum, so: sizes + checks per slice, slice totals,
+    // then offsets per slice
+    const uint32_t n_thr = n_frames < (1u << 16) ? 1u : std::min<uint32_t>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    struct Slice { uint64_t bytes = 0, end = 0; int rc = JAADB_OK, slots = 1; bool sbr = false; };
+    std::vector<Slice> sl(n_thr);
+    auto bounds = [&](uint32_t t) { return std::make_pair((uint32_t)((uint64_t)n_frames * t / n_thr), (uint32_t)((uint64_t)n_frames * (t + 1) / n_thr)); };
+    auto pass1 = [&](uint32_t t) {
+      Slice& S = sl[t];
+      const auto [lo, hi] = bounds(t);
+      for (uint32_t i = lo; i < hi; ++i) {
+        const jaadb_frame_desc& d = frames[i];
+        if (d.stream_id < 0 || (size_t)d.stream_id >= n_streams || !e->streams[d.stream_id].open) { S.rc = JAADB_E_NOSTREAM; return; }
+        if (d.nbytes > blob_bytes || d.offset > blob_bytes - d.nbytes || d.nbytes >= (1u << 29)) { S.rc = JAADB_E_INVALID; return; }
+        const StreamHost& sh = e->streams[d.stream_id];
+        const uint32_t sz = (uint32_t)sh.out_channels * (uint32_t)sh.sample_length * per;
+        size[i] = sz;
+        S.bytes += sz;
+        if (pcm_offsets) {
+          if ((pcm_offsets[i] & 3u) || pcm_offsets[i] > UINT64_MAX - sz) { S.rc = JAADB_E_INVALID; return; }
+          off[i] = pcm_offsets[i];
+          S.end = std::max(S.end, off[i] + sz);
+        }
+        S.slots = std::max(S.slots, sh.n_slots);
+        S.sbr = S.sbr || sh.sbr != 0;
       }
-      if (d.nbytes > blob_bytes || d.offset > blob_bytes - d.nbytes || d.nbytes >= (1u << 29)) {
-        e->set_error("frame exceeds the blob");
-        rc = JAADB_E_INVALID;
-        break;
-      }
-      const StreamHost& sh = e->streams[d.stream_id];
-      const uint32_t sz = (uint32_t)sh.out_channels * (uint32_t)sh.sample_length * per;
-      size[i] = sz;
-      if (pcm_offsets) {
-        if ((pcm_offsets[i] & 3u) || pcm_offsets[i] > UINT64_MAX - sz) { e->set_error("pcm offsets must be 4-byte aligned and in range"); rc = JAADB_E_INVALID; break; }
-        off[i] = pcm_offsets[i];
-      } else {
-        off[i] = pos;
-        pos += sz;
-      }
-      end = std::max(end, off[i] + sz);
-      max_slots = std::max(max_slots, sh.n_slots);
-      any_sbr = any_sbr || sh.sbr != 0;
+    };
+    auto pass2 = [&](uint32_t t, uint64_t pos) {
+      const auto [lo, hi] = bounds(t);
+      for (uint32_t i = lo; i < hi; ++i) { off[i] = pos; pos += size[i]; }
+    };
+    auto run = [&](auto&& fn) {
+      if (n_thr == 1) { fn(0u); return; }
+      std::vector<std::thread> pool;
+      pool.reserve(n_thr);
+      uint32_t started = 0;
+      try { for (; started + 1 < n_thr; ++started) pool.emplace_back(fn, started + 1); } catch (...) {}
+      fn(0u);
+      for (uint32_t t = started + 1; t < n_thr; ++t) fn(t);   // (threads the host refused)
+      for (auto& th : pool) th.join();
+    };
+    run(pass1);
+    uint64_t end = 0;
+    std::vector<uint64_t> start(n_thr + 1, 0);
+    for (uint32_t t = 0; t < n_thr; ++t) {
+      if (sl[t].rc != JAADB_OK && rc == JAADB_OK) rc = sl[t].rc;
+      start[t + 1] = start[t] + sl[t].bytes;
+      end = std::max(end, sl[t].end);
+      max_slots = std::max(max_slots, sl[t].slots);
+      any_sbr = any_sbr || sl[t].sbr;
+    }
+    if (rc == JAADB_E_NOSTREAM) e->set_error("frame refers to an unknown stream");
+    else if (rc == JAADB_E_INVALID) e->set_error("a frame exceeds the blob, or a pcm offset is misaligned or out of range");
+    if (rc == JAADB_OK && !pcm_offsets) {
+      run([&](uint32_t t) { pass2(t, start[t]); });
+      end = start[n_thr];
     }
     pcm_total = end;
   }
@@ -1541,7 +1572,8 @@ int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const
   if (out_dev && !e->opts.chunk_frames) {
     // nothing to overlap with when the PCM stays in HBM: chunks only bound the workspace (quantised coefficients and side
     // information, 2448 bytes per channel-frame), 16 GB of it
-    chunk = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, (16ull << 30) / ((uint64_t)max_slots * 2448ull));
+    // (and 256 Ki frames keep the host's per-chunk indexing -- about as long as the chunk's kernels -- off the critical path)
+    chunk = (uint32_t)std::min<uint64_t>(262144ull, (16ull << 30) / ((uint64_t)max_slots * 2448ull));
   }
   if (n_frames <= chunk + chunk / 2) chunk = n_frames;
   struct Range { uint32_t i0, i1; uint64_t lo, hi; };
@@ -1549,7 +1581,7 @@ int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const
   // the first chunks are short (from 1/8 of a chunk, growing by a quarter each): the PCM download -- the long pole of the
   // call -- starts after a fraction of a chunk's kernel time instead of a whole one, and stays fed while the chunks grow
   // (a chunk's kernels take up to 3/4 of the time of its download, so faster growth would starve the copy engine)
-  const bool ramp = !e->opts.chunk_frames && !out_dev && n_frames >= 4 * chunk;
+  const bool ramp = !e->opts.chunk_frames && n_frames >= 4 * chunk;
   uint32_t step = ramp ? chunk / 8 : chunk;
   for (uint32_t i0 = 0; i0 < n_frames;) {
     Range r{i0, std::min(n_frames, i0 + step), ~0ull, 0};
