@@ -422,6 +422,20 @@ int init_sbr(jaadb_engine* e) {
                                  T::SBR_T_HUFFMAN_NOISE_BAL_3_0DB_N};
   for (int i = 0; i < 10; ++i)
     if ((rc = e->upload(huff[i], huff_n[i], &D.huff[i]))) return rc;
+  // first-eight-bits tables of the Huffman trees (huff_decode): [23:16] code length + [15:0] value for a leaf within eight
+  // bits, else bit 31 + the node the bit-serial walk continues from
+  auto build_huff_lut = [](const int16_t* tree, int bias, uint32_t* lut) {
+    for (uint32_t w = 0; w < 256; ++w) {
+      int index = 0, len = 0;
+      while (index >= 0 && len < 8) { index = tree[index * 2 + ((w >> (7 - len)) & 1u)]; ++len; }
+      lut[w] = index < 0 ? (((uint32_t)len << 16) | (uint32_t)(uint16_t)(int16_t)(index + bias)) : (0x80000000u | (uint32_t)index);
+    }
+  };
+  {
+    std::vector<uint32_t> lut(10 * 256);
+    for (int i = 0; i < 10; ++i) build_huff_lut(huff[i], 64, lut.data() + 256 * i);
+    if ((rc = e->upload(lut.data(), lut.size(), &D.huff_lut))) return rc;
+  }
   if ((rc = e->upload(JT(SBR_E_DEQ_TAB), T::SBR_E_DEQ_TAB_N, &D.e_deq))) return rc;
   if ((rc = e->upload(JT(SBR_Q_DIV_TAB), T::SBR_Q_DIV_TAB_N, &D.q_div))) return rc;
   if ((rc = e->upload(JT(SBR_Q_DIV2_TAB), T::SBR_Q_DIV2_TAB_N, &D.q_div2))) return rc;
@@ -444,6 +458,11 @@ int init_sbr(jaadb_engine* e) {
                                  T::PS_F_HUFF_ICC_N, T::PS_T_HUFF_ICC_N, T::PS_F_HUFF_IPD_N, T::PS_T_HUFF_IPD_N, T::PS_F_HUFF_OPD_N, T::PS_T_HUFF_OPD_N};
     for (int i = 0; i < 10; ++i)
       if ((rc = e->upload(ph[i], ph_n[i], &D.ps_huff[i]))) return rc;
+    {
+      std::vector<uint32_t> lut(10 * 256);
+      for (int i = 0; i < 10; ++i) build_huff_lut(ph[i], 31, lut.data() + 256 * i);
+      if ((rc = e->upload(lut.data(), lut.size(), &D.ps_huff_lut))) return rc;
+    }
     if ((rc = e->upload(JT(PS_IPDOPD_COS_TAB), 9, &D.ps_ipdopd_cos))) return rc;
     if ((rc = e->upload(JT(PS_IPDOPD_SIN_TAB), 9, &D.ps_ipdopd_sin))) return rc;
     if ((rc = e->upload(JT(PS_FILTER_A), 3, &D.ps_filter_a))) return rc;

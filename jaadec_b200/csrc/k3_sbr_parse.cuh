@@ -537,15 +537,37 @@ __device__ inline int sbr_invf_mode(SbrBits& ld, SbrChanParse& c, int N_Q) {  //
   return 0;
 }
 
-__device__ inline int sbr_huff(SbrBits& ld, const int16_t* __restrict__ t, int& out) {  // :280-289
+// Channel.decodeHuffman (:280-289) / ps Huffman.read (ps/Huffman.java:264-276): a binary tree walked one bit per node.  The
+// walk through the bounds-checked reader was 45 % of this kernel's instructions (round-1 profile), and the codes are short,
+// so the first eight bits go through a 256-entry table built from the same tree on the host (build_huff_lut in
+// jaadb_engine.cu): a leaf within eight bits -> [23:16] code length, [15:0] the decoded value; otherwise bit 31 and the node
+// the walk continues from.  With fewer than eight bits left in the payload the bit-serial walk runs from the root, so the
+// end-of-stream behaviour is the reference's bit for bit.
+__device__ __forceinline__ int huff_decode(SbrBits& ld, const int16_t* __restrict__ t, const uint32_t* __restrict__ lut, int bias, int& out) {
   int index = 0;
+  if (ld.left() >= 8u) {
+    const uint32_t wi = ld.pos >> 5;
+    const uint32_t w = __funnelshift_l(ld.word(wi + 1), ld.word(wi), ld.pos & 31u);
+    const uint32_t e = __ldg(lut + (w >> 24));
+    if (!(e & 0x80000000u)) {
+      ld.pos += e >> 16;
+      out = (int)(int16_t)(e & 0xFFFFu);
+      return 0;
+    }
+    ld.pos += 8;
+    index = (int)(e & 0xFFFFu);
+  }
   while (index >= 0) {
     int bit;
     SBR_RD(bit, 1);
     index = t[index * 2 + bit];
   }
-  out = index + 64;
+  out = index + bias;
   return 0;
+}
+
+__device__ __forceinline__ int sbr_huff(SbrBits& ld, const SbrTablesDev& T, int table, int& out) {
+  return huff_decode(ld, T.huff[table], T.huff_lut + 256 * table, 64, out);
 }
 
 __device__ inline void sbr_extract_envelope(const SbrElemDev& S, SbrChanParse& c) {  // :192-240
@@ -589,9 +611,9 @@ __device__ inline int sbr_envelope(SbrBits& ld, const SbrCtx& C, SbrChanParse& c
   if ((c.L_E == 1) && (c.frame_class == SBR_FIXFIX)) c.amp_res = 0;
   else c.amp_res = S.hdr.amp_res;
   const int delta = coupled ? 1 : 0;
-  const int16_t *t_huff, *f_huff;
-  if (coupled) { t_huff = C.T->huff[c.amp_res ? 6 : 2]; f_huff = C.T->huff[c.amp_res ? 7 : 3]; }
-  else { t_huff = C.T->huff[c.amp_res ? 4 : 0]; f_huff = C.T->huff[c.amp_res ? 5 : 1]; }
+  int t_huff, f_huff;   // table numbers (SbrTablesDev::huff)
+  if (coupled) { t_huff = c.amp_res ? 6 : 2; f_huff = c.amp_res ? 7 : 3; }
+  else { t_huff = c.amp_res ? 4 : 0; f_huff = c.amp_res ? 5 : 1; }
   for (int env = 0; env < c.L_E; env++) {
     const int nb = S.n[c.f[env]];
     int v;
@@ -599,9 +621,9 @@ __device__ inline int sbr_envelope(SbrBits& ld, const SbrCtx& C, SbrChanParse& c
       const int bits = coupled ? (c.amp_res ? 5 : 6) : (c.amp_res ? 6 : 7);
       SBR_RD(v, bits);
       c.E[0][env] = (int16_t)(v << delta);
-      for (int band = 1; band < nb; band++) { SBR_TRY(sbr_huff(ld, f_huff, v)); c.E[band][env] = (int16_t)(v << delta); }
+      for (int band = 1; band < nb; band++) { SBR_TRY(sbr_huff(ld, *C.T, f_huff, v)); c.E[band][env] = (int16_t)(v << delta); }
     } else {
-      for (int band = 0; band < nb; band++) { SBR_TRY(sbr_huff(ld, t_huff, v)); c.E[band][env] = (int16_t)(v << delta); }
+      for (int band = 0; band < nb; band++) { SBR_TRY(sbr_huff(ld, *C.T, t_huff, v)); c.E[band][env] = (int16_t)(v << delta); }
     }
   }
   sbr_extract_envelope(S, c);
@@ -611,16 +633,15 @@ __device__ inline int sbr_envelope(SbrBits& ld, const SbrCtx& C, SbrChanParse& c
 __device__ inline int sbr_noise(SbrBits& ld, const SbrCtx& C, SbrChanParse& c, bool coupled) {  // :243-312
   const SbrElemDev& S = *C.S;
   const int delta = coupled ? 1 : 0;
-  const int16_t* t_huff = C.T->huff[coupled ? 9 : 8];
-  const int16_t* f_huff = C.T->huff[coupled ? 7 : 5];
+  const int t_huff = coupled ? 9 : 8, f_huff = coupled ? 7 : 5;
   for (int noise = 0; noise < c.L_Q; noise++) {
     int v;
     if (c.bs_df_noise[noise] == 0) {
       SBR_RD(v, 5);
       c.Q[0][noise] = (int16_t)(v << delta);
-      for (int band = 1; band < S.N_Q; band++) { SBR_TRY(sbr_huff(ld, f_huff, v)); c.Q[band][noise] = (int16_t)(v << delta); }
+      for (int band = 1; band < S.N_Q; band++) { SBR_TRY(sbr_huff(ld, *C.T, f_huff, v)); c.Q[band][noise] = (int16_t)(v << delta); }
     } else {
-      for (int band = 0; band < S.N_Q; band++) { SBR_TRY(sbr_huff(ld, t_huff, v)); c.Q[band][noise] = (int16_t)(v << delta); }
+      for (int band = 0; band < S.N_Q; band++) { SBR_TRY(sbr_huff(ld, *C.T, t_huff, v)); c.Q[band][noise] = (int16_t)(v << delta); }
     }
   }
   for (int l = 0; l < c.L_Q; l++) {
@@ -653,15 +674,8 @@ __device__ inline int sbr_harmonics(SbrBits& ld, SbrChanParse& c, int N_high) {
 __device__ inline int ps_nr_par(int id) { return id % 3 == 0 ? 10 : (id % 3 == 1 ? 20 : 34); }
 __device__ inline int ps_stride(int id) { return (id % 3) == 0 ? 2 : 0; }   // ICMode.stride
 
-__device__ inline int ps_huff(SbrBits& ld, const int16_t* __restrict__ t, int& out) {  // ps/Huffman.java:264-276
-  int index = 0;
-  while (index >= 0) {
-    int bit;
-    SBR_RD(bit, 1);
-    index = t[index * 2 + bit];
-  }
-  out = index + 31;
-  return 0;
+__device__ __forceinline__ int ps_huff(SbrBits& ld, const SbrTablesDev& T, int table, int& out) {  // ps/Huffman.java:264-276
+  return huff_decode(ld, T.ps_huff[table], T.ps_huff_lut + 256 * table, 31, out);
 }
 
 __device__ inline int ps_read_mode(SbrBits& ld, PsParamDev& p) {
@@ -682,8 +696,8 @@ __device__ inline int ps_read_data(SbrBits& ld, const SbrTablesDev& T, PsParamDe
     int dt, v;
     SBR_RD(dt, 1);
     p.dt[n] = (uint8_t)dt;
-    const int16_t* h = icc ? T.ps_huff[dt ? 5 : 4] : (p.mode < 3 ? T.ps_huff[dt ? 1 : 0] : T.ps_huff[dt ? 3 : 2]);
-    for (int i = 0; i < nr; i++) { SBR_TRY(ps_huff(ld, h, v)); p.index[n][i] = (int8_t)v; }
+    const int h = icc ? (dt ? 5 : 4) : (p.mode < 3 ? (dt ? 1 : 0) : (dt ? 3 : 2));
+    for (int i = 0; i < nr; i++) { SBR_TRY(ps_huff(ld, T, h, v)); p.index[n][i] = (int8_t)v; }
   }
   return 0;
 }
@@ -698,8 +712,8 @@ __device__ inline int ps_read_pd(SbrBits& ld, const SbrTablesDev& T, PsPdDev& p,
     int dt, v;
     SBR_RD(dt, 1);
     p.dt[n] = (uint8_t)dt;
-    const int16_t* h = T.ps_huff[(opd ? 8 : 6) + (dt ? 1 : 0)];
-    for (int i = 0; i < nr; i++) { SBR_TRY(ps_huff(ld, h, v)); p.index[n][i] = (int8_t)v; }
+    const int h = (opd ? 8 : 6) + (dt ? 1 : 0);
+    for (int i = 0; i < nr; i++) { SBR_TRY(ps_huff(ld, T, h, v)); p.index[n][i] = (int8_t)v; }
   }
   return 0;
 }

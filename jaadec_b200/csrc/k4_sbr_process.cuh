@@ -1282,18 +1282,22 @@ constexpr int kK5Threads = 96;
 constexpr int kK5PhaseThread = 80;  // an otherwise idle thread: the sequential IPD/OPD phase bookkeeping
 constexpr int kK5Bands = 71;        // 10 hybrid sub-bands + QMF bands 3..63
 constexpr int kK5AllPass = 30;      // of which run the all-pass chain: the hybrid ones and QMF bands 3..22
-constexpr int kK5Floats = 2 * 32 * kXsStride + 2 * 32 * 24 + 32 * 20 + 3 * 88 + kK5Bands * 28 + kK5AllPass * 30 + 22 * 8 + 72 + 22 * 5 * 4 + 80;
+constexpr int kK5EStride = 65;      // energy plane row: 64 bands + 1 (the slot threads read a column without bank conflicts)
+constexpr int kK5Floats = 32 * kK5EStride + 2 * 32 * 24 + 32 * 20 + 3 * 88 + kK5Bands * 28 + kK5AllPass * 30 + 22 * 8 + 72 + 22 * 5 * 4 + 80;
 static_assert(kK5Floats % 4 == 0, "PsFrameDev must land 16-byte aligned");
 constexpr size_t k5_smem_bytes() { return sizeof(float) * kK5Floats + sizeof(PsFrameDev); }
 
-__global__ void __launch_bounds__(kK5Threads)
+__global__ void __launch_bounds__(kK5Threads, 6)
 k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev* __restrict__ sframes,
              const PsFrameDev* __restrict__ ps_frames, PsChanDev* __restrict__ ps_chans, const float* __restrict__ xg,
              float* __restrict__ xps, SbrTablesDev T, K4Tile tile) {
   extern __shared__ __align__(16) float k5_smem[];
-  float* xl = k5_smem;                                   // [32][kXsStride]
-  float* xr = xl + 32 * kXsStride;                       // [32][kXsStride]
-  float* hyl = xr + 32 * kXsStride;                      // [32][12][2]
+  // The frame's two 32 x 64 QMF matrices are NOT staged in shared memory (they were: 33 KB of the 58 KB a CTA needed, three
+  // CTAs = nine warps per SM): the decorrelator's band threads read X_left from the tile workspace (L2) slot by slot and
+  // write both outputs straight to xps; the only whole-matrix quantity another thread needs is |X|^2 for the transient
+  // detector's band energies, which gets its own plane.
+  float* eplane = k5_smem;                               // [32][kK5EStride] |X_left[n][band]|^2, QMF bands 3..63
+  float* hyl = eplane + 32 * kK5EStride;                 // [32][12][2]
   float* hyr = hyl + 32 * 24;                            // [32][12][2]
   float* pg = hyr + 32 * 24;                             // [32][20] band energies, then transient ratios
   float* hwork = pg + 32 * 20;                           // [3][44][2] hybrid analysis input
@@ -1304,8 +1308,6 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
   float* phases = hybuf + 72;                            // [22][5][4] IPD/OPD: phaseLeft, phaseRight per (group, envelope)
   float* pdprev = phases + 22 * 5 * 4;                   // [20][2][2] PDData.prev
   PsFrameDev* pp = reinterpret_cast<PsFrameDev*>(pdprev + 80);
-#define XL(l, k, c) xl[(l) * kXsStride + (k) * 2 + (c)]
-#define XR(l, k, c) xr[(l) * kXsStride + (k) * 2 + (c)]
 #define HYL(n, k, c) hyl[((n) * 12 + (k)) * 2 + (c)]
 #define HYR(n, k, c) hyr[((n) * 12 + (k)) * 2 + (c)]
   const int t = threadIdx.x;
@@ -1376,17 +1378,20 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
     __syncthreads();
     if (t < (int)(sizeof(PsFrameDev) / 16)) reinterpret_cast<uint4*>(pp)[t] = __ldg(reinterpret_cast<const uint4*>(pf) + t);
     const float* X = Xrun + 32 * (size_t)(fp->ord - ord_lo) * kXgRow;
-    // X_left: the band-limited copy of Xsbr (SBR1.processPS); hybrid analysis input: QMF bands 0..2 of slots 6..37
+    // X_left = the band-limited copy of Xsbr (SBR1.processPS): band t of slot l is X[l + 2][t] below the limit, zero above.
+    // Hybrid analysis input: QMF bands 0..2 of slots 6..37
+    const int lim_lo = k4_x_limit(fp, mode, 0), lim_hi = k4_x_limit(fp, mode, 31), fs = mode == 2 ? fp->t_E[0] : 0;
+    float* outl = xps + ((size_t)(blockIdx.x * tile.ft + (it - tile.lo)) * 2) * 32 * kXgRow;
+    float* outr = outl + 32 * kXgRow;
     if (t < 64) {
-      const int lim_lo = k4_x_limit(fp, mode, 0), lim_hi = k4_x_limit(fp, mode, 31), fs = mode == 2 ? fp->t_E[0] : 0;
       float2 xv[32];
 #pragma unroll
       for (int l = 0; l < 32; ++l) xv[l] = __ldg(reinterpret_cast<const float2*>(X + (size_t)(l + kSbrHfAdj) * kXgRow) + t);
 #pragma unroll
       for (int l = 0; l < 32; ++l) {
         const int lim = l < fs ? lim_lo : lim_hi;
-        XL(l, t, 0) = t < lim ? xv[l].x : 0.f;
-        XL(l, t, 1) = t < lim ? xv[l].y : 0.f;
+        const float re = t < lim ? xv[l].x : 0.f, im = t < lim ? xv[l].y : 0.f;
+        eplane[l * kK5EStride + t] = (re * re) + (im * im);
       }
     } else {
       // work[0..11] = history, work[12 + n] = X[n + 6][band]: rows 6..31 come from X_left, rows 32..37 straight
@@ -1503,9 +1508,12 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
           const int lo = gb[g2], hi2 = g2 < 10 ? gb[g2] + 1 : gb[g2 + 1];
 #pragma unroll
           for (int s2 = lo; s2 < hi2; ++s2) {
-            const float re = g2 < 10 ? HYL(i, s2, 0) : XL(i, s2, 0);
-            const float im = g2 < 10 ? HYL(i, s2, 1) : XL(i, s2, 1);
-            P[pb] += (re * re) + (im * im);
+            if (g2 < 10) {
+              const float re = HYL(i, s2, 0), im = HYL(i, s2, 1);
+              P[pb] += (re * re) + (im * im);
+            } else {
+              P[pb] += eplane[i * kK5EStride + s2];   // = (re * re) + (im * im) of X_left[i][s2], formed by the band's thread
+            }
           }
         }
 #pragma unroll
@@ -1582,7 +1590,12 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
       const bool bkm = bk != 0;   // FBType.bkm tests `& ~NEGATE_IPD_MASK` (FBType.java:71-73, A-13): true for every bk != 0
       float G11 = 0, G12 = 0, G21 = 0, G22 = 0, dG11 = 0, dG12 = 0, dG21 = 0, dG22 = 0;
       int env = -1, env_end = 0;
+      // X_left[n][sb] of a QMF band comes from the tile workspace, one slot ahead of its use
+      const float2* xcol = reinterpret_cast<const float2*>(X + (size_t)kSbrHfAdj * kXgRow) + sb;
+      float2 x_next = hyb ? make_float2(0.f, 0.f) : __ldg(xcol);
       for (int n = 0; n < 32; ++n) {
+        const float2 x_cur = x_next;
+        if (!hyb && n < 31) x_next = __ldg(xcol + (size_t)(n + 1) * (kXgRow / 2));
         if (n == env_end) {
           // next envelope: target H from the IID / ICC indices (:424-478), linear interpolation over its length
           do { ++env; env_end = pp->border[env + 1]; } while (env + 1 < num_env && env_end <= n);
@@ -1629,8 +1642,9 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
           }
         }
         // -- decorrelate
-        const float re = hyb ? HYL(n, sb, 0) : XL(n, sb, 0);
-        const float im = hyb ? HYL(n, sb, 1) : XL(n, sb, 1);
+        const int lim = n < fs ? lim_lo : lim_hi;
+        const float re = hyb ? HYL(n, sb, 0) : (sb < lim ? x_cur.x : 0.f);
+        const float im = hyb ? HYL(n, sb, 1) : (sb < lim ? x_cur.y : 0.f);
         float r0Re, r0Im;
         if (delay_band) {
           float* d = my_dly + 2 * di;
@@ -1678,7 +1692,10 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
           oIm += (G12 * re) + (G22 * rRe);
         }
         if (hyb) { HYL(n, sb, 0) = lRe; HYL(n, sb, 1) = lIm; HYR(n, sb, 0) = oRe; HYR(n, sb, 1) = oIm; }
-        else { XL(n, sb, 0) = lRe; XL(n, sb, 1) = lIm; XR(n, sb, 0) = oRe; XR(n, sb, 1) = oIm; }
+        else {
+          reinterpret_cast<float2*>(outl + (size_t)n * kXgRow)[sb] = make_float2(lRe, lIm);
+          reinterpret_cast<float2*>(outr + (size_t)n * kXgRow)[sb] = make_float2(oRe, oIm);
+        }
       }
       if (sb == ps_group_border(gr)) {
         hprev[gr * 8] = hp11; hprev[gr * 8 + 1] = hp12; hprev[gr * 8 + 2] = hp21; hprev[gr * 8 + 3] = hp22;
@@ -1689,31 +1706,20 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
       td = (td + 32) % 2; s0 = (s0 + 32) % 3; s1 = (s1 + 32) % 4; s2 = (s2 + 32) % 5;
     }
     __syncthreads();
-    // ---- hybrid synthesis (ps/Filterbank.java:70-86) for both channels: thread n
+    // ---- hybrid synthesis (ps/Filterbank.java:70-86) for both channels: thread n; QMF bands 0..2 of the two matrices go out
     if (t < 32) {
+      float a0[2] = {0, 0}, b0[2] = {0, 0}, a1[2] = {0, 0}, b1[2] = {0, 0}, a2[2] = {0, 0}, b2[2] = {0, 0};
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        float a0 = 0, b0 = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { a0 += HYL(t, k, c); b0 += HYR(t, k, c); }
-        XL(t, 0, c) = a0; XR(t, 0, c) = b0;
-        float a1 = 0, b1 = 0;
-        a1 += HYL(t, 8, c); a1 += HYL(t, 9, c); b1 += HYR(t, 8, c); b1 += HYR(t, 9, c);
-        XL(t, 1, c) = a1; XR(t, 1, c) = b1;
-        float a2 = 0, b2 = 0;
-        a2 += HYL(t, 10, c); a2 += HYL(t, 11, c); b2 += HYR(t, 10, c); b2 += HYR(t, 11, c);
-        XL(t, 2, c) = a2; XR(t, 2, c) = b2;
+        for (int k = 0; k < 8; ++k) { a0[c] += HYL(t, k, c); b0[c] += HYR(t, k, c); }
+        a1[c] += HYL(t, 8, c); a1[c] += HYL(t, 9, c); b1[c] += HYR(t, 8, c); b1[c] += HYR(t, 9, c);
+        a2[c] += HYL(t, 10, c); a2[c] += HYL(t, 11, c); b2[c] += HYR(t, 10, c); b2[c] += HYR(t, 11, c);
       }
-    }
-    __syncthreads();
-    // ---- the two matrices go out: thread t = band
-    if (t < 64) {
-      float* outl = xps + ((size_t)(blockIdx.x * tile.ft + (it - tile.lo)) * 2) * 32 * kXgRow;
-      float* outr = outl + 32 * kXgRow;
-      for (int l = 0; l < 32; ++l) {
-        reinterpret_cast<float2*>(outl + (size_t)l * kXgRow)[t] = make_float2(XL(l, t, 0), XL(l, t, 1));
-        reinterpret_cast<float2*>(outr + (size_t)l * kXgRow)[t] = make_float2(XR(l, t, 0), XR(l, t, 1));
-      }
+      float2* ol = reinterpret_cast<float2*>(outl + (size_t)t * kXgRow);
+      float2* orr = reinterpret_cast<float2*>(outr + (size_t)t * kXgRow);
+      ol[0] = make_float2(a0[0], a0[1]); ol[1] = make_float2(a1[0], a1[1]); ol[2] = make_float2(a2[0], a2[1]);
+      orr[0] = make_float2(b0[0], b0[1]); orr[1] = make_float2(b1[0], b1[1]); orr[2] = make_float2(b2[0], b2[1]);
     }
   }
   __syncthreads();
@@ -1735,8 +1741,6 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
   if (t < 80) (&pst->pd_prev[0][0][0])[t] = pdprev[t];
   if (t == kK5PhaseThread) pst->phase_hist = phase_hist;
   if (t < 20) { pst->P_PeakDecayNrg[t] = peak; pst->P_prev[t] = pprev; pst->P_SmoothPeakDecayDiffNrg_prev[t] = smooth_prev; }
-#undef XL
-#undef XR
 #undef HYL
 #undef HYR
 }

@@ -192,6 +192,8 @@ static_assert(sizeof(SbrChanDev) % 16 == 0, "SbrChanDev is copied with 16-byte a
 // Read-only tables of the SBR tool (engine-owned device memory).
 struct SbrTablesDev {
   const int16_t* huff[10];          // t_env15, f_env15, t_bal15, f_bal15, t_env30, f_env30, t_bal30, f_bal30, t_noise30, t_nbal30
+  const uint32_t* huff_lut;         // [10][256] first-eight-bits tables of the same trees (k3_sbr_parse.cuh huff_decode)
+  const uint32_t* ps_huff_lut;      // [10][256]
   const float* e_deq;               // [64]
   const float* q_div;               // [31]
   const float* q_div2;              // [31]
