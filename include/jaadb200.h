@@ -208,8 +208,8 @@ int jaadb_batch_tap(jaadb_batch* b, uint32_t frame, uint32_t ch, int16_t* q, int
  * sbr_types.cuh, SbrFrameDev); returns its size, 0 if the frame's stream carries no SBR, or a negative JAADB_E_* code. */
 int jaadb_batch_tap_sbr(jaadb_batch* b, uint32_t frame, uint32_t ch, void* out, uint32_t out_bytes);
 /* PS parity tap: the parametric-stereo parameters of frame `frame` after PSImpl.ps_data_decode (A/ps/PSImpl.java:129-199) as
- * the mixing stage uses them (PsFrameDev, 224 bytes: use_ps, num_env, border_position[6], iid / icc mode, iid[5][20],
- * icc[5][20]); returns its size, 0 if the frame's stream carries no parametric stereo, or a negative JAADB_E_* code. */
+ * the mixing stage uses them (PsFrameDev, 320 bytes: use_ps, num_env, border_position[6], iid / icc mode, iid[5][20],
+ * icc[5][20], Extension.nr_par, ExtData.enabled, ipd[5][17]); returns its size, 0 if the frame's stream carries no parametric stereo, or a negative JAADB_E_* code. */
 int jaadb_batch_tap_ps(jaadb_batch* b, uint32_t frame, void* out, uint32_t out_bytes);
 
 /* ---- container indexers (host side; frames for jaadb_decode) --------------

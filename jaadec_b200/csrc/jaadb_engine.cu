@@ -228,7 +228,8 @@ struct jaadb_engine {
   static constexpr int kK4MaxParts = 8;
   cudaStream_t k4_stream[kK4MaxParts - 1] = {};
   cudaEvent_t k4_fork = nullptr, k4_join[kK4MaxParts - 1] = {};
-  int k4_parts = 2;
+  int k4_parts = 0;        // parts the K4 pipeline is cut into (launch_decode); 0: one part per full wave of K4b warps
+  int sm_count = 148;
 
   // workspace of the one-call path (jaadb_decode): grow-only, so a steady stream of calls allocates nothing.
   // The call is cut into chunks of consecutive frames; chunk k's PCM goes out over PCIe on copy_stream while
@@ -527,9 +528,13 @@ int init_sbr(jaadb_engine* e) {
   CUDA_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->d_sbr_elem), sizeof(SbrElemDev) * ns * 2));
   CUDA_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->d_sbr_chan), sizeof(SbrChanDev) * ns * kSbrChansPerStream));
   CUDA_TRY(e, cudaMalloc(reinterpret_cast<void**>(&e->d_ps_chan), sizeof(PsChanDev) * ns));
-  cudaFuncSetAttribute(k3_sbr_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SbrElemDev) * kK3WarpsPerBlock));
+  cudaFuncSetAttribute(k3_sbr_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_smem_bytes());
+#ifdef K3_CARVEOUT
+  cudaFuncSetAttribute(k3_sbr_parse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, K3_CARVEOUT);
+#endif
   cudaFuncSetAttribute(k4a_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4a_smem_bytes());
   cudaFuncSetAttribute(k4b_hf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4b_smem_bytes());
+  cudaFuncSetAttribute(k4b_hf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // five CTAs of 44 KB
 #define K4C_ATTR(FMT)                                                                                                        \
   cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes()); \
   cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes()); \
@@ -853,7 +858,7 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
   if (n_sbr_runs) {
     // SBR payload parse before the filterbank: an exception inside SBR.decode fails the whole frame
     const int blocks = (int)((n_sbr_runs + kK3WarpsPerBlock - 1) / kK3WarpsPerBlock);
-    k3_sbr_parse_kernel<<<blocks, 32 * kK3WarpsPerBlock, sizeof(SbrElemDev) * kK3WarpsPerBlock, e->stream>>>(
+    k3_sbr_parse_kernel<<<blocks, 32 * kK3WarpsPerBlock, k3_smem_bytes(), e->stream>>>(
         B.blob, B.frames, B.fside, B.sbr_runs, n_sbr_runs, B.run_frames, e->d_sbr_elem, B.sbr_frames, B.ps_frames, e->sbr_tables, e->sbr_const);
     ++*launches;
   }
@@ -923,7 +928,15 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
     // half's analysis / synthesis, and the part-filled last wave of a K4b launch is filled from the other stream.
     struct Part { uint32_t p0, pn, q0, qn; cudaStream_t st; };   // plain runs [p0, p0 + pn), SBR+PS runs [q0, q0 + qn)
     Part parts[jaadb_engine::kK4MaxParts];
-    const int n_parts = (n_k4_runs >= 8u * (uint32_t)e->k4_parts) ? e->k4_parts : 1;
+    // Part size: K4b's waves are whole (every warp walks the same number of frames), so a part is cut to fill the SMs'
+    // resident K4b warps once -- 8192 channel runs are 2.77 waves of 2960: three parts of 0.92 waves instead of two parts
+    // of two waves each.
+    int want = e->k4_parts;
+    if (want <= 0) {
+      const uint32_t wave = (uint32_t)e->sm_count * K4B_MIN_BLOCKS * kK4bWarps;
+      want = (int)std::min<uint32_t>(std::max<uint32_t>((n_k4_runs + wave / 2) / wave, 1u), (uint32_t)jaadb_engine::kK4MaxParts);
+    }
+    const int n_parts = (n_k4_runs >= 8u * (uint32_t)want) ? want : 1;
     for (int i = 0; i < n_parts; ++i) {
       // (cut between elements: a CPE's two channel runs are neighbours)
       const uint32_t pa = (uint32_t)((uint64_t)n_plain * i / n_parts) & ~1u, pb = (i + 1 == n_parts) ? n_plain : ((uint32_t)((uint64_t)n_plain * (i + 1) / n_parts) & ~1u);
@@ -1040,7 +1053,9 @@ int jaadb_engine_create(const jaadb_options* opts, jaadb_engine** out) {
     if (cudaEventCreate(&ev) != cudaSuccess) return fail(JAADB_E_CUDA);
   if (const char* v = getenv("JAADB200_K4_PARTS")) e->k4_parts = std::min(std::max(atoi(v), 1), (int)jaadb_engine::kK4MaxParts);   // tuning experiments only
   if (cudaEventCreateWithFlags(&e->k4_fork, cudaEventDisableTiming) != cudaSuccess) return fail(JAADB_E_CUDA);
-  for (int i = 0; i + 1 < e->k4_parts; ++i) {
+  cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, opts->device);
+  if (e->sm_count <= 0) e->sm_count = 148;
+  for (int i = 0; i + 1 < jaadb_engine::kK4MaxParts; ++i) {
     if (cudaStreamCreateWithFlags(&e->k4_stream[i], cudaStreamNonBlocking) != cudaSuccess) return fail(JAADB_E_CUDA);
     if (cudaEventCreateWithFlags(&e->k4_join[i], cudaEventDisableTiming) != cudaSuccess) return fail(JAADB_E_CUDA);
   }

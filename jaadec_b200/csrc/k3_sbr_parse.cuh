@@ -25,18 +25,67 @@ namespace jaadb {
 enum { SBR_FIXFIX = 0, SBR_FIXVAR = 1, SBR_VARFIX = 2, SBR_VARVAR = 3 };
 enum { SBR_LO_RES = 0, SBR_HI_RES = 1 };
 
+// The Huffman tables (20 KB of 8-bit front tables, the trees behind them) are the only global data the parse touches again
+// and again; with 200 KB of the SM's L1 carved out as shared memory for the element states they compete for what is left
+// with data that is read once (payload words, frame descriptors, the state copy-in).  So: keep the former, do not
+// allocate the latter.
+#ifndef K3_L1_HINTS
+#define K3_L1_HINTS 1
+#endif
+__device__ __forceinline__ uint32_t k3_ld_keep(const uint32_t* p) {
+#if K3_L1_HINTS
+  uint32_t v;
+  asm("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ int k3_ld_keep(const int16_t* p) {
+#if K3_L1_HINTS
+  int v;
+  asm("ld.global.nc.L1::evict_last.s16 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint32_t k3_ld_stream(const uint32_t* p) {
+#if K3_L1_HINTS
+  uint32_t v;
+  asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint32_t k3_ld_stream_rw(const uint32_t* p) {   // data this kernel also writes: no .nc
+#if K3_L1_HINTS
+  uint32_t v;
+  asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return *p;
+#endif
+}
+
+// Bit reader over one SBR payload.  The warp stages the payload's words in shared memory, already in big-endian bit
+// order (k3_sbr_parse_kernel), so a read is two shared loads and a funnel shift: no 64-bit address arithmetic, no byte
+// swap and no trip to L1 per field.  `pos` / `end` count bits from bit 31 of words[0].
 struct SbrBits {
   const uint32_t* words;
   uint32_t pos, end;
-  __device__ __forceinline__ uint32_t word(uint32_t i) const { return __byte_perm(__ldg(words + i), 0, 0x0123); }
+  __device__ __forceinline__ uint32_t word(uint32_t i) const { return words[i]; }
   __device__ __forceinline__ uint32_t left() const { return end > pos ? end - pos : 0u; }
+  __device__ __forceinline__ uint32_t peek32() const {
+    const uint32_t wi = pos >> 5;
+    return __funnelshift_l(words[wi + 1], words[wi], pos & 31u);
+  }
   // n <= 25
   __device__ __forceinline__ bool get(int n, int& v) {
     if (n == 0) { v = 0; return true; }
-    if (left() < (uint32_t)n) return false;
-    const uint32_t wi = pos >> 5;
-    const uint32_t w = __funnelshift_l(word(wi + 1), word(wi), pos & 31u);
-    v = (int)(w >> (32 - n));
+    if (pos + (uint32_t)n > end) return false;
+    v = (int)(peek32() >> (32 - n));
     pos += n;
     return true;
   }
@@ -546,9 +595,7 @@ __device__ inline int sbr_invf_mode(SbrBits& ld, SbrChanParse& c, int N_Q) {  //
 __device__ __forceinline__ int huff_decode(SbrBits& ld, const int16_t* __restrict__ t, const uint32_t* __restrict__ lut, int bias, int& out) {
   int index = 0;
   if (ld.left() >= 8u) {
-    const uint32_t wi = ld.pos >> 5;
-    const uint32_t w = __funnelshift_l(ld.word(wi + 1), ld.word(wi), ld.pos & 31u);
-    const uint32_t e = __ldg(lut + (w >> 24));
+    const uint32_t e = k3_ld_keep(lut + (ld.peek32() >> 24));
     if (!(e & 0x80000000u)) {
       ld.pos += e >> 16;
       out = (int)(int16_t)(e & 0xFFFFu);
@@ -560,7 +607,7 @@ __device__ __forceinline__ int huff_decode(SbrBits& ld, const int16_t* __restric
   while (index >= 0) {
     int bit;
     SBR_RD(bit, 1);
-    index = t[index * 2 + bit];
+    index = k3_ld_keep(t + index * 2 + bit);
   }
   out = index + bias;
   return 0;
@@ -616,15 +663,18 @@ __device__ inline int sbr_envelope(SbrBits& ld, const SbrCtx& C, SbrChanParse& c
   else { t_huff = c.amp_res ? 4 : 0; f_huff = c.amp_res ? 5 : 1; }
   for (int env = 0; env < c.L_E; env++) {
     const int nb = S.n[c.f[env]];
-    int v;
+    int v, band = 0, table = t_huff;
     if (c.bs_df_env[env] == 0) {
       const int bits = coupled ? (c.amp_res ? 5 : 6) : (c.amp_res ? 6 : 7);
       SBR_RD(v, bits);
       c.E[0][env] = (int16_t)(v << delta);
-      for (int band = 1; band < nb; band++) { SBR_TRY(sbr_huff(ld, *C.T, f_huff, v)); c.E[band][env] = (int16_t)(v << delta); }
-    } else {
-      for (int band = 0; band < nb; band++) { SBR_TRY(sbr_huff(ld, *C.T, t_huff, v)); c.E[band][env] = (int16_t)(v << delta); }
+      band = 1;
+      table = f_huff;
     }
+    const int16_t* tree = C.T->huff[table];
+    const uint32_t* lut = C.T->huff_lut + 256 * table;
+#pragma unroll 1
+    for (; band < nb; band++) { SBR_TRY(huff_decode(ld, tree, lut, 64, v)); c.E[band][env] = (int16_t)(v << delta); }
   }
   sbr_extract_envelope(S, c);
   return 0;
@@ -635,14 +685,17 @@ __device__ inline int sbr_noise(SbrBits& ld, const SbrCtx& C, SbrChanParse& c, b
   const int delta = coupled ? 1 : 0;
   const int t_huff = coupled ? 9 : 8, f_huff = coupled ? 7 : 5;
   for (int noise = 0; noise < c.L_Q; noise++) {
-    int v;
+    int v, band = 0, table = t_huff;
     if (c.bs_df_noise[noise] == 0) {
       SBR_RD(v, 5);
       c.Q[0][noise] = (int16_t)(v << delta);
-      for (int band = 1; band < S.N_Q; band++) { SBR_TRY(sbr_huff(ld, *C.T, f_huff, v)); c.Q[band][noise] = (int16_t)(v << delta); }
-    } else {
-      for (int band = 0; band < S.N_Q; band++) { SBR_TRY(sbr_huff(ld, *C.T, t_huff, v)); c.Q[band][noise] = (int16_t)(v << delta); }
+      band = 1;
+      table = f_huff;
     }
+    const int16_t* tree = C.T->huff[table];
+    const uint32_t* lut = C.T->huff_lut + 256 * table;
+#pragma unroll 1
+    for (; band < S.N_Q; band++) { SBR_TRY(huff_decode(ld, tree, lut, 64, v)); c.Q[band][noise] = (int16_t)(v << delta); }
   }
   for (int l = 0; l < c.L_Q; l++) {
     if (c.bs_df_noise[l] == 0) {
@@ -724,8 +777,8 @@ __device__ inline int ps_decode(SbrBits& ld, const SbrTablesDev& T, PsParseDev& 
   SBR_RD(v, 1);
   if (v) {
     P.header_read = 1;
-    SBR_TRY(ps_read_mode(ld, P.iid));
-    SBR_TRY(ps_read_mode(ld, P.icc));
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) SBR_TRY(ps_read_mode(ld, k ? P.icc : P.iid));
     // Extension.readMode (ps/Extension.java:31-38)
     SBR_RD(v, 1);
     P.ext_enabled = (uint8_t)v;
@@ -740,8 +793,8 @@ __device__ inline int ps_decode(SbrBits& ld, const SbrTablesDev& T, PsParseDev& 
   P.num_env = (uint8_t)num_env;
   if (P.var_borders)
     for (int n = 1; n < num_env + 1; n++) { SBR_RD(v, 5); P.border_position[n] = (uint8_t)(v + 1); }
-  SBR_TRY(ps_read_data(ld, T, P.iid, false, num_env));
-  SBR_TRY(ps_read_data(ld, T, P.icc, true, num_env));
+#pragma unroll 1
+  for (int k = 0; k < 2; ++k) SBR_TRY(ps_read_data(ld, T, k ? P.icc : P.iid, k == 1, num_env));
   if (P.ext_enabled) {
     // Extension.readData (ps/Extension.java:40-59): cnt bytes in a sub-stream; extension id 0 is ExtData.readData
     // (ps/ExtData.java:17-25), every other id only consumes its two bits
@@ -758,8 +811,8 @@ __device__ inline int ps_decode(SbrBits& ld, const SbrTablesDev& T, PsParseDev& 
         if (!sub.get(1, v)) return JAADB_ST_EOS;
         P.ext_data_enabled = (uint8_t)v;
         if (v) {
-          SBR_TRY(ps_read_pd(sub, T, P.ipd, false, num_env));
-          SBR_TRY(ps_read_pd(sub, T, P.opd, true, num_env));
+#pragma unroll 1
+          for (int k = 0; k < 2; ++k) SBR_TRY(ps_read_pd(sub, T, k ? P.opd : P.ipd, k == 1, num_env));
         }
         if (!sub.get(1, v)) return JAADB_ST_EOS;
       }
@@ -770,35 +823,57 @@ __device__ inline int ps_decode(SbrBits& ld, const SbrTablesDev& T, PsParseDev& 
   return 0;
 }
 
+// ps_data_decode and what it calls run on the whole warp: every lane reads the same fields of the element's state in
+// shared memory, so the control flow is uniform; element-wise steps (time-differential rows, the stride expansion, the
+// copies) take one lane per parameter, the frequency-differential running sums stay on lane 0.  Rows are finished with a
+// __syncwarp() before anything reads them.
+
 // Envelope.decode (:45-74) for one envelope of one parameter set
-__device__ inline void ps_decode_env(PsParamDev& p, bool icc, int env) {
+__device__ inline void ps_decode_env(PsParamDev& p, bool icc, int env, int lane) {
   int8_t* ix = p.index[env];
-  if (p.mode < 0) { p.dt[env] = 0; for (int i = 0; i < 34; ++i) ix[i] = 0; return; }
+  if (p.mode < 0) {
+    if (lane == 0) p.dt[env] = 0;
+    for (int i = lane; i < 34; i += 32) ix[i] = 0;
+    __syncwarp();
+    return;
+  }
   const int st = ps_stride(p.mode), nr = ps_nr_par(p.mode);
   const int lim = icc ? 7 : (p.mode < 3 ? 7 : 15);
   const int lo = icc ? 0 : -lim;
   const int8_t* prev = env == 0 ? p.first : p.index[env - 1];
   if (p.dt[env]) {
-    for (int i = 0; i < nr; i++) ix[i] = (int8_t)min(max(prev[i * st] + ix[i], lo), lim);
-  } else {
+    for (int i = lane; i < nr; i += 32) ix[i] = (int8_t)min(max(prev[i * st] + ix[i], lo), lim);
+  } else if (lane == 0) {
     int pc = ix[0];
+#pragma unroll 1
     for (int i = 1; i < nr; i++) { pc = min(max(pc + ix[i], lo), lim); ix[i] = (int8_t)pc; }
   }
-  if (st > 1)
-    for (int i = st * nr - 1; i > 0; --i) ix[i] = ix[i / st];
+  __syncwarp();
+  if (st > 1) {
+    // for (i = st * nr - 1; i > 0; --i) ix[i] = ix[i / st]: every entry takes the value its source had before the loop
+    // (the sources lie below the entries still to be written); st > 1 only comes with nr = 10, i.e. 20 entries
+    const int n = st * nr;
+    int8_t v = 0;
+    if (lane < n) v = ix[lane / st];
+    __syncwarp();
+    if (lane > 0 && lane < n) ix[lane] = v;
+    __syncwarp();
+  }
 }
 
-// PSImpl.ps_data_decode (:137-199) -> the frame record K4 mixes with
-__device__ inline void ps_data_decode(PsParseDev& P, PsFrameDev& o) {
+// PSImpl.ps_data_decode (:137-199) -> the frame record K4 mixes with.  Returns Extension.nr_par as the record holds it.
+__device__ inline int ps_data_decode(PsParseDev& P, PsFrameDev& o, int lane) {
   int num_env = P.data_available ? P.num_env : 0;
   PsParamDev* ps[2] = {&P.iid, &P.icc};
   for (int k = 0; k < 2; ++k) {
     PsParamDev& p = *ps[k];
     if (num_env == 0) {
-      if (p.mode >= 0) { for (int i = 0; i < 34; ++i) p.index[0][i] = p.first[i]; }
-      else { p.dt[0] = 0; for (int i = 0; i < 34; ++i) p.index[0][i] = 0; }
+      const bool on = p.mode >= 0;
+      if (!on && lane == 0) p.dt[0] = 0;
+      for (int i = lane; i < 34; i += 32) p.index[0][i] = on ? p.first[i] : (int8_t)0;
+      __syncwarp();
     } else {
-      for (int env = 0; env < num_env; env++) ps_decode_env(p, k == 1, env);
+      for (int env = 0; env < num_env; env++) ps_decode_env(p, k == 1, env, lane);
     }
   }
   // Extension.decode / ExtData.decode (ps/Extension.java:61-64, ExtData.java:27-32) with PDMode: stride 1, clip = idx & 7
@@ -807,69 +882,93 @@ __device__ inline void ps_data_decode(PsParseDev& P, PsFrameDev& o) {
   if (ext_live && P.ext_data_enabled) {
     for (int k = 0; k < 2; ++k) {
       PsPdDev& p = *pd[k];
+      const bool on = p.mode >= 0;
       if (num_env == 0) {
-        if (p.mode >= 0) { for (int i = 0; i < 17; ++i) p.index[0][i] = p.first[i]; }
-        else { p.dt[0] = 0; for (int i = 0; i < 17; ++i) p.index[0][i] = 0; }
+        if (!on && lane == 0) p.dt[0] = 0;
+        if (lane < 17) p.index[0][lane] = on ? p.first[lane] : (int8_t)0;
+        __syncwarp();
       } else {
         for (int env = 0; env < num_env; env++) {
           int8_t* ix = p.index[env];
-          if (p.mode < 0) { p.dt[env] = 0; for (int i = 0; i < 17; ++i) ix[i] = 0; continue; }
-          const int nr = ps_pd_nr_par(p.mode);
-          const int8_t* prev = env == 0 ? p.first : p.index[env - 1];
-          if (p.dt[env]) {
-            for (int i = 0; i < nr; i++) ix[i] = (int8_t)((prev[i] + ix[i]) & 7);
+          if (!on) {
+            if (lane == 0) p.dt[env] = 0;
+            if (lane < 17) ix[lane] = 0;
           } else {
-            int pc = ix[0];
-            for (int i = 1; i < nr; i++) { pc = (pc + ix[i]) & 7; ix[i] = (int8_t)pc; }
+            const int nr = ps_pd_nr_par(p.mode);
+            const int8_t* prev = env == 0 ? p.first : p.index[env - 1];
+            if (p.dt[env]) {
+              if (lane < nr) ix[lane] = (int8_t)((prev[lane] + ix[lane]) & 7);
+            } else if (lane == 0) {
+              int pc = ix[0];
+#pragma unroll 1
+              for (int i = 1; i < nr; i++) { pc = (pc + ix[i]) & 7; ix[i] = (int8_t)pc; }
+            }
           }
+          __syncwarp();
         }
       }
     }
   }
   if (num_env == 0) num_env = 1;
   for (int k = 0; k < 2; ++k)
-    for (int i = 0; i < 34; ++i) ps[k]->first[i] = ps[k]->index[num_env - 1][i];
+    for (int i = lane; i < 34; i += 32) ps[k]->first[i] = ps[k]->index[num_env - 1][i];
   // ExtData.update runs whether or not the frame carried phase data (ps/ExtData.java:34-37); ExtData.restore in the
   // variable-border branch below calls update as well (:39-42), i.e. changes nothing more
-  if (ext_live)
-    for (int k = 0; k < 2; ++k)
-      for (int i = 0; i < 17; ++i) pd[k]->first[i] = pd[k]->index[num_env - 1][i];
-  P.data_available = 0;
+  if (ext_live && lane < 17)
+    for (int k = 0; k < 2; ++k) pd[k]->first[lane] = pd[k]->index[num_env - 1][lane];
   const int L = 32;
-  if (!P.var_borders) {
-    P.border_position[0] = 0;
-    for (int env = 1; env < num_env; env++) P.border_position[env] = (uint8_t)((env * L) / num_env);
-    P.border_position[num_env] = L;
-  } else {
-    P.border_position[0] = 0;
-    if (P.border_position[num_env] < L) {
-      for (int k = 0; k < 2; ++k)
-        for (int i = 0; i < 34; ++i) ps[k]->index[num_env][i] = ps[k]->index[num_env - 1][i];   // Envelope.restore
-      ++num_env;
+  const bool var_borders = P.var_borders != 0;
+  const bool restore = var_borders && P.border_position[num_env] < L;
+  __syncwarp();   // (every lane has read data_available / border_position[num_env] before lane 0 moves them)
+  if (restore)
+    for (int k = 0; k < 2; ++k)
+      for (int i = lane; i < 34; i += 32) ps[k]->index[num_env][i] = ps[k]->index[num_env - 1][i];   // Envelope.restore
+  if (lane == 0) {
+    P.data_available = 0;
+    if (!var_borders) {
+      P.border_position[0] = 0;
+#pragma unroll 1
+      for (int env = 1; env < num_env; env++) P.border_position[env] = (uint8_t)((env * L) / num_env);
       P.border_position[num_env] = L;
-    }
-    int bpl = P.border_position[0];
-    for (int env = 1; env < num_env; env++) {
-      const int bp = P.border_position[env];
-      const int mx = L - (num_env - env);
-      bpl = min(max(bp, bpl + 1), mx);
-      if (bpl != bp) P.border_position[env] = (uint8_t)bpl;
+    } else {
+      P.border_position[0] = 0;
+      int ne = num_env;
+      if (restore) { ++ne; P.border_position[ne] = L; }
+      int bpl = P.border_position[0];
+#pragma unroll 1
+      for (int env = 1; env < ne; env++) {
+        const int bp = P.border_position[env];
+        const int mx = L - (ne - env);
+        bpl = min(max(bp, bpl + 1), mx);
+        if (bpl != bp) P.border_position[env] = (uint8_t)bpl;
+      }
     }
   }
-  P.num_env = (uint8_t)num_env;
-  o.use_ps = 1;
-  o.num_env = (uint8_t)num_env;
-  for (int i = 0; i < 6; ++i) o.border[i] = P.border_position[i];
-  o.iid_mode = P.iid.mode < 0 ? 0 : P.iid.mode;
-  o.icc_mode = P.icc.mode < 0 ? 1 : P.icc.mode;
-  for (int env = 0; env < 5; ++env)
-    for (int i = 0; i < 20; ++i) { o.iid[env][i] = P.iid.index[env][i]; o.icc[env][i] = P.icc.index[env][i]; }
+  if (restore) ++num_env;
   // Extension.nr_par (ps/Extension.java:81-86, ExtData.java:49-54).  255: the extension is on while IID is off -- JAAD
   // dereferences the null PDMode (NullPointerException); the caller fails the frame
-  o.nr_ipdopd_par = !ext_live ? 0 : (P.ipd.mode < 0 ? 255 : (uint8_t)max(ps_pd_nr_par(P.ipd.mode), 11));
-  o.enable_ipdopd = P.ext_data_enabled;
-  for (int env = 0; env < 5; ++env)
-    for (int i = 0; i < 17; ++i) o.ipd[env][i] = P.ipd.index[env][i];
+  const int nr_ipdopd = !ext_live ? 0 : (P.ipd.mode < 0 ? 255 : max(ps_pd_nr_par(P.ipd.mode), 11));
+  __syncwarp();
+  if (lane == 0) {
+    P.num_env = (uint8_t)num_env;
+    o.use_ps = 1;
+    o.num_env = (uint8_t)num_env;
+    o.iid_mode = P.iid.mode < 0 ? 0 : P.iid.mode;
+    o.icc_mode = P.icc.mode < 0 ? 1 : P.icc.mode;
+    o.nr_ipdopd_par = (uint8_t)nr_ipdopd;
+    o.enable_ipdopd = P.ext_data_enabled;
+  }
+  if (lane < 6) o.border[lane] = P.border_position[lane];
+  for (int idx = lane; idx < 5 * 20; idx += 32) {
+    const int env = idx / 20, i = idx - env * 20;
+    o.iid[env][i] = P.iid.index[env][i];
+    o.icc[env][i] = P.icc.index[env][i];
+  }
+  for (int idx = lane; idx < 5 * 17; idx += 32) {
+    const int env = idx / 17, i = idx - env * 17;
+    o.ipd[env][i] = P.ipd.index[env][i];
+  }
+  return nr_ipdopd;
 }
 
 // SBR.readExtendedData (:229-242).  Extension payloads (parametric stereo = id 2) are skipped in this build: the
@@ -903,87 +1002,106 @@ __device__ inline int sbr_extended_data(SbrBits& ld, const SbrTablesDev& T, PsPa
 }
 
 // SBR1.sbr_data (:34-60) / SBR2.sbr_data (:35-135).  `valid` as SBR.decode sets it.
+// The three element layouts (single channel, coupled pair, independent pair) are step lists over ONE expansion of each
+// syntax function: with every call written out, the kernel carried five copies of the envelope / noise readers and three
+// of the grid (230 KB of SASS, two of each on the path of a stereo frame), and it is instruction-fetch bound.
+enum { K3_END = 0, K3_GRID, K3_DTDF, K3_INVF, K3_COUPLE, K3_ENV, K3_NOISE, K3_ZERO, K3_HARM, K3_DEQ, K3_EXT, K3_SAVE };
+#define K3S(op, ch, flag) (uint8_t)((op) | ((ch) << 4) | ((flag) << 5))
+__constant__ uint8_t c_k3_steps[3][20] = {
+    // SBR1.sbr_data: dequantChannel comes before the harmonics; the extension may carry parametric stereo (flag)
+    {K3S(K3_GRID, 0, 0), K3S(K3_DTDF, 0, 0), K3S(K3_INVF, 0, 0), K3S(K3_ENV, 0, 0), K3S(K3_NOISE, 0, 0), K3S(K3_DEQ, 0, 0),
+     K3S(K3_ZERO, 0, 0), K3S(K3_HARM, 0, 0), K3S(K3_EXT, 0, 1), K3_END},
+    // SBR2.sbr_data, bs_coupling: the second channel's dt/df flags are read with its OLD L_E / L_Q (the grid is copied
+    // over only afterwards, Channel.couple), and its envelopes / noise floors use the balance tables (flag)
+    {K3S(K3_GRID, 0, 0), K3S(K3_DTDF, 0, 0), K3S(K3_DTDF, 1, 0), K3S(K3_INVF, 0, 0), K3S(K3_COUPLE, 0, 0), K3S(K3_ENV, 0, 0),
+     K3S(K3_NOISE, 0, 0), K3S(K3_ENV, 1, 1), K3S(K3_NOISE, 1, 1), K3S(K3_ZERO, 0, 0), K3S(K3_ZERO, 1, 0), K3S(K3_HARM, 0, 0),
+     K3S(K3_HARM, 1, 0), K3S(K3_DEQ, 0, 0), K3S(K3_EXT, 0, 0), K3_END},
+    // SBR2.sbr_data, independent channels: a second grid that fails puts the first channel's grid back (flag)
+    {K3S(K3_SAVE, 0, 0), K3S(K3_GRID, 0, 0), K3S(K3_GRID, 1, 1), K3S(K3_DTDF, 0, 0), K3S(K3_DTDF, 1, 0), K3S(K3_INVF, 0, 0),
+     K3S(K3_INVF, 1, 0), K3S(K3_ENV, 0, 0), K3S(K3_ENV, 1, 0), K3S(K3_NOISE, 0, 0), K3S(K3_NOISE, 1, 0), K3S(K3_ZERO, 0, 0),
+     K3S(K3_ZERO, 1, 0), K3S(K3_HARM, 0, 0), K3S(K3_HARM, 1, 0), K3S(K3_DEQ, 0, 0), K3S(K3_EXT, 0, 0), K3_END}};
+#undef K3S
+
 __device__ inline int sbr_data(SbrBits& ld, const SbrCtx& C, bool stereo, bool with_ps, int& result) {
   SbrElemDev& S = *C.S;
-  SbrChanParse& c0 = S.ch[0];
-  SbrChanParse& c1 = S.ch[1];
   int v, eos;
   result = 0;
   SBR_RD(v, 1);
   if (v) { SBR_RD(v, 4); if (stereo) SBR_RD(v, 4); }
-  if (!stereo) {
-    int r = sbr_grid(ld, c0, eos);
-    if (r < 0) return -r;
-    if (r > 0) { result = r; return 0; }
-    SBR_TRY(sbr_dtdf(ld, c0));
-    SBR_TRY(sbr_invf_mode(ld, c0, S.N_Q));
-    SBR_TRY(sbr_envelope(ld, C, c0, false));
-    SBR_TRY(sbr_noise(ld, C, c0, false));
-    // NoiseEnvelope.dequantChannel happens here in the reference; the float tables are evaluated by all lanes after the
-    // syntax (same inputs: E, Q, amp_res, f, n) -- also when the rest of the payload fails
-    S.dequant = 1;
-    for (int i = 0; i < 64; ++i) c0.bs_add_harmonic[i] = 0;
-    SBR_TRY(sbr_harmonics(ld, c0, S.N_high));
-    SBR_TRY(sbr_extended_data(ld, *C.T, with_ps ? &S.ps : nullptr));
-    return 0;
+  int layout = 0;
+  if (stereo) {
+    SBR_RD(v, 1);
+    S.bs_coupling = (uint8_t)v;
+    layout = v ? 1 : 2;
   }
-  SBR_RD(v, 1);
-  S.bs_coupling = (uint8_t)v;
-  if (S.bs_coupling) {
-    int r = sbr_grid(ld, c0, eos);
-    if (r < 0) return -r;
-    if (r > 0) { result = r; return 0; }
-    SBR_TRY(sbr_dtdf(ld, c0));
-    SBR_TRY(sbr_dtdf(ld, c1));          // with ch1's OLD L_E / L_Q: the grid is copied over only below
-    SBR_TRY(sbr_invf_mode(ld, c0, S.N_Q));
-    // Channel.couple (:103-122)
-    c1.frame_class = c0.frame_class;
-    c1.L_E = c0.L_E;
-    c1.L_Q = c0.L_Q;
-    c1.bs_pointer = c0.bs_pointer;
-    for (int i = 0; i <= c0.L_E; i++) { c1.t_E[i] = c0.t_E[i]; c1.f[i] = c0.f[i]; }
-    for (int i = 0; i <= c0.L_Q; i++) c1.t_Q[i] = c0.t_Q[i];
-    for (int i = 0; i < S.N_Q; i++) c1.bs_invf_mode[i] = c0.bs_invf_mode[i];
-    SBR_TRY(sbr_envelope(ld, C, c0, false));
-    SBR_TRY(sbr_noise(ld, C, c0, false));
-    SBR_TRY(sbr_envelope(ld, C, c1, true));
-    SBR_TRY(sbr_noise(ld, C, c1, true));
-    for (int i = 0; i < 64; ++i) { c0.bs_add_harmonic[i] = 0; c1.bs_add_harmonic[i] = 0; }
-    SBR_TRY(sbr_harmonics(ld, c0, S.N_high));
-    SBR_TRY(sbr_harmonics(ld, c1, S.N_high));
-  } else {
-    uint8_t saved_t_E[6] = {0, 0, 0, 0, 0, 0}, saved_t_Q[3] = {0, 0, 0};
-    const int saved_L_E = c0.L_E, saved_L_Q = c0.L_Q, saved_class = c0.frame_class;
-    for (int i = 0; i < saved_L_E && i < 6; i++) saved_t_E[i] = c0.t_E[i];
-    for (int i = 0; i < saved_L_Q && i < 3; i++) saved_t_Q[i] = c0.t_Q[i];
-    int r = sbr_grid(ld, c0, eos);
-    if (r < 0) return -r;
-    if (r > 0) { result = r; return 0; }
-    r = sbr_grid(ld, c1, eos);
-    if (r < 0) return -r;
-    if (r > 0) {
-      c0.frame_class = (uint8_t)saved_class;
-      c0.L_E = (uint8_t)saved_L_E;
-      c0.L_Q = (uint8_t)saved_L_Q;
-      for (int i = 0; i < 6; i++) c0.t_E[i] = saved_t_E[i];
-      for (int i = 0; i < 3; i++) c0.t_Q[i] = saved_t_Q[i];
-      result = r;
-      return 0;
+  uint8_t saved_t_E[6] = {0, 0, 0, 0, 0, 0}, saved_t_Q[3] = {0, 0, 0};
+  int saved_L_E = 0, saved_L_Q = 0, saved_class = 0;
+  const uint8_t* steps = c_k3_steps[layout];
+#pragma unroll 1
+  for (int pc = 0;; ++pc) {
+    const int step = steps[pc];
+    const int op = step & 15, flag = step >> 5;
+    SbrChanParse& c = S.ch[(step >> 4) & 1];
+    if (op == K3_END) break;
+    switch (op) {
+      case K3_SAVE: {
+        saved_L_E = c.L_E; saved_L_Q = c.L_Q; saved_class = c.frame_class;
+        for (int i = 0; i < saved_L_E && i < 6; i++) saved_t_E[i] = c.t_E[i];
+        for (int i = 0; i < saved_L_Q && i < 3; i++) saved_t_Q[i] = c.t_Q[i];
+        break;
+      }
+      case K3_GRID: {
+        const int r = sbr_grid(ld, c, eos);
+        if (r < 0) return -r;
+        if (r > 0) {
+          if (flag) {
+            SbrChanParse& c0 = S.ch[0];
+            c0.frame_class = (uint8_t)saved_class;
+            c0.L_E = (uint8_t)saved_L_E;
+            c0.L_Q = (uint8_t)saved_L_Q;
+            for (int i = 0; i < 6; i++) c0.t_E[i] = saved_t_E[i];
+            for (int i = 0; i < 3; i++) c0.t_Q[i] = saved_t_Q[i];
+          }
+          result = r;
+          return 0;
+        }
+        break;
+      }
+      case K3_DTDF: SBR_TRY(sbr_dtdf(ld, c)); break;
+      case K3_INVF: SBR_TRY(sbr_invf_mode(ld, c, S.N_Q)); break;
+      case K3_COUPLE: {
+        // Channel.couple (:103-122)
+        const SbrChanParse& c0 = S.ch[0];
+        SbrChanParse& c1 = S.ch[1];
+        c1.frame_class = c0.frame_class;
+        c1.L_E = c0.L_E;
+        c1.L_Q = c0.L_Q;
+        c1.bs_pointer = c0.bs_pointer;
+        for (int i = 0; i <= c0.L_E; i++) { c1.t_E[i] = c0.t_E[i]; c1.f[i] = c0.f[i]; }
+        for (int i = 0; i <= c0.L_Q; i++) c1.t_Q[i] = c0.t_Q[i];
+        for (int i = 0; i < S.N_Q; i++) c1.bs_invf_mode[i] = c0.bs_invf_mode[i];
+        break;
+      }
+      case K3_ENV: SBR_TRY(sbr_envelope(ld, C, c, flag != 0)); break;
+      case K3_NOISE: SBR_TRY(sbr_noise(ld, C, c, flag != 0)); break;
+      case K3_ZERO: {
+        uint32_t* h = reinterpret_cast<uint32_t*>(c.bs_add_harmonic);
+#pragma unroll 1
+        for (int i = 0; i < 16; ++i) h[i] = 0u;
+        break;
+      }
+      case K3_HARM: SBR_TRY(sbr_harmonics(ld, c, S.N_high)); break;
+      case K3_DEQ:
+        // NoiseEnvelope.dequantChannel (x 2, or unmap: SBR2.java:128-133) happens here in the reference; the float tables
+        // are evaluated by all lanes after the syntax (same inputs: E, Q, amp_res, f, n) -- also when the rest of the
+        // payload fails
+        S.dequant = 1;
+        break;
+      default:   // K3_EXT
+        SBR_TRY(sbr_extended_data(ld, *C.T, (flag && with_ps) ? &S.ps : nullptr));
+        break;
     }
-    SBR_TRY(sbr_dtdf(ld, c0));
-    SBR_TRY(sbr_dtdf(ld, c1));
-    SBR_TRY(sbr_invf_mode(ld, c0, S.N_Q));
-    SBR_TRY(sbr_invf_mode(ld, c1, S.N_Q));
-    SBR_TRY(sbr_envelope(ld, C, c0, false));
-    SBR_TRY(sbr_envelope(ld, C, c1, false));
-    SBR_TRY(sbr_noise(ld, C, c0, false));
-    SBR_TRY(sbr_noise(ld, C, c1, false));
-    for (int i = 0; i < 64; ++i) { c0.bs_add_harmonic[i] = 0; c1.bs_add_harmonic[i] = 0; }
-    SBR_TRY(sbr_harmonics(ld, c0, S.N_high));
-    SBR_TRY(sbr_harmonics(ld, c1, S.N_high));
   }
-  S.dequant = 1;   // dequantChannel x 2 or unmap (SBR2.java:128-133)
-  SBR_TRY(sbr_extended_data(ld, *C.T, nullptr));
   return 0;
 }
 
@@ -1065,6 +1183,10 @@ struct SbrConstTables {
 };
 
 constexpr int kK3WarpsPerBlock = 4;
+// a fill element carries at most 269 payload bytes (count 15 + 255 - 1): 68 words, one more for a start inside a word and
+// one for the word the funnel shift reads past the end
+constexpr int kK3StageWords = 72;
+constexpr size_t k3_smem_bytes() { return (sizeof(SbrElemDev) + 4 * kK3StageWords) * kK3WarpsPerBlock; }
 
 __global__ void __launch_bounds__(32 * kK3WarpsPerBlock)
 k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ frames, FrameSide* __restrict__ fside,
@@ -1077,11 +1199,12 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
   if (r >= n_runs) return;
   const SbrRunDev run = runs[r];
   SbrElemDev* S = reinterpret_cast<SbrElemDev*>(k3_smem) + warp;
+  uint32_t* stage = reinterpret_cast<uint32_t*>(k3_smem + sizeof(SbrElemDev) * kK3WarpsPerBlock) + warp * kK3StageWords;
   SbrElemDev* G = elems + (size_t)run.stream_slot * 2 + run.element;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(G);
     uint32_t* dst = reinterpret_cast<uint32_t*>(S);
-    for (int i = lane; i < (int)(sizeof(SbrElemDev) / 4); i += 32) dst[i] = src[i];
+    for (int i = lane; i < (int)(sizeof(SbrElemDev) / 4); i += 32) dst[i] = k3_ld_stream_rw(src + i);
   }
   __syncwarp();
   SbrCtx C;
@@ -1098,9 +1221,18 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
     int mode = 0;          // what K4 does with the frame (SbrFrameDev.mode)
     int frame_status = 0;
     int dequant = 0;       // NoiseEnvelope.dequantChannel / unmap ran for this frame (lane 0 decides, all lanes do it)
+    // ---- the frame's payload for this element, staged by the warp (SbrBits); a frame without one stages nothing
+    const FrameSide fs = fside[f];
+    const uint32_t pay_bits = (run.element < 2) ? fs.sbr_bits[run.element] : 0u;
+    const uint32_t pay_off = (run.element < 2) ? fs.sbr_bit_off[run.element] : 0u;
+    if (pay_bits) {
+      const uint64_t addr = reinterpret_cast<uint64_t>(blob) + frames[f].blob_off;
+      const uint32_t* gw = reinterpret_cast<const uint32_t*>(addr - (addr & 3u)) + (pay_off >> 5);
+      const uint32_t nw = min((((pay_off & 31u) + pay_bits + 31u) >> 5) + 1u, (uint32_t)kK3StageWords);
+      for (uint32_t i = lane; i < nw; i += 32) stage[i] = __byte_perm(k3_ld_stream(gw + i), 0, 0x0123);
+    }
+    __syncwarp();
     if (lane == 0) {
-      const FrameDev fr = frames[f];
-      FrameSide fs = fside[f];
       frame_status = fs.status;
       S->dequant = 0;
       // JAAD's element objects (and their SBR) are per instance tag: a frame that carries another tag does not touch
@@ -1115,15 +1247,15 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
       // ChannelElement.decode invalidates the element's SBR at the start of every frame (ChannelElement.java:58-61);
       // the element was reached iff K1 counted it
       if (!foreign && S->opened && run.element < fs.n_elements) S->valid = 0;
-      const uint32_t nbits = foreign ? 0u : fs.sbr_bits[run.element];
+      const uint32_t nbits = foreign ? 0u : pay_bits;
       if (nbits) {
         // the FIL payload was seen by K1 (also in frames that failed later on): decodeSBR runs
         S->opened = 1;
-        const uint64_t addr = reinterpret_cast<uint64_t>(blob) + fr.blob_off;
         SbrBits ld;
-        ld.words = reinterpret_cast<const uint32_t*>(addr - (addr & 3u));
-        ld.pos = fs.sbr_bit_off[run.element];
-        ld.end = ld.pos + nbits;
+        ld.words = stage;
+        ld.pos = pay_off & 31u;
+        // (a span beyond the staging buffer cannot come from a fill element; it would end as an early end of stream)
+        ld.end = min(ld.pos + nbits, 32u * (uint32_t)(kK3StageWords - 1));
         int ext = 0;
         ld.get(4, ext);
         const int st = sbr_decode(ld, C, stereo, run.ps != 0, ext == 14);
@@ -1133,7 +1265,6 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
           // SyntacticElements.java:169-203), and K1, which stops at its first error, only records a payload it got past
           // -- so whatever K1 reported happened later in the frame and JAAD never gets there.
           frame_status = st;
-          fs.status = st;
           fside[f].status = st;
         }
       }
@@ -1155,26 +1286,32 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
           }
         }
       }
+      dequant = S->dequant;
     }
-    int use_ps = 0;
-    if (lane == 0 && run.ps) {
-      // SBR1.process: parametric stereo runs iff this frame brought ps_data (SBR1.isPSUsed); PSImpl.ps_data_decode
-      PsFrameDev* po = ps_out + run.ps_base + it;
-      po->use_ps = 0;
-      if (mode != 0 && S->ps.opened && S->ps.data_available) ps_data_decode(S->ps, *po);
-      if (po->use_ps && po->nr_ipdopd_par == 255) {
-        // JAAD dies of a NullPointerException inside ps_mix_phase (see ps_data_decode): the frame fails
-        po->use_ps = 0;
-        if (frame_status == 0) { frame_status = JAADB_ST_ARRAY_BOUNDS; fside[f].status = JAADB_ST_ARRAY_BOUNDS; }
-        mode = 0;
-      }
-      use_ps = po->use_ps;
-    }
-    if (lane == 0) dequant = S->dequant;
     dequant = __shfl_sync(0xFFFFFFFFu, dequant, 0);
     mode = __shfl_sync(0xFFFFFFFFu, mode, 0);
     frame_status = __shfl_sync(0xFFFFFFFFu, frame_status, 0);
-    use_ps = __shfl_sync(0xFFFFFFFFu, use_ps, 0);
+    __syncwarp();
+    int use_ps = 0;
+    if (run.ps) {
+      // SBR1.process: parametric stereo runs iff this frame brought ps_data (SBR1.isPSUsed); PSImpl.ps_data_decode
+      PsFrameDev* po = ps_out + run.ps_base + it;
+      if (mode != 0 && S->ps.opened && S->ps.data_available) {
+        const int nr_par = ps_data_decode(S->ps, *po, lane);
+        use_ps = 1;
+        if (nr_par == 255) {
+          // JAAD dies of a NullPointerException inside ps_mix_phase (see ps_data_decode): the frame fails
+          use_ps = 0;
+          __syncwarp();
+          if (lane == 0) {
+            po->use_ps = 0;
+            if (frame_status == 0) fside[f].status = JAADB_ST_ARRAY_BOUNDS;
+          }
+          if (frame_status == 0) frame_status = JAADB_ST_ARRAY_BOUNDS;
+          mode = 0;
+        }
+      } else if (lane == 0) po->use_ps = 0;
+    }
     const bool processed = frame_status == 0 && mode != 0;
     __syncwarp();
     // ---- frame records (all lanes)

@@ -294,6 +294,9 @@ k4a_analysis_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const Ru
 #define K4B_WARPS 4
 #endif
 constexpr int kK4bWarps = K4B_WARPS;
+#ifndef K4B_MIN_BLOCKS
+#define K4B_MIN_BLOCKS 5
+#endif
 constexpr int kK4bMaxNL = 32;
 constexpr int kK4bPwCols = 50;   // >= SBR.MAX_M, even
 struct K4bGain {
@@ -303,21 +306,27 @@ struct K4bGain {
   uint8_t nb[64], lb[64];        // noise-floor band, limiter band
   uint8_t sflag[kSbrMaxLE][64];  // S_index_mapped != 0
 };
+// Of a frame's record only the part behind the dequantised envelopes is staged in shared memory; E_orig / Q_div / Q_div2
+// (a handful of reads per band in calculate_gain) come straight from the record in global memory, and Channel.E_curr lives
+// in the channel's state (SbrChanDev::E_curr; the warp that owns the run is its only reader and writer).
+constexpr int kK4bRecHead = (int)offsetof(SbrFrameDev, f_table_res);   // bytes of the record that stay in global memory
+constexpr int kK4bRecTail = (int)sizeof(SbrFrameDev) - kK4bRecHead;
+static_assert(kK4bRecHead % 16 == 0 && kK4bRecTail % 16 == 0 && kK4bRecTail <= 32 * 16, "one uint4 per lane moves the staged part");
 struct __align__(16) K4bSmem {
-  SbrFrameDev fp;
-  float E_curr[kSbrMaxLE][64];
   union {
     K4bGain g;                   // calculate_gain's working set
     float pw[38][kK4bPwCols];    // before that: |X|^2 of the generated band samples, [slot][m] (estimate_current_envelope)
   };
+  uint8_t rec_tail[kK4bRecTail]; // SbrFrameDev from f_table_res on; `fp` below points kK4bRecHead bytes in front of it
   float eband[64];               // envelope energy per frequency band (bs_interpol_freq == 0)
   float bw[8];
   float ringG[5][64], ringQ[5][64];   // G_temp_prev / Q_temp_prev: the smoothing ring, by ring position
   uint8_t seq_i[192], seq_l[192];     // hf_assembly's slot order: for every envelope l, slots t_E[l] .. t_E[l + 1] - 1
 };
+static_assert(offsetof(K4bSmem, rec_tail) >= (size_t)kK4bRecHead && offsetof(K4bSmem, rec_tail) % 16 == 0, "fp stays inside the warp's block");
 constexpr size_t k4b_smem_bytes() { return sizeof(K4bSmem) * kK4bWarps; }
 
-__global__ void __launch_bounds__(32 * kK4bWarps)
+__global__ void __launch_bounds__(32 * kK4bWarps, K4B_MIN_BLOCKS)
 k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrameDev* __restrict__ run_frames,
               const SbrFrameDev* __restrict__ sframes, const float* __restrict__ core, SbrChanDev* __restrict__ chans,
               float* xg, SbrTablesDev T, K4Tile tile) {
@@ -334,7 +343,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
 
   // ---- recursive state in: the smoothing ring, chirp factors (lanes < 8), phases
   for (int i = lane; i < 5 * 64; i += 32) { (&W.ringG[0][0])[i] = (&st->G_temp_prev[0][0])[i]; (&W.ringQ[0][0])[i] = (&st->Q_temp_prev[0][0])[i]; }
-  for (int i = lane; i < kSbrMaxLE * 64; i += 32) (&W.E_curr[0][0])[i] = (&st->E_curr[0][0])[i];   // (see SbrChanDev::E_curr)
+  float* const E_curr = &st->E_curr[0][0];   // [l * 64 + m], (see SbrChanDev::E_curr)
   int ring_index = st->GQ_ringbuf_index;
   int index_noise_prev = st->index_noise_prev, psi_is_prev = st->psi_is_prev;
   float bw_prev = 0.f;
@@ -343,25 +352,20 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
 
   uint32_t n_done = 0;   // processed frames of the tile so far
   int64_t last_it = -1;
-  const SbrFrameDev* fp = &W.fp;
+  // fp-> reaches the staged fields; the three float tables in front of them must be read through `gfp`
+  const SbrFrameDev* fp = reinterpret_cast<const SbrFrameDev*>(W.rec_tail - kK4bRecHead);
   // the frame records are fetched one frame ahead
-  constexpr int kRecVec = (int)(sizeof(SbrFrameDev) / 16);
-  uint4 rec[4];
+  constexpr int kRecVec = kK4bRecTail / 16;
+  uint4 rec = make_uint4(0u, 0u, 0u, 0u);
   auto fetch_record = [&](uint32_t it2) {
-    const uint4* src = reinterpret_cast<const uint4*>(k4_frame(sframes, run, it2));
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (lane + 32 * u < kRecVec) rec[u] = __ldg(src + lane + 32 * u);
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(k4_frame(sframes, run, it2)) + kK4bRecHead);
+    if (lane < kRecVec) rec = __ldg(src + lane);
   };
   fetch_record(tile.lo);
   for (uint32_t it = tile.lo; it < hi; ++it) {
     __syncwarp();
-    {
-      uint4* dst = reinterpret_cast<uint4*>(&W.fp);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (lane + 32 * u < kRecVec) dst[lane + 32 * u] = rec[u];
-    }
+    if (lane < kRecVec) reinterpret_cast<uint4*>(W.rec_tail)[lane] = rec;
+    const SbrFrameDev* gfp = k4_frame(sframes, run, it);
     if (it + 1 < hi) fetch_record(it + 1);
     __syncwarp();
     const int mode = fp->mode;
@@ -540,7 +544,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
           for (int m = lane; m < M; m += 32) {
             float nrg = 0;
             for (int sl = l_i; sl < u_i; ++sl) nrg += W.pw[sl][m];
-            W.E_curr[l][m] = nrg / div;
+            E_curr[(l) * 64 + (m)] = nrg / div;
           }
         } else {
           // one sum per frequency band of the envelope's resolution, taken by the lane of the band's first m
@@ -573,7 +577,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int m = lane + 32 * q;
-            if (m < M) W.E_curr[l][m] = W.eband[pb[q]];
+            if (m < M) E_curr[(l) * 64 + (m)] = W.eband[pb[q]];
           }
           __syncwarp();
         }
@@ -605,7 +609,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
                 nrg += (v.x * v.x) + (v.y * v.y);
               }
           }
-          W.E_curr[l][m] = nrg / div;
+          E_curr[(l) * 64 + (m)] = nrg / div;
         }
       }
     }
@@ -680,8 +684,8 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
         const int l = task / N_L, kb = task - l * N_L, res = fp->f[l];
         float acc1 = 0, acc2 = 0;
         for (int m = fp->f_table_lim[kb]; m < fp->f_table_lim[kb + 1]; m++) {
-          acc1 += fp->E_orig[l][W.g.rb[res][m]];
-          acc2 += W.E_curr[l][m];
+          acc1 += __ldg(&gfp->E_orig[l][W.g.rb[res][m]]);
+          acc2 += E_curr[(l) * 64 + (m)];
         }
         float G_max = ((EPS + acc1) / (EPS + acc2)) * limg;
         G_max = fminf(G_max, 1e10f);
@@ -701,12 +705,12 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
           if (((l >= l_A) || (fp->bs_add_harmonic_prev[hb] != 0 && flag_prev)) && centre) S_index_mapped = fp->bs_add_harmonic[hb];
           const int tb = t_noise_band(l);
           const float delta = (l == l_A || l == fp->prevEnvIsShort) ? 0.f : 1.f;
-          const float Q_div = fp->Q_div[tb][W.g.nb[m]];
-          const float Q_div2 = fp->Q_div2[tb][W.g.nb[m]];
-          const float E_o = fp->E_orig[l][rb];
+          const float Q_div = __ldg(&gfp->Q_div[tb][W.g.nb[m]]);
+          const float Q_div2 = __ldg(&gfp->Q_div2[tb][W.g.nb[m]]);
+          const float E_o = __ldg(&gfp->E_orig[l][rb]);
           const float Q_M = E_o * Q_div2;
           const float S_M = (S_index_mapped == 0) ? 0.f : E_o * Q_div;
-          float G = E_o / (1.0f + W.E_curr[l][m]);
+          float G = E_o / (1.0f + E_curr[(l) * 64 + (m)]);
           if ((S_mapped == 0) && (delta == 1)) G *= Q_div;
           else if (S_mapped == 1) G *= Q_div2;
           const float G_max = W.g.gmax[l][W.g.lb[m]];
@@ -726,7 +730,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
         for (int m = fp->f_table_lim[kb]; m < fp->f_table_lim[kb + 1]; m++) {
           const bool sf = W.g.sflag[l][m] != 0;
           if (sf) den += W.g.S[l][m];
-          den += W.E_curr[l][m] * W.g.G[l][m];
+          den += E_curr[(l) * 64 + (m)] * W.g.G[l][m];
           if (!sf && (l != l_A)) den += W.g.Q[l][m];
         }
         float G_boost = (W.g.acc1[l][kb] + EPS) / (den + EPS);
@@ -758,8 +762,8 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
         const int ml1 = fp->f_table_lim[k], ml2 = fp->f_table_lim[k + 1];
         for (int m = ml1; m < ml2; m++) {
           if ((m + kx) == fp->f_table_res[res][current_res_band + 1]) current_res_band++;
-          acc1 += fp->E_orig[l][current_res_band];
-          acc2 += W.E_curr[l][m];
+          acc1 += __ldg(&gfp->E_orig[l][current_res_band]);
+          acc2 += E_curr[(l) * 64 + (m)];
         }
         float G_max = ((EPS + acc1) / (EPS + acc2)) * limg;
         G_max = fminf(G_max, 1e10f);
@@ -775,20 +779,20 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
             if ((m + kx) == (fp->f_table_res[SBR_HI_RES][current_hi_res_band + 1] + fp->f_table_res[SBR_HI_RES][current_hi_res_band]) >> 1)
               S_index_mapped = fp->bs_add_harmonic[current_hi_res_band];
           }
-          const float Q_div = fp->Q_div[current_t_noise_band][current_f_noise_band];
-          const float Q_div2 = fp->Q_div2[current_t_noise_band][current_f_noise_band];
-          const float E_o = fp->E_orig[l][current_res_band2];
+          const float Q_div = __ldg(&gfp->Q_div[current_t_noise_band][current_f_noise_band]);
+          const float Q_div2 = __ldg(&gfp->Q_div2[current_t_noise_band][current_f_noise_band]);
+          const float E_o = __ldg(&gfp->E_orig[l][current_res_band2]);
           const float Q_M = E_o * Q_div2;
           float S_M;
           if (S_index_mapped == 0) S_M = 0;
           else { S_M = E_o * Q_div; den += S_M; }
-          float G = E_o / (1.0f + W.E_curr[l][m]);
+          float G = E_o / (1.0f + E_curr[(l) * 64 + (m)]);
           if ((S_mapped == 0) && (delta == 1)) G *= Q_div;
           else if (S_mapped == 1) G *= Q_div2;
           float Q_M_lim, G_lim;
           if (G_max > G) { Q_M_lim = Q_M; G_lim = G; }
           else { Q_M_lim = Q_M * G_max / G; G_lim = G_max; }
-          den += W.E_curr[l][m] * G_lim;
+          den += E_curr[(l) * 64 + (m)] * G_lim;
           if ((S_index_mapped == 0) && (l != l_A)) den += Q_M_lim;
           W.g.G[l][m] = G_lim;
           W.g.Q[l][m] = Q_M_lim;
@@ -912,7 +916,6 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
 
   // ---- recursive state out
   for (int i = lane; i < 5 * 64; i += 32) { (&st->G_temp_prev[0][0])[i] = (&W.ringG[0][0])[i]; (&st->Q_temp_prev[0][0])[i] = (&W.ringQ[0][0])[i]; }
-  for (int i = lane; i < kSbrMaxLE * 64; i += 32) (&st->E_curr[0][0])[i] = (&W.E_curr[0][0])[i];
   if (lane < 8) { st->bwArray_prev[lane] = bw_prev; st->bs_invf_mode_prev[lane] = (uint8_t)invf_prev; }
   if (lane == 0) { st->GQ_ringbuf_index = ring_index; st->index_noise_prev = index_noise_prev; st->psi_is_prev = psi_is_prev; }
   if (last_it >= 0) {
