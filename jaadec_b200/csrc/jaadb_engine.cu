@@ -228,7 +228,7 @@ struct jaadb_engine {
   static constexpr int kK4MaxParts = 8;
   cudaStream_t k4_stream[kK4MaxParts - 1] = {};
   cudaEvent_t k4_fork = nullptr, k4_join[kK4MaxParts - 1] = {};
-  int k4_parts = 0;        // parts the K4 pipeline is cut into (launch_decode); 0: one part per full wave of K4b warps
+  int k4_parts = 2;        // parts the K4 pipeline is cut into (launch_decode); 0: one part per full wave of K4b warps
   int sm_count = 148;
 
   // workspace of the one-call path (jaadb_decode): grow-only, so a steady stream of calls allocates nothing.
@@ -534,7 +534,7 @@ int init_sbr(jaadb_engine* e) {
 #endif
   cudaFuncSetAttribute(k4a_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4a_smem_bytes());
   cudaFuncSetAttribute(k4b_hf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4b_smem_bytes());
-  cudaFuncSetAttribute(k4b_hf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // five CTAs of 44 KB
+  cudaFuncSetAttribute(k4b_hf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // two CTAs of ten warps, 110 KB each
 #define K4C_ATTR(FMT)                                                                                                        \
   cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes()); \
   cudaFuncSetAttribute(k4c_synthesis_kernel<FMT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4c_smem_bytes()); \
@@ -841,7 +841,7 @@ struct DecodeBufs {
 };
 
 #ifndef K4_TILE_BYTES
-#define K4_TILE_BYTES (8192ull << 20)   // measured: 1.5 GB -> 8 GB takes the SBR stages of configs 3 / 4 from 75 / 199 ms to 72 / 176 ms
+#define K4_TILE_BYTES (16384ull << 20)   // measured: 1.5 GB -> 8 GB took the SBR stages of configs 3 / 4 from 75 / 199 ms to 72 / 176 ms, 8 -> 16 GB 65.4 / 154.0 -> 64.9 / 152.2 ms
 #endif
 constexpr uint64_t kK4TileBytes = K4_TILE_BYTES;   // upper bound of the K4 tile workspace (Xsbr matrices of one tile)
 
@@ -928,9 +928,11 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
     // half's analysis / synthesis, and the part-filled last wave of a K4b launch is filled from the other stream.
     struct Part { uint32_t p0, pn, q0, qn; cudaStream_t st; };   // plain runs [p0, p0 + pn), SBR+PS runs [q0, q0 + qn)
     Part parts[jaadb_engine::kK4MaxParts];
-    // Part size: K4b's waves are whole (every warp walks the same number of frames), so a part is cut to fill the SMs'
-    // resident K4b warps once -- 8192 channel runs are 2.77 waves of 2960: three parts of 0.92 waves instead of two parts
-    // of two waves each.
+    // (0 = one part per full wave of K4b warps: 8192 channel runs are 2.77 waves of 2960, i.e. three parts.  Measured after
+    // K4b went to five CTAs per SM: 66.9 / 156.3 ms for configs 3 / 4 against 65.8 / 154.9 ms with two parts, so two stays.
+    // Also measured and dropped: sending K3 and K2 down in the same parts, so that part p + 1 is parsed underneath part p's
+    // QMF pipeline -- K3 starves next to the K4 kernels and the last part's pipeline waits for it: 105.7 / 195.1 ms with two
+    // parts, worse with more.)
     int want = e->k4_parts;
     if (want <= 0) {
       const uint32_t wave = (uint32_t)e->sm_count * K4B_MIN_BLOCKS * kK4bWarps;

@@ -291,11 +291,27 @@ k4a_analysis_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const Ru
 
 // ---- K4b: HF generation (sbr/HFGeneration.java:17-245) + HF adjustment (sbr/HFAdjustment.java:20-415)
 #ifndef K4B_WARPS
-#define K4B_WARPS 4
+#define K4B_WARPS 10
 #endif
 constexpr int kK4bWarps = K4B_WARPS;
 #ifndef K4B_MIN_BLOCKS
-#define K4B_MIN_BLOCKS 5
+#define K4B_MIN_BLOCKS 2
+#endif
+#ifndef K4B_PREFETCH
+#define K4B_PREFETCH 1
+#endif
+// K4B_ALIGN: the warps of a CTA pass the phases of a frame (generation, envelope estimate, gains, assembly) together.  They
+// are independent channels; the barriers are there for the instruction caches only (87 KB of SASS, 53 KB of it on the
+// path of a regular frame, every phase a loop of 4 .. 10 KB: warps spread over the phases evict each other's loops).
+#ifndef K4B_ALIGN
+#define K4B_ALIGN 1
+#endif
+#if K4B_ALIGN
+#define K4B_PHASE() __syncthreads()
+#define K4B_SKIP_FRAME() do { __syncthreads(); __syncthreads(); __syncthreads(); __syncthreads(); } while (0)
+#else
+#define K4B_PHASE() do {} while (0)
+#define K4B_SKIP_FRAME() do {} while (0)
 #endif
 constexpr int kK4bMaxNL = 32;
 constexpr int kK4bPwCols = 50;   // >= SBR.MAX_M, even
@@ -333,7 +349,15 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
   extern __shared__ __align__(16) uint8_t k4b_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t r = blockIdx.x * kK4bWarps + warp;
+#if K4B_ALIGN
+  // (a warp without a run, or whose run ends before this tile, keeps the CTA's barriers company)
+  if (r >= n_runs || tile.lo >= runs[r].count) {
+    for (uint32_t k = 0; k < tile.ft; ++k) K4B_SKIP_FRAME();
+    return;
+  }
+#else
   if (r >= n_runs) return;
+#endif
   K4bSmem& W = reinterpret_cast<K4bSmem*>(k4b_raw)[warp];
   const K4RunDev run = runs[r];
   if (tile.lo >= run.count) return;
@@ -362,19 +386,39 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
     if (lane < kRecVec) rec = __ldg(src + lane);
   };
   fetch_record(tile.lo);
-  for (uint32_t it = tile.lo; it < hi; ++it) {
+#if K4B_ALIGN
+  const uint32_t it_end = tile.lo + tile.ft;   // the same trip count for every warp of the CTA
+#else
+  const uint32_t it_end = hi;
+#endif
+  for (uint32_t it = tile.lo; it < it_end; ++it) {
+    if (K4B_ALIGN && it >= hi) { K4B_SKIP_FRAME(); continue; }
     __syncwarp();
     if (lane < kRecVec) reinterpret_cast<uint4*>(W.rec_tail)[lane] = rec;
     const SbrFrameDev* gfp = k4_frame(sframes, run, it);
     if (it + 1 < hi) fetch_record(it + 1);
     __syncwarp();
     const int mode = fp->mode;
-    if (fp->frame_status != 0 || mode == 0) continue;
+    if (fp->frame_status != 0 || mode == 0) { K4B_SKIP_FRAME(); continue; }
     float* X = Xrun + 32 * (size_t)n_done * kXgRow;   // row 0 of this frame's Xsbr
     ++n_done;
     last_it = it;
-    if (mode != 2) continue;
+    if (mode != 2) { K4B_SKIP_FRAME(); continue; }
+    K4B_PHASE();
     const int kx = fp->kx, M = fp->M, L_E = fp->L_E;
+#if K4B_PREFETCH
+    // The tile's matrices are far larger than L2 and were written by the analysis kernel before this one started, so every
+    // pass over a column waited a full DRAM latency per block of four slots (long_scoreboard: 30 % of the stall samples).
+    // The low band of the NEXT frame's rows is asked into L2 while this frame is worked on (32 new rows of <= 4 lines).
+    if (n_done < tile.ft) {
+      const char* nx = reinterpret_cast<const char*>(X + (size_t)(32 + kSbrHfGen) * kXgRow);
+      const int nl = min((kx * 8 + 127) >> 7, 4);
+      for (int i = lane; i < 32 * nl; i += 32) {
+        const int row = i / nl, ln = i - row * nl;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)row * kXgRow * sizeof(float) + ln * 128));
+      }
+    }
+#endif
     // (borders beyond the matrix can only come from a damaged grid, where the reference dies with an index error; the
     // clamps keep the accesses inside the tile)
     const int first_slot = min((int)fp->t_E[0], 38), last_slot = min((int)fp->t_E[L_E], 38);
@@ -523,6 +567,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
     __syncwarp();
 
     // ---- HF adjustment (HFAdjustment.java)
+    K4B_PHASE();
     // estimate_current_envelope (:78-131).  With a sorted grid every sample it reads was produced just above and its
     // |X|^2 sits in W.pw; the sums below add the same terms in the same order as the reference.
     if (pw_ok) {
@@ -619,6 +664,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
     for (int i = lane; i < 3 * kSbrMaxLE * 64; i += 32) (&W.g.G[0][0])[i] = 0.f;
     __syncwarp();
 
+    K4B_PHASE();
     // calculate_gain (:242-415)
     const float EPS = 1e-12f;
     const int l_A = fp->l_A;
@@ -810,6 +856,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
     }
     __syncwarp();
 
+    K4B_PHASE();
     // hf_assembly (:133-240): lane m walks the slots of its band.  The reference's 5-entry ring (written at
     // GQ_ringbuf_index, read oldest to newest) is kept age-ordered in registers while a band is walked: A[0] = oldest ...
     // A[4] = newest, and goes back to its ring positions afterwards.
@@ -1285,22 +1332,29 @@ constexpr int kK5Threads = 96;
 constexpr int kK5PhaseThread = 80;  // an otherwise idle thread: the sequential IPD/OPD phase bookkeeping
 constexpr int kK5Bands = 71;        // 10 hybrid sub-bands + QMF bands 3..63
 constexpr int kK5AllPass = 30;      // of which run the all-pass chain: the hybrid ones and QMF bands 3..22
-constexpr int kK5EStride = 65;      // energy plane row: 64 bands + 1 (the slot threads read a column without bank conflicts)
-constexpr int kK5Floats = 32 * kK5EStride + 2 * 32 * 24 + 32 * 20 + 3 * 88 + kK5Bands * 28 + kK5AllPass * 30 + 22 * 8 + 72 + 22 * 5 * 4 + 80;
+constexpr int kK5Floats = 2 * 32 * 24 + 32 * 20 + 3 * 88 + kK5Bands * 28 + kK5AllPass * 30 + 22 * 8 + 72 + 22 * 5 * 4 + 80;
+#ifndef K5_MIN_BLOCKS
+#define K5_MIN_BLOCKS 6
+#endif
+// QMF band 3..63 -> its parameter band minus 8 (groups 10..21 of the 20-band configuration, ps/PSTables.java group_border20)
+__host__ __device__ constexpr int k5_qmf_pb(int band) {
+  return band < 9 ? band - 3 : (band < 11 ? 6 : (band < 14 ? 7 : (band < 18 ? 8 : (band < 23 ? 9 : (band < 35 ? 10 : 11)))));
+}
 static_assert(kK5Floats % 4 == 0, "PsFrameDev must land 16-byte aligned");
 constexpr size_t k5_smem_bytes() { return sizeof(float) * kK5Floats + sizeof(PsFrameDev); }
 
-__global__ void __launch_bounds__(kK5Threads, 6)
+__global__ void __launch_bounds__(kK5Threads, K5_MIN_BLOCKS)
 k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev* __restrict__ sframes,
              const PsFrameDev* __restrict__ ps_frames, PsChanDev* __restrict__ ps_chans, const float* __restrict__ xg,
              float* __restrict__ xps, SbrTablesDev T, K4Tile tile) {
   extern __shared__ __align__(16) float k5_smem[];
   // The frame's two 32 x 64 QMF matrices are NOT staged in shared memory (they were: 33 KB of the 58 KB a CTA needed, three
   // CTAs = nine warps per SM): the decorrelator's band threads read X_left from the tile workspace (L2) slot by slot and
-  // write both outputs straight to xps; the only whole-matrix quantity another thread needs is |X|^2 for the transient
-  // detector's band energies, which gets its own plane.
-  float* eplane = k5_smem;                               // [32][kK5EStride] |X_left[n][band]|^2, QMF bands 3..63
-  float* hyl = eplane + 32 * kK5EStride;                 // [32][12][2]
+  // write both outputs straight to xps.  The only whole-matrix quantity another thread needs is |X|^2 for the transient
+  // detector's band energies: the second warp sums them per slot straight from the slot's row in the workspace (512
+  // contiguous bytes per lane) while the first runs the hybrid analysis -- an 8 KB energy plane in between (band threads
+  // write, slot threads read) held the kernel at six CTAs per SM.
+  float* hyl = k5_smem;                                  // [32][12][2]
   float* hyr = hyl + 32 * 24;                            // [32][12][2]
   float* pg = hyr + 32 * 24;                             // [32][20] band energies, then transient ratios
   float* hwork = pg + 32 * 20;                           // [3][44][2] hybrid analysis input
@@ -1386,31 +1440,19 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
     const int lim_lo = k4_x_limit(fp, mode, 0), lim_hi = k4_x_limit(fp, mode, 31), fs = mode == 2 ? fp->t_E[0] : 0;
     float* outl = xps + ((size_t)(blockIdx.x * tile.ft + (it - tile.lo)) * 2) * 32 * kXgRow;
     float* outr = outl + 32 * kXgRow;
-    if (t < 64) {
-      float2 xv[32];
-#pragma unroll
-      for (int l = 0; l < 32; ++l) xv[l] = __ldg(reinterpret_cast<const float2*>(X + (size_t)(l + kSbrHfAdj) * kXgRow) + t);
-#pragma unroll
-      for (int l = 0; l < 32; ++l) {
-        const int lim = l < fs ? lim_lo : lim_hi;
-        const float re = t < lim ? xv[l].x : 0.f, im = t < lim ? xv[l].y : 0.f;
-        eplane[l * kK5EStride + t] = (re * re) + (im * im);
-      }
-    } else {
-      // work[0..11] = history, work[12 + n] = X[n + 6][band]: rows 6..31 come from X_left, rows 32..37 straight
-      // from Xsbr (:108-113) -- for bands 0..2 both are the unmodified analysis output
-      for (int i = t - 64; i < 3 * 44; i += 32) {
-        const int band = i / 44, j = i % 44;
-        float2 v;
-        if (j < 12) v = make_float2(hybuf[(band * 12 + j) * 2], hybuf[(band * 12 + j) * 2 + 1]);
-        else v = __ldg(reinterpret_cast<const float2*>(X + (size_t)(j - 12 + 6 + kSbrHfAdj) * kXgRow) + band);
-        hwork[(band * 44 + j) * 2] = v.x;
-        hwork[(band * 44 + j) * 2 + 1] = v.y;
-      }
+    // Hybrid analysis input: work[0..11] = history, work[12 + n] = X[n + 6][band]: rows 6..31 come from X_left, rows 32..37
+    // straight from Xsbr (:108-113) -- for bands 0..2 both are the unmodified analysis output
+    for (int i = t; i < 3 * 44; i += kK5Threads) {
+      const int band = i / 44, j = i % 44;
+      float2 v;
+      if (j < 12) v = make_float2(hybuf[(band * 12 + j) * 2], hybuf[(band * 12 + j) * 2 + 1]);
+      else v = __ldg(reinterpret_cast<const float2*>(X + (size_t)(j - 12 + 6 + kSbrHfAdj) * kXgRow) + band);
+      hwork[(band * 44 + j) * 2] = v.x;
+      hwork[(band * 44 + j) * 2 + 1] = v.y;
     }
     __syncthreads();
     const int num_env = pp->num_env;
-    if (t >= 32 && t < 68) { const int u = t - 32, band = u / 12, j = u % 12; hybuf[(band * 12 + j) * 2] = hwork[(band * 44 + 32 + j) * 2]; hybuf[(band * 12 + j) * 2 + 1] = hwork[(band * 44 + 32 + j) * 2 + 1]; }
+    for (int u = t - 64; u >= 0 && u < 36; u += 32) { const int band = u / 12, j = u % 12; hybuf[(band * 12 + j) * 2] = hwork[(band * 44 + 32 + j) * 2]; hybuf[(band * 12 + j) * 2 + 1] = hwork[(band * 44 + 32 + j) * 2 + 1]; }
     // ---- hybrid analysis (ps/Filterbank.java:18-68): thread n
     if (t < 32) {
       const int i = t;
@@ -1499,29 +1541,50 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
       }
 #pragma unroll
       for (int k = 0; k < 12; ++k) { HYR(i, k, 0) = 0.f; HYR(i, k, 1) = 0.f; }
-      // ---- energy per parameter band (ps_decorrelate, :213-234): groups in order, sub-bands in order
+      // ---- energy per parameter band (ps_decorrelate, :213-234): groups in order, sub-bands in order.  Parameter bands
+      // 0..7 belong to the hybrid sub-bands (groups 0..9), 8..19 to the QMF bands (groups 10..21, the next warp).
       {
-        constexpr int gb[23] = {6, 7, 0, 1, 2, 3, 9, 8, 10, 11, 3, 4, 5, 6, 7, 8, 9, 11, 14, 18, 23, 35, 64};
-        float P[20];
+        constexpr int gb[10] = {6, 7, 0, 1, 2, 3, 9, 8, 10, 11};
+        float P[8];
 #pragma unroll
-        for (int b2 = 0; b2 < 20; ++b2) P[b2] = 0.f;
+        for (int b2 = 0; b2 < 8; ++b2) P[b2] = 0.f;
 #pragma unroll
-        for (int g2 = 0; g2 < 22; ++g2) {
+        for (int g2 = 0; g2 < 10; ++g2) {
           const int pb = g2 == 0 ? 1 : (g2 == 1 ? 0 : g2 - 2);
-          const int lo = gb[g2], hi2 = g2 < 10 ? gb[g2] + 1 : gb[g2 + 1];
+          const float re = HYL(i, gb[g2], 0), im = HYL(i, gb[g2], 1);
+          P[pb] += (re * re) + (im * im);
+        }
 #pragma unroll
-          for (int s2 = lo; s2 < hi2; ++s2) {
-            if (g2 < 10) {
-              const float re = HYL(i, s2, 0), im = HYL(i, s2, 1);
-              P[pb] += (re * re) + (im * im);
-            } else {
-              P[pb] += eplane[i * kK5EStride + s2];   // = (re * re) + (im * im) of X_left[i][s2], formed by the band's thread
+        for (int b2 = 0; b2 < 8; ++b2) pg[i * 20 + b2] = P[b2];
+      }
+    } else if (t < 64) {
+      // X_left = the band-limited copy of Xsbr (SBR1.processPS): band b of slot l is X[l + 2][b] below the limit, zero above
+      const int i = t - 32;
+      const float4* row = reinterpret_cast<const float4*>(X + (size_t)(i + kSbrHfAdj) * kXgRow);   // [j] = bands 2j, 2j + 1
+      const int lim = i < fs ? lim_lo : lim_hi;
+      float P[12];
+#pragma unroll
+      for (int b2 = 0; b2 < 12; ++b2) P[b2] = 0.f;
+#pragma unroll
+      for (int j0 = 0; j0 < 32; j0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (j0 + u > 0) v[u] = __ldg(row + j0 + u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int band = 2 * (j0 + u) + h;
+            if (band >= 3) {
+              const float re = h ? v[u].z : v[u].x, im = h ? v[u].w : v[u].y;
+              P[k5_qmf_pb(band)] += band < lim ? (re * re) + (im * im) : 0.f;
             }
           }
         }
-#pragma unroll
-        for (int b2 = 0; b2 < 20; ++b2) pg[i * 20 + b2] = P[b2];
       }
+#pragma unroll
+      for (int b2 = 0; b2 < 12; ++b2) pg[i * 20 + 8 + b2] = P[b2];
     }
     __syncthreads();
     // ---- transient reduction ratio (:236-264): thread bk, sequential in time
