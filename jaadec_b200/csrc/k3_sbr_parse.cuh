@@ -29,6 +29,14 @@ enum { SBR_LO_RES = 0, SBR_HI_RES = 1 };
 // and again; with 200 KB of the SM's L1 carved out as shared memory for the element states they compete for what is left
 // with data that is read once (payload words, frame descriptors, the state copy-in).  So: keep the former, do not
 // allocate the latter.
+// JAADB_BOUNDS_ASSERT: debug builds only (tools/build_variants.sh): device-side asserts on the index ranges of the
+// shared-memory windows below; the product build compiles them out.
+#ifdef JAADB_BOUNDS_ASSERT
+#include <cassert>
+#define JAADB_ASSERT(x) assert(x)
+#else
+#define JAADB_ASSERT(x) do {} while (0)
+#endif
 #ifndef K3_L1_HINTS
 #define K3_L1_HINTS 1
 #endif
@@ -79,6 +87,7 @@ struct SbrBits {
   __device__ __forceinline__ uint32_t left() const { return end > pos ? end - pos : 0u; }
   __device__ __forceinline__ uint32_t peek32() const {
     const uint32_t wi = pos >> 5;
+    JAADB_ASSERT(wi + 1 < 72u);   // kK3StageWords
     return __funnelshift_l(words[wi + 1], words[wi], pos & 31u);
   }
   // n <= 25

@@ -298,7 +298,7 @@ constexpr int kK4bWarps = K4B_WARPS;
 #define K4B_MIN_BLOCKS 2
 #endif
 #ifndef K4B_PREFETCH
-#define K4B_PREFETCH 1
+#define K4B_PREFETCH 3   // bit 0: this frame's generated band before the gains, bit 1: the next frame's low band before the assembly
 #endif
 // K4B_ALIGN: the warps of a CTA pass the phases of a frame (generation, envelope estimate, gains, assembly) together.  They
 // are independent channels; the barriers are there for the instruction caches only (87 KB of SASS, 53 KB of it on the
@@ -395,6 +395,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
     if (K4B_ALIGN && it >= hi) { K4B_SKIP_FRAME(); continue; }
     __syncwarp();
     if (lane < kRecVec) reinterpret_cast<uint4*>(W.rec_tail)[lane] = rec;
+    JAADB_ASSERT(reinterpret_cast<const uint8_t*>(fp) >= reinterpret_cast<const uint8_t*>(&W) && n_done <= tile.ft);
     const SbrFrameDev* gfp = k4_frame(sframes, run, it);
     if (it + 1 < hi) fetch_record(it + 1);
     __syncwarp();
@@ -406,19 +407,6 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
     if (mode != 2) { K4B_SKIP_FRAME(); continue; }
     K4B_PHASE();
     const int kx = fp->kx, M = fp->M, L_E = fp->L_E;
-#if K4B_PREFETCH
-    // The tile's matrices are far larger than L2 and were written by the analysis kernel before this one started, so every
-    // pass over a column waited a full DRAM latency per block of four slots (long_scoreboard: 30 % of the stall samples).
-    // The low band of the NEXT frame's rows is asked into L2 while this frame is worked on (32 new rows of <= 4 lines).
-    if (n_done < tile.ft) {
-      const char* nx = reinterpret_cast<const char*>(X + (size_t)(32 + kSbrHfGen) * kXgRow);
-      const int nl = min((kx * 8 + 127) >> 7, 4);
-      for (int i = lane; i < 32 * nl; i += 32) {
-        const int row = i / nl, ln = i - row * nl;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)row * kXgRow * sizeof(float) + ln * 128));
-      }
-    }
-#endif
     // (borders beyond the matrix can only come from a damaged grid, where the reference dies with an index error; the
     // clamps keep the accesses inside the tile)
     const int first_slot = min((int)fp->t_E[0], 38), last_slot = min((int)fp->t_E[L_E], 38);
@@ -664,6 +652,22 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
     for (int i = lane; i < 3 * kSbrMaxLE * 64; i += 32) (&W.g.G[0][0])[i] = 0.f;
     __syncwarp();
 
+#if K4B_PREFETCH
+    // The tile's matrices are far larger than L2, and the throughput kernels of the other half of the batch stream through
+    // it all the time: what this warp generated a phase ago is back in DRAM when the assembly walks it (long_scoreboard on
+    // that load: 13 % of the stall samples), and so is the next frame's low band, which the analysis kernel wrote before
+    // this kernel started.  Both are asked into L2 one phase ahead of their use.
+    if (K4B_PREFETCH & 1) {
+      const int r0 = first_slot + kSbrHfAdj, nr = last_slot - first_slot;
+      const char* base = reinterpret_cast<const char*>(X + (size_t)r0 * kXgRow) + ((kx * 8) & ~127);
+      const int nl = (((kx + M) * 8 + 127) >> 7) - ((kx * 8) >> 7);
+      JAADB_ASSERT(nr >= 0 && r0 + nr <= 40 && nl >= 0 && ((kx * 8) & ~127) + nl * 128 <= (int)(kXgRow * sizeof(float)));
+      for (int i = lane; i < nr * nl; i += 32) {
+        const int row = i / nl, ln = i - row * nl;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)row * kXgRow * sizeof(float) + ln * 128));
+      }
+    }
+#endif
     K4B_PHASE();
     // calculate_gain (:242-415)
     const float EPS = 1e-12f;
@@ -856,6 +860,16 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
     }
     __syncwarp();
 
+#if K4B_PREFETCH
+    if ((K4B_PREFETCH & 2) && n_done < tile.ft) {   // the next frame's 32 new rows, bands below kx
+      const char* nx = reinterpret_cast<const char*>(X + (size_t)(32 + kSbrHfGen) * kXgRow);
+      const int nl = min((kx * 8 + 127) >> 7, 4);
+      for (int i = lane; i < 32 * nl; i += 32) {
+        const int row = i / nl, ln = i - row * nl;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)row * kXgRow * sizeof(float) + ln * 128));
+      }
+    }
+#endif
     K4B_PHASE();
     // hf_assembly (:133-240): lane m walks the slots of its band.  The reference's 5-entry ring (written at
     // GQ_ringbuf_index, read oldest to newest) is kept age-ordered in registers while a band is walked: A[0] = oldest ...
@@ -1561,6 +1575,7 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
       // X_left = the band-limited copy of Xsbr (SBR1.processPS): band b of slot l is X[l + 2][b] below the limit, zero above
       const int i = t - 32;
       const float4* row = reinterpret_cast<const float4*>(X + (size_t)(i + kSbrHfAdj) * kXgRow);   // [j] = bands 2j, 2j + 1
+      JAADB_ASSERT(fp->ord - ord_lo < tile.ft && (size_t)(32 * (fp->ord - ord_lo) + i + kSbrHfAdj) < tile.rows);
       const int lim = i < fs ? lim_lo : lim_hi;
       float P[12];
 #pragma unroll
