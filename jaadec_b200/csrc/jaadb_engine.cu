@@ -840,6 +840,10 @@ struct DecodeBufs {
   uint32_t k4_banks;       // FrameIndex::k4_banks
 };
 
+// Streams of three to six channels (up to 5.1: 384 threads, 107 KB of shared memory): two CTAs per SM need <= 80 registers
+#ifndef K2_MC_MIN_BLOCKS
+#define K2_MC_MIN_BLOCKS 2
+#endif
 #ifndef K4_TILE_BYTES
 #define K4_TILE_BYTES (16384ull << 20)   // measured: 1.5 GB -> 8 GB took the SBR stages of configs 3 / 4 from 75 / 199 ms to 72 / 176 ms, 8 -> 16 GB 65.4 / 154.0 -> 64.9 / 152.2 ms
 #endif
@@ -894,6 +898,7 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
 #define LAUNCH_K2(FMT)                                                                                              \
   do {                                                                                                              \
     if (threads <= 128) k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS><<<g.n_segs, threads, smem, e->stream>>>(A, e->tables); \
+    else if (threads <= 384 && K2_MC_MIN_BLOCKS > 1) k2_filterbank_kernel<FMT, 384, K2_MC_MIN_BLOCKS><<<g.n_segs, threads, smem, e->stream>>>(A, e->tables); \
     else k2_filterbank_kernel<FMT, 512, 1><<<g.n_segs, threads, smem, e->stream>>>(A, e->tables);                   \
   } while (0)
     if (e->opts.pcm_format == JAADB_PCM_S16LE) LAUNCH_K2(0);
@@ -1076,6 +1081,8 @@ int jaadb_engine_create(const jaadb_options* opts, jaadb_engine** out) {
   // (the one- / two-channel instantiation wants as many resident CTAs as its registers allow: all of the SM's shared memory)
 #define K2_ATTR(FMT)                                                                                                     \
   cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max);             \
+  cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 384, K2_MC_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max); \
+  cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 384, K2_MC_MIN_BLOCKS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
   cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2max2); \
   if (K2_CARVEOUT >= 0) cudaFuncSetAttribute(k2_filterbank_kernel<FMT, 128, K2_STEREO_MIN_BLOCKS>, cudaFuncAttributePreferredSharedMemoryCarveout, K2_CARVEOUT)
   K2_ATTR(0); K2_ATTR(1); K2_ATTR(2);
