@@ -27,9 +27,12 @@
 #include "k4_sbr_process.cuh"
 
 // resident CTAs per SM the one- / two-channel filterbank kernel is compiled for.  Measured on B200 (config 2, round 2
-// session D): 5 (96 registers, 12 bytes of spills) 18.9 ms; 4 (128 registers) 19.6 ms; 6 does not fit the shared memory.
+// session D): 5 (96 registers, 12 bytes of spills) 18.9 ms; 4 (128 registers) 19.6 ms; 6 did not fit the shared memory.
+// Session AB, after the kernel had lost its register prefetch and the exchange-2 planes had moved 8 floats closer (37 840
+// bytes per CTA: six fit with 48 bytes to spare): 6 (80 registers, 0 .. 12 bytes of spills) 18.0 ms against 18.2 ms with 5;
+// issue slots 64 %, but `no_instructions` is now the top stall (17.6 %): 24 warps spread over 80 KB of SASS.
 #ifndef K2_STEREO_MIN_BLOCKS
-#define K2_STEREO_MIN_BLOCKS 5
+#define K2_STEREO_MIN_BLOCKS 6
 #endif
 // shared-memory carve-out preference of the one- / two-channel filterbank kernel in percent (-1: the driver's choice).  The
 // kernel's table look-ups (IQ, windows, twiddles) live in what is left of the 256 KB for L1.

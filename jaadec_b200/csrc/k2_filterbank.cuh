@@ -31,7 +31,7 @@ namespace jaadb {
 constexpr int kThreadsPerChannel = 64;
 // shared memory per channel (floats): spectrum (1024 + 1 pad per 32) / FFT exchange 2 (two planes of 576) / packed PCM,
 // overlap (1024), FFT exchange 1 + post-twiddled buffer (two planes of 576)
-constexpr int kSpecStride = 1152;
+constexpr int kSpecStride = 1136;   // spectrum: 1024 + 1024 / 32 padding words; as exchange 2: planes re [0, 568) | im [568, 1136)
 constexpr int kXchgStride = 8 * 72;     // 8 blocks of 8x8 complex, rows padded to 9; 8 short windows of 64 + 8
 constexpr int kK2ChFloats = kSpecStride + 1024 + 2 * kXchgStride;
 constexpr int kK2StageBytesPerCh = 2048 + (int)sizeof(IcsSide);   // q[1024] int16 + IcsSide of the next frame (+ its K2FrameDev, once)
@@ -791,10 +791,11 @@ k2_filterbank_kernel(const K2Args A, const TablesDev T) {
       }
     }
     // The spectrum was consumed before the channel barrier above, so its storage now carries exchange 2 (planes re | im,
-    // 576 floats each: 8 pad floats per 64 keep both the strided writes and the contiguous reads conflict-free); the
-    // post-twiddled buffer then goes where exchange 1 was.
+    // 8 blocks of 72 floats each: 8 pad floats per 64 keep both the strided writes and the contiguous reads conflict-free;
+    // the last block's pad is never touched, so the planes sit 568 apart -- those 64 bytes per channel are what lets a
+    // sixth two-channel CTA fit the SM); the post-twiddled buffer then goes where exchange 1 was.
     float* x2re = my_spec;
-    float* x2im = my_spec + 576;
+    float* x2im = my_spec + 568;
     float* bre = my_xre;               // post-twiddled buffer as planes re[512] | im[512] (short: 8 windows of 64 at stride 72)
     float* bim = my_xim;
     if (!is_short) {
