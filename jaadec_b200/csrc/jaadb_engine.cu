@@ -204,7 +204,6 @@ struct jaadb_engine {
   std::vector<int32_t> free_slots;
   std::vector<uint32_t> scratch_count, scratch_run_of, scratch_fill, scratch_size;
   std::vector<jaadb_frame_desc> scratch_frames, scratch_frames_sm;   // jaadb_decode_containers: frame-major table, stream-major scratch
-  std::vector<uint64_t> scratch_off;
   FrameIndex scratch_ix;
   // device tables
   std::vector<void*> table_allocs;
@@ -258,6 +257,8 @@ struct jaadb_engine {
     DevBuf<PsFrameDev> ps_frames;
     DevBuf<float> core;
     FrameSide* h_fside = nullptr;      // pinned
+    uint64_t* h_off = nullptr;         // pinned: PCM placement of every frame of a call (uploaded while the host goes on)
+    size_t h_off_cap = 0;
     uint32_t* h_pcm_bytes = nullptr;   // pinned
     size_t h_cap = 0;
     // pinned descriptor staging, double buffered (chunk k uses slot k & 1)
@@ -1132,6 +1133,7 @@ void jaadb_engine_destroy(jaadb_engine* e) {
   W.run_frames.release(); W.pcm_bytes.release(); W.pcm_off.release(); W.k2frames.release(); W.segs.release(); W.ovl_stage.release();
   W.sbr_runs.release(); W.k4_runs.release(); W.sbr_frames.release(); W.core.release(); W.ps_frames.release();
   if (W.h_fside) cudaFreeHost(W.h_fside);
+  if (W.h_off) cudaFreeHost(W.h_off);
   if (W.h_pcm_bytes) cudaFreeHost(W.h_pcm_bytes);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -1502,10 +1504,19 @@ int64_t jaadb_decode_containers(jaadb_engine* e, int32_t kind, const uint8_t* bl
     e->set_error("the containers hold more frames than max_frames");
     return JAADB_E_CAPACITY;
   }
-  if (frames_out && n) memcpy(frames_out, e->scratch_frames.data(), (size_t)n * sizeof(jaadb_frame_desc));
   if (n == 0) { cudaStreamSynchronize(e->stream); return 0; }
   if (trace) fprintf(stderr, "[jaadb] containers indexed (%lld frames) at %.2f ms\n", (long long)n,
                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count());
+  // the caller's copy of the frame table (30 MB for two million frames) is made next to the decode, not in front of it
+  std::thread copy_out;
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{copy_out};   // (also on an exception)
+  if (frames_out) {
+    try {
+      copy_out = std::thread([&] { memcpy(frames_out, e->scratch_frames.data(), (size_t)n * sizeof(jaadb_frame_desc)); });
+    } catch (...) {
+      memcpy(frames_out, e->scratch_frames.data(), (size_t)n * sizeof(jaadb_frame_desc));
+    }
+  }
   rc = decode_impl(e, blob, blob_bytes, e->scratch_frames.data(), (uint32_t)n, pcm_out, pcm_capacity, nullptr, results, true);
   return rc ? rc : n;
 }
@@ -1537,7 +1548,21 @@ int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const
     else cudaGetLastError();
     if (out_dev && (reinterpret_cast<uintptr_t>(pcm_out) & 3u)) { cudaStreamSynchronize(e->stream); e->set_error("device pcm_out must be 4-byte aligned"); return JAADB_E_INVALID; }
   }
-  std::vector<uint64_t>& off = e->scratch_off;
+  // (pinned: from a pageable vector the upload below would be a blocking copy queued behind the containers' 15 ms on the
+  // bus -- the host reached the first chunk 4 ms later than the GPU could have started it)
+  if (W.h_off_cap < n_frames) {
+    if (W.h_off) cudaFreeHost(W.h_off);
+    W.h_off = nullptr;
+    W.h_off_cap = 0;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&W.h_off), sizeof(uint64_t) * (size_t)n_frames, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      cudaStreamSynchronize(e->stream);
+      e->set_error("workspace allocation (pinned PCM offsets)");
+      return JAADB_E_NOMEM;
+    }
+    W.h_off_cap = n_frames;
+  }
+  uint64_t* const off = W.h_off;
   std::vector<uint32_t>& size = e->scratch_size;
   // One pass over the frame table: PCM placement (the caller's offsets, or frames packed back to back in array order), the
   // checks of every descriptor -- before the first kernel: a bad one in a later chunk must not leave the streams of the
@@ -1548,7 +1573,6 @@ int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const
   bool any_sbr = false;
   int rc = JAADB_OK;
   {
-    if (off.size() < n_frames) off.resize(n_frames);
     if (size.size() < n_frames) size.resize(n_frames);
     const size_t n_streams = e->streams.size();
     const uint32_t per = (e->opts.pcm_format == JAADB_PCM_F32_PLANAR) ? 4u : 2u;
@@ -1631,7 +1655,8 @@ int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const
   uint32_t step = ramp ? chunk / 8 : chunk;
   for (uint32_t i0 = 0; i0 < n_frames;) {
     Range r{i0, std::min(n_frames, i0 + step), ~0ull, 0};
-    for (uint32_t i = r.i0; i < r.i1; ++i) { r.lo = std::min(r.lo, off[i]); r.hi = std::max(r.hi, off[i] + size[i]); }
+    if (!pcm_offsets) { r.lo = off[r.i0]; r.hi = off[r.i1 - 1] + size[r.i1 - 1]; }   // packed back to back in array order
+    else for (uint32_t i = r.i0; i < r.i1; ++i) { r.lo = std::min(r.lo, off[i]); r.hi = std::max(r.hi, off[i] + size[i]); }
     ranges.push_back(r);
     i0 = r.i1;
     step = std::min(chunk, step + step / 4);
@@ -1712,7 +1737,7 @@ int decode_impl(jaadb_engine* e, const uint8_t* blob, uint64_t blob_bytes, const
   }
 
   // PCM placement of every frame
-  CUDA_TRY(e, cudaMemcpyAsync(W.pcm_off.p, off.data(), sizeof(uint64_t) * n_frames, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(W.pcm_off.p, off, sizeof(uint64_t) * n_frames, cudaMemcpyHostToDevice, e->stream));
 
   FrameIndex& ix = e->scratch_ix;
   uint32_t launches = 0;
