@@ -752,7 +752,7 @@ int index_frames(jaadb_engine* e, const jaadb_frame_desc* fd, uint32_t n, uint64
     for (uint32_t r = g.first_run; r < g.first_run + g.n_runs; ++r) { total += ix.runs[r].count; longest = std::max(longest, ix.runs[r].count); }
     uint32_t G = 0;
     if (e->opts.k2_segment_frames) G = e->opts.k2_segment_frames;
-    else if (g.n_runs * 2 <= kK2SegCtas) G = (uint32_t)std::max<uint64_t>(2, (total + kK2SegCtas - 1) / kK2SegCtas);
+    else if (g.n_runs < 2 * kK2SegCtas) G = (uint32_t)std::max<uint64_t>(2, (total + 2 * kK2SegCtas - 1) / (2 * kK2SegCtas));   // two waves of segments
     if (G >= longest) G = 0;
     g.first_seg = (uint32_t)ix.segs.size();
     g.segmented = G != 0;

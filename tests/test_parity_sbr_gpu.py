@@ -256,3 +256,27 @@ def test_ps_ipdopd_parameters_equal_generator_truth_and_state_crosses_calls():
             b.close()
         eng.close()
     assert n_rot > 60
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg_no", [3, 4])
+@pytest.mark.parametrize("segment", [2, 7])
+def test_sbr_streams_with_a_segmented_core_filterbank(cfg_no, segment):
+    """K2 cuts the runs of small batches into segments decoded by different CTAs (a segment re-runs the frame before it for
+    the overlap it starts from).  For SBR streams the core PCM it hands to the QMF stages must not change: float PCM of the
+    whole stream bit-identical to the oracle, in one call and across calls."""
+    cfg = gen.config(cfg_no, n_frames=23)
+    wl = Workload(cfg, 3, base_seed=990 + cfg_no, with_truth=False)
+    decs = wl.oracle_decoders()
+    eng = Engine(max_streams=8, pcm_format=PCM_F32_PLANAR, k2_segment_frames=segment)
+    ids = [eng.open_adts(*wl.hdr, expect_sbr=cfg.sbr_mode) for _ in range(3)]
+    per = 2 * 2048 * 4
+    for lo, hi in ((0, 9), (9, 23)):
+        frames, index = wl.frame_table(ids, lo, hi)
+        pcm, res = eng.decode(wl.blob, frames)
+        for i, (s, f) in enumerate(index):
+            r = decs[s].decode_frame(wl.frame_bytes(s, f))
+            assert res["status"][i] == 0 and r["status"] == 0
+            got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(2, 2048)
+            assert same_float_bits(got, r["f32"]), (s, f)
+    eng.close()
