@@ -1421,7 +1421,7 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
     for (int i = 0; i < 8; ++i) hprev[t * 8 + i] = pst->h_prev[t][i];
   if (t < 72) hybuf[t] = (&pst->hyb_buffer[0][0][0])[t];
   if (t < 80) pdprev[t] = (&pst->pd_prev[0][0][0])[t];
-  int phase_hist = pst->phase_hist;             // (thread kK5PhaseThread carries it)
+  int phase_hist = pst->phase_hist;             // (uniform: every thread counts the pairs)
   float peak = 0, pprev = 0, smooth_prev = 0;   // transient detector of parameter band t
   if (t < 20) { peak = pst->P_PeakDecayNrg[t]; pprev = pst->P_prev[t]; smooth_prev = pst->P_SmoothPeakDecayDiffNrg_prev[t]; }
   // per-band constants of the decorrelator (ps/PSImpl.java:266-396)
@@ -1618,38 +1618,46 @@ k5_ps_kernel(const K4RunDev* __restrict__ runs, uint32_t run0, const SbrFrameDev
         pg[n * 20 + t] = ((sm * gamma) <= nrg) ? 1.0f : (nrg / (sm * gamma));
       }
     }
-    // ---- IPD/OPD phase rotation parameters (ps_mix_phase, :488-560), thread kK5PhaseThread alongside the transient
-    // detector: sequential over (group, envelope) in the reference's order, because phase_hist moves once per pair and the
-    // groups 0/3 and 1/2 share a parameter band's history.  Quirks kept (SURVEY A-15): opd_index is read from ipd -- so
-    // ipd.prev and opd.prev always hold the same values (pdprev) -- and the value "before previous" comes from opd.prev for both.
+    // ---- IPD/OPD phase rotation parameters (ps_mix_phase, :488-560) alongside the transient detector.  Quirks kept
+    // (SURVEY A-15): opd_index is read from ipd -- so ipd.prev and opd.prev always hold the same values (pdprev) -- and the
+    // value "before previous" comes from opd.prev for both.
     const int nr_ipdopd_par = pp->nr_ipdopd_par;
-    if (t == kK5PhaseThread && nr_ipdopd_par) {
-      for (int g2 = 0; g2 < 22; ++g2) {
-        const int b2 = ps_bk(g2);
-        if (b2 >= nr_ipdopd_par) continue;
-        for (int env = 0; env < num_env; ++env) {
-          float* pv = pdprev + (b2 * 2 + phase_hist) * 2;
-          float tl0 = (pv[0] * 0.25f), tl1 = (pv[1] * 0.25f), tr0 = (pv[0] * 0.25f), tr1 = (pv[1] * 0.25f);
-          const int ix = min(abs((int)pp->ipd[env][b2]), 8);
-          const float c0 = __ldg(T.ps_ipdopd_cos + ix), s0v = __ldg(T.ps_ipdopd_sin + ix);
-          pv[0] = c0; pv[1] = s0v;
-          tl0 += c0; tl1 += s0v; tr0 += c0; tr1 += s0v;
-          phase_hist = (phase_hist + 1) % 2;
-          const float* pb = pdprev + (b2 * 2 + phase_hist) * 2;
-          tl0 += (pb[0] * 0.5f); tl1 += (pb[1] * 0.5f); tr0 += (pb[0] * 0.5f); tr1 += (pb[1] * 0.5f);
-          // magnitude_c (:402-404): (float) Math.sqrt of a float sum of squares -- a correctly rounded float sqrt is the same value
-          const float xy = __fsqrt_rn((tr0 * tr0) + (tr1 * tr1)), pq = __fsqrt_rn((tl0 * tl0) + (tl1 * tl1));
-          float pl0 = 0.f, pl1 = 0.f, pr0 = 0.f, pr1 = 0.f;
-          if (xy != 0.f) { pl0 = __fdiv_rn(tr0, xy); pl1 = __fdiv_rn(tr1, xy); }
-          const float xypq = (xy * pq);
-          if (xypq != 0.f) {
-            const float tmp1 = (tr0 * tl0) + (tr1 * tl1), tmp2 = (tr1 * tl0) - (tr0 * tl1);
-            pr0 = __fdiv_rn(tmp1, xypq); pr1 = __fdiv_rn(tmp2, xypq);
+    if (nr_ipdopd_par) {
+      // The reference walks (group, envelope) pairs in group order and flips phase_hist once per pair; the groups it visits
+      // are 0 .. nr_ipdopd_par + 1, so pair (g, env) sees phase_hist + g * num_env + env.  A parameter band's history is only
+      // touched by its own pairs (bands 0 and 1 have two groups each: 1, 2 and 0, 3), so the bands run on one thread each
+      // -- threads that have no decorrelator band -- with their pairs in the reference's order.
+      const int b2 = t - (kK5Threads - 20);
+      if (b2 >= 0 && b2 < nr_ipdopd_par) {
+        const int ga = b2 == 0 ? 1 : (b2 == 1 ? 0 : b2 + 2), gb = b2 == 0 ? 2 : (b2 == 1 ? 3 : -1);
+        for (int k = 0; k < 2; ++k) {
+          const int g2 = k ? gb : ga;
+          if (g2 < 0) break;
+          for (int env = 0; env < num_env; ++env) {
+            const int ph0 = (phase_hist + g2 * num_env + env) & 1;
+            float* pv = pdprev + (b2 * 2 + ph0) * 2;
+            float tl0 = (pv[0] * 0.25f), tl1 = (pv[1] * 0.25f), tr0 = (pv[0] * 0.25f), tr1 = (pv[1] * 0.25f);
+            const int ix = min(abs((int)pp->ipd[env][b2]), 8);
+            const float c0 = __ldg(T.ps_ipdopd_cos + ix), s0v = __ldg(T.ps_ipdopd_sin + ix);
+            pv[0] = c0; pv[1] = s0v;
+            tl0 += c0; tl1 += s0v; tr0 += c0; tr1 += s0v;
+            const float* pb = pdprev + (b2 * 2 + (ph0 ^ 1)) * 2;
+            tl0 += (pb[0] * 0.5f); tl1 += (pb[1] * 0.5f); tr0 += (pb[0] * 0.5f); tr1 += (pb[1] * 0.5f);
+            // magnitude_c (:402-404): (float) Math.sqrt of a float sum of squares -- a correctly rounded float sqrt is the same value
+            const float xy = __fsqrt_rn((tr0 * tr0) + (tr1 * tr1)), pq = __fsqrt_rn((tl0 * tl0) + (tl1 * tl1));
+            float pl0 = 0.f, pl1 = 0.f, pr0 = 0.f, pr1 = 0.f;
+            if (xy != 0.f) { pl0 = __fdiv_rn(tr0, xy); pl1 = __fdiv_rn(tr1, xy); }
+            const float xypq = (xy * pq);
+            if (xypq != 0.f) {
+              const float tmp1 = (tr0 * tl0) + (tr1 * tl1), tmp2 = (tr1 * tl0) - (tr0 * tl1);
+              pr0 = __fdiv_rn(tmp1, xypq); pr1 = __fdiv_rn(tmp2, xypq);
+            }
+            float* ph = phases + (g2 * 5 + env) * 4;
+            ph[0] = pl0; ph[1] = pl1; ph[2] = pr0; ph[3] = pr1;
           }
-          float* ph = phases + (g2 * 5 + env) * 4;
-          ph[0] = pl0; ph[1] = pl1; ph[2] = pr0; ph[3] = pr1;
         }
       }
+      phase_hist = (phase_hist + min(22, nr_ipdopd_par + 2) * num_env) & 1;   // (every thread keeps the count)
     }
     // the mixing matrices the groups ended the previous envelope with (read by every band of the group before any of
     // them stores the new ones)
