@@ -1,0 +1,13 @@
+#!/bin/bash
+# round-2 GPU session X2: validation of the final build: GPU suite, smoke, the default bench line, the reference arm, launch lists
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+O=gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > $O/r2x2_pytest.log 2>&1; echo "pytest rc=$?" >> $O/r2x2_pytest.log
+tail -3 $O/r2x2_pytest.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/r2x2_smoke.log 2>&1; tail -2 $O/r2x2_smoke.log
+python bench.py > $O/r2x2_bench_default.json 2> $O/r2x2_bench_default.err; echo "bench rc=$?"; cut -c1-300 $O/r2x2_bench_default.json
+python bench.py --impl reference --steps 2 --warmup 1 > $O/r2x2_bench_reference.json 2> $O/r2x2_bench_reference.err; echo "ref rc=$?"; cut -c1-200 $O/r2x2_bench_reference.json
+for c in 2 3 4 5; do
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/r2x2_launches_c$c.csv python bench.py --config $c --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extras > $O/r2x2_ncu_c$c.log 2>&1
+done
