@@ -52,10 +52,12 @@ NAMES = {1: "AAC-LC 44.1 kHz stereo ADTS, one 10 s stream, long windows only",
          5: "AAC-LC 5.1 48 kHz MP4 files (mp4 demux path)"}
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch at the default sizes, from the committed
 # `ncu --set full` captures (profiles/README.md names the file per entry); None where no capture exists
-NCU_TRAFFIC = {(2, "k2_filterbank_kernel"): 9.565e9 + 7.877e9}
+NCU_TRAFFIC = {(2, "k2_filterbank_kernel"): 9.512e9 + 7.871e9, (5, "k2_filterbank_kernel"): 28.394e9 + 23.691e9}
 # what limits the dominant kernel according to those captures (issue-slot utilisation of the SM sub-partitions)
 NCU_LIMITER = {(2, "k2_filterbank_kernel"): {"limiter": "issue/latency (instruction fetch + L1 table look-ups), not HBM",
-                                             "issue_slot_frac": 0.61, "dram_frac": 0.12, "source": "profiles/r2_k1_k2_ncu_raw.txt"}}
+                                             "issue_slot_frac": 0.64, "dram_frac": 0.12, "source": "profiles/r2_late_k2_k4_k5_ncu_raw.txt"},
+               (5, "k2_filterbank_kernel"): {"limiter": "issue/latency, not HBM", "issue_slot_frac": 0.63, "dram_frac": 0.11,
+                                             "source": "profiles/r2_late_k2_k4_k5_ncu_raw.txt"}}
 
 
 def read_peaks():
