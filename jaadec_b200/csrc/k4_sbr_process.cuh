@@ -300,17 +300,29 @@ constexpr int kK4bWarps = K4B_WARPS;
 #ifndef K4B_PREFETCH
 #define K4B_PREFETCH 3   // bit 0: this frame's generated band before the gains, bit 1: the next frame's low band before the assembly
 #endif
-// K4B_ALIGN: the warps of a CTA pass the phases of a frame (generation, envelope estimate, gains, assembly) together.  They
+// K4B_ALIGN: the warps of a CTA pass the phases of a frame together (1: generation, envelope estimate, gains, assembly; 2: in
+// front of the two long ones, generation and assembly, only -- measured 57.1 / 141.5 ms against 57.7 / 141.6 ms for the SBR
+// stage of configs 3 / 4; 3: generation, gains, assembly: 57.3 / 141.8 ms).  They
 // are independent channels; the barriers are there for the instruction caches only (87 KB of SASS, 53 KB of it on the
 // path of a regular frame, every phase a loop of 4 .. 10 KB: warps spread over the phases evict each other's loops).
 #ifndef K4B_ALIGN
-#define K4B_ALIGN 1
+#define K4B_ALIGN 2
 #endif
-#if K4B_ALIGN
+#if K4B_ALIGN == 1
 #define K4B_PHASE() __syncthreads()
+#define K4B_PHASE_MINOR() __syncthreads()
 #define K4B_SKIP_FRAME() do { __syncthreads(); __syncthreads(); __syncthreads(); __syncthreads(); } while (0)
+#elif K4B_ALIGN == 2   // only in front of the two long phases (generation, assembly)
+#define K4B_PHASE() __syncthreads()
+#define K4B_PHASE_MINOR() do {} while (0)
+#define K4B_SKIP_FRAME() do { __syncthreads(); __syncthreads(); } while (0)
+#elif K4B_ALIGN == 3   // generation, gains, assembly
+#define K4B_PHASE() __syncthreads()
+#define K4B_PHASE_MINOR() do {} while (0)
+#define K4B_SKIP_FRAME() do { __syncthreads(); __syncthreads(); __syncthreads(); } while (0)
 #else
 #define K4B_PHASE() do {} while (0)
+#define K4B_PHASE_MINOR() do {} while (0)
 #define K4B_SKIP_FRAME() do {} while (0)
 #endif
 constexpr int kK4bMaxNL = 32;
@@ -555,7 +567,7 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
     __syncwarp();
 
     // ---- HF adjustment (HFAdjustment.java)
-    K4B_PHASE();
+    K4B_PHASE_MINOR();
     // estimate_current_envelope (:78-131).  With a sorted grid every sample it reads was produced just above and its
     // |X|^2 sits in W.pw; the sums below add the same terms in the same order as the reference.
     if (pw_ok) {
@@ -668,7 +680,11 @@ k4b_hf_kernel(const K4RunDev* __restrict__ runs, uint32_t n_runs, const RunFrame
       }
     }
 #endif
+#if K4B_ALIGN == 2
+    K4B_PHASE_MINOR();
+#else
     K4B_PHASE();
+#endif
     // calculate_gain (:242-415)
     const float EPS = 1e-12f;
     const int l_A = fp->l_A;
