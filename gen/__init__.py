@@ -31,7 +31,7 @@ class _Cfg(C.Structure):
         ("sf_index", C.c_int32), ("chan_cfg", C.c_int32), ("n_frames", C.c_int32), ("target_bytes", C.c_int32),
         ("long_only", C.c_int32), ("adts", C.c_int32), ("p_transient", C.c_float), ("p_common_window", C.c_float),
         ("p_tns", C.c_float), ("p_is", C.c_float), ("ms_mode", C.c_int32), ("sbr_mode", C.c_int32),
-        ("target_rms", C.c_float), ("sbr_quirk", C.c_int32), ("sbr_downsampled", C.c_int32), ("p_pns", C.c_float), ("tns_mild", C.c_int32), ("ps_ext", C.c_float), ("ps_iso", C.c_int32),
+        ("target_rms", C.c_float), ("sbr_quirk", C.c_int32), ("sbr_downsampled", C.c_int32), ("p_pns", C.c_float), ("tns_mild", C.c_int32), ("ps_ext", C.c_float), ("ps_iso", C.c_int32), ("p_pulse", C.c_float), ("pulse_wild", C.c_int32), ("p_drc", C.c_float),
     ]
 
 
@@ -77,11 +77,14 @@ class GenConfig:
     tns_mild: bool = False    # TNS filters an ISO decoder can apply: order <= 12 (long) / 7 (short), small coefficients
     ps_ext: float = 0.0       # probability that a parametric-stereo header enables the IPD/OPD extension
     ps_iso: bool = False      # PS modes restricted to the ones JAAD decodes the way ISO/IEC 14496-3 says (10-band, type-A mixing)
+    p_pulse: float = 0.0      # probability that a long-window ICS carries pulse_data (truth q = what an ISO decoder reconstructs)
+    pulse_wild: bool = False  # pulses may also land past max_sfb (decoders must leave those alone; FFmpeg does not)
+    p_drc: float = 0.0        # probability that a frame ends with a dynamic_range_info fill element (JAAD parses and drops it)
 
     def c(self) -> _Cfg:
         return _Cfg(self.sf_index, self.chan_cfg, self.n_frames, self.target_bytes, int(self.long_only), int(self.adts),
                     self.p_transient, self.p_common_window, self.p_tns, self.p_is, self.ms_mode, self.sbr_mode,
-                    self.target_rms, int(self.sbr_quirk), int(self.sbr_downsampled), self.p_pns, int(self.tns_mild), self.ps_ext, int(self.ps_iso))
+                    self.target_rms, int(self.sbr_quirk), int(self.sbr_downsampled), self.p_pns, int(self.tns_mild), self.ps_ext, int(self.ps_iso), self.p_pulse, int(self.pulse_wild), self.p_drc)
 
 
 # BASELINE.json configurations.  Seeds: 0xAAC0 + 1000*config + stream_id.

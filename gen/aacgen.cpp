@@ -145,6 +145,8 @@ struct Ctx {
   double psExt = 0;     // > 0: PS headers enable the IPD/OPD extension with this probability
   bool psIso = false;   // PS modes restricted to the ones JAAD decodes like ISO/IEC 14496-3 (aacgen_ps.inc)
   bool tnsMild = false; // TNS filters an ISO decoder can apply without blowing up: order <= 12 / 7, small reflection coefficients
+  double pPulse = 0;    // > 0: probability that a long-window ICS carries pulse_data (ISO/IEC 14496-3 4.6.3.3)
+  bool pulseWild = false; // pulses may also land past max_sfb (no encoder does that; decoders differ: FFmpeg uses stale band data)
   explicit Ctx(uint64_t seed, int sfi) : rng(seed), sfIndex(sfi) {}
 };
 
@@ -455,6 +457,45 @@ void writeIcsInfo(BitWriter& bw, const IcsPlan& p) {
   }
 }
 
+// pulse_data (ISO/IEC 14496-3 4.4.2.7 table 4.7, 4.6.3.3): up to four pulses; the decoder adds each amplitude to the magnitude
+// of the quantised coefficient at its position.  IcsPlan::q stays what an ISO decoder must end up with (the ground truth);
+// the coefficient that goes into the bitstream is the one with the pulse taken off.  Pulses that land in bands without
+// spectral data (codebooks 0, 13, 14, 15, or past max_sfb) carry any amplitude: a decoder has to leave those alone.
+struct PulsePlan {
+  int count = 0, startSfb = 0;
+  int offset[4] = {0, 0, 0, 0};   // the 5-bit increments
+  int amp[4] = {0, 0, 0, 0};
+  int pos[4] = {0, 0, 0, 0};
+  int16_t qtx[4] = {0, 0, 0, 0};  // transmitted coefficient at pos (valid when coded)
+  bool coded[4] = {false, false, false, false};
+};
+
+void planPulses(Ctx& c, const IcsPlan& p, PulsePlan& pp) {
+  if (p.ws == 2 || p.maxSfb == 0 || !(c.pPulse > 0) || !c.rng.chance(c.pPulse)) return;
+  pp.startSfb = c.rng.range(0, std::min(p.maxSfb, p.nswb) - 1);
+  const int want = c.rng.range(1, 4);
+  int pos = p.swb[pp.startSfb];
+  for (int i = 0; i < want; ++i) {
+    const int inc = c.rng.range(0, 31);
+    if (pos + inc > 1023 || (!c.pulseWild && pos + inc >= p.swb[p.maxSfb])) break;
+    pos += inc;
+    int amp = c.rng.range(0, 15);
+    int sfb = 0;
+    while (sfb < p.maxSfb && p.swb[sfb + 1] <= pos) ++sfb;
+    const int cb = sfb < p.maxSfb ? p.cb[sfb] : 0;
+    bool coded = cb >= 1 && cb <= 11;
+    for (int j = 0; j < pp.count; ++j) if (pp.pos[j] == pos) coded = false, amp = 0;  // (inc 0: one pulse per coefficient is enough)
+    int16_t qtx = 0;
+    if (coded) {
+      const int qf = p.q[pos];
+      amp = qf > 0 ? std::min(amp, qf - 1) : std::min(amp, -qf);
+      qtx = (int16_t)(qf > 0 ? qf - amp : qf + amp);
+    }
+    pp.offset[i] = inc; pp.amp[i] = amp; pp.pos[i] = pos; pp.qtx[i] = qtx; pp.coded[i] = coded;
+    pp.count = i + 1;
+  }
+}
+
 void writeIcs(Ctx& c, BitWriter& bw, const IcsPlan& p, bool commonWindow) {
   bw.put(p.globalGain, 8);
   if (!commonWindow) writeIcsInfo(bw, p);
@@ -490,15 +531,26 @@ void writeIcs(Ctx& c, BitWriter& bw, const IcsPlan& p, bool commonWindow) {
     if (cb >= 14) { int d = p.sf[i] - curIs; bw.put(g_sfCode[d + 60], g_sfLen[d + 60]); curIs = p.sf[i]; }
     else { int d = p.sf[i] - cur; bw.put(g_sfCode[d + 60], g_sfLen[d + 60]); cur = p.sf[i]; }
   }
-  bw.put(0, 1);  // pulse_data_present
+  PulsePlan pp;
+  planPulses(c, p, pp);
+  bw.put(pp.count ? 1 : 0, 1);  // pulse_data_present
+  if (pp.count) {
+    bw.put(pp.count - 1, 2);
+    bw.put(pp.startSfb, 6);
+    for (int i = 0; i < pp.count; ++i) { bw.put(pp.offset[i], 5); bw.put(pp.amp[i], 4); }
+  }
   bw.put(p.tns ? 1 : 0, 1);
   if (p.tns) bw.append(p.tnsBits);
   bw.put(0, 1);  // gain_control_data_present
+  IcsPlan& mp = const_cast<IcsPlan&>(p);
+  int16_t keep[4];
+  for (int i = 0; i < pp.count; ++i) if (pp.coded[i]) { keep[i] = mp.q[pp.pos[i]]; mp.q[pp.pos[i]] = pp.qtx[i]; }
   int groupOff = 0;
   for (int g = 0; g < p.ngroups; ++g) {
     for (int sfb = 0; sfb < p.maxSfb; ++sfb) writeBand(bw, p, g, sfb, groupOff);
     groupOff += p.glen[g] * 128;
   }
+  for (int i = 0; i < pp.count; ++i) if (pp.coded[i]) mp.q[pp.pos[i]] = keep[i];
 }
 
 #include "aacgen_sbr.inc"
@@ -529,6 +581,10 @@ struct jg_config {
   int32_t tns_mild;       // 1: TNS filters an ISO decoder can apply (orders <= 12 / 7, small coefficients)
   float ps_ext;           // > 0: probability that a PS header enables the IPD/OPD extension (ps/Extension.java)
   int32_t ps_iso;         // 1: only the PS modes on which JAAD and ISO/IEC 14496-3 agree (cross-checks against other decoders)
+  float p_pulse;          // > 0: probability that a long-window ICS carries pulse_data; the truth's q is what an ISO decoder
+                          //      reconstructs (JAAD parses the pulses and never applies them, A/syntax/ICStream.java:17)
+  int32_t pulse_wild;     // 1: pulses may also land past max_sfb
+  float p_drc;            // > 0: probability that a frame ends with a dynamic_range_info fill element (+ sometimes padding)
 };
 
 // Ground truth per ICS (element order, L before R); arrays may be NULL.
@@ -562,6 +618,8 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
   c.tnsMild = cfg->tns_mild != 0;
   c.psExt = cfg->ps_ext;
   c.psIso = cfg->ps_iso != 0;
+  c.pPulse = cfg->p_pulse;
+  c.pulseWild = cfg->pulse_wild != 0;
   const int nIcs = jg_ics_per_frame(cfg->chan_cfg);
   const int nEl = jg_elements_per_frame(cfg->chan_cfg);
   // element layout
@@ -715,6 +773,39 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
                       (truth && truth->sbr) ? truth->sbr + ((size_t)f * nIcs + icsIdx) * kSbrTruthInts : nullptr, nullptr,
                       cfg->sbr_quirk != 0);
         icsIdx += 2;
+      }
+    }
+    // fill elements real encoders add after the audio elements: dynamic_range_info (extension type 11; JAAD parses it into
+    // an object nobody reads, syntax/DRC.java) and plain padding (types 0 / 1)
+    if (cfg->p_drc > 0 && c.rng.chance(cfg->p_drc)) {
+      BitWriter d;
+      d.put(11, 4);
+      const bool pce = c.rng.chance(0.3), excl = c.rng.chance(0.3), bands = c.rng.chance(0.4), ref = c.rng.chance(0.5);
+      int nb = 1;
+      d.put(pce, 1);
+      if (pce) { d.put(c.rng.range(0, 15), 4); d.put(0, 4); }
+      d.put(excl, 1);
+      if (excl) { for (int i = 0; i < 7; ++i) d.put(c.rng.range(0, 1), 1); d.put(0, 1); }   // (JAAD cannot take a second group)
+      d.put(bands, 1);
+      if (bands) {
+        const int inc = c.rng.range(0, 6);
+        d.put(inc, 4); d.put(c.rng.range(0, 15), 4);
+        nb += inc;
+        for (int i = 0; i < nb; ++i) d.put(c.rng.range(0, 255), 8);
+      }
+      d.put(ref, 1);
+      if (ref) { d.put(c.rng.range(0, 127), 7); d.put(0, 1); }
+      for (int i = 0; i < nb; ++i) { d.put(c.rng.range(0, 1), 1); d.put(c.rng.range(0, 127), 7); }
+      d.align();
+      const int cnt = (int)d.buf.size();
+      bw.put(6, 3);
+      if (cnt >= 15) { bw.put(15, 4); bw.put(cnt - 14, 8); } else bw.put(cnt, 4);
+      for (uint8_t b : d.buf) bw.put(b, 8);
+      if (c.rng.chance(0.5)) {
+        const int pad = c.rng.range(0, 20);                      // fill_element: count bytes, type 0 (FILL) or 1 (FILL_DATA)
+        bw.put(6, 3);
+        if (pad >= 15) { bw.put(15, 4); bw.put(pad - 14, 8); } else bw.put(pad, 4);
+        if (pad > 0) { bw.put(c.rng.range(0, 1), 4); bw.put(0, 4); for (int i = 1; i < pad; ++i) bw.put(0xA5, 8); }
       }
     }
     bw.put(7, 3);  // END

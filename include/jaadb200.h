@@ -73,6 +73,12 @@ extern "C" {
 
 #define JAADB_FLAG_PROFILE 1u   /* record per-kernel CUDA-event timings (jaadb_batch_timings) */
 #define JAADB_FLAG_DEBUG_TAPS 2u /* keep the dequantised spectra for jaadb_batch_tap (parity tests) */
+/* JAAD parses pulse_data and never applies it ("TODO: apply pulse data", A/syntax/ICStream.java:17,148-170); that is the
+ * default and the parity mode.  With JAADB_FLAG_PULSE_ISO the pulses are added to the quantised coefficients ahead of the
+ * inverse quantisation (ISO/IEC 14496-3 4.6.3.3); bands without spectral data (codebooks 0, 13, 14, 15, past max_sfb) are
+ * left alone, a magnitude past JAAD's IQ_TABLE (8190) fails the frame with JAADB_ST_ARRAY_BOUNDS.  Checked bit for bit against
+ * the oracle's pulseMode 1, which agrees with FFmpeg's decoder to > 90 dB. */
+#define JAADB_FLAG_PULSE_ISO 4u
 
 typedef struct jaadb_engine jaadb_engine;
 typedef struct jaadb_batch jaadb_batch;

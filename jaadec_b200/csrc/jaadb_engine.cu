@@ -860,7 +860,8 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
     const int threads = kK1Threads;
     const int blocks = (int)((n_frames + threads - 1) / threads);
     k1_parse_kernel<<<blocks, threads, k1_smem_bytes(e->lut_entries), e->stream>>>(B.blob, B.frames, n_frames, B.fside, B.iside, B.q,
-                                                                                   e->tables, e->d_layouts);
+                                                                                   e->tables, e->d_layouts,
+                                                                                   (e->opts.flags & JAADB_FLAG_PULSE_ISO) ? 1 : 0);
     ++*launches;
   }
   if (n_sbr_runs) {

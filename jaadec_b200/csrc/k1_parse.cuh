@@ -189,7 +189,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
                                                const TablesDev& T, int sf_index, bool common, IcsInfoRegs& in,
                                                IcsSide* side, int16_t* __restrict__ q, int ms_mask,
                                                uint8_t* __restrict__ cb_lane, const int16_t* __restrict__ s_swb, bool discard,
-                                               int dup_ch, uint32_t& dup_pend, uint32_t& pns_draws) {
+                                               int dup_ch, uint32_t& dup_pend, uint32_t& pns_draws, bool pulse_iso) {
   // discard: the element is not part of the stream's layout (see the element loop): it is parsed for its errors and its
   // length only, nothing is stored
   // codebook per (group, sfb) of this lane's ICS: shared memory, one byte column per thread
@@ -288,10 +288,12 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
 
   // ---- pulse_data (ICStream.java:76-83,148-170) and tns_data (TNS.java:35-61): parsed, never applied by JAAD;
   //      gain_control_data: SSR only.  Rare and short: the lanes diverge here and rejoin at the __syncwarp.
+  uint32_t pulse_pos = 0;   // JAADB_FLAG_PULSE_ISO: where pulse_data starts (read again after the spectral data)
   if (go) {
     if (br.read1()) {
       if (is_short) fail(status, go, JAADB_ST_PULSE_SHORT);
       else {
+        if (pulse_iso) pulse_pos = br.pos;
         const int count = (int)br.read(2) + 1;
         const int start = (int)br.read(6);
         const int swb_count = T.swb_long_count[sf_index];
@@ -450,6 +452,34 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
     }
     if (status) go = false;
   }
+  // ---- JAADB_FLAG_PULSE_ISO: the pulses JAAD parses and never applies ("TODO: apply pulse data", ICStream.java:17), added to
+  //      the quantised coefficients as ISO/IEC 14496-3 4.6.3.3 says: quant[k] += amp if quant[k] > 0, else -= amp.  Long
+  //      windows only, so q is in natural order here.  Only coefficients of bands with spectral data take a pulse (codebooks
+  //      1..11 below max_sfb); a magnitude past IQ_TABLE fails the frame like an escape value of that size.  Rare and short:
+  //      the lanes diverge and rejoin below.  (Elements outside the stream's layout store no coefficients: nothing to do.)
+  if (go && pulse_pos != 0u && !discard) {
+    const uint32_t resume = br.pos;
+    br.pos = pulse_pos;
+    const int count = (int)br.read(2) + 1;
+    int sfb = (int)br.read(6);
+    const int16_t* __restrict__ swb = s_swb + sf_index * 53;
+    int off = swb[sfb];
+    for (int i = 0; i < count && go; ++i) {
+      off += (int)br.read(5);
+      const int amp = (int)br.read(4);
+      while (sfb < max_sfb && swb[sfb + 1] <= off) ++sfb;
+      if (sfb < max_sfb) {
+        const int hcb = CB(sfb);
+        if (hcb >= 1 && hcb <= 11) {
+          int v = q[off];
+          v = v > 0 ? v + amp : v - amp;
+          if (v > 8190 || v < -8190) fail(status, go, JAADB_ST_ARRAY_BOUNDS);
+          else q[off] = (int16_t)v;
+        }
+      }
+    }
+    br.pos = resume;
+  }
   if (go && !discard) store_ics_header(side, in, 1, 1, ms_mask, common ? 1 : 0);
   __syncwarp();
 #undef CB
@@ -458,7 +488,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
 __global__ void __launch_bounds__(kK1Threads, 4)   // 64 registers: four CTAs per SM (the shared-memory limit)
 k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ frames, uint32_t n_frames,
                 FrameSide* __restrict__ fside, IcsSide* __restrict__ iside_all, int16_t* __restrict__ q_all, TablesDev T,
-                const LayoutDev* __restrict__ layouts) {
+                const LayoutDev* __restrict__ layouts, int pulse_iso) {
   extern __shared__ uint32_t s_lut[];
   // shared memory: Huffman LUTs | SWB offset tables (long [12][53], short [12][17]) | per-lane codebook columns
   int16_t* s_swb = reinterpret_cast<int16_t*>(s_lut + T.huff_lut_entries);
@@ -594,8 +624,37 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
             if (br.bits_left() < (uint32_t)(8 * count) || br.overrun()) { br.skip(8 * count); fail(status, active, JAADB_ST_EOS); }
             else {
               const uint32_t ext = br.peek() >> 28;
-              if (ext == 11) fail(status, active, JAADB_ST_UNSUPPORTED_ELEMENT);  // dynamic range info
-              else {
+              if (ext == 11) {
+                // dynamic_range_info (DRC.decode, syntax/DRC.java:31-83): JAAD parses it into an object nobody reads
+                // (SyntacticElements.java:216-224).  The parse can still end the frame: a read past the fill element's
+                // sub-stream is an EOSException, a second group of excluded-channel flags runs over `new boolean[7]`
+                // (DRC.java:27,72-82; the flag is read before the store is checked).  Rare and short: the lanes diverge.
+                const uint32_t sub_end = br.pos + 8u * (uint32_t)count;
+                br.skip(4);
+                int st = 0, bands = 1;
+                uint32_t v = 0;
+#define DRC_READ(n) do { if (!st) { if (sub_end - br.pos < (uint32_t)(n)) st = JAADB_ST_EOS; else v = br.read(n); } } while (0)
+                DRC_READ(1);
+                if (!st && v) DRC_READ(8);                                  // pce_tag_present: tag(4) + reserved(4)
+                DRC_READ(1);
+                if (!st && v) {                                             // excluded_chns_present
+                  DRC_READ(7);
+                  DRC_READ(1);
+                  if (!st && v) { DRC_READ(1); if (!st) st = JAADB_ST_ARRAY_BOUNDS; }
+                }
+                DRC_READ(1);
+                if (!st && v) {                                             // drc_bands_present: increment(4) + interpolation(4)
+                  DRC_READ(8);
+                  if (!st) bands += (int)(v >> 4);
+                  for (int i = 0; i < bands; ++i) DRC_READ(8);
+                }
+                DRC_READ(1);
+                if (!st && v) DRC_READ(8);                                  // prog_ref_level(7) + reserved(1)
+                for (int i = 0; i < bands; ++i) DRC_READ(8);                // dyn_rng_sgn(1) + dyn_rng_ctl(7)
+#undef DRC_READ
+                br.pos = sub_end;
+                if (st) fail(status, active, st);
+              } else {
                 if ((ext == 13 || ext == 14) && el > 0 && el <= 2 && !layout_bad) {
                   fs.sbr_bit_off[el - 1] = br.pos;   // relative to the aligned word base of the frame
                   fs.sbr_bits[el - 1] = 8u * (uint32_t)count;
@@ -612,7 +671,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
     __syncwarp();
     parse_ics_warp(go, br, status, s_lut, T, sf_index, common, in, iside + ch, qbase + ch * 1024, ms_mask,
                    s_cb + threadIdx.x, s_swb, layout_bad, (layout_bad && dup_slot >= 0) ? dup_slot + (ch - ch0) : -1, dup_pend,
-                   pns_draws);
+                   pns_draws, pulse_iso != 0);
     if (go) {
       if (status) active = false;
       else if (is_cpe_left) pend_r = true;

@@ -9,7 +9,7 @@ from . import _lib
 from ._lib import FrameDesc, FrameResult, Options, StreamInfo, Timings
 
 PCM_S16LE, PCM_S16BE, PCM_F32_PLANAR = 0, 1, 2
-FLAG_PROFILE, FLAG_DEBUG_TAPS = 1, 2
+FLAG_PROFILE, FLAG_DEBUG_TAPS, FLAG_PULSE_ISO = 1, 2, 4
 TNS_JAAD, TNS_ISO = 0, 1
 CONTAINER_ADTS, CONTAINER_MP4 = 0, 1
 

@@ -36,6 +36,7 @@ def lib():
         _lib.jo_open_asc.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         _lib.jo_close.argtypes = [C.c_void_p]
         _lib.jo_set_tns_mode.argtypes = [C.c_void_p, C.c_int]
+        _lib.jo_set_pulse_mode.argtypes = [C.c_void_p, C.c_int]
         _lib.jo_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.jo_tap_ics.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.jo_tap_msused.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -79,6 +80,11 @@ class Decoder:
     def set_tns_mode(self, mode: int) -> "Decoder":
         """0 = JAAD (TNS data parsed and ignored, tools/TNS.java:63-68), 1 = the ISO 14496-3 4.6.9 all-pole filter."""
         lib().jo_set_tns_mode(self._h, int(mode))
+        return self
+
+    def set_pulse_mode(self, mode: int) -> "Decoder":
+        """0 = JAAD (pulse_data parsed and ignored, syntax/ICStream.java:17), 1 = the pulses of ISO 14496-3 4.6.3.3 applied."""
+        lib().jo_set_pulse_mode(self._h, int(mode))
         return self
 
     def close(self):

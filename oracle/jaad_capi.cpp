@@ -69,6 +69,8 @@ void jo_close(void* hv) { delete static_cast<Handle*>(hv); }
 
 // 0 = JAAD (TNS parsed, never applied), 1 = ISO/IEC 14496-3 4.6.9 filter (DecoderConfig::tnsMode)
 void jo_set_tns_mode(void* hv, int mode) { static_cast<Handle*>(hv)->dec->config.tnsMode = mode; }
+// 0 = JAAD (pulse_data parsed, never applied), 1 = ISO/IEC 14496-3 4.6.3.3 (DecoderConfig::pulseMode)
+void jo_set_pulse_mode(void* hv, int mode) { static_cast<Handle*>(hv)->dec->config.pulseMode = mode; }
 
 // meta[0..3] = status, channels, sampleLength, sampleRate.
 // pcm_f32: planar [channels][sampleLength] (may be NULL); pcm_s16: interleaved (may be NULL).

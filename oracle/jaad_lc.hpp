@@ -113,8 +113,11 @@ struct DecoderConfig {
   // on every decoder that ran before; the oracle (and the engine) give each Decoder its own generator with JAAD's seed,
   // which is exactly "this stream decoded alone in a fresh JVM".  (2) tnsMode 0 = JAAD (TNS.process is a stub,
   // tools/TNS.java:63-68), 1 = the ISO/IEC 14496-3 4.6.9 all-pole filter (TNS::process below).
+  // (3) pulseMode 0 = JAAD (pulse_data parsed, never applied: "TODO: apply pulse data", ICStream.java:17), 1 = the pulses of
+  // ISO/IEC 14496-3 4.6.3.3 are added to the quantised coefficients before the inverse quantisation.
   mutable int32_t pnsState = 0x1F2E3D4C;
   int tnsMode = 0;
+  int pulseMode = 0;
 
   int getFrameLength() const { return frameLengthFlag ? 960 : 1024; }
   bool isUpSampled() const { return hasOutputFrequency && !outputFrequency.same(sampleFrequency); }
@@ -617,6 +620,8 @@ struct ICStream {
   // taps for the parity tests (not part of JAAD): raw integers behind the floats
   int16_t q[1024];        // quantised coefficients in iqData layout
   int16_t sfIndex[MAX_SECTIONS];  // SCALEFACTOR_TABLE index (-1: 0.0f); noise bands store index|0x4000
+  // pulse_data as parsed (JAAD keeps pulseOffset[] / pulseAmp[] the same way, ICStream.java:39-41, and never reads them again)
+  int pulseCount = 0, pulseOffset[4] = {0, 0, 0, 0}, pulseAmp[4] = {0, 0, 0, 0};
   bool infoDecoded = false;
 
   explicit ICStream(const DecoderConfig& c) : info(c) {
@@ -678,17 +683,42 @@ struct ICStream {
     }
   }
 
-  void decodePulseData(BitStream& in) {  // :148-170  (parsed, never applied)
-    int pulseCount = in.readBits(2) + 1;
+  void decodePulseData(BitStream& in) {  // :148-170  (parsed; applied in pulseMode 1 only)
+    pulseCount = in.readBits(2) + 1;
     int pulseStartSWB = in.readBits(6);
     if (pulseStartSWB >= info.swbCount) throw AACException(ST_PULSE_RANGE, "pulse SWB out of range");
     int off = info.swbOffsets[pulseStartSWB];
     off += in.readBits(5);
-    in.readBits(4);
+    pulseOffset[0] = off;
+    pulseAmp[0] = in.readBits(4);
     for (int i = 1; i < pulseCount; i++) {
       off = in.readBits(5) + off;
       if (off > 1023) throw AACException(ST_PULSE_RANGE, "pulse offset out of range");
-      in.readBits(4);
+      pulseOffset[i] = off;
+      pulseAmp[i] = in.readBits(4);
+    }
+  }
+
+  // Not in JAAD (pulseMode 1).  ISO/IEC 14496-3 4.6.3.3: "if (quant[k] > 0) quant[k] += pulse_amp else quant[k] -= pulse_amp",
+  // ahead of the inverse quantisation; here after JAAD's fused decode + dequantisation, redoing that one coefficient with the
+  // same two operations (IQ_TABLE look-up, one multiplication by the band's scalefactor).  Only coefficients of bands that
+  // carry spectral data take a pulse (codebooks 1..11 below max_sfb): the others have no quantised value and no scalefactor
+  // of their own (FFmpeg's decoder draws the same line).  A magnitude past IQ_TABLE's 8191 entries fails like any other.
+  void applyPulses() {
+    const float* IQ = JT(IQ_TABLE);
+    for (int i = 0; i < pulseCount; i++) {
+      const int pos = pulseOffset[i];
+      int sfb = 0;
+      while (sfb < info.maxSFB && info.swbOffsets[sfb + 1] <= pos) sfb++;
+      if (sfb >= info.maxSFB) continue;
+      const int hcb = sfbCB[sfb];
+      if (hcb < 1 || hcb > 11) continue;
+      const int v = q[pos] > 0 ? q[pos] + pulseAmp[i] : q[pos] - pulseAmp[i];
+      const int a = v > 0 ? v : -v;
+      if (a > 8190) throw AACException(ST_ARRAY_BOUNDS, "IQ table index out of range");
+      iqData[pos] = (v > 0) ? IQ[v] : -IQ[-v];
+      iqData[pos] *= scaleFactors[sfb];
+      q[pos] = (int16_t)v;
     }
   }
 
@@ -792,6 +822,7 @@ struct ICStream {
       }
       groupOff += groupLen << 7;
     }
+    if (conf.pulseMode == 1 && pulseDataPresent) applyPulses();
   }
   static void decodeSpectralData_(BitStream& in, int hcb, int* buf) { ::jaad::decodeSpectralData(in, hcb, buf, 0); }
 
@@ -1030,6 +1061,34 @@ struct SyntacticElements {
     for (int i = 0; i < count; i++) in.readBits(8);
   }
 
+  // DRC.decode (syntax/DRC.java:31-83), reached from decodeFIL for extension type 11 (EXT_DYNAMIC_RANGE).  JAAD parses
+  // dynamic_range_info into a DRC object nobody reads; what matters here is where the parse can end a frame: a read past the
+  // fill element's sub-stream (EOSException), and `excludeMask = new boolean[7]` (DRC.java:27) taking a second group of seven
+  // excluded-channel flags (DRC.java:72-82: ArrayIndexOutOfBoundsException; the flag is read before the store is checked,
+  // JLS 15.26.1, so an over-read there is still the EOS).
+  static void decodeDynamicRangeInfo(BitStream& in) {
+    int bandCount = 1;
+    if (in.readBool()) { in.readBits(4); in.readBits(4); }
+    if (in.readBool()) {
+      int exclChs = 0;
+      do {
+        for (int i = 0; i < 7; i++) {
+          in.readBool();
+          if (exclChs >= 7) throw AACException(ST_ARRAY_BOUNDS, "excludeMask index out of bounds");
+          exclChs++;
+        }
+      } while (exclChs < 57 && in.readBool());
+    }
+    if (in.readBool()) {
+      int bandsIncrement = in.readBits(4);
+      in.readBits(4);
+      bandCount += bandsIncrement;
+      for (int i = 0; i < bandCount; i++) in.readBits(8);
+    }
+    if (in.readBool()) { in.readBits(7); in.readBits(1); }
+    for (int i = 0; i < bandCount; i++) { in.readBool(); in.readBits(7); }
+  }
+
   void decodeFIL(BitStream& in0) {  // :169-203
     int count = in0.readBits(4);
     if (count == 15) count += in0.readBits(8) - 1;
@@ -1037,8 +1096,7 @@ struct SyntacticElements {
     BitStream in = in0.readSubStream(8 * count);
     int type = in.readBits(4);
     switch (type) {
-      case 11:
-        throw AACException(ST_UNSUPPORTED_ELEMENT, "dynamic range info is outside the engine's scope");
+      case 11: decodeDynamicRangeInfo(in); break;   // :219-224: "decoded but unused"
       case 13: case 14: {
         ChannelElement* prev = audioElements.empty() ? nullptr : audioElements.back();
         if (prev) prev->decodeSBR(in, type == 14);

@@ -283,6 +283,40 @@ def test_pns_matches_a_numpy_restatement_of_the_java_loop():
     assert n_bands > 100
 
 
+def test_pulse_data_iso_mode_reconstructs_the_generator_truth():
+    """pulse_data (ICStream.java:148-170 parses it; "TODO: apply pulse data", :17).  In the default mode the oracle does what
+    JAAD does: the coefficients come out as transmitted, i.e. without the pulses.  In pulseMode 1 (ISO/IEC 14496-3 4.6.3.3) the
+    quantised coefficients equal the generator's ground truth -- the values an encoder had before it took the pulses off --
+    and the dequantised value of a pulsed coefficient is IQ_TABLE[|q|] * scalefactor like any other."""
+    cfg = gen.config(2, n_frames=24, p_transient=0.2, p_pulse=0.9, pulse_wild=True, ms_mode=0, p_is=0.0)
+    st = gen.generate(cfg, gen.seed_for(2, 43), with_truth=True)
+    plain = gen.generate(gen.config(2, n_frames=24, p_transient=0.2, ms_mode=0, p_is=0.0), gen.seed_for(2, 43))
+    assert not np.array_equal(st.data, plain.data)                      # pulse_data is in the stream
+    d_jaad = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)
+    d_iso = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg).set_pulse_mode(1)
+    n_pulsed = 0
+    for f in range(cfg.n_frames):
+        fr = st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]]
+        ra, rb = d_jaad.decode_frame(fr), d_iso.decode_frame(fr)
+        assert ra["status"] == 0 and rb["status"] == 0
+        ta, tb = oracle_taps(d_jaad), oracle_taps(d_iso)
+        for c in range(2):
+            want = st.truth["q"][f, c]
+            assert np.array_equal(tb[c]["q"], want), (f, c)
+            diff = np.nonzero(ta[c]["q"] != want)[0]
+            n_pulsed += len(diff)
+            assert len(diff) <= 4 and (ta[c]["info"][1] != 2 or len(diff) == 0)
+            # the transmitted coefficient is the true one with up to 15 taken off its magnitude, sign kept (or zero)
+            for k in diff:
+                a, b = int(ta[c]["q"][k]), int(want[k])
+                assert abs(b) - abs(a) in range(1, 16) and (a == 0 or (a > 0) == (b > 0)), (f, c, k, a, b)
+            # outside the pulsed coefficients the two modes are the same decoder
+            same = np.ones(1024, bool)
+            same[diff] = False
+            assert np.array_equal(ta[c]["spec"][same].view(np.uint32), tb[c]["spec"][same].view(np.uint32))
+    assert n_pulsed > 20
+
+
 def _tns_float64(spec, tns, ws, max_sfb, sf_index=3):
     """ISO/IEC 14496-3 4.6.9.3 in float64, from the signed coefficient indices (generator truth), formula tables."""
     out = spec.astype(np.float64).copy()

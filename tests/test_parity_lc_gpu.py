@@ -411,3 +411,66 @@ def test_device_resident_blob_and_pcm(cfg_no, n_frames):
             assert np.array_equal(got_d[i * per:(i + 1) * per].view(np.int16).reshape(info.sample_length, info.channels), r["s16"]), (s, f)
     for e in engs:
         e.close()
+
+
+PULSE_CASES = [
+    ("stereo_48k", gen.config(2, n_frames=30, p_transient=0.3, p_pulse=0.8, pulse_wild=True), 4),
+    ("stereo_48k_pns_tns", gen.config(2, n_frames=16, p_transient=0.2, p_pulse=0.9, pulse_wild=True, p_pns=0.2, p_tns=0.5, tns_mild=True), 2),
+    ("c1_44k_long_only", gen.config(1, n_frames=20, p_pulse=1.0), 2),
+    ("mono_24k", gen.GenConfig(sf_index=6, chan_cfg=1, n_frames=20, target_bytes=171, p_transient=0.3, p_pulse=0.8, pulse_wild=True), 2),
+    ("c5_51_48k", gen.config(5, n_frames=10, adts=True, p_transient=0.3, p_pulse=0.8, pulse_wild=True), 2),
+    ("sf_8k", gen.GenConfig(sf_index=11, chan_cfg=2, n_frames=12, target_bytes=300, p_transient=0.3, p_pulse=0.8, pulse_wild=True), 2),
+]
+
+
+@pytest.mark.parametrize("label,cfg,n_streams", PULSE_CASES, ids=[c[0] for c in PULSE_CASES])
+@pytest.mark.parametrize("iso", [True, False])
+def test_pulse_data_jaad_and_iso_mode(label, cfg, n_streams, iso):
+    """pulse_data (ICStream.java:148-170).  JAAD parses it and never applies it (ICStream.java:17): the default mode does the
+    same and must match the oracle's default.  JAADB_FLAG_PULSE_ISO adds the pulses to the quantised coefficients (ISO/IEC
+    14496-3 4.6.3.3), like the oracle's pulseMode 1 (pinned against FFmpeg in tests/test_oracle_vs_libavcodec_cpu.py): the
+    quantised coefficients then equal the generator's ground truth, spectrum and PCM are bit-identical to the oracle's.
+    The generator also drops pulses on bands without spectral data and past max_sfb; both sides leave those alone."""
+    from jaadec_b200 import FLAG_PULSE_ISO, TNS_ISO
+    wl = Workload(cfg, n_streams, base_seed=gen.seed_for(2, 1100))
+    decs = [d.set_pulse_mode(1 if iso else 0).set_tns_mode(1 if iso else 0) for d in wl.oracle_decoders()]
+    eng = Engine(max_streams=16, pcm_format=PCM_F32_PLANAR, flags=FLAG_DEBUG_TAPS | (FLAG_PULSE_ISO if iso else 0),
+                 tns_mode=TNS_ISO if iso else 0)
+    ids = [eng.open_adts(*wl.hdr) for _ in range(n_streams)]
+    frames, index = wl.frame_table(ids)
+    b = eng.batch(frames, wl.blob.nbytes)
+    b.upload(wl.blob)
+    b.decode()
+    pcm, res = b.download()
+    info0 = eng.stream_info(ids[0])
+    ch, ln = info0.channels, info0.sample_length
+    per = ch * ln * 4
+    n_pulsed = 0
+    for i, (s, f) in enumerate(index):
+        r = decs[s].decode_frame(wl.frame_bytes(s, f))
+        assert res["status"][i] == 0 and r["status"] == 0
+        taps, el = [], 0
+        while True:
+            t = decs[s].tap_ics(el, 0)
+            if t is None:
+                break
+            taps.append(t)
+            t2 = decs[s].tap_ics(el, 1)
+            if t2 is not None:
+                taps.append(t2)
+            el += 1
+        truth = wl.streams[s].truth
+        assert len(taps) == truth["q"].shape[1]
+        for c, t in enumerate(taps):
+            g = b.tap(i, c)
+            assert np.array_equal(g["q"], t["q"]), (label, s, f, c, "q vs oracle")
+            if iso:
+                assert np.array_equal(g["q"], truth["q"][f, c]), (label, s, f, c, "q vs generator")
+            else:
+                n_pulsed += int((g["q"] != truth["q"][f, c]).sum())
+            assert same_float_bits(g["spec"], t["spec"]), (label, s, f, c, "spectrum")
+        got = pcm[i * per:(i + 1) * per].view(np.float32).reshape(ch, ln)
+        assert same_float_bits(got, r["f32"]), (label, s, f, "float pcm")
+    assert iso or n_pulsed > 10     # the streams do carry pulses: without them the transmitted coefficients are not the truth
+    b.close()
+    eng.close()
