@@ -620,6 +620,7 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
   c.psIso = cfg->ps_iso != 0;
   c.pPulse = cfg->p_pulse;
   c.pulseWild = cfg->pulse_wild != 0;
+  Rng drcRng(seed ^ 0xD2C0D2C0D2C0D2C0ull);   // its own generator: the audio elements are the ones of the stream without p_drc
   const int nIcs = jg_ics_per_frame(cfg->chan_cfg);
   const int nEl = jg_elements_per_frame(cfg->chan_cfg);
   // element layout
@@ -777,35 +778,35 @@ int64_t jg_generate(const jg_config* cfg, uint64_t seed, uint8_t* out, int64_t c
     }
     // fill elements real encoders add after the audio elements: dynamic_range_info (extension type 11; JAAD parses it into
     // an object nobody reads, syntax/DRC.java) and plain padding (types 0 / 1)
-    if (cfg->p_drc > 0 && c.rng.chance(cfg->p_drc)) {
+    if (cfg->p_drc > 0 && drcRng.chance(cfg->p_drc)) {
       BitWriter d;
       d.put(11, 4);
-      const bool pce = c.rng.chance(0.3), excl = c.rng.chance(0.3), bands = c.rng.chance(0.4), ref = c.rng.chance(0.5);
+      const bool pce = drcRng.chance(0.3), excl = drcRng.chance(0.3), bands = drcRng.chance(0.4), ref = drcRng.chance(0.5);
       int nb = 1;
       d.put(pce, 1);
-      if (pce) { d.put(c.rng.range(0, 15), 4); d.put(0, 4); }
+      if (pce) { d.put(drcRng.range(0, 15), 4); d.put(0, 4); }
       d.put(excl, 1);
-      if (excl) { for (int i = 0; i < 7; ++i) d.put(c.rng.range(0, 1), 1); d.put(0, 1); }   // (JAAD cannot take a second group)
+      if (excl) { for (int i = 0; i < 7; ++i) d.put(drcRng.range(0, 1), 1); d.put(0, 1); }   // (JAAD cannot take a second group)
       d.put(bands, 1);
       if (bands) {
-        const int inc = c.rng.range(0, 6);
-        d.put(inc, 4); d.put(c.rng.range(0, 15), 4);
+        const int inc = drcRng.range(0, 6);
+        d.put(inc, 4); d.put(drcRng.range(0, 15), 4);
         nb += inc;
-        for (int i = 0; i < nb; ++i) d.put(c.rng.range(0, 255), 8);
+        for (int i = 0; i < nb; ++i) d.put(drcRng.range(0, 255), 8);
       }
       d.put(ref, 1);
-      if (ref) { d.put(c.rng.range(0, 127), 7); d.put(0, 1); }
-      for (int i = 0; i < nb; ++i) { d.put(c.rng.range(0, 1), 1); d.put(c.rng.range(0, 127), 7); }
+      if (ref) { d.put(drcRng.range(0, 127), 7); d.put(0, 1); }
+      for (int i = 0; i < nb; ++i) { d.put(drcRng.range(0, 1), 1); d.put(drcRng.range(0, 127), 7); }
       d.align();
       const int cnt = (int)d.buf.size();
       bw.put(6, 3);
       if (cnt >= 15) { bw.put(15, 4); bw.put(cnt - 14, 8); } else bw.put(cnt, 4);
       for (uint8_t b : d.buf) bw.put(b, 8);
-      if (c.rng.chance(0.5)) {
-        const int pad = c.rng.range(0, 20);                      // fill_element: count bytes, type 0 (FILL) or 1 (FILL_DATA)
+      if (drcRng.chance(0.5)) {
+        const int pad = drcRng.range(0, 20);                      // fill_element: count bytes, type 0 (FILL) or 1 (FILL_DATA)
         bw.put(6, 3);
         if (pad >= 15) { bw.put(15, 4); bw.put(pad - 14, 8); } else bw.put(pad, 4);
-        if (pad > 0) { bw.put(c.rng.range(0, 1), 4); bw.put(0, 4); for (int i = 1; i < pad; ++i) bw.put(0xA5, 8); }
+        if (pad > 0) { bw.put(drcRng.range(0, 1), 4); bw.put(0, 4); for (int i = 1; i < pad; ++i) bw.put(0xA5, 8); }
       }
     }
     bw.put(7, 3);  // END

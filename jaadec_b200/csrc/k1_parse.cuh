@@ -183,6 +183,76 @@ __device__ __forceinline__ void note_dup_shape(uint32_t& pend, int slot, const I
   if (n < 4) pend |= ((uint32_t)(slot & 7) | ((uint32_t)(in.shape & 1) << 3) | 16u) << (5 * n);
 }
 
+// Out-of-line readers for the two rare side paths below (dynamic_range_info, ISO pulses): n <= 25 bits at an absolute bit
+// position of the frame's word array, straight from global memory -- nothing of the hot reader's register state is touched,
+// and the code stays out of the parse loops' instruction stream.
+__device__ __noinline__ uint32_t slow_bits(const uint32_t* __restrict__ words, uint32_t last_word, uint32_t pos, int n) {
+  const uint32_t wi = pos >> 5;
+  const uint32_t a = wi <= last_word ? __byte_perm(__ldg(words + wi), 0, 0x0123) : 0u;
+  const uint32_t b = wi + 1 <= last_word ? __byte_perm(__ldg(words + wi + 1), 0, 0x0123) : 0u;
+  return __funnelshift_l(b, a, pos & 31u) >> (32 - n);
+}
+
+// dynamic_range_info (DRC.decode, syntax/DRC.java:31-83) inside a fill element whose sub-stream is [pos - 4, sub_end): JAAD
+// parses it into an object nobody reads (SyntacticElements.java:216-224).  The parse can still end the frame: a read past
+// the sub-stream is an EOSException, a second group of excluded-channel flags runs over `new boolean[7]` (DRC.java:27,72-82;
+// the flag is read before the store is checked, so an over-read there is still the EOS).  Returns a status.
+__device__ __noinline__ int drc_parse(const uint32_t* __restrict__ words, uint32_t last_word, uint32_t pos, uint32_t sub_end) {
+  int st = 0, bands = 1;
+  uint32_t v = 0;
+#define DRC_READ(n) do { if (!st) { if (sub_end - pos < (uint32_t)(n)) st = JAADB_ST_EOS; else { v = slow_bits(words, last_word, pos, n); pos += (n); } } } while (0)
+  DRC_READ(1);
+  if (!st && v) DRC_READ(8);                                  // pce_tag_present: tag(4) + reserved(4)
+  DRC_READ(1);
+  if (!st && v) {                                             // excluded_chns_present
+    DRC_READ(7);
+    DRC_READ(1);
+    if (!st && v) { DRC_READ(1); if (!st) st = JAADB_ST_ARRAY_BOUNDS; }
+  }
+  DRC_READ(1);
+  if (!st && v) {                                             // drc_bands_present: increment(4) + interpolation(4)
+    DRC_READ(8);
+    if (!st) bands += (int)(v >> 4);
+    for (int i = 0; i < bands; ++i) DRC_READ(8);
+  }
+  DRC_READ(1);
+  if (!st && v) DRC_READ(8);                                  // prog_ref_level(7) + reserved(1)
+  for (int i = 0; i < bands; ++i) DRC_READ(8);                // dyn_rng_sgn(1) + dyn_rng_ctl(7)
+#undef DRC_READ
+  return st;
+}
+
+// JAADB_FLAG_PULSE_ISO: the pulses JAAD parses and never applies ("TODO: apply pulse data", ICStream.java:17), added to the
+// quantised coefficients as ISO/IEC 14496-3 4.6.3.3 says: quant[k] += amp if quant[k] > 0, else -= amp.  Long windows only,
+// so q is in natural order.  Only coefficients of bands with spectral data take a pulse (codebooks 1..11 below max_sfb); a
+// magnitude past IQ_TABLE fails the frame like an escape value of that size.  pos: where pulse_data starts (validated by the
+// first parse).  Returns a status.
+__device__ __noinline__ int pulse_apply(const uint32_t* __restrict__ words, uint32_t last_word, uint32_t pos,
+                                        const int16_t* __restrict__ swb, int max_sfb, const uint8_t* __restrict__ cb_lane,
+                                        int cb_stride, int16_t* __restrict__ q) {
+  const int count = (int)slow_bits(words, last_word, pos, 2) + 1;
+  int sfb = (int)slow_bits(words, last_word, pos + 2, 6);
+  pos += 8;
+  int off = swb[sfb];
+  for (int i = 0; i < count; ++i) {
+    const uint32_t v9 = slow_bits(words, last_word, pos, 9);
+    pos += 9;
+    off += (int)(v9 >> 4);
+    const int amp = (int)(v9 & 15u);
+    while (sfb < max_sfb && swb[sfb + 1] <= off) ++sfb;
+    if (sfb < max_sfb) {
+      const int hcb = cb_lane[sfb * cb_stride];
+      if (hcb >= 1 && hcb <= 11) {
+        int v = q[off];
+        v = v > 0 ? v + amp : v - amp;
+        if (v > 8190 || v < -8190) return JAADB_ST_ARRAY_BOUNDS;
+        q[off] = (int16_t)v;
+      }
+    }
+  }
+  return 0;
+}
+
 // individual_channel_stream (ICStream.decode, ICStream.java:60-111) for the lanes with go == true.
 // `in` holds the shared ics_info when common_window is set.  Returns with status updated.
 __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& status, const uint32_t* __restrict__ lut,
@@ -288,12 +358,16 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
 
   // ---- pulse_data (ICStream.java:76-83,148-170) and tns_data (TNS.java:35-61): parsed, never applied by JAAD;
   //      gain_control_data: SSR only.  Rare and short: the lanes diverge here and rejoin at the __syncwarp.
-  uint32_t pulse_pos = 0;   // JAADB_FLAG_PULSE_ISO: where pulse_data starts (read again after the spectral data)
+  // JAADB_FLAG_PULSE_ISO: where pulse_data starts (it is read again after the spectral data), kept in the four spare rows of
+  // the lane's codebook column instead of a register that would live across the spectral loop
+  if (pulse_iso) { CB(124) = 0; CB(125) = 0; CB(126) = 0; CB(127) = 0; }
   if (go) {
     if (br.read1()) {
       if (is_short) fail(status, go, JAADB_ST_PULSE_SHORT);
       else {
-        if (pulse_iso) pulse_pos = br.pos;
+        if (pulse_iso) {
+          CB(124) = (uint8_t)br.pos; CB(125) = (uint8_t)(br.pos >> 8); CB(126) = (uint8_t)(br.pos >> 16); CB(127) = (uint8_t)(br.pos >> 24);
+        }
         const int count = (int)br.read(2) + 1;
         const int start = (int)br.read(6);
         const int swb_count = T.swb_long_count[sf_index];
@@ -452,33 +526,14 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
     }
     if (status) go = false;
   }
-  // ---- JAADB_FLAG_PULSE_ISO: the pulses JAAD parses and never applies ("TODO: apply pulse data", ICStream.java:17), added to
-  //      the quantised coefficients as ISO/IEC 14496-3 4.6.3.3 says: quant[k] += amp if quant[k] > 0, else -= amp.  Long
-  //      windows only, so q is in natural order here.  Only coefficients of bands with spectral data take a pulse (codebooks
-  //      1..11 below max_sfb); a magnitude past IQ_TABLE fails the frame like an escape value of that size.  Rare and short:
-  //      the lanes diverge and rejoin below.  (Elements outside the stream's layout store no coefficients: nothing to do.)
-  if (go && pulse_pos != 0u && !discard) {
-    const uint32_t resume = br.pos;
-    br.pos = pulse_pos;
-    const int count = (int)br.read(2) + 1;
-    int sfb = (int)br.read(6);
-    const int16_t* __restrict__ swb = s_swb + sf_index * 53;
-    int off = swb[sfb];
-    for (int i = 0; i < count && go; ++i) {
-      off += (int)br.read(5);
-      const int amp = (int)br.read(4);
-      while (sfb < max_sfb && swb[sfb + 1] <= off) ++sfb;
-      if (sfb < max_sfb) {
-        const int hcb = CB(sfb);
-        if (hcb >= 1 && hcb <= 11) {
-          int v = q[off];
-          v = v > 0 ? v + amp : v - amp;
-          if (v > 8190 || v < -8190) fail(status, go, JAADB_ST_ARRAY_BOUNDS);
-          else q[off] = (int16_t)v;
-        }
-      }
+  // ---- JAADB_FLAG_PULSE_ISO (pulse_apply above).  Rare and short: the lanes diverge and rejoin below.  (Elements outside
+  //      the stream's layout store no coefficients: nothing to do.)
+  if (pulse_iso && go && !discard) {
+    const uint32_t pulse_pos = (uint32_t)CB(124) | ((uint32_t)CB(125) << 8) | ((uint32_t)CB(126) << 16) | ((uint32_t)CB(127) << 24);
+    if (pulse_pos != 0u) {
+      const int st = pulse_apply(br.words, br.last_word, pulse_pos, s_swb + sf_index * 53, max_sfb, cb_lane, kK1Threads, q);
+      if (st) fail(status, go, st);
     }
-    br.pos = resume;
   }
   if (go && !discard) store_ics_header(side, in, 1, 1, ms_mask, common ? 1 : 0);
   __syncwarp();
@@ -625,33 +680,9 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
             else {
               const uint32_t ext = br.peek() >> 28;
               if (ext == 11) {
-                // dynamic_range_info (DRC.decode, syntax/DRC.java:31-83): JAAD parses it into an object nobody reads
-                // (SyntacticElements.java:216-224).  The parse can still end the frame: a read past the fill element's
-                // sub-stream is an EOSException, a second group of excluded-channel flags runs over `new boolean[7]`
-                // (DRC.java:27,72-82; the flag is read before the store is checked).  Rare and short: the lanes diverge.
+                // dynamic range info: parsed and dropped, like JAAD does (drc_parse above)
                 const uint32_t sub_end = br.pos + 8u * (uint32_t)count;
-                br.skip(4);
-                int st = 0, bands = 1;
-                uint32_t v = 0;
-#define DRC_READ(n) do { if (!st) { if (sub_end - br.pos < (uint32_t)(n)) st = JAADB_ST_EOS; else v = br.read(n); } } while (0)
-                DRC_READ(1);
-                if (!st && v) DRC_READ(8);                                  // pce_tag_present: tag(4) + reserved(4)
-                DRC_READ(1);
-                if (!st && v) {                                             // excluded_chns_present
-                  DRC_READ(7);
-                  DRC_READ(1);
-                  if (!st && v) { DRC_READ(1); if (!st) st = JAADB_ST_ARRAY_BOUNDS; }
-                }
-                DRC_READ(1);
-                if (!st && v) {                                             // drc_bands_present: increment(4) + interpolation(4)
-                  DRC_READ(8);
-                  if (!st) bands += (int)(v >> 4);
-                  for (int i = 0; i < bands; ++i) DRC_READ(8);
-                }
-                DRC_READ(1);
-                if (!st && v) DRC_READ(8);                                  // prog_ref_level(7) + reserved(1)
-                for (int i = 0; i < bands; ++i) DRC_READ(8);                // dyn_rng_sgn(1) + dyn_rng_ctl(7)
-#undef DRC_READ
+                const int st = drc_parse(br.words, br.last_word, br.pos + 4u, sub_end);
                 br.pos = sub_end;
                 if (st) fail(status, active, st);
               } else {

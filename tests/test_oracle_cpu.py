@@ -317,6 +317,81 @@ def test_pulse_data_iso_mode_reconstructs_the_generator_truth():
     assert n_pulsed > 20
 
 
+def _fil(ext_payload_bits: str) -> str:
+    """A fill element (id 6) around an extension payload given as a bit string (padded to whole bytes)."""
+    bits = ext_payload_bits + "0" * (-len(ext_payload_bits) % 8)
+    cnt = len(bits) // 8
+    assert 0 < cnt < 15
+    return "110" + format(cnt, "04b") + bits
+
+
+def _splice_before_end(frame: np.ndarray, element_bits: str) -> np.ndarray:
+    """Insert syntactic elements in front of a frame's END element.  The generator's frames end with the END id (111) and
+    byte-alignment zeros, so the last '111' followed only by zeros is the END."""
+    bits = "".join(format(int(b), "08b") for b in frame)
+    body = bits.rstrip("0")
+    assert body.endswith("111")
+    out = body[:-3] + element_bits + "111"
+    out += "0" * (-len(out) % 8)
+    return np.frombuffer(int(out, 2).to_bytes(len(out) // 8, "big"), np.uint8).copy()
+
+
+DRC_CASES = [
+    # (label, dynamic_range_info bits after the 4-bit extension type 1011, expected status)
+    ("minimal", "0" "0" "0" "0" + "1" "0101010", 0),
+    ("pce_tag_excluded_bands_ref", "1" "0011" "0000" + "1" "1010101" "0" + "1" "0010" "0000" "00010000" "00100000" "01000000"
+     + "1" "1000000" "0" + "0" "0000001" "1" "0000010" "0" "0000011", 0),
+    ("second_excluded_group", "0" + "1" "0000000" "1" "0000000" "0" + "0" "0" + "0" "0000000", 13),
+]
+
+
+@pytest.mark.parametrize("label,drc_bits,want", DRC_CASES, ids=[c[0] for c in DRC_CASES])
+def test_dynamic_range_info_is_parsed_and_dropped(label, drc_bits, want):
+    """A fill element with extension type 11 (SyntacticElements.java:181-183 -> DRC.decode, syntax/DRC.java:31-83; "decoded but
+    unused", SyntacticElements.java:216).  The frame decodes exactly as it does without the element.  What the parse can
+    still do is end the frame: JAAD's `excludeMask = new boolean[7]` cannot take a second group of excluded-channel flags
+    (ArrayIndexOutOfBoundsException, status 13), and a payload that stops short is an EOSException (no output, status 1)."""
+    cfg = gen.config(2, n_frames=3, p_transient=0.0)
+    st = gen.generate(cfg, gen.seed_for(2, 77))
+    a = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)
+    b = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg)
+    for f in range(cfg.n_frames):
+        fr = st.data[st.offsets[f]: st.offsets[f] + st.sizes[f]]
+        ra = a.decode_frame(fr)
+        rb = b.decode_frame(_splice_before_end(fr, _fil("1011" + drc_bits)))
+        assert ra["status"] == 0 and rb["status"] == want, (f, rb["status"])
+        if want == 0:
+            assert np.array_equal(ra["f32"].view(np.uint32), rb["f32"].view(np.uint32))
+
+
+def test_truncated_dynamic_range_info_is_an_end_of_stream():
+    cfg = gen.config(2, n_frames=1, p_transient=0.0)
+    st = gen.generate(cfg, gen.seed_for(2, 78))
+    fr = st.data[st.offsets[0]: st.offsets[0] + st.sizes[0]]
+    # drc_bands_present with an increment of 7: eight band tops + eight gains do not fit the 3 payload bytes
+    bad = _splice_before_end(fr, _fil("1011" + "0" "0" "1" "0111" "0000" + "0" * 8))
+    r = oracle.Decoder.create_adts(2, cfg.sf_index, cfg.chan_cfg).decode_frame(bad)
+    assert r["status"] == 1
+
+
+def test_generated_drc_and_padding_fill_elements_change_nothing():
+    """The generator's p_drc knob (dynamic_range_info and padding fill elements after the audio elements, as encoders place
+    them): same PCM as the stream without them, frame by frame -- also through the SBR path, where a fill element that is
+    not an SBR payload must not be taken for one."""
+    import dataclasses
+    for base in (gen.config(2, n_frames=10, p_transient=0.3), gen.config(3, n_frames=8), gen.config(5, n_frames=4, adts=True)):
+        with_drc = dataclasses.replace(base, p_drc=0.7)
+        s0, s1 = gen.generate(base, gen.seed_for(2, 79)), gen.generate(with_drc, gen.seed_for(2, 79))
+        assert s1.data.nbytes > s0.data.nbytes
+        d0 = oracle.Decoder.create_adts(2, base.sf_index, base.chan_cfg)
+        d1 = oracle.Decoder.create_adts(2, base.sf_index, base.chan_cfg)
+        for f in range(base.n_frames):
+            r0 = d0.decode_frame(s0.data[s0.offsets[f]: s0.offsets[f] + s0.sizes[f]])
+            r1 = d1.decode_frame(s1.data[s1.offsets[f]: s1.offsets[f] + s1.sizes[f]])
+            assert r0["status"] == 0 and r1["status"] == 0
+            assert np.array_equal(r0["f32"].view(np.uint32), r1["f32"].view(np.uint32))
+
+
 def _tns_float64(spec, tns, ws, max_sfb, sf_index=3):
     """ISO/IEC 14496-3 4.6.9.3 in float64, from the signed coefficient indices (generator truth), formula tables."""
     out = spec.astype(np.float64).copy()
