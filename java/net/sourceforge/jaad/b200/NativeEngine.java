@@ -24,6 +24,9 @@ public final class NativeEngine implements AutoCloseable {
 	public static final StructLayout FRAME_RESULT = MemoryLayout.structLayout(
 			JAVA_INT.withName("status"), JAVA_SHORT.withName("channels"), JAVA_SHORT.withName("sample_length"),
 			JAVA_INT.withName("sample_rate"), JAVA_INT.withName("pcm_bytes"));
+	/** jaadb_options.flags (include/jaadb200.h): per-kernel timings, parity-test taps, ISO pulse application
+	 *  (JAAD parses pulse_data and never applies it, syntax/ICStream.java:17; the default keeps that). */
+	public static final int FLAG_PROFILE = 1, FLAG_DEBUG_TAPS = 2, FLAG_PULSE_ISO = 4;
 	/** jaadb_options { int32 device; uint32 max_streams; int32 pcm_format; int32 tns_mode; uint32 flags; uint32 chunk_frames;
 	 *  uint32 sbr_tile_frames; uint32 k2_segment_frames; } -- the three tuning knobs stay 0 (defaults) here */
 	static final StructLayout OPTIONS = MemoryLayout.structLayout(

@@ -52,6 +52,8 @@ def cases():
         # how tools/jaad_verify runs JAAD: one process per file) and the IPD/OPD extension of parametric stereo
         "lc_pns_48k": (gen.config(2, n_frames=12, p_transient=0.35, p_pns=0.25), 3, None),
         "ps_ipdopd_mono": (gen.config(4, n_frames=30, ps_ext=0.8), 2, None),
+        # fill elements behind the audio elements: dynamic range info (JAAD parses it and drops it, syntax/DRC.java) + padding
+        "lc_drc_48k": (gen.config(2, n_frames=12, p_transient=0.3, p_drc=0.7), 2, None),
     }
 
 

@@ -19,7 +19,7 @@ import oracle
 from helpers import Workload
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = ["lc_c1_long_44k", "lc_c2_mixed_48k", "lc_mono_24k", "lc_c5_51_raw", "lc_pns_48k"]
+GOLDEN_CASES = ["lc_c1_long_44k", "lc_c2_mixed_48k", "lc_mono_24k", "lc_c5_51_raw", "lc_pns_48k", "lc_drc_48k"]
 
 CASES = [
     ("c1", gen.config(1, n_frames=10), 2),

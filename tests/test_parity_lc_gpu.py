@@ -170,7 +170,7 @@ def test_asc_open_5_1_raw_frames():
 
 
 GOLDEN_CASES = ["lc_c1_long_44k", "lc_c2_mixed_48k", "lc_mono_24k", "lc_c5_51_raw", "sbr_c3_stereo", "sbr_mono", "ps_c4_mono",
-                "sbr_ds_stereo", "ps_ds_mono", "lc_pns_48k", "ps_ipdopd_mono"]
+                "sbr_ds_stereo", "ps_ds_mono", "lc_pns_48k", "ps_ipdopd_mono", "lc_drc_48k"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
