@@ -49,7 +49,8 @@ struct __align__(8) FrameSide {
   uint32_t sbr_bits[2];
   uint32_t pns_draws;     // values the frame's parse took from the PNS generator (ICStream.java:241-257), also in frames
                           // that failed later on: the generator has moved by then
-  uint32_t pad;
+  uint32_t notes;         // window-shape updates of elements outside the layout that name objects of the stream, for the
+                          // pre-pass to resolve (note_dup_shape, k1_parse.cuh): 3 x 9 bits, only in frames that end in an error
 };
 static_assert(sizeof(FrameSide) == 32, "FrameSide layout");
 

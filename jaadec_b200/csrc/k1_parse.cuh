@@ -170,17 +170,21 @@ __host__ __device__ constexpr size_t k1_smem_bytes(uint32_t lut_entries) {
 
 __device__ __forceinline__ void fail(int& status, bool& flag, int code) { status = code; flag = false; }
 
-// JAAD keeps ONE object per (element type, instance tag) (SyntacticElements.java:39-41): an element that shows the type and
-// tag of an element this frame has already decoded -- only damaged frames do that -- is decoded into the same object, and
-// its ics_info moves that channel's window shapes once more (ICSInfo.java:90-91) before the frame dies further on.  Such a
-// frame is never transformed, so all that survives it is windowShape[CURRENT] = the LAST shape read: the updates are
-// collected here (up to four: [2:0] channel slot, [3] shape, [4] valid, five bits each) and, if the frame does end in an
-// error, written over the slot's header at the end of the parse -- K2 then does what it does for every frame.
-__device__ __forceinline__ void note_dup_shape(uint32_t& pend, int slot, const IcsInfoRegs& in) {
-  if (slot < 0 || !in.shape_ok) return;
+// JAAD keeps ONE object per (element type, instance tag) (SyntacticElements.java:39-41).  A damaged frame can show an element
+// the stream's layout does not have at that position -- a lost bit in an element id or a tag -- and that element can name
+// one of the stream's OWN objects: the one an earlier element of this frame was decoded into (its type and tag a second
+// time), or one whose own element the frame has not reached yet (a 5.1 frame whose leading SCE id reads CPE, tag 0).  JAAD
+// decodes the element into that object, so its ics_info moves the object's window shapes (ICSInfo.java:90-91) before the
+// frame dies further on.  Such a frame is never transformed, so all that survives it is windowShape[CURRENT] = the LAST shape
+// read.  The updates are collected here as notes of nine bits -- [1:0] element type, [5:2] instance tag, [6] channel of the
+// element, [7] shape, [8] valid; up to three -- and, if the frame does end in an error, (a) written over the header of the
+// slot when the object is one this frame decoded before, which the frame itself tells, and (b) handed to the pre-pass in
+// FrameSide::notes, which knows the tags of the stream's elements and resolves the others (k2_prepass_kernel).
+__device__ __forceinline__ void note_dup_shape(uint32_t& pend, int note_id, int k, const IcsInfoRegs& in) {
+  if (note_id < 0 || !in.shape_ok) return;
   int n = 0;
-  while (n < 4 && ((pend >> (5 * n + 4)) & 1u)) ++n;
-  if (n < 4) pend |= ((uint32_t)(slot & 7) | ((uint32_t)(in.shape & 1) << 3) | 16u) << (5 * n);
+  while (n < 3 && ((pend >> (9 * n + 8)) & 1u)) ++n;
+  if (n < 3) pend |= ((uint32_t)note_id | ((uint32_t)(k & 1) << 6) | ((uint32_t)(in.shape & 1) << 7) | 256u) << (9 * n);
 }
 
 // Out-of-line readers for the two rare side paths below (dynamic_range_info, ISO pulses): n <= 25 bits at an absolute bit
@@ -259,7 +263,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
                                                const TablesDev& T, int sf_index, bool common, IcsInfoRegs& in,
                                                IcsSide* side, int16_t* __restrict__ q, int ms_mask,
                                                uint8_t* __restrict__ cb_lane, const int16_t* __restrict__ s_swb, bool discard,
-                                               int dup_ch, uint32_t& dup_pend, uint32_t& pns_draws, bool pulse_iso) {
+                                               int note_id, int note_k, uint32_t& dup_pend, uint32_t& pns_draws, bool pulse_iso) {
   // discard: the element is not part of the stream's layout (see the element loop): it is parsed for its errors and its
   // length only, nothing is stored
   // codebook per (group, sfb) of this lane's ICS: shared memory, one byte column per thread
@@ -271,7 +275,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
       int st = parse_ics_info(br, in);
       // window_shape bookkeeping happens before predictor data is looked at (ICSInfo.java:90-91)
       if (!discard) store_ics_header(side, in, 0, 1, 0, 0);
-      else note_dup_shape(dup_pend, dup_ch, in);
+      else note_dup_shape(dup_pend, note_id, note_k, in);
       if (st) fail(status, go, st);
     }
   }
@@ -568,7 +572,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
   fs.n_elements = 0;
   fs.sbr_bit_off[0] = fs.sbr_bit_off[1] = 0;
   fs.sbr_bits[0] = fs.sbr_bits[1] = 0;
-  fs.pad = 0;
+  fs.notes = 0;
   uint32_t pns_draws = 0;
   int status = JAADB_ST_OK;
   bool active = valid;
@@ -586,7 +590,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
   int el = 0, n_good = 0;
   bool layout_bad = false;
   int n_in_layout = 0;            // elements parsed while the frame still followed the stream's layout
-  int dup_slot = -1;              // first channel slot of the in-layout element whose object the current element addresses again
+  int note_id = -1;               // the current element is outside the layout: its type | tag << 2 (note_dup_shape)
   uint32_t dup_pend = 0;          // note_dup_shape
   bool pend_r = false;            // the right channel of the current CPE is next
   int ch0 = 0, ms_mask = 0;
@@ -619,10 +623,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
           // JAADB_ST_LAYOUT only if nothing else stops it first.
           if (el >= lay.n_elements || lay.el_type[el] != type) layout_bad = true;
           if (!layout_bad) n_in_layout = el + 1;
-          dup_slot = -1;
-          if (layout_bad)
-            for (int j = 0; j < n_in_layout && j < 4; ++j)
-              if (lay.el_type[j] == type && ((uint32_t)(fs.tags >> (4 * j)) & 15u) == tag) dup_slot = lay.el_first_ch[j];
+          note_id = layout_bad ? (int)((uint32_t)type | (tag << 2)) : -1;
           {
             ch0 = layout_bad ? 0 : lay.el_first_ch[el];
             ch = ch0;
@@ -638,11 +639,15 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
               if (common) {
                 const int st = parse_ics_info(br, in);
                 if (!layout_bad) store_ics_header(iside + ch0, in, 0, 1, 0, 1);
-                else note_dup_shape(dup_pend, dup_slot, in);
+                else note_dup_shape(dup_pend, note_id, 0, in);
                 if (st) { fail(status, active, st); go = false; }  // thrown inside infoL.decode: R's setCommonData never ran (CPE.java:95-96)
                 else {
-                  if (!layout_bad) store_ics_header(iside + ch0 + 1, in, 0, 1, 0, 1);  // setCommonData updates R's window shape too
-                  else note_dup_shape(dup_pend, dup_slot >= 0 ? dup_slot + 1 : -1, in);
+                  // setCommonData updates R's window shape too -- unless the frame ended inside infoL.decode (the reader here
+                  // runs on and reports the end of the stream later: JAAD's EOSException came before setCommonData)
+                  if (!br.overrun()) {
+                    if (!layout_bad) store_ics_header(iside + ch0 + 1, in, 0, 1, 0, 1);
+                    else note_dup_shape(dup_pend, note_id, 1, in);
+                  }
                   ms_mask = (int)br.read(2);
                   uint32_t msv[4] = {0u, 0u, 0u, 0u};
                   if (ms_mask == 1) {
@@ -701,7 +706,7 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
     }
     __syncwarp();
     parse_ics_warp(go, br, status, s_lut, T, sf_index, common, in, iside + ch, qbase + ch * 1024, ms_mask,
-                   s_cb + threadIdx.x, s_swb, layout_bad, (layout_bad && dup_slot >= 0) ? dup_slot + (ch - ch0) : -1, dup_pend,
+                   s_cb + threadIdx.x, s_swb, layout_bad, layout_bad ? note_id : -1, ch - ch0, dup_pend,
                    pns_draws, pulse_iso != 0);
     if (go) {
       if (status) active = false;
@@ -714,11 +719,16 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
     if (br.overrun()) status = JAADB_ST_EOS;
     if (status == JAADB_ST_OK && (layout_bad || el != lay.n_elements)) status = JAADB_ST_LAYOUT;
     if (dup_pend && status != JAADB_ST_OK && status != JAADB_ST_LAYOUT) {
-      for (int n = 0; n < 4 && ((dup_pend >> (5 * n + 4)) & 1u); ++n) {
-        IcsSide* const s = iside + ((dup_pend >> (5 * n)) & 7u);
-        s->window_shape = (uint8_t)((dup_pend >> (5 * n + 3)) & 1u);
-        s->info_decoded = 1;
+      for (int n = 0; n < 3 && ((dup_pend >> (9 * n + 8)) & 1u); ++n) {
+        const uint32_t nt = dup_pend >> (9 * n);
+        for (int j = 0; j < n_in_layout && j < 4; ++j)
+          if (lay.el_type[j] == (nt & 3u) && ((uint32_t)(fs.tags >> (4 * j)) & 15u) == ((nt >> 2) & 15u)) {
+            IcsSide* const s = iside + lay.el_first_ch[j] + ((nt >> 6) & 1u);
+            s->window_shape = (uint8_t)((nt >> 7) & 1u);
+            s->info_decoded = 1;
+          }
       }
+      fs.notes = dup_pend;
     }
     fs.status = status;
     fs.pns_draws = pns_draws;

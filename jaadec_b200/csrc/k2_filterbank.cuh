@@ -379,12 +379,14 @@ k2_prepass_kernel(const RunDev* __restrict__ runs, uint32_t n_runs, const RunFra
     const bool valid = it < run.count;
     RunFrameDev rf{0u, 0u};
     uint4 fsw = make_uint4(0, 0, 0, 0);   // status, tags | n_elements << 16 | n_started << 24, sbr_bit_off[2]
-    uint32_t draws = 0;
+    uint32_t draws = 0, notes = 0;
     uint64_t poff = 0;
     if (valid) {
       rf = run_frames[run.first + it];
       fsw = *reinterpret_cast<const uint4*>(fside + rf.frame);
-      draws = fside[rf.frame].pns_draws;
+      const uint2 dn = *reinterpret_cast<const uint2*>(&fside[rf.frame].pns_draws);   // pns_draws, notes
+      draws = dn.x;
+      notes = dn.y;
       poff = pcm_off[rf.frame];
     }
     const uint32_t next_ics = (it + 1 < run.count) ? run_frames[run.first + it + 1].ics_base : 0u;
@@ -427,8 +429,26 @@ k2_prepass_kernel(const RunDev* __restrict__ runs, uint32_t n_runs, const RunFra
       const bool shape_ok = my_el >= 4 || ((diff >> (4 * my_el)) & 15u) == 0;   // the element belongs to the stream
       const bool el_live = shape_ok && my_el < n_good;                         // ... and was parsed completely
       // window-shape bookkeeping of ICSInfo.decode / setCommonData (ICSInfo.java:90-91,196-197): in failing frames too
-      const bool upd = valid && ((h0 >> 8) & 0xFFu) != 0 && shape_ok;
-      const uint32_t sbit = (h0 >> 24) & 1u;
+      bool upd = valid && ((h0 >> 8) & 0xFFu) != 0 && shape_ok;
+      uint32_t sbit = (h0 >> 24) & 1u;
+      // A frame that ended in an error can have decoded an element into THIS element's object from another place of the
+      // frame (SyntacticElements.java:39-41: one object per type and tag): an element of the same type at another position
+      // of the layout that shows this element's tag (K1 parsed it into that position's slots), or an element outside the
+      // layout (K1's notes, note_dup_shape).  Its ics_info moved this object's window shape like the element's own does;
+      // the later one in the bitstream wins.  Rare (damaged element ids / tags): the lanes diverge, no votes inside.
+      if (valid && fsw.x != 0u && fsw.x != (uint32_t)JAADB_ST_LAYOUT && (diff | notes) != 0u && my_el < 4 && ((exp_mask >> (4 * my_el)) & 1u)) {
+        const uint32_t my_type = lay.el_type[my_el], my_tag = (exp_tags >> (4 * my_el)) & 15u;
+        const int k = c - lay.el_first_ch[my_el];
+        for (int e = 0; e < n_started; ++e) {
+          if (e == my_el || !((diff >> (4 * e)) & 15u) || lay.el_type[e] != my_type || ((tags >> (4 * e)) & 15u) != my_tag) continue;
+          const uint32_t hs = *reinterpret_cast<const uint32_t*>(iside + rf.ics_base + lay.el_first_ch[e] + k);
+          if (((hs >> 8) & 0xFFu) != 0 && (!upd || e > my_el)) { upd = true; sbit = (hs >> 24) & 1u; }
+        }
+        for (int n = 0; n < 3; ++n) {
+          const uint32_t nt = notes >> (9 * n);
+          if ((nt & 256u) && (nt & 3u) == my_type && ((nt >> 2) & 15u) == my_tag && (int)((nt >> 6) & 1u) == k) { upd = true; sbit = (nt >> 7) & 1u; }
+        }
+      }
       const uint32_t U = __ballot_sync(0xFFFFFFFFu, upd), S = __ballot_sync(0xFFFFFFFFu, upd && sbit);
       const uint32_t below = U & lt_mask;
       const uint32_t prev = below ? ((S >> (31 - __clz((int)below))) & 1u) : ((shape_cur >> c) & 1u);

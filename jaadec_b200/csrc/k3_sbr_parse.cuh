@@ -977,6 +977,18 @@ __device__ inline int ps_data_decode(PsParseDev& P, PsFrameDev& o, int lane) {
     const int env = idx / 17, i = idx - env * 17;
     o.ipd[env][i] = P.ipd.index[env][i];
   }
+  // ps_mix_phase indexes sf_iid / cos_betas / the alpha tables with |iid| <= num_steps and 0 <= icc <= 7 for every parameter
+  // band of every envelope (PSImpl.java:424-478).  The delta decoding clips what it adds up, but not a frequency-differential
+  // row's first value, and a header that switches from the fine to the coarse IID grid leaves the carried row where it was:
+  // such indices are an ArrayIndexOutOfBoundsException in JAAD -- 254: the caller fails the frame (like 255 above)
+  const int num_steps = (P.iid.mode < 0 ? 0 : P.iid.mode) >= 3 ? 15 : 7;
+  bool oob = false;
+  for (int idx = lane; idx < num_env * 20; idx += 32) {
+    const int env = idx / 20, i = idx - env * 20;
+    const int a = P.iid.index[env][i], b = P.icc.index[env][i];
+    oob |= (a > num_steps) || (a < -num_steps) || b < 0 || b > 7;
+  }
+  if (__any_sync(0xFFFFFFFFu, oob) && nr_ipdopd != 255) return 254;
   return nr_ipdopd;
 }
 
@@ -1293,6 +1305,16 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
             if (pst != 0) { frame_status = pst; fside[f].status = pst; mode = 0; }
             else sbr_limiter_table(C);
           }
+          // calculate_gain opens every envelope with get_S_mapped(ch, l, 0) (HFAdjustment.java:46-76,262): for a low-
+          // resolution envelope it walks bs_add_harmonic from 2 * band - (N_high & 1), i.e. from index -1 when N_high is
+          // odd -- an ArrayIndexOutOfBoundsException in JAAD (FAAD2's C reads the byte in front of the array).  Encoders
+          // do pair odd N_high with low-resolution envelopes; JAAD fails every such frame, and so does the engine.
+          if (mode == 2 && (S->N_high & 1)) {
+            bool lo = false;
+            for (int c = 0; c < nch; ++c)
+              for (int l = 0; l < S->ch[c].L_E; ++l) lo |= S->ch[c].f[l] == SBR_LO_RES;
+            if (lo) { frame_status = JAADB_ST_ARRAY_BOUNDS; fside[f].status = JAADB_ST_ARRAY_BOUNDS; mode = 0; }
+          }
         }
       }
       dequant = S->dequant;
@@ -1308,8 +1330,9 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
       if (mode != 0 && S->ps.opened && S->ps.data_available) {
         const int nr_par = ps_data_decode(S->ps, *po, lane);
         use_ps = 1;
-        if (nr_par == 255) {
-          // JAAD dies of a NullPointerException inside ps_mix_phase (see ps_data_decode): the frame fails
+        if (nr_par >= 254) {
+          // JAAD dies of a NullPointerException (255) or of an index past its tables (254) inside ps_mix_phase (see
+          // ps_data_decode): the frame fails
           use_ps = 0;
           __syncwarp();
           if (lane == 0) {

@@ -112,6 +112,12 @@ class Decoder:
             out["s16"] = s16[: ch * ln].reshape(ln, ch).copy()
         return out
 
+    def saw_sbr_payload(self) -> bool:
+        """The parse of the frame just decoded reached a fill element that claims an SBR payload (for the fuzz tools: in a stream
+        opened without SBR, JAAD creates an SBR object on the spot, the engine needs that decision at stream_open)."""
+        lib().jo_saw_sbr_payload.argtypes = [C.c_void_p]
+        return bool(lib().jo_saw_sbr_payload(self._h))
+
     def tap_ics(self, el: int, ch: int):
         q = np.zeros(1024, np.int16)
         sf = np.zeros(120, np.int16)

@@ -128,6 +128,9 @@ int jo_tap_ics(void* hv, int el, int ch, int16_t* q1024, int16_t* sfidx120, uint
   return e->type;
 }
 
+// 1 when the parse of the frame just decoded reached a fill element with an SBR payload (extension type 13 / 14)
+int jo_saw_sbr_payload(void* hv) { return static_cast<Handle*>(hv)->dec->syn.sbrPayloadSeen ? 1 : 0; }
+
 int jo_tap_msused(void* hv, int el, uint8_t* ms128) {
   Handle* h = static_cast<Handle*>(hv);
   auto& ae = h->dec->syn.audioElements;

@@ -1098,6 +1098,7 @@ struct SyntacticElements {
     switch (type) {
       case 11: decodeDynamicRangeInfo(in); break;   // :219-224: "decoded but unused"
       case 13: case 14: {
+        sbrPayloadSeen = true;
         ChannelElement* prev = audioElements.empty() ? nullptr : audioElements.back();
         if (prev) prev->decodeSBR(in, type == 14);
         break;
@@ -1106,7 +1107,11 @@ struct SyntacticElements {
     }
   }
 
+  // tap for the corrupted-stream tools (not JAAD): the frame's parse reached a fill element that claims an SBR payload
+  bool sbrPayloadSeen = false;
+
   void decode(BitStream& in) {  // :57-132 (non error-resilient branch)
+    sbrPayloadSeen = false;
     if (config->profile.errorResilient())
       throw AACException(ST_UNSUPPORTED_ELEMENT, "error resilient syntax is outside the engine's scope");
     for (;;) {

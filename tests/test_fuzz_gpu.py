@@ -33,12 +33,13 @@ def test_corrupted_lc_streams_match_the_oracle(cfg_no, streams, frames, seed, p)
 
 @pytest.mark.parametrize("cfg_no,seed,tile,ds", [(3, 5, 0, False), (4, 6, 3, False), (3, 15, 5, True), (4, 16, 0, True)])
 def test_corrupted_sbr_streams_do_not_derail_the_engine(cfg_no, seed, tile, ds):
-    """HE-AAC: the same exercise, also for ASC-opened streams on the down-sampled SBR tool.  A handful of frames per thousand
-    end differently (index errors inside JAAD's SBR / PS tools that the engine does not emulate, DESIGN.md section 7);
-    everything else must match bit for bit."""
+    """HE-AAC: the same exercise, also for ASC-opened streams on the down-sampled SBR tool.  Index errors inside JAAD's SBR /
+    PS tools (uncaught ArrayIndexOutOfBoundsExceptions) are reported as JAADB_ST_ARRAY_BOUNDS like the oracle does and end the
+    comparison of that stream (tools/fuzz_gpu.py says why); a frame or two per thousand mutated ones may still end differently
+    (foreign element objects); everything else must match bit for bit."""
     r = fuzz_gpu.run(cfg_no, 24, 24, seed, 0.3, tile=tile, verbose=False, downsampled=ds)
     assert r["mutated"] > 100
-    assert len(r["bad_status"]) + len(r["bad_pcm"]) <= 3, (r["bad_status"], r["bad_pcm"])
+    assert r["bad_status"] == [] and r["bad_pcm"] == [], (r["bad_status"], r["bad_pcm"])
 
 
 @pytest.mark.parametrize("cfg_no,seed", [(3, 23), (4, 42)])
@@ -46,8 +47,30 @@ def test_fuzz_regressions(cfg_no, seed):
     """Runs that once showed PCM off the oracle: an SBR payload error that has to win over a later
     core error, JAAD's never-cleared E_orig / Q_div / E_curr arrays read through a limiter table that outlived a header
     change, and an element object decoded twice in one frame.  What may remain are the documented status deviations: index
-    errors inside JAAD's SBR / PS tools (oracle 13, engine decodes on) and elements outside the engine's scope (engine 10)."""
+    errors inside JAAD's SBR / PS tools (oracle 13) that the engine does not see coming, and elements outside the engine's
+    scope (engine 10).  Since the end of round 2 the two index errors the sweeps kept finding -- get_S_mapped with an odd
+    N_high, parametric-stereo indices past the tables -- are reported by the engine too: these runs have no deviation left."""
     r = fuzz_gpu.run(cfg_no, 48, 32, seed, 0.3, verbose=False)
     assert r["mutated"] > 300
     assert r["bad_pcm"] == [], r["bad_pcm"]
-    assert all((g, o) == (0, 13) or g == 10 for (_, _, g, o) in r["bad_status"]), r["bad_status"]
+    assert r["bad_status"] == [], r["bad_status"]
+
+
+@pytest.mark.parametrize("cfg_no,seed,over,iso", [
+    (2, 61, dict(p_drc=0.9), False),                       # dynamic range info + padding behind the audio elements
+    (2, 62, dict(p_drc=0.9, p_pulse=0.7), False),          # ... and pulse data, parsed and dropped (JAAD's mode)
+    (2, 63, dict(p_drc=0.5, p_pulse=0.9, pulse_wild=True), True),   # pulses applied (JAADB_FLAG_PULSE_ISO / oracle pulseMode 1)
+    (5, 64, dict(p_drc=0.9, p_pulse=0.5), False),          # 5.1: the fill elements follow four audio elements
+    (3, 65, dict(p_drc=0.9), False),                       # HE-AAC: a fill element that is not the SBR payload
+])
+def test_corrupted_fill_elements_and_pulse_data(cfg_no, seed, over, iso):
+    """The side paths K1 walks out of line (drc_parse, pulse_apply) under damage: a dynamic-range-info element that is cut
+    short or whose flags are flipped must end the frame exactly where JAAD's DRC.decode does (EOS inside the fill element's
+    sub-stream, the second group of excluded-channel flags), and the frames after it must still match."""
+    r = fuzz_gpu.run(cfg_no, 32, 24, seed, 0.4, verbose=False, gen_over=over, pulse_iso=iso)
+    assert r["mutated"] > 200
+    if cfg_no == 3:
+        assert len(r["bad_status"]) + len(r["bad_pcm"]) <= 3, (r["bad_status"], r["bad_pcm"])
+    else:
+        assert r["bad_status"] == [], r["bad_status"]
+        assert r["bad_pcm"] == [], r["bad_pcm"]

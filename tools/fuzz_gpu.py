@@ -13,8 +13,11 @@ from helpers import Workload
 from jaadec_b200 import Engine, PCM_F32_PLANAR
 
 
-def run(cfg_no, n, nf, seed, p_corrupt=0.25, tile=0, verbose=True, downsampled=False):
-    cfg = gen.config(cfg_no, n_frames=nf, adts=True) if cfg_no == 5 else gen.config(cfg_no, n_frames=nf)
+def run(cfg_no, n, nf, seed, p_corrupt=0.25, tile=0, verbose=True, downsampled=False, gen_over=None, pulse_iso=False):
+    """gen_over: generator knobs on top of the BASELINE config (e.g. p_drc, p_pulse: fill elements with dynamic range info,
+    pulse data); pulse_iso: JAADB_FLAG_PULSE_ISO on the engine against the oracle's pulseMode 1."""
+    over = dict(gen_over or {})
+    cfg = gen.config(cfg_no, n_frames=nf, adts=True, **over) if cfg_no == 5 else gen.config(cfg_no, n_frames=nf, **over)
     asc = None
     if downsampled:
         # opened from an AAC-LC ASC at the core rate, SBR / PS implicit: JAAD's down-sampled SBR tool (SURVEY A-20)
@@ -44,8 +47,9 @@ def run(cfg_no, n, nf, seed, p_corrupt=0.25, tile=0, verbose=True, downsampled=F
                 b = int(rng.integers(0, min(nb, 8) * 8))
                 blob[o + b // 8] ^= 1 << (7 - b % 8)
             n_mut += 1
-    decs = wl.oracle_decoders()
-    eng = Engine(max_streams=n, pcm_format=PCM_F32_PLANAR, sbr_tile_frames=tile)
+    decs = [d.set_pulse_mode(1 if pulse_iso else 0) for d in wl.oracle_decoders()]
+    from jaadec_b200 import FLAG_PULSE_ISO
+    eng = Engine(max_streams=n, pcm_format=PCM_F32_PLANAR, sbr_tile_frames=tile, flags=FLAG_PULSE_ISO if pulse_iso else 0)
     if asc is not None:
         ids = [eng.open_asc(asc, expect_sbr=cfg.sbr_mode) for _ in range(n)]
     else:
@@ -63,6 +67,15 @@ def run(cfg_no, n, nf, seed, p_corrupt=0.25, tile=0, verbose=True, downsampled=F
         hist[r["status"]] = hist.get(r["status"], 0) + 1
         if s in dead:
             continue
+        if cfg.sbr_mode == 0 and decs[s].saw_sbr_payload():
+            # a damaged fill element that claims an SBR payload in a stream opened without SBR: JAAD creates an SBR object for
+            # the element on the spot, parses the bytes (and usually dies of their end: EOS), and from a payload that does
+            # parse on it delivers 2048-sample frames (sbr/SBR.java:98-101); the engine takes that decision at stream_open
+            # (include/jaadb200.h) and reads over the element.  The two decoders are different decoders from here on (JAAD's
+            # element keeps the SBR object even when the parse died), whatever this frame's two statuses say.
+            n_sbr_switch += 1
+            dead.add(s)
+            continue
         if res["status"][i] == 11 and r["status"] == 0:
             # an element_instance_tag (or element type) the stream did not use before: JAAD decodes the frame against other
             # element objects; the engine reports JAADB_ST_LAYOUT.  Both leave the stream's own objects alone.
@@ -75,6 +88,15 @@ def run(cfg_no, n, nf, seed, p_corrupt=0.25, tile=0, verbose=True, downsampled=F
         if res["status"][i] != r["status"]:
             bad_status.append((s, f, int(res["status"][i]), r["status"]))
             dead.add(s)   # the two decoders' states have diverged: stop comparing this stream
+            continue
+        if r["status"] == 13 and cfg.sbr_mode:
+            # a Java ArrayIndexOutOfBoundsException (inside the SBR / PS tools in almost every case: get_S_mapped with an odd
+            # N_high, parametric-stereo indices past the tables).  Nothing in JAAD catches it -- Decoder.decodeFrame swallows
+            # the EOSException only -- so it ends the decode in the middle of the frame's processing (QMF analysis and HF
+            # adjustment done, synthesis and the end-of-frame bookkeeping not).  The engine reports the same status and
+            # leaves the frame out as a whole; there is no JAAD behaviour "after" to compare with.
+            n_err += 1
+            dead.add(s)
             continue
         if r["status"] != 0:
             n_err += 1
