@@ -641,13 +641,13 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
                 if (!layout_bad) store_ics_header(iside + ch0, in, 0, 1, 0, 1);
                 else note_dup_shape(dup_pend, note_id, 0, in);
                 if (st) { fail(status, active, st); go = false; }  // thrown inside infoL.decode: R's setCommonData never ran (CPE.java:95-96)
+                // the frame ended inside infoL.decode: JAAD's EOSException comes before setCommonData, so R keeps its window
+                // shape (the reader here would run on over zeros, and the channels' final headers would update R after all)
+                else if (br.overrun()) { fail(status, active, JAADB_ST_EOS); go = false; }
                 else {
-                  // setCommonData updates R's window shape too -- unless the frame ended inside infoL.decode (the reader here
-                  // runs on and reports the end of the stream later: JAAD's EOSException came before setCommonData)
-                  if (!br.overrun()) {
-                    if (!layout_bad) store_ics_header(iside + ch0 + 1, in, 0, 1, 0, 1);
-                    else note_dup_shape(dup_pend, note_id, 1, in);
-                  }
+                  // setCommonData updates R's window shape too
+                  if (!layout_bad) store_ics_header(iside + ch0 + 1, in, 0, 1, 0, 1);
+                  else note_dup_shape(dup_pend, note_id, 1, in);
                   ms_mask = (int)br.read(2);
                   uint32_t msv[4] = {0u, 0u, 0u, 0u};
                   if (ms_mask == 1) {

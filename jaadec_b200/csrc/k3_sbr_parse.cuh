@@ -1305,6 +1305,18 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
             if (pst != 0) { frame_status = pst; fside[f].status = pst; mode = 0; }
             else sbr_limiter_table(C);
           }
+          // hf_generation walks the patches of every processed frame (HFGeneration.java:61-70): a source or target band
+          // outside the 64 QMF bands -- patches that outlived a header change in a frame that failed -- ends the frame
+          if (mode == 2) {
+            int k0 = S->kx;
+            bool bad = false;
+            for (int i = 0; i < S->noPatches; ++i) {
+              const int nsb = S->patchNoSubbands[i], p0 = S->patchStartSubband[i];
+              if (nsb > 0 && (k0 < 0 || k0 + nsb > 64 || p0 < 0 || p0 + nsb > 64)) bad = true;
+              k0 += nsb;
+            }
+            if (bad) { frame_status = JAADB_ST_SBR; fside[f].status = JAADB_ST_SBR; mode = 0; }
+          }
           // calculate_gain opens every envelope with get_S_mapped(ch, l, 0) (HFAdjustment.java:46-76,262): for a low-
           // resolution envelope it walks bs_add_harmonic from 2 * band - (N_high & 1), i.e. from index -1 when N_high is
           // odd -- an ArrayIndexOutOfBoundsException in JAAD (FAAD2's C reads the byte in front of the array).  Encoders
