@@ -74,6 +74,15 @@ def test_iso_tns_mode_agrees_with_libavcodec():
     assert compare(cfg, gen.seed_for(2, 1800), tns_mode=0).min() < 40.0
 
 
+def test_streams_with_dynamic_range_info_agree_with_libavcodec():
+    """Fill elements behind the audio elements (dynamic range info, padding): FFmpeg parses them like JAAD does, applies
+    nothing, and must land on the same PCM -- i.e. the generator's elements are well-formed to a decoder that shares no code
+    with it, and the oracle's DRC.decode restatement leaves the bit position where a second implementation leaves it."""
+    cfg = gen.config(2, n_frames=40, p_transient=0.3, p_tns=0.0, p_drc=0.8)
+    s = compare(cfg, gen.seed_for(2, 1950))
+    assert s.min() > 90.0, (s.min(), np.median(s))
+
+
 def test_iso_pulse_mode_agrees_with_libavcodec():
     """pulse_data (ISO/IEC 14496-3 4.6.3.3): JAAD parses it and stops there ("TODO: apply pulse data", ICStream.java:17).  The
     oracle's pulseMode 1 (what JAADB_FLAG_PULSE_ISO on the engine is checked against bit for bit) against a decoder that
