@@ -52,7 +52,9 @@ extern "C" {
                                          (JAAD keeps one object per type and tag, A/syntax/Element.java:36-38, and would decode
                                          such a frame against fresh ones); the stream's state is left as JAAD leaves it */
 #define JAADB_ST_PROFILE 12           /* "unsupported profile"               A/Decoder.java:110 */
-#define JAADB_ST_ARRAY_BOUNDS 13      /* a Java ArrayIndexOutOfBoundsException (IQ index > 8190, sf index < 0 ...) */
+#define JAADB_ST_ARRAY_BOUNDS 13      /* a Java ArrayIndexOutOfBoundsException (IQ index > 8190, sf index < 0, and inside the
+                                       * SBR / PS tools: get_S_mapped with an odd N_high and a low-resolution envelope,
+                                       * A/sbr/HFAdjustment.java:64-75; PS indices past the tables, A/ps/PSImpl.java:424-478) */
 #define JAADB_ST_SBR 14               /* AACException raised inside the SBR tool */
 #define JAADB_ST_CONFIG 15
 

@@ -870,6 +870,27 @@ __device__ inline void ps_decode_env(PsParamDev& p, bool icc, int env, int lane)
   }
 }
 
+// What ends a frame inside JAAD's HF generation / adjustment although its payload parsed (lane 0):
+//  * hf_generation walks the patches of every processed frame (HFGeneration.java:61-70): a source or target band outside the
+//    64 QMF bands -- patches that outlived a header change in a frame that failed -- ends the frame (the oracle's status);
+//  * calculate_gain opens every envelope with get_S_mapped(ch, l, 0) (HFAdjustment.java:46-76,262): for a low-resolution
+//    envelope it walks bs_add_harmonic from 2 * band - (N_high & 1), i.e. from index -1 when N_high is odd -- an
+//    ArrayIndexOutOfBoundsException in JAAD (FAAD2's C reads the byte in front of the array).  Encoders do pair an odd
+//    N_high with low-resolution envelopes; JAAD fails every such frame, and so does the engine.
+__device__ __forceinline__ int sbr_process_errors(const SbrElemDev& S, int nch) {
+  int k0 = S.kx;
+  for (int i = 0; i < S.noPatches; ++i) {
+    const int nsb = S.patchNoSubbands[i], p0 = S.patchStartSubband[i];
+    if (nsb > 0 && (k0 < 0 || k0 + nsb > 64 || p0 < 0 || p0 + nsb > 64)) return JAADB_ST_SBR;
+    k0 += nsb;
+  }
+  if (S.N_high & 1)
+    for (int c = 0; c < nch; ++c)
+      for (int l = 0; l < S.ch[c].L_E; ++l)
+        if (S.ch[c].f[l] == SBR_LO_RES) return JAADB_ST_ARRAY_BOUNDS;
+  return 0;
+}
+
 // PSImpl.ps_data_decode (:137-199) -> the frame record K4 mixes with.  Returns Extension.nr_par as the record holds it.
 __device__ inline int ps_data_decode(PsParseDev& P, PsFrameDev& o, int lane) {
   int num_env = P.data_available ? P.num_env : 0;
@@ -955,7 +976,7 @@ __device__ inline int ps_data_decode(PsParseDev& P, PsFrameDev& o, int lane) {
   }
   if (restore) ++num_env;
   // Extension.nr_par (ps/Extension.java:81-86, ExtData.java:49-54).  255: the extension is on while IID is off -- JAAD
-  // dereferences the null PDMode (NullPointerException); the caller fails the frame
+  // dereferences the null PDMode (NullPointerException); the caller fails the frame.  254: ps_index_oob
   const int nr_ipdopd = !ext_live ? 0 : (P.ipd.mode < 0 ? 255 : max(ps_pd_nr_par(P.ipd.mode), 11));
   __syncwarp();
   if (lane == 0) {
@@ -968,27 +989,26 @@ __device__ inline int ps_data_decode(PsParseDev& P, PsFrameDev& o, int lane) {
     o.enable_ipdopd = P.ext_data_enabled;
   }
   if (lane < 6) o.border[lane] = P.border_position[lane];
+  // (ps_mix_phase indexes its tables with |iid| <= num_steps and 0 <= icc <= 7 for every parameter band of every envelope,
+  // PSImpl.java:424-478; the delta decoding clips what it adds up, but not a frequency-differential row's first value, and a
+  // header that goes from the fine to the coarse IID grid leaves the carried row where it was: an index past the tables is an
+  // ArrayIndexOutOfBoundsException in JAAD -- 254: the caller fails the frame)
+  const int num_steps = P.iid.mode >= 3 ? 15 : 7;
+  bool oob = false;
   for (int idx = lane; idx < 5 * 20; idx += 32) {
     const int env = idx / 20, i = idx - env * 20;
-    o.iid[env][i] = P.iid.index[env][i];
-    o.icc[env][i] = P.icc.index[env][i];
+    const int a = P.iid.index[env][i], b = P.icc.index[env][i];
+    o.iid[env][i] = (int8_t)a;
+    o.icc[env][i] = (int8_t)b;
+    oob |= env < num_env && (a > num_steps || a < -num_steps || (unsigned)b > 7u);
   }
   for (int idx = lane; idx < 5 * 17; idx += 32) {
     const int env = idx / 17, i = idx - env * 17;
     o.ipd[env][i] = P.ipd.index[env][i];
   }
-  // ps_mix_phase indexes sf_iid / cos_betas / the alpha tables with |iid| <= num_steps and 0 <= icc <= 7 for every parameter
-  // band of every envelope (PSImpl.java:424-478).  The delta decoding clips what it adds up, but not a frequency-differential
-  // row's first value, and a header that switches from the fine to the coarse IID grid leaves the carried row where it was:
-  // such indices are an ArrayIndexOutOfBoundsException in JAAD -- 254: the caller fails the frame (like 255 above)
-  const int num_steps = (P.iid.mode < 0 ? 0 : P.iid.mode) >= 3 ? 15 : 7;
-  bool oob = false;
-  for (int idx = lane; idx < num_env * 20; idx += 32) {
-    const int env = idx / 20, i = idx - env * 20;
-    const int a = P.iid.index[env][i], b = P.icc.index[env][i];
-    oob |= (a > num_steps) || (a < -num_steps) || b < 0 || b > 7;
-  }
-  if (__any_sync(0xFFFFFFFFu, oob) && nr_ipdopd != 255) return 254;
+#ifndef K3_NO_PSCHK
+  if (nr_ipdopd != 255 && __any_sync(0xFFFFFFFFu, oob)) return 254;
+#endif
   return nr_ipdopd;
 }
 
@@ -1305,28 +1325,6 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
             if (pst != 0) { frame_status = pst; fside[f].status = pst; mode = 0; }
             else sbr_limiter_table(C);
           }
-          // hf_generation walks the patches of every processed frame (HFGeneration.java:61-70): a source or target band
-          // outside the 64 QMF bands -- patches that outlived a header change in a frame that failed -- ends the frame
-          if (mode == 2) {
-            int k0 = S->kx;
-            bool bad = false;
-            for (int i = 0; i < S->noPatches; ++i) {
-              const int nsb = S->patchNoSubbands[i], p0 = S->patchStartSubband[i];
-              if (nsb > 0 && (k0 < 0 || k0 + nsb > 64 || p0 < 0 || p0 + nsb > 64)) bad = true;
-              k0 += nsb;
-            }
-            if (bad) { frame_status = JAADB_ST_SBR; fside[f].status = JAADB_ST_SBR; mode = 0; }
-          }
-          // calculate_gain opens every envelope with get_S_mapped(ch, l, 0) (HFAdjustment.java:46-76,262): for a low-
-          // resolution envelope it walks bs_add_harmonic from 2 * band - (N_high & 1), i.e. from index -1 when N_high is
-          // odd -- an ArrayIndexOutOfBoundsException in JAAD (FAAD2's C reads the byte in front of the array).  Encoders
-          // do pair odd N_high with low-resolution envelopes; JAAD fails every such frame, and so does the engine.
-          if (mode == 2 && (S->N_high & 1)) {
-            bool lo = false;
-            for (int c = 0; c < nch; ++c)
-              for (int l = 0; l < S->ch[c].L_E; ++l) lo |= S->ch[c].f[l] == SBR_LO_RES;
-            if (lo) { frame_status = JAADB_ST_ARRAY_BOUNDS; fside[f].status = JAADB_ST_ARRAY_BOUNDS; mode = 0; }
-          }
         }
       }
       dequant = S->dequant;
@@ -1335,6 +1333,17 @@ k3_sbr_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict
     mode = __shfl_sync(0xFFFFFFFFu, mode, 0);
     frame_status = __shfl_sync(0xFFFFFFFFu, frame_status, 0);
     __syncwarp();
+#ifndef K3_NO_PROCCHK
+    if (mode == 2 && frame_status == 0) {
+      // (every lane: the element's tables are in shared memory, the answer is the same in all of them)
+      const int xst = sbr_process_errors(*S, nch);
+      if (xst != 0) {
+        frame_status = xst;
+        mode = 0;
+        if (lane == 0) fside[f].status = xst;
+      }
+    }
+#endif
     int use_ps = 0;
     if (run.ps) {
       // SBR1.process: parametric stereo runs iff this frame brought ps_data (SBR1.isPSUsed); PSImpl.ps_data_decode
