@@ -277,7 +277,7 @@ def measure(config_no, n_streams, n_frames, steps, warmup, local_rank, rank, wor
             # differential parameters then start from the previous pass's last frame, and a few HE-AAC v2 frames per
             # thousand streams run their parametric-stereo indices past JAAD's tables -- frames JAAD fails too (an
             # ArrayIndexOutOfBoundsException in ps_mix_phase), reported as `bad_frames_repeat_pass`
-            _, r0 = batch.download(want_results=True)
+            _, r0 = batch.download(want_results=True, want_pcm=False)
             n_bad_first = int((r0["status"] != 0).sum())
     batch.sync()
     if sampler:
@@ -309,7 +309,7 @@ def measure(config_no, n_streams, n_frames, steps, warmup, local_rank, rank, wor
     clocks = sampler.stop() if sampler else None
     elapsed = allreduce_max(t1 - t0 - flush_s)
     value = world * wl.audio_s * steps / elapsed
-    _, results = batch.download(want_results=True)
+    _, results = batch.download(want_results=True, want_pcm=False)
     n_bad_repeat = int((results["status"] != 0).sum())
     n_bad = n_bad_repeat if n_bad_first is None else n_bad_first
     pcm_bytes = batch.pcm_bytes

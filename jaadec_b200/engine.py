@@ -185,11 +185,14 @@ class Batch:
     def sync(self):
         self.engine._check(self._lib.jaadb_batch_sync(self._h), "batch_sync")
 
-    def download(self, pcm_out: np.ndarray | None = None, want_results: bool = True):
-        if pcm_out is None:
+    def download(self, pcm_out: np.ndarray | None = None, want_results: bool = True, want_pcm: bool = True):
+        """PCM and per-frame results of the decoded batch.  want_pcm=False fetches the results only (jaadb_batch_download with
+        a NULL pcm_out): status / channels / sizes of every frame without moving the PCM off the device."""
+        if pcm_out is None and want_pcm:
             pcm_out = np.zeros(self.pcm_bytes, np.uint8)
         results = np.zeros(len(self.frames), FRAME_RESULT_DTYPE) if want_results else None
-        self.engine._check(self._lib.jaadb_batch_download(self._h, _ptr(pcm_out), pcm_out.nbytes, _ptr(results)), "batch_download")
+        self.engine._check(self._lib.jaadb_batch_download(self._h, _ptr(pcm_out), 0 if pcm_out is None else pcm_out.nbytes, _ptr(results)),
+                           "batch_download")
         return pcm_out, results
 
     def timings(self) -> Timings:

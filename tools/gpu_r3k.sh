@@ -4,6 +4,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 O=gpurun_out
+timeout 900 python -m pytest tests -q -m gpu -x > $O/r3k_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $O/r3k_pytest.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/r3k_smoke.log 2>&1; tail -2 $O/r3k_smoke.log
 python bench.py > $O/r3k_bench_default.json 2> $O/r3k_bench_default.err; echo "bench rc=$?"; cut -c1-300 $O/r3k_bench_default.json
 python bench.py --impl reference > $O/r3k_bench_reference.json 2> $O/r3k_bench_reference.err; echo "ref rc=$?"; cut -c1-300 $O/r3k_bench_reference.json
