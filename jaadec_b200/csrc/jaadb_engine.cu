@@ -232,6 +232,7 @@ struct jaadb_engine {
   cudaEvent_t k4_fork = nullptr, k4_join[kK4MaxParts - 1] = {};
   int k4_parts = 2;        // parts the K4 pipeline is cut into (launch_decode); 0: one part per full wave of K4b warps
   int sm_count = 148;
+  int k1_lanes_force = -1;   // JAADB_K1_LANES_LOG2 (testing): frames per warp of the parse kernel, log2; -1: by batch size
 
   // workspace of the one-call path (jaadb_decode): grow-only, so a steady stream of calls allocates nothing.
   // The call is cut into chunks of consecutive frames; chunk k's PCM goes out over PCIe on copy_stream while
@@ -858,10 +859,15 @@ cudaError_t launch_decode(jaadb_engine* e, const FrameIndex::Group* groups, size
                    uint32_t n_k4_runs, const DecodeBufs& B, cudaEvent_t after_k1, cudaEvent_t after_k2, uint32_t* launches) {
   {
     const int threads = kK1Threads;
-    const int blocks = (int)((n_frames + threads - 1) / threads);
+    // four CTAs of eight warps per SM are resident (64 registers, 56 KB of shared memory each)
+    const uint32_t lanes_log2 = e->k1_lanes_force >= 0 ? (uint32_t)e->k1_lanes_force
+                                                       : k1_lanes_log2(n_frames, (uint32_t)e->sm_count * 4u * (uint32_t)(kK1Threads / 32));
+    const uint32_t per_block = (uint32_t)(kK1Threads / 32) << lanes_log2;
+    const int blocks = (int)((n_frames + per_block - 1) / per_block);
     k1_parse_kernel<<<blocks, threads, k1_smem_bytes(e->lut_entries), e->stream>>>(B.blob, B.frames, n_frames, B.fside, B.iside, B.q,
                                                                                    e->tables, e->d_layouts,
-                                                                                   (e->opts.flags & JAADB_FLAG_PULSE_ISO) ? 1 : 0);
+                                                                                   (e->opts.flags & JAADB_FLAG_PULSE_ISO) ? 1 : 0,
+                                                                                   lanes_log2);
     ++*launches;
   }
   if (n_sbr_runs) {
@@ -1067,6 +1073,7 @@ int jaadb_engine_create(const jaadb_options* opts, jaadb_engine** out) {
   if (cudaEventCreateWithFlags(&e->k4_fork, cudaEventDisableTiming) != cudaSuccess) return fail(JAADB_E_CUDA);
   cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, opts->device);
   if (e->sm_count <= 0) e->sm_count = 148;
+  if (const char* v = getenv("JAADB_K1_LANES_LOG2")) { const int l = atoi(v); if (l >= 0 && l <= 5) e->k1_lanes_force = l; }
   for (int i = 0; i + 1 < jaadb_engine::kK4MaxParts; ++i) {
     if (cudaStreamCreateWithFlags(&e->k4_stream[i], cudaStreamNonBlocking) != cudaSuccess) return fail(JAADB_E_CUDA);
     if (cudaEventCreateWithFlags(&e->k4_join[i], cudaEventDisableTiming) != cudaSuccess) return fail(JAADB_E_CUDA);

@@ -164,6 +164,12 @@ __device__ __forceinline__ void store_ics_header(IcsSide* s, const IcsInfoRegs& 
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 constexpr int kSwbTableEntries = 12 * 53 + 12 * 17 + 4;   // int16 entries (+4 keeps what follows 8-byte aligned)
 constexpr int kK1Threads = 256;
+// frames per warp (log2) for a batch of n frames on a GPU that holds `resident_warps` K1 warps at a time
+inline uint32_t k1_lanes_log2(uint32_t n_frames, uint32_t resident_warps) {
+  uint32_t l = 0;
+  while (l < 5 && ((uint64_t)resident_warps << l) < n_frames) ++l;
+  return l;
+}
 __host__ __device__ constexpr size_t k1_smem_bytes(uint32_t lut_entries) {
   return (size_t)lut_entries * 4 + kSwbTableEntries * 2 + (size_t)(kMaxSfbEntries + 8) * kK1Threads;
 }
@@ -547,7 +553,7 @@ __device__ __forceinline__ void parse_ics_warp(bool go, BitReader& br, int& stat
 __global__ void __launch_bounds__(kK1Threads, 4)   // 64 registers: four CTAs per SM (the shared-memory limit)
 k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ frames, uint32_t n_frames,
                 FrameSide* __restrict__ fside, IcsSide* __restrict__ iside_all, int16_t* __restrict__ q_all, TablesDev T,
-                const LayoutDev* __restrict__ layouts, int pulse_iso) {
+                const LayoutDev* __restrict__ layouts, int pulse_iso, uint32_t lanes_log2) {
   extern __shared__ uint32_t s_lut[];
   // shared memory: Huffman LUTs | SWB offset tables (long [12][53], short [12][17]) | per-lane codebook columns
   int16_t* s_swb = reinterpret_cast<int16_t*>(s_lut + T.huff_lut_entries);
@@ -556,8 +562,13 @@ k1_parse_kernel(const uint8_t* __restrict__ blob, const FrameDev* __restrict__ f
   for (int i = threadIdx.x; i < 12 * 53; i += blockDim.x) s_swb[i] = T.swb_long[i];
   for (int i = threadIdx.x; i < 12 * 17; i += blockDim.x) s_swb[12 * 53 + i] = T.swb_short[i];
   __syncthreads();
-  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = f < n_frames;
+  // Frames per warp: 32 for a batch that fills the GPU; fewer -- down to ONE -- for a small one (a tick of a live batch:
+  // a few thousand frames).  A warp's 32 frames advance in lock-step, so its time is the longest frame's with every branch
+  // any lane takes; a small batch cannot use the lanes for throughput anyway and gets the latency of a frame parsed alone
+  // (k1_lanes_log2: as many warps as the GPU holds in one wave before the warps start to fill up).
+  const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t f = ((gt >> 5) << lanes_log2) + (threadIdx.x & 31u);
+  const bool valid = (threadIdx.x & 31u) < (1u << lanes_log2) && f < n_frames;
   FrameDev fr;
   fr.blob_off = 0; fr.nbytes = 0; fr.stream_slot = 0; fr.ics_base = 0; fr.sf_index = 0; fr.layout = 0; fr.profile_ok = 1; fr.flags = 0;
   if (valid) fr = frames[f];

@@ -474,3 +474,31 @@ def test_pulse_data_jaad_and_iso_mode(label, cfg, n_streams, iso):
     assert iso or n_pulsed > 10     # the streams do carry pulses: without them the transmitted coefficients are not the truth
     b.close()
     eng.close()
+
+
+@pytest.mark.parametrize("lanes_log2", [0, 1, 3, 5])
+def test_parse_kernel_frames_per_warp(lanes_log2, monkeypatch):
+    """K1 gives a small batch fewer frames per warp (down to one: the latency of a frame parsed alone instead of the lock-step
+    time of 32) and a batch that fills the GPU all 32 lanes; the mapping is by batch size.  JAADB_K1_LANES_LOG2 forces it, so
+    that every mapping sees the same streams: statuses, quantised coefficients and PCM identical to the oracle for each."""
+    monkeypatch.setenv("JAADB_K1_LANES_LOG2", str(lanes_log2))
+    cfg = gen.config(5, n_frames=12, adts=True, p_transient=0.3, p_pns=0.1, p_pulse=0.3, p_drc=0.5)
+    wl = Workload(cfg, 7, base_seed=gen.seed_for(2, 1500))       # 84 frames: not a multiple of any warp load
+    ref = run_oracle(wl)
+    eng = Engine(max_streams=16, pcm_format=PCM_F32_PLANAR, flags=FLAG_DEBUG_TAPS)
+    ids = [eng.open_adts(*wl.hdr) for _ in range(7)]
+    frames, index = wl.frame_table(ids)
+    b = eng.batch(frames, wl.blob.nbytes)
+    b.upload(wl.blob)
+    b.decode()
+    pcm, res = b.download()
+    per = 6 * 1024 * 4
+    for i, (s, f) in enumerate(index):
+        r = ref[(s, f)]
+        assert res["status"][i] == 0 and r["status"] == 0
+        for c, t in enumerate(r["taps"]):
+            g = b.tap(i, c)
+            assert np.array_equal(g["q"], t["q"]) and np.array_equal(g["sfidx"], t["sfidx"]), (lanes_log2, s, f, c)
+        assert same_float_bits(pcm[i * per:(i + 1) * per].view(np.float32).reshape(6, 1024), r["f32"]), (lanes_log2, s, f)
+    b.close()
+    eng.close()
