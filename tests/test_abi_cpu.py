@@ -79,3 +79,21 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(root, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, os.path.join(root, f)
+
+
+def test_python_mirror_constants_equal_the_header():
+    """The ctypes mirror (jaadec_b200/engine.py) re-states the header's option values; they must be the header's."""
+    import re
+    import jaadec_b200 as jb
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "jaadb200.h")).read()
+
+    def define(name):
+        m = re.search(r"#define\s+%s\s+(\d+)u?\b" % name, hdr)
+        assert m, name
+        return int(m.group(1))
+
+    pairs = {"JAADB_FLAG_PROFILE": jb.FLAG_PROFILE, "JAADB_FLAG_DEBUG_TAPS": jb.FLAG_DEBUG_TAPS, "JAADB_FLAG_PULSE_ISO": jb.FLAG_PULSE_ISO,
+             "JAADB_TNS_JAAD": jb.TNS_JAAD, "JAADB_TNS_ISO": jb.TNS_ISO, "JAADB_PCM_S16LE": jb.PCM_S16LE, "JAADB_PCM_S16BE": jb.PCM_S16BE,
+             "JAADB_PCM_F32_PLANAR": jb.PCM_F32_PLANAR}
+    for name, value in pairs.items():
+        assert define(name) == value, name
