@@ -5,7 +5,7 @@ aborts the batch, and later frames of the stream must still match -- i.e. the st
 
 Known, documented deviations are counted separately by tools/fuzz_gpu.py: frames that address
 element objects the stream does not own (JAAD decodes them against fresh objects, the engine reports JAADB_ST_LAYOUT),
-elements outside the engine's scope (CCE / PCE / DRC: both fail, JAAD possibly with a later error), and an SBR payload
+elements outside the engine's scope (CCE / PCE: both fail, JAAD possibly with a later error), and an SBR payload
 showing up in a stream that was opened without SBR."""
 import os
 import sys

@@ -82,7 +82,7 @@ def run(cfg_no, n, nf, seed, p_corrupt=0.25, tile=0, verbose=True, downsampled=F
             n_foreign += 1
             continue
         if res["status"][i] == 10 and r["status"] != 0:
-            # CCE / PCE / DRC / gain control: the engine stops at the element, JAAD parses on and dies of something else
+            # CCE / PCE / gain control: the engine stops at the element, JAAD parses on and dies of something else
             n_unsupported += 1
             continue
         if res["status"][i] != r["status"]:
